@@ -1,0 +1,227 @@
+/*
+ * b200ctr.h — C ABI of libb200ctr.so: the sm_100a implementation of the DARE + QNN-alpha
+ * training / inference hot path of biyotteu/toss-next-ctr-prediction.
+ *
+ * The reference has no FFI/plugin layer: its boundary is the Python surface of
+ * src/models/{wrapper,dare,qnn_alpha,feature_embed}.py plus the step body of src/train.py:152-203.
+ * Every entry point below replaces the ATen/cuBLAS op chain behind one of those call sites
+ * (cited per function, file:line relative to the reference root).  INTEGRATION.md shows the
+ * ctypes binding and the namespace-package overlay that makes the reference's own train.py/infer.py
+ * call into this library unmodified.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch) owns all memory;
+ *   - row-major tensors, explicit leading dimensions (in elements) where a slice of a wider buffer is legal;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); all calls are
+ *     asynchronous on it, never synchronise, never allocate;
+ *   - return value: 0 = OK, negative = B200CTR_E_* ; b200ctr_last_error() gives a thread-local message;
+ *   - index tensors (seq, x_cat) come as int64 (the collate contract, dataset.py:98-124) or int32 (the on-disk
+ *     dtype) selected by `idx_is_64`;
+ *   - dropout uses a counter-based hash RNG keyed by (seed, stream_id, element index): the backward pass
+ *     regenerates masks instead of storing them.  p = 0 disables it (eval / parity mode).
+ *   - there is no CPU fallback: a non-sm_100 device yields B200CTR_E_ARCH.
+ */
+#ifndef B200CTR_H
+#define B200CTR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CTR_OK 0
+#define B200CTR_E_INVALID_ARG (-1)
+#define B200CTR_E_UNSUPPORTED_SHAPE (-2)
+#define B200CTR_E_CUDA (-3)
+#define B200CTR_E_ARCH (-4)
+
+#define B200CTR_ABI_VERSION 1
+
+int b200ctr_version(void);
+const char* b200ctr_last_error(void);
+/* 0 if the current device is sm_100 (B200); B200CTR_E_ARCH otherwise. */
+int b200ctr_check_device(void);
+
+/* ---- dropout descriptor ------------------------------------------------------------------------- */
+typedef struct {
+  float p;            /* drop probability; 0 => identity */
+  uint32_t seed_lo;   /* 64-bit seed */
+  uint32_t seed_hi;
+  uint32_t stream_id; /* distinct per dropout site and per step */
+} b200ctr_dropout_t;
+
+/* ---- dense contraction ---------------------------------------------------------------------------
+ * C[M,N] = epilogue( alpha * opA(A)[M,K] . opB(B)[K,N] )
+ *   transA = 0: A stored [M,K] (lda >= K)      transA = 1: A stored [K,M] (lda >= M)
+ *   transB = 0: B stored [K,N] (ldb >= N)      transB = 1: B stored [N,K] (ldb >= K)   (nn.Linear weight)
+ * epilogue order: v = alpha*acc; v += accum[m,n]; v += bias[n]; if pre_out: pre_out = v; v = act(v);
+ *                 v *= dropout keep/(1-p); v *= mask(mask_src); v += residual; C = v.
+ *                 (accum = pre-activation addend: a K-split contraction such as cat([z, inter]) @ W^T;
+ *                  residual = post-activation addend; both may alias C.)
+ * Replaces every F.linear / matmul on the path: dare.py:64,67 (in_proj, out_proj, FFN), qnn_alpha.py:92,96,129
+ * (z.U, quad.V, MLP), wrapper.py:41,97 (ctx_mlp, fc head) and their autograd backward GEMMs.
+ * `workspace` (>= b200ctr_gemm_workspace_bytes) is required only when split_k > 1.                       */
+#define B200CTR_ACT_NONE 0
+#define B200CTR_ACT_RELU 1
+#define B200CTR_ACT_GELU 2
+#define B200CTR_MASK_NONE 0
+#define B200CTR_MASK_NONZERO 1  /* v *= (mask_src != 0) ? mask_scale : 0   (ReLU(+dropout) backward from the saved output) */
+#define B200CTR_MASK_GELU_GRAD 2 /* v *= gelu'(mask_src)                    (GELU backward from the saved pre-activation)    */
+typedef struct {
+  float alpha;
+  const float* bias;       /* [N] or NULL */
+  int act;
+  float* pre_out;          /* [M,N] (ld_pre) or NULL */
+  int64_t ld_pre;
+  b200ctr_dropout_t drop;  /* applied after act (element id = m*N + n) */
+  int mask_mode;
+  const float* mask_src;   /* [M,N] (ld_mask) */
+  int64_t ld_mask;
+  float mask_scale;
+  const float* residual;   /* [M,N] (ld_res) or NULL */
+  int64_t ld_res;
+  const float* accum;      /* [M,N] (ld_accum) or NULL */
+  int64_t ld_accum;
+} b200ctr_epilogue_t;
+
+int64_t b200ctr_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int split_k);
+int b200ctr_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K,
+                 const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                 const b200ctr_epilogue_t* epi_host, int split_k, void* workspace, void* stream);
+/* out[n] = sum_m X[m,n]  (bias gradients; deterministic two-pass).  workspace >= 4*N*256 bytes. */
+int b200ctr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* workspace, void* stream);
+
+/* ---- numeric / binary feature embedding  (feature_embed.py:19-27, 42-48) ------------------------------
+ * fold:  P = w @ w_out^T (F,D),  Q = b @ w_out^T (F,D) (Q = 0 when b == NULL)
+ * fwd :  out[b,f,:] = x[b,f]*P[f,:] + Q[f,:]   written at out + b*ld_b + f*D (skipped when out == NULL);
+ *        mean_out[b,:] (ld_mean) = mean_f out[b,f,:]
+ * bwd :  dP[f,:] = sum_b x[b,f]*g[b,f,:], dQ[f,:] = sum_b g[b,f,:], g = dout[b,f,:] + dmean[b,:]/F
+ * unfold: dw = dP @ w_out, db = dQ @ w_out, dw_out = dP^T @ w + dQ^T @ b                                   */
+int b200ctr_numbin_fold(const float* w, const float* b, const float* w_out, float* P, float* Q,
+                        int F, int fe, int D, void* stream);
+int b200ctr_numbin_fwd(const float* x, const float* P, const float* Q, float* out, int64_t ld_b,
+                       float* mean_out, int64_t ld_mean, int64_t B, int F, int D, void* stream);
+int b200ctr_numbin_bwd(const float* x, const float* dout, int64_t ld_b, const float* dmean, int64_t ld_dmean,
+                       float* dP, float* dQ, int64_t B, int F, int D, void* stream);
+int b200ctr_numbin_unfold(const float* dP, const float* dQ, const float* w, const float* b, const float* w_out,
+                          float* dw, float* db, float* dw_out, int F, int fe, int D, void* stream);
+
+/* ---- hashed-categorical gather + projection  (wrapper.py:106-112, 149-150, 119-121, 128-136) ---------
+ * tables/projs: device arrays of Fc device pointers; dims/cards: device int32[Fc].
+ * fwd: e = E_c[x_cat[b,c]] @ W_c^T ; out[b,c,:] = dropout(e) at out + b*ld_b + c*D ; mean_out = mean_c e (pre-dropout);
+ *      q_out[b,:] = e[b,q_idx,:] (pre-dropout, S1 query) when q_idx >= 0.
+ * bwd: g = dropout'(dout[b,c,:]) + dmean[b,:]/Fc + (c==q_idx)*dq[b,:]; dE_c[idx] += W_c^T g ; dW_c += g (x) row.   */
+int b200ctr_cat_fwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
+                    const int32_t* dims, const int32_t* cards, float* out, int64_t ld_b,
+                    float* mean_out, int64_t ld_mean, int q_idx, float* q_out,
+                    int64_t B, int Fc, int D, b200ctr_dropout_t drop, void* stream);
+int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
+                    const int32_t* dims, const int32_t* cards, const float* dout, int64_t ld_b,
+                    const float* dmean, int64_t ld_dmean, int q_idx, const float* dq,
+                    float* const* dtables, float* const* dprojs,
+                    int64_t B, int Fc, int D, b200ctr_dropout_t drop, void* stream);
+
+/* ---- query mix  (wrapper.py:128-136): q = a*s1 + b*s2 ; bwd: ds2pre = b*dq*(s2>0) --------------------- */
+int b200ctr_axpby(const float* x, const float* y, float a, float b, float* out, int64_t n, void* stream);
+/* out = scale * dy * (y > 0)   (ReLU backward from the saved output, ctx_mlp: wrapper.py:41-43) */
+int b200ctr_relu_bwd(const float* dy, const float* y, float scale, float* out, int64_t n, void* stream);
+/* out = sigmoid(x)   (prob = sigmoid(logits), wrapper.py:175) */
+int b200ctr_sigmoid(const float* x, float* out, int64_t n, void* stream);
+/* dst[r, c] += src[r, c] over a (rows, cols) window of two row-strided buffers */
+int b200ctr_add2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* stream);
+
+/* ---- DARE retrieval  (dare.py:116-138) -----------------------------------------------------------------
+ * fwd: score[b,p] = dot(emb_att[seq[b,p]], q[b]) + rec[p]; pad -> -1e9; sorted top-K under the canonical
+ *      order (score desc, position asc); sel_rep[b,k,:] = emb_rep[seq[b,idx[b,k]]] (zero row for pad slots).
+ *      Outputs: sel_rep (B,K,D), vals (B,K), idx (B,K) int32 positions, tok (B,K) int32 tokens (pad_id at pad slots).
+ * bwd: dq[b,:] = sum_k dvals[b,k]*emb_att[tok]; sparse table gradients, accumulated either
+ *      into dense gradient tables (datt/drep, atomics) ...                                                  */
+int b200ctr_retrieve_fwd(const void* seq, int idx_is_64, const float* q, const float* emb_att, const float* emb_rep,
+                         const float* rec, int64_t B, int L, int K, int D, int pad_id, int64_t vocab,
+                         float* sel_rep, float* vals, int32_t* idx, int32_t* tok, void* stream);
+int b200ctr_retrieve_bwd(const int32_t* tok, const float* q, const float* emb_att,
+                         const float* dsel_rep, const float* dvals, int64_t B, int K, int D, int pad_id,
+                         float* dq, float* datt_dense, float* drep_dense, void* stream);
+
+/* ---- DARE encoder layer pieces  (dare.py:29-37, 53-70) ---------------------------------------------------
+ * attention: qkv (M=B*K, 3D) packed [q|k|v]; bias[i,j] = relmean[j-i+max_len] (relmean = mean over heads of
+ *   pbias.rel.weight, length 2*max_len+1, may be NULL); softmax(q k^T/sqrt(hd) + bias); dropout on probabilities;
+ *   o (M,D); lse (B,H,K) saved for the backward, which recomputes probabilities.
+ * add_rmsnorm: s = a + b ; y = w * s * rsqrt(mean(s^2)+eps) ; saves s and r.                                 */
+int b200ctr_attn_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D,
+                     float* o, float* lse, b200ctr_dropout_t drop, void* stream);
+int b200ctr_attn_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
+                     const float* d_o, int64_t B, int K, int H, int D, float* dqkv, float* drelmean,
+                     b200ctr_dropout_t drop, void* stream);
+int b200ctr_add_rmsnorm_fwd(const float* a, const float* b, const float* w, float eps, int64_t M, int D,
+                            float* s_out, float* y_out, float* r_out, void* stream);
+/* dx = rmsnorm'(dy) (+ dx_add) ; dw[D] += sum_m dy*s*r (atomic; caller zeroes dw) */
+int b200ctr_rmsnorm_bwd(const float* dy, const float* s, const float* w, const float* r, int64_t M, int D,
+                        const float* dx_add, float* dx, float* dw, void* stream);
+/* relmean[t] = mean_h rel[t,h] ; drel[t,h] = drelmean[t]/H */
+int b200ctr_relmean_fwd(const float* rel, int T, int H, float* relmean, void* stream);
+int b200ctr_relmean_bwd(const float* drelmean, int T, int H, float* drel, void* stream);
+
+/* ---- gated pooling + aux head  (dare.py:151-161) ------------------------------------------------------- */
+int b200ctr_pool_fwd(const float* x, const float* vals, const float* aux_w, const float* aux_b, int gating_relu,
+                     int64_t B, int K, int D, float* u, int64_t ld_u, float* aux, float* w_out,
+                     b200ctr_dropout_t drop, void* stream);
+int b200ctr_pool_bwd(const float* x, const float* vals, const float* w, const float* aux_w, const float* u, int64_t ld_u,
+                     const float* du, int64_t ld_du, const float* daux, int gating_relu, int64_t B, int K, int D,
+                     float* dx, float* dvals, float* daux_w, float* daux_b, b200ctr_dropout_t drop, void* stream);
+
+/* ---- QNN-alpha pieces  (qnn_alpha.py:24-26, 86-97, 109-130) ----------------------------------------------
+ * rowrms: z[b,:] = w * x[b,:] * rsqrt(mean(x^2)+eps) over N = F*D columns (z written with ld_z), r[b].
+ * fm_reduce: A (B,F,C) -> s[b,c] = sum_f A, quad[b,c] = s^2 - sum_f A^2.
+ * fm_grad:   dA[b,f,c] = dquad[b,c] * 2 * (s[b,c] - A[b,f,c])  (in place over A).
+ * se_gate:   m = colsum/B; gate = sigmoid(W2 relu(W1 m + b1) + b2) (single CTA); bwd gives dm and weight grads.
+ * se_apply:  out = inter * gate * dropout ; bwd: dinter = dout*drop*gate + dm/B ; gprod = dout*drop*inter.     */
+int b200ctr_rowrms_fwd(const float* x, int64_t ldx, const float* w, float eps, int64_t B, int64_t N,
+                       float* z, int64_t ld_z, float* r, void* stream);
+int b200ctr_rowrms_bwd(const float* dz, int64_t ld_dz, const float* x, int64_t ldx, const float* w, const float* r,
+                       int64_t B, int64_t N, float* dx, int64_t ld_dx, float* dw_partial, int n_partials, void* stream);
+int b200ctr_fm_reduce(const float* A, int64_t B, int F, int C, float* s, float* quad, void* stream);
+int b200ctr_fm_grad(float* A, const float* s, const float* dquad, int64_t B, int F, int C, void* stream);
+int b200ctr_se_gate_fwd(const float* colsum, float inv_B, const float* w1, const float* b1, const float* w2,
+                        const float* b2, int C, int Cr, float* mean, float* h1, float* gate, void* stream);
+int b200ctr_se_gate_bwd(const float* dgate, const float* mean, const float* h1, const float* gate,
+                        const float* w1, const float* w2, int C, int Cr,
+                        float* dw1, float* db1, float* dw2, float* db2, float* dmean, void* stream);
+int b200ctr_se_apply_fwd(const float* inter, const float* gate, int64_t B, int C, float* out, int64_t ld_out,
+                         b200ctr_dropout_t drop, void* stream);
+int b200ctr_se_apply_bwd(const float* dout, int64_t ld_dout, const float* inter, const float* gate, const float* dmean,
+                         float inv_B, int64_t B, int C, float* dinter, float* gprod, b200ctr_dropout_t drop, void* stream);
+
+/* ---- loss  (train.py:71-90, 165-168) ---------------------------------------------------------------------
+ * loss = wll(logits,y) + aux_w * wll(aux,y), wll = 0.5*(mean_{y=1} softplus(-z) + mean_{y=0} softplus(z)).
+ * Writes loss[0], counts[0..1] = (n_pos, n_neg), dlogits, daux (daux = 0 when aux_w == 0), prob = sigmoid(logits).
+ * n_pos_total / n_neg_total > 0 override the local counts (data-parallel: global class counts, C3).            */
+int b200ctr_bce_wll(const float* logits, const float* aux, const float* y, float aux_w, int64_t B,
+                    const int32_t* counts_override, float* loss, int32_t* counts, float* dlogits, float* daux,
+                    float* prob, void* stream);
+
+/* ---- clip + AdamW + EMA  (train.py:193-199, utils/ema.py:91-131) -----------------------------------------
+ * sqnorm: acc[0] += sum x^2 (double accumulation in-kernel, atomic across CTAs; caller zeroes acc).
+ * clip_coef: coef[0] = min(1, max_norm / (sqrt(acc[0]) + 1e-6)) ; max_norm <= 0 => 1.
+ * adamw_ema: torch.optim.AdamW step order (decay, lerp m, v, bias-corrected update) with g scaled by coef[0],
+ *            then ema = decay*ema + (1-decay)*p when ema != NULL.                                             */
+int b200ctr_sqnorm(const float* x, int64_t n, double* acc, void* stream);
+int b200ctr_clip_coef(const double* acc, float max_norm, float* coef, float* total_norm, void* stream);
+int b200ctr_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
+                      float lr, float wd, float beta1, float beta2, float eps, int64_t step,
+                      const float* coef, float ema_decay, void* stream);
+/* sparse rows of a big table: rows listed in tok[n_slots] (duplicates + pad_id allowed).  owner[vocab] scratch. */
+int b200ctr_rows_claim(const int32_t* tok, int64_t n_slots, int pad_id, int32_t* owner, void* stream);
+int b200ctr_rows_sqnorm(const int32_t* tok, int64_t n_slots, int pad_id, const int32_t* owner,
+                        const float* g_dense, int D, double* acc, void* stream);
+int b200ctr_rows_zero(const int32_t* tok, int64_t n_slots, int pad_id, const int32_t* owner,
+                      float* g_dense, int D, void* stream);
+
+/* ---- fold-ensemble  (infer.py:122-158, utils/metrics.py:68-71): p = sigmoid(mean_m logit(clamp(p_m))) ---- */
+int b200ctr_logit_mean(const float* probs, int n_models, int64_t B, float eps, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CTR_H */

@@ -1,0 +1,230 @@
+"""GPU parity tests of individual libb200ctr kernels against the oracle / exact arithmetic (run with -m gpu)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctr_oracle as O
+from tests.helpers import GOLDEN, max_err_scaled
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4   # north_star: fp32 rel <= 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from b200ctr import _lib
+    _lib.check(_lib.load().b200ctr_check_device(), "device")
+    return torch.device("cuda:0")
+
+
+def _rand(gen, *shape):
+    return torch.randn(*shape, generator=gen)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (37, 5, 19), (128, 64, 16), (300, 70, 129), (257, 200, 64), (64, 513, 300),
+                                   (1000, 1, 256), (1, 256, 1000)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_all_layouts(dev, M, N, K, ta, tb):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = _rand(g, K, M) if ta else _rand(g, M, K)
+    b = _rand(g, N, K) if tb else _rand(g, K, N)
+    ref = (a.t() if ta else a).double() @ (b.t() if tb else b).double()
+    out = ops.gemm(a.to(dev), b.to(dev), trans_a=ta, trans_b=tb)
+    assert max_err_scaled(out.cpu(), ref) < 1e-5
+
+
+def test_gemm_strided_views_and_splitk(dev):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(5)
+    big = _rand(g, 4096, 96).to(dev)
+    w = _rand(g, 40, 50).to(dev)
+    a = big[:, 16:56]                       # (4096, 40) ld 96
+    ref = a.double().cpu().t() @ big[:, 3:53].double().cpu()
+    for sk in (1, 4, 16):
+        out = ops.gemm(a, big[:, 3:53], trans_a=True, split_k=sk)     # unaligned second operand -> scalar path
+        assert max_err_scaled(out.cpu(), ref) < 1e-5
+    outv = torch.zeros(4096, 128, device=dev)
+    ops.gemm(a, w, out=outv[:, 64:114])
+    assert max_err_scaled(outv[:, 64:114].cpu(), a.double().cpu() @ w.double().cpu()) < 1e-5
+    assert float(outv[:, :64].abs().max()) == 0.0 and float(outv[:, 114:].abs().max()) == 0.0
+
+
+def test_gemm_epilogues(dev):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 200, 96, 64
+    a, w, bias, res, acc = _rand(g, M, K), _rand(g, N, K), _rand(g, N), _rand(g, M, N), _rand(g, M, N)
+    ad, wd, bd, rd, accd = (t.to(dev) for t in (a, w, bias, res, acc))
+    lin = a.double() @ w.double().t()
+    # bias + gelu + saved pre-activation + residual
+    pre = torch.empty(M, N, device=dev)
+    out = ops.gemm(ad, wd, trans_b=True, bias=bd, act=ops.ACT_GELU, pre_out=pre, residual=rd)
+    pre_ref = lin + bias.double()
+    assert max_err_scaled(pre.cpu(), pre_ref) < 1e-5
+    assert max_err_scaled(out.cpu(), O.gelu_fwd(pre_ref) + res.double()) < 1e-5
+    # accum (pre-activation) + relu
+    out = ops.gemm(ad, wd, trans_b=True, accum=accd, bias=bd, act=ops.ACT_RELU)
+    assert max_err_scaled(out.cpu(), torch.relu(lin + acc.double() + bias.double())) < 1e-5
+    # masks
+    out = ops.gemm(ad, wd, trans_b=True, mask_mode=ops.MASK_NONZERO, mask_src=torch.relu(rd), mask_scale=1.25)
+    assert max_err_scaled(out.cpu(), lin * (res > 0).double() * 1.25) < 1e-5
+    out = ops.gemm(ad, wd, trans_b=True, mask_mode=ops.MASK_GELU_GRAD, mask_src=rd)
+    assert max_err_scaled(out.cpu(), lin * O.gelu_grad(res.double())) < 1e-5
+    # split-k goes through the same epilogue
+    out = ops.gemm(ad, wd, trans_b=True, bias=bd, act=ops.ACT_RELU, split_k=4)
+    assert max_err_scaled(out.cpu(), torch.relu(lin + bias.double())) < 1e-5
+
+
+def test_gemm_dropout_is_regenerable_and_unbiased(dev):
+    from b200ctr import ops
+    M, N, K = 512, 384, 8
+    a = torch.ones(M, K, device=dev)
+    w = torch.ones(N, K, device=dev) / K
+    d = ops.drop(0.25, 1234567, 77)
+    o1 = ops.gemm(a, w, trans_b=True, dropout=d)
+    o2 = ops.gemm(a, w, trans_b=True, dropout=d)
+    assert torch.equal(o1, o2)                                   # stateless: backward regenerates the same mask
+    vals = torch.unique(o1)
+    assert set(np.round(vals.cpu().numpy(), 5)) <= {0.0, np.float32(round(1 / 0.75, 5))}
+    keep = float((o1 != 0).float().mean())
+    assert abs(keep - 0.75) < 0.01
+    o3 = ops.gemm(a, w, trans_b=True, dropout=ops.drop(0.25, 1234567, 78))
+    assert not torch.equal(o1, o3)
+
+
+def test_colsum(dev):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(3)
+    for M, N in [(1, 7), (1000, 64), (5000, 130)]:
+        x = _rand(g, M, N)
+        assert max_err_scaled(ops.colsum(x.to(dev)).cpu(), x.double().sum(0)) < 1e-5
+
+
+def test_retrieval_dyadic_bit_exact_against_reference(dev):
+    """Golden fixture from the real DARE.topk_select on a dyadic grid: values bit-equal, index order canonical."""
+    from b200ctr import ops
+    z = np.load(os.path.join(GOLDEN, "retrieval_dyadic.npz"))
+    K = int(z["K"])
+    seq = torch.from_numpy(z["seq"])
+    rec = O.recency_table(seq.shape[1], float(z["tau"]))
+    scores = torch.from_numpy(z["scores"])
+    order = torch.sort(scores, dim=1, descending=True, stable=True).indices[:, :K]
+    for seq_dev in (seq.to(dev), seq.int().to(dev)):               # int64 (collate contract) and int32 (on-disk dtype)
+        sel, vals, idx, tok = ops.retrieve_fwd(seq_dev, torch.from_numpy(z["q"]).to(dev), torch.from_numpy(z["emb_att"]).to(dev),
+                                               torch.from_numpy(z["emb_rep"]).to(dev), rec.to(dev), K, 0)
+        assert torch.equal(vals.cpu(), torch.from_numpy(z["vals"]))                 # bit-exact scores of the reference
+        assert torch.equal(idx.cpu().long(), order)                                # canonical (score desc, pos asc)
+        assert torch.equal(tok.cpu().long(), torch.gather(seq, 1, order))
+        osel, ovals, oidx = O.retrieve_fwd(seq, torch.from_numpy(z["q"]), torch.from_numpy(z["emb_att"]),
+                                           torch.from_numpy(z["emb_rep"]), rec, K)
+        assert torch.equal(sel.cpu(), osel)                                        # gathered rows bit-identical
+        assert torch.equal(sel.cpu().sum(1), torch.from_numpy(z["sel_rep"]).sum(1))  # same multiset as the reference
+
+
+@pytest.mark.parametrize("L,K", [(1, 1), (7, 7), (40, 12), (64, 20), (100, 33), (400, 60), (600, 80)])
+def test_retrieval_random_vs_oracle(dev, L, K):
+    """Generic inputs: scores agree to fp32 rounding; selections agree except at K-boundary near-ties (counted)."""
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(L * 131 + K)
+    B, V, D = 33, 500, 64
+    att, rep = _rand(g, V, D), _rand(g, V, D)
+    att[0] = 0; rep[0] = 0
+    q = _rand(g, B, D)
+    seq = torch.randint(1, V, (B, L), generator=g)
+    lens = torch.randint(0, L + 1, (B,), generator=g)
+    lens[0] = 0; lens[1] = L
+    for b in range(B):
+        seq[b, :L - int(lens[b])] = 0
+    rec = O.recency_table(L, 16.0)
+    sel, vals, idx, tok = ops.retrieve_fwd(seq.to(dev), q.to(dev), att.to(dev), rep.to(dev), rec.to(dev), K, 0)
+    osel, ovals, oidx = O.retrieve_fwd(seq, q, att, rep, rec, K)
+    assert torch.allclose(vals.cpu(), ovals, rtol=1e-5, atol=1e-4)
+    # descending, ties broken by ascending position
+    v = vals.cpu(); ix = idx.cpu()
+    assert bool((v[:, 1:] <= v[:, :-1]).all())
+    tie = v[:, 1:] == v[:, :-1]
+    assert bool((ix[:, 1:][tie] > ix[:, :-1][tie]).all())
+    mism = (ix.long() != oidx)
+    # any disagreement must sit on a near-tie (|score gap| < 4 ulp-ish)
+    if mism.any():
+        gap = (v - ovals).abs()[mism]
+        assert float(gap.max()) < 1e-4
+    assert mism.float().mean() < 0.01
+    valid = tok.cpu() != 0
+    assert torch.equal(valid, torch.gather(seq, 1, ix.long()) != 0)
+    assert bool((sel.cpu()[~valid] == 0).all())
+    assert bool((v[~valid] == -1e9).all())
+    # number of valid slots = min(K, l)
+    assert torch.equal(valid.sum(1), torch.minimum(lens, torch.tensor(K)))
+
+
+def test_retrieve_bwd_vs_oracle(dev):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(99)
+    B, V, D, L, K = 17, 120, 64, 50, 14
+    att, rep = _rand(g, V, D), _rand(g, V, D)
+    att[0] = 0; rep[0] = 0
+    q = _rand(g, B, D)
+    seq = torch.randint(1, 12, (B, L), generator=g)             # heavy token duplication -> atomics accumulate
+    seq[:, :20] = 0
+    seq[0] = 0
+    rec = O.recency_table(L, 8.0)
+    sel, vals, idx, tok = ops.retrieve_fwd(seq.to(dev), q.to(dev), att.to(dev), rep.to(dev), rec.to(dev), K, 0)
+    dsel, dvals = _rand(g, B, K, D), _rand(g, B, K)
+    datt = torch.zeros(V, D, device=dev); drep = torch.zeros(V, D, device=dev)
+    dq = ops.retrieve_bwd(tok, q.to(dev), att.to(dev), dsel.to(dev), dvals.to(dev), 0, datt, drep)
+    odq, odatt, odrep = O.retrieve_bwd(seq, q, att, rep, idx.cpu().long(), dsel, dvals, 0)
+    assert max_err_scaled(dq.cpu(), odq) < TOL
+    assert max_err_scaled(datt.cpu(), odatt) < TOL
+    assert max_err_scaled(drep.cpu(), odrep) < TOL
+    assert float(datt[0].abs().max()) == 0 and float(drep[0].abs().max()) == 0
+
+
+def test_bce_wll_vs_oracle(dev):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(4)
+    for B, mode in [(1, "pos"), (5, "neg"), (777, "mix"), (8192, "mix")]:
+        z, a = _rand(g, B) * 3, _rand(g, B)
+        y = {"pos": torch.ones(B), "neg": torch.zeros(B), "mix": (torch.rand(B, generator=g) < 0.1).float()}[mode]
+        loss, dz, da, prob, counts = ops.bce_wll(z.to(dev), a.to(dev), y.to(dev), 0.1)
+        l0, d0 = O.bce_wll(z.double(), y.double())
+        l1, d1 = O.bce_wll(a.double(), y.double())
+        assert abs(float(loss.cpu()) - float(l0 + 0.1 * l1)) < 1e-5
+        assert max_err_scaled(dz.cpu(), d0) < 1e-5 and max_err_scaled(da.cpu(), 0.1 * d1) < 1e-5
+        assert torch.allclose(prob.cpu(), torch.sigmoid(z), atol=1e-6)
+        assert counts.cpu().tolist() == [int(y.sum()), B - int(y.sum())]
+
+
+def test_adamw_ema_clip_vs_oracle(dev):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(8)
+    n = 10007
+    p, gr = _rand(g, n), _rand(g, n)
+    m, v, ema = torch.zeros(n), torch.zeros(n), p.clone()
+    pd, gd, md, vd, ed = (t.clone().to(dev) for t in (p, gr, m, v, ema))
+    acc = torch.zeros(1, device=dev, dtype=torch.float64)
+    coef = torch.ones(1, device=dev); tn = torch.zeros(1, device=dev)
+    for step in (1, 2, 3):
+        acc.zero_()
+        ops.sqnorm_(gd, acc)
+        ops.clip_coef(acc, 0.5, coef, tn)
+        c, tot = O.clip_coef({"g": gr}, 0.5)
+        assert abs(float(tn.cpu()) - tot) < 1e-4 * tot and abs(float(coef.cpu()) - c) < 1e-6
+        ops.adamw_ema_(pd, gd, md, vd, ed, 3e-3, 1e-2, step, coef, 0.9)
+        O.adamw_step(p, gr * c, m, v, step, 3e-3, 1e-2)
+        O.ema_update(ema, p, 0.9)
+        assert max_err_scaled(pd.cpu(), p) < 1e-5 and max_err_scaled(ed.cpu(), ema) < 1e-5
+        assert max_err_scaled(md.cpu(), m) < 1e-5 and max_err_scaled(vd.cpu(), v) < 1e-4   # v carries coef^2 (fp32 coef)
+
+
+def test_logit_mean_vs_reference_formula(dev):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(2)
+    P = torch.rand(5, 1000, generator=g)
+    P[0, 0] = 0.0; P[1, 1] = 1.0
+    Pc = torch.clamp(P, 1e-7, 1 - 1e-7)                                   # fp32, exactly as utils/metrics.py:31-33
+    ref = torch.sigmoid((torch.log(Pc) - torch.log1p(-Pc)).mean(0))      # utils/metrics.py:68-71
+    assert torch.allclose(ops.logit_mean(P.to(dev)).cpu(), ref, atol=1e-5)

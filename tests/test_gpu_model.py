@@ -1,0 +1,179 @@
+"""GPU parity of the whole hot path (drop-in modules and the fused trainer) against the reference-generated golden
+fixtures and the oracle (run with -m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctr_oracle as O
+from tests.helpers import CASES, batch_of, group, load_case, max_err_scaled, spec_of
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _build(cfg, z, dev):
+    import b200ctr
+    g = cfg["golden"]
+    cat_cols = cfg["data"]["cat_cols"]
+    card = {c: cfg["data"]["hash_buckets"][c] + cfg["data"]["hash_buckets_margin"] for c in cat_cols}
+    m = b200ctr.CTRModel(cfg, g["seq_vocab"], g["num_dim"], g["mask_dim"], card, cat_cols)
+    m.load_state_dict(group(z, "init/"), strict=True)
+    if hasattr(m, "fc"):
+        m.fc[2].p = 0.0          # same override oracle/make_golden.py applies to the reference (hard-coded Dropout(0.1))
+    return m.to(dev)
+
+
+@pytest.mark.parametrize("kind", CASES)
+def test_module_forward_backward_matches_reference(kind):
+    """The drop-in CTRModel on the reference's own inputs: logits/prob/aux and every autograd gradient."""
+    from b200ctr import ops
+    dev = torch.device("cuda:0")
+    z, cfg = load_case(kind)
+    m = _build(cfg, z, dev).train()
+    batch, y = batch_of(z, 0)
+    logits, prob, aux = m(batch)
+    assert max_err_scaled(logits.detach().cpu(), torch.from_numpy(z["step0/logits"])) < TOL
+    assert max_err_scaled(prob.cpu(), torch.from_numpy(z["step0/prob"])) < TOL
+    assert max_err_scaled(aux.detach().cpu(), torch.from_numpy(z["step0/aux"])) < TOL
+    loss, dz, da, _, _ = ops.bce_wll(logits.detach(), aux.detach(), y.to(dev), m.aux_weight)
+    assert abs(float(loss.cpu()) - float(z["step0/loss"])) < 1e-5
+    outs, grads = [logits], [dz]
+    if m.aux_weight > 0:
+        outs.append(aux); grads.append(da)
+    torch.autograd.backward(outs, grads)
+    ref = group(z, "grad0/")
+    got = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    assert set(got) == set(ref), set(got) ^ set(ref)
+    for n, g in ref.items():
+        assert max_err_scaled(got[n].cpu(), g) < TOL, (n, max_err_scaled(got[n].cpu(), g))
+
+
+@pytest.mark.parametrize("kind", CASES)
+def test_unmodified_step_body_with_torch_optimizer(kind):
+    """Tier A: the reference's step body (torch AdamW + clip_grad_norm_) driving the drop-in module reproduces the
+    reference's parameters after 3 steps."""
+    from b200ctr import ops
+    dev = torch.device("cuda:0")
+    z, cfg = load_case(kind)
+    m = _build(cfg, z, dev).train()
+    opt = torch.optim.AdamW(m.parameters(), lr=cfg["train"]["lr"], weight_decay=cfg["train"]["weight_decay"])
+    for s in range(3):
+        batch, y = batch_of(z, s)
+        opt.param_groups[0]["lr"] = float(z[f"step{s}/lr"])
+        opt.zero_grad(set_to_none=True)
+        logits, prob, aux = m(batch)
+        loss, dzz, da, _, _ = ops.bce_wll(logits.detach(), aux.detach(), y.to(dev), m.aux_weight)
+        outs, grads = [logits], [dzz]
+        if m.aux_weight > 0:
+            outs.append(aux); grads.append(da)
+        torch.autograd.backward(outs, grads)
+        if cfg["train"]["grad_clip_norm"] > 0:
+            tn = torch.nn.utils.clip_grad_norm_(m.parameters(), cfg["train"]["grad_clip_norm"])
+            assert abs(float(tn) - float(z[f"step{s}/total_norm"])) < 2e-4 * float(tn)
+        opt.step()
+        assert abs(float(loss.cpu()) - float(z[f"step{s}/loss"])) < 2e-4
+    for k, v in group(z, "final/").items():
+        assert max_err_scaled(m.state_dict()[k].cpu(), v) < 1e-3, k
+
+
+@pytest.mark.parametrize("kind", CASES)
+def test_fused_trainer_matches_reference(kind):
+    """Tier B: FusedTrainer (flat buffers, fused clip/AdamW/EMA, row-sparse table grads) == reference after 3 steps."""
+    import b200ctr
+    dev = torch.device("cuda:0")
+    z, cfg = load_case(kind)
+    m = _build(cfg, z, dev).train()
+    tr = b200ctr.FusedTrainer(m, cfg, steps_per_epoch=cfg["golden"]["steps_per_epoch"])
+    for s in range(3):
+        batch, y = batch_of(z, s)
+        assert abs(tr.lr_at(s + 1) - float(z[f"step{s}/lr"])) < 1e-15
+        loss = tr.step(batch, y)
+        assert abs(float(loss.cpu()) - float(z[f"step{s}/loss"])) < 2e-4
+        if cfg["train"]["grad_clip_norm"] > 0:
+            assert abs(float(tr.total_norm.cpu()) - float(z[f"step{s}/total_norm"])) < 2e-4 * float(z[f"step{s}/total_norm"])
+    sd = m.state_dict()
+    for k, v in group(z, "final/").items():
+        assert max_err_scaled(sd[k].cpu(), v) < 1e-3, k
+    ema = tr.ema_state()
+    for k, v in group(z, "ema/").items():
+        assert max_err_scaled(ema[k].cpu(), v) < 1e-3, k
+    # the persistent dense gradient tables are back to all-zero
+    for n in ("dare.emb_att.weight", "dare.emb_rep.weight"):
+        assert float(tr.tables[n]["g"].abs().max()) == 0.0
+
+
+def test_submodules_standalone_vs_oracle():
+    """DARE / DAREEncoderLayer / QNNAlphaDetailed / SEBlock / feature embeddings used on their own (as in the
+    reference's module API), checked against the oracle including input gradients."""
+    import b200ctr
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    B, K, D = 9, 11, 64
+    # encoder layer
+    layer = b200ctr.DAREEncoderLayer(D, 8, 0.0, 96, 0.0, "rms", True, max_len=K).to(dev)
+    x = torch.randn(B, K, D, generator=g)
+    xd = x.to(dev).requires_grad_(True)
+    y = layer(xd)
+    dy = torch.randn(B, K, D, generator=g)
+    y.backward(dy.to(dev))
+    sd = {k: v.detach().cpu() for k, v in layer.state_dict().items()}
+    p = dict(in_w=sd["mha.in_proj_weight"], in_b=sd["mha.in_proj_bias"], out_w=sd["mha.out_proj.weight"],
+             out_b=sd["mha.out_proj.bias"], n1=sd["norm1.w"], f1_w=sd["ffn.0.weight"], f1_b=sd["ffn.0.bias"],
+             f2_w=sd["ffn.3.weight"], f2_b=sd["ffn.3.bias"], n2=sd["norm2.w"], rel=sd["pbias.rel.weight"])
+    oy, c = O.encoder_layer_fwd(x, p, 8, K)
+    odx, og = O.encoder_layer_bwd(dy, c, p, 8)
+    assert max_err_scaled(y.detach().cpu(), oy) < TOL
+    assert max_err_scaled(xd.grad.cpu(), odx) < TOL
+    assert max_err_scaled(layer.pbias.rel.weight.grad.cpu(), og["rel"]) < TOL
+    assert max_err_scaled(layer.mha.in_proj_weight.grad.cpu(), og["in_w"]) < TOL
+    # numeric embedding
+    ne = b200ctr.NumericFeatureEmbedding(13, 12, D).to(dev)
+    with torch.no_grad():
+        ne.bias.add_(0.1 * torch.randn(13, 12, generator=g).to(dev))
+    xn = torch.randn(B, 13, generator=g)
+    out = ne(xn)
+    do = torch.randn(B, 13, D, generator=g)
+    out.backward(do.to(dev))
+    w, b, wo = ne.weight.detach().cpu(), ne.bias.detach().cpu(), ne.out_proj.weight.detach().cpu()
+    assert max_err_scaled(out.detach().cpu(), O.numbin_fwd(xn, w, b, wo)) < TOL
+    dw, db, dwo = O.numbin_bwd(xn, w, b, wo, do)
+    assert max_err_scaled(ne.weight.grad.cpu(), dw) < TOL and max_err_scaled(ne.bias.grad.cpu(), db) < TOL
+    assert max_err_scaled(ne.out_proj.weight.grad.cpu(), dwo) < TOL
+    # SE block
+    se = b200ctr.SEBlock(72, 8).to(dev)
+    xs = torch.randn(B, 72, generator=g)
+    xsd = xs.to(dev).requires_grad_(True)
+    ys = se(xsd)
+    ys.backward(torch.ones_like(ys))
+    xr = xs.clone().requires_grad_(True)
+    w1, b1, w2, b2 = (t.detach().cpu() for t in (se.fc[0].weight, se.fc[0].bias, se.fc[2].weight, se.fc[2].bias))
+    gate = torch.sigmoid(torch.relu(xr.mean(0, keepdim=True) @ w1.t() + b1) @ w2.t() + b2)
+    (xr * gate).sum().backward()
+    assert max_err_scaled(ys.detach().cpu(), (xr * gate).detach()) < TOL
+    assert max_err_scaled(xsd.grad.cpu(), xr.grad) < TOL
+
+
+def test_state_dict_contract_and_ema_interop():
+    """state_dict keys/shapes/dtypes follow SURVEY App. B; load_state_dict(strict=True) round-trips."""
+    dev = torch.device("cuda:0")
+    z, cfg = load_case("qnn_concat")
+    m = _build(cfg, z, dev)
+    sd = m.state_dict()
+    init = group(z, "init/")
+    assert list(sd.keys()) == list(init.keys())
+    for k in sd:
+        assert sd[k].dtype == torch.float32 and tuple(sd[k].shape) == tuple(init[k].shape)
+    assert len(list(m.named_buffers())) == 0
+    assert float(sd["dare.emb_att.weight"][0].abs().max()) == 0.0
+
+
+def test_no_cpu_fallback():
+    import b200ctr
+    z, cfg = load_case("base_s1")
+    g = cfg["golden"]
+    cat_cols = cfg["data"]["cat_cols"]
+    card = {c: cfg["data"]["hash_buckets"][c] + cfg["data"]["hash_buckets_margin"] for c in cat_cols}
+    m = b200ctr.CTRModel(cfg, g["seq_vocab"], g["num_dim"], g["mask_dim"], card, cat_cols)   # stays on CPU
+    batch, _ = batch_of(z, 0)
+    with pytest.raises(b200ctr.B200CtrError):
+        m(batch)

@@ -1,0 +1,499 @@
+"""Thin tensor-level wrappers over the C ABI (one Python function per entry point).
+
+PyTorch is used for device memory and streams only: every function takes CUDA tensors, passes raw
+pointers + the current stream to libb200ctr, and returns the output tensor(s).  No compute happens in torch.
+All wrappers raise if a tensor is not on a CUDA device (there is no fallback path).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import Dropout, Epilogue, NO_DROP, check
+
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+MASK_NONE, MASK_NONZERO, MASK_GELU_GRAD = 0, 1, 2
+
+LAUNCHES = 0          # number of C-ABI kernel-launching calls made (bench.py reports it)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("b200ctr ops need CUDA tensors (no CPU fallback exists)")
+    return t.data_ptr()
+
+
+def _f32(t: torch.Tensor, name="tensor"):
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Leading dimension of a 2-D (possibly row-strided) view with unit inner stride."""
+    assert t.dim() == 2 and (t.shape[1] == 1 or t.stride(1) == 1), (t.shape, t.stride())
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def drop(p: float, seed: int, stream_id: int) -> Dropout:
+    if p <= 0.0:
+        return NO_DROP
+    return Dropout(float(p), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, stream_id & 0xFFFFFFFF)
+
+
+def _split_k_for(M: int, N: int, K: int) -> int:
+    bn = 128 if N > 64 else 64
+    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+    if tiles >= 148 or K < 2048:
+        return 1
+    return int(max(1, min(296 // tiles, K // 512, 256)))
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, out: Optional[torch.Tensor] = None,
+         bias=None, act=ACT_NONE, pre_out=None, dropout: Dropout = NO_DROP, mask_mode=MASK_NONE, mask_src=None,
+         mask_scale=1.0, residual=None, accum=None, alpha=1.0, split_k: Optional[int] = None) -> torch.Tensor:
+    """out[M,N] = epilogue(alpha * op(a) @ op(b)); see include/b200ctr.h:b200ctr_gemm."""
+    lib = _lib.load()
+    _f32(a, "a"); _f32(b, "b")
+    M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    Kb, N = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
+    assert K == Kb, (a.shape, b.shape, trans_a, trans_b)
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    assert out.shape == (M, N)
+    e = Epilogue()
+    e.alpha = alpha
+    e.bias = _p(bias)
+    e.act = act
+    e.pre_out = _p(pre_out); e.ld_pre = _ld(pre_out) if pre_out is not None else 0
+    e.drop = dropout
+    e.mask_mode = mask_mode
+    e.mask_src = _p(mask_src); e.ld_mask = _ld(mask_src) if mask_src is not None else 0
+    e.mask_scale = mask_scale
+    e.residual = _p(residual); e.ld_res = _ld(residual) if residual is not None else 0
+    e.accum = _p(accum); e.ld_accum = _ld(accum) if accum is not None else 0
+    if split_k is None:
+        split_k = _split_k_for(M, N, K)
+    ws = None
+    if split_k > 1:
+        ws = torch.empty((split_k * M * N,), device=a.device, dtype=torch.float32)
+    check(lib.b200ctr_gemm(int(trans_a), int(trans_b), M, N, K, _p(a), _ld(a), _p(b), _ld(b), _p(out), _ld(out),
+                           ctypes.byref(e), split_k, _p(ws), _stream()), "gemm")
+    _count(2 if split_k > 1 else 1)
+    return out
+
+
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    M, N = x.shape
+    if out is None:
+        out = torch.empty((N,), device=x.device, dtype=torch.float32)
+    ws = torch.empty((256 * N,), device=x.device, dtype=torch.float32)
+    check(lib.b200ctr_colsum(_p(x), _ld(x), M, N, _p(out), _p(ws), _stream()), "colsum")
+    _count(2)
+    return out
+
+
+# ---- numeric / binary embedding ---------------------------------------------------------------------------
+def numbin_fold(w, b, w_out):
+    lib = _lib.load()
+    F, fe = w.shape
+    D = w_out.shape[0]
+    P = torch.empty((F, D), device=w.device, dtype=torch.float32)
+    Q = torch.empty((F, D), device=w.device, dtype=torch.float32)
+    check(lib.b200ctr_numbin_fold(_p(w), _p(b), _p(w_out), _p(P), _p(Q), F, fe, D, _stream()), "numbin_fold")
+    _count()
+    return P, Q
+
+
+def numbin_fwd(x, P, Q, out, ld_b, mean_out, ld_mean):
+    """out: tensor whose data_ptr is the address of element [0,0,0] of the (B,F,D) destination (or None)."""
+    lib = _lib.load()
+    B, F = x.shape
+    D = P.shape[1]
+    check(lib.b200ctr_numbin_fwd(_p(x), _p(P), _p(Q), _p(out), ld_b, _p(mean_out), ld_mean, B, F, D, _stream()),
+          "numbin_fwd")
+    _count()
+
+
+def numbin_bwd(x, dout, ld_b, dmean, ld_dmean, D):
+    lib = _lib.load()
+    B, F = x.shape
+    dP = torch.empty((F, D), device=x.device, dtype=torch.float32)
+    dQ = torch.empty((F, D), device=x.device, dtype=torch.float32)
+    check(lib.b200ctr_numbin_bwd(_p(x), _p(dout), ld_b, _p(dmean), ld_dmean, _p(dP), _p(dQ), B, F, D, _stream()),
+          "numbin_bwd")
+    _count(3)
+    return dP, dQ
+
+
+def numbin_unfold(dP, dQ, w, b, w_out):
+    lib = _lib.load()
+    F, fe = w.shape
+    D = w_out.shape[0]
+    dw = torch.empty_like(w)
+    db = torch.empty_like(b) if b is not None else None
+    dwo = torch.empty_like(w_out)
+    check(lib.b200ctr_numbin_unfold(_p(dP), _p(dQ), _p(w), _p(b), _p(w_out), _p(dw), _p(db), _p(dwo), F, fe, D,
+                                    _stream()), "numbin_unfold")
+    _count()
+    return dw, db, dwo
+
+
+# ---- categorical ----------------------------------------------------------------------------------------------
+class CatTables:
+    """Device-side descriptor arrays (pointer tables, dims, cards) for the Fc categorical tables."""
+
+    def __init__(self, tables: Sequence[torch.Tensor], projs: Sequence[torch.Tensor]):
+        dev = tables[0].device
+        self.tables, self.projs = list(tables), list(projs)
+        self.Fc = len(tables)
+        for t, p in zip(tables, projs):
+            assert t.is_contiguous() and p.is_contiguous() and t.dtype == torch.float32
+            if t.shape[1] > 64:
+                raise _lib.B200CtrError(f"categorical embedding dim {t.shape[1]} > 64 is not built")
+        self.t_ptrs = torch.tensor([t.data_ptr() for t in tables], dtype=torch.int64, device=dev)
+        self.p_ptrs = torch.tensor([p.data_ptr() for p in projs], dtype=torch.int64, device=dev)
+        self.dims = torch.tensor([t.shape[1] for t in tables], dtype=torch.int32, device=dev)
+        self.cards = torch.tensor([t.shape[0] for t in tables], dtype=torch.int32, device=dev)
+        self._key = tuple(t.data_ptr() for t in tables) + tuple(p.data_ptr() for p in projs)
+
+    def matches(self, tables, projs) -> bool:
+        return self._key == tuple(t.data_ptr() for t in tables) + tuple(p.data_ptr() for p in projs)
+
+
+def _ptr_table(ts: Sequence[torch.Tensor]) -> torch.Tensor:
+    return torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64, device=ts[0].device)
+
+
+def _idx64(t: torch.Tensor) -> int:
+    if t.dtype == torch.int64:
+        return 1
+    if t.dtype == torch.int32:
+        return 0
+    raise TypeError(f"index tensor must be int64 or int32, got {t.dtype}")
+
+
+def cat_fwd(x_cat, ct: CatTables, out, ld_b, mean_out, ld_mean, q_idx, q_out, D, dropout=NO_DROP):
+    lib = _lib.load()
+    B, Fc = x_cat.shape
+    assert Fc == ct.Fc and x_cat.is_contiguous()
+    check(lib.b200ctr_cat_fwd(_p(x_cat), _idx64(x_cat), _p(ct.t_ptrs), _p(ct.p_ptrs), _p(ct.dims), _p(ct.cards),
+                              _p(out), ld_b, _p(mean_out), ld_mean, q_idx, _p(q_out), B, Fc, D, dropout, _stream()),
+          "cat_fwd")
+    _count()
+
+
+def cat_bwd(x_cat, ct: CatTables, dout, ld_b, dmean, ld_dmean, q_idx, dq, dtables, dprojs, D, dropout=NO_DROP):
+    """dtables/dprojs: lists of ZEROED gradient tensors (accumulated into)."""
+    lib = _lib.load()
+    B, Fc = x_cat.shape
+    dt_ptrs, dp_ptrs = _ptr_table(dtables), _ptr_table(dprojs)
+    check(lib.b200ctr_cat_bwd(_p(x_cat), _idx64(x_cat), _p(ct.t_ptrs), _p(ct.p_ptrs), _p(ct.dims), _p(ct.cards),
+                              _p(dout), ld_b, _p(dmean), ld_dmean, q_idx, _p(dq), _p(dt_ptrs), _p(dp_ptrs),
+                              B, Fc, D, dropout, _stream()), "cat_bwd")
+    _count()
+
+
+def axpby(x, y, a, b, out=None):
+    lib = _lib.load()
+    ref = x if x is not None else y
+    if out is None:
+        out = torch.empty_like(ref)
+    check(lib.b200ctr_axpby(_p(x), _p(y), a, b, _p(out), ref.numel(), _stream()), "axpby")
+    _count()
+    return out
+
+
+def relu_bwd(dy, y, scale=1.0):
+    lib = _lib.load()
+    out = torch.empty_like(dy)
+    check(lib.b200ctr_relu_bwd(_p(dy), _p(y), float(scale), _p(out), dy.numel(), _stream()), "relu_bwd")
+    _count()
+    return out
+
+
+def sigmoid(x):
+    lib = _lib.load()
+    out = torch.empty_like(x)
+    check(lib.b200ctr_sigmoid(_p(x), _p(out), x.numel(), _stream()), "sigmoid")
+    _count()
+    return out
+
+
+def add2d_(dst, src):
+    """dst += src for 2-D row-strided views of equal shape."""
+    lib = _lib.load()
+    assert dst.shape == src.shape
+    check(lib.b200ctr_add2d(_p(dst), _ld(dst), _p(src), _ld(src), dst.shape[0], dst.shape[1], _stream()), "add2d")
+    _count()
+    return dst
+
+
+# ---- DARE ------------------------------------------------------------------------------------------------------
+def retrieve_fwd(seq, q, emb_att, emb_rep, rec, K, pad_id):
+    lib = _lib.load()
+    B, L = seq.shape
+    D = q.shape[1]
+    dev = q.device
+    assert seq.is_contiguous() and q.is_contiguous() and emb_att.is_contiguous() and emb_rep.is_contiguous()
+    sel = torch.empty((B, K, D), device=dev, dtype=torch.float32)
+    vals = torch.empty((B, K), device=dev, dtype=torch.float32)
+    idx = torch.empty((B, K), device=dev, dtype=torch.int32)
+    tok = torch.empty((B, K), device=dev, dtype=torch.int32)
+    check(lib.b200ctr_retrieve_fwd(_p(seq), _idx64(seq), _p(q), _p(emb_att), _p(emb_rep), _p(rec), B, L, K, D, pad_id,
+                                   emb_att.shape[0], _p(sel), _p(vals), _p(idx), _p(tok), _stream()), "retrieve_fwd")
+    _count()
+    return sel, vals, idx, tok
+
+
+def retrieve_bwd(tok, q, emb_att, dsel_rep, dvals, pad_id, datt_dense=None, drep_dense=None):
+    lib = _lib.load()
+    B, K = tok.shape
+    D = q.shape[1]
+    dq = torch.empty_like(q)
+    check(lib.b200ctr_retrieve_bwd(_p(tok), _p(q), _p(emb_att), _p(dsel_rep), _p(dvals), B, K, D, pad_id, _p(dq),
+                                   _p(datt_dense), _p(drep_dense), _stream()), "retrieve_bwd")
+    _count()
+    return dq
+
+
+def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP):
+    lib = _lib.load()
+    o = torch.empty((B * K, D), device=qkv.device, dtype=torch.float32)
+    lse = torch.empty((B, H, K), device=qkv.device, dtype=torch.float32)
+    check(lib.b200ctr_attn_fwd(_p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), dropout, _stream()), "attn_fwd")
+    _count()
+    return o, lse
+
+
+def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=NO_DROP):
+    lib = _lib.load()
+    dqkv = torch.empty_like(qkv)
+    check(lib.b200ctr_attn_bwd(_p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv), _p(drelmean),
+                               dropout, _stream()), "attn_bwd")
+    _count()
+    return dqkv
+
+
+def add_rmsnorm_fwd(a, b, w, eps=1e-6, save_sum=True):
+    lib = _lib.load()
+    M, D = a.shape
+    s = torch.empty_like(a) if save_sum else None
+    y = torch.empty_like(a)
+    r = torch.empty((M,), device=a.device, dtype=torch.float32)
+    check(lib.b200ctr_add_rmsnorm_fwd(_p(a), _p(b), _p(w), eps, M, D, _p(s), _p(y), _p(r), _stream()), "add_rmsnorm_fwd")
+    _count()
+    return s, y, r
+
+
+def rmsnorm_bwd(dy, s, w, r, dw, dx_add=None):
+    """dw: zeroed (D,) tensor, accumulated into."""
+    lib = _lib.load()
+    M, D = dy.shape
+    dx = torch.empty_like(dy)
+    check(lib.b200ctr_rmsnorm_bwd(_p(dy), _p(s), _p(w), _p(r), M, D, _p(dx_add), _p(dx), _p(dw), _stream()), "rmsnorm_bwd")
+    _count()
+    return dx
+
+
+def relmean_fwd(rel):
+    lib = _lib.load()
+    T, H = rel.shape
+    out = torch.empty((T,), device=rel.device, dtype=torch.float32)
+    check(lib.b200ctr_relmean_fwd(_p(rel), T, H, _p(out), _stream()), "relmean_fwd")
+    _count()
+    return out
+
+
+def relmean_bwd(drelmean, H):
+    lib = _lib.load()
+    T = drelmean.shape[0]
+    out = torch.empty((T, H), device=drelmean.device, dtype=torch.float32)
+    check(lib.b200ctr_relmean_bwd(_p(drelmean), T, H, _p(out), _stream()), "relmean_bwd")
+    _count()
+    return out
+
+
+def pool_fwd(x, vals, aux_w, aux_b, gating_relu, u, ld_u, dropout=NO_DROP):
+    lib = _lib.load()
+    B, K, D = x.shape
+    aux = torch.empty((B,), device=x.device, dtype=torch.float32)
+    w = torch.empty((B, K), device=x.device, dtype=torch.float32)
+    check(lib.b200ctr_pool_fwd(_p(x), _p(vals), _p(aux_w), _p(aux_b), int(gating_relu), B, K, D, _p(u), ld_u, _p(aux), _p(w),
+                               dropout, _stream()), "pool_fwd")
+    _count()
+    return aux, w
+
+
+def pool_bwd(x, vals, w, aux_w, u, ld_u, du, ld_du, daux, gating_relu, daux_w, daux_b, dropout=NO_DROP):
+    lib = _lib.load()
+    B, K, D = x.shape
+    dx = torch.empty_like(x)
+    dvals = torch.empty_like(vals)
+    check(lib.b200ctr_pool_bwd(_p(x), _p(vals), _p(w), _p(aux_w), _p(u), ld_u, _p(du), ld_du, _p(daux), int(gating_relu),
+                               B, K, D, _p(dx), _p(dvals), _p(daux_w), _p(daux_b), dropout, _stream()), "pool_bwd")
+    _count()
+    return dx, dvals
+
+
+# ---- QNN-alpha -------------------------------------------------------------------------------------------------
+def rowrms_fwd(x, w, eps=1e-6):
+    lib = _lib.load()
+    B, N = x.shape
+    z = torch.empty((B, N), device=x.device, dtype=torch.float32)
+    r = torch.empty((B,), device=x.device, dtype=torch.float32)
+    check(lib.b200ctr_rowrms_fwd(_p(x), _ld(x), _p(w), eps, B, N, _p(z), N, _p(r), _stream()), "rowrms_fwd")
+    _count()
+    return z, r
+
+
+def rowrms_bwd(dz, x, w, r, n_partials=296):
+    lib = _lib.load()
+    B, N = x.shape
+    n_partials = max(1, min(n_partials, B))
+    dx = torch.empty((B, N), device=x.device, dtype=torch.float32)
+    part = torch.empty((n_partials, N), device=x.device, dtype=torch.float32)
+    check(lib.b200ctr_rowrms_bwd(_p(dz), _ld(dz), _p(x), _ld(x), _p(w), _p(r), B, N, _p(dx), N, _p(part), n_partials,
+                                 _stream()), "rowrms_bwd")
+    _count()
+    return dx, colsum(part)
+
+
+def fm_reduce(A, B, F, C):
+    lib = _lib.load()
+    s = torch.empty((B, C), device=A.device, dtype=torch.float32)
+    quad = torch.empty((B, C), device=A.device, dtype=torch.float32)
+    check(lib.b200ctr_fm_reduce(_p(A), B, F, C, _p(s), _p(quad), _stream()), "fm_reduce")
+    _count()
+    return s, quad
+
+
+def fm_grad_(A, s, dquad, B, F, C):
+    lib = _lib.load()
+    check(lib.b200ctr_fm_grad(_p(A), _p(s), _p(dquad), B, F, C, _stream()), "fm_grad")
+    _count()
+    return A
+
+
+def se_gate_fwd(csum, B, w1, b1, w2, b2):
+    lib = _lib.load()
+    C, Cr = w2.shape
+    mean = torch.empty((C,), device=csum.device, dtype=torch.float32)
+    h1 = torch.empty((Cr,), device=csum.device, dtype=torch.float32)
+    gate = torch.empty((C,), device=csum.device, dtype=torch.float32)
+    check(lib.b200ctr_se_gate_fwd(_p(csum), 1.0 / B, _p(w1), _p(b1), _p(w2), _p(b2), C, Cr, _p(mean), _p(h1), _p(gate),
+                                  _stream()), "se_gate_fwd")
+    _count()
+    return mean, h1, gate
+
+
+def se_gate_bwd(dgate, mean, h1, gate, w1, w2):
+    lib = _lib.load()
+    C, Cr = w2.shape
+    dw1, dw2 = torch.empty_like(w1), torch.empty_like(w2)
+    db1 = torch.empty((Cr,), device=w1.device, dtype=torch.float32)
+    db2 = torch.empty((C,), device=w1.device, dtype=torch.float32)
+    dmean = torch.empty((C,), device=w1.device, dtype=torch.float32)
+    check(lib.b200ctr_se_gate_bwd(_p(dgate), _p(mean), _p(h1), _p(gate), _p(w1), _p(w2), C, Cr, _p(dw1), _p(db1), _p(dw2),
+                                  _p(db2), _p(dmean), _stream()), "se_gate_bwd")
+    _count()
+    return dw1, db1, dw2, db2, dmean
+
+
+def se_apply_fwd(inter, gate, dropout=NO_DROP):
+    lib = _lib.load()
+    B, C = inter.shape
+    out = torch.empty_like(inter)
+    check(lib.b200ctr_se_apply_fwd(_p(inter), _p(gate), B, C, _p(out), C, dropout, _stream()), "se_apply_fwd")
+    _count()
+    return out
+
+
+def se_apply_bwd(dout, inter, gate, dmean, B_total, want_dinter, want_gprod, dropout=NO_DROP):
+    lib = _lib.load()
+    B, C = inter.shape
+    dinter = torch.empty_like(inter) if want_dinter else None
+    gprod = torch.empty_like(inter) if want_gprod else None
+    check(lib.b200ctr_se_apply_bwd(_p(dout), _ld(dout), _p(inter), _p(gate), _p(dmean), 1.0 / B_total, B, C, _p(dinter),
+                                   _p(gprod), dropout, _stream()), "se_apply_bwd")
+    _count()
+    return dinter, gprod
+
+
+# ---- loss / optimiser -----------------------------------------------------------------------------------------
+def bce_wll(logits, aux, y, aux_w, counts_override=None, want_prob=True):
+    lib = _lib.load()
+    B = logits.shape[0]
+    dev = logits.device
+    loss = torch.empty((1,), device=dev, dtype=torch.float32)
+    counts = torch.empty((2,), device=dev, dtype=torch.int32)
+    dz = torch.empty_like(logits)
+    da = torch.empty_like(logits) if aux is not None else None
+    prob = torch.empty_like(logits) if want_prob else None
+    check(lib.b200ctr_bce_wll(_p(logits), _p(aux), _p(y), float(aux_w), B, _p(counts_override), _p(loss), _p(counts),
+                              _p(dz), _p(da), _p(prob), _stream()), "bce_wll")
+    _count()
+    return loss, dz, da, prob, counts
+
+
+def sqnorm_(x, acc):
+    lib = _lib.load()
+    check(lib.b200ctr_sqnorm(_p(x), x.numel(), _p(acc), _stream()), "sqnorm")
+    _count()
+
+
+def clip_coef(acc, max_norm, coef, total_norm=None):
+    lib = _lib.load()
+    check(lib.b200ctr_clip_coef(_p(acc), float(max_norm), _p(coef), _p(total_norm), _stream()), "clip_coef")
+    _count()
+
+
+def adamw_ema_(p, g, m, v, ema, lr, wd, step, coef, ema_decay, beta1=0.9, beta2=0.999, eps=1e-8):
+    lib = _lib.load()
+    check(lib.b200ctr_adamw_ema(_p(p), _p(g), _p(m), _p(v), _p(ema), p.numel(), lr, wd, beta1, beta2, eps, step, _p(coef),
+                                ema_decay, _stream()), "adamw_ema")
+    _count()
+
+
+def rows_claim(tok, pad_id, owner):
+    lib = _lib.load()
+    check(lib.b200ctr_rows_claim(_p(tok), tok.numel(), pad_id, _p(owner), _stream()), "rows_claim")
+    _count()
+
+
+def rows_sqnorm(tok, pad_id, owner, g_dense, acc):
+    lib = _lib.load()
+    check(lib.b200ctr_rows_sqnorm(_p(tok), tok.numel(), pad_id, _p(owner), _p(g_dense), g_dense.shape[1], _p(acc),
+                                  _stream()), "rows_sqnorm")
+    _count()
+
+
+def rows_zero(tok, pad_id, owner, g_dense):
+    lib = _lib.load()
+    check(lib.b200ctr_rows_zero(_p(tok), tok.numel(), pad_id, _p(owner), _p(g_dense), g_dense.shape[1], _stream()),
+          "rows_zero")
+    _count()
+
+
+def logit_mean(probs, eps=1e-7):
+    lib = _lib.load()
+    M, B = probs.shape
+    out = torch.empty((B,), device=probs.device, dtype=torch.float32)
+    check(lib.b200ctr_logit_mean(_p(probs), M, B, eps, _p(out), _stream()), "logit_mean")
+    _count()
+    return out

@@ -1,0 +1,248 @@
+"""Fused training step (the fast tier): mirrors the step body of the reference's train loop
+(src/train.py:152-203) without autograd and without per-parameter optimizer launches.
+
+    lr <- cosine_warmup_lr        (utils/sched.py:3-11)
+    logits, aux <- model(batch)   (hotpath.model_fwd, dropout on)
+    loss <- bce_wll(logits) + aux_w * bce_wll(aux)            (train.py:71-90,165-168; one kernel, no host sync)
+    backward                       (hotpath.model_bwd into ONE flat gradient buffer + row-sparse table grads)
+    clip_grad_norm_                (global L2 over dense grads + the distinct touched table rows; coef stays on device)
+    AdamW                          (one fused kernel over the flat buffer, one per big table)
+    EMA                            (fused into the AdamW kernels; utils/ema.py:91-131)
+
+Layout: every "small" parameter (everything except the two seq_vocab x D tables) lives in one flat fp32 buffer
+with 16-byte aligned segments; the nn.Module's parameters are re-pointed at views of it, so state_dict(), eval and
+checkpoints keep working on the same storage.  Parameters that never receive a gradient under the cfg (ctx_mlp in
+S1 mode, aux_head when aux_head_weight == 0) sit in a tail segment the optimizer skips: torch.optim.AdamW skips
+grad-less parameters entirely (no weight decay either), and this reproduces that.
+
+The two big tables keep separate p/m/v/ema buffers plus a persistent, all-zero dense gradient table: the backward
+kernel accumulates the K touched rows per sample into it, one representative slot per distinct row is elected
+(rows_claim) for the norm, the fused AdamW pass reads it, and the touched rows are re-zeroed afterwards.  (A row-lazy
+optimizer that avoids the dense passes is the planned next step; see DESIGN.md.)
+
+Data parallel (one process per GPU): dense grads are all-reduced (NCCL), class counts (C3), the SE squeeze (C4)
+and the table-row gradients are exchanged so that N ranks with B/N samples each reproduce the 1-GPU global batch.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import hotpath as hp
+from . import ops
+from .modules import CTRModel
+
+
+def cosine_warmup_lr(epoch, step, steps_per_epoch, base_lr, warmup_epochs=1, total_epochs=10):
+    """utils/sched.py:3-11."""
+    g = epoch * steps_per_epoch + step
+    warm = warmup_epochs * steps_per_epoch
+    total = total_epochs * steps_per_epoch
+    if g < warm:
+        return base_lr * (g + 1) / max(1, warm)
+    prog = (g - warm) / max(1, total - warm)
+    return 0.5 * base_lr * (1.0 + math.cos(math.pi * prog))
+
+
+def ema_decay_at(n_updates: int, base: float, warmup_steps: int = 0, warmup_type: str = "linear") -> float:
+    """utils/ema.py:72-88."""
+    d = base
+    if warmup_steps <= 0 or warmup_type == "none":
+        return d
+    t = min(1.0, (n_updates + 1) / warmup_steps)
+    if warmup_type == "linear":
+        dec = 1.0 - (1.0 - d) * t
+    elif warmup_type == "cosine":
+        dec = 1.0 - (1.0 - d) * 0.5 * (1 + math.cos(math.pi * (1 - t)))
+    else:
+        dec = d
+    return float(max(0.0, min(1.0, dec)))
+
+
+BIG_TABLES = ("dare.emb_att.weight", "dare.emb_rep.weight")
+
+
+class FusedTrainer:
+    def __init__(self, model: CTRModel, cfg: dict, steps_per_epoch: int = 1, seed: Optional[int] = None,
+                 process_group=None):
+        self.model, self.cfg = model, cfg
+        self.spec: hp.ModelSpec = model._spec
+        spec = self.spec
+        tr = cfg["train"]
+        self.base_lr, self.wd = float(tr["lr"]), float(tr["weight_decay"])
+        self.clip = float(tr.get("grad_clip_norm", 0.0))
+        self.warmup_epochs, self.epochs = int(tr.get("warmup_epochs", 1)), int(tr.get("epochs", 10))
+        self.steps_per_epoch = int(steps_per_epoch)
+        ema = cfg.get("ema") or {}
+        self.ema_on = bool(ema.get("enabled", False))
+        self.ema_decay = float(ema.get("decay", 0.999))
+        self.ema_warm, self.ema_type = int(ema.get("warmup_steps", 0)), str(ema.get("warmup_type", "linear"))
+        self.seed = int(cfg.get("seed", 0) if seed is None else seed)
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        params = dict(model.named_parameters())
+        dev = next(iter(params.values())).device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedTrainer needs the model on a CUDA device (no CPU fallback)")
+        self.dev = dev
+        # parameters that never get a gradient under this cfg (torch AdamW skips them)
+        frozen = set()
+        if spec.query_mode == "S1":
+            frozen |= {n for n in params if n.startswith("ctx_mlp.")}
+        if spec.aux_weight <= 0:
+            frozen |= {n for n in params if n.startswith("dare.aux_head.")}
+        small = [n for n in params if n not in BIG_TABLES]
+        active = [n for n in small if n not in frozen] + [n for n in small if n in frozen]
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        n_active = 0
+        for n in active:
+            self.offsets[n] = off
+            off += (params[n].numel() + 3) // 4 * 4
+            if n not in frozen:
+                n_active = off
+        self.n_flat, self.n_active = off, n_active
+        self.flat_p = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(n_active, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(n_active, device=dev, dtype=torch.float32)
+        self.P: Dict[str, torch.Tensor] = {}
+        self.Gv: Dict[str, torch.Tensor] = {}
+        for n in active:
+            p = params[n]
+            o = self.offsets[n]
+            view = self.flat_p[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view                       # the module now aliases the flat buffer
+            self.P[n] = view
+            self.Gv[n] = self.flat_g[o:o + p.numel()].view(p.shape)
+        self.flat_ema = self.flat_p.clone() if self.ema_on else None
+        self.tables: Dict[str, dict] = {}
+        for n in BIG_TABLES:
+            p = params[n].data
+            self.P[n] = p
+            t = dict(p=p, m=torch.zeros_like(p), v=torch.zeros_like(p), g=torch.zeros_like(p),
+                     ema=p.clone() if self.ema_on else None)
+            self.tables[n] = t
+            self.Gv[n] = t["g"]
+        self.owner = torch.empty(params[BIG_TABLES[0]].shape[0], device=dev, dtype=torch.int32)
+        self.acc = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.coef = torch.ones(1, device=dev, dtype=torch.float32)
+        self.total_norm = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.global_step = 0
+        self.n_ema = 0
+        self.cache: dict = {}
+
+    # ---- helpers ---------------------------------------------------------------------------------------------
+    def _G(self, name: str) -> torch.Tensor:
+        return self.Gv[name]
+
+    def to_device(self, batch: Dict[str, torch.Tensor], y: Optional[torch.Tensor]):
+        """Host (pinned) -> device copies of one collate_sharded batch (dataset.py:98-124)."""
+        dev = self.dev
+        out = {"X_num": batch["X_num"].to(dev, non_blocking=True), "X_mask": batch["X_mask"].to(dev, non_blocking=True),
+               "X_cat": batch["X_cat"].to(dev, non_blocking=True), "seq": batch["seq"].to(dev, non_blocking=True)}
+        if out["X_num"].dtype != torch.float32:
+            out["X_num"] = out["X_num"].float()
+        if out["X_mask"].dtype != torch.float32:
+            out["X_mask"] = out["X_mask"].float()
+        yd = y.to(dev, non_blocking=True).float() if y is not None else None
+        return out, yd
+
+    def lr_at(self, global_step_1based: int) -> float:
+        g = global_step_1based - 1
+        epoch, step = divmod(g, max(1, self.steps_per_epoch))
+        return cosine_warmup_lr(epoch, step, self.steps_per_epoch, self.base_lr, self.warmup_epochs, self.epochs)
+
+    def _allreduce(self, t: torch.Tensor):
+        if self.pg is not None and self.world > 1:
+            torch.distributed.all_reduce(t, group=self.pg)
+        return t
+
+    # ---- one optimisation step ---------------------------------------------------------------------------------
+    def step(self, batch: Dict[str, torch.Tensor], y: torch.Tensor, lr: Optional[float] = None) -> torch.Tensor:
+        """batch: collate_sharded dict (CPU pinned or device tensors).  Returns the loss as a 1-element device
+        tensor (no host sync; the caller decides when to read it)."""
+        spec = self.spec
+        self.global_step += 1
+        lr = self.lr_at(self.global_step) if lr is None else lr
+        dbatch, yd = self.to_device(batch, y)
+        B_local = yd.shape[0]
+        dc = hp.DropCtl(True, seed=self.seed, step=self.global_step)
+        self.flat_g.zero_()
+        hook = (lambda t: self._allreduce(t)) if self.world > 1 else None
+        logits, aux, sv = hp.model_fwd(self.P, spec, dbatch, dc, self.cache, B_total=B_local * self.world, colsum_hook=hook)
+        counts_override = None
+        if self.world > 1:
+            counts_override = torch.stack([(yd > 0.5).sum(), (yd <= 0.5).sum()]).to(torch.int32)   # 2 ints (C3)
+            self._allreduce(counts_override)
+        loss, dz, daux, _, _ = ops.bce_wll(logits, aux, yd, spec.aux_weight, counts_override, want_prob=False)
+        hp.model_bwd(self.P, spec, sv, dz, daux if spec.aux_weight > 0 else None, dc, self._G, colsum_hook=hook)
+        tok = sv["dare"]["tok"]
+        if self.world > 1:
+            self._allreduce(self.flat_g[:self.n_active])                                            # C2
+            tok = self._exchange_table_grads(tok)                                                   # C1
+            self._allreduce(loss)
+        # ---- global-norm clip (coef stays on the device) ----
+        self.acc.zero_()
+        ops.sqnorm_(self.flat_g[:self.n_active], self.acc)
+        ops.rows_claim(tok, spec.pad_id, self.owner)
+        for n in BIG_TABLES:
+            ops.rows_sqnorm(tok, spec.pad_id, self.owner, self.tables[n]["g"], self.acc)
+        ops.clip_coef(self.acc, self.clip, self.coef, self.total_norm)
+        # ---- AdamW (+EMA) ----
+        d = ema_decay_at(self.n_ema, self.ema_decay, self.ema_warm, self.ema_type) if self.ema_on else 0.0
+        ops.adamw_ema_(self.flat_p[:self.n_active], self.flat_g[:self.n_active], self.flat_m, self.flat_v,
+                       self.flat_ema[:self.n_active] if self.ema_on else None, lr, self.wd, self.global_step, self.coef, d)
+        for n in BIG_TABLES:
+            t = self.tables[n]
+            ops.adamw_ema_(t["p"], t["g"], t["m"], t["v"], t["ema"], lr, self.wd, self.global_step, self.coef, d)
+            ops.rows_zero(tok, spec.pad_id, self.owner, t["g"])
+        if self.ema_on:
+            self.n_ema += 1
+        self.last_logits = logits
+        return loss
+
+    def _exchange_table_grads(self, tok: torch.Tensor) -> torch.Tensor:
+        """Replicated tables under data parallelism: gather every rank's (token, gradient-row) pairs and apply the
+        remote ones locally, so each replica sees the full global-batch table gradient (C1, all-gather form)."""
+        D = self.spec.D
+        flat_tok = tok.reshape(-1)
+        rows = {n: self.tables[n]["g"][flat_tok.long()] for n in BIG_TABLES}     # local contributions (dedup'ed sums)
+        toks = [torch.empty_like(flat_tok) for _ in range(self.world)]
+        torch.distributed.all_gather(toks, flat_tok, group=self.pg)
+        rank = torch.distributed.get_rank(self.pg)
+        # a row summed locally appears once per local slot: only the owner slot carries it, the others send zeros
+        ops.rows_claim(flat_tok, self.spec.pad_id, self.owner)
+        own = (self.owner[flat_tok.long()] == torch.arange(flat_tok.numel(), device=self.dev, dtype=torch.int32)) & \
+              (flat_tok != self.spec.pad_id)
+        for n in BIG_TABLES:
+            send = rows[n] * own.unsqueeze(1)
+            recv = [torch.empty_like(send) for _ in range(self.world)]
+            torch.distributed.all_gather(recv, send, group=self.pg)
+            for r in range(self.world):
+                if r != rank:
+                    self.tables[n]["g"].index_add_(0, toks[r].long(), recv[r])
+        return torch.cat(toks)
+
+    # ---- evaluation / state ----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def predict(self, batch: Dict[str, torch.Tensor]):
+        dbatch, _ = self.to_device(batch, None)
+        dc = hp.DropCtl(False)
+        logits, aux, _ = hp.model_fwd(self.P, self.spec, dbatch, dc, self.cache)
+        return logits, ops.sigmoid(logits), aux
+
+    def ema_state(self) -> Dict[str, torch.Tensor]:
+        """EMA shadows keyed like ModelEMA.shadow_params (utils/ema.py:51-58)."""
+        if not self.ema_on:
+            return {}
+        out = {}
+        for n, o in self.offsets.items():
+            p = self.P[n]
+            out[n] = self.flat_ema[o:o + p.numel()].view(p.shape)
+        for n in BIG_TABLES:
+            out[n] = self.tables[n]["ema"]
+        return out

@@ -1,0 +1,97 @@
+// Shared device/host helpers for libb200ctr (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/b200ctr.h"
+
+namespace b200ctr {
+
+// ---- error plumbing (thread-local message, never throws, never exits) ------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define B200_REQUIRE(cond, code, ...)                 \
+  do {                                                \
+    if (!(cond)) {                                    \
+      ::b200ctr::set_error(__VA_ARGS__);              \
+      return (code);                                  \
+    }                                                 \
+  } while (0)
+
+// launch-config errors are picked up without a device sync
+#define B200_LAUNCH_CHECK(name)                                        \
+  do {                                                                 \
+    cudaError_t e__ = cudaPeekAtLastError();                           \
+    if (e__ != cudaSuccess) return ::b200ctr::cuda_fail(e__, name);    \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+__host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+int num_sms();
+
+// ---- counter-based dropout RNG -----------------------------------------------------------------------
+// u32 hash of (seed, stream_id, element index): two rounds of a multiply-xorshift mixer (lowbias32 constants)
+// around the key injections.  Stateless, so the backward pass regenerates the mask.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t rng_u32(const b200ctr_dropout_t& d, uint64_t idx) {
+  uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
+  uint32_t x = mix32(lo ^ d.seed_lo);
+  x = mix32(x + 0x9E3779B9U * (d.stream_id + 1u) + (hi ^ d.seed_hi) * 0x85EBCA6BU);
+  return x;
+}
+// keep-scale: 1/(1-p) if kept, 0 if dropped.  p == 0 short-circuits (exact identity).
+__device__ __forceinline__ float drop_scale(const b200ctr_dropout_t& d, uint64_t idx) {
+  if (d.p <= 0.f) return 1.f;
+  float u = (float)(rng_u32(d, idx) >> 8) * (1.0f / 16777216.0f);   // [0,1)
+  return u >= d.p ? 1.f / (1.f - d.p) : 0.f;
+}
+
+// ---- math ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  float pdf = expf(-0.5f * x * x) * 0.39894228040143268f;
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// torch softplus(beta=1, threshold=20)
+__device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `red` is >= 32 floats of shared memory; result valid in every thread
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) t = warp_sum(t);
+  if (threadIdx.x == 0) red[0] = t;
+  __syncthreads();
+  return red[0];
+}
+
+// 128-bit streaming loads (read-only path, no L1 allocation) for gather rows
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+}  // namespace b200ctr

@@ -1,0 +1,415 @@
+// K1: numeric / binary feature embedding (rank-1 folded) and hashed-categorical gather + projection,
+// forward and backward.  Reference: src/models/feature_embed.py:19-27,42-48 and src/models/wrapper.py:106-136.
+#include "common.cuh"
+#include <algorithm>
+
+namespace b200ctr {
+
+// ------------------------------------------------------------------------------------------------------
+// numeric / binary: out[b,f,:] = x[b,f] * P[f,:] + Q[f,:],  P = w @ w_out^T, Q = b @ w_out^T
+// ------------------------------------------------------------------------------------------------------
+__global__ void numbin_fold_kernel(const float* __restrict__ w, const float* __restrict__ b,
+                                   const float* __restrict__ w_out, float* __restrict__ P, float* __restrict__ Q,
+                                   int F, int fe, int D) {
+  int f = blockIdx.x, d = threadIdx.x;
+  if (d >= D) return;
+  float p = 0.f, q = 0.f;
+  for (int e = 0; e < fe; ++e) {
+    float wo = w_out[d * fe + e];
+    p = fmaf(w[f * fe + e], wo, p);
+    if (b) q = fmaf(b[f * fe + e], wo, q);
+  }
+  P[f * D + d] = p;
+  Q[f * D + d] = q;
+}
+
+// one block per sample (grid-stride); D/4 float4 lanes per feature row, blockDim/(D/4) rows in flight
+__global__ void __launch_bounds__(256)
+numbin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ P, const float* __restrict__ Q,
+                  float* __restrict__ out, int64_t ld_b, float* __restrict__ mean_out, int64_t ld_mean,
+                  int64_t B, int F, int D) {
+  __shared__ float4 red[256];
+  const int D4 = D >> 2;
+  const int lane = threadIdx.x % D4, rg = threadIdx.x / D4, nrg = blockDim.x / D4;
+  const float4* P4 = reinterpret_cast<const float4*>(P);
+  const float4* Q4 = reinterpret_cast<const float4*>(Q);
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rg < nrg) {
+      for (int f = rg; f < F; f += nrg) {
+        float xv = x[b * F + f];
+        float4 p = __ldg(P4 + f * D4 + lane), q = __ldg(Q4 + f * D4 + lane);
+        float4 o = make_float4(fmaf(xv, p.x, q.x), fmaf(xv, p.y, q.y), fmaf(xv, p.z, q.z), fmaf(xv, p.w, q.w));
+        if (out) *reinterpret_cast<float4*>(out + b * ld_b + (int64_t)f * D + lane * 4) = o;
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      }
+    }
+    if (mean_out) {
+      red[threadIdx.x] = acc;
+      __syncthreads();
+      if (rg == 0) {
+        float4 s = red[lane];
+        for (int r = 1; r < nrg; ++r) {
+          float4 t = red[r * D4 + lane];
+          s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        float inv = 1.f / (float)F;
+        *reinterpret_cast<float4*>(mean_out + b * ld_mean + lane * 4) = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// dP[f,:] += sum_b x[b,f]*g, dQ[f,:] += sum_b g ; each block owns a contiguous chunk of samples,
+// each thread a fixed set of (f, d4) pairs; one atomic per pair per block.
+__global__ void __launch_bounds__(256)
+numbin_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, int64_t ld_b,
+                  const float* __restrict__ dmean, int64_t ld_dmean, float* __restrict__ dP, float* __restrict__ dQ,
+                  int64_t B, int F, int D, int64_t chunk) {
+  const int D4 = D >> 2;
+  const int npairs = F * D4;
+  const int64_t b0 = (int64_t)blockIdx.x * chunk, b1 = min(B, b0 + chunk);
+  const float invF = 1.f / (float)F;
+  for (int pr = threadIdx.x; pr < npairs; pr += blockDim.x) {
+    int f = pr / D4, l = pr % D4;
+    float4 ap = make_float4(0.f, 0.f, 0.f, 0.f), aq = ap;
+    for (int64_t b = b0; b < b1; ++b) {
+      float4 g = dout ? *reinterpret_cast<const float4*>(dout + b * ld_b + (int64_t)f * D + l * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dmean) {
+        float4 m = *reinterpret_cast<const float4*>(dmean + b * ld_dmean + l * 4);
+        g.x = fmaf(m.x, invF, g.x); g.y = fmaf(m.y, invF, g.y); g.z = fmaf(m.z, invF, g.z); g.w = fmaf(m.w, invF, g.w);
+      }
+      float xv = x[b * F + f];
+      ap.x = fmaf(xv, g.x, ap.x); ap.y = fmaf(xv, g.y, ap.y); ap.z = fmaf(xv, g.z, ap.z); ap.w = fmaf(xv, g.w, ap.w);
+      aq.x += g.x; aq.y += g.y; aq.z += g.z; aq.w += g.w;
+    }
+    float* p = dP + f * D + l * 4;
+    float* q = dQ + f * D + l * 4;
+    atomicAdd(p + 0, ap.x); atomicAdd(p + 1, ap.y); atomicAdd(p + 2, ap.z); atomicAdd(p + 3, ap.w);
+    atomicAdd(q + 0, aq.x); atomicAdd(q + 1, aq.y); atomicAdd(q + 2, aq.z); atomicAdd(q + 3, aq.w);
+  }
+}
+
+// blocks [0,F): dw[f,:], db[f,:] ; blocks [F, F+D): dw_out[d,:]
+__global__ void numbin_unfold_kernel(const float* __restrict__ dP, const float* __restrict__ dQ, const float* __restrict__ w,
+                                     const float* __restrict__ b, const float* __restrict__ w_out, float* __restrict__ dw,
+                                     float* __restrict__ db, float* __restrict__ dw_out, int F, int fe, int D) {
+  int e = threadIdx.x;
+  if (e >= fe) return;
+  if ((int)blockIdx.x < F) {
+    int f = blockIdx.x;
+    float a = 0.f, c = 0.f;
+    for (int d = 0; d < D; ++d) {
+      float wo = w_out[d * fe + e];
+      a = fmaf(dP[f * D + d], wo, a);
+      c = fmaf(dQ[f * D + d], wo, c);
+    }
+    dw[f * fe + e] = a;
+    if (db) db[f * fe + e] = c;
+  } else {
+    int d = blockIdx.x - F;
+    float a = 0.f;
+    for (int f = 0; f < F; ++f) {
+      a = fmaf(dP[f * D + d], w[f * fe + e], a);
+      if (b) a = fmaf(dQ[f * D + d], b[f * fe + e], a);
+    }
+    dw_out[d * fe + e] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// categorical gather + projection.  D == 64 (two outputs per lane).
+// ------------------------------------------------------------------------------------------------------
+constexpr int CAT_D = 64;
+constexpr int CAT_MAXDC = 64;
+constexpr int CAT_SPW = 4;            // samples per warp per block pass
+constexpr int CAT_WARPS = 8;
+
+template <typename IT>
+__global__ void __launch_bounds__(CAT_WARPS * 32)
+cat_fwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ tables, const float* const* __restrict__ projs,
+               const int32_t* __restrict__ dims, const int32_t* __restrict__ cards, float* __restrict__ out, int64_t ld_b,
+               float* __restrict__ mean_out, int64_t ld_mean, int q_idx, float* __restrict__ q_out,
+               int64_t B, int Fc, b200ctr_dropout_t drop) {
+  __shared__ float Wt[CAT_MAXDC][CAT_D + 1];               // W_c transposed: Wt[j][n]
+  __shared__ float rows[CAT_WARPS][CAT_SPW][CAT_MAXDC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b_base = ((int64_t)blockIdx.x * CAT_WARPS + warp) * CAT_SPW;
+  float m0[CAT_SPW], m1[CAT_SPW];
+#pragma unroll
+  for (int s = 0; s < CAT_SPW; ++s) m0[s] = m1[s] = 0.f;
+  for (int c = 0; c < Fc; ++c) {
+    const int dc = dims[c];
+    const float* W = projs[c];
+    const float* T = tables[c];
+    const int card = cards[c];
+    __syncthreads();
+    for (int i = threadIdx.x; i < CAT_D * dc; i += blockDim.x) {
+      int n = i / dc, j = i % dc;
+      Wt[j][n] = W[i];
+    }
+#pragma unroll
+    for (int s = 0; s < CAT_SPW; ++s) {
+      int64_t b = b_base + s;
+      if (b < B) {
+        int64_t id = (int64_t)x_cat[b * Fc + c];
+        id = id < 0 ? 0 : (id >= card ? card - 1 : id);     // memory-safe clamp (reference would raise)
+        for (int j = lane; j < dc; j += 32) rows[warp][s][j] = T[id * dc + j];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < CAT_SPW; ++s) {
+      int64_t b = b_base + s;
+      if (b >= B) continue;
+      float a0 = 0.f, a1 = 0.f;
+      for (int j = 0; j < dc; ++j) {
+        float r = rows[warp][s][j];
+        a0 = fmaf(r, Wt[j][lane], a0);
+        a1 = fmaf(r, Wt[j][lane + 32], a1);
+      }
+      m0[s] += a0; m1[s] += a1;
+      if (q_out && c == q_idx) { q_out[b * CAT_D + lane] = a0; q_out[b * CAT_D + lane + 32] = a1; }
+      uint64_t eid = ((uint64_t)b * Fc + c) * CAT_D;
+      float* o = out + b * ld_b + (int64_t)c * CAT_D;
+      o[lane] = a0 * drop_scale(drop, eid + lane);
+      o[lane + 32] = a1 * drop_scale(drop, eid + lane + 32);
+    }
+  }
+  if (mean_out) {
+    float inv = 1.f / (float)Fc;
+#pragma unroll
+    for (int s = 0; s < CAT_SPW; ++s) {
+      int64_t b = b_base + s;
+      if (b < B) { mean_out[b * ld_mean + lane] = m0[s] * inv; mean_out[b * ld_mean + lane + 32] = m1[s] * inv; }
+    }
+  }
+}
+
+// grid (NBX, Fc).  Block (bx, c) walks sample tiles of 32 with stride NBX: stages g and the gathered rows,
+// accumulates dW_c in registers (one atomic per element per block at the end) and scatters dE_c rows.
+constexpr int CATB_TS = 32;
+template <typename IT>
+__global__ void __launch_bounds__(256)
+cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ tables, const float* const* __restrict__ projs,
+               const int32_t* __restrict__ dims, const int32_t* __restrict__ cards, const float* __restrict__ dout, int64_t ld_b,
+               const float* __restrict__ dmean, int64_t ld_dmean, int q_idx, const float* __restrict__ dq,
+               float* const* __restrict__ dtables, float* const* __restrict__ dprojs, int64_t B, int Fc,
+               b200ctr_dropout_t drop) {
+  __shared__ float Ws[CAT_D][CAT_MAXDC + 1];           // natural layout W[n][j]
+  __shared__ float gs[CATB_TS][CAT_D + 1];
+  __shared__ float rs[CATB_TS][CAT_MAXDC + 1];
+  __shared__ int64_t ids[CATB_TS];
+  const int c = blockIdx.y;
+  const int dc = dims[c];
+  const int card = cards[c];
+  const float* W = projs[c];
+  const float* T = tables[c];
+  float* dT = dtables[c];
+  float* dW = dprojs[c];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < CAT_D * dc; i += blockDim.x) Ws[i / dc][i % dc] = W[i];
+  // this thread's dW elements: e = tid + k*256 < 64*dc  (<= 16 of them)
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  const float invFc = 1.f / (float)Fc;
+  const int64_t ntiles = ceil_div(B, (int64_t)CATB_TS);
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t b0 = t * CATB_TS;
+    __syncthreads();
+    if (tid < CATB_TS) {
+      int64_t b = b0 + tid;
+      int64_t id = 0;
+      if (b < B) { id = (int64_t)x_cat[b * Fc + c]; id = id < 0 ? 0 : (id >= card ? card - 1 : id); }
+      ids[tid] = id;
+    }
+    for (int i = tid; i < CATB_TS * CAT_D; i += blockDim.x) {
+      int s = i / CAT_D, n = i % CAT_D;
+      int64_t b = b0 + s;
+      float g = 0.f;
+      if (b < B) {
+        if (dout) g = dout[b * ld_b + (int64_t)c * CAT_D + n] * drop_scale(drop, ((uint64_t)b * Fc + c) * CAT_D + n);
+        if (dmean) g = fmaf(dmean[b * ld_dmean + n], invFc, g);
+        if (dq && c == q_idx) g += dq[b * CAT_D + n];
+      }
+      gs[s][n] = g;
+    }
+    __syncthreads();
+    for (int i = tid; i < CATB_TS * dc; i += blockDim.x) {
+      int s = i / dc, j = i % dc;
+      rs[s][j] = (b0 + s < B) ? T[ids[s] * dc + j] : 0.f;
+    }
+    __syncthreads();
+    // dW[n][j] += sum_s g[s][n] * row[s][j]
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      int e = tid + k * 256;
+      if (e < CAT_D * dc) {
+        int n = e / dc, j = e % dc;
+        float a = acc[k];
+#pragma unroll 8
+        for (int s = 0; s < CATB_TS; ++s) a = fmaf(gs[s][n], rs[s][j], a);
+        acc[k] = a;
+      }
+    }
+    // dE[id][j] += sum_n W[n][j] * g[n]   (warp per sample, lane per j)
+    for (int s = warp; s < CATB_TS; s += 8) {
+      if (b0 + s >= B) continue;
+      for (int j = lane; j < dc; j += 32) {
+        float a = 0.f;
+#pragma unroll 8
+        for (int n = 0; n < CAT_D; ++n) a = fmaf(Ws[n][j], gs[s][n], a);
+        atomicAdd(dT + ids[s] * dc + j, a);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    int e = tid + k * 256;
+    if (e < CAT_D * dc) atomicAdd(dW + e, acc[k]);
+  }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float a, float b,
+                             float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a * (x ? x[i] : 0.f) + b * (y ? y[i] : 0.f);
+}
+
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float scale,
+                                float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = y[i] > 0.f ? scale * dy[i] : 0.f;
+}
+__global__ void sigmoid_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = sigmoidf_(x[i]);
+}
+__global__ void add2d_kernel(float* __restrict__ dst, int64_t ld_dst, const float* __restrict__ src, int64_t ld_src,
+                             int64_t rows, int64_t cols) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  int64_t r = i / cols, c = i % cols;
+  dst[r * ld_dst + c] += src[r * ld_src + c];
+}
+
+}  // namespace b200ctr
+
+using namespace b200ctr;
+
+extern "C" int b200ctr_relu_bwd(const float* dy, const float* y, float scale, float* out, int64_t n, void* stream) {
+  B200_REQUIRE(dy && y && out, B200CTR_E_INVALID_ARG, "relu_bwd: null pointer");
+  if (n == 0) return B200CTR_OK;
+  relu_bwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(dy, y, scale, out, n);
+  B200_LAUNCH_CHECK("relu_bwd_kernel");
+  return B200CTR_OK;
+}
+extern "C" int b200ctr_sigmoid(const float* x, float* out, int64_t n, void* stream) {
+  B200_REQUIRE(x && out, B200CTR_E_INVALID_ARG, "sigmoid: null pointer");
+  if (n == 0) return B200CTR_OK;
+  sigmoid_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(x, out, n);
+  B200_LAUNCH_CHECK("sigmoid_kernel");
+  return B200CTR_OK;
+}
+extern "C" int b200ctr_add2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* stream) {
+  B200_REQUIRE(dst && src, B200CTR_E_INVALID_ARG, "add2d: null pointer");
+  if (rows * cols == 0) return B200CTR_OK;
+  add2d_kernel<<<(unsigned)ceil_div(rows * cols, 256), 256, 0, as_stream(stream)>>>(dst, ld_dst, src, ld_src, rows, cols);
+  B200_LAUNCH_CHECK("add2d_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_numbin_fold(const float* w, const float* b, const float* w_out, float* P, float* Q, int F, int fe,
+                                   int D, void* stream) {
+  B200_REQUIRE(w && w_out && P && Q, B200CTR_E_INVALID_ARG, "numbin_fold: null pointer");
+  B200_REQUIRE(D > 0 && D <= 1024, B200CTR_E_UNSUPPORTED_SHAPE, "numbin_fold: D=%d unsupported", D);
+  if (F == 0) return B200CTR_OK;
+  numbin_fold_kernel<<<F, D, 0, as_stream(stream)>>>(w, b, w_out, P, Q, F, fe, D);
+  B200_LAUNCH_CHECK("numbin_fold_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_numbin_fwd(const float* x, const float* P, const float* Q, float* out, int64_t ld_b,
+                                  float* mean_out, int64_t ld_mean, int64_t B, int F, int D, void* stream) {
+  B200_REQUIRE(x && P && Q && (out || mean_out), B200CTR_E_INVALID_ARG, "numbin_fwd: null pointer");
+  B200_REQUIRE(D % 4 == 0 && D >= 4 && D <= 256 && 256 % (D / 4) == 0, B200CTR_E_UNSUPPORTED_SHAPE, "numbin_fwd: D=%d unsupported", D);
+  B200_REQUIRE(ld_b % 4 == 0 && (!mean_out || ld_mean % 4 == 0), B200CTR_E_INVALID_ARG, "numbin_fwd: leading dims must be multiples of 4");
+  if (B == 0 || F == 0) return B200CTR_OK;
+  int grid = (int)std::min<int64_t>(B, (int64_t)num_sms() * 8);
+  numbin_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, P, Q, out, ld_b, mean_out, ld_mean, B, F, D);
+  B200_LAUNCH_CHECK("numbin_fwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_numbin_bwd(const float* x, const float* dout, int64_t ld_b, const float* dmean, int64_t ld_dmean,
+                                  float* dP, float* dQ, int64_t B, int F, int D, void* stream) {
+  B200_REQUIRE(x && dP && dQ && (dout || dmean), B200CTR_E_INVALID_ARG, "numbin_bwd: null pointer");
+  B200_REQUIRE(D % 4 == 0, B200CTR_E_UNSUPPORTED_SHAPE, "numbin_bwd: D=%d unsupported", D);
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(dP, 0, sizeof(float) * F * D, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dQ, 0, sizeof(float) * F * D, st);
+  if (e != cudaSuccess) return cuda_fail(e, "numbin_bwd memset");
+  if (B == 0 || F == 0) return B200CTR_OK;
+  int64_t chunk = 32;
+  int grid = (int)ceil_div(B, chunk);
+  numbin_bwd_kernel<<<grid, 256, 0, st>>>(x, dout, ld_b, dmean, ld_dmean, dP, dQ, B, F, D, chunk);
+  B200_LAUNCH_CHECK("numbin_bwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_numbin_unfold(const float* dP, const float* dQ, const float* w, const float* b, const float* w_out,
+                                     float* dw, float* db, float* dw_out, int F, int fe, int D, void* stream) {
+  B200_REQUIRE(dP && dQ && w && w_out && dw && dw_out, B200CTR_E_INVALID_ARG, "numbin_unfold: null pointer");
+  B200_REQUIRE(fe > 0 && fe <= 1024, B200CTR_E_UNSUPPORTED_SHAPE, "numbin_unfold: fe=%d unsupported", fe);
+  numbin_unfold_kernel<<<F + D, fe, 0, as_stream(stream)>>>(dP, dQ, w, b, w_out, dw, db, dw_out, F, fe, D);
+  B200_LAUNCH_CHECK("numbin_unfold_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_cat_fwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
+                               const int32_t* dims, const int32_t* cards, float* out, int64_t ld_b, float* mean_out,
+                               int64_t ld_mean, int q_idx, float* q_out, int64_t B, int Fc, int D, b200ctr_dropout_t drop,
+                               void* stream) {
+  B200_REQUIRE(x_cat && tables && projs && dims && cards && out, B200CTR_E_INVALID_ARG, "cat_fwd: null pointer");
+  B200_REQUIRE(D == CAT_D, B200CTR_E_UNSUPPORTED_SHAPE, "cat_fwd: emb_dim=%d unsupported (kernel is specialised for 64)", D);
+  if (B == 0 || Fc == 0) return B200CTR_OK;
+  int grid = (int)ceil_div(B, (int64_t)CAT_WARPS * CAT_SPW);
+  cudaStream_t st = as_stream(stream);
+  if (idx_is_64)
+    cat_fwd_kernel<int64_t><<<grid, CAT_WARPS * 32, 0, st>>>((const int64_t*)x_cat, tables, projs, dims, cards, out, ld_b,
+                                                              mean_out, ld_mean, q_idx, q_out, B, Fc, drop);
+  else
+    cat_fwd_kernel<int32_t><<<grid, CAT_WARPS * 32, 0, st>>>((const int32_t*)x_cat, tables, projs, dims, cards, out, ld_b,
+                                                              mean_out, ld_mean, q_idx, q_out, B, Fc, drop);
+  B200_LAUNCH_CHECK("cat_fwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
+                               const int32_t* dims, const int32_t* cards, const float* dout, int64_t ld_b,
+                               const float* dmean, int64_t ld_dmean, int q_idx, const float* dq, float* const* dtables,
+                               float* const* dprojs, int64_t B, int Fc, int D, b200ctr_dropout_t drop, void* stream) {
+  B200_REQUIRE(x_cat && tables && projs && dims && cards && dtables && dprojs, B200CTR_E_INVALID_ARG, "cat_bwd: null pointer");
+  B200_REQUIRE(D == CAT_D, B200CTR_E_UNSUPPORTED_SHAPE, "cat_bwd: emb_dim=%d unsupported (kernel is specialised for 64)", D);
+  if (B == 0 || Fc == 0) return B200CTR_OK;
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(B, (int64_t)CATB_TS), 16), (unsigned)Fc);
+  cudaStream_t st = as_stream(stream);
+  if (idx_is_64)
+    cat_bwd_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)x_cat, tables, projs, dims, cards, dout, ld_b, dmean,
+                                                   ld_dmean, q_idx, dq, dtables, dprojs, B, Fc, drop);
+  else
+    cat_bwd_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)x_cat, tables, projs, dims, cards, dout, ld_b, dmean,
+                                                   ld_dmean, q_idx, dq, dtables, dprojs, B, Fc, drop);
+  B200_LAUNCH_CHECK("cat_bwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_axpby(const float* x, const float* y, float a, float b, float* out, int64_t n, void* stream) {
+  B200_REQUIRE(out && (x || y), B200CTR_E_INVALID_ARG, "axpby: null pointer");
+  if (n == 0) return B200CTR_OK;
+  axpby_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(x, y, a, b, out, n);
+  B200_LAUNCH_CHECK("axpby_kernel");
+  return B200CTR_OK;
+}

@@ -1,0 +1,331 @@
+// K2b pieces: tiny-head attention (head_dim 8) with Toeplitz relative-position bias, residual + RMSNorm,
+// and their backward.  Reference: src/models/dare.py:29-37 (PositionalBias), 53-70 (DAREEncoderLayer),
+// torch.nn.MultiheadAttention math (q scaled by 1/sqrt(hd), additive float mask, dropout on probabilities).
+//
+// Attention runs one CTA per sample with K and V of all heads resident in shared memory; each thread owns one
+// (query row, head) pair, so the K x K probabilities never leave registers.  Only the per-row log-sum-exp is
+// saved; the backward pass recomputes probabilities (the reference stores B*H*K*K floats per layer instead).
+#include "common.cuh"
+#include <algorithm>
+
+namespace b200ctr {
+
+constexpr int AT_D = 64;
+constexpr int AT_HD = 8;
+constexpr int AT_THREADS = 256;
+
+__device__ __forceinline__ float dot8(const float* a, const float4& b0, const float4& b1) {
+  float s = a[0] * b0.x;
+  s = fmaf(a[1], b0.y, s); s = fmaf(a[2], b0.z, s); s = fmaf(a[3], b0.w, s);
+  s = fmaf(a[4], b1.x, s); s = fmaf(a[5], b1.y, s); s = fmaf(a[6], b1.z, s); s = fmaf(a[7], b1.w, s);
+  return s;
+}
+
+__global__ void __launch_bounds__(AT_THREADS)
+attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, int K, int H,
+                float* __restrict__ o, float* __restrict__ lse, b200ctr_dropout_t drop) {
+  extern __shared__ __align__(16) float sm[];
+  float* ks = sm;                         // K x 64
+  float* vs = ks + (size_t)K * AT_D;      // K x 64
+  float* bias = vs + (size_t)K * AT_D;    // 2K-1 : bias[(j-i)+K-1]
+  const int64_t b = blockIdx.x;
+  const float* base = qkv + b * (int64_t)K * 3 * AT_D;
+  for (int i = threadIdx.x; i < K * (AT_D / 4); i += AT_THREADS) {
+    int r = i / (AT_D / 4), c = i % (AT_D / 4);
+    reinterpret_cast<float4*>(ks)[i] = *reinterpret_cast<const float4*>(base + (int64_t)r * 3 * AT_D + AT_D + c * 4);
+    reinterpret_cast<float4*>(vs)[i] = *reinterpret_cast<const float4*>(base + (int64_t)r * 3 * AT_D + 2 * AT_D + c * 4);
+  }
+  for (int t = threadIdx.x; t < 2 * K - 1; t += AT_THREADS) {
+    int d = t - (K - 1);                                   // j - i
+    int di = min(max(d, -max_len), max_len) + max_len;
+    bias[t] = relmean ? relmean[di] : 0.f;
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)AT_HD);
+  for (int item = threadIdx.x; item < K * H; item += AT_THREADS) {
+    const int h = item / K, i = item % K;
+    float q[AT_HD];
+    {
+      const float4* qp = reinterpret_cast<const float4*>(base + (int64_t)i * 3 * AT_D + h * AT_HD);
+      float4 a = qp[0], c = qp[1];
+      q[0] = a.x * scale; q[1] = a.y * scale; q[2] = a.z * scale; q[3] = a.w * scale;
+      q[4] = c.x * scale; q[5] = c.y * scale; q[6] = c.z * scale; q[7] = c.w * scale;
+    }
+    const float* bi = bias + (K - 1) - i;                  // bi[j] = bias[j-i+K-1]
+    float m = -INFINITY;
+    for (int j = 0; j < K; ++j) {
+      const float4* kp = reinterpret_cast<const float4*>(ks + (size_t)j * AT_D + h * AT_HD);
+      float s = dot8(q, kp[0], kp[1]) + bi[j];
+      m = fmaxf(m, s);
+    }
+    float l = 0.f;
+    float acc[AT_HD];
+#pragma unroll
+    for (int d = 0; d < AT_HD; ++d) acc[d] = 0.f;
+    const uint64_t eid0 = (((uint64_t)b * H + h) * K + i) * K;
+    for (int j = 0; j < K; ++j) {
+      const float4* kp = reinterpret_cast<const float4*>(ks + (size_t)j * AT_D + h * AT_HD);
+      float s = dot8(q, kp[0], kp[1]) + bi[j];
+      float e = expf(s - m);
+      l += e;
+      float ed = e * drop_scale(drop, eid0 + j);
+      const float4* vp = reinterpret_cast<const float4*>(vs + (size_t)j * AT_D + h * AT_HD);
+      float4 v0 = vp[0], v1 = vp[1];
+      acc[0] = fmaf(ed, v0.x, acc[0]); acc[1] = fmaf(ed, v0.y, acc[1]); acc[2] = fmaf(ed, v0.z, acc[2]); acc[3] = fmaf(ed, v0.w, acc[3]);
+      acc[4] = fmaf(ed, v1.x, acc[4]); acc[5] = fmaf(ed, v1.y, acc[5]); acc[6] = fmaf(ed, v1.z, acc[6]); acc[7] = fmaf(ed, v1.w, acc[7]);
+    }
+    float inv = 1.f / l;
+    float4* op = reinterpret_cast<float4*>(o + (b * K + i) * (int64_t)AT_D + h * AT_HD);
+    op[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    op[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+    lse[(b * H + h) * (int64_t)K + i] = m + logf(l);
+  }
+}
+
+__global__ void __launch_bounds__(AT_THREADS)
+attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, const float* __restrict__ o,
+                const float* __restrict__ lse, const float* __restrict__ d_o, int K, int H, float* __restrict__ dqkv,
+                float* __restrict__ drelmean, b200ctr_dropout_t drop) {
+  extern __shared__ __align__(16) float sm[];
+  float* qs = sm;                            // K x 64 (pre-scaled by 1/sqrt(hd))
+  float* ks = qs + (size_t)K * AT_D;
+  float* vs = ks + (size_t)K * AT_D;
+  float* dos = vs + (size_t)K * AT_D;
+  float* lses = dos + (size_t)K * AT_D;      // K*H  [h*K+i]
+  float* dsum = lses + (size_t)K * H;        // K*H
+  float* bias = dsum + (size_t)K * H;        // 2K-1
+  float* dbias = bias + (2 * K - 1);         // 2K-1
+  const int64_t b = blockIdx.x;
+  const float* base = qkv + b * (int64_t)K * 3 * AT_D;
+  const float scale = rsqrtf((float)AT_HD);
+  for (int i = threadIdx.x; i < K * (AT_D / 4); i += AT_THREADS) {
+    int r = i / (AT_D / 4), c = i % (AT_D / 4);
+    float4 qv = *reinterpret_cast<const float4*>(base + (int64_t)r * 3 * AT_D + c * 4);
+    qv.x *= scale; qv.y *= scale; qv.z *= scale; qv.w *= scale;
+    reinterpret_cast<float4*>(qs)[i] = qv;
+    reinterpret_cast<float4*>(ks)[i] = *reinterpret_cast<const float4*>(base + (int64_t)r * 3 * AT_D + AT_D + c * 4);
+    reinterpret_cast<float4*>(vs)[i] = *reinterpret_cast<const float4*>(base + (int64_t)r * 3 * AT_D + 2 * AT_D + c * 4);
+    reinterpret_cast<float4*>(dos)[i] = *reinterpret_cast<const float4*>(d_o + (b * K + r) * (int64_t)AT_D + c * 4);
+  }
+  for (int t = threadIdx.x; t < 2 * K - 1; t += AT_THREADS) {
+    int d = t - (K - 1);
+    int di = min(max(d, -max_len), max_len) + max_len;
+    bias[t] = relmean ? relmean[di] : 0.f;
+    dbias[t] = 0.f;
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < K * H; item += AT_THREADS) {
+    const int h = item / K, i = item % K;
+    lses[item] = lse[(b * H + h) * (int64_t)K + i];
+    const float4* op = reinterpret_cast<const float4*>(o + (b * K + i) * (int64_t)AT_D + h * AT_HD);
+    const float4* dp = reinterpret_cast<const float4*>(dos + (size_t)i * AT_D + h * AT_HD);
+    float4 o0 = op[0], o1 = op[1], d0 = dp[0], d1 = dp[1];
+    dsum[item] = o0.x * d0.x + o0.y * d0.y + o0.z * d0.z + o0.w * d0.w + o1.x * d1.x + o1.y * d1.y + o1.z * d1.z + o1.w * d1.w;
+  }
+  __syncthreads();
+  // phase 1: thread per (i,h) -> dq_i, dbias
+  for (int item = threadIdx.x; item < K * H; item += AT_THREADS) {
+    const int h = item / K, i = item % K;
+    float q[AT_HD], dd[AT_HD], dq[AT_HD];
+#pragma unroll
+    for (int d = 0; d < AT_HD; ++d) { q[d] = qs[(size_t)i * AT_D + h * AT_HD + d]; dd[d] = dos[(size_t)i * AT_D + h * AT_HD + d]; dq[d] = 0.f; }
+    const float L = lses[item], Di = dsum[item];
+    const float* bi = bias + (K - 1) - i;
+    float* dbi = dbias + (K - 1) - i;
+    const uint64_t eid0 = (((uint64_t)b * H + h) * K + i) * K;
+    for (int j = 0; j < K; ++j) {
+      const float4* kp = reinterpret_cast<const float4*>(ks + (size_t)j * AT_D + h * AT_HD);
+      const float4* vp = reinterpret_cast<const float4*>(vs + (size_t)j * AT_D + h * AT_HD);
+      float4 k0 = kp[0], k1 = kp[1];
+      float s = dot8(q, k0, k1) + bi[j];
+      float p = expf(s - L);
+      float dp = dot8(dd, vp[0], vp[1]) * drop_scale(drop, eid0 + j);
+      float ds = p * (dp - Di);
+      dq[0] = fmaf(ds, k0.x, dq[0]); dq[1] = fmaf(ds, k0.y, dq[1]); dq[2] = fmaf(ds, k0.z, dq[2]); dq[3] = fmaf(ds, k0.w, dq[3]);
+      dq[4] = fmaf(ds, k1.x, dq[4]); dq[5] = fmaf(ds, k1.y, dq[5]); dq[6] = fmaf(ds, k1.z, dq[6]); dq[7] = fmaf(ds, k1.w, dq[7]);
+      if (drelmean) atomicAdd(dbi + j, ds);
+    }
+    float4* out = reinterpret_cast<float4*>(dqkv + (b * K + i) * (int64_t)(3 * AT_D) + h * AT_HD);
+    out[0] = make_float4(dq[0] * scale, dq[1] * scale, dq[2] * scale, dq[3] * scale);
+    out[1] = make_float4(dq[4] * scale, dq[5] * scale, dq[6] * scale, dq[7] * scale);
+  }
+  // phase 2: thread per (j,h) -> dk_j, dv_j
+  for (int item = threadIdx.x; item < K * H; item += AT_THREADS) {
+    const int h = item / K, j = item % K;
+    float kk[AT_HD], vv[AT_HD], dk[AT_HD], dv[AT_HD];
+#pragma unroll
+    for (int d = 0; d < AT_HD; ++d) { kk[d] = ks[(size_t)j * AT_D + h * AT_HD + d]; vv[d] = vs[(size_t)j * AT_D + h * AT_HD + d]; dk[d] = 0.f; dv[d] = 0.f; }
+    for (int i = 0; i < K; ++i) {
+      const float4* qp = reinterpret_cast<const float4*>(qs + (size_t)i * AT_D + h * AT_HD);
+      const float4* dp4 = reinterpret_cast<const float4*>(dos + (size_t)i * AT_D + h * AT_HD);
+      float4 q0 = qp[0], q1 = qp[1], d0 = dp4[0], d1 = dp4[1];
+      float s = dot8(kk, q0, q1) + bias[(j - i) + K - 1];
+      float p = expf(s - lses[h * K + i]);
+      float dsc = drop_scale(drop, (((uint64_t)b * H + h) * K + i) * K + j);
+      float pd = p * dsc;
+      dv[0] = fmaf(pd, d0.x, dv[0]); dv[1] = fmaf(pd, d0.y, dv[1]); dv[2] = fmaf(pd, d0.z, dv[2]); dv[3] = fmaf(pd, d0.w, dv[3]);
+      dv[4] = fmaf(pd, d1.x, dv[4]); dv[5] = fmaf(pd, d1.y, dv[5]); dv[6] = fmaf(pd, d1.z, dv[6]); dv[7] = fmaf(pd, d1.w, dv[7]);
+      float dp = dot8(vv, d0, d1) * dsc;
+      float ds = p * (dp - dsum[h * K + i]);
+      dk[0] = fmaf(ds, q0.x, dk[0]); dk[1] = fmaf(ds, q0.y, dk[1]); dk[2] = fmaf(ds, q0.z, dk[2]); dk[3] = fmaf(ds, q0.w, dk[3]);
+      dk[4] = fmaf(ds, q1.x, dk[4]); dk[5] = fmaf(ds, q1.y, dk[5]); dk[6] = fmaf(ds, q1.z, dk[6]); dk[7] = fmaf(ds, q1.w, dk[7]);
+    }
+    float4* outk = reinterpret_cast<float4*>(dqkv + (b * K + j) * (int64_t)(3 * AT_D) + AT_D + h * AT_HD);
+    float4* outv = reinterpret_cast<float4*>(dqkv + (b * K + j) * (int64_t)(3 * AT_D) + 2 * AT_D + h * AT_HD);
+    outk[0] = make_float4(dk[0], dk[1], dk[2], dk[3]); outk[1] = make_float4(dk[4], dk[5], dk[6], dk[7]);   // qs carries the scale
+    outv[0] = make_float4(dv[0], dv[1], dv[2], dv[3]); outv[1] = make_float4(dv[4], dv[5], dv[6], dv[7]);
+  }
+  if (drelmean) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * K - 1; t += AT_THREADS) {
+      int d = t - (K - 1);
+      int di = min(max(d, -max_len), max_len) + max_len;
+      atomicAdd(drelmean + di, dbias[t]);
+    }
+  }
+}
+
+// warp per row, D == 64
+__global__ void __launch_bounds__(256)
+add_rmsnorm_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ w, float eps,
+                       int64_t M, float* __restrict__ s_out, float* __restrict__ y_out, float* __restrict__ r_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float2 wv = reinterpret_cast<const float2*>(w)[lane];
+  for (int64_t m = warp; m < M; m += nwarps) {
+    float2 s = reinterpret_cast<const float2*>(a + m * AT_D)[lane];
+    if (b) { float2 t = reinterpret_cast<const float2*>(b + m * AT_D)[lane]; s.x += t.x; s.y += t.y; }
+    float ss = warp_sum(s.x * s.x + s.y * s.y);
+    float r = rsqrtf(ss * (1.f / AT_D) + eps);
+    if (s_out) reinterpret_cast<float2*>(s_out + m * AT_D)[lane] = s;
+    reinterpret_cast<float2*>(y_out + m * AT_D)[lane] = make_float2(wv.x * s.x * r, wv.y * s.y * r);
+    if (lane == 0 && r_out) r_out[m] = r;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const float* __restrict__ w,
+                   const float* __restrict__ r, int64_t M, const float* __restrict__ dx_add, float* __restrict__ dx,
+                   float* __restrict__ dw) {
+  __shared__ float2 red[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float2 wv = reinterpret_cast<const float2*>(w)[lane];
+  float2 dwa = make_float2(0.f, 0.f);
+  for (int64_t m = warp; m < M; m += nwarps) {
+    float2 d = reinterpret_cast<const float2*>(dy + m * AT_D)[lane];
+    float2 x = reinterpret_cast<const float2*>(s + m * AT_D)[lane];
+    float rr = r[m];
+    float2 g = make_float2(d.x * wv.x, d.y * wv.y);
+    float dot = warp_sum(g.x * x.x + g.y * x.y) * (1.f / AT_D);
+    float c = rr * rr * rr * dot;
+    float2 out = make_float2(rr * g.x - x.x * c, rr * g.y - x.y * c);
+    if (dx_add) { float2 t = reinterpret_cast<const float2*>(dx_add + m * AT_D)[lane]; out.x += t.x; out.y += t.y; }
+    reinterpret_cast<float2*>(dx + m * AT_D)[lane] = out;
+    dwa.x = fmaf(d.x * x.x, rr, dwa.x);
+    dwa.y = fmaf(d.y * x.y, rr, dwa.y);
+  }
+  red[wid][lane] = dwa;
+  __syncthreads();
+  if (wid == 0) {
+    float2 t = red[0][lane];
+    for (int k = 1; k < 8; ++k) { t.x += red[k][lane].x; t.y += red[k][lane].y; }
+    atomicAdd(dw + 2 * lane, t.x);
+    atomicAdd(dw + 2 * lane + 1, t.y);
+  }
+}
+
+__global__ void relmean_fwd_kernel(const float* __restrict__ rel, int T, int H, float* __restrict__ relmean) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float s = 0.f;
+  for (int h = 0; h < H; ++h) s += rel[t * H + h];
+  relmean[t] = s / (float)H;
+}
+__global__ void relmean_bwd_kernel(const float* __restrict__ drelmean, int T, int H, float* __restrict__ drel) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * H) return;
+  drel[i] = drelmean[i / H] / (float)H;
+}
+
+static int set_attn_smem(const void* fn, size_t bytes) {
+  if (bytes > 227 * 1024) {
+    set_error("attention: K too large for one CTA's shared memory (%zu bytes)", bytes);
+    return B200CTR_E_UNSUPPORTED_SHAPE;
+  }
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attention smem)");
+  }
+  return B200CTR_OK;
+}
+
+}  // namespace b200ctr
+
+using namespace b200ctr;
+
+extern "C" int b200ctr_attn_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D, float* o,
+                                float* lse, b200ctr_dropout_t drop, void* stream) {
+  B200_REQUIRE(qkv && o && lse, B200CTR_E_INVALID_ARG, "attn_fwd: null pointer");
+  B200_REQUIRE(D == AT_D && H * AT_HD == D, B200CTR_E_UNSUPPORTED_SHAPE,
+               "attn_fwd: only emb_dim=64 with head_dim=8 is built (got D=%d, H=%d)", D, H);
+  if (B == 0 || K == 0) return B200CTR_OK;
+  size_t smem = ((size_t)2 * K * AT_D + 2 * K) * sizeof(float);
+  int rc = set_attn_smem((const void*)attn_fwd_kernel, smem);
+  if (rc) return rc;
+  attn_fwd_kernel<<<(unsigned)B, AT_THREADS, smem, as_stream(stream)>>>(qkv, relmean, max_len, K, H, o, lse, drop);
+  B200_LAUNCH_CHECK("attn_fwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_attn_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
+                                const float* d_o, int64_t B, int K, int H, int D, float* dqkv, float* drelmean,
+                                b200ctr_dropout_t drop, void* stream) {
+  B200_REQUIRE(qkv && o && lse && d_o && dqkv, B200CTR_E_INVALID_ARG, "attn_bwd: null pointer");
+  B200_REQUIRE(D == AT_D && H * AT_HD == D, B200CTR_E_UNSUPPORTED_SHAPE,
+               "attn_bwd: only emb_dim=64 with head_dim=8 is built (got D=%d, H=%d)", D, H);
+  if (B == 0 || K == 0) return B200CTR_OK;
+  size_t smem = ((size_t)4 * K * AT_D + 2 * (size_t)K * H + 4 * K) * sizeof(float);
+  int rc = set_attn_smem((const void*)attn_bwd_kernel, smem);
+  if (rc) return rc;
+  attn_bwd_kernel<<<(unsigned)B, AT_THREADS, smem, as_stream(stream)>>>(qkv, relmean, max_len, o, lse, d_o, K, H, dqkv, drelmean, drop);
+  B200_LAUNCH_CHECK("attn_bwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_add_rmsnorm_fwd(const float* a, const float* b, const float* w, float eps, int64_t M, int D,
+                                       float* s_out, float* y_out, float* r_out, void* stream) {
+  B200_REQUIRE(a && w && y_out, B200CTR_E_INVALID_ARG, "add_rmsnorm_fwd: null pointer");
+  B200_REQUIRE(D == AT_D, B200CTR_E_UNSUPPORTED_SHAPE, "add_rmsnorm_fwd: D=%d unsupported (64 only)", D);
+  if (M == 0) return B200CTR_OK;
+  int grid = (int)std::min<int64_t>(ceil_div(M, 8), (int64_t)num_sms() * 16);
+  add_rmsnorm_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(a, b, w, eps, M, s_out, y_out, r_out);
+  B200_LAUNCH_CHECK("add_rmsnorm_fwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_rmsnorm_bwd(const float* dy, const float* s, const float* w, const float* r, int64_t M, int D,
+                                   const float* dx_add, float* dx, float* dw, void* stream) {
+  B200_REQUIRE(dy && s && w && r && dx && dw, B200CTR_E_INVALID_ARG, "rmsnorm_bwd: null pointer");
+  B200_REQUIRE(D == AT_D, B200CTR_E_UNSUPPORTED_SHAPE, "rmsnorm_bwd: D=%d unsupported (64 only)", D);
+  if (M == 0) return B200CTR_OK;
+  int grid = (int)std::min<int64_t>(ceil_div(M, 8), (int64_t)num_sms() * 8);
+  rmsnorm_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(dy, s, w, r, M, dx_add, dx, dw);
+  B200_LAUNCH_CHECK("rmsnorm_bwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_relmean_fwd(const float* rel, int T, int H, float* relmean, void* stream) {
+  B200_REQUIRE(rel && relmean, B200CTR_E_INVALID_ARG, "relmean_fwd: null pointer");
+  relmean_fwd_kernel<<<(T + 127) / 128, 128, 0, as_stream(stream)>>>(rel, T, H, relmean);
+  B200_LAUNCH_CHECK("relmean_fwd_kernel");
+  return B200CTR_OK;
+}
+extern "C" int b200ctr_relmean_bwd(const float* drelmean, int T, int H, float* drel, void* stream) {
+  B200_REQUIRE(drelmean && drel, B200CTR_E_INVALID_ARG, "relmean_bwd: null pointer");
+  relmean_bwd_kernel<<<(T * H + 127) / 128, 128, 0, as_stream(stream)>>>(drelmean, T, H, drel);
+  B200_LAUNCH_CHECK("relmean_bwd_kernel");
+  return B200CTR_OK;
+}

@@ -1,0 +1,264 @@
+// K3 pieces that are not plain contractions: row RMSNorm over F*D, the FM-trick reductions of the low-rank
+// quadratic interaction, the batch-statistic SE gate and its application.
+// Reference: src/models/qnn_alpha.py:6-12 (RMSNorm), 24-26 (SEBlock), 86-97 (_pair_interaction_all), 109-130.
+#include "common.cuh"
+#include <algorithm>
+
+namespace b200ctr {
+
+constexpr int RR_THREADS = 256;
+constexpr int RR_MAXV = 16;          // float4 slots per thread => N <= 16*4*256 = 16384
+
+__global__ void __launch_bounds__(RR_THREADS)
+rowrms_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, float eps, int64_t N,
+                  float* __restrict__ z, int64_t ld_z, float* __restrict__ r) {
+  __shared__ float red[32];
+  const int64_t b = blockIdx.x;
+  const float4* xr = reinterpret_cast<const float4*>(x + b * ldx);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  float4* zr = reinterpret_cast<float4*>(z + b * ld_z);
+  const int n4 = (int)(N >> 2);
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n4; i += RR_THREADS) {
+    float4 v = xr[i];
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = block_sum(ss, red);
+  const float rr = rsqrtf(ss / (float)N + eps);
+  for (int i = threadIdx.x; i < n4; i += RR_THREADS) {
+    float4 v = xr[i], ww = __ldg(w4 + i);
+    zr[i] = make_float4(ww.x * v.x * rr, ww.y * v.y * rr, ww.z * v.z * rr, ww.w * v.w * rr);
+  }
+  if (threadIdx.x == 0) r[b] = rr;
+}
+
+// grid = n_partials CTAs; CTA p handles rows p, p+P, ...; per-thread register accumulators for dw.
+__global__ void __launch_bounds__(RR_THREADS)
+rowrms_bwd_kernel(const float* __restrict__ dz, int64_t ld_dz, const float* __restrict__ x, int64_t ldx,
+                  const float* __restrict__ w, const float* __restrict__ r, int64_t B, int64_t N, float* __restrict__ dx,
+                  int64_t ld_dx, float* __restrict__ dw_partial) {
+  __shared__ float red[32];
+  const int n4 = (int)(N >> 2);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  float4 acc[RR_MAXV];
+#pragma unroll
+  for (int s = 0; s < RR_MAXV; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const float4* dzr = reinterpret_cast<const float4*>(dz + b * ld_dz);
+    const float4* xr = reinterpret_cast<const float4*>(x + b * ldx);
+    float4* dxr = reinterpret_cast<float4*>(dx + b * ld_dx);
+    const float rr = r[b];
+    float dot = 0.f;
+#pragma unroll
+    for (int s = 0; s < RR_MAXV; ++s) {
+      int i = threadIdx.x + s * RR_THREADS;
+      if (i < n4) {
+        float4 d = dzr[i], v = xr[i], ww = __ldg(w4 + i);
+        dot += d.x * ww.x * v.x + d.y * ww.y * v.y + d.z * ww.z * v.z + d.w * ww.w * v.w;
+      }
+    }
+    dot = block_sum(dot, red) / (float)N;
+    const float c = rr * rr * rr * dot;
+#pragma unroll
+    for (int s = 0; s < RR_MAXV; ++s) {
+      int i = threadIdx.x + s * RR_THREADS;
+      if (i < n4) {
+        float4 d = dzr[i], v = xr[i], ww = __ldg(w4 + i);
+        dxr[i] = make_float4(rr * d.x * ww.x - v.x * c, rr * d.y * ww.y - v.y * c, rr * d.z * ww.z - v.z * c, rr * d.w * ww.w - v.w * c);
+        acc[s].x = fmaf(d.x * v.x, rr, acc[s].x); acc[s].y = fmaf(d.y * v.y, rr, acc[s].y);
+        acc[s].z = fmaf(d.z * v.z, rr, acc[s].z); acc[s].w = fmaf(d.w * v.w, rr, acc[s].w);
+      }
+    }
+  }
+  float4* out = reinterpret_cast<float4*>(dw_partial + (int64_t)blockIdx.x * N);
+#pragma unroll
+  for (int s = 0; s < RR_MAXV; ++s) {
+    int i = threadIdx.x + s * RR_THREADS;
+    if (i < n4) out[i] = acc[s];
+  }
+}
+
+// A (B,F,C): s[b,c] = sum_f A, quad = s^2 - sum_f A^2.  One CTA per sample.
+__global__ void __launch_bounds__(256)
+fm_reduce_kernel(const float* __restrict__ A, int F, int C, float* __restrict__ s, float* __restrict__ quad) {
+  const int64_t b = blockIdx.x;
+  const float* Ab = A + b * (int64_t)F * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int f = 0; f < F; ++f) { float v = Ab[(int64_t)f * C + c]; a += v; q = fmaf(v, v, q); }
+    s[b * C + c] = a;
+    quad[b * C + c] = a * a - q;
+  }
+}
+
+__global__ void fm_grad_kernel(float* __restrict__ A, const float* __restrict__ s, const float* __restrict__ dquad,
+                               int64_t total, int F, int C) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int64_t b = i / ((int64_t)F * C);
+  int c = (int)(i % C);
+  A[i] = dquad[b * C + c] * 2.f * (s[b * C + c] - A[i]);
+}
+
+// single CTA: m = colsum/B ; h1 = relu(W1 m + b1) ; gate = sigmoid(W2 h1 + b2).  W1 (Cr,C), W2 (C,Cr).
+__global__ void __launch_bounds__(1024)
+se_gate_fwd_kernel(const float* __restrict__ colsum, float inv_B, const float* __restrict__ w1, const float* __restrict__ b1,
+                   const float* __restrict__ w2, const float* __restrict__ b2, int C, int Cr, float* __restrict__ mean,
+                   float* __restrict__ h1, float* __restrict__ gate) {
+  extern __shared__ float sm[];
+  float* ms = sm;            // C
+  float* hs = ms + C;        // Cr
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { float m = colsum[c] * inv_B; ms[c] = m; mean[c] = m; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = warp; j < Cr; j += nw) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(w1[(int64_t)j * C + c], ms[c], a);
+    a = warp_sum(a);
+    if (lane == 0) { float h = fmaxf(a + b1[j], 0.f); hs[j] = h; h1[j] = h; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = b2[c];
+    for (int j = 0; j < Cr; ++j) a = fmaf(w2[(int64_t)c * Cr + j], hs[j], a);
+    gate[c] = sigmoidf_(a);
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+se_gate_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ mean, const float* __restrict__ h1,
+                   const float* __restrict__ gate, const float* __restrict__ w1, const float* __restrict__ w2, int C, int Cr,
+                   float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2,
+                   float* __restrict__ dmean) {
+  extern __shared__ float sm[];
+  float* da2 = sm;           // C
+  float* dh1 = da2 + C;      // Cr
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float g = gate[c];
+    float d = dgate[c] * g * (1.f - g);
+    da2[c] = d;
+    db2[c] = d;
+    for (int j = 0; j < Cr; ++j) dw2[(int64_t)c * Cr + j] = d * h1[j];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = warp; j < Cr; j += nw) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(da2[c], w2[(int64_t)c * Cr + j], a);
+    a = warp_sum(a);
+    if (lane == 0) { float d = h1[j] > 0.f ? a : 0.f; dh1[j] = d; db1[j] = d; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float m = mean[c];
+    float a = 0.f;
+    for (int j = 0; j < Cr; ++j) {
+      float d = dh1[j];
+      dw1[(int64_t)j * C + c] = d * m;
+      a = fmaf(d, w1[(int64_t)j * C + c], a);
+    }
+    dmean[c] = a;
+  }
+}
+
+__global__ void se_apply_fwd_kernel(const float* __restrict__ inter, const float* __restrict__ gate, int64_t B, int C,
+                                    float* __restrict__ out, int64_t ld_out, b200ctr_dropout_t drop) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  int64_t b = i / C;
+  int c = (int)(i % C);
+  float g = gate ? gate[c] : 1.f;
+  out[b * ld_out + c] = inter[i] * g * drop_scale(drop, (uint64_t)i);
+}
+
+__global__ void se_apply_bwd_kernel(const float* __restrict__ dout, int64_t ld_dout, const float* __restrict__ inter,
+                                    const float* __restrict__ gate, const float* __restrict__ dmean, float inv_B, int64_t B,
+                                    int C, float* __restrict__ dinter, float* __restrict__ gprod, b200ctr_dropout_t drop) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  int64_t b = i / C;
+  int c = (int)(i % C);
+  float d = dout[b * ld_dout + c] * drop_scale(drop, (uint64_t)i);
+  if (gprod) gprod[i] = d * inter[i];
+  if (dinter) dinter[i] = d * (gate ? gate[c] : 1.f) + (dmean ? dmean[c] * inv_B : 0.f);
+}
+
+}  // namespace b200ctr
+
+using namespace b200ctr;
+
+extern "C" int b200ctr_rowrms_fwd(const float* x, int64_t ldx, const float* w, float eps, int64_t B, int64_t N, float* z,
+                                  int64_t ld_z, float* r, void* stream) {
+  B200_REQUIRE(x && w && z && r, B200CTR_E_INVALID_ARG, "rowrms_fwd: null pointer");
+  B200_REQUIRE(N % 4 == 0 && ldx % 4 == 0 && ld_z % 4 == 0, B200CTR_E_UNSUPPORTED_SHAPE, "rowrms_fwd: N and leading dims must be multiples of 4");
+  if (B == 0) return B200CTR_OK;
+  rowrms_fwd_kernel<<<(unsigned)B, RR_THREADS, 0, as_stream(stream)>>>(x, ldx, w, eps, N, z, ld_z, r);
+  B200_LAUNCH_CHECK("rowrms_fwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_rowrms_bwd(const float* dz, int64_t ld_dz, const float* x, int64_t ldx, const float* w, const float* r,
+                                  int64_t B, int64_t N, float* dx, int64_t ld_dx, float* dw_partial, int n_partials, void* stream) {
+  B200_REQUIRE(dz && x && w && r && dx && dw_partial, B200CTR_E_INVALID_ARG, "rowrms_bwd: null pointer");
+  B200_REQUIRE(N % 4 == 0 && ldx % 4 == 0 && ld_dz % 4 == 0 && ld_dx % 4 == 0, B200CTR_E_UNSUPPORTED_SHAPE, "rowrms_bwd: alignment");
+  B200_REQUIRE(N <= (int64_t)RR_MAXV * 4 * RR_THREADS, B200CTR_E_UNSUPPORTED_SHAPE, "rowrms_bwd: F*D=%lld exceeds %d", (long long)N, RR_MAXV * 4 * RR_THREADS);
+  B200_REQUIRE(n_partials >= 1, B200CTR_E_INVALID_ARG, "rowrms_bwd: n_partials");
+  rowrms_bwd_kernel<<<n_partials, RR_THREADS, 0, as_stream(stream)>>>(dz, ld_dz, x, ldx, w, r, B, N, dx, ld_dx, dw_partial);
+  B200_LAUNCH_CHECK("rowrms_bwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_fm_reduce(const float* A, int64_t B, int F, int C, float* s, float* quad, void* stream) {
+  B200_REQUIRE(A && s && quad, B200CTR_E_INVALID_ARG, "fm_reduce: null pointer");
+  if (B == 0) return B200CTR_OK;
+  int threads = C <= 128 ? 128 : 256;
+  fm_reduce_kernel<<<(unsigned)B, threads, 0, as_stream(stream)>>>(A, F, C, s, quad);
+  B200_LAUNCH_CHECK("fm_reduce_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_fm_grad(float* A, const float* s, const float* dquad, int64_t B, int F, int C, void* stream) {
+  B200_REQUIRE(A && s && dquad, B200CTR_E_INVALID_ARG, "fm_grad: null pointer");
+  int64_t total = B * F * C;
+  if (total == 0) return B200CTR_OK;
+  fm_grad_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(A, s, dquad, total, F, C);
+  B200_LAUNCH_CHECK("fm_grad_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_se_gate_fwd(const float* colsum, float inv_B, const float* w1, const float* b1, const float* w2,
+                                   const float* b2, int C, int Cr, float* mean, float* h1, float* gate, void* stream) {
+  B200_REQUIRE(colsum && w1 && b1 && w2 && b2 && mean && h1 && gate, B200CTR_E_INVALID_ARG, "se_gate_fwd: null pointer");
+  B200_REQUIRE((size_t)(C + Cr) * 4 <= 48 * 1024, B200CTR_E_UNSUPPORTED_SHAPE, "se_gate_fwd: C=%d too large", C);
+  se_gate_fwd_kernel<<<1, 1024, (size_t)(C + Cr) * 4, as_stream(stream)>>>(colsum, inv_B, w1, b1, w2, b2, C, Cr, mean, h1, gate);
+  B200_LAUNCH_CHECK("se_gate_fwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_se_gate_bwd(const float* dgate, const float* mean, const float* h1, const float* gate, const float* w1,
+                                   const float* w2, int C, int Cr, float* dw1, float* db1, float* dw2, float* db2, float* dmean,
+                                   void* stream) {
+  B200_REQUIRE(dgate && mean && h1 && gate && w1 && w2 && dw1 && db1 && dw2 && db2 && dmean, B200CTR_E_INVALID_ARG, "se_gate_bwd: null pointer");
+  B200_REQUIRE((size_t)(C + Cr) * 4 <= 48 * 1024, B200CTR_E_UNSUPPORTED_SHAPE, "se_gate_bwd: C=%d too large", C);
+  se_gate_bwd_kernel<<<1, 1024, (size_t)(C + Cr) * 4, as_stream(stream)>>>(dgate, mean, h1, gate, w1, w2, C, Cr, dw1, db1, dw2, db2, dmean);
+  B200_LAUNCH_CHECK("se_gate_bwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_se_apply_fwd(const float* inter, const float* gate, int64_t B, int C, float* out, int64_t ld_out,
+                                    b200ctr_dropout_t drop, void* stream) {
+  B200_REQUIRE(inter && out, B200CTR_E_INVALID_ARG, "se_apply_fwd: null pointer");
+  if (B * C == 0) return B200CTR_OK;
+  se_apply_fwd_kernel<<<(unsigned)ceil_div(B * C, 256), 256, 0, as_stream(stream)>>>(inter, gate, B, C, out, ld_out, drop);
+  B200_LAUNCH_CHECK("se_apply_fwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_se_apply_bwd(const float* dout, int64_t ld_dout, const float* inter, const float* gate, const float* dmean,
+                                    float inv_B, int64_t B, int C, float* dinter, float* gprod, b200ctr_dropout_t drop, void* stream) {
+  B200_REQUIRE(dout && inter && (dinter || gprod), B200CTR_E_INVALID_ARG, "se_apply_bwd: null pointer");
+  if (B * C == 0) return B200CTR_OK;
+  se_apply_bwd_kernel<<<(unsigned)ceil_div(B * C, 256), 256, 0, as_stream(stream)>>>(dout, ld_dout, inter, gate, dmean, inv_B, B, C, dinter, gprod, drop);
+  B200_LAUNCH_CHECK("se_apply_bwd_kernel");
+  return B200CTR_OK;
+}
