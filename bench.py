@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — train samples/s (fwd + bwd + clip + AdamW + EMA) of the DARE + QNN-alpha hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # the reference algorithm on the host CPU
+
+Workload (BASELINE.json configs[1]): cfgs/dare_qnn_next.yaml — B=8192, L=400, K=60, 3 encoder layers, QNN-alpha
+(6 heads, rank 16, proj 192, MLP 512-256), 35 hashed-categorical tables, 82 numeric + 82 mask features, two
+10,000,000 x 64 sequence tables, fp32 (the cfg's `amp: none`), dropout ON (train mode), EMA 0.999 — on synthetic
+Toss-shaped data (b200ctr.synth).  One process per GPU; N > 1 = data parallel, B per GPU fixed (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM; `e2e` = the same step
+through FusedTrainer.step() with pinned HOST batches (H2D inside the timed region) and a D2H read of the loss every
+step.  `roofline` describes the dominant kernel family of the step, timed live with CUDA events on the launch stream.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "toss-next-ctr-prediction_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "train samples/sec (fwd+bwd+opt)"
+UNIT = "samples/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]), tf_sus=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_cfg(name: str):
+    from b200ctr import configs
+    return getattr(configs, name)()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU reference arm (the oracle port of the reference algorithm; bench.py may execute oracle/ here only)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference(cfg_name: str, steps: int, warmup: int, sample_B: int = 512, vocab: int = 1_000_001):
+    from b200ctr import configs, synth
+    from oracle import ctr_oracle as O
+    cfg = build_cfg(cfg_name)
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    cols = cfg["data"]["cat_cols"]
+    spec = O.ModelSpec(cfg, configs.N_NUM, configs.N_NUM, cols)
+    g = torch.Generator().manual_seed(cfg["seed"])
+    D = spec.D
+    sd = {}
+    qa = cfg["model"]["qnn_alpha"]
+    fe = int(qa.get("feature_embed_dim", 16))
+    sd["num_embed.weight"] = torch.randn(configs.N_NUM, fe, generator=g) * 0.02
+    sd["num_embed.bias"] = torch.zeros(configs.N_NUM, fe)
+    sd["num_embed.out_proj.weight"] = torch.randn(D, fe, generator=g) * fe ** -0.5
+    sd["mask_embed.weight"] = torch.randn(configs.N_NUM, fe, generator=g) * 0.02
+    sd["mask_embed.out_proj.weight"] = torch.randn(D, fe, generator=g) * fe ** -0.5
+    card = configs.cardinals(cfg)
+    dims = cfg["model"].get("cat_embedding_dims", {})
+    for c in cols:
+        dc = int(dims.get(c, D))
+        sd[f"cat_embs.{c}.weight"] = torch.randn(card[c], dc, generator=g)
+        sd[f"cat_proj.{c}.weight"] = torch.randn(D, dc, generator=g) * dc ** -0.5
+    sd["ctx_mlp.0.weight"] = torch.randn(D, 3 * D, generator=g) * (3 * D) ** -0.5
+    sd["ctx_mlp.0.bias"] = torch.zeros(D)
+    for n in ("dare.emb_att.weight", "dare.emb_rep.weight"):
+        sd[n] = torch.randn(vocab, D, generator=g)
+        sd[n][0] = 0
+    ffn = cfg["sequence"]["tfm"]["ffn_hidden"] if spec.transformer else 0
+    K = spec.top_k
+    for i in range(spec.n_layers):
+        p = f"dare.layers.{i}."
+        sd[p + "mha.in_proj_weight"] = torch.randn(3 * D, D, generator=g) * D ** -0.5
+        sd[p + "mha.in_proj_bias"] = torch.zeros(3 * D)
+        sd[p + "mha.out_proj.weight"] = torch.randn(D, D, generator=g) * D ** -0.5
+        sd[p + "mha.out_proj.bias"] = torch.zeros(D)
+        sd[p + "norm1.w"] = torch.ones(D)
+        sd[p + "ffn.0.weight"] = torch.randn(ffn, D, generator=g) * D ** -0.5
+        sd[p + "ffn.0.bias"] = torch.zeros(ffn)
+        sd[p + "ffn.3.weight"] = torch.randn(D, ffn, generator=g) * ffn ** -0.5
+        sd[p + "ffn.3.bias"] = torch.zeros(D)
+        sd[p + "norm2.w"] = torch.ones(D)
+        sd[p + "pbias.rel.weight"] = torch.randn(2 * K + 1, spec.n_heads, generator=g)
+    sd["dare.aux_head.weight"] = torch.randn(1, D, generator=g) * D ** -0.5
+    sd["dare.aux_head.bias"] = torch.zeros(1)
+    if spec.use_qnn:
+        F = 1 + 2 * configs.N_NUM + len(cols)
+        H, r, Pd = qa["heads"], qa["rank"], qa["proj_dim"]
+        sd["qnn.pre_norm.w"] = torch.ones(F * D)
+        sd["qnn.U"] = torch.randn(H, D, r, generator=g) * 0.02
+        sd["qnn.V"] = torch.randn(H, r, Pd, generator=g) * 0.02
+        HP = H * Pd
+        sd["qnn.se.fc.0.weight"] = torch.randn(HP // 8, HP, generator=g) * HP ** -0.5
+        sd["qnn.se.fc.0.bias"] = torch.zeros(HP // 8)
+        sd["qnn.se.fc.2.weight"] = torch.randn(HP, HP // 8, generator=g) * (HP // 8) ** -0.5
+        sd["qnn.se.fc.2.bias"] = torch.zeros(HP)
+        ind = HP + F * D
+        for li, h in enumerate(list(qa["mlp_hidden"]) + [1]):
+            sd[f"qnn.mlp.{3 * li}.weight"] = torch.randn(h, ind, generator=g) * ind ** -0.5
+            sd[f"qnn.mlp.{3 * li}.bias"] = torch.zeros(h)
+            ind = h
+    ema = cfg.get("ema") or {}
+    tr = O.OracleTrainer(sd, spec, cfg["train"]["lr"], cfg["train"]["weight_decay"], cfg["train"]["grad_clip_norm"],
+                         ema_decay=ema.get("decay") if ema.get("enabled") else None)
+    schema = synth.ToySchema(cfg, configs.N_NUM, configs.N_NUM, seed=cfg["seed"])
+    times = []
+    for s in range(warmup + steps):
+        b, y = schema.batch(sample_B, seed=1000 + s)
+        bt = {k: torch.from_numpy(v) for k, v in b.items()}
+        t0 = time.perf_counter()
+        tr.step(bt, torch.from_numpy(y))
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times)
+    return dict(value=sample_B * len(times) / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"{len(times)} steps x B={sample_B} of the same workload, seq_vocab={vocab} (covers the synthetic token "
+                       f"range; the shipped 10,000,000-row tables would add ~10 s/step of dense AdamW), dropout off, fp32, "
+                       f"torch CPU ops on {cores} threads"), dt / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, sec = cpu_reference(args.cfg, max(1, args.steps), max(0, args.warmup), sample_B=args.ref_batch)
+    cfg = build_cfg(args.cfg)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, cfg["train"]["batch_size"]), "reference_step_batch": args.ref_batch},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(cfg, B):
+    s = cfg["sequence"]
+    return (f"cfgs/{cfg['exp_name']}.yaml: B={B}/GPU, L={s['max_len']}, top_k={s['top_k']}, query={s['query_mode']}, "
+            f"{s.get('tfm', {}).get('n_layers', 0) if s['transformer_block'] else 0} encoder layers, QNN-alpha "
+            f"{'on' if cfg['model']['qnn_alpha']['enabled'] else 'off'}, seq_vocab=10,000,000 x 64 x 2 tables, fp32, dropout on, "
+            f"EMA {'on' if (cfg.get('ema') or {}).get('enabled') else 'off'}")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch.distributed as dist
+    import b200ctr
+    from b200ctr import configs, ops, synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    b200ctr._lib.check(b200ctr.load().b200ctr_check_device(), "device check")
+    cfg = build_cfg(args.cfg)
+    B = args.batch or cfg["train"]["batch_size"]
+    vocab = args.vocab
+    cols = cfg["data"]["cat_cols"]
+    torch.manual_seed(cfg["seed"])
+    with torch.device(dev):
+        model = b200ctr.CTRModel(cfg, vocab, configs.N_NUM, configs.N_NUM, configs.cardinals(cfg), cols)
+    model.train()
+    steps_per_epoch = 1000
+    trainer = b200ctr.FusedTrainer(model, cfg, steps_per_epoch=steps_per_epoch, process_group=pg)
+    schema = synth.ToySchema(cfg, configs.N_NUM, configs.N_NUM, seed=cfg["seed"])
+    NB = 4
+    host, dev_b = [], []
+    for i in range(NB):
+        b, y = schema.batch(B, seed=cfg["seed"] + 100 * rank + i)
+        hb = {k: torch.from_numpy(v).pin_memory() for k, v in b.items()}
+        hy = torch.from_numpy(y).pin_memory()
+        host.append((hb, hy))
+        dev_b.append(({k: v.to(dev) for k, v in hb.items()}, hy.to(dev)))
+    h2d = sum(v.numel() * v.element_size() for v in host[0][0].values()) + host[0][1].numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(loop_fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loop_fn(n)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def dev_loop(n):
+        for i in range(n):
+            bb, yy = dev_b[i % NB]
+            trainer.step(bb, yy)
+
+    def host_loop(n):
+        for i in range(n):
+            hb, hy = host[i % NB]
+            loss = trainer.step(hb, hy)
+            float(loss)                      # D2H read of the step's loss (train.py:202)
+
+    # ---- warm-up, then the device-resident timed region (with live per-kernel timing) ----
+    dev_loop(max(3, args.warmup))
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ops.LAUNCHES
+    ops.profile_start()
+    ms = timed(dev_loop, args.steps)
+    prof = ops.profile_stop()
+    launches = ops.LAUNCHES - l0
+    clocks = sampler.stop() if sampler else None
+    # ---- end-to-end through the public API with host batches ----
+    host_loop(2)
+    ms_e2e = timed(host_loop, args.steps)
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        pk = peaks()
+        tot_ms = sum(v[1] for v in prof.values())
+        fam = {}
+        for tag, (n, t) in prof.items():
+            f = tag.split("[")[0]
+            a = fam.setdefault(f, [0, 0.0])
+            a[0] += n; a[1] += t
+        top = sorted(fam.items(), key=lambda kv: -kv[1][1])
+        flops = 0.0
+        for tag, (n, t) in prof.items():
+            if tag.startswith("gemm["):
+                M, N, K = tag[5:-3].split("x")
+                flops += 2.0 * int(M) * int(N) * int(K) * n
+        gemm_n, gemm_ms = fam.get("gemm", [0, 0.0])
+        roof = None
+        if gemm_n:
+            ach = flops / (gemm_ms * 1e-3) / 1e12
+            roof = {"kernel": "gemm_kernel (fp32 CUDA-core contraction; every dense projection of the step)", "bound": "tensor",
+                    "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"], "traffic": None,
+                    "peak_source": f"{pk['src']} bf16 sustained", "launches": gemm_n, "avg_launch_ms": gemm_ms / gemm_n,
+                    "share_of_step": gemm_ms / tot_ms}
+        # gather kernel (north_star: gather GB/s vs HBM peak): algorithmic bytes of retrieve_fwd on these batches
+        L, Kk, D = cfg["sequence"]["max_len"], cfg["sequence"]["top_k"], 64
+        gbytes = 0.0
+        for i in range(args.steps):
+            seq = host[i % NB][0]["seq"]
+            ell = (seq != 0).sum(1).double()
+            kv = torch.clamp(ell, max=Kk)
+            gbytes += float((8 * L + 4 * D * ell + 4 * D * kv + 4 * D + 4 * D * Kk + 12 * Kk).sum())
+        gather = None
+        if "retrieve_fwd" in prof:
+            n, t = prof["retrieve_fwd"]
+            ach = gbytes / (t * 1e-3) / 1e9
+            gather = {"kernel": "retrieve_fwd_kernel", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                      "frac": ach / pk["hbm"], "frac_of_nominal_8TBs": ach / 8000.0, "traffic": None, "avg_launch_ms": t / n,
+                      "bytes_convention": "8L + 4D*l + 4D*min(K,l) + 4D + 4D*K + 12K per sample; every logical row use counted once"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(cfg, B), "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2_policy": f"{NB} distinct batches rotate; each step touches >10 GB (two 2.56 GB tables + optimizer state "
+                                    f"+ activations), far above the 126 MB L2",
+                       "seq_vocab": vocab},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": 4 * world,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "gather_roofline": gather,
+            "kernel_time_share": {k: round(v[1] / tot_ms, 4) for k, v in top[:12]},
+            "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in top[:12]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_reference(args.cfg, 2, 1, sample_B=args.ref_batch)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200ctr", choices=["b200ctr", "reference"])
+    ap.add_argument("--cfg", default="dare_qnn_next")
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug only; invalidates the headline)")
+    ap.add_argument("--vocab", type=int, default=10_000_000)
+    ap.add_argument("--ref-batch", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

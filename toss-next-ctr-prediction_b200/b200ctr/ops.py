@@ -25,6 +25,39 @@ def _count(n=1):
     LAUNCHES += n
 
 
+# ---- optional per-call device timing (bench.py: roofline of the dominant kernel, measured live) ---------------
+_PROF = None          # None = off; else {tag: [ (start_event, end_event), ... ]}
+_TAG = None           # extra tag for the next call (gemm shapes)
+
+
+def profile_start():
+    global _PROF
+    _PROF = {}
+
+
+def profile_stop():
+    """Returns {tag: (n_calls, total_ms)}; synchronises the device."""
+    global _PROF
+    prof, _PROF = _PROF, None
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (prof or {}).items()}
+
+
+def _run(what, fn, *args):
+    global _TAG
+    if _PROF is None:
+        rc = fn(*args)
+    else:
+        tag = what if _TAG is None else f"{what}{_TAG}"
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        _PROF.setdefault(tag, []).append((a, b))
+    _TAG = None
+    check(rc, what)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -91,8 +124,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, out:
     ws = None
     if split_k > 1:
         ws = torch.empty((split_k * M * N,), device=a.device, dtype=torch.float32)
-    check(lib.b200ctr_gemm(int(trans_a), int(trans_b), M, N, K, _p(a), _ld(a), _p(b), _ld(b), _p(out), _ld(out),
-                           ctypes.byref(e), split_k, _p(ws), _stream()), "gemm")
+    global _TAG
+    if _PROF is not None:
+        _TAG = f"[{M}x{N}x{K}{'T' if trans_a else 'N'}{'T' if trans_b else 'N'}]"
+    _run("gemm", lib.b200ctr_gemm, int(trans_a), int(trans_b), M, N, K, _p(a), _ld(a), _p(b), _ld(b), _p(out), _ld(out),
+                           ctypes.byref(e), split_k, _p(ws), _stream())
     _count(2 if split_k > 1 else 1)
     return out
 
@@ -103,7 +139,7 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if out is None:
         out = torch.empty((N,), device=x.device, dtype=torch.float32)
     ws = torch.empty((256 * N,), device=x.device, dtype=torch.float32)
-    check(lib.b200ctr_colsum(_p(x), _ld(x), M, N, _p(out), _p(ws), _stream()), "colsum")
+    _run("colsum", lib.b200ctr_colsum, _p(x), _ld(x), M, N, _p(out), _p(ws), _stream())
     _count(2)
     return out
 
@@ -115,7 +151,7 @@ def numbin_fold(w, b, w_out):
     D = w_out.shape[0]
     P = torch.empty((F, D), device=w.device, dtype=torch.float32)
     Q = torch.empty((F, D), device=w.device, dtype=torch.float32)
-    check(lib.b200ctr_numbin_fold(_p(w), _p(b), _p(w_out), _p(P), _p(Q), F, fe, D, _stream()), "numbin_fold")
+    _run("numbin_fold", lib.b200ctr_numbin_fold, _p(w), _p(b), _p(w_out), _p(P), _p(Q), F, fe, D, _stream())
     _count()
     return P, Q
 
@@ -125,8 +161,7 @@ def numbin_fwd(x, P, Q, out, ld_b, mean_out, ld_mean):
     lib = _lib.load()
     B, F = x.shape
     D = P.shape[1]
-    check(lib.b200ctr_numbin_fwd(_p(x), _p(P), _p(Q), _p(out), ld_b, _p(mean_out), ld_mean, B, F, D, _stream()),
-          "numbin_fwd")
+    _run("numbin_fwd", lib.b200ctr_numbin_fwd, _p(x), _p(P), _p(Q), _p(out), ld_b, _p(mean_out), ld_mean, B, F, D, _stream())
     _count()
 
 
@@ -135,8 +170,7 @@ def numbin_bwd(x, dout, ld_b, dmean, ld_dmean, D):
     B, F = x.shape
     dP = torch.empty((F, D), device=x.device, dtype=torch.float32)
     dQ = torch.empty((F, D), device=x.device, dtype=torch.float32)
-    check(lib.b200ctr_numbin_bwd(_p(x), _p(dout), ld_b, _p(dmean), ld_dmean, _p(dP), _p(dQ), B, F, D, _stream()),
-          "numbin_bwd")
+    _run("numbin_bwd", lib.b200ctr_numbin_bwd, _p(x), _p(dout), ld_b, _p(dmean), ld_dmean, _p(dP), _p(dQ), B, F, D, _stream())
     _count(3)
     return dP, dQ
 
@@ -148,8 +182,8 @@ def numbin_unfold(dP, dQ, w, b, w_out):
     dw = torch.empty_like(w)
     db = torch.empty_like(b) if b is not None else None
     dwo = torch.empty_like(w_out)
-    check(lib.b200ctr_numbin_unfold(_p(dP), _p(dQ), _p(w), _p(b), _p(w_out), _p(dw), _p(db), _p(dwo), F, fe, D,
-                                    _stream()), "numbin_unfold")
+    _run("numbin_unfold", lib.b200ctr_numbin_unfold, _p(dP), _p(dQ), _p(w), _p(b), _p(w_out), _p(dw), _p(db), _p(dwo), F, fe, D,
+                                    _stream())
     _count()
     return dw, db, dwo
 
@@ -192,9 +226,8 @@ def cat_fwd(x_cat, ct: CatTables, out, ld_b, mean_out, ld_mean, q_idx, q_out, D,
     lib = _lib.load()
     B, Fc = x_cat.shape
     assert Fc == ct.Fc and x_cat.is_contiguous()
-    check(lib.b200ctr_cat_fwd(_p(x_cat), _idx64(x_cat), _p(ct.t_ptrs), _p(ct.p_ptrs), _p(ct.dims), _p(ct.cards),
-                              _p(out), ld_b, _p(mean_out), ld_mean, q_idx, _p(q_out), B, Fc, D, dropout, _stream()),
-          "cat_fwd")
+    _run("cat_fwd", lib.b200ctr_cat_fwd, _p(x_cat), _idx64(x_cat), _p(ct.t_ptrs), _p(ct.p_ptrs), _p(ct.dims), _p(ct.cards),
+                              _p(out), ld_b, _p(mean_out), ld_mean, q_idx, _p(q_out), B, Fc, D, dropout, _stream())
     _count()
 
 
@@ -203,9 +236,9 @@ def cat_bwd(x_cat, ct: CatTables, dout, ld_b, dmean, ld_dmean, q_idx, dq, dtable
     lib = _lib.load()
     B, Fc = x_cat.shape
     dt_ptrs, dp_ptrs = _ptr_table(dtables), _ptr_table(dprojs)
-    check(lib.b200ctr_cat_bwd(_p(x_cat), _idx64(x_cat), _p(ct.t_ptrs), _p(ct.p_ptrs), _p(ct.dims), _p(ct.cards),
+    _run("cat_bwd", lib.b200ctr_cat_bwd, _p(x_cat), _idx64(x_cat), _p(ct.t_ptrs), _p(ct.p_ptrs), _p(ct.dims), _p(ct.cards),
                               _p(dout), ld_b, _p(dmean), ld_dmean, q_idx, _p(dq), _p(dt_ptrs), _p(dp_ptrs),
-                              B, Fc, D, dropout, _stream()), "cat_bwd")
+                              B, Fc, D, dropout, _stream())
     _count()
 
 
@@ -214,7 +247,7 @@ def axpby(x, y, a, b, out=None):
     ref = x if x is not None else y
     if out is None:
         out = torch.empty_like(ref)
-    check(lib.b200ctr_axpby(_p(x), _p(y), a, b, _p(out), ref.numel(), _stream()), "axpby")
+    _run("axpby", lib.b200ctr_axpby, _p(x), _p(y), a, b, _p(out), ref.numel(), _stream())
     _count()
     return out
 
@@ -222,7 +255,7 @@ def axpby(x, y, a, b, out=None):
 def relu_bwd(dy, y, scale=1.0):
     lib = _lib.load()
     out = torch.empty_like(dy)
-    check(lib.b200ctr_relu_bwd(_p(dy), _p(y), float(scale), _p(out), dy.numel(), _stream()), "relu_bwd")
+    _run("relu_bwd", lib.b200ctr_relu_bwd, _p(dy), _p(y), float(scale), _p(out), dy.numel(), _stream())
     _count()
     return out
 
@@ -230,7 +263,7 @@ def relu_bwd(dy, y, scale=1.0):
 def sigmoid(x):
     lib = _lib.load()
     out = torch.empty_like(x)
-    check(lib.b200ctr_sigmoid(_p(x), _p(out), x.numel(), _stream()), "sigmoid")
+    _run("sigmoid", lib.b200ctr_sigmoid, _p(x), _p(out), x.numel(), _stream())
     _count()
     return out
 
@@ -239,7 +272,7 @@ def add2d_(dst, src):
     """dst += src for 2-D row-strided views of equal shape."""
     lib = _lib.load()
     assert dst.shape == src.shape
-    check(lib.b200ctr_add2d(_p(dst), _ld(dst), _p(src), _ld(src), dst.shape[0], dst.shape[1], _stream()), "add2d")
+    _run("add2d", lib.b200ctr_add2d, _p(dst), _ld(dst), _p(src), _ld(src), dst.shape[0], dst.shape[1], _stream())
     _count()
     return dst
 
@@ -255,8 +288,8 @@ def retrieve_fwd(seq, q, emb_att, emb_rep, rec, K, pad_id):
     vals = torch.empty((B, K), device=dev, dtype=torch.float32)
     idx = torch.empty((B, K), device=dev, dtype=torch.int32)
     tok = torch.empty((B, K), device=dev, dtype=torch.int32)
-    check(lib.b200ctr_retrieve_fwd(_p(seq), _idx64(seq), _p(q), _p(emb_att), _p(emb_rep), _p(rec), B, L, K, D, pad_id,
-                                   emb_att.shape[0], _p(sel), _p(vals), _p(idx), _p(tok), _stream()), "retrieve_fwd")
+    _run("retrieve_fwd", lib.b200ctr_retrieve_fwd, _p(seq), _idx64(seq), _p(q), _p(emb_att), _p(emb_rep), _p(rec), B, L, K, D, pad_id,
+                                   emb_att.shape[0], _p(sel), _p(vals), _p(idx), _p(tok), _stream())
     _count()
     return sel, vals, idx, tok
 
@@ -266,8 +299,8 @@ def retrieve_bwd(tok, q, emb_att, dsel_rep, dvals, pad_id, datt_dense=None, drep
     B, K = tok.shape
     D = q.shape[1]
     dq = torch.empty_like(q)
-    check(lib.b200ctr_retrieve_bwd(_p(tok), _p(q), _p(emb_att), _p(dsel_rep), _p(dvals), B, K, D, pad_id, _p(dq),
-                                   _p(datt_dense), _p(drep_dense), _stream()), "retrieve_bwd")
+    _run("retrieve_bwd", lib.b200ctr_retrieve_bwd, _p(tok), _p(q), _p(emb_att), _p(dsel_rep), _p(dvals), B, K, D, pad_id, _p(dq),
+                                   _p(datt_dense), _p(drep_dense), _stream())
     _count()
     return dq
 
@@ -276,7 +309,7 @@ def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP):
     lib = _lib.load()
     o = torch.empty((B * K, D), device=qkv.device, dtype=torch.float32)
     lse = torch.empty((B, H, K), device=qkv.device, dtype=torch.float32)
-    check(lib.b200ctr_attn_fwd(_p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), dropout, _stream()), "attn_fwd")
+    _run("attn_fwd", lib.b200ctr_attn_fwd, _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), dropout, _stream())
     _count()
     return o, lse
 
@@ -284,8 +317,8 @@ def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP):
 def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=NO_DROP):
     lib = _lib.load()
     dqkv = torch.empty_like(qkv)
-    check(lib.b200ctr_attn_bwd(_p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv), _p(drelmean),
-                               dropout, _stream()), "attn_bwd")
+    _run("attn_bwd", lib.b200ctr_attn_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv), _p(drelmean),
+                               dropout, _stream())
     _count()
     return dqkv
 
@@ -296,7 +329,7 @@ def add_rmsnorm_fwd(a, b, w, eps=1e-6, save_sum=True):
     s = torch.empty_like(a) if save_sum else None
     y = torch.empty_like(a)
     r = torch.empty((M,), device=a.device, dtype=torch.float32)
-    check(lib.b200ctr_add_rmsnorm_fwd(_p(a), _p(b), _p(w), eps, M, D, _p(s), _p(y), _p(r), _stream()), "add_rmsnorm_fwd")
+    _run("add_rmsnorm_fwd", lib.b200ctr_add_rmsnorm_fwd, _p(a), _p(b), _p(w), eps, M, D, _p(s), _p(y), _p(r), _stream())
     _count()
     return s, y, r
 
@@ -306,7 +339,7 @@ def rmsnorm_bwd(dy, s, w, r, dw, dx_add=None):
     lib = _lib.load()
     M, D = dy.shape
     dx = torch.empty_like(dy)
-    check(lib.b200ctr_rmsnorm_bwd(_p(dy), _p(s), _p(w), _p(r), M, D, _p(dx_add), _p(dx), _p(dw), _stream()), "rmsnorm_bwd")
+    _run("rmsnorm_bwd", lib.b200ctr_rmsnorm_bwd, _p(dy), _p(s), _p(w), _p(r), M, D, _p(dx_add), _p(dx), _p(dw), _stream())
     _count()
     return dx
 
@@ -315,7 +348,7 @@ def relmean_fwd(rel):
     lib = _lib.load()
     T, H = rel.shape
     out = torch.empty((T,), device=rel.device, dtype=torch.float32)
-    check(lib.b200ctr_relmean_fwd(_p(rel), T, H, _p(out), _stream()), "relmean_fwd")
+    _run("relmean_fwd", lib.b200ctr_relmean_fwd, _p(rel), T, H, _p(out), _stream())
     _count()
     return out
 
@@ -324,7 +357,7 @@ def relmean_bwd(drelmean, H):
     lib = _lib.load()
     T = drelmean.shape[0]
     out = torch.empty((T, H), device=drelmean.device, dtype=torch.float32)
-    check(lib.b200ctr_relmean_bwd(_p(drelmean), T, H, _p(out), _stream()), "relmean_bwd")
+    _run("relmean_bwd", lib.b200ctr_relmean_bwd, _p(drelmean), T, H, _p(out), _stream())
     _count()
     return out
 
@@ -334,8 +367,8 @@ def pool_fwd(x, vals, aux_w, aux_b, gating_relu, u, ld_u, dropout=NO_DROP):
     B, K, D = x.shape
     aux = torch.empty((B,), device=x.device, dtype=torch.float32)
     w = torch.empty((B, K), device=x.device, dtype=torch.float32)
-    check(lib.b200ctr_pool_fwd(_p(x), _p(vals), _p(aux_w), _p(aux_b), int(gating_relu), B, K, D, _p(u), ld_u, _p(aux), _p(w),
-                               dropout, _stream()), "pool_fwd")
+    _run("pool_fwd", lib.b200ctr_pool_fwd, _p(x), _p(vals), _p(aux_w), _p(aux_b), int(gating_relu), B, K, D, _p(u), ld_u, _p(aux), _p(w),
+                               dropout, _stream())
     _count()
     return aux, w
 
@@ -345,8 +378,8 @@ def pool_bwd(x, vals, w, aux_w, u, ld_u, du, ld_du, daux, gating_relu, daux_w, d
     B, K, D = x.shape
     dx = torch.empty_like(x)
     dvals = torch.empty_like(vals)
-    check(lib.b200ctr_pool_bwd(_p(x), _p(vals), _p(w), _p(aux_w), _p(u), ld_u, _p(du), ld_du, _p(daux), int(gating_relu),
-                               B, K, D, _p(dx), _p(dvals), _p(daux_w), _p(daux_b), dropout, _stream()), "pool_bwd")
+    _run("pool_bwd", lib.b200ctr_pool_bwd, _p(x), _p(vals), _p(w), _p(aux_w), _p(u), ld_u, _p(du), ld_du, _p(daux), int(gating_relu),
+                               B, K, D, _p(dx), _p(dvals), _p(daux_w), _p(daux_b), dropout, _stream())
     _count()
     return dx, dvals
 
@@ -357,7 +390,7 @@ def rowrms_fwd(x, w, eps=1e-6):
     B, N = x.shape
     z = torch.empty((B, N), device=x.device, dtype=torch.float32)
     r = torch.empty((B,), device=x.device, dtype=torch.float32)
-    check(lib.b200ctr_rowrms_fwd(_p(x), _ld(x), _p(w), eps, B, N, _p(z), N, _p(r), _stream()), "rowrms_fwd")
+    _run("rowrms_fwd", lib.b200ctr_rowrms_fwd, _p(x), _ld(x), _p(w), eps, B, N, _p(z), N, _p(r), _stream())
     _count()
     return z, r
 
@@ -368,8 +401,8 @@ def rowrms_bwd(dz, x, w, r, n_partials=296):
     n_partials = max(1, min(n_partials, B))
     dx = torch.empty((B, N), device=x.device, dtype=torch.float32)
     part = torch.empty((n_partials, N), device=x.device, dtype=torch.float32)
-    check(lib.b200ctr_rowrms_bwd(_p(dz), _ld(dz), _p(x), _ld(x), _p(w), _p(r), B, N, _p(dx), N, _p(part), n_partials,
-                                 _stream()), "rowrms_bwd")
+    _run("rowrms_bwd", lib.b200ctr_rowrms_bwd, _p(dz), _ld(dz), _p(x), _ld(x), _p(w), _p(r), B, N, _p(dx), N, _p(part), n_partials,
+                                 _stream())
     _count()
     return dx, colsum(part)
 
@@ -378,14 +411,14 @@ def fm_reduce(A, B, F, C):
     lib = _lib.load()
     s = torch.empty((B, C), device=A.device, dtype=torch.float32)
     quad = torch.empty((B, C), device=A.device, dtype=torch.float32)
-    check(lib.b200ctr_fm_reduce(_p(A), B, F, C, _p(s), _p(quad), _stream()), "fm_reduce")
+    _run("fm_reduce", lib.b200ctr_fm_reduce, _p(A), B, F, C, _p(s), _p(quad), _stream())
     _count()
     return s, quad
 
 
 def fm_grad_(A, s, dquad, B, F, C):
     lib = _lib.load()
-    check(lib.b200ctr_fm_grad(_p(A), _p(s), _p(dquad), B, F, C, _stream()), "fm_grad")
+    _run("fm_grad", lib.b200ctr_fm_grad, _p(A), _p(s), _p(dquad), B, F, C, _stream())
     _count()
     return A
 
@@ -396,8 +429,8 @@ def se_gate_fwd(csum, B, w1, b1, w2, b2):
     mean = torch.empty((C,), device=csum.device, dtype=torch.float32)
     h1 = torch.empty((Cr,), device=csum.device, dtype=torch.float32)
     gate = torch.empty((C,), device=csum.device, dtype=torch.float32)
-    check(lib.b200ctr_se_gate_fwd(_p(csum), 1.0 / B, _p(w1), _p(b1), _p(w2), _p(b2), C, Cr, _p(mean), _p(h1), _p(gate),
-                                  _stream()), "se_gate_fwd")
+    _run("se_gate_fwd", lib.b200ctr_se_gate_fwd, _p(csum), 1.0 / B, _p(w1), _p(b1), _p(w2), _p(b2), C, Cr, _p(mean), _p(h1), _p(gate),
+                                  _stream())
     _count()
     return mean, h1, gate
 
@@ -409,8 +442,8 @@ def se_gate_bwd(dgate, mean, h1, gate, w1, w2):
     db1 = torch.empty((Cr,), device=w1.device, dtype=torch.float32)
     db2 = torch.empty((C,), device=w1.device, dtype=torch.float32)
     dmean = torch.empty((C,), device=w1.device, dtype=torch.float32)
-    check(lib.b200ctr_se_gate_bwd(_p(dgate), _p(mean), _p(h1), _p(gate), _p(w1), _p(w2), C, Cr, _p(dw1), _p(db1), _p(dw2),
-                                  _p(db2), _p(dmean), _stream()), "se_gate_bwd")
+    _run("se_gate_bwd", lib.b200ctr_se_gate_bwd, _p(dgate), _p(mean), _p(h1), _p(gate), _p(w1), _p(w2), C, Cr, _p(dw1), _p(db1), _p(dw2),
+                                  _p(db2), _p(dmean), _stream())
     _count()
     return dw1, db1, dw2, db2, dmean
 
@@ -419,7 +452,7 @@ def se_apply_fwd(inter, gate, dropout=NO_DROP):
     lib = _lib.load()
     B, C = inter.shape
     out = torch.empty_like(inter)
-    check(lib.b200ctr_se_apply_fwd(_p(inter), _p(gate), B, C, _p(out), C, dropout, _stream()), "se_apply_fwd")
+    _run("se_apply_fwd", lib.b200ctr_se_apply_fwd, _p(inter), _p(gate), B, C, _p(out), C, dropout, _stream())
     _count()
     return out
 
@@ -429,8 +462,8 @@ def se_apply_bwd(dout, inter, gate, dmean, B_total, want_dinter, want_gprod, dro
     B, C = inter.shape
     dinter = torch.empty_like(inter) if want_dinter else None
     gprod = torch.empty_like(inter) if want_gprod else None
-    check(lib.b200ctr_se_apply_bwd(_p(dout), _ld(dout), _p(inter), _p(gate), _p(dmean), 1.0 / B_total, B, C, _p(dinter),
-                                   _p(gprod), dropout, _stream()), "se_apply_bwd")
+    _run("se_apply_bwd", lib.b200ctr_se_apply_bwd, _p(dout), _ld(dout), _p(inter), _p(gate), _p(dmean), 1.0 / B_total, B, C, _p(dinter),
+                                   _p(gprod), dropout, _stream())
     _count()
     return dinter, gprod
 
@@ -445,48 +478,47 @@ def bce_wll(logits, aux, y, aux_w, counts_override=None, want_prob=True):
     dz = torch.empty_like(logits)
     da = torch.empty_like(logits) if aux is not None else None
     prob = torch.empty_like(logits) if want_prob else None
-    check(lib.b200ctr_bce_wll(_p(logits), _p(aux), _p(y), float(aux_w), B, _p(counts_override), _p(loss), _p(counts),
-                              _p(dz), _p(da), _p(prob), _stream()), "bce_wll")
+    _run("bce_wll", lib.b200ctr_bce_wll, _p(logits), _p(aux), _p(y), float(aux_w), B, _p(counts_override), _p(loss), _p(counts),
+                              _p(dz), _p(da), _p(prob), _stream())
     _count()
     return loss, dz, da, prob, counts
 
 
 def sqnorm_(x, acc):
     lib = _lib.load()
-    check(lib.b200ctr_sqnorm(_p(x), x.numel(), _p(acc), _stream()), "sqnorm")
+    _run("sqnorm", lib.b200ctr_sqnorm, _p(x), x.numel(), _p(acc), _stream())
     _count()
 
 
 def clip_coef(acc, max_norm, coef, total_norm=None):
     lib = _lib.load()
-    check(lib.b200ctr_clip_coef(_p(acc), float(max_norm), _p(coef), _p(total_norm), _stream()), "clip_coef")
+    _run("clip_coef", lib.b200ctr_clip_coef, _p(acc), float(max_norm), _p(coef), _p(total_norm), _stream())
     _count()
 
 
 def adamw_ema_(p, g, m, v, ema, lr, wd, step, coef, ema_decay, beta1=0.9, beta2=0.999, eps=1e-8):
     lib = _lib.load()
-    check(lib.b200ctr_adamw_ema(_p(p), _p(g), _p(m), _p(v), _p(ema), p.numel(), lr, wd, beta1, beta2, eps, step, _p(coef),
-                                ema_decay, _stream()), "adamw_ema")
+    _run("adamw_ema", lib.b200ctr_adamw_ema, _p(p), _p(g), _p(m), _p(v), _p(ema), p.numel(), lr, wd, beta1, beta2, eps, step, _p(coef),
+                                ema_decay, _stream())
     _count()
 
 
 def rows_claim(tok, pad_id, owner):
     lib = _lib.load()
-    check(lib.b200ctr_rows_claim(_p(tok), tok.numel(), pad_id, _p(owner), _stream()), "rows_claim")
+    _run("rows_claim", lib.b200ctr_rows_claim, _p(tok), tok.numel(), pad_id, _p(owner), _stream())
     _count()
 
 
 def rows_sqnorm(tok, pad_id, owner, g_dense, acc):
     lib = _lib.load()
-    check(lib.b200ctr_rows_sqnorm(_p(tok), tok.numel(), pad_id, _p(owner), _p(g_dense), g_dense.shape[1], _p(acc),
-                                  _stream()), "rows_sqnorm")
+    _run("rows_sqnorm", lib.b200ctr_rows_sqnorm, _p(tok), tok.numel(), pad_id, _p(owner), _p(g_dense), g_dense.shape[1], _p(acc),
+                                  _stream())
     _count()
 
 
 def rows_zero(tok, pad_id, owner, g_dense):
     lib = _lib.load()
-    check(lib.b200ctr_rows_zero(_p(tok), tok.numel(), pad_id, _p(owner), _p(g_dense), g_dense.shape[1], _stream()),
-          "rows_zero")
+    _run("rows_zero", lib.b200ctr_rows_zero, _p(tok), tok.numel(), pad_id, _p(owner), _p(g_dense), g_dense.shape[1], _stream())
     _count()
 
 
@@ -494,6 +526,6 @@ def logit_mean(probs, eps=1e-7):
     lib = _lib.load()
     M, B = probs.shape
     out = torch.empty((B,), device=probs.device, dtype=torch.float32)
-    check(lib.b200ctr_logit_mean(_p(probs), M, B, eps, _p(out), _stream()), "logit_mean")
+    _run("logit_mean", lib.b200ctr_logit_mean, _p(probs), M, B, eps, _p(out), _stream())
     _count()
     return out

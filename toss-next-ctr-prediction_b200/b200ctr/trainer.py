@@ -166,6 +166,8 @@ class FusedTrainer:
         """batch: collate_sharded dict (CPU pinned or device tensors).  Returns the loss as a 1-element device
         tensor (no host sync; the caller decides when to read it)."""
         spec = self.spec
+        if not spec.use_qnn:
+            spec.p_fc = float(self.model.fc[2].p)
         self.global_step += 1
         lr = self.lr_at(self.global_step) if lr is None else lr
         dbatch, yd = self.to_device(batch, y)
