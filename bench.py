@@ -192,7 +192,8 @@ def workload_name(cfg, B):
     s = cfg["sequence"]
     return (f"cfgs/{cfg['exp_name']}.yaml: B={B}/GPU, L={s['max_len']}, top_k={s['top_k']}, query={s['query_mode']}, "
             f"{s.get('tfm', {}).get('n_layers', 0) if s['transformer_block'] else 0} encoder layers, QNN-alpha "
-            f"{'on' if cfg['model']['qnn_alpha']['enabled'] else 'off'}, seq_vocab=10,000,000 x 64 x 2 tables, fp32, dropout on, "
+            f"{'on' if cfg['model']['qnn_alpha']['enabled'] else 'off'}, seq_vocab=10,000,000 x 64 x 2 tables, "
+            f"amp={cfg.get('amp', 'none')} (fp32 master weights + optimizer), dropout on, "
             f"EMA {'on' if (cfg.get('ema') or {}).get('enabled') else 'off'}")
 
 
@@ -216,6 +217,7 @@ def run_cuda(args):
         pg = dist.group.WORLD
     b200ctr._lib.check(b200ctr.load().b200ctr_check_device(), "device check")
     cfg = build_cfg(args.cfg)
+    cfg["amp"] = args.amp
     B = args.batch or cfg["train"]["batch_size"]
     vocab = args.vocab
     cols = cfg["data"]["cat_cols"]
@@ -289,16 +291,20 @@ def run_cuda(args):
             a = fam.setdefault(f, [0, 0.0])
             a[0] += n; a[1] += t
         top = sorted(fam.items(), key=lambda kv: -kv[1][1])
-        flops = 0.0
+        flops = {"gemm": 0.0, "gemm_bf16": 0.0}
         for tag, (n, t) in prof.items():
-            if tag.startswith("gemm["):
-                M, N, K = tag[5:-3].split("x")
-                flops += 2.0 * int(M) * int(N) * int(K) * n
-        gemm_n, gemm_ms = fam.get("gemm", [0, 0.0])
+            for famname in flops:
+                if tag.startswith(famname + "["):
+                    M, N, K = tag[len(famname) + 1:-3].split("x")
+                    flops[famname] += 2.0 * int(M) * int(N) * int(K) * n
         roof = None
+        famname = "gemm_bf16" if fam.get("gemm_bf16", [0, 0.0])[1] >= fam.get("gemm", [0, 0.0])[1] else "gemm"
+        gemm_n, gemm_ms = fam.get(famname, [0, 0.0])
         if gemm_n:
-            ach = flops / (gemm_ms * 1e-3) / 1e12
-            roof = {"kernel": "gemm_kernel (fp32 CUDA-core contraction; every dense projection of the step)", "bound": "tensor",
+            ach = flops[famname] / (gemm_ms * 1e-3) / 1e12
+            kname = ("gemm_tc_kernel (tcgen05.mma kind::f16, bf16 operands converted on load, fp32 TMEM accumulators)"
+                     if famname == "gemm_bf16" else "gemm_kernel (fp32 CUDA-core contraction)")
+            roof = {"kernel": kname + "; every dense projection of the step", "bound": "tensor",
                     "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"], "traffic": None,
                     "peak_source": f"{pk['src']} bf16 sustained", "launches": gemm_n, "avg_launch_ms": gemm_ms / gemm_n,
                     "share_of_step": gemm_ms / tot_ms}
@@ -319,8 +325,8 @@ def run_cuda(args):
                       "bytes_convention": "8L + 4D*l + 4D*min(K,l) + 4D + 4D*K + 12K per sample; every logical row use counted once"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
-            "data": "synthetic",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.amp == "bf16" else "fp32", "data": "synthetic",
             "config": {"workload": workload_name(cfg, B), "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2_policy": f"{NB} distinct batches rotate; each step touches >10 GB (two 2.56 GB tables + optimizer state "
                                     f"+ activations), far above the 126 MB L2",
@@ -333,6 +339,9 @@ def run_cuda(args):
             "gather_roofline": gather,
             "kernel_time_share": {k: round(v[1] / tot_ms, 4) for k, v in top[:12]},
             "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in top[:12]},
+            "gemm_shapes_ms_per_step": {k: [v[0] // args.steps, round(v[1] / args.steps, 4)] for k, v in
+                                        sorted(((t, v) for t, v in prof.items() if t.startswith("gemm")),
+                                               key=lambda kv: -kv[1][1])[:16]},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference(args.cfg, 2, 1, sample_B=args.ref_batch)
@@ -353,6 +362,9 @@ def main():
     ap.add_argument("--vocab", type=int, default=10_000_000)
     ap.add_argument("--ref-batch", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--amp", default="bf16", choices=["none", "bf16"],
+                    help="matmul precision of the training step: bf16 = the reference's `amp: bf16` autocast mode on the "
+                         "tcgen05 tensor cores (fp32 accumulate, fp32 master weights/optimizer); none = exact fp32 CUDA cores")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

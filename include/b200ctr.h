@@ -89,6 +89,12 @@ int64_t b200ctr_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int split_
 int b200ctr_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K,
                  const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                  const b200ctr_epilogue_t* epi_host, int split_k, void* workspace, void* stream);
+/* Same contract as b200ctr_gemm, computed on the tcgen05 tensor cores: operands are rounded to bf16 on their way
+ * into shared memory (the reference's `amp: bf16` autocast semantics for matmul / linear), accumulation and the
+ * epilogue are fp32, inputs and outputs stay fp32 in HBM.  transA && transB is not built.                        */
+int b200ctr_gemm_bf16(int transA, int transB, int64_t M, int64_t N, int64_t K,
+                      const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                      const b200ctr_epilogue_t* epi_host, int split_k, void* workspace, void* stream);
 /* out[n] = sum_m X[m,n]  (bias gradients; deterministic two-pass).  workspace >= 4*N*256 bytes. */
 int b200ctr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* workspace, void* stream);
 

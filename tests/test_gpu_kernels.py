@@ -84,7 +84,7 @@ def test_gemm_dropout_is_regenerable_and_unbiased(dev):
     a = torch.ones(M, K, device=dev)
     w = torch.ones(N, K, device=dev) / K
     d = ops.drop(0.25, 1234567, 77)
-    o1 = ops.gemm(a, w, trans_b=True, dropout=d)
+    o1 = ops.gemm(a, w, trans_b=True, dropout=d, tc=True)
     o2 = ops.gemm(a, w, trans_b=True, dropout=d)
     assert torch.equal(o1, o2)                                   # stateless: backward regenerates the same mask
     vals = torch.unique(o1)
@@ -228,3 +228,47 @@ def test_logit_mean_vs_reference_formula(dev):
     Pc = torch.clamp(P, 1e-7, 1 - 1e-7)                                   # fp32, exactly as utils/metrics.py:31-33
     ref = torch.sigmoid((torch.log(Pc) - torch.log1p(-Pc)).mean(0))      # utils/metrics.py:68-71
     assert torch.allclose(ops.logit_mean(P.to(dev)).cpu(), ref, atol=1e-5)
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).double()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 70, 129), (1000, 96, 64), (257, 192, 100), (4096, 384, 64),
+                                   (512, 512, 1024), (130, 1152, 96), (64, 200, 4096)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False)])
+def test_gemm_bf16_tensor_core_all_layouts(dev, M, N, K, ta, tb):
+    """tcgen05 path: operands rounded to bf16, fp32 accumulation => equals the fp64 product of the bf16-rounded
+    operands to fp32 accumulation accuracy (a layout / descriptor error would show up as O(1) differences)."""
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    a = _rand(g, K, M) if ta else _rand(g, M, K)
+    b = _rand(g, N, K) if tb else _rand(g, K, N)
+    ref = (_bf16_round(a).t() if ta else _bf16_round(a)) @ (_bf16_round(b).t() if tb else _bf16_round(b))
+    with ops.precision("bf16"):
+        out = ops.gemm(a.to(dev), b.to(dev), trans_a=ta, trans_b=tb, tc=True)
+        out_sk = ops.gemm(a.to(dev), b.to(dev), trans_a=ta, trans_b=tb, split_k=3, tc=True)
+    assert max_err_scaled(out.cpu(), ref) < 2e-5
+    assert max_err_scaled(out_sk.cpu(), ref) < 2e-5
+    # and stays within bf16 rounding of the exact fp32 product
+    exact = (a.t() if ta else a).double() @ (b.t() if tb else b).double()
+    assert max_err_scaled(out.cpu(), exact) < 2e-2
+
+
+def test_gemm_bf16_epilogue_and_strided_views(dev):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(21)
+    M, N, K = 700, 192, 128
+    big = _rand(g, M, 3 * K).to(dev)
+    a = big[:, K:2 * K]
+    w, bias, res = _rand(g, N, K).to(dev), _rand(g, N).to(dev), _rand(g, M, N).to(dev)
+    lin = _bf16_round(a.cpu()) @ _bf16_round(w.cpu()).t()
+    with ops.precision("bf16"):
+        pre = torch.empty(M, N, device=dev)
+        out = ops.gemm(a, w, trans_b=True, bias=bias, act=ops.ACT_GELU, pre_out=pre, residual=res, tc=True)
+        assert max_err_scaled(pre.cpu(), lin + bias.cpu().double()) < 2e-5
+        assert max_err_scaled(out.cpu(), O.gelu_fwd(lin + bias.cpu().double()) + res.cpu().double()) < 2e-5
+        d = ops.drop(0.3, 99, 5)
+        o1 = ops.gemm(a, w, trans_b=True, dropout=d, tc=True)
+    o2 = ops.gemm(a, w, trans_b=True, dropout=d)             # fp32 path: same mask (same element ids)
+    assert torch.equal(o1 == 0, o2 == 0)

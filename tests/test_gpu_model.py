@@ -177,3 +177,28 @@ def test_no_cpu_fallback():
     batch, _ = batch_of(z, 0)
     with pytest.raises(b200ctr.B200CtrError):
         m(batch)
+
+
+def test_bf16_amp_mode_tracks_fp32():
+    """amp: bf16 (tcgen05 contractions) vs exact fp32 on the same model/batch: logits and gradients agree to bf16
+    rounding (stated tolerance: 3e-2 / 5e-2 of the tensor's max-abs; the top-k selection is fp32 in both)."""
+    from b200ctr import ops
+    dev = torch.device("cuda:0")
+    z, cfg = load_case("qnn_concat")
+    outs = {}
+    for mode in ("fp32", "bf16"):
+        m = _build(cfg, z, dev).train()
+        batch, y = batch_of(z, 0)
+        with ops.precision(mode):
+            logits, prob, aux = m(batch)
+            loss, dz, da, _, _ = ops.bce_wll(logits.detach(), aux.detach(), y.to(dev), m.aux_weight)
+            torch.autograd.backward([logits, aux], [dz, da])
+        outs[mode] = (logits.detach().cpu(), {n: p.grad.cpu() for n, p in m.named_parameters() if p.grad is not None})
+    assert max_err_scaled(outs["bf16"][0], outs["fp32"][0]) < 3e-2
+    for n, g in outs["fp32"][1].items():
+        assert max_err_scaled(outs["bf16"][1][n], g) < 5e-2, n
+    # and autocast selects the tensor-core path exactly like the reference's train loop would
+    m = _build(cfg, z, dev).train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        l2, _, _ = m(batch)
+    assert l2.dtype == torch.float32 and max_err_scaled(l2.detach().cpu(), outs["bf16"][0]) < 1e-6

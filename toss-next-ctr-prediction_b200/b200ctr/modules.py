@@ -182,11 +182,16 @@ class _StageFn(torch.autograd.Function):
     def forward(ctx, holder, *tensors):
         ctx.set_materialize_grads(False)
         ctx.holder = holder
+        # the reference's train loop wraps forward+loss in torch autocast when cfg.amp is bf16/fp16 (train.py:158-161):
+        # under autocast the contractions run on the tensor cores with bf16 operands; validation/inference run
+        # outside autocast and stay exact fp32.  The backward pass reuses the forward's mode.
+        ctx.prec = "bf16" if torch.is_autocast_enabled() else ops.get_precision()
         names = holder["names"]
         n_in = holder["n_inputs"]
         inputs = tensors[:n_in]
         P = dict(zip(names, tensors[n_in:]))
-        outs, sv = holder["fwd"](P, inputs)
+        with ops.precision(ctx.prec):
+            outs, sv = holder["fwd"](P, inputs)
         ctx.P, ctx.sv = P, sv
         ctx.n_in = n_in
         nd = holder.get("non_diff", ())
@@ -198,7 +203,8 @@ class _StageFn(torch.autograd.Function):
     def backward(ctx, *douts):
         holder = ctx.holder
         G = _GradStore(ctx.P)
-        dins = holder["bwd"](ctx.P, ctx.sv, douts, G)
+        with ops.precision(ctx.prec):
+            dins = holder["bwd"](ctx.P, ctx.sv, [d.float() if d is not None else None for d in douts], G)
         grads = [G.grads.get(n) for n in holder["names"]]
         dins = list(dins) + [None] * (ctx.n_in - len(dins))
         ctx.sv = None

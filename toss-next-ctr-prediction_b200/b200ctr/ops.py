@@ -88,6 +88,35 @@ def drop(p: float, seed: int, stream_id: int) -> Dropout:
     return Dropout(float(p), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, stream_id & 0xFFFFFFFF)
 
 
+# ---- matmul precision -------------------------------------------------------------------------------------------
+# "fp32": CUDA-core contraction, exact fp32 (the reference's default `amp: none`, TF32 off).
+# "bf16": tcgen05 tensor-core contraction with bf16 operands / fp32 accumulation (the reference's `amp: bf16` autocast).
+_PRECISION = "fp32"
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+class precision:
+    """Context manager: `with ops.precision("bf16"): ...`"""
+
+    def __init__(self, mode: str):
+        if mode not in ("fp32", "bf16"):
+            raise ValueError(f"unknown matmul precision {mode!r}")
+        self.mode = mode
+
+    def __enter__(self):
+        global _PRECISION
+        self.prev, _PRECISION = _PRECISION, self.mode
+        return self
+
+    def __exit__(self, *exc):
+        global _PRECISION
+        _PRECISION = self.prev
+        return False
+
+
 def _split_k_for(M: int, N: int, K: int) -> int:
     bn = 128 if N > 64 else 64
     tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
@@ -98,7 +127,8 @@ def _split_k_for(M: int, N: int, K: int) -> int:
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, out: Optional[torch.Tensor] = None,
          bias=None, act=ACT_NONE, pre_out=None, dropout: Dropout = NO_DROP, mask_mode=MASK_NONE, mask_src=None,
-         mask_scale=1.0, residual=None, accum=None, alpha=1.0, split_k: Optional[int] = None) -> torch.Tensor:
+         mask_scale=1.0, residual=None, accum=None, alpha=1.0, split_k: Optional[int] = None,
+         tc: Optional[bool] = None) -> torch.Tensor:
     """out[M,N] = epilogue(alpha * op(a) @ op(b)); see include/b200ctr.h:b200ctr_gemm."""
     lib = _lib.load()
     _f32(a, "a"); _f32(b, "b")
@@ -125,9 +155,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, out:
     if split_k > 1:
         ws = torch.empty((split_k * M * N,), device=a.device, dtype=torch.float32)
     global _TAG
+    if tc is None:      # tiny contractions are not worth a TMEM allocation; transA && transB is not built
+        use_tc = (_PRECISION == "bf16") and not (trans_a and trans_b) and (M * N * K >= (1 << 20)) and K >= 32
+    else:
+        use_tc = bool(tc)
     if _PROF is not None:
         _TAG = f"[{M}x{N}x{K}{'T' if trans_a else 'N'}{'T' if trans_b else 'N'}]"
-    _run("gemm", lib.b200ctr_gemm, int(trans_a), int(trans_b), M, N, K, _p(a), _ld(a), _p(b), _ld(b), _p(out), _ld(out),
+    _run("gemm_bf16" if use_tc else "gemm", lib.b200ctr_gemm_bf16 if use_tc else lib.b200ctr_gemm, int(trans_a), int(trans_b), M, N, K, _p(a), _ld(a), _p(b), _ld(b), _p(out), _ld(out),
                            ctypes.byref(e), split_k, _p(ws), _stream())
     _count(2 if split_k > 1 else 1)
     return out

@@ -80,6 +80,10 @@ class FusedTrainer:
         self.ema_decay = float(ema.get("decay", 0.999))
         self.ema_warm, self.ema_type = int(ema.get("warmup_steps", 0)), str(ema.get("warmup_type", "linear"))
         self.seed = int(cfg.get("seed", 0) if seed is None else seed)
+        amp = str(cfg.get("amp", "none")).lower()
+        if amp not in ("none", "bf16"):
+            raise ValueError("FusedTrainer supports amp: none (fp32) and amp: bf16; fp16 + GradScaler is not built")
+        self.prec = "bf16" if amp == "bf16" else "fp32"
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         params = dict(model.named_parameters())
@@ -165,6 +169,10 @@ class FusedTrainer:
     def step(self, batch: Dict[str, torch.Tensor], y: torch.Tensor, lr: Optional[float] = None) -> torch.Tensor:
         """batch: collate_sharded dict (CPU pinned or device tensors).  Returns the loss as a 1-element device
         tensor (no host sync; the caller decides when to read it)."""
+        with ops.precision(self.prec):
+            return self._step(batch, y, lr)
+
+    def _step(self, batch, y, lr):
         spec = self.spec
         if not spec.use_qnn:
             spec.p_fc = float(self.model.fc[2].p)

@@ -4,34 +4,9 @@
 // true fp32: TF32 is off by default) and for every shape the tcgen05 path does not cover.  Tiles: 128 x {64,128} x 16,
 // 256 threads, 8x4 / 8x8 register micro-tiles arranged as 4x4 blocks so shared-memory float4 reads are
 // conflict-free; register-prefetched double buffering; optional deterministic split-K (partials + reduce).
-#include "common.cuh"
+#include "gemm_common.cuh"
 
 namespace b200ctr {
-
-struct EpiDev {
-  float alpha;
-  const float* bias;
-  int act;
-  float* pre_out; int64_t ld_pre;
-  b200ctr_dropout_t drop;
-  int mask_mode; const float* mask_src; int64_t ld_mask; float mask_scale;
-  const float* residual; int64_t ld_res;
-  const float* accum; int64_t ld_accum;
-};
-
-__device__ __forceinline__ float apply_epi(float acc, int64_t m, int64_t n, int64_t N, const EpiDev& e) {
-  float v = e.alpha * acc;
-  if (e.accum) v += e.accum[m * e.ld_accum + n];
-  if (e.bias) v += e.bias[n];
-  if (e.pre_out) e.pre_out[m * e.ld_pre + n] = v;
-  if (e.act == B200CTR_ACT_RELU) v = fmaxf(v, 0.f);
-  else if (e.act == B200CTR_ACT_GELU) v = gelu_erf(v);
-  if (e.drop.p > 0.f) v *= drop_scale(e.drop, (uint64_t)(m * N + n));
-  if (e.mask_mode == B200CTR_MASK_NONZERO) v = (e.mask_src[m * e.ld_mask + n] != 0.f) ? v * e.mask_scale : 0.f;
-  else if (e.mask_mode == B200CTR_MASK_GELU_GRAD) v *= gelu_erf_grad(e.mask_src[m * e.ld_mask + n]);
-  if (e.residual) v += e.residual[m * e.ld_res + n];
-  return v;
-}
 
 constexpr int BK = 16;
 constexpr int NT = 256;
@@ -220,6 +195,15 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
   float s = 0.f;
   for (int z = 0; z < split_k; ++z) s += partial[(int64_t)z * M * N + i];   // fixed order: deterministic
   C[m * ldc + n] = apply_epi(s, m, n, N, epi);
+}
+
+int launch_splitk_reduce(const float* partial, int split_k, int64_t M, int64_t N, float* C, int64_t ldc, const EpiDev& epi,
+                         cudaStream_t st) {
+  int64_t tot = M * N;
+  if (tot == 0) return B200CTR_OK;
+  splitk_reduce_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(partial, split_k, M, N, C, ldc, epi);
+  B200_LAUNCH_CHECK("splitk_reduce_kernel");
+  return B200CTR_OK;
 }
 
 // column sums, two deterministic passes: [M,N] -> partial[P,N] -> out[N]

@@ -1,0 +1,300 @@
+// Dense contraction on the 5th-gen tensor cores (tcgen05 + TMEM), bf16 operands / fp32 accumulation.
+//
+// This is the `amp: bf16` path of the reference (autocast casts matmul operands to bf16): activations and
+// weights stay fp32 in HBM (so every other kernel is shared with the fp32 parity path) and are converted to bf16
+// on their way into shared memory.  Because the operands pass through registers for the conversion anyway, the
+// kernel writes them straight into the canonical UMMA shared-memory layout (SWIZZLE_NONE "interleaved" core
+// matrices: 8 rows x 16 bytes), choosing K-major or MN-major per operand from its global contiguity, so all of
+// NN / NT / TN contractions run without a transpose pass.
+//
+//   CTA = 256 threads, tile 128 x BN (BN in {64,96,128,192,256}) x 64, 2 smem stages.
+//   loop: all warps stage tile kt (LDG.128 -> cvt.bf16x2 -> STS.128) | fence.proxy.async | bar |
+//         one thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (K=16 each), tcgen05.commit -> mbarrier[stage];
+//         the MMAs of tile kt run asynchronously under the staging of tile kt+1.
+//   epilogue: tcgen05.ld 32x32b.x32 (TMEM -> registers), transposed through shared memory so that the fused
+//         epilogue (bias / act / dropout / masks / residual) reads and writes global memory coalesced.
+//   split-K: grid.z slices of K write raw partials; the shared reduce kernel applies the epilogue.
+#include "gemm_common.cuh"
+#include <algorithm>
+
+namespace b200ctr {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_NT = 256;
+constexpr int TC_STAGES = 2;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+// bounded spin: a wrong phase would otherwise hang the GPU; trap instead (the host sees a CUDA error)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  asm volatile("trap;");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// SWIZZLE_NONE smem matrix descriptor: start>>4 | LBO>>4 @16 | SBO>>4 @32 | version=1 @46
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// Stage one operand tile (R mn-rows x 64 k) into the canonical interleaved layout:
+//   core matrix (mn-group g, k-group c) at ((c * R/8) + g) * 128 bytes; SBO = 128, LBO = R*16.
+//   KMAJOR  (global [mn][k], k contiguous): unit = (row r, k-group c), 16-B smem row = 8 consecutive k of row r.
+//   MNMAJOR (global [k][mn], mn contiguous): unit = (k row, mn-group g), 16-B smem row = 8 consecutive mn at row k.
+// Consecutive threads take consecutive smem rows (16-B stride) => conflict-free STS.128, 32-B global sectors.
+template <int R, bool KMAJOR>
+__device__ __forceinline__ void stage_operand(unsigned char* smem, const float* __restrict__ g, int64_t ld, int64_t mn0,
+                                              int64_t mn_end, int64_t k0, int64_t k_end, bool vec_ok, int tid) {
+  constexpr int UNITS = R * 8;
+  static_assert(UNITS % TC_NT == 0, "tile/threads mismatch");
+#pragma unroll 4
+  for (int it = 0; it < UNITS / TC_NT; ++it) {
+    const int u = tid + it * TC_NT;
+    float v[8];
+    uint32_t off;
+    if (KMAJOR) {
+      const int r = u % R, c = u / R;
+      off = (uint32_t)((c * (R / 8) + (r >> 3)) * 128 + (r & 7) * 16);
+      const int64_t m = mn0 + r, k = k0 + c * 8;
+      if (m < mn_end && vec_ok && k + 7 < k_end) {
+        const float4* p = reinterpret_cast<const float4*>(g + m * ld + k);
+        float4 a = __ldg(p), b = __ldg(p + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (m < mn_end && k + j < k_end) ? g[m * ld + k + j] : 0.f;
+      }
+    } else {
+      const int kk = u % TC_BK, gidx = u / TC_BK;
+      off = (uint32_t)(((kk >> 3) * (R / 8) + gidx) * 128 + (kk & 7) * 16);
+      const int64_t k = k0 + kk, m = mn0 + gidx * 8;
+      if (k < k_end && vec_ok && m + 7 < mn_end) {
+        const float4* p = reinterpret_cast<const float4*>(g + k * ld + m);
+        float4 a = __ldg(p), b = __ldg(p + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (k < k_end && m + j < mn_end) ? g[k * ld + m + j] : 0.f;
+      }
+    }
+    uint4 packed = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(smem + off) = packed;
+  }
+}
+
+template <int BN, bool TA, bool TB>
+__global__ void __launch_bounds__(TC_NT)
+gemm_tc_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+               int64_t ldb, float* __restrict__ C, int64_t ldc, EpiDev epi, int split_k, int64_t k_chunk,
+               float* __restrict__ partial) {
+  constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  constexpr int B_BYTES = BN * TC_BK * 2;
+  constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sA = smem;                              // [STAGES][A_BYTES]
+  unsigned char* sB = smem + TC_STAGES * A_BYTES;        // [STAGES][B_BYTES]
+  __shared__ __align__(8) unsigned long long mbar[TC_STAGES];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.y * TC_BM, n0 = (int64_t)blockIdx.x * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * k_chunk;
+  const int64_t kend = min(K, kbeg + k_chunk);
+  const int KT = (int)((kend - kbeg + TC_BK - 1) / TC_BK);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TC_STAGES; ++s) mbar_init(smem_u32(&mbar[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  const bool a_vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool b_vec = ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((TA ? 1u : 0u) << 15) | ((TB ? 0u : 1u) << 16) |
+                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  constexpr uint32_t LBO_A = TC_BM * 16, LBO_B = BN * 16, SBO = 128;
+
+  for (int kt = 0; kt < KT; ++kt) {
+    const int s = kt % TC_STAGES;
+    if (kt >= TC_STAGES) mbar_wait(smem_u32(&mbar[s]), (uint32_t)(((kt / TC_STAGES) - 1) & 1));   // stage free again
+    const int64_t k0 = kbeg + (int64_t)kt * TC_BK;
+    // A operand: opA(A)[m,k].  !TA: stored [M,K] -> K-major.  TA: stored [K,M] -> MN-major.
+    stage_operand<TC_BM, !TA>(sA + s * A_BYTES, A, lda, m0, M, k0, kend, a_vec, tid);
+    // B operand: opB(B)[k,n] as the UMMA "B" (N x K).  TB: stored [N,K] -> K-major.  !TB: stored [K,N] -> MN-major.
+    stage_operand<BN, TB>(sB + s * B_BYTES, B, ldb, n0, N, k0, kend, b_vec, tid);
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sA + s * A_BYTES), b_base = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+      for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+        const uint64_t da = make_desc(a_base + k4 * 2 * LBO_A, LBO_A, SBO);
+        const uint64_t db = make_desc(b_base + k4 * 2 * LBO_B, LBO_B, SBO);
+        umma_bf16(tmem_d, da, db, idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
+      }
+      umma_commit(smem_u32(&mbar[s]));
+    }
+  }
+  if (KT > 0) mbar_wait(smem_u32(&mbar[(KT - 1) % TC_STAGES]), (uint32_t)(((KT - 1) / TC_STAGES) & 1));
+  tc_fence_after();
+  __syncthreads();     // every warp is past its last smem/MMA dependency: the stage buffers become epilogue scratch
+
+  // ---- epilogue: TMEM -> registers -> smem transpose -> coalesced global -------------------------------------
+  float* scratch = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+  const int lane_grp = warp & 3;                 // TMEM lanes [32*lane_grp, +32) are visible to this warp
+  const int col_half = warp >> 2;                // warps 0-3: first half of the column chunks, 4-7: second half
+  constexpr int NCHUNK = BN / 32;
+  for (int cc = col_half; cc < NCHUNK; cc += 2) {
+    uint32_t r[32];
+    if (KT > 0) tmem_ld32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(cc * 32), r);
+    else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = __uint_as_float(r[j]);
+    __syncwarp();
+    const int64_t n = n0 + cc * 32 + lane;
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+      const int64_t m = m0 + lane_grp * 32 + rr;
+      if (m < M && n < N) {
+        float acc = scratch[rr * 33 + lane];
+        if (split_k > 1) partial[((int64_t)blockIdx.z * M + m) * N + n] = acc;
+        else C[m * ldc + n] = apply_epi(acc, m, n, N, epi);
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN>
+static int launch_tc(int tA, int tB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                     int64_t ldb, float* C, int64_t ldc, const EpiDev& e, int split_k, float* ws, cudaStream_t st) {
+  int64_t k_chunk = ceil_div(ceil_div(K, (int64_t)split_k), (int64_t)TC_BK) * TC_BK;
+  if (k_chunk <= 0) k_chunk = TC_BK;
+  dim3 grid((unsigned)ceil_div(N, (int64_t)BN), (unsigned)ceil_div(M, (int64_t)TC_BM), (unsigned)split_k);
+  size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2);
+  smem = std::max(smem, (size_t)8 * 32 * 33 * 4);
+#define TC_LAUNCH(TA_, TB_)                                                                                       \
+  do {                                                                                                            \
+    auto fn = gemm_tc_kernel<BN, TA_, TB_>;                                                                       \
+    if (smem + 1024 > 48 * 1024) {                                                                                \
+      cudaError_t ee = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+      if (ee != cudaSuccess) return cuda_fail(ee, "cudaFuncSetAttribute(gemm_tc smem)");                          \
+    }                                                                                                             \
+    fn<<<grid, TC_NT, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e, split_k, k_chunk, ws);                      \
+  } while (0)
+  if (!tA && !tB) TC_LAUNCH(false, false);
+  else if (!tA && tB) TC_LAUNCH(false, true);
+  else if (tA && !tB) TC_LAUNCH(true, false);
+  else {
+    set_error("gemm_bf16: transA && transB is not built");
+    return B200CTR_E_UNSUPPORTED_SHAPE;
+  }
+#undef TC_LAUNCH
+  return B200CTR_OK;
+}
+
+}  // namespace b200ctr
+
+using namespace b200ctr;
+
+extern "C" int b200ctr_gemm_bf16(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                                 const float* B, int64_t ldb, float* C, int64_t ldc, const b200ctr_epilogue_t* eh,
+                                 int split_k, void* workspace, void* stream) {
+  B200_REQUIRE(M >= 0 && N >= 0 && K >= 0, B200CTR_E_INVALID_ARG, "gemm_bf16: negative dimension");
+  if (M == 0 || N == 0) return B200CTR_OK;
+  B200_REQUIRE(A && B && C, B200CTR_E_INVALID_ARG, "gemm_bf16: null operand");
+  B200_REQUIRE(split_k >= 1 && split_k <= 1024, B200CTR_E_INVALID_ARG, "gemm_bf16: split_k out of range");
+  B200_REQUIRE(split_k == 1 || workspace, B200CTR_E_INVALID_ARG, "gemm_bf16: split_k > 1 needs a workspace");
+  B200_REQUIRE(ceil_div(M, (int64_t)TC_BM) <= 65535, B200CTR_E_UNSUPPORTED_SHAPE, "gemm_bf16: M too large for one launch");
+  EpiDev e{};
+  e.alpha = 1.f;
+  if (eh) {
+    e.alpha = eh->alpha; e.bias = eh->bias; e.act = eh->act; e.pre_out = eh->pre_out; e.ld_pre = eh->ld_pre;
+    e.drop = eh->drop; e.mask_mode = eh->mask_mode; e.mask_src = eh->mask_src; e.ld_mask = eh->ld_mask;
+    e.mask_scale = eh->mask_scale; e.residual = eh->residual; e.ld_res = eh->ld_res;
+    e.accum = eh->accum; e.ld_accum = eh->ld_accum;
+    B200_REQUIRE(e.mask_mode == B200CTR_MASK_NONE || e.mask_src, B200CTR_E_INVALID_ARG, "gemm_bf16: mask_mode without mask_src");
+  }
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  float* ws = (float*)workspace;
+  if (N <= 64) rc = launch_tc<64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
+  else if (N <= 96) rc = launch_tc<96>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
+  else if (N <= 128) rc = launch_tc<128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
+  else if (N % 192 == 0 && N <= 768) rc = launch_tc<192>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
+  else if (N % 256 == 0) rc = launch_tc<256>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
+  else rc = launch_tc<128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
+  if (rc) return rc;
+  B200_LAUNCH_CHECK("gemm_tc_kernel");
+  if (split_k > 1) {
+    rc = launch_splitk_reduce((const float*)workspace, split_k, M, N, C, ldc, e, st);
+    if (rc) return rc;
+  }
+  return B200CTR_OK;
+}
