@@ -95,7 +95,7 @@ int b200ctr_gemm(int transA, int transB, int64_t M, int64_t N, int64_t K,
 int b200ctr_gemm_bf16(int transA, int transB, int64_t M, int64_t N, int64_t K,
                       const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                       const b200ctr_epilogue_t* epi_host, int split_k, void* workspace, void* stream);
-/* out[n] = sum_m X[m,n]  (bias gradients; deterministic two-pass).  workspace >= 4*N*256 bytes. */
+/* out[n] = sum_m X[m,n]  (bias gradients; deterministic two-pass).  workspace >= 4*N*1184 bytes. */
 int b200ctr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* workspace, void* stream);
 
 /* ---- numeric / binary feature embedding  (feature_embed.py:19-27, 42-48) ------------------------------
@@ -223,6 +223,30 @@ int b200ctr_rows_sqnorm(const int32_t* tok, int64_t n_slots, int pad_id, const i
                         const float* g_dense, int D, double* acc, void* stream);
 int b200ctr_rows_zero(const int32_t* tok, int64_t n_slots, int pad_id, const int32_t* owner,
                       float* g_dense, int D, void* stream);
+
+/* ---- row-lazy, replay-exact AdamW + EMA for the seq_vocab x 64 tables (csrc/rowopt.cu) ----------------------------
+ * state[row] = (last_step << 1) | has_moments.  History (device arrays indexed by step, entry 0 = identity):
+ *   hist4[s] = {1 - lr_s*wd, lr_s/(1-b1^s), sqrt(1-b2^s), ema_decay_s}; C[s] = prod_{u<=s}(1-lr_u*wd);
+ *   S[s] = d_s*S[s-1] + (1-d_s)*C[s]; logD[s] = sum_{u<=s} log d_u.
+ * catchup: rows listed in tok (owner slots only) -> step target_step with zero gradient (what dense AdamW/EMA
+ *          would have done to an untouched row); update: catch up to step-1, then the AdamW step with the
+ *          accumulated gradient row scaled by coef[0], EMA, and the gradient row is re-zeroed; flush: all rows.  */
+int b200ctr_rowopt_push(void* hist4, float* C, float* S, float* logD, int64_t capacity, int64_t t,
+                        float decay_mul, float step_size, float bc2_sqrt, float ema_d, float C_t, float S_t, float logD_t,
+                        void* stream);
+int b200ctr_rows_claim_any(const void* tok, int idx_is_64, int64_t n_slots, int pad_id, int64_t vocab, int32_t* owner,
+                           void* stream);
+int b200ctr_rowopt_catchup(const void* tok, int idx_is_64, int64_t n_slots, int pad_id, int64_t vocab, const int32_t* owner,
+                           int32_t* state, float* p, float* m, float* v, float* ema, int D, int64_t target_step,
+                           const void* hist4, const float* C, const float* S, const float* logD,
+                           float beta1, float beta2, float eps, void* stream);
+int b200ctr_rowopt_update(const int32_t* tok, int64_t n_slots, int pad_id, const int32_t* owner, int32_t* state,
+                          float* p, float* g, float* m, float* v, float* ema, int D, int64_t step, const float* coef,
+                          const void* hist4, const float* C, const float* S, const float* logD,
+                          float beta1, float beta2, float eps, void* stream);
+int b200ctr_rowopt_flush(int32_t* state, float* p, float* m, float* v, float* ema, int64_t n_rows, int D,
+                         int64_t target_step, const void* hist4, const float* C, const float* S, const float* logD,
+                         float beta1, float beta2, float eps, void* stream);
 
 /* ---- fold-ensemble  (infer.py:122-158, utils/metrics.py:68-71): p = sigmoid(mean_m logit(clamp(p_m))) ---- */
 int b200ctr_logit_mean(const float* probs, int n_models, int64_t B, float eps, float* out, void* stream);

@@ -172,7 +172,7 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     M, N = x.shape
     if out is None:
         out = torch.empty((N,), device=x.device, dtype=torch.float32)
-    ws = torch.empty((256 * N,), device=x.device, dtype=torch.float32)
+    ws = torch.empty((1184 * N,), device=x.device, dtype=torch.float32)
     _run("colsum", lib.b200ctr_colsum, _p(x), _ld(x), M, N, _p(out), _p(ws), _stream())
     _count(2)
     return out
@@ -563,3 +563,70 @@ def logit_mean(probs, eps=1e-7):
     _run("logit_mean", lib.b200ctr_logit_mean, _p(probs), M, B, eps, _p(out), _stream())
     _count()
     return out
+
+
+# ---- row-lazy table optimiser -------------------------------------------------------------------------------------
+class RowHistory:
+    """Device-side per-step constants for the row-lazy AdamW/EMA (see csrc/rowopt.cu) + their host recurrences."""
+
+    def __init__(self, device, capacity: int, beta1=0.9, beta2=0.999, eps=1e-8):
+        import numpy as np
+        self.np = np
+        self.cap = int(capacity)
+        self.h4 = torch.zeros((self.cap, 4), device=device, dtype=torch.float32)
+        self.C = torch.ones(self.cap, device=device, dtype=torch.float32)
+        self.S = torch.ones(self.cap, device=device, dtype=torch.float32)
+        self.logD = torch.zeros(self.cap, device=device, dtype=torch.float32)
+        self.b1, self.b2, self.eps = float(np.float32(beta1)), float(np.float32(beta2)), float(eps)
+        self.c, self.s, self.ld = 1.0, 1.0, 0.0          # double recurrences on the host
+        self.t = 0
+
+    def push(self, t: int, lr: float, wd: float, ema_d: float):
+        """Register step t (must be called once per step, in order)."""
+        import math
+        np = self.np
+        assert t == self.t + 1, (t, self.t)
+        lib = _lib.load()
+        lr32 = np.float32(lr)
+        decay_mul = np.float32(1.0) - lr32 * np.float32(wd)                 # as adamw_ema_kernel: 1.f - lr*wd
+        bc1 = np.float32(1.0 - self.b1 ** t)
+        step_size = np.float32(lr32 / bc1)
+        bc2s = np.float32(math.sqrt(1.0 - self.b2 ** t))
+        d32 = np.float32(ema_d)
+        self.c *= float(decay_mul)
+        self.s = float(d32) * self.s + (1.0 - float(d32)) * self.c
+        self.ld += math.log(float(d32)) if d32 > 0 else -1e30
+        _run("rowopt_push", lib.b200ctr_rowopt_push, _p(self.h4), _p(self.C), _p(self.S), _p(self.logD), self.cap, t,
+             float(decay_mul), float(step_size), float(bc2s), float(d32), self.c, self.s, self.ld, _stream())
+        self.t = t
+        _count()
+
+    def args(self):
+        return (_p(self.h4), _p(self.C), _p(self.S), _p(self.logD), self.b1, self.b2, self.eps)
+
+
+def rows_claim_any(tok, pad_id, vocab, owner):
+    lib = _lib.load()
+    _run("rows_claim_any", lib.b200ctr_rows_claim_any, _p(tok), _idx64(tok), tok.numel(), pad_id, vocab, _p(owner), _stream())
+    _count()
+
+
+def rowopt_catchup(tok, pad_id, owner, state, p, m, v, ema, target, hist: RowHistory):
+    lib = _lib.load()
+    _run("rowopt_catchup", lib.b200ctr_rowopt_catchup, _p(tok), _idx64(tok), tok.numel(), pad_id, p.shape[0], _p(owner), _p(state),
+         _p(p), _p(m), _p(v), _p(ema), p.shape[1], target, *hist.args(), _stream())
+    _count()
+
+
+def rowopt_update(tok, pad_id, owner, state, p, g, m, v, ema, step, coef, hist: RowHistory):
+    lib = _lib.load()
+    _run("rowopt_update", lib.b200ctr_rowopt_update, _p(tok), tok.numel(), pad_id, _p(owner), _p(state), _p(p), _p(g), _p(m), _p(v),
+         _p(ema), p.shape[1], step, _p(coef), *hist.args(), _stream())
+    _count()
+
+
+def rowopt_flush(state, p, m, v, ema, target, hist: RowHistory):
+    lib = _lib.load()
+    _run("rowopt_flush", lib.b200ctr_rowopt_flush, _p(state), _p(p), _p(m), _p(v), _p(ema), p.shape[0], p.shape[1], target,
+         *hist.args(), _stream())
+    _count()

@@ -66,7 +66,7 @@ BIG_TABLES = ("dare.emb_att.weight", "dare.emb_rep.weight")
 
 class FusedTrainer:
     def __init__(self, model: CTRModel, cfg: dict, steps_per_epoch: int = 1, seed: Optional[int] = None,
-                 process_group=None):
+                 process_group=None, lazy_tables: bool = True):
         self.model, self.cfg = model, cfg
         self.spec: hp.ModelSpec = model._spec
         spec = self.spec
@@ -131,7 +131,16 @@ class FusedTrainer:
                      ema=p.clone() if self.ema_on else None)
             self.tables[n] = t
             self.Gv[n] = t["g"]
-        self.owner = torch.empty(params[BIG_TABLES[0]].shape[0], device=dev, dtype=torch.int32)
+        self.vocab = params[BIG_TABLES[0]].shape[0]
+        self.lazy = bool(lazy_tables)
+        if self.lazy:
+            cap = min(max(self.epochs * self.steps_per_epoch + 64, 4096), 1 << 22)
+            self.hist = ops.RowHistory(dev, cap)
+            for n in BIG_TABLES:
+                self.tables[n]["state"] = torch.zeros(self.vocab, device=dev, dtype=torch.int32)
+            # state_dict()/checkpointing through the nn.Module sees fully-updated tables
+            model.register_state_dict_pre_hook(lambda *a, **k: self.sync_tables())
+        self.owner = torch.empty(max(self.vocab, 1), device=dev, dtype=torch.int32)
         self.acc = torch.zeros(1, device=dev, dtype=torch.float64)
         self.coef = torch.ones(1, device=dev, dtype=torch.float32)
         self.total_norm = torch.zeros(1, device=dev, dtype=torch.float32)
@@ -182,6 +191,17 @@ class FusedTrainer:
         B_local = yd.shape[0]
         dc = hp.DropCtl(True, seed=self.seed, step=self.global_step)
         self.flat_g.zero_()
+        d = ema_decay_at(self.n_ema, self.ema_decay, self.ema_warm, self.ema_type) if self.ema_on else 0.0
+        if self.lazy:
+            # rows this batch is about to read are brought to step t-1 (exactly what dense AdamW/EMA would hold)
+            self.hist.push(self.global_step, lr, self.wd, d if self.ema_on else 1.0)
+            if self.global_step > 1:
+                seq = dbatch["seq"]
+                ops.rows_claim_any(seq, spec.pad_id, self.vocab, self.owner)
+                for n in BIG_TABLES:
+                    t = self.tables[n]
+                    ops.rowopt_catchup(seq, spec.pad_id, self.owner, t["state"], t["p"], t["m"], t["v"], t["ema"],
+                                       self.global_step - 1, self.hist)
         hook = (lambda t: self._allreduce(t)) if self.world > 1 else None
         logits, aux, sv = hp.model_fwd(self.P, spec, dbatch, dc, self.cache, B_total=B_local * self.world, colsum_hook=hook)
         counts_override = None
@@ -203,13 +223,16 @@ class FusedTrainer:
             ops.rows_sqnorm(tok, spec.pad_id, self.owner, self.tables[n]["g"], self.acc)
         ops.clip_coef(self.acc, self.clip, self.coef, self.total_norm)
         # ---- AdamW (+EMA) ----
-        d = ema_decay_at(self.n_ema, self.ema_decay, self.ema_warm, self.ema_type) if self.ema_on else 0.0
         ops.adamw_ema_(self.flat_p[:self.n_active], self.flat_g[:self.n_active], self.flat_m, self.flat_v,
                        self.flat_ema[:self.n_active] if self.ema_on else None, lr, self.wd, self.global_step, self.coef, d)
         for n in BIG_TABLES:
             t = self.tables[n]
-            ops.adamw_ema_(t["p"], t["g"], t["m"], t["v"], t["ema"], lr, self.wd, self.global_step, self.coef, d)
-            ops.rows_zero(tok, spec.pad_id, self.owner, t["g"])
+            if self.lazy:
+                ops.rowopt_update(tok, spec.pad_id, self.owner, t["state"], t["p"], t["g"], t["m"], t["v"], t["ema"],
+                                  self.global_step, self.coef, self.hist)
+            else:
+                ops.adamw_ema_(t["p"], t["g"], t["m"], t["v"], t["ema"], lr, self.wd, self.global_step, self.coef, d)
+                ops.rows_zero(tok, spec.pad_id, self.owner, t["g"])
         if self.ema_on:
             self.n_ema += 1
         self.last_logits = logits
@@ -238,8 +261,17 @@ class FusedTrainer:
         return torch.cat(toks)
 
     # ---- evaluation / state ----------------------------------------------------------------------------------
+    def sync_tables(self):
+        """Bring every row of the big tables (p, m, v, ema) to the current step.  Needed before anything other than
+        FusedTrainer.step reads them (evaluation, state_dict, EMA swap-in); a dense pass, once per epoch in practice."""
+        if self.lazy and self.global_step > 0:
+            for n in BIG_TABLES:
+                t = self.tables[n]
+                ops.rowopt_flush(t["state"], t["p"], t["m"], t["v"], t["ema"], self.global_step, self.hist)
+
     @torch.no_grad()
     def predict(self, batch: Dict[str, torch.Tensor]):
+        self.sync_tables()
         dbatch, _ = self.to_device(batch, None)
         dc = hp.DropCtl(False)
         logits, aux, _ = hp.model_fwd(self.P, self.spec, dbatch, dc, self.cache)
@@ -249,6 +281,7 @@ class FusedTrainer:
         """EMA shadows keyed like ModelEMA.shadow_params (utils/ema.py:51-58)."""
         if not self.ema_on:
             return {}
+        self.sync_tables()
         out = {}
         for n, o in self.offsets.items():
             p = self.P[n]

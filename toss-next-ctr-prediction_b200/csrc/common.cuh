@@ -52,11 +52,28 @@ __device__ __forceinline__ float drop_scale(const b200ctr_dropout_t& d, uint64_t
 }
 
 // ---- math ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// erf-GELU (nn.GELU() default) and its derivative.  erf(|x|/sqrt2) = 1 - poly(t) * exp(-x^2/2), t = 1/(1 + p|x|/sqrt2)
+// (Abramowitz-Stegun 7.1.26, |error| < 1.5e-7): one exp shared between the cdf and the pdf, no erff() call.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& ex) {
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  ex = __expf(-0.5f * x * x);
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float erf_abs = 1.f - poly * t * ex;
+  cdf = 0.5f * (1.f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, ex;
+  gelu_parts(x, cdf, ex);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-  float pdf = expf(-0.5f * x * x) * 0.39894228040143268f;
-  return cdf + x * pdf;
+  float cdf, ex;
+  gelu_parts(x, cdf, ex);
+  return fmaf(x * 0.39894228040143268f, ex, cdf);
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 // torch softplus(beta=1, threshold=20)

@@ -21,6 +21,8 @@ __device__ __forceinline__ float dot8(const float* a, const float4& b0, const fl
   return s;
 }
 
+// Each thread owns TWO query rows (i, i + ceil(K/2)) of one head: every K/V row read from shared memory feeds
+// 32 FMAs instead of 16, and K=60 x 8 heads fits one pass of the 256-thread CTA.
 __global__ void __launch_bounds__(AT_THREADS)
 attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, int K, int H,
                 float* __restrict__ o, float* __restrict__ lse, b200ctr_dropout_t drop) {
@@ -42,44 +44,70 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean
   }
   __syncthreads();
   const float scale = rsqrtf((float)AT_HD);
-  for (int item = threadIdx.x; item < K * H; item += AT_THREADS) {
-    const int h = item / K, i = item % K;
-    float q[AT_HD];
+  const int half = (K + 1) >> 1;
+  for (int item = threadIdx.x; item < half * H; item += AT_THREADS) {
+    const int h = item / half, ia = item % half;
+    const int ib_raw = ia + half;
+    const bool has_b = ib_raw < K;
+    const int ib = has_b ? ib_raw : ia;
+    float qa[AT_HD], qb[AT_HD];
     {
-      const float4* qp = reinterpret_cast<const float4*>(base + (int64_t)i * 3 * AT_D + h * AT_HD);
+      const float4* qp = reinterpret_cast<const float4*>(base + (int64_t)ia * 3 * AT_D + h * AT_HD);
       float4 a = qp[0], c = qp[1];
-      q[0] = a.x * scale; q[1] = a.y * scale; q[2] = a.z * scale; q[3] = a.w * scale;
-      q[4] = c.x * scale; q[5] = c.y * scale; q[6] = c.z * scale; q[7] = c.w * scale;
+      qa[0] = a.x * scale; qa[1] = a.y * scale; qa[2] = a.z * scale; qa[3] = a.w * scale;
+      qa[4] = c.x * scale; qa[5] = c.y * scale; qa[6] = c.z * scale; qa[7] = c.w * scale;
+      qp = reinterpret_cast<const float4*>(base + (int64_t)ib * 3 * AT_D + h * AT_HD);
+      a = qp[0]; c = qp[1];
+      qb[0] = a.x * scale; qb[1] = a.y * scale; qb[2] = a.z * scale; qb[3] = a.w * scale;
+      qb[4] = c.x * scale; qb[5] = c.y * scale; qb[6] = c.z * scale; qb[7] = c.w * scale;
     }
-    const float* bi = bias + (K - 1) - i;                  // bi[j] = bias[j-i+K-1]
-    float m = -INFINITY;
+    const float* ba = bias + (K - 1) - ia;                 // ba[j] = bias[j-ia+K-1]
+    const float* bb = bias + (K - 1) - ib;
+    float ma = -INFINITY, mb = -INFINITY;
     for (int j = 0; j < K; ++j) {
       const float4* kp = reinterpret_cast<const float4*>(ks + (size_t)j * AT_D + h * AT_HD);
-      float s = dot8(q, kp[0], kp[1]) + bi[j];
-      m = fmaxf(m, s);
+      const float4 k0 = kp[0], k1 = kp[1];
+      ma = fmaxf(ma, dot8(qa, k0, k1) + ba[j]);
+      mb = fmaxf(mb, dot8(qb, k0, k1) + bb[j]);
     }
-    float l = 0.f;
-    float acc[AT_HD];
+    float la = 0.f, lb = 0.f;
+    float aa[AT_HD], ab[AT_HD];
 #pragma unroll
-    for (int d = 0; d < AT_HD; ++d) acc[d] = 0.f;
-    const uint64_t eid0 = (((uint64_t)b * H + h) * K + i) * K;
+    for (int d = 0; d < AT_HD; ++d) { aa[d] = 0.f; ab[d] = 0.f; }
+    const uint64_t ea0 = (((uint64_t)b * H + h) * K + ia) * K, eb0 = (((uint64_t)b * H + h) * K + ib) * K;
     for (int j = 0; j < K; ++j) {
       const float4* kp = reinterpret_cast<const float4*>(ks + (size_t)j * AT_D + h * AT_HD);
-      float s = dot8(q, kp[0], kp[1]) + bi[j];
-      float e = expf(s - m);
-      l += e;
-      float ed = e * drop_scale(drop, eid0 + j);
       const float4* vp = reinterpret_cast<const float4*>(vs + (size_t)j * AT_D + h * AT_HD);
-      float4 v0 = vp[0], v1 = vp[1];
-      acc[0] = fmaf(ed, v0.x, acc[0]); acc[1] = fmaf(ed, v0.y, acc[1]); acc[2] = fmaf(ed, v0.z, acc[2]); acc[3] = fmaf(ed, v0.w, acc[3]);
-      acc[4] = fmaf(ed, v1.x, acc[4]); acc[5] = fmaf(ed, v1.y, acc[5]); acc[6] = fmaf(ed, v1.z, acc[6]); acc[7] = fmaf(ed, v1.w, acc[7]);
+      const float4 k0 = kp[0], k1 = kp[1], v0 = vp[0], v1 = vp[1];
+      const float pa = expf(dot8(qa, k0, k1) + ba[j] - ma);
+      const float pb = expf(dot8(qb, k0, k1) + bb[j] - mb);
+      la += pa; lb += pb;
+      const float da = pa * drop_scale(drop, ea0 + j), db = pb * drop_scale(drop, eb0 + j);
+      aa[0] = fmaf(da, v0.x, aa[0]); aa[1] = fmaf(da, v0.y, aa[1]); aa[2] = fmaf(da, v0.z, aa[2]); aa[3] = fmaf(da, v0.w, aa[3]);
+      aa[4] = fmaf(da, v1.x, aa[4]); aa[5] = fmaf(da, v1.y, aa[5]); aa[6] = fmaf(da, v1.z, aa[6]); aa[7] = fmaf(da, v1.w, aa[7]);
+      ab[0] = fmaf(db, v0.x, ab[0]); ab[1] = fmaf(db, v0.y, ab[1]); ab[2] = fmaf(db, v0.z, ab[2]); ab[3] = fmaf(db, v0.w, ab[3]);
+      ab[4] = fmaf(db, v1.x, ab[4]); ab[5] = fmaf(db, v1.y, ab[5]); ab[6] = fmaf(db, v1.z, ab[6]); ab[7] = fmaf(db, v1.w, ab[7]);
     }
-    float inv = 1.f / l;
-    float4* op = reinterpret_cast<float4*>(o + (b * K + i) * (int64_t)AT_D + h * AT_HD);
-    op[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
-    op[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
-    lse[(b * H + h) * (int64_t)K + i] = m + logf(l);
+    {
+      const float inv = 1.f / la;
+      float4* op = reinterpret_cast<float4*>(o + (b * K + ia) * (int64_t)AT_D + h * AT_HD);
+      op[0] = make_float4(aa[0] * inv, aa[1] * inv, aa[2] * inv, aa[3] * inv);
+      op[1] = make_float4(aa[4] * inv, aa[5] * inv, aa[6] * inv, aa[7] * inv);
+      lse[(b * H + h) * (int64_t)K + ia] = ma + logf(la);
+    }
+    if (has_b) {
+      const float inv = 1.f / lb;
+      float4* op = reinterpret_cast<float4*>(o + (b * K + ib) * (int64_t)AT_D + h * AT_HD);
+      op[0] = make_float4(ab[0] * inv, ab[1] * inv, ab[2] * inv, ab[3] * inv);
+      op[1] = make_float4(ab[4] * inv, ab[5] * inv, ab[6] * inv, ab[7] * inv);
+      lse[(b * H + h) * (int64_t)K + ib] = mb + logf(lb);
+    }
   }
+}
+
+__device__ __forceinline__ void axpy8(float* acc, float a, const float4& x0, const float4& x1) {
+  acc[0] = fmaf(a, x0.x, acc[0]); acc[1] = fmaf(a, x0.y, acc[1]); acc[2] = fmaf(a, x0.z, acc[2]); acc[3] = fmaf(a, x0.w, acc[3]);
+  acc[4] = fmaf(a, x1.x, acc[4]); acc[5] = fmaf(a, x1.y, acc[5]); acc[6] = fmaf(a, x1.z, acc[6]); acc[7] = fmaf(a, x1.w, acc[7]);
 }
 
 __global__ void __launch_bounds__(AT_THREADS)
@@ -123,57 +151,89 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean
     dsum[item] = o0.x * d0.x + o0.y * d0.y + o0.z * d0.z + o0.w * d0.w + o1.x * d1.x + o1.y * d1.y + o1.z * d1.z + o1.w * d1.w;
   }
   __syncthreads();
-  // phase 1: thread per (i,h) -> dq_i, dbias
-  for (int item = threadIdx.x; item < K * H; item += AT_THREADS) {
-    const int h = item / K, i = item % K;
-    float q[AT_HD], dd[AT_HD], dq[AT_HD];
+  const int half = (K + 1) >> 1;
+  // phase 1: thread per (head, query rows ia/ib) -> dq, dbias
+  for (int item = threadIdx.x; item < half * H; item += AT_THREADS) {
+    const int h = item / half, ia = item % half;
+    const int ib_raw = ia + half;
+    const bool has_b = ib_raw < K;
+    const int ib = has_b ? ib_raw : ia;
+    float qa[AT_HD], qb[AT_HD], da[AT_HD], db[AT_HD], ga[AT_HD], gb[AT_HD];
 #pragma unroll
-    for (int d = 0; d < AT_HD; ++d) { q[d] = qs[(size_t)i * AT_D + h * AT_HD + d]; dd[d] = dos[(size_t)i * AT_D + h * AT_HD + d]; dq[d] = 0.f; }
-    const float L = lses[item], Di = dsum[item];
-    const float* bi = bias + (K - 1) - i;
-    float* dbi = dbias + (K - 1) - i;
-    const uint64_t eid0 = (((uint64_t)b * H + h) * K + i) * K;
+    for (int d = 0; d < AT_HD; ++d) {
+      qa[d] = qs[(size_t)ia * AT_D + h * AT_HD + d]; qb[d] = qs[(size_t)ib * AT_D + h * AT_HD + d];
+      da[d] = dos[(size_t)ia * AT_D + h * AT_HD + d]; db[d] = dos[(size_t)ib * AT_D + h * AT_HD + d];
+      ga[d] = 0.f; gb[d] = 0.f;
+    }
+    const float La = lses[h * K + ia], Lb = lses[h * K + ib], Da = dsum[h * K + ia], Db = dsum[h * K + ib];
+    const float* ba = bias + (K - 1) - ia;
+    const float* bb = bias + (K - 1) - ib;
+    float* dba = dbias + (K - 1) - ia;
+    float* dbb = dbias + (K - 1) - ib;
+    const uint64_t ea0 = (((uint64_t)b * H + h) * K + ia) * K, eb0 = (((uint64_t)b * H + h) * K + ib) * K;
     for (int j = 0; j < K; ++j) {
       const float4* kp = reinterpret_cast<const float4*>(ks + (size_t)j * AT_D + h * AT_HD);
       const float4* vp = reinterpret_cast<const float4*>(vs + (size_t)j * AT_D + h * AT_HD);
-      float4 k0 = kp[0], k1 = kp[1];
-      float s = dot8(q, k0, k1) + bi[j];
-      float p = expf(s - L);
-      float dp = dot8(dd, vp[0], vp[1]) * drop_scale(drop, eid0 + j);
-      float ds = p * (dp - Di);
-      dq[0] = fmaf(ds, k0.x, dq[0]); dq[1] = fmaf(ds, k0.y, dq[1]); dq[2] = fmaf(ds, k0.z, dq[2]); dq[3] = fmaf(ds, k0.w, dq[3]);
-      dq[4] = fmaf(ds, k1.x, dq[4]); dq[5] = fmaf(ds, k1.y, dq[5]); dq[6] = fmaf(ds, k1.z, dq[6]); dq[7] = fmaf(ds, k1.w, dq[7]);
-      if (drelmean) atomicAdd(dbi + j, ds);
+      const float4 k0 = kp[0], k1 = kp[1], v0 = vp[0], v1 = vp[1];
+      const float pa = expf(dot8(qa, k0, k1) + ba[j] - La);
+      const float pb = expf(dot8(qb, k0, k1) + bb[j] - Lb);
+      const float dsa = pa * (dot8(da, v0, v1) * drop_scale(drop, ea0 + j) - Da);
+      const float dsb = pb * (dot8(db, v0, v1) * drop_scale(drop, eb0 + j) - Db);
+      axpy8(ga, dsa, k0, k1);
+      axpy8(gb, dsb, k0, k1);
+      if (drelmean) {
+        atomicAdd(dba + j, dsa);
+        if (has_b) atomicAdd(dbb + j, dsb);
+      }
     }
-    float4* out = reinterpret_cast<float4*>(dqkv + (b * K + i) * (int64_t)(3 * AT_D) + h * AT_HD);
-    out[0] = make_float4(dq[0] * scale, dq[1] * scale, dq[2] * scale, dq[3] * scale);
-    out[1] = make_float4(dq[4] * scale, dq[5] * scale, dq[6] * scale, dq[7] * scale);
+    float4* out = reinterpret_cast<float4*>(dqkv + (b * K + ia) * (int64_t)(3 * AT_D) + h * AT_HD);
+    out[0] = make_float4(ga[0] * scale, ga[1] * scale, ga[2] * scale, ga[3] * scale);
+    out[1] = make_float4(ga[4] * scale, ga[5] * scale, ga[6] * scale, ga[7] * scale);
+    if (has_b) {
+      out = reinterpret_cast<float4*>(dqkv + (b * K + ib) * (int64_t)(3 * AT_D) + h * AT_HD);
+      out[0] = make_float4(gb[0] * scale, gb[1] * scale, gb[2] * scale, gb[3] * scale);
+      out[1] = make_float4(gb[4] * scale, gb[5] * scale, gb[6] * scale, gb[7] * scale);
+    }
   }
-  // phase 2: thread per (j,h) -> dk_j, dv_j
-  for (int item = threadIdx.x; item < K * H; item += AT_THREADS) {
-    const int h = item / K, j = item % K;
-    float kk[AT_HD], vv[AT_HD], dk[AT_HD], dv[AT_HD];
+  // phase 2: thread per (head, key rows ja/jb) -> dk, dv
+  for (int item = threadIdx.x; item < half * H; item += AT_THREADS) {
+    const int h = item / half, ja = item % half;
+    const int jb_raw = ja + half;
+    const bool has_b = jb_raw < K;
+    const int jb = has_b ? jb_raw : ja;
+    float ka[AT_HD], kb[AT_HD], va[AT_HD], vb[AT_HD], dka[AT_HD], dkb[AT_HD], dva[AT_HD], dvb[AT_HD];
 #pragma unroll
-    for (int d = 0; d < AT_HD; ++d) { kk[d] = ks[(size_t)j * AT_D + h * AT_HD + d]; vv[d] = vs[(size_t)j * AT_D + h * AT_HD + d]; dk[d] = 0.f; dv[d] = 0.f; }
+    for (int d = 0; d < AT_HD; ++d) {
+      ka[d] = ks[(size_t)ja * AT_D + h * AT_HD + d]; kb[d] = ks[(size_t)jb * AT_D + h * AT_HD + d];
+      va[d] = vs[(size_t)ja * AT_D + h * AT_HD + d]; vb[d] = vs[(size_t)jb * AT_D + h * AT_HD + d];
+      dka[d] = 0.f; dkb[d] = 0.f; dva[d] = 0.f; dvb[d] = 0.f;
+    }
     for (int i = 0; i < K; ++i) {
       const float4* qp = reinterpret_cast<const float4*>(qs + (size_t)i * AT_D + h * AT_HD);
       const float4* dp4 = reinterpret_cast<const float4*>(dos + (size_t)i * AT_D + h * AT_HD);
-      float4 q0 = qp[0], q1 = qp[1], d0 = dp4[0], d1 = dp4[1];
-      float s = dot8(kk, q0, q1) + bias[(j - i) + K - 1];
-      float p = expf(s - lses[h * K + i]);
-      float dsc = drop_scale(drop, (((uint64_t)b * H + h) * K + i) * K + j);
-      float pd = p * dsc;
-      dv[0] = fmaf(pd, d0.x, dv[0]); dv[1] = fmaf(pd, d0.y, dv[1]); dv[2] = fmaf(pd, d0.z, dv[2]); dv[3] = fmaf(pd, d0.w, dv[3]);
-      dv[4] = fmaf(pd, d1.x, dv[4]); dv[5] = fmaf(pd, d1.y, dv[5]); dv[6] = fmaf(pd, d1.z, dv[6]); dv[7] = fmaf(pd, d1.w, dv[7]);
-      float dp = dot8(vv, d0, d1) * dsc;
-      float ds = p * (dp - dsum[h * K + i]);
-      dk[0] = fmaf(ds, q0.x, dk[0]); dk[1] = fmaf(ds, q0.y, dk[1]); dk[2] = fmaf(ds, q0.z, dk[2]); dk[3] = fmaf(ds, q0.w, dk[3]);
-      dk[4] = fmaf(ds, q1.x, dk[4]); dk[5] = fmaf(ds, q1.y, dk[5]); dk[6] = fmaf(ds, q1.z, dk[6]); dk[7] = fmaf(ds, q1.w, dk[7]);
+      const float4 q0 = qp[0], q1 = qp[1], d0 = dp4[0], d1 = dp4[1];
+      const float L = lses[h * K + i], Di = dsum[h * K + i];
+      const uint64_t e0 = (((uint64_t)b * H + h) * K + i) * K;
+      const float pa = expf(dot8(ka, q0, q1) + bias[(ja - i) + K - 1] - L);
+      const float pb = expf(dot8(kb, q0, q1) + bias[(jb - i) + K - 1] - L);
+      const float sa = drop_scale(drop, e0 + ja), sb = drop_scale(drop, e0 + jb);
+      axpy8(dva, pa * sa, d0, d1);
+      axpy8(dvb, pb * sb, d0, d1);
+      const float dsa = pa * (dot8(va, d0, d1) * sa - Di);
+      const float dsb = pb * (dot8(vb, d0, d1) * sb - Di);
+      axpy8(dka, dsa, q0, q1);                       // qs carries the 1/sqrt(hd) scale
+      axpy8(dkb, dsb, q0, q1);
     }
-    float4* outk = reinterpret_cast<float4*>(dqkv + (b * K + j) * (int64_t)(3 * AT_D) + AT_D + h * AT_HD);
-    float4* outv = reinterpret_cast<float4*>(dqkv + (b * K + j) * (int64_t)(3 * AT_D) + 2 * AT_D + h * AT_HD);
-    outk[0] = make_float4(dk[0], dk[1], dk[2], dk[3]); outk[1] = make_float4(dk[4], dk[5], dk[6], dk[7]);   // qs carries the scale
-    outv[0] = make_float4(dv[0], dv[1], dv[2], dv[3]); outv[1] = make_float4(dv[4], dv[5], dv[6], dv[7]);
+    float4* outk = reinterpret_cast<float4*>(dqkv + (b * K + ja) * (int64_t)(3 * AT_D) + AT_D + h * AT_HD);
+    float4* outv = reinterpret_cast<float4*>(dqkv + (b * K + ja) * (int64_t)(3 * AT_D) + 2 * AT_D + h * AT_HD);
+    outk[0] = make_float4(dka[0], dka[1], dka[2], dka[3]); outk[1] = make_float4(dka[4], dka[5], dka[6], dka[7]);
+    outv[0] = make_float4(dva[0], dva[1], dva[2], dva[3]); outv[1] = make_float4(dva[4], dva[5], dva[6], dva[7]);
+    if (has_b) {
+      outk = reinterpret_cast<float4*>(dqkv + (b * K + jb) * (int64_t)(3 * AT_D) + AT_D + h * AT_HD);
+      outv = reinterpret_cast<float4*>(dqkv + (b * K + jb) * (int64_t)(3 * AT_D) + 2 * AT_D + h * AT_HD);
+      outk[0] = make_float4(dkb[0], dkb[1], dkb[2], dkb[3]); outk[1] = make_float4(dkb[4], dkb[5], dkb[6], dkb[7]);
+      outv[0] = make_float4(dvb[0], dvb[1], dvb[2], dvb[3]); outv[1] = make_float4(dvb[4], dvb[5], dvb[6], dvb[7]);
+    }
   }
   if (drelmean) {
     __syncthreads();

@@ -5,6 +5,7 @@
 // 256 threads, 8x4 / 8x8 register micro-tiles arranged as 4x4 blocks so shared-memory float4 reads are
 // conflict-free; register-prefetched double buffering; optional deterministic split-K (partials + reduce).
 #include "gemm_common.cuh"
+#include <algorithm>
 
 namespace b200ctr {
 
@@ -206,8 +207,45 @@ int launch_splitk_reduce(const float* partial, int split_k, int64_t M, int64_t N
   return B200CTR_OK;
 }
 
-// column sums, two deterministic passes: [M,N] -> partial[P,N] -> out[N]
+// column sums, two deterministic passes: [M,N] -> partial[P,N] -> out[N].
+// pass 1 (N % 4 == 0, N <= 1024): a block tiles rows x float4-columns (N/4 lanes per row, 256/(N/4) rows per step),
+// strides over the rows with 4 independent row-steps in flight, then reduces its row-lanes through shared memory.
 constexpr int CS_PARTS = 256;
+constexpr int CS_MAXP = 1184;
+__global__ void __launch_bounds__(256)
+colsum_pass1_v4(const float* __restrict__ X, int64_t ldx, int64_t M, int N, float* __restrict__ part) {
+  __shared__ float4 red[256];
+  const int n4 = N >> 2;
+  const int lanes_per_row = n4;                       // <= 256
+  const int rows_per_step = 256 / lanes_per_row;      // >= 1
+  const int c = threadIdx.x % lanes_per_row, rl = threadIdx.x / lanes_per_row;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rl < rows_per_step) {
+    const int64_t stride = (int64_t)gridDim.x * rows_per_step;
+    int64_t r = (int64_t)blockIdx.x * rows_per_step + rl;
+    for (; r + 3 * stride < M; r += 4 * stride) {
+      float4 a0 = *reinterpret_cast<const float4*>(X + r * ldx + c * 4);
+      float4 a1 = *reinterpret_cast<const float4*>(X + (r + stride) * ldx + c * 4);
+      float4 a2 = *reinterpret_cast<const float4*>(X + (r + 2 * stride) * ldx + c * 4);
+      float4 a3 = *reinterpret_cast<const float4*>(X + (r + 3 * stride) * ldx + c * 4);
+      acc.x += (a0.x + a1.x) + (a2.x + a3.x); acc.y += (a0.y + a1.y) + (a2.y + a3.y);
+      acc.z += (a0.z + a1.z) + (a2.z + a3.z); acc.w += (a0.w + a1.w) + (a2.w + a3.w);
+    }
+    for (; r < M; r += stride) {
+      float4 a0 = *reinterpret_cast<const float4*>(X + r * ldx + c * 4);
+      acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 1; k < rows_per_step; ++k) {
+      float4 t = red[k * lanes_per_row + c];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    *reinterpret_cast<float4*>(part + (int64_t)blockIdx.x * N + c * 4) = acc;
+  }
+}
 __global__ void colsum_pass1(const float* __restrict__ X, int64_t ldx, int64_t M, int64_t N, float* __restrict__ part) {
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
@@ -218,11 +256,11 @@ __global__ void colsum_pass1(const float* __restrict__ X, int64_t ldx, int64_t M
   for (int64_t r = r0; r < r1; ++r) s += X[r * ldx + n];
   part[(int64_t)p * N + n] = s;
 }
-__global__ void colsum_pass2(const float* __restrict__ part, int64_t N, float* __restrict__ out) {
+__global__ void colsum_pass2(const float* __restrict__ part, int P, int64_t N, float* __restrict__ out) {
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
-  for (int p = 0; p < CS_PARTS; ++p) s += part[(int64_t)p * N + n];
+  for (int p = 0; p < P; ++p) s += part[(int64_t)p * N + n];
   out[n] = s;
 }
 
@@ -303,10 +341,19 @@ extern "C" int b200ctr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N,
   B200_REQUIRE(X && out && workspace, B200CTR_E_INVALID_ARG, "colsum: null pointer");
   if (N == 0) return B200CTR_OK;
   cudaStream_t st = as_stream(stream);
-  dim3 g1((unsigned)ceil_div(N, 128), CS_PARTS);
-  colsum_pass1<<<g1, 128, 0, st>>>(X, ldx, M, N, (float*)workspace);
-  B200_LAUNCH_CHECK("colsum_pass1");
-  colsum_pass2<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>((const float*)workspace, N, out);
+  const bool v4 = (N % 4 == 0) && N <= 1024 && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  if (v4) {
+    int rows_per_step = 256 / (int)(N / 4);
+    int P = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div(M, (int64_t)rows_per_step * 8)), std::min<int64_t>(CS_MAXP, (int64_t)num_sms() * 8));
+    colsum_pass1_v4<<<P, 256, 0, st>>>(X, ldx, M, (int)N, (float*)workspace);
+    B200_LAUNCH_CHECK("colsum_pass1_v4");
+    colsum_pass2<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>((const float*)workspace, P, N, out);
+  } else {
+    dim3 g1((unsigned)ceil_div(N, 128), CS_PARTS);
+    colsum_pass1<<<g1, 128, 0, st>>>(X, ldx, M, N, (float*)workspace);
+    B200_LAUNCH_CHECK("colsum_pass1");
+    colsum_pass2<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>((const float*)workspace, CS_PARTS, N, out);
+  }
   B200_LAUNCH_CHECK("colsum_pass2");
   return B200CTR_OK;
 }

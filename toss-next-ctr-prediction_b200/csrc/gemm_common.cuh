@@ -29,6 +29,51 @@ __device__ __forceinline__ float apply_epi(float acc, int64_t m, int64_t n, int6
   return v;
 }
 
+// 4-wide epilogue (n multiple of 4, all row pointers 16-byte aligned: checked by the caller via epi_vec_ok)
+struct EpiAux4 { float4 accum, mask, res; };
+__device__ __forceinline__ void epi_load4(EpiAux4& a, int64_t m, int64_t n, const EpiDev& e) {
+  if (e.accum) a.accum = *reinterpret_cast<const float4*>(e.accum + m * e.ld_accum + n);
+  if (e.mask_mode != B200CTR_MASK_NONE) a.mask = *reinterpret_cast<const float4*>(e.mask_src + m * e.ld_mask + n);
+  if (e.residual) a.res = *reinterpret_cast<const float4*>(e.residual + m * e.ld_res + n);
+}
+__device__ __forceinline__ float4 apply_epi4(float4 acc, const EpiAux4& a, int64_t m, int64_t n, int64_t N, const EpiDev& e) {
+  float v[4] = {e.alpha * acc.x, e.alpha * acc.y, e.alpha * acc.z, e.alpha * acc.w};
+  if (e.accum) { v[0] += a.accum.x; v[1] += a.accum.y; v[2] += a.accum.z; v[3] += a.accum.w; }
+  if (e.bias) {
+    float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (e.pre_out) *reinterpret_cast<float4*>(e.pre_out + m * e.ld_pre + n) = make_float4(v[0], v[1], v[2], v[3]);
+  if (e.act == B200CTR_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (e.act == B200CTR_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (e.drop.p > 0.f) {
+    const uint64_t id = (uint64_t)(m * N + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] *= drop_scale(e.drop, id + j);
+  }
+  if (e.mask_mode == B200CTR_MASK_NONZERO) {
+    const float mk[4] = {a.mask.x, a.mask.y, a.mask.z, a.mask.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (mk[j] != 0.f) ? v[j] * e.mask_scale : 0.f;
+  } else if (e.mask_mode == B200CTR_MASK_GELU_GRAD) {
+    const float mk[4] = {a.mask.x, a.mask.y, a.mask.z, a.mask.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] *= gelu_erf_grad(mk[j]);
+  }
+  if (e.residual) { v[0] += a.res.x; v[1] += a.res.y; v[2] += a.res.z; v[3] += a.res.w; }
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+__host__ __device__ inline bool ptr_al16(const void* p, int64_t ld) { return p == nullptr || (((uintptr_t)p & 15) == 0 && (ld & 3) == 0); }
+inline bool epi_vec_ok(const EpiDev& e, const float* C, int64_t ldc, int64_t N) {
+  return (N & 3) == 0 && ptr_al16(C, ldc) && ptr_al16(e.bias, 0) && ptr_al16(e.pre_out, e.ld_pre) &&
+         ptr_al16(e.mask_src, e.ld_mask) && ptr_al16(e.residual, e.ld_res) && ptr_al16(e.accum, e.ld_accum);
+}
+
 // splits written by either contraction kernel -> C with the fused epilogue (defined in gemm.cu)
 int launch_splitk_reduce(const float* partial, int split_k, int64_t M, int64_t N, float* C, int64_t ldc, const EpiDev& epi,
                          cudaStream_t st);

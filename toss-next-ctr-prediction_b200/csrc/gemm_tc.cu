@@ -131,10 +131,10 @@ __device__ __forceinline__ void stage_operand(unsigned char* smem, const float* 
 }
 
 template <int BN, bool TA, bool TB>
-__global__ void __launch_bounds__(TC_NT)
+__global__ void __launch_bounds__(TC_NT, 2)
 gemm_tc_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
                int64_t ldb, float* __restrict__ C, int64_t ldc, EpiDev epi, int split_k, int64_t k_chunk,
-               float* __restrict__ partial) {
+               float* __restrict__ partial, int vec_epi) {
   constexpr int A_BYTES = TC_BM * TC_BK * 2;
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
@@ -197,11 +197,15 @@ gemm_tc_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int
   tc_fence_after();
   __syncthreads();     // every warp is past its last smem/MMA dependency: the stage buffers become epilogue scratch
 
-  // ---- epilogue: TMEM -> registers -> smem transpose -> coalesced global -------------------------------------
-  float* scratch = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+  // ---- epilogue: TMEM -> registers -> smem transpose -> coalesced, 128-bit global accesses ---------------------
+  // per warp: a 32 x 32 fp32 chunk goes through a 32 x 36 scratch (16-B aligned rows, conflict-free both ways);
+  // then 8 lanes cover one row (float4 each), 4 rows per instruction, auxiliary operands loaded 4 rows ahead.
+  constexpr int SROW = 36;
+  float* scratch = reinterpret_cast<float*>(smem) + warp * (32 * SROW);
   const int lane_grp = warp & 3;                 // TMEM lanes [32*lane_grp, +32) are visible to this warp
-  const int col_half = warp >> 2;                // warps 0-3: first half of the column chunks, 4-7: second half
+  const int col_half = warp >> 2;                // warps 0-3: even column chunks, 4-7: odd column chunks
   constexpr int NCHUNK = BN / 32;
+  const int rg = lane >> 3, c4 = lane & 7;
   for (int cc = col_half; cc < NCHUNK; cc += 2) {
     uint32_t r[32];
     if (KT > 0) tmem_ld32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(cc * 32), r);
@@ -210,16 +214,42 @@ gemm_tc_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int
       for (int j = 0; j < 32; ++j) r[j] = 0u;
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = __uint_as_float(r[j]);
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<uint4*>(scratch + lane * SROW + q * 4) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
     __syncwarp();
-    const int64_t n = n0 + cc * 32 + lane;
+    if (vec_epi) {
+      const int64_t n = n0 + cc * 32 + c4 * 4;
+#pragma unroll
+      for (int pg = 0; pg < 2; ++pg) {
+        float4 acc[4];
+        EpiAux4 aux[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = (pg * 4 + u) * 4 + rg;
+          const int64_t m = m0 + lane_grp * 32 + row;
+          acc[u] = *reinterpret_cast<const float4*>(scratch + row * SROW + c4 * 4);
+          if (split_k == 1 && m < M && n < N) epi_load4(aux[u], m, n, epi);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = (pg * 4 + u) * 4 + rg;
+          const int64_t m = m0 + lane_grp * 32 + row;
+          if (m < M && n < N) {
+            if (split_k > 1) *reinterpret_cast<float4*>(partial + ((int64_t)blockIdx.z * M + m) * N + n) = acc[u];
+            else *reinterpret_cast<float4*>(C + m * ldc + n) = apply_epi4(acc[u], aux[u], m, n, N, epi);
+          }
+        }
+      }
+    } else {
+      const int64_t n = n0 + cc * 32 + lane;
 #pragma unroll 4
-    for (int rr = 0; rr < 32; ++rr) {
-      const int64_t m = m0 + lane_grp * 32 + rr;
-      if (m < M && n < N) {
-        float acc = scratch[rr * 33 + lane];
-        if (split_k > 1) partial[((int64_t)blockIdx.z * M + m) * N + n] = acc;
-        else C[m * ldc + n] = apply_epi(acc, m, n, N, epi);
+      for (int rr = 0; rr < 32; ++rr) {
+        const int64_t m = m0 + lane_grp * 32 + rr;
+        if (m < M && n < N) {
+          float acc = scratch[rr * SROW + lane];
+          if (split_k > 1) partial[((int64_t)blockIdx.z * M + m) * N + n] = acc;
+          else C[m * ldc + n] = apply_epi(acc, m, n, N, epi);
+        }
       }
     }
     __syncwarp();
@@ -238,7 +268,8 @@ static int launch_tc(int tA, int tB, int64_t M, int64_t N, int64_t K, const floa
   if (k_chunk <= 0) k_chunk = TC_BK;
   dim3 grid((unsigned)ceil_div(N, (int64_t)BN), (unsigned)ceil_div(M, (int64_t)TC_BM), (unsigned)split_k);
   size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2);
-  smem = std::max(smem, (size_t)8 * 32 * 33 * 4);
+  smem = std::max(smem, (size_t)8 * 32 * 36 * 4);
+  const int vec = epi_vec_ok(e, C, ldc, N) ? 1 : 0;
 #define TC_LAUNCH(TA_, TB_)                                                                                       \
   do {                                                                                                            \
     auto fn = gemm_tc_kernel<BN, TA_, TB_>;                                                                       \
@@ -246,7 +277,7 @@ static int launch_tc(int tA, int tB, int64_t M, int64_t N, int64_t K, const floa
       cudaError_t ee = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
       if (ee != cudaSuccess) return cuda_fail(ee, "cudaFuncSetAttribute(gemm_tc smem)");                          \
     }                                                                                                             \
-    fn<<<grid, TC_NT, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e, split_k, k_chunk, ws);                      \
+    fn<<<grid, TC_NT, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e, split_k, k_chunk, ws, vec);                 \
   } while (0)
   if (!tA && !tB) TC_LAUNCH(false, false);
   else if (!tA && tB) TC_LAUNCH(false, true);

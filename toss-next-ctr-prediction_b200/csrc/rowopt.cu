@@ -1,0 +1,239 @@
+// Row-lazy, replay-exact AdamW + EMA for the two seq_vocab x 64 sequence tables.
+//
+// The reference runs dense torch.optim.AdamW + ModelEMA over all 10,000,000 rows of both tables every step
+// (src/train.py:138,193-199; src/utils/ema.py:91-131): weight decay, moment decay and the EMA recurrence touch
+// 1.28 G parameters although only <= B*K rows receive a gradient (SURVEY hard part 2, ~46 GB of traffic/step even
+// when fused).  Here every row carries `state = (last_step << 1) | has_moments` and is brought up to date lazily:
+//   * rows about to be READ by a forward pass (every token of the batch) are caught up to step t-1 first, so the
+//     forward sees exactly the values dense AdamW would have produced;
+//   * rows that received a gradient get step t applied (g scaled by the global clip coefficient);
+//   * a dense flush brings all rows to the current step before state_dict / evaluation.
+// Catch-up of a row whose moments are zero (never touched) is closed-form from per-step prefix tables
+// (C = prod(1 - lr*wd), S = EMA of C, logD = sum log d); a row with non-zero moments REPLAYS the skipped steps with the
+// dense kernel's own per-element update (g = 0), so touched rows are bit-identical to the dense path.
+// History entry per step s (float4): {1 - lr_s*wd, lr_s / (1 - b1^s), sqrt(1 - b2^s), ema_decay_s}.
+#include "common.cuh"
+#include <algorithm>
+
+namespace b200ctr {
+
+constexpr int RO_D = 64;
+
+struct RowHist {
+  const float4* h;      // [steps+1]  per-step constants
+  const float* C;       // [steps+1]  C[0] = 1
+  const float* S;       // [steps+1]  S[0] = 1
+  const float* logD;    // [steps+1]  logD[0] = 0
+  float beta1, beta2, eps;
+};
+
+// bring one row (2 elements per lane) from `last` to `target` with zero gradient
+__device__ __forceinline__ void row_catchup(float2& p, float2& m, float2& v, float2& e, bool has_ema, bool has_mom,
+                                            int last, int target, const RowHist& H) {
+  if (target <= last) return;
+  if (!has_mom) {
+    const float ca = H.C[last], cb = H.C[target];
+    const float ratio = cb / ca;
+    if (has_ema) {
+      const float Dm = expf(H.logD[target] - H.logD[last]);
+      const float w = (H.S[target] - H.S[last] * Dm) / ca;
+      e.x = e.x * Dm + p.x * w;
+      e.y = e.y * Dm + p.y * w;
+    }
+    p.x *= ratio; p.y *= ratio;
+    return;
+  }
+  for (int s = last + 1; s <= target; ++s) {
+    const float4 c = __ldg(H.h + s);
+    p.x *= c.x; p.y *= c.x;
+    m.x = m.x + (0.f - m.x) * (1.f - H.beta1);   // lerp_(g = 0, 1 - b1), written exactly as the dense kernel computes it
+    m.y = m.y + (0.f - m.y) * (1.f - H.beta1);
+    v.x *= H.beta2; v.y *= H.beta2;
+    p.x -= c.y * (m.x / (sqrtf(v.x) / c.z + H.eps));
+    p.y -= c.y * (m.y / (sqrtf(v.y) / c.z + H.eps));
+    if (has_ema) { e.x = e.x * c.w + p.x * (1.f - c.w); e.y = e.y * c.w + p.y * (1.f - c.w); }
+  }
+}
+
+__global__ void rowopt_push_kernel(float4* h, float* C, float* S, float* logD, int t, float4 entry, float c, float s, float ld) {
+  h[t] = entry; C[t] = c; S[t] = s; logD[t] = ld;
+}
+
+template <typename IT>
+__global__ void rows_claim_any_kernel(const IT* __restrict__ tok, int64_t n, int pad_id, int64_t vocab, int32_t* __restrict__ owner) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t t = (int64_t)tok[i];
+  if (t != pad_id && t >= 0 && t < vocab) owner[t] = (int32_t)i;
+}
+
+// warp per slot; only the slot that owns its row does work
+template <typename IT>
+__global__ void __launch_bounds__(256)
+rowopt_catchup_kernel(const IT* __restrict__ tok, int64_t n, int pad_id, int64_t vocab, const int32_t* __restrict__ owner,
+                      int32_t* __restrict__ state, float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ V,
+                      float* __restrict__ E, int target, RowHist H) {
+  const int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (; w < n; w += nw) {
+    const int64_t t = (int64_t)tok[w];
+    if (t == pad_id || t < 0 || t >= vocab) continue;
+    if (owner[t] != (int32_t)w) continue;
+    const int32_t st = state[t];
+    const int last = st >> 1;
+    if (last >= target) continue;
+    const bool has_mom = st & 1;
+    float2* p2 = reinterpret_cast<float2*>(P + t * RO_D) + lane;
+    float2 p = *p2, m = make_float2(0.f, 0.f), v = m, e = m;
+    if (has_mom) { m = reinterpret_cast<float2*>(Mo + t * RO_D)[lane]; v = reinterpret_cast<float2*>(V + t * RO_D)[lane]; }
+    if (E) e = reinterpret_cast<float2*>(E + t * RO_D)[lane];
+    row_catchup(p, m, v, e, E != nullptr, has_mom, last, target, H);
+    *p2 = p;
+    if (has_mom) { reinterpret_cast<float2*>(Mo + t * RO_D)[lane] = m; reinterpret_cast<float2*>(V + t * RO_D)[lane] = v; }
+    if (E) reinterpret_cast<float2*>(E + t * RO_D)[lane] = e;
+    __syncwarp();
+    if (lane == 0) state[t] = (target << 1) | (st & 1);
+  }
+}
+
+// apply step t to every distinct row listed in tok (owner slot only): catch up to t-1, then the AdamW step with the
+// accumulated gradient row (scaled by the clip coefficient), EMA, and re-zero the gradient row.
+__global__ void __launch_bounds__(256)
+rowopt_update_kernel(const int32_t* __restrict__ tok, int64_t n, int pad_id, const int32_t* __restrict__ owner,
+                     int32_t* __restrict__ state, float* __restrict__ P, float* __restrict__ G, float* __restrict__ Mo,
+                     float* __restrict__ V, float* __restrict__ E, int t_step, const float* __restrict__ coef, RowHist H) {
+  const int lane = threadIdx.x & 31;
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float c = coef ? coef[0] : 1.f;
+  const float4 hc = __ldg(H.h + t_step);
+  for (; w < n; w += nw) {
+    const int t = tok[w];
+    if (t == pad_id || owner[t] != (int32_t)w) continue;
+    const int32_t st = state[t];
+    const bool has_mom = st & 1;
+    float2* p2 = reinterpret_cast<float2*>(P + (int64_t)t * RO_D) + lane;
+    float2* g2 = reinterpret_cast<float2*>(G + (int64_t)t * RO_D) + lane;
+    float2* m2 = reinterpret_cast<float2*>(Mo + (int64_t)t * RO_D) + lane;
+    float2* v2 = reinterpret_cast<float2*>(V + (int64_t)t * RO_D) + lane;
+    float2 p = *p2, g = *g2, m = make_float2(0.f, 0.f), v = m, e = m;
+    if (has_mom) { m = *m2; v = *v2; }
+    if (E) e = reinterpret_cast<float2*>(E + (int64_t)t * RO_D)[lane];
+    row_catchup(p, m, v, e, E != nullptr, has_mom, st >> 1, t_step - 1, H);
+    g.x *= c; g.y *= c;
+    p.x *= hc.x; p.y *= hc.x;
+    m.x = m.x + (g.x - m.x) * (1.f - H.beta1); m.y = m.y + (g.y - m.y) * (1.f - H.beta1);
+    v.x = v.x * H.beta2 + (1.f - H.beta2) * g.x * g.x; v.y = v.y * H.beta2 + (1.f - H.beta2) * g.y * g.y;
+    p.x -= hc.y * (m.x / (sqrtf(v.x) / hc.z + H.eps));
+    p.y -= hc.y * (m.y / (sqrtf(v.y) / hc.z + H.eps));
+    *p2 = p; *m2 = m; *v2 = v;
+    *g2 = make_float2(0.f, 0.f);
+    if (E) {
+      e.x = e.x * hc.w + p.x * (1.f - hc.w); e.y = e.y * hc.w + p.y * (1.f - hc.w);
+      reinterpret_cast<float2*>(E + (int64_t)t * RO_D)[lane] = e;
+    }
+    __syncwarp();
+    if (lane == 0) state[t] = (t_step << 1) | 1;
+  }
+}
+
+// dense flush: every row to `target`
+__global__ void __launch_bounds__(256)
+rowopt_flush_kernel(int32_t* __restrict__ state, float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ V,
+                    float* __restrict__ E, int64_t n_rows, int target, RowHist H) {
+  const int lane = threadIdx.x & 31;
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (; r < n_rows; r += nw) {
+    const int32_t st = state[r];
+    const int last = st >> 1;
+    if (last >= target) continue;
+    const bool has_mom = st & 1;
+    float2* p2 = reinterpret_cast<float2*>(P + r * RO_D) + lane;
+    float2 p = *p2, m = make_float2(0.f, 0.f), v = m, e = m;
+    if (has_mom) { m = reinterpret_cast<float2*>(Mo + r * RO_D)[lane]; v = reinterpret_cast<float2*>(V + r * RO_D)[lane]; }
+    if (E) e = reinterpret_cast<float2*>(E + r * RO_D)[lane];
+    row_catchup(p, m, v, e, E != nullptr, has_mom, last, target, H);
+    *p2 = p;
+    if (has_mom) { reinterpret_cast<float2*>(Mo + r * RO_D)[lane] = m; reinterpret_cast<float2*>(V + r * RO_D)[lane] = v; }
+    if (E) reinterpret_cast<float2*>(E + r * RO_D)[lane] = e;
+    __syncwarp();
+    if (lane == 0) state[r] = (target << 1) | (st & 1);
+  }
+}
+
+static RowHist make_hist(const void* h, const float* C, const float* S, const float* logD, float b1, float b2, float eps) {
+  RowHist H;
+  H.h = reinterpret_cast<const float4*>(h); H.C = C; H.S = S; H.logD = logD; H.beta1 = b1; H.beta2 = b2; H.eps = eps;
+  return H;
+}
+
+}  // namespace b200ctr
+
+using namespace b200ctr;
+
+extern "C" int b200ctr_rowopt_push(void* hist4, float* C, float* S, float* logD, int64_t capacity, int64_t t,
+                                   float decay_mul, float step_size, float bc2_sqrt, float ema_d, float C_t, float S_t,
+                                   float logD_t, void* stream) {
+  B200_REQUIRE(hist4 && C && S && logD, B200CTR_E_INVALID_ARG, "rowopt_push: null pointer");
+  B200_REQUIRE(t >= 0 && t < capacity, B200CTR_E_INVALID_ARG, "rowopt_push: step %lld outside history capacity %lld", (long long)t, (long long)capacity);
+  rowopt_push_kernel<<<1, 1, 0, as_stream(stream)>>>((float4*)hist4, C, S, logD, (int)t, make_float4(decay_mul, step_size, bc2_sqrt, ema_d), C_t, S_t, logD_t);
+  B200_LAUNCH_CHECK("rowopt_push_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_rows_claim_any(const void* tok, int idx_is_64, int64_t n_slots, int pad_id, int64_t vocab, int32_t* owner,
+                                      void* stream) {
+  B200_REQUIRE(tok && owner, B200CTR_E_INVALID_ARG, "rows_claim_any: null pointer");
+  B200_REQUIRE(n_slots < (1LL << 31), B200CTR_E_UNSUPPORTED_SHAPE, "rows_claim_any: too many slots");
+  if (n_slots == 0) return B200CTR_OK;
+  unsigned grid = (unsigned)ceil_div(n_slots, 256);
+  if (idx_is_64) rows_claim_any_kernel<int64_t><<<grid, 256, 0, as_stream(stream)>>>((const int64_t*)tok, n_slots, pad_id, vocab, owner);
+  else rows_claim_any_kernel<int32_t><<<grid, 256, 0, as_stream(stream)>>>((const int32_t*)tok, n_slots, pad_id, vocab, owner);
+  B200_LAUNCH_CHECK("rows_claim_any_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_rowopt_catchup(const void* tok, int idx_is_64, int64_t n_slots, int pad_id, int64_t vocab,
+                                      const int32_t* owner, int32_t* state, float* p, float* m, float* v, float* ema, int D,
+                                      int64_t target_step, const void* hist4, const float* C, const float* S, const float* logD,
+                                      float beta1, float beta2, float eps, void* stream) {
+  B200_REQUIRE(tok && owner && state && p && m && v && hist4 && C && S && logD, B200CTR_E_INVALID_ARG, "rowopt_catchup: null pointer");
+  B200_REQUIRE(D == RO_D, B200CTR_E_UNSUPPORTED_SHAPE, "rowopt_catchup: D=%d unsupported (64 only)", D);
+  if (n_slots == 0 || target_step <= 0) return B200CTR_OK;
+  RowHist H = make_hist(hist4, C, S, logD, beta1, beta2, eps);
+  int grid = (int)std::min<int64_t>(ceil_div(n_slots, 8), (int64_t)num_sms() * 16);
+  if (idx_is_64) rowopt_catchup_kernel<int64_t><<<grid, 256, 0, as_stream(stream)>>>((const int64_t*)tok, n_slots, pad_id, vocab, owner, state, p, m, v, ema, (int)target_step, H);
+  else rowopt_catchup_kernel<int32_t><<<grid, 256, 0, as_stream(stream)>>>((const int32_t*)tok, n_slots, pad_id, vocab, owner, state, p, m, v, ema, (int)target_step, H);
+  B200_LAUNCH_CHECK("rowopt_catchup_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_rowopt_update(const int32_t* tok, int64_t n_slots, int pad_id, const int32_t* owner, int32_t* state,
+                                     float* p, float* g, float* m, float* v, float* ema, int D, int64_t step, const float* coef,
+                                     const void* hist4, const float* C, const float* S, const float* logD, float beta1,
+                                     float beta2, float eps, void* stream) {
+  B200_REQUIRE(tok && owner && state && p && g && m && v && hist4 && C && S && logD, B200CTR_E_INVALID_ARG, "rowopt_update: null pointer");
+  B200_REQUIRE(D == RO_D, B200CTR_E_UNSUPPORTED_SHAPE, "rowopt_update: D=%d unsupported (64 only)", D);
+  B200_REQUIRE(step >= 1, B200CTR_E_INVALID_ARG, "rowopt_update: step must be >= 1");
+  if (n_slots == 0) return B200CTR_OK;
+  RowHist H = make_hist(hist4, C, S, logD, beta1, beta2, eps);
+  int grid = (int)std::min<int64_t>(ceil_div(n_slots, 8), (int64_t)num_sms() * 16);
+  rowopt_update_kernel<<<grid, 256, 0, as_stream(stream)>>>(tok, n_slots, pad_id, owner, state, p, g, m, v, ema, (int)step, coef, H);
+  B200_LAUNCH_CHECK("rowopt_update_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_rowopt_flush(int32_t* state, float* p, float* m, float* v, float* ema, int64_t n_rows, int D,
+                                    int64_t target_step, const void* hist4, const float* C, const float* S, const float* logD,
+                                    float beta1, float beta2, float eps, void* stream) {
+  B200_REQUIRE(state && p && m && v && hist4 && C && S && logD, B200CTR_E_INVALID_ARG, "rowopt_flush: null pointer");
+  B200_REQUIRE(D == RO_D, B200CTR_E_UNSUPPORTED_SHAPE, "rowopt_flush: D=%d unsupported (64 only)", D);
+  if (n_rows == 0 || target_step <= 0) return B200CTR_OK;
+  RowHist H = make_hist(hist4, C, S, logD, beta1, beta2, eps);
+  int grid = (int)std::min<int64_t>(ceil_div(n_rows, 8), (int64_t)num_sms() * 32);
+  rowopt_flush_kernel<<<grid, 256, 0, as_stream(stream)>>>(state, p, m, v, ema, n_rows, (int)target_step, H);
+  B200_LAUNCH_CHECK("rowopt_flush_kernel");
+  return B200CTR_OK;
+}
