@@ -16,6 +16,7 @@
 //   split-K: grid.z slices of K write raw partials; the shared reduce kernel applies the epilogue.
 #include "gemm_common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace b200ctr {
 
@@ -261,6 +262,286 @@ gemm_tc_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int
   }
 }
 
+
+// =============================================================================================================
+// v2: persistent, warp-specialised pipeline.
+//   warps 0-7  producers : stream operand tiles (LDG.128 -> bf16 -> STS.128) into a WS_STAGES-deep ring
+//   warps 8-11 epilogue  : TMEM -> registers -> smem transpose -> fused epilogue -> coalesced 128-bit stores
+//   warp  12   MMA       : one thread issues tcgen05.mma, tcgen05.commit releases ring slots / publishes accumulators
+// Two TMEM accumulator buffers: the epilogue of tile i overlaps the loads and MMAs of tile i+1 (for the K=64
+// encoder shapes a tile is a single ring slot, so the ring runs WS_STAGES tiles ahead of the epilogue).
+// Each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; tile -> (m-tile, n-tile, k-split).
+// =============================================================================================================
+// role split (producer warps, epilogue warps): (4, 8) for the output-heavy small-K shapes, (8, 4) for deep-K shapes
+constexpr int WS_NT = 13 * 32;     // 416 threads in both splits
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int R, bool KMAJOR, int WS_PROD_THREADS>
+__device__ __forceinline__ void stage_operand_ws(unsigned char* smem, const float* __restrict__ g, int64_t ld, int64_t mn0,
+                                                 int64_t mn_end, int64_t k0, int64_t k_end, bool vec_ok, int ptid) {
+  constexpr int UNITS = R * 8;
+  static_assert(UNITS % WS_PROD_THREADS == 0, "tile/threads mismatch");
+  constexpr int ITERS = UNITS / WS_PROD_THREADS;
+  constexpr int UNR = (ITERS % 4 == 0) ? 4 : ((ITERS % 3 == 0) ? 3 : ((ITERS % 2 == 0) ? 2 : 1));
+#pragma unroll 1
+  for (int it0 = 0; it0 < ITERS; it0 += UNR) {
+    float4 va[UNR], vb[UNR];
+    uint32_t off[UNR];
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const int u = ptid + (it0 + q) * WS_PROD_THREADS;
+      va[q] = make_float4(0.f, 0.f, 0.f, 0.f); vb[q] = va[q];
+      if (KMAJOR) {
+        const int r = u % R, c = u / R;
+        off[q] = (uint32_t)((c * (R / 8) + (r >> 3)) * 128 + (r & 7) * 16);
+        const int64_t m = mn0 + r, k = k0 + c * 8;
+        if (m < mn_end) {
+          const float* p = g + m * ld + k;
+          if (vec_ok && k + 7 < k_end) { va[q] = __ldg(reinterpret_cast<const float4*>(p)); vb[q] = __ldg(reinterpret_cast<const float4*>(p) + 1); }
+          else {
+            float t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = (k + j < k_end) ? p[j] : 0.f;
+            va[q] = make_float4(t[0], t[1], t[2], t[3]); vb[q] = make_float4(t[4], t[5], t[6], t[7]);
+          }
+        }
+      } else {
+        const int kk = u % TC_BK, gidx = u / TC_BK;
+        off[q] = (uint32_t)(((kk >> 3) * (R / 8) + gidx) * 128 + (kk & 7) * 16);
+        const int64_t k = k0 + kk, m = mn0 + gidx * 8;
+        if (k < k_end) {
+          const float* p = g + k * ld + m;
+          if (vec_ok && m + 7 < mn_end) { va[q] = __ldg(reinterpret_cast<const float4*>(p)); vb[q] = __ldg(reinterpret_cast<const float4*>(p) + 1); }
+          else {
+            float t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = (m + j < mn_end) ? p[j] : 0.f;
+            va[q] = make_float4(t[0], t[1], t[2], t[3]); vb[q] = make_float4(t[4], t[5], t[6], t[7]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      uint4 packed = make_uint4(pack_bf16(va[q].x, va[q].y), pack_bf16(va[q].z, va[q].w), pack_bf16(vb[q].x, vb[q].y), pack_bf16(vb[q].z, vb[q].w));
+      *reinterpret_cast<uint4*>(smem + off[q]) = packed;
+    }
+  }
+}
+
+template <int BN, bool TA, bool TB, int STAGES, int WS_PROD_WARPS, int WS_EPI_WARPS>
+__global__ void __launch_bounds__(WS_NT, 1)
+gemm_tc_ws_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                  int64_t ldb, float* __restrict__ C, int64_t ldc, EpiDev epi, int split_k, int64_t k_chunk,
+                  float* __restrict__ partial, int vec_epi, int tiles_m, int tiles_n) {
+  constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  constexpr int B_BYTES = BN * TC_BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int ACC_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);     // columns per accumulator buffer
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
+  constexpr int SROW = 36;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* epi_scratch = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);       // WS_EPI_WARPS x 32 x SROW floats
+  __shared__ __align__(8) unsigned long long full_bar[STAGES], empty_bar[STAGES], accfull_bar[2], accempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total_tiles = tiles_m * tiles_n * split_k;
+
+  if (warp == WS_PROD_WARPS + WS_EPI_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), WS_PROD_WARPS); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    mbar_init(smem_u32(&accfull_bar[0]), 1); mbar_init(smem_u32(&accfull_bar[1]), 1);
+    mbar_init(smem_u32(&accempty_bar[0]), WS_EPI_WARPS); mbar_init(smem_u32(&accempty_bar[1]), WS_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < WS_PROD_WARPS) {
+    // ------------------------------------------------ producers ------------------------------------------------
+    const bool a_vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const bool b_vec = ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    uint32_t g = 0;                                       // ring position across all tiles of this CTA
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % tiles_n, mt = (t / tiles_n) % tiles_m, z = t / (tiles_n * tiles_m);
+      const int64_t m0 = (int64_t)mt * TC_BM, n0 = (int64_t)nt * BN;
+      const int64_t kbeg = (int64_t)z * k_chunk, kend = min(K, kbeg + k_chunk);
+      const int KT = (int)((kend - kbeg + TC_BK - 1) / TC_BK);
+      for (int kt = 0; kt < KT; ++kt, ++g) {
+        const int s = g % STAGES;
+        const uint32_t use = g / STAGES;
+        if (use > 0) mbar_wait(smem_u32(&empty_bar[s]), (use - 1) & 1);
+        unsigned char* sa = smem + s * STAGE_BYTES;
+        unsigned char* sb = sa + A_BYTES;
+        const int64_t k0 = kbeg + (int64_t)kt * TC_BK;
+        stage_operand_ws<TC_BM, !TA, WS_PROD_WARPS * 32>(sa, A, lda, m0, M, k0, kend, a_vec, tid);
+        stage_operand_ws<BN, TB, WS_PROD_WARPS * 32>(sb, B, ldb, n0, N, k0, kend, b_vec, tid);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+      }
+    }
+  } else if (warp == WS_PROD_WARPS + WS_EPI_WARPS) {
+    // ------------------------------------------------ MMA issuer -----------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((TA ? 1u : 0u) << 15) | ((TB ? 0u : 1u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      constexpr uint32_t LBO_A = TC_BM * 16, LBO_B = BN * 16, SBO = 128;
+      uint32_t g = 0, a = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++a) {
+        const int z = t / (tiles_n * tiles_m);
+        const int64_t kbeg = (int64_t)z * k_chunk, kend = min(K, kbeg + k_chunk);
+        const int KT = (int)((kend - kbeg + TC_BK - 1) / TC_BK);
+        const uint32_t buf = a & 1, use = a >> 1;
+        if (use > 0) mbar_wait(smem_u32(&accempty_bar[buf]), (use - 1) & 1);      // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
+        for (int kt = 0; kt < KT; ++kt, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(smem_u32(&full_bar[s]), (g / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES), b_base = a_base + A_BYTES;
+#pragma unroll
+          for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+            const uint64_t da = make_desc(a_base + k4 * 2 * LBO_A, LBO_A, SBO);
+            const uint64_t db = make_desc(b_base + k4 * 2 * LBO_B, LBO_B, SBO);
+            umma_bf16(tmem_d, da, db, idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));            // ring slot reusable once these MMAs have read it
+        }
+        umma_commit(smem_u32(&accfull_bar[buf]));          // accumulator complete (also covers KT == 0)
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue -------------------------------------------------
+    static_assert(WS_PROD_WARPS % 4 == 0 && WS_EPI_WARPS % 4 == 0 && WS_PROD_WARPS + WS_EPI_WARPS == 12, "role split");
+    const int ewarp = warp - WS_PROD_WARPS;                // 0 .. WS_EPI_WARPS-1
+    const int ew = ewarp & 3;                              // TMEM lane group == warp % 4
+    const int cgrp = ewarp >> 2;                           // column group of this warp
+    constexpr int NCG = WS_EPI_WARPS / 4;
+    float* scratch = epi_scratch + ewarp * (32 * SROW);
+    constexpr int NCHUNK = BN / 32;
+    const int rg = lane >> 3, c4 = lane & 7;
+    uint32_t a = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++a) {
+      const int nt = t % tiles_n, mt = (t / tiles_n) % tiles_m, z = t / (tiles_n * tiles_m);
+      const int64_t m0 = (int64_t)mt * TC_BM, n0 = (int64_t)nt * BN;
+      const int64_t kbeg = (int64_t)z * k_chunk, kend = min(K, kbeg + k_chunk);
+      const bool has_k = kend > kbeg;
+      const uint32_t buf = a & 1, use = a >> 1;
+      mbar_wait(smem_u32(&accfull_bar[buf]), use & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
+      if (cgrp >= NCHUNK) {                                   // (BN = 32*k with fewer chunks than column groups)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&accempty_bar[buf]));
+      }
+      for (int cc = cgrp; cc < NCHUNK; cc += NCG) {
+        uint32_t r[32];
+        if (has_k) tmem_ld32(tmem_d + ((uint32_t)(ew * 32) << 16) + (uint32_t)(cc * 32), r);
+        else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (cc + NCG >= NCHUNK) {        // this warp's last TMEM read of the buffer: hand it back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&accempty_bar[buf]));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(scratch + lane * SROW + q * 4) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        __syncwarp();
+        if (vec_epi) {
+          const int64_t n = n0 + cc * 32 + c4 * 4;
+#pragma unroll
+          for (int pg = 0; pg < 2; ++pg) {
+            float4 acc[4];
+            EpiAux4 aux[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int row = (pg * 4 + u) * 4 + rg;
+              const int64_t m = m0 + ew * 32 + row;
+              acc[u] = *reinterpret_cast<const float4*>(scratch + row * SROW + c4 * 4);
+              if (split_k == 1 && m < M && n < N) epi_load4(aux[u], m, n, epi);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int row = (pg * 4 + u) * 4 + rg;
+              const int64_t m = m0 + ew * 32 + row;
+              if (m < M && n < N) {
+                if (split_k > 1) *reinterpret_cast<float4*>(partial + ((int64_t)z * M + m) * N + n) = acc[u];
+                else *reinterpret_cast<float4*>(C + m * ldc + n) = apply_epi4(acc[u], aux[u], m, n, N, epi);
+              }
+            }
+          }
+        } else {
+          const int64_t n = n0 + cc * 32 + lane;
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int64_t m = m0 + ew * 32 + rr;
+            if (m < M && n < N) {
+              float acc = scratch[rr * SROW + lane];
+              if (split_k > 1) partial[((int64_t)z * M + m) * N + n] = acc;
+              else C[m * ldc + n] = apply_epi(acc, m, n, N, epi);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WS_PROD_WARPS + WS_EPI_WARPS) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN>
+static int launch_tc_ws(int tA, int tB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                        int64_t ldb, float* C, int64_t ldc, const EpiDev& e, int split_k, float* ws, cudaStream_t st) {
+  int64_t k_chunk = ceil_div(ceil_div(K, (int64_t)split_k), (int64_t)TC_BK) * TC_BK;
+  if (k_chunk <= 0) k_chunk = TC_BK;
+  const int tiles_m = (int)ceil_div(M, (int64_t)TC_BM), tiles_n = (int)ceil_div(N, (int64_t)BN);
+  const int64_t total = (int64_t)tiles_m * tiles_n * split_k;
+  constexpr int STAGES = BN <= 128 ? 5 : (BN <= 192 ? 4 : 3);
+  const bool deep_k = k_chunk > 512;                     // deep-K: loads dominate -> 8 producer warps; else 8 epilogue warps
+  size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + (size_t)8 * 32 * 36 * 4;
+  const int vec = epi_vec_ok(e, C, ldc, N) ? 1 : 0;
+  const int grid = (int)std::min<int64_t>(total, (int64_t)num_sms());
+#define WS_LAUNCH1(TA_, TB_, PW_, EW_)                                                                            \
+  do {                                                                                                            \
+    auto fn = gemm_tc_ws_kernel<BN, TA_, TB_, STAGES, PW_, EW_>;                                                  \
+    cudaError_t ee = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+    if (ee != cudaSuccess) return cuda_fail(ee, "cudaFuncSetAttribute(gemm_tc_ws smem)");                         \
+    fn<<<grid, WS_NT, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e, split_k, k_chunk, ws, vec, tiles_m, tiles_n); \
+  } while (0)
+#define WS_LAUNCH(TA_, TB_) do { if (deep_k) WS_LAUNCH1(TA_, TB_, 8, 4); else WS_LAUNCH1(TA_, TB_, 4, 8); } while (0)
+  if (!tA && !tB) WS_LAUNCH(false, false);
+  else if (!tA && tB) WS_LAUNCH(false, true);
+  else if (tA && !tB) WS_LAUNCH(true, false);
+  else {
+    set_error("gemm_bf16: transA && transB is not built");
+    return B200CTR_E_UNSUPPORTED_SHAPE;
+  }
+#undef WS_LAUNCH
+#undef WS_LAUNCH1
+  return B200CTR_OK;
+}
+
 template <int BN>
 static int launch_tc(int tA, int tB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                      int64_t ldb, float* C, int64_t ldc, const EpiDev& e, int split_k, float* ws, cudaStream_t st) {
@@ -315,12 +596,20 @@ extern "C" int b200ctr_gemm_bf16(int transA, int transB, int64_t M, int64_t N, i
   cudaStream_t st = as_stream(stream);
   int rc;
   float* ws = (float*)workspace;
-  if (N <= 64) rc = launch_tc<64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
-  else if (N <= 96) rc = launch_tc<96>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
-  else if (N <= 128) rc = launch_tc<128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
-  else if (N % 192 == 0 && N <= 768) rc = launch_tc<192>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
-  else if (N % 256 == 0) rc = launch_tc<256>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
-  else rc = launch_tc<128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
+  static const bool use_v1 = getenv("B200CTR_TC_V1") != nullptr;      // A/B switch: the non-persistent first version
+#define TC_DISPATCH(FN)                                                                                          \
+  if (N <= 64) rc = FN<64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);                 \
+  else if (N <= 96) rc = FN<96>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);            \
+  else if (N <= 128) rc = FN<128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);          \
+  else if (N % 192 == 0 && N <= 768) rc = FN<192>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st); \
+  else if (N % 256 == 0) rc = FN<256>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);      \
+  else rc = FN<128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
+  // measured on B200 (profiles/): the persistent pipeline wins when the K loop is deep (MLP / weight-gradient shapes);
+  // for the single-k-tile, output-heavy encoder shapes two resident non-persistent CTAs (16 epilogue warps) are faster.
+  static const bool force_ws = getenv("B200CTR_TC_WS") != nullptr;
+  const int64_t k_per_split = ceil_div(K, (int64_t)split_k);
+  if (!force_ws && (use_v1 || k_per_split <= 512)) { TC_DISPATCH(launch_tc) } else { TC_DISPATCH(launch_tc_ws) }
+#undef TC_DISPATCH
   if (rc) return rc;
   B200_LAUNCH_CHECK("gemm_tc_kernel");
   if (split_k > 1) {
