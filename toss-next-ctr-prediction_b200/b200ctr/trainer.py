@@ -212,6 +212,12 @@ class FusedTrainer:
         hp.model_bwd(self.P, spec, sv, dz, daux if spec.aux_weight > 0 else None, dc, self._G, colsum_hook=hook)
         tok = sv["dare"]["tok"]
         if self.world > 1:
+            # the SE gate's weight gradients are functions of batch-global sums (already all-reduced inside
+            # qnn_bwd), hence identical on every rank: pre-divide so the dense all-reduce(sum) leaves them unchanged
+            if spec.use_qnn and spec.use_se:
+                for n in ("qnn.se.fc.0.weight", "qnn.se.fc.0.bias", "qnn.se.fc.2.weight", "qnn.se.fc.2.bias"):
+                    g = self.Gv[n].view(-1)
+                    ops.axpby(g, None, 1.0 / self.world, 0.0, out=g)
             self._allreduce(self.flat_g[:self.n_active])                                            # C2
             tok = self._exchange_table_grads(tok)                                                   # C1
             self._allreduce(loss)
