@@ -169,6 +169,26 @@ int b200ctr_rmsnorm_bwd(const float* dy, const float* s, const float* w, const f
 int b200ctr_relmean_fwd(const float* rel, int T, int H, float* relmean, void* stream);
 int b200ctr_relmean_bwd(const float* drelmean, int T, int H, float* drel, void* stream);
 
+/* ---- fused encoder FFN block on tcgen05 (dare.py:67-69; the `amp: bf16` path) -----------------------------
+ * x2 = RMSNorm_n2(s2), s2 = x1 + W2.dropout(GELU(W1.x1 + b1)) + b2 ; operands rounded to bf16, fp32 accumulation
+ * in TMEM; the (T, hidden) activation never reaches HBM.  w1 (hidden, D), w2 (D, hidden) row-major as in the
+ * reference's nn.Linear; dropout element id = m*hidden + n (identical to the unfused gemm epilogue, so the
+ * backward regenerates the same mask).  s2_out / r2_out (saved for the backward) may be NULL.
+ * D == 64, hidden % 64 == 0, hidden <= 512.                                                                 */
+int b200ctr_ffn_fwd(const float* x1, const float* w1, const float* b1, const float* w2, const float* b2,
+                    const float* n2w, float eps, int64_t T, int D, int hidden, float* s2_out, float* r2_out,
+                    float* x2_out, b200ctr_dropout_t drop, void* stream);
+
+/* Backward of b200ctr_ffn_fwd: recomputes the hidden activation from x1 (dropout mask regenerated), accumulates
+ * dW1 / dW2 in TMEM across a persistent loop (deterministic cross-CTA reduction afterwards) and returns
+ * dx1 = dL/dx1 (including the residual branch).  dw1 (hidden, D), db1 (hidden), dw2 (D, hidden), db2 (D), dn2 (D)
+ * are overwritten.  workspace >= b200ctr_ffn_bwd_workspace_bytes(T, hidden).  hidden % 128 == 0, hidden <= 384.  */
+int64_t b200ctr_ffn_bwd_workspace_bytes(int64_t T, int hidden);
+int b200ctr_ffn_bwd(const float* dy, const float* s2, const float* r2, const float* n2w, const float* x1,
+                    const float* w1, const float* b1, const float* w2, int64_t T, int D, int hidden,
+                    float* dx1, float* dw1, float* db1, float* dw2, float* db2, float* dn2,
+                    void* workspace, b200ctr_dropout_t drop, void* stream);
+
 /* ---- gated pooling + aux head  (dare.py:151-161) ------------------------------------------------------- */
 int b200ctr_pool_fwd(const float* x, const float* vals, const float* aux_w, const float* aux_b, int gating_relu,
                      int64_t B, int K, int D, float* u, int64_t ld_u, float* aux, float* w_out,

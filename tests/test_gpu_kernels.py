@@ -272,3 +272,68 @@ def test_gemm_bf16_epilogue_and_strided_views(dev):
         o1 = ops.gemm(a, w, trans_b=True, dropout=d, tc=True)
     o2 = ops.gemm(a, w, trans_b=True, dropout=d)             # fp32 path: same mask (same element ids)
     assert torch.equal(o1 == 0, o2 == 0)
+
+
+# ---- fused tcgen05 FFN block (csrc/ffn_fused.cu) vs the unfused bf16 composition and vs torch --------------------
+def _ffn_inputs(T, hidden, seed):
+    g = torch.Generator().manual_seed(seed)
+    x1 = _rand(g, T, 64)
+    w1 = _rand(g, hidden, 64) * 64 ** -0.5
+    b1 = _rand(g, hidden) * 0.1
+    w2 = _rand(g, 64, hidden) * hidden ** -0.5
+    b2 = _rand(g, 64) * 0.1
+    n2 = 1.0 + 0.1 * _rand(g, 64)
+    return x1, w1, b1, w2, b2, n2
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("T,hidden,p", [(128, 128, 0.0), (1000, 384, 0.0), (1000, 384, 0.1), (128 * 300 + 17, 384, 0.1), (5, 256, 0.0)])
+def test_ffn_fwd_fused_matches_unfused(dev, T, hidden, p):
+    from b200ctr import ops
+    x1, w1, b1, w2, b2, n2 = (t.to(dev) for t in _ffn_inputs(T, hidden, 3 + T))
+    dr = ops.drop(p, 1234, 77)
+    x2, s2, r2 = ops.ffn_fwd(x1, w1, b1, w2, b2, n2, dr)
+    with ops.precision("bf16"):
+        fd = ops.gemm(x1, w1, trans_b=True, bias=b1, act=ops.ACT_GELU, dropout=dr, tc=True)
+        h2 = ops.gemm(fd, w2, trans_b=True, bias=b2, tc=True)
+    s2u, x2u, r2u = ops.add_rmsnorm_fwd(x1, h2, n2)
+    assert max_err_scaled(s2.cpu(), s2u.cpu()) < 2e-3
+    assert max_err_scaled(x2.cpu(), x2u.cpu()) < 2e-3
+    assert max_err_scaled(r2.cpu(), r2u.cpu()) < 2e-3
+    if p == 0.0:
+        pre = _bf(x1) @ _bf(w1).t() + b1
+        fdr = torch.nn.functional.gelu(pre)
+        s2r = x1 + _bf(fdr) @ _bf(w2).t() + b2
+        rr = torch.rsqrt((s2r * s2r).mean(1) + 1e-6)
+        assert max_err_scaled(s2.cpu(), s2r.cpu()) < 2e-3
+        assert max_err_scaled(x2.cpu(), (n2 * s2r * rr[:, None]).cpu()) < 2e-3
+
+
+@pytest.mark.parametrize("T,hidden,p", [(128, 128, 0.0), (1000, 384, 0.0), (1000, 384, 0.1), (128 * 300 + 17, 384, 0.1), (5, 256, 0.0)])
+def test_ffn_bwd_fused_matches_unfused(dev, T, hidden, p):
+    from b200ctr import ops
+    x1, w1, b1, w2, b2, n2 = (t.to(dev) for t in _ffn_inputs(T, hidden, 9 + T))
+    dy = torch.randn(T, 64, generator=torch.Generator().manual_seed(T)).to(dev)
+    dr = ops.drop(p, 4321, 55)
+    x2, s2, r2 = ops.ffn_fwd(x1, w1, b1, w2, b2, n2, dr)
+    z = lambda *s: torch.zeros(*s, device=dev)
+    dw1, db1, dw2, db2, dn2 = z(hidden, 64), z(hidden), z(64, hidden), z(64), z(64)
+    dx1 = ops.ffn_bwd(dy, s2, r2, n2, x1, w1, b1, w2, dw1, db1, dw2, db2, dn2, dr)
+    # unfused composition (hotpath.encoder_layer_bwd before fusion), same dropout stream
+    with ops.precision("bf16"):
+        pre = torch.empty(T, hidden, device=dev)
+        fd = ops.gemm(x1, w1, trans_b=True, bias=b1, act=ops.ACT_GELU, pre_out=pre, dropout=dr, tc=True)
+        dn2u = z(64)
+        d_s2 = ops.rmsnorm_bwd(dy, s2, n2, r2, dn2u)
+        dw2u = ops.gemm(d_s2, fd, trans_a=True, tc=True)
+        db2u = ops.colsum(d_s2)
+        dpre = ops.gemm(d_s2, w2, dropout=dr, mask_mode=ops.MASK_GELU_GRAD, mask_src=pre, tc=True)
+        dw1u = ops.gemm(dpre, x1, trans_a=True, tc=True)
+        db1u = ops.colsum(dpre)
+        dx1u = ops.gemm(dpre, w1, residual=d_s2, tc=True)
+    for name, a, b in (("dx1", dx1, dx1u), ("dw1", dw1, dw1u), ("db1", db1, db1u), ("dw2", dw2, dw2u), ("db2", db2, db2u),
+                       ("dn2", dn2, dn2u)):
+        assert max_err_scaled(a.cpu(), b.cpu()) < 5e-3, name

@@ -135,11 +135,17 @@ def encoder_layer_fwd(x: Tensor, P: Dict[str, Tensor], i: int, spec: ModelSpec, 
     o, lse = ops.attn_fwd(qkv, relmean, spec.top_k, B, K, H, D, dc(spec.p_mha, SITE_LAYER0 + 2 * i))
     h = ops.gemm(o, P[n["out_w"]], trans_b=True, bias=P[n["out_b"]])
     s1, x1, r1 = ops.add_rmsnorm_fwd(x, h, P[n["n1"]])
-    pre = torch.empty((x.shape[0], spec.ffn_hidden), device=x.device, dtype=torch.float32)
-    fd = ops.gemm(x1, P[n["f1_w"]], trans_b=True, bias=P[n["f1_b"]], act=ops.ACT_GELU, pre_out=pre,
-                  dropout=dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1))
-    h2 = ops.gemm(fd, P[n["f2_w"]], trans_b=True, bias=P[n["f2_b"]])
-    s2, x2, r2 = ops.add_rmsnorm_fwd(x1, h2, P[n["n2"]])
+    if ops.get_precision() == "bf16" and ops.ffn_fused_ok(spec.ffn_hidden, D):
+        # one tcgen05 kernel: the (tokens, ffn_hidden) activation stays on the SM; the backward recomputes it from x1
+        x2, s2, r2 = ops.ffn_fwd(x1, P[n["f1_w"]], P[n["f1_b"]], P[n["f2_w"]], P[n["f2_b"]], P[n["n2"]],
+                                 dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1))
+        pre = fd = None
+    else:
+        pre = torch.empty((x.shape[0], spec.ffn_hidden), device=x.device, dtype=torch.float32)
+        fd = ops.gemm(x1, P[n["f1_w"]], trans_b=True, bias=P[n["f1_b"]], act=ops.ACT_GELU, pre_out=pre,
+                      dropout=dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1))
+        h2 = ops.gemm(fd, P[n["f2_w"]], trans_b=True, bias=P[n["f2_b"]])
+        s2, x2, r2 = ops.add_rmsnorm_fwd(x1, h2, P[n["n2"]])
     return x2, dict(x=x, relmean=relmean, qkv=qkv, o=o, lse=lse, s1=s1, x1=x1, r1=r1, pre=pre, fd=fd, s2=s2, r2=r2)
 
 
@@ -147,16 +153,21 @@ def encoder_layer_bwd(dy: Tensor, sv: dict, P: Dict[str, Tensor], i: int, spec: 
                       G: Callable[[str], Tensor]) -> Tensor:
     n = _layer_names(i)
     D, H = spec.D, spec.n_heads
-    d_s2 = ops.rmsnorm_bwd(dy, sv["s2"], P[n["n2"]], sv["r2"], G(n["n2"]))
-    # FFN second linear
-    ops.gemm(d_s2, sv["fd"], trans_a=True, out=G(n["f2_w"]))
-    ops.colsum(d_s2, out=G(n["f2_b"]))
-    # dpre = (d_s2 @ W2) * dropout_mask * gelu'(pre): dropout regenerated from the same stream + element ids
-    dpre = ops.gemm(d_s2, P[n["f2_w"]], dropout=dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1), mask_mode=ops.MASK_GELU_GRAD,
-                    mask_src=sv["pre"])
-    ops.gemm(dpre, sv["x1"], trans_a=True, out=G(n["f1_w"]))
-    ops.colsum(dpre, out=G(n["f1_b"]))
-    dx1 = ops.gemm(dpre, P[n["f1_w"]], residual=d_s2)
+    if sv["pre"] is None:         # fused tcgen05 FFN (forward saved only x1, s2, r2)
+        dx1 = ops.ffn_bwd(dy, sv["s2"], sv["r2"], P[n["n2"]], sv["x1"], P[n["f1_w"]], P[n["f1_b"]], P[n["f2_w"]],
+                          G(n["f1_w"]), G(n["f1_b"]), G(n["f2_w"]), G(n["f2_b"]), G(n["n2"]),
+                          dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1))
+    else:
+        d_s2 = ops.rmsnorm_bwd(dy, sv["s2"], P[n["n2"]], sv["r2"], G(n["n2"]))
+        # FFN second linear
+        ops.gemm(d_s2, sv["fd"], trans_a=True, out=G(n["f2_w"]))
+        ops.colsum(d_s2, out=G(n["f2_b"]))
+        # dpre = (d_s2 @ W2) * dropout_mask * gelu'(pre): dropout regenerated from the same stream + element ids
+        dpre = ops.gemm(d_s2, P[n["f2_w"]], dropout=dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1), mask_mode=ops.MASK_GELU_GRAD,
+                        mask_src=sv["pre"])
+        ops.gemm(dpre, sv["x1"], trans_a=True, out=G(n["f1_w"]))
+        ops.colsum(dpre, out=G(n["f1_b"]))
+        dx1 = ops.gemm(dpre, P[n["f1_w"]], residual=d_s2)
     d_s1 = ops.rmsnorm_bwd(dx1, sv["s1"], P[n["n1"]], sv["r1"], G(n["n1"]))
     ops.gemm(d_s1, sv["o"], trans_a=True, out=G(n["out_w"]))
     ops.colsum(d_s1, out=G(n["out_b"]))

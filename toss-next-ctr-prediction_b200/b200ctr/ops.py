@@ -368,6 +368,41 @@ def add_rmsnorm_fwd(a, b, w, eps=1e-6, save_sum=True):
     return s, y, r
 
 
+def ffn_fused_ok(hidden: int, D: int = 64) -> bool:
+    """Shapes the fused tcgen05 FFN kernels are built for (else: the unfused gemm composition)."""
+    return D == 64 and hidden % 128 == 0 and 0 < hidden <= 384
+
+
+def ffn_fwd(x1, w1, b1, w2, b2, n2w, dropout: Dropout = NO_DROP, eps=1e-6, save=True):
+    """Fused FFN block (bf16 tensor cores): returns (x2, s2, r2); s2/r2 are None when save=False."""
+    lib = _lib.load()
+    T, D = x1.shape
+    hidden = w1.shape[0]
+    x2 = torch.empty_like(x1)
+    s2 = torch.empty_like(x1) if save else None
+    r2 = torch.empty((T,), device=x1.device, dtype=torch.float32) if save else None
+    _run("ffn_fwd", lib.b200ctr_ffn_fwd, _p(_f32(x1)), _p(w1), _p(b1), _p(w2), _p(b2), _p(n2w), eps, T, D, hidden,
+         _p(s2), _p(r2), _p(x2), dropout, _stream())
+    _count()
+    return x2, s2, r2
+
+
+def ffn_bwd(dy, s2, r2, n2w, x1, w1, b1, w2, dw1, db1, dw2, db2, dn2, dropout: Dropout = NO_DROP):
+    """Backward of ffn_fwd; returns dx1 and overwrites the five parameter-gradient tensors."""
+    lib = _lib.load()
+    T, D = x1.shape
+    hidden = w1.shape[0]
+    nbytes = lib.b200ctr_ffn_bwd_workspace_bytes(T, hidden)
+    ws = torch.empty((nbytes,), device=x1.device, dtype=torch.uint8)
+    dx1 = torch.empty_like(x1)
+    for t in (dw1, db1, dw2, db2, dn2):
+        assert t.is_contiguous()
+    _run("ffn_bwd", lib.b200ctr_ffn_bwd, _p(_f32(dy)), _p(s2), _p(r2), _p(n2w), _p(x1), _p(w1), _p(b1), _p(w2), T, D, hidden,
+         _p(dx1), _p(dw1), _p(db1), _p(dw2), _p(db2), _p(dn2), _p(ws), dropout, _stream())
+    _count(3)
+    return dx1
+
+
 def rmsnorm_bwd(dy, s, w, r, dw, dx_add=None):
     """dw: zeroed (D,) tensor, accumulated into."""
     lib = _lib.load()

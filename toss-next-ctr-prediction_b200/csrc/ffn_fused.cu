@@ -1,0 +1,735 @@
+// Fused encoder FFN block on tcgen05 (the `amp: bf16` path of DAREEncoderLayer's second half, dare.py:67-69):
+//
+//     x2 = RMSNorm_n2( x1 + W2 . dropout(GELU(W1 . x1 + b1)) + b2 )
+//
+// The unfused composition streams the (tokens x ffn_hidden) pre-activation and activation through HBM
+// (2 x 755 MB per layer at B=8192, K=60) and is bound by that traffic at 27 FLOP/B; here a 128-token tile never
+// leaves the SM: both weight matrices stay resident in shared memory as bf16 UMMA operands, the hidden dimension
+// is walked in 64-wide chunks whose pre-activation lives in TMEM, the GELU/dropout epilogue writes the bf16
+// activation straight into the A-operand layout of the second contraction, and the residual + RMSNorm run on the
+// TMEM accumulator of that contraction with one thread per token row.
+//
+//   persistent CTA (one per SM), 13 warps:
+//     warps 0-3   stream x1 tiles (fp32 -> bf16 K-major core matrices, double buffered), then run the final
+//                 residual + RMSNorm epilogue of the previous tile (thread == token row == TMEM lane)
+//     warps 4-11  GELU epilogue: TMEM chunk -> +b1 -> erf-GELU -> dropout -> bf16 -> smem A operand of GEMM2
+//     warp  12    one thread issues every tcgen05.mma; tcgen05.commit -> mbarriers hand buffers back
+//
+// Shared-memory operand layout is the canonical SWIZZLE_NONE one of gemm_tc.cu: 8 x 16-byte core matrices,
+// k-group stride R*16 bytes ("LBO"), mn-group stride 128 bytes ("SBO").
+#include "tc_common.cuh"
+#include <algorithm>
+
+namespace b200ctr {
+
+constexpr int FF_D = 64;          // emb_dim
+constexpr int FF_TM = 128;        // tokens per tile (UMMA M)
+constexpr int FF_HC = 64;         // hidden chunk (UMMA N of GEMM1, K of GEMM2)
+constexpr int FF_NT = 13 * 32;
+constexpr int FF_A_BYTES = FF_TM * FF_D * 2;        // 16 KB: x1 tile, bf16
+constexpr int FF_FD_BYTES = FF_TM * FF_HC * 2;      // 16 KB: activation chunk, bf16
+constexpr int FF_WCHUNK = FF_HC * FF_D * 2;         // 8 KB of W1 or W2 per hidden chunk
+
+struct FfnBars {
+  unsigned long long a_full[2], a_empty[2], p_full, p_empty, fd_full[2], fd_empty[2], h2_full[2], h2_empty[2];
+  uint32_t tmem_base;
+};
+
+// W1 [hidden][64] fp32 -> per 64-row chunk a K-major B operand (N = hidden rows, K = d)
+__device__ __forceinline__ void ffn_stage_w1(unsigned char* w1s, const float* __restrict__ w1, int hidden, int tid, int nt) {
+  for (int u = tid; u < hidden * 8; u += nt) {
+    const int h = u >> 3, kc = u & 7;
+    const float4* p = reinterpret_cast<const float4*>(w1 + (size_t)h * FF_D + kc * 8);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    const int c = h >> 6, r = h & 63;
+    *reinterpret_cast<uint4*>(w1s + c * FF_WCHUNK + (kc * 8 + (r >> 3)) * 128 + (r & 7) * 16) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+}
+// W2 [64][hidden] fp32 -> per 64-column chunk a K-major B operand (N = d rows, K = hidden within the chunk)
+__device__ __forceinline__ void ffn_stage_w2(unsigned char* w2s, const float* __restrict__ w2, int hidden, int tid, int nt) {
+  const int hg_per_row = hidden >> 3;
+  for (int u = tid; u < FF_D * hg_per_row; u += nt) {
+    const int d = u / hg_per_row, hg = u % hg_per_row;
+    const float4* p = reinterpret_cast<const float4*>(w2 + (size_t)d * hidden + hg * 8);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    const int c = hg >> 3, kc = hg & 7;
+    *reinterpret_cast<uint4*>(w2s + c * FF_WCHUNK + (kc * 8 + (d >> 3)) * 128 + (d & 7) * 16) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+}
+// one 128-token x 64 fp32 tile -> bf16 K-major A operand (R = 128); 128 threads, rows >= T are zero-filled
+__device__ __forceinline__ void ffn_stage_tile(unsigned char* dst, const float* __restrict__ x, int64_t m0, int64_t T, int ptid) {
+  float4 va[8], vb[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int u = ptid + it * 128;
+    const int r = u & 127, c = u >> 7;
+    const int64_t m = m0 + r;
+    va[it] = make_float4(0.f, 0.f, 0.f, 0.f); vb[it] = va[it];
+    if (m < T) {
+      const float4* p = reinterpret_cast<const float4*>(x + m * FF_D + c * 8);
+      va[it] = __ldg(p); vb[it] = __ldg(p + 1);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int u = ptid + it * 128;
+    const int r = u & 127, c = u >> 7;
+    *reinterpret_cast<uint4*>(dst + (c * 16 + (r >> 3)) * 128 + (r & 7) * 16) =
+        make_uint4(pack_bf16(va[it].x, va[it].y), pack_bf16(va[it].z, va[it].w), pack_bf16(vb[it].x, vb[it].y), pack_bf16(vb[it].z, vb[it].w));
+  }
+}
+
+// D[tmem] (+)= A[smem, K-major, R_A rows] . B[smem, K-major, R_B rows]^T over `ksteps` K=16 steps
+__device__ __forceinline__ void ffn_mma_kk(uint32_t tmem_d, uint32_t a_base, uint32_t lbo_a, uint32_t b_base, uint32_t lbo_b,
+                                           uint32_t idesc, int ksteps, bool accumulate) {
+#pragma unroll 1
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint64_t da = make_desc(a_base + ks * 2 * lbo_a, lbo_a, 128);
+    const uint64_t db = make_desc(b_base + ks * 2 * lbo_b, lbo_b, 128);
+    umma_bf16(tmem_d, da, db, idesc, (accumulate || ks > 0) ? 1u : 0u);
+  }
+}
+
+__global__ void __launch_bounds__(FF_NT, 1)
+ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const float* __restrict__ b1,
+               const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ n2w, float eps,
+               int64_t T, int hidden, float* __restrict__ s2_out, float* __restrict__ r2_out, float* __restrict__ x2_out,
+               b200ctr_dropout_t drop) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int NC = hidden / FF_HC;
+  unsigned char* w1s = smem;
+  unsigned char* w2s = w1s + (size_t)NC * FF_WCHUNK;
+  unsigned char* as = w2s + (size_t)NC * FF_WCHUNK;            // [2][16 KB]
+  unsigned char* fds = as + 2 * FF_A_BYTES;                    // [2][16 KB]
+  float* b1s = reinterpret_cast<float*>(fds + 2 * FF_FD_BYTES);
+  float* b2s = b1s + hidden;
+  float* n2s = b2s + FF_D;
+  FfnBars* bars = reinterpret_cast<FfnBars*>(n2s + FF_D);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t tiles = (T + FF_TM - 1) / FF_TM;
+  const int n_it = (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);      // tiles of this CTA
+
+  if (warp == 12) tmem_alloc(&bars->tmem_base, 256);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bars->a_full[s]), 4); mbar_init(smem_u32(&bars->a_empty[s]), 1);
+      mbar_init(smem_u32(&bars->fd_full[s]), 8); mbar_init(smem_u32(&bars->fd_empty[s]), 1);
+      mbar_init(smem_u32(&bars->h2_full[s]), 1); mbar_init(smem_u32(&bars->h2_empty[s]), 4);
+    }
+    mbar_init(smem_u32(&bars->p_full), 1); mbar_init(smem_u32(&bars->p_empty), 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  ffn_stage_w1(w1s, w1, hidden, tid, FF_NT);
+  ffn_stage_w2(w2s, w2, hidden, tid, FF_NT);
+  for (int i = tid; i < hidden; i += FF_NT) b1s[i] = b1[i];
+  if (tid < FF_D) { b2s[tid] = b2[tid]; n2s[tid] = n2w[tid]; }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t P_COL = 0, H2_COL = 64;          // h2 buffers at columns 64 and 128
+
+  if (warp < 4) {
+    // ---------------------------------------- tile loader + final epilogue ----------------------------------
+    if (n_it > 0) {
+      ffn_stage_tile(as, x1, (int64_t)blockIdx.x * FF_TM, T, tid);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[0]));
+    }
+    for (int it = 0; it < n_it; ++it) {
+      if (it + 1 < n_it) {
+        const int nb = (it + 1) & 1;
+        if (it + 1 >= 2) mbar_wait(smem_u32(&bars->a_empty[nb]), (uint32_t)((((it + 1) >> 1) - 1) & 1));
+        ffn_stage_tile(as + nb * FF_A_BYTES, x1, ((int64_t)blockIdx.x + (int64_t)(it + 1) * gridDim.x) * FF_TM, T, tid);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[nb]));
+      }
+      const int hb = it & 1;
+      mbar_wait(smem_u32(&bars->h2_full[hb]), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      uint32_t v[64];
+      const uint32_t taddr = tmem + H2_COL + hb * 64 + ((uint32_t)(warp * 32) << 16);
+      tmem_ld32(taddr, v);
+      tmem_ld32(taddr + 32, v + 32);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->h2_empty[hb]));
+      const int64_t m = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM + warp * 32 + lane;
+      if (m < T) {
+        const float4* xr = reinterpret_cast<const float4*>(x1 + m * FF_D);
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 xv = __ldg(xr + j);
+          float s0 = __uint_as_float(v[4 * j]) + b2s[4 * j] + xv.x;
+          float s1 = __uint_as_float(v[4 * j + 1]) + b2s[4 * j + 1] + xv.y;
+          float s2 = __uint_as_float(v[4 * j + 2]) + b2s[4 * j + 2] + xv.z;
+          float s3 = __uint_as_float(v[4 * j + 3]) + b2s[4 * j + 3] + xv.w;
+          ss = fmaf(s0, s0, ss); ss = fmaf(s1, s1, ss); ss = fmaf(s2, s2, ss); ss = fmaf(s3, s3, ss);
+          v[4 * j] = __float_as_uint(s0); v[4 * j + 1] = __float_as_uint(s1);
+          v[4 * j + 2] = __float_as_uint(s2); v[4 * j + 3] = __float_as_uint(s3);
+        }
+        const float r = rsqrtf(ss * (1.f / FF_D) + eps);
+        if (r2_out) r2_out[m] = r;
+        if (s2_out) {
+          float4* sp = reinterpret_cast<float4*>(s2_out + m * FF_D);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            sp[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+        float4* yp = reinterpret_cast<float4*>(x2_out + m * FF_D);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          yp[j] = make_float4(n2s[4 * j] * __uint_as_float(v[4 * j]) * r, n2s[4 * j + 1] * __uint_as_float(v[4 * j + 1]) * r,
+                              n2s[4 * j + 2] * __uint_as_float(v[4 * j + 2]) * r, n2s[4 * j + 3] * __uint_as_float(v[4 * j + 3]) * r);
+      }
+    }
+  } else if (warp < 12) {
+    // ---------------------------------------- GELU epilogue -----------------------------------------------------
+    const int ew = warp - 4, q = ew & 3, half = ew >> 2;
+    const int r = q * 32 + lane;
+    uint32_t g = 0;
+    for (int it = 0; it < n_it; ++it) {
+      const int64_t m = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM + r;
+      for (int c = 0; c < NC; ++c, ++g) {
+        mbar_wait(smem_u32(&bars->p_full), g & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tmem + P_COL + half * 32 + ((uint32_t)(q * 32) << 16), v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->p_empty));
+        const int n0 = c * FF_HC + half * 32;
+        const uint64_t e0 = (uint64_t)m * (uint64_t)hidden + (uint64_t)n0;
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float f0 = gelu_erf(__uint_as_float(v[j]) + b1s[n0 + j]);
+          float f1 = gelu_erf(__uint_as_float(v[j + 1]) + b1s[n0 + j + 1]);
+          if (drop.p > 0.f) { f0 *= drop_scale(drop, e0 + j); f1 *= drop_scale(drop, e0 + j + 1); }
+          pk[j >> 1] = pack_bf16(f0, f1);
+        }
+        const int fb = g & 1;
+        if (g >= 2) mbar_wait(smem_u32(&bars->fd_empty[fb]), ((g >> 1) - 1) & 1);
+        unsigned char* dst = fds + fb * FF_FD_BYTES;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const int kg = half * 4 + j4;
+          *reinterpret_cast<uint4*>(dst + (kg * 16 + (r >> 3)) * 128 + (r & 7) * 16) =
+              make_uint4(pk[4 * j4], pk[4 * j4 + 1], pk[4 * j4 + 2], pk[4 * j4 + 3]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->fd_full[fb]));
+      }
+    }
+  } else if (lane == 0) {
+    // ---------------------------------------- MMA issuer ---------------------------------------------------------
+    const uint32_t idesc = umma_idesc(FF_TM, FF_HC, false, false);       // M=128, N=64, both operands K-major
+    const uint32_t as_u = smem_u32(as), fd_u = smem_u32(fds), w1_u = smem_u32(w1s), w2_u = smem_u32(w2s);
+    const uint32_t total = (uint32_t)n_it * (uint32_t)NC;
+    auto gemm2 = [&](uint32_t gg) {
+      const uint32_t it2 = gg / NC, c2 = gg % NC, fb = gg & 1, hb = it2 & 1;
+      mbar_wait(smem_u32(&bars->fd_full[fb]), (gg >> 1) & 1);
+      if (c2 == 0 && it2 >= 2) mbar_wait(smem_u32(&bars->h2_empty[hb]), ((it2 >> 1) - 1) & 1);
+      tc_fence_after();
+      ffn_mma_kk(tmem + H2_COL + hb * 64, fd_u + fb * FF_FD_BYTES, FF_TM * 16, w2_u + c2 * FF_WCHUNK, FF_D * 16, idesc,
+                 FF_HC / 16, c2 > 0);
+      umma_commit(smem_u32(&bars->fd_empty[fb]));
+      if (c2 == (uint32_t)NC - 1) umma_commit(smem_u32(&bars->h2_full[hb]));
+    };
+    for (uint32_t g = 0; g < total; ++g) {
+      const uint32_t it = g / NC, c = g % NC, ab = it & 1;
+      if (c == 0) mbar_wait(smem_u32(&bars->a_full[ab]), (it >> 1) & 1);
+      if (g > 0) mbar_wait(smem_u32(&bars->p_empty), (g - 1) & 1);
+      tc_fence_after();
+      ffn_mma_kk(tmem + P_COL, as_u + ab * FF_A_BYTES, FF_TM * 16, w1_u + c * FF_WCHUNK, FF_HC * 16, idesc, FF_D / 16, false);
+      umma_commit(smem_u32(&bars->p_full));
+      if (c == (uint32_t)NC - 1) umma_commit(smem_u32(&bars->a_empty[ab]));
+      if (g > 0) gemm2(g - 1);
+    }
+    if (total > 0) gemm2(total - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    __syncwarp();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+
+// =============================================================================================================
+// Backward, kernel 1 of 2 (per 128-token tile; weight gradients accumulate in TMEM across the persistent loop):
+//   d_s2  = RMSNorm'(dy; s2, r2, n2)                                  (loader warps, fp32, also -> HBM for kernel 2)
+//   P     = x1 . W1_c^T (+b1)   Q = d_s2 . W2[:, c]                   (two 128x64x64 MMAs per 64-wide hidden chunk)
+//   fd    = dropout(GELU(P)) ;  dpre = Q * mask * GELU'(P)            (epilogue warps; dropout mask regenerated)
+//   dW2^T[blk] += fd^T . d_s2 ;  dW1[blk] += dpre^T . x1              (M = 128 hidden rows, K = 128 tokens; the bf16
+//        activation / gradient buffers written K-major by the epilogue are re-read MN-major: same bytes,
+//        LBO/SBO exchanged in the descriptor, no transpose)
+//   dpre  -> HBM as the bf16 shared-memory image (kernel 2 = dx1 = dpre . W1 + d_s2 bulk-copies it back)
+//   db1 (transpose-reduce over the 32 rows of a warp), db2, dn2 (column-owner lanes of the loader warps)
+// TMEM: P 64 | Q 64 | dW1 hidden/2 | dW2^T hidden/2 columns = 512 at ffn_hidden = 384.
+// =============================================================================================================
+struct FfnBwdBars {
+  unsigned long long in_full[2], in_empty[2], pq_full, pq_empty, blk_full, blk_empty, done;
+  uint32_t tmem_base;
+};
+constexpr int FF_IN_BYTES = 2 * FF_A_BYTES;            // x1 tile + d_s2 tile (bf16)
+constexpr int FF_BLK_BYTES = FF_TM * 128 * 2;          // 32 KB: 128 tokens x 128 hidden, bf16
+
+// W2 [64][hidden] fp32 -> per 64-column chunk an MN-major B operand (N = hidden within the chunk, K = d)
+__device__ __forceinline__ void ffn_stage_w2_mn(unsigned char* w2s, const float* __restrict__ w2, int hidden, int tid, int nt) {
+  const int hg_per_row = hidden >> 3;
+  for (int u = tid; u < FF_D * hg_per_row; u += nt) {
+    const int d = u / hg_per_row, hg = u % hg_per_row;
+    const float4* p = reinterpret_cast<const float4*>(w2 + (size_t)d * hidden + hg * 8);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    const int c = hg >> 3, ng = hg & 7;
+    *reinterpret_cast<uint4*>(w2s + c * FF_WCHUNK + ((d >> 3) * 8 + ng) * 128 + (d & 7) * 16) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+}
+
+// lane j <- sum over the warp's 32 lanes of v[j]  (31 shuffles; v is destroyed)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(FF_NT, 1)
+ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, const float* __restrict__ r2,
+                const float* __restrict__ n2w, const float* __restrict__ x1, const float* __restrict__ w1,
+                const float* __restrict__ b1, const float* __restrict__ w2, int64_t T, int hidden,
+                float* __restrict__ ds2_out, unsigned char* __restrict__ dpre_spill, float* __restrict__ ws,
+                b200ctr_dropout_t drop) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int NC = hidden / FF_HC, NB = hidden / 128;
+  unsigned char* w1s = smem;
+  unsigned char* w2s = w1s + (size_t)NC * FF_WCHUNK;
+  unsigned char* ins = w2s + (size_t)NC * FF_WCHUNK;           // [2][x1 16 KB | d_s2 16 KB]
+  unsigned char* fdb = ins + 2 * FF_IN_BYTES;                  // 32 KB activation block
+  unsigned char* dpb = fdb + FF_BLK_BYTES;                     // 32 KB dpre block
+  float* b1s = reinterpret_cast<float*>(dpb + FF_BLK_BYTES);
+  FfnBwdBars* bars = reinterpret_cast<FfnBwdBars*>(b1s + hidden);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t tiles = (T + FF_TM - 1) / FF_TM;
+  const int n_it = (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  // per-CTA partial sums: dW1 [hidden][64] | dW2^T [hidden][64] | db1 [4][hidden] | db2 [4][64] | dn2 [4][64]
+  const size_t ws_per_cta = (size_t)2 * hidden * FF_D + (size_t)4 * hidden + 8 * FF_D;
+  float* wsc = ws + (size_t)blockIdx.x * ws_per_cta;
+  float* ws_db1 = wsc + (size_t)2 * hidden * FF_D;
+  float* ws_db2 = ws_db1 + (size_t)4 * hidden;
+  float* ws_dn2 = ws_db2 + 4 * FF_D;
+
+  if (warp == 12) tmem_alloc(&bars->tmem_base, 512);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->in_full[s]), 4); mbar_init(smem_u32(&bars->in_empty[s]), 1); }
+    mbar_init(smem_u32(&bars->pq_full), 1); mbar_init(smem_u32(&bars->pq_empty), 8);
+    mbar_init(smem_u32(&bars->blk_full), 8); mbar_init(smem_u32(&bars->blk_empty), 1);
+    mbar_init(smem_u32(&bars->done), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  ffn_stage_w1(w1s, w1, hidden, tid, FF_NT);
+  ffn_stage_w2_mn(w2s, w2, hidden, tid, FF_NT);
+  for (int i = tid; i < hidden; i += FF_NT) b1s[i] = b1[i];
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t P_COL = 0, Q_COL = 64, DW1_COL = 128, DW2_COL = 128 + (uint32_t)NB * 64;
+
+  if (warp < 4) {
+    // ------------------------------- loader: x1 tile + d_s2 = RMSNorm'(dy) -----------------------------------
+    const float2 nw = reinterpret_cast<const float2*>(n2w)[lane];
+    float2 dn_acc = make_float2(0.f, 0.f), db_acc = make_float2(0.f, 0.f);
+    for (int it = 0; it < n_it; ++it) {
+      const int ib = it & 1;
+      if (it >= 2) mbar_wait(smem_u32(&bars->in_empty[ib]), (uint32_t)(((it >> 1) - 1) & 1));
+      const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM;
+      unsigned char* xs = ins + ib * FF_IN_BYTES;
+      unsigned char* dss = xs + FF_A_BYTES;
+      ffn_stage_tile(xs, x1, m0, T, tid);
+#pragma unroll 1
+      for (int rr = 0; rr < 32; rr += 4) {
+        float2 d[4], s[4];
+        float r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t m = m0 + warp * 32 + rr + u;
+          d[u] = make_float2(0.f, 0.f); s[u] = d[u]; r[u] = 0.f;
+          if (m < T) {
+            d[u] = __ldg(reinterpret_cast<const float2*>(dy + m * FF_D) + lane);
+            s[u] = __ldg(reinterpret_cast<const float2*>(s2 + m * FF_D) + lane);
+            r[u] = __ldg(r2 + m);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = warp * 32 + rr + u;
+          const int64_t m = m0 + row;
+          const float2 g = make_float2(d[u].x * nw.x, d[u].y * nw.y);
+          const float dot = warp_sum(g.x * s[u].x + g.y * s[u].y) * (1.f / FF_D);
+          const float c = r[u] * r[u] * r[u] * dot;
+          const float2 o = make_float2(r[u] * g.x - s[u].x * c, r[u] * g.y - s[u].y * c);
+          dn_acc.x = fmaf(d[u].x * s[u].x, r[u], dn_acc.x);
+          dn_acc.y = fmaf(d[u].y * s[u].y, r[u], dn_acc.y);
+          db_acc.x += o.x; db_acc.y += o.y;
+          if (m < T) reinterpret_cast<float2*>(ds2_out + m * FF_D)[lane] = o;
+          *reinterpret_cast<uint32_t*>(dss + ((lane >> 2) * 16 + (row >> 3)) * 128 + (row & 7) * 16 + (lane & 3) * 4) = pack_bf16(o.x, o.y);
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->in_full[ib]));
+    }
+    reinterpret_cast<float2*>(ws_db2 + warp * FF_D)[lane] = db_acc;
+    reinterpret_cast<float2*>(ws_dn2 + warp * FF_D)[lane] = dn_acc;
+  } else if (warp < 12) {
+    // ------------------------------- epilogue: fd, dpre, db1 ---------------------------------------------------
+    const int ew = warp - 4, q = ew & 3, half = ew >> 2;
+    const int r = q * 32 + lane;
+    float db1_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t g = 0;
+    for (int it = 0; it < n_it; ++it) {
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+      const int64_t m = tile * FF_TM + r;
+      for (int c = 0; c < NC; ++c, ++g) {
+        mbar_wait(smem_u32(&bars->pq_full), g & 1);
+        tc_fence_after();
+        uint32_t pv[32], qv[32];
+        const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+        tmem_ld32(tmem + P_COL + half * 32 + lane_bits, pv);
+        tmem_ld32(tmem + Q_COL + half * 32 + lane_bits, qv);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->pq_empty));
+        const int n0 = c * FF_HC + half * 32;
+        const uint64_t e0 = (uint64_t)m * (uint64_t)hidden + (uint64_t)n0;
+        uint32_t fpk[16], dpk[16];
+        float dp[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float pre = __uint_as_float(pv[j]) + b1s[n0 + j];
+          float cdf, ex;
+          gelu_parts(pre, cdf, ex);
+          const float ds = (drop.p > 0.f) ? drop_scale(drop, e0 + j) : 1.f;
+          const float f = pre * cdf * ds;
+          dp[j] = __uint_as_float(qv[j]) * ds * fmaf(pre * 0.39894228040143268f, ex, cdf);
+          pv[j] = __float_as_uint(f);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          fpk[j >> 1] = pack_bf16(__uint_as_float(pv[j]), __uint_as_float(pv[j + 1]));
+          dpk[j >> 1] = pack_bf16(dp[j], dp[j + 1]);
+        }
+        const uint32_t bk = (uint32_t)it * NB + (uint32_t)(c >> 1);
+        if ((c & 1) == 0 && bk >= 1) mbar_wait(smem_u32(&bars->blk_empty), (bk - 1) & 1);
+        unsigned char* spill = dpre_spill + ((size_t)tile * NB + (c >> 1)) * FF_BLK_BYTES;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const int kg = (c & 1) * 8 + half * 4 + j4;
+          const uint32_t off = (uint32_t)((kg * 16 + (r >> 3)) * 128 + (r & 7) * 16);
+          const uint4 dv = make_uint4(dpk[4 * j4], dpk[4 * j4 + 1], dpk[4 * j4 + 2], dpk[4 * j4 + 3]);
+          *reinterpret_cast<uint4*>(fdb + off) = make_uint4(fpk[4 * j4], fpk[4 * j4 + 1], fpk[4 * j4 + 2], fpk[4 * j4 + 3]);
+          *reinterpret_cast<uint4*>(dpb + off) = dv;
+          *reinterpret_cast<uint4*>(spill + off) = dv;
+        }
+        if (c & 1) {
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->blk_full));
+        }
+        const float cs = warp_colsum32(dp, lane);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) db1_acc[k] += (k == c) ? cs : 0.f;
+      }
+    }
+    // weight-gradient accumulators: TMEM -> this CTA's partial-sum slab
+    mbar_wait(smem_u32(&bars->done), 0);
+    tc_fence_after();
+    for (int which = 0; which < 2; ++which) {
+      for (int b = 0; b < NB; ++b) {
+        uint32_t v[32];
+        tmem_ld32(tmem + (which ? DW2_COL : DW1_COL) + b * 64 + half * 32 + ((uint32_t)(q * 32) << 16), v);
+        float4* dst = reinterpret_cast<float4*>(wsc + ((size_t)which * hidden + b * 128 + r) * FF_D + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      }
+    }
+    for (int c = 0; c < NC; ++c) {
+      float vsel = 0.f;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) vsel = (k == c) ? db1_acc[k] : vsel;
+      ws_db1[(size_t)q * hidden + c * FF_HC + half * 32 + lane] = vsel;
+    }
+  } else if (lane == 0) {
+    // ------------------------------- MMA issuer ---------------------------------------------------------------------
+    const uint32_t idesc_p = umma_idesc(FF_TM, FF_HC, false, false);     // x1 (K-major) . W1 chunk (K-major)
+    const uint32_t idesc_q = umma_idesc(FF_TM, FF_HC, false, true);      // d_s2 (K-major) . W2 chunk (MN-major)
+    const uint32_t idesc_w = umma_idesc(128, FF_D, true, true);          // block^T (MN view) . tile (MN view)
+    const uint32_t in_u = smem_u32(ins), w1_u = smem_u32(w1s), w2_u = smem_u32(w2s), fd_u = smem_u32(fdb), dp_u = smem_u32(dpb);
+    const uint32_t total = (uint32_t)n_it * (uint32_t)NC;
+    auto wgrad = [&](uint32_t bk) {
+      const uint32_t it2 = bk / NB, b2 = bk % NB, ib2 = it2 & 1;
+      mbar_wait(smem_u32(&bars->blk_full), bk & 1);
+      tc_fence_after();
+      const uint32_t xs_u = in_u + ib2 * FF_IN_BYTES, ds_u = xs_u + FF_A_BYTES;
+#pragma unroll 1
+      for (int ks = 0; ks < 8; ++ks) {        // K = 128 tokens; MN-major views: k-group stride 128 B, mn-group stride 2048 B
+        const uint32_t acc = (it2 > 0 || ks > 0) ? 1u : 0u;
+        umma_bf16(tmem + DW2_COL + b2 * 64, make_desc(fd_u + ks * 256, 128, 2048), make_desc(ds_u + ks * 256, 128, 2048), idesc_w, acc);
+        umma_bf16(tmem + DW1_COL + b2 * 64, make_desc(dp_u + ks * 256, 128, 2048), make_desc(xs_u + ks * 256, 128, 2048), idesc_w, acc);
+      }
+      umma_commit(smem_u32(&bars->blk_empty));
+      if (b2 == (uint32_t)NB - 1) umma_commit(smem_u32(&bars->in_empty[ib2]));
+    };
+    for (uint32_t g = 0; g < total; ++g) {
+      const uint32_t it = g / NC, c = g % NC, ib = it & 1;
+      if (c == 0) mbar_wait(smem_u32(&bars->in_full[ib]), (it >> 1) & 1);
+      if (g > 0) mbar_wait(smem_u32(&bars->pq_empty), (g - 1) & 1);
+      tc_fence_after();
+      const uint32_t xs_u = in_u + ib * FF_IN_BYTES, ds_u = xs_u + FF_A_BYTES;
+      ffn_mma_kk(tmem + P_COL, xs_u, FF_TM * 16, w1_u + c * FF_WCHUNK, FF_HC * 16, idesc_p, FF_D / 16, false);
+      ffn_mma_kk(tmem + Q_COL, ds_u, FF_TM * 16, w2_u + c * FF_WCHUNK, FF_HC * 16, idesc_q, FF_D / 16, false);
+      umma_commit(smem_u32(&bars->pq_full));
+      if (g > 0 && ((g - 1) % NC) % 2 == 1) wgrad((g - 1) / 2);
+    }
+    if (total > 0) wgrad(total / 2 - 1);
+    umma_commit(smem_u32(&bars->done));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    __syncwarp();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// deterministic cross-CTA reduction of kernel 1's partial sums (and the dW2^T -> dW2 transpose)
+__global__ void ffn_bwd_reduce_kernel(const float* __restrict__ ws, int n_cta, int hidden, float* __restrict__ dw1,
+                                      float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2,
+                                      float* __restrict__ dn2) {
+  const size_t per = (size_t)2 * hidden * FF_D + (size_t)4 * hidden + 8 * FF_D;
+  const int HD = hidden * FF_D;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * HD) {
+    float acc = 0.f;
+    for (int c = 0; c < n_cta; ++c) acc += ws[(size_t)c * per + i];
+    if (i < HD) dw1[i] = acc;
+    else { const int j = i - HD, h = j / FF_D, d = j % FF_D; dw2[(size_t)d * hidden + h] = acc; }
+  } else if (i < 2 * HD + hidden) {
+    const int h = i - 2 * HD;
+    float acc = 0.f;
+    for (int c = 0; c < n_cta; ++c)
+      for (int qq = 0; qq < 4; ++qq) acc += ws[(size_t)c * per + 2 * HD + (size_t)qq * hidden + h];
+    db1[h] = acc;
+  } else if (i < 2 * HD + hidden + 2 * FF_D) {
+    const int j = i - 2 * HD - hidden, which = j / FF_D, d = j % FF_D;
+    float acc = 0.f;
+    for (int c = 0; c < n_cta; ++c)
+      for (int w = 0; w < 4; ++w) acc += ws[(size_t)c * per + 2 * HD + (size_t)4 * hidden + which * 4 * FF_D + w * FF_D + d];
+    (which ? dn2 : db2)[d] = acc;
+  }
+}
+
+// =============================================================================================================
+// Backward, kernel 2 of 2:  dx1 = dpre . W1 + d_s2.   dpre tiles come back from HBM with one bulk (TMA) copy per
+// 32 KB block, already in UMMA operand order.  6 warps: 0 = bulk-copy producer, 1 = MMA, 2-5 = epilogue.
+// =============================================================================================================
+constexpr int FF2_STAGES = 4;
+constexpr int FF2_NT = 6 * 32;
+struct Ffn2Bars {
+  unsigned long long full[FF2_STAGES], empty[FF2_STAGES], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(FF2_NT, 1)
+ffn_bwd2_kernel(const unsigned char* __restrict__ dpre_spill, const float* __restrict__ w1, const float* __restrict__ ds2,
+                int64_t T, int hidden, float* __restrict__ dx1) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int NB = hidden / 128;
+  unsigned char* w1s = smem;                                   // NB x 16 KB: MN-major B operand (N = d, K = hidden)
+  unsigned char* ring = w1s + (size_t)NB * 16384;              // FF2_STAGES x 32 KB
+  Ffn2Bars* bars = reinterpret_cast<Ffn2Bars*>(ring + (size_t)FF2_STAGES * FF_BLK_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t tiles = (T + FF_TM - 1) / FF_TM;
+  const int n_it = (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+  if (warp == 1) tmem_alloc(&bars->tmem_base, 128);
+  if (tid == 0) {
+    for (int s = 0; s < FF2_STAGES; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->acc_full[s]), 1); mbar_init(smem_u32(&bars->acc_empty[s]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // W1 [hidden][64]: unit (hidden row h, d-group ng) -> core (k-group h/8, n-group ng), row h%8, 8 consecutive d
+  for (int u = tid; u < hidden * 8; u += FF2_NT) {
+    const int h = u >> 3, ng = u & 7;
+    const float4* p = reinterpret_cast<const float4*>(w1 + (size_t)h * FF_D + ng * 8);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    const int blk = h >> 7, hh = h & 127;
+    *reinterpret_cast<uint4*>(w1s + blk * 16384 + ((hh >> 3) * 8 + ng) * 128 + (hh & 7) * 16) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int it = 0; it < n_it; ++it) {
+        const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+        for (int b = 0; b < NB; ++b, ++g) {
+          const uint32_t s = g % FF2_STAGES, use = g / FF2_STAGES;
+          if (use > 0) mbar_wait(smem_u32(&bars->empty[s]), (use - 1) & 1);
+          const uint32_t bar = smem_u32(&bars->full[s]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)FF_BLK_BYTES) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(ring + (size_t)s * FF_BLK_BYTES)), "l"(dpre_spill + ((size_t)tile * NB + b) * FF_BLK_BYTES),
+                         "r"((uint32_t)FF_BLK_BYTES), "r"(bar) : "memory");
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(FF_TM, FF_D, false, true);
+      const uint32_t ring_u = smem_u32(ring), w1_u = smem_u32(w1s);
+      uint32_t g = 0;
+      for (int it = 0; it < n_it; ++it) {
+        const uint32_t ab = it & 1;
+        if (it >= 2) mbar_wait(smem_u32(&bars->acc_empty[ab]), ((it >> 1) - 1) & 1);
+        for (int b = 0; b < NB; ++b, ++g) {
+          const uint32_t s = g % FF2_STAGES;
+          mbar_wait(smem_u32(&bars->full[s]), (g / FF2_STAGES) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks)
+            umma_bf16(tmem + ab * 64, make_desc(ring_u + s * FF_BLK_BYTES + ks * 2 * 2048, 2048, 128),
+                      make_desc(w1_u + b * 16384 + ks * 2 * 1024, 1024, 128), idesc, (b > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&bars->empty[s]));
+        }
+        umma_commit(smem_u32(&bars->acc_full[ab]));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t ab = it & 1;
+      mbar_wait(smem_u32(&bars->acc_full[ab]), (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[64];
+      const uint32_t taddr = tmem + ab * 64 + ((uint32_t)(q * 32) << 16);
+      tmem_ld32(taddr, v);
+      tmem_ld32(taddr + 32, v + 32);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
+      const int64_t m = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM + q * 32 + lane;
+      if (m < T) {
+        const float4* rp = reinterpret_cast<const float4*>(ds2 + m * FF_D);
+        float4* op = reinterpret_cast<float4*>(dx1 + m * FF_D);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 a = __ldg(rp + j);
+          op[j] = make_float4(__uint_as_float(v[4 * j]) + a.x, __uint_as_float(v[4 * j + 1]) + a.y,
+                              __uint_as_float(v[4 * j + 2]) + a.z, __uint_as_float(v[4 * j + 3]) + a.w);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+static size_t ffn_fwd_smem(int hidden) {
+  return (size_t)2 * (hidden / FF_HC) * FF_WCHUNK + 2 * FF_A_BYTES + 2 * FF_FD_BYTES + ((size_t)hidden + 2 * FF_D) * 4 + sizeof(FfnBars) + 16;
+}
+
+}  // namespace b200ctr
+
+using namespace b200ctr;
+
+extern "C" int b200ctr_ffn_fwd(const float* x1, const float* w1, const float* b1, const float* w2, const float* b2,
+                               const float* n2w, float eps, int64_t T, int D, int hidden, float* s2_out, float* r2_out,
+                               float* x2_out, b200ctr_dropout_t drop, void* stream) {
+  B200_REQUIRE(x1 && w1 && b1 && w2 && b2 && n2w && x2_out, B200CTR_E_INVALID_ARG, "ffn_fwd: null pointer");
+  B200_REQUIRE(D == FF_D, B200CTR_E_UNSUPPORTED_SHAPE, "ffn_fwd: D=%d unsupported (64 only)", D);
+  B200_REQUIRE(hidden > 0 && hidden % FF_HC == 0 && hidden <= 512, B200CTR_E_UNSUPPORTED_SHAPE,
+               "ffn_fwd: ffn_hidden=%d unsupported (multiple of 64, <= 512)", hidden);
+  if (T == 0) return B200CTR_OK;
+  const size_t smem = ffn_fwd_smem(hidden);
+  cudaError_t e = cudaFuncSetAttribute(ffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ffn_fwd smem)");
+  const int64_t tiles = ceil_div(T, (int64_t)FF_TM);
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)num_sms());
+  ffn_fwd_kernel<<<grid, FF_NT, smem, as_stream(stream)>>>(x1, w1, b1, w2, b2, n2w, eps, T, hidden, s2_out, r2_out, x2_out, drop);
+  B200_LAUNCH_CHECK("ffn_fwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int64_t b200ctr_ffn_bwd_workspace_bytes(int64_t T, int hidden) {
+  if (T <= 0 || hidden <= 0) return 0;
+  const int64_t tiles = ceil_div(T, (int64_t)FF_TM);
+  const int64_t spill = tiles * (hidden / 128) * (int64_t)FF_BLK_BYTES;
+  const int64_t per_cta = ((int64_t)2 * hidden * FF_D + (int64_t)4 * hidden + 8 * FF_D) * 4;
+  return spill + per_cta * num_sms() + T * FF_D * 4;
+}
+
+extern "C" int b200ctr_ffn_bwd(const float* dy, const float* s2, const float* r2, const float* n2w, const float* x1,
+                               const float* w1, const float* b1, const float* w2, int64_t T, int D, int hidden,
+                               float* dx1, float* dw1, float* db1, float* dw2, float* db2, float* dn2,
+                               void* workspace, b200ctr_dropout_t drop, void* stream) {
+  B200_REQUIRE(dy && s2 && r2 && n2w && x1 && w1 && b1 && w2 && dx1 && dw1 && db1 && dw2 && db2 && dn2 && workspace,
+               B200CTR_E_INVALID_ARG, "ffn_bwd: null pointer");
+  B200_REQUIRE(D == FF_D, B200CTR_E_UNSUPPORTED_SHAPE, "ffn_bwd: D=%d unsupported (64 only)", D);
+  B200_REQUIRE(hidden > 0 && hidden % 128 == 0 && hidden <= 384, B200CTR_E_UNSUPPORTED_SHAPE,
+               "ffn_bwd: ffn_hidden=%d unsupported (multiple of 128, <= 384)", hidden);
+  B200_REQUIRE(T > 0, B200CTR_E_INVALID_ARG, "ffn_bwd: empty input");
+  cudaStream_t st = as_stream(stream);
+  const int64_t tiles = ceil_div(T, (int64_t)FF_TM);
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)num_sms());
+  const int NB = hidden / 128;
+  unsigned char* spill = (unsigned char*)workspace;
+  float* ws = (float*)(spill + (size_t)tiles * NB * FF_BLK_BYTES);
+  const size_t per_cta = (size_t)2 * hidden * FF_D + (size_t)4 * hidden + 8 * FF_D;
+  float* ds2 = ws + per_cta * (size_t)num_sms();
+  const size_t smem1 = (size_t)2 * (hidden / FF_HC) * FF_WCHUNK + 2 * FF_IN_BYTES + 2 * FF_BLK_BYTES + (size_t)hidden * 4 + sizeof(FfnBwdBars) + 16;
+  cudaError_t e = cudaFuncSetAttribute(ffn_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ffn_bwd1 smem)");
+  ffn_bwd1_kernel<<<grid, FF_NT, smem1, st>>>(dy, s2, r2, n2w, x1, w1, b1, w2, T, hidden, ds2, spill, ws, drop);
+  B200_LAUNCH_CHECK("ffn_bwd1_kernel");
+  const int n_out = 2 * hidden * FF_D + hidden + 2 * FF_D;
+  ffn_bwd_reduce_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(ws, grid, hidden, dw1, db1, dw2, db2, dn2);
+  B200_LAUNCH_CHECK("ffn_bwd_reduce_kernel");
+  const size_t smem2 = (size_t)NB * 16384 + (size_t)FF2_STAGES * FF_BLK_BYTES + sizeof(Ffn2Bars) + 16;
+  e = cudaFuncSetAttribute(ffn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ffn_bwd2 smem)");
+  ffn_bwd2_kernel<<<grid, FF2_NT, smem2, st>>>(spill, w1, ds2, T, hidden, dx1);
+  B200_LAUNCH_CHECK("ffn_bwd2_kernel");
+  return B200CTR_OK;
+}
