@@ -74,7 +74,7 @@ typedef struct {
   int act;
   float* pre_out;          /* [M,N] (ld_pre) or NULL */
   int64_t ld_pre;
-  b200ctr_dropout_t drop;  /* applied after act (element id = m*N + n) */
+  b200ctr_dropout_t drop;  /* applied after act (row key = m, column = n) */
   int mask_mode;
   const float* mask_src;   /* [M,N] (ld_mask) */
   int64_t ld_mask;
@@ -160,6 +160,13 @@ int b200ctr_attn_fwd(const float* qkv, const float* relmean, int max_len, int64_
 int b200ctr_attn_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
                      const float* d_o, int64_t B, int K, int H, int D, float* dqkv, float* drelmean,
                      b200ctr_dropout_t drop, void* stream);
+/* Same contracts on the warp-level tensor cores (mma.sync m16n8k8, TF32 operands, fp32 accumulation): the
+ * `amp: bf16` path.  head_dim 8 == the k extent of the instruction; dropout masks are identical to the fp32 kernels'. */
+int b200ctr_attn_tc_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D,
+                        float* o, float* lse, b200ctr_dropout_t drop, void* stream);
+int b200ctr_attn_tc_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
+                        const float* d_o, int64_t B, int K, int H, int D, float* dqkv, float* drelmean,
+                        b200ctr_dropout_t drop, void* stream);
 int b200ctr_add_rmsnorm_fwd(const float* a, const float* b, const float* w, float eps, int64_t M, int D,
                             float* s_out, float* y_out, float* r_out, void* stream);
 /* dx = rmsnorm'(dy) (+ dx_add) ; dw[D] += sum_m dy*s*r (atomic; caller zeroes dw) */
@@ -172,7 +179,7 @@ int b200ctr_relmean_bwd(const float* drelmean, int T, int H, float* drel, void* 
 /* ---- fused encoder FFN block on tcgen05 (dare.py:67-69; the `amp: bf16` path) -----------------------------
  * x2 = RMSNorm_n2(s2), s2 = x1 + W2.dropout(GELU(W1.x1 + b1)) + b2 ; operands rounded to bf16, fp32 accumulation
  * in TMEM; the (T, hidden) activation never reaches HBM.  w1 (hidden, D), w2 (D, hidden) row-major as in the
- * reference's nn.Linear; dropout element id = m*hidden + n (identical to the unfused gemm epilogue, so the
+ * reference's nn.Linear; dropout element = (row m, column n) (identical to the unfused gemm epilogue, so the
  * backward regenerates the same mask).  s2_out / r2_out (saved for the backward) may be NULL.
  * D == 64, hidden % 64 == 0, hidden <= 512.                                                                 */
 int b200ctr_ffn_fwd(const float* x1, const float* w1, const float* b1, const float* w2, const float* b2,

@@ -337,3 +337,28 @@ def test_ffn_bwd_fused_matches_unfused(dev, T, hidden, p):
     for name, a, b in (("dx1", dx1, dx1u), ("dw1", dw1, dw1u), ("db1", db1, db1u), ("dw2", dw2, dw2u), ("db2", db2, db2u),
                        ("dn2", dn2, dn2u)):
         assert max_err_scaled(a.cpu(), b.cpu()) < 5e-3, name
+
+
+# ---- TF32 tensor-core attention (csrc/attn_tc.cu) vs the exact fp32 CUDA-core kernels (same dropout masks) ----------
+@pytest.mark.parametrize("B,K,p", [(3, 60, 0.0), (5, 60, 0.1), (2, 100, 0.1), (2, 148, 0.1), (4, 5, 0.0), (3, 16, 0.1), (2, 80, 0.0), (1, 1, 0.0)])
+def test_attn_tc_matches_fp32_kernels(dev, B, K, p):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(100 * B + K)
+    qkv = (_rand(g, B * K, 192) * 0.8).to(dev)
+    relmean = (_rand(g, 2 * K + 1) * 0.5).to(dev)
+    d_o = _rand(g, B * K, 64).to(dev)
+    dr = ops.drop(p, 99, 3)
+    o_ref, lse_ref = ops.attn_fwd(qkv, relmean, K, B, K, 8, 64, dr, tc=False)
+    o, lse = ops.attn_fwd(qkv, relmean, K, B, K, 8, 64, dr, tc=True)
+    assert max_err_scaled(o.cpu(), o_ref.cpu()) < 3e-3
+    assert max_err_scaled(lse.cpu(), lse_ref.cpu()) < 3e-3
+    drel_ref = torch.zeros_like(relmean)
+    drel = torch.zeros_like(relmean)
+    dq_ref = ops.attn_bwd(qkv, relmean, K, o_ref, lse_ref, d_o, B, K, 8, 64, drel_ref, dr, tc=False)
+    dq = ops.attn_bwd(qkv, relmean, K, o_ref, lse_ref, d_o, B, K, 8, 64, drel, dr, tc=True)
+    # dq: TF32 operands; dk / dv: bf16 P^T / dS^T operands (the amp: bf16 matmul policy).  Scale by the largest gradient
+    # of the call so that exactly-zero reference blocks (K = 1: softmax over one key) compare in absolute terms.
+    gmax = float(dq_ref.abs().max()) + 1e-30
+    for sl, name, tol in ((slice(0, 64), "dq", 5e-3), (slice(64, 128), "dk", 1.5e-2), (slice(128, 192), "dv", 1.5e-2)):
+        assert float((dq[:, sl] - dq_ref[:, sl]).abs().max()) / gmax < tol, name
+    assert float((drel - drel_ref).abs().max()) / (float(drel_ref.abs().max()) + gmax) < 5e-3

@@ -339,20 +339,30 @@ def retrieve_bwd(tok, q, emb_att, dsel_rep, dvals, pad_id, datt_dense=None, drep
     return dq
 
 
-def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP):
+def _attn_tc(tc: Optional[bool], K: int, H: int, D: int) -> bool:
+    """bf16 precision mode runs attention on the tensor cores (TF32 mma.sync); fp32 mode keeps the exact CUDA-core kernels."""
+    if tc is None:
+        tc = _PRECISION == "bf16"
+    return bool(tc) and D == 64 and H == 8 and K <= 160
+
+
+def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP, tc: Optional[bool] = None):
     lib = _lib.load()
     o = torch.empty((B * K, D), device=qkv.device, dtype=torch.float32)
     lse = torch.empty((B, H, K), device=qkv.device, dtype=torch.float32)
-    _run("attn_fwd", lib.b200ctr_attn_fwd, _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), dropout, _stream())
+    use_tc = _attn_tc(tc, K, H, D)
+    _run("attn_tc_fwd" if use_tc else "attn_fwd", lib.b200ctr_attn_tc_fwd if use_tc else lib.b200ctr_attn_fwd,
+         _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), dropout, _stream())
     _count()
     return o, lse
 
 
-def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=NO_DROP):
+def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=NO_DROP, tc: Optional[bool] = None):
     lib = _lib.load()
     dqkv = torch.empty_like(qkv)
-    _run("attn_bwd", lib.b200ctr_attn_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv), _p(drelmean),
-                               dropout, _stream())
+    use_tc = _attn_tc(tc, K, H, D)
+    _run("attn_tc_bwd" if use_tc else "attn_bwd", lib.b200ctr_attn_tc_bwd if use_tc else lib.b200ctr_attn_bwd,
+         _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv), _p(drelmean), dropout, _stream())
     _count()
     return dqkv
 

@@ -1,0 +1,393 @@
+// Tiny-head attention (head_dim 8) of the DARE encoder layer on the warp-level tensor-core path
+// (mma.sync m16n8k8, TF32 operands, fp32 accumulation) -- the `amp: bf16` counterpart of encoder.cu's exact-fp32
+// CUDA-core kernels.  Reference: torch MultiheadAttention math inside src/models/dare.py:53-70 (q scaled by
+// 1/sqrt(hd), additive Toeplitz bias from PositionalBias dare.py:29-37, dropout on the probabilities).
+//
+// head_dim = 8 is exactly the k extent of m16n8k8, so Q.K^T needs one MMA per 16 x 8 score tile and P.V one per
+// 8 keys; contraction depth 8 is far too shallow for tcgen05 (K = 16 per instruction, 128-row tiles), and the
+// kernel is bound by the exp / dropout-hash work per score anyway, so the legacy HMMA path is the right tool here.
+//
+// One CTA per sample; q (pre-scaled), k, v [, dO] of all heads staged once in shared memory as TF32 with a row
+// stride of 68 words, which makes every fragment load bank-conflict free.  A warp owns (head, 16-query tile):
+//   forward : S = QK^T for all keys stays in registers -> exact two-pass softmax -> dropout -> O = P.V
+//             (the score tile's accumulator layout is fed back as the A operand by permuting the key index:
+//              k-slot t <-> key 2t, k-slot t+4 <-> key 2t+1, with V rows read in the same order; no shuffles)
+//   backward: one warp per head, one pass over the scores: recompute P, dP = dO.V^T, dS -> dQ += dS.K, dbias;
+//             P and dS tiles are transposed in registers (movmatrix on bf16 pairs) for dV += P^T.dO, dK += dS^T.Q
+// Probabilities are never stored (only the per-row log-sum-exp), exactly like the fp32 kernels.
+#include "common.cuh"
+#include <cuda_bf16.h>
+#include <algorithm>
+
+namespace b200ctr {
+
+constexpr int TA_D = 64;
+constexpr int TA_HD = 8;
+constexpr int TA_H = 8;
+constexpr int TA_RS = 68;          // shared-memory row stride in 32-bit words
+constexpr int TA_THREADS = 256;
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// stage one [K x 64] fp32 slice (row stride ld) as TF32 into smem [Kp][68]; rows >= K are zero
+__device__ __forceinline__ void ta_stage(uint32_t* dst, const float* __restrict__ src, int64_t ld, int K, int Kp, float scale) {
+  for (int i = threadIdx.x; i < Kp * 16; i += TA_THREADS) {
+    const int r = i >> 4, c = i & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < K) v = *reinterpret_cast<const float4*>(src + (int64_t)r * ld + c * 4);
+    *reinterpret_cast<uint4*>(dst + r * TA_RS + c * 4) =
+        make_uint4(to_tf32(v.x * scale), to_tf32(v.y * scale), to_tf32(v.z * scale), to_tf32(v.w * scale));
+  }
+}
+
+// A fragment (16 rows x 8 head dims) straight from global memory: each fragment is used by exactly one warp
+__device__ __forceinline__ void ta_load_afrag(uint32_t (&a)[4], const float* __restrict__ base, int64_t ld, int ra, int rb, int K,
+                                              int col, float scale) {
+  const float x0 = ra < K ? __ldg(base + (int64_t)ra * ld + col) : 0.f, x1 = rb < K ? __ldg(base + (int64_t)rb * ld + col) : 0.f;
+  const float x2 = ra < K ? __ldg(base + (int64_t)ra * ld + col + 4) : 0.f, x3 = rb < K ? __ldg(base + (int64_t)rb * ld + col + 4) : 0.f;
+  a[0] = to_tf32(x0 * scale); a[1] = to_tf32(x1 * scale); a[2] = to_tf32(x2 * scale); a[3] = to_tf32(x3 * scale);
+}
+
+// NT = number of 8-key tiles (keys padded to a multiple of 16); Kp = 8 * NT
+template <int NT>
+__global__ void __launch_bounds__(TA_THREADS)
+attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, int K,
+                   float* __restrict__ o, float* __restrict__ lse, b200ctr_dropout_t drop) {
+  constexpr int Kp = NT * 8, MT = NT / 2;
+  extern __shared__ __align__(16) uint32_t sm_u[];
+  uint32_t* ks = sm_u;
+  uint32_t* vs = ks + Kp * TA_RS;
+  float* bias = reinterpret_cast<float*>(vs + Kp * TA_RS);         // 2K-1 : bias[(j-i)+K-1]
+  const int64_t b = blockIdx.x;
+  const float* base = qkv + b * (int64_t)K * 3 * TA_D;
+  ta_stage(ks, base + TA_D, 3 * TA_D, K, Kp, 1.f);
+  ta_stage(vs, base + 2 * TA_D, 3 * TA_D, K, Kp, 1.f);
+  for (int t = threadIdx.x; t < 2 * K - 1; t += TA_THREADS) {
+    const int d = t - (K - 1);
+    bias[t] = relmean ? relmean[min(max(d, -max_len), max_len) + max_len] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const DropCtx dctx = drop_ctx(drop);
+  for (int item = warp; item < TA_H * MT; item += TA_THREADS / 32) {
+    const int h = item / MT, i = item % MT;
+    const int qa = 16 * i + g, qb = qa + 8;
+    uint32_t a[4];
+    ta_load_afrag(a, base, 3 * TA_D, qa, qb, K, h * 8 + t, rsqrtf((float)TA_HD));
+    float s[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      mma_tf32(s[j], a, ks[(8 * j + g) * TA_RS + h * 8 + t], ks[(8 * j + g) * TA_RS + h * 8 + t + 4]);
+    }
+    const float* ba = bias + (K - 1) - min(qa, K - 1);
+    const float* bb = bias + (K - 1) - min(qb, K - 1);
+    float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int kc = 8 * j + 2 * t;
+      s[j][0] = kc < K ? s[j][0] + ba[kc] : -INFINITY;
+      s[j][1] = kc + 1 < K ? s[j][1] + ba[kc + 1] : -INFINITY;
+      s[j][2] = kc < K ? s[j][2] + bb[kc] : -INFINITY;
+      s[j][3] = kc + 1 < K ? s[j][3] + bb[kc + 1] : -INFINITY;
+      ma = fmaxf(ma, fmaxf(s[j][0], s[j][1]));
+      mb = fmaxf(mb, fmaxf(s[j][2], s[j][3]));
+    }
+    ma = quad_max(ma); mb = quad_max(mb);
+    float la = 0.f, lb = 0.f;
+    float oc[4] = {0.f, 0.f, 0.f, 0.f};
+    // dropout: row id = (b, h, query), column = key
+    const uint32_t keya = dctx.on ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qa) : 0u;
+    const uint32_t keyb = dctx.on ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qb) : 0u;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      float p0 = __expf(s[j][0] - ma), p1 = __expf(s[j][1] - ma), p2 = __expf(s[j][2] - mb), p3 = __expf(s[j][3] - mb);
+      la += p0 + p1; lb += p2 + p3;
+      if (dctx.on) {
+        float c0, c1, c2, c3;
+        drop_pair(dctx, keya, (uint32_t)(4 * j + t), c0, c1);
+        drop_pair(dctx, keyb, (uint32_t)(4 * j + t), c2, c3);
+        p0 *= c0; p1 *= c1; p2 *= c2; p3 *= c3;
+      }
+      const uint32_t pa[4] = {to_tf32(p0), to_tf32(p2), to_tf32(p1), to_tf32(p3)};
+      mma_tf32(oc, pa, vs[(8 * j + 2 * t) * TA_RS + h * 8 + g], vs[(8 * j + 2 * t + 1) * TA_RS + h * 8 + g]);
+    }
+    la = quad_sum(la); lb = quad_sum(lb);
+    if (qa < K) {
+      const float inv = 1.f / la;
+      *reinterpret_cast<float2*>(o + (b * K + qa) * (int64_t)TA_D + h * 8 + 2 * t) = make_float2(oc[0] * inv, oc[1] * inv);
+      if (t == 0) lse[(b * TA_H + h) * (int64_t)K + qa] = ma + logf(la);
+    }
+    if (qb < K) {
+      const float inv = 1.f / lb;
+      *reinterpret_cast<float2*>(o + (b * K + qb) * (int64_t)TA_D + h * 8 + 2 * t) = make_float2(oc[2] * inv, oc[3] * inv);
+      if (t == 0) lse[(b * TA_H + h) * (int64_t)K + qb] = mb + logf(lb);
+    }
+  }
+}
+
+// ---- backward: ONE pass over the scores, one warp per head ----------------------------------------------------
+// For every (16-query tile i, 16-key block jb) the warp recomputes P and dS once (TF32 MMAs for S = QK^T and
+// dP = dO.V^T), accumulates dQ += dS.K (TF32), and then needs the TRANSPOSED tiles for dV += P^T.dO and
+// dK += dS^T.Q: the accumulator fragments are packed to bf16 pairs and transposed in registers with
+// movmatrix (8x8 b16), which yields exactly the A fragment of mma.m16n8k16 (16 keys x 16 queries); its B fragment
+// (queries x head dims) is read from bf16 copies of Q^T and dO^T in shared memory.  dK / dV for all keys of the
+// head live in the warp's registers, so nothing but dbias needs an atomic.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t movmatrix_t(uint32_t x) {
+  uint32_t r;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(TA_THREADS, (NT <= 10 ? 2 : 1))
+attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, const float* __restrict__ o,
+                   const float* __restrict__ lse, const float* __restrict__ d_o, int K, float* __restrict__ dqkv,
+                   float* __restrict__ drelmean, b200ctr_dropout_t drop) {
+  constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2;
+  constexpr int TS = Kp + 8;                                   // bf16 row stride of the transposed copies
+  extern __shared__ __align__(16) uint32_t sm_u[];
+  uint32_t* ks = sm_u;
+  uint32_t* vs = ks + Kp * TA_RS;
+  __nv_bfloat16* qT = reinterpret_cast<__nv_bfloat16*>(vs + Kp * TA_RS);     // [64][TS]  (pre-scaled q)^T
+  __nv_bfloat16* doT = qT + 64 * TS;                                          // [64][TS]  dO^T
+  float* lses = reinterpret_cast<float*>(doT + 64 * TS);        // [H][Kp]  (+inf on padded rows -> P = 0)
+  float* dsum = lses + TA_H * Kp;                               // [H][Kp]
+  float* bias = dsum + TA_H * Kp;                               // 2K-1
+  float* dbias = bias + (2 * K - 1);                            // 2Kp+1 : dbias[(key - query) + Kp]
+  const int64_t b = blockIdx.x;
+  const float* base = qkv + b * (int64_t)K * 3 * TA_D;
+  const float* dob = d_o + b * (int64_t)K * TA_D;
+  const float scale = rsqrtf((float)TA_HD);
+  ta_stage(ks, base + TA_D, 3 * TA_D, K, Kp, 1.f);
+  ta_stage(vs, base + 2 * TA_D, 3 * TA_D, K, Kp, 1.f);
+  for (int i = threadIdx.x; i < Kp * 64; i += TA_THREADS) {
+    const int r = i >> 6, c = i & 63;                           // coalesced global reads; transposed smem writes
+    float qv = 0.f, dv = 0.f;
+    if (r < K) { qv = base[(int64_t)r * 3 * TA_D + c] * scale; dv = dob[(int64_t)r * TA_D + c]; }
+    qT[c * TS + r] = __float2bfloat16(qv);
+    doT[c * TS + r] = __float2bfloat16(dv);
+  }
+  for (int tt = threadIdx.x; tt < 2 * K - 1; tt += TA_THREADS) {
+    const int d = tt - (K - 1);
+    bias[tt] = relmean ? relmean[min(max(d, -max_len), max_len) + max_len] : 0.f;
+  }
+  for (int tt = threadIdx.x; tt < 2 * Kp + 1; tt += TA_THREADS) dbias[tt] = 0.f;
+  for (int item = threadIdx.x; item < Kp * TA_H; item += TA_THREADS) {
+    const int h = item / Kp, i = item % Kp;
+    float L = INFINITY, dsv = 0.f;
+    if (i < K) {
+      L = lse[(b * TA_H + h) * (int64_t)K + i];
+      const float4* op = reinterpret_cast<const float4*>(o + (b * K + i) * (int64_t)TA_D + h * TA_HD);
+      const float4* dp = reinterpret_cast<const float4*>(dob + (int64_t)i * TA_D + h * TA_HD);
+      const float4 o0 = op[0], o1 = op[1], d0 = dp[0], d1 = dp[1];
+      dsv = o0.x * d0.x + o0.y * d0.y + o0.z * d0.z + o0.w * d0.w + o1.x * d1.x + o1.y * d1.y + o1.z * d1.z + o1.w * d1.w;
+    }
+    lses[item] = L; dsum[item] = dsv;
+  }
+  __syncthreads();
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;      // warp == head
+  const DropCtx dctx = drop_ctx(drop);
+  float dk[NB][4], dv[NB][4];
+#pragma unroll
+  for (int jb = 0; jb < NB; ++jb) { dk[jb][0] = dk[jb][1] = dk[jb][2] = dk[jb][3] = 0.f; dv[jb][0] = dv[jb][1] = dv[jb][2] = dv[jb][3] = 0.f; }
+  // dbias: a thread's four dS values of tile (i, j) lie on the diagonals 8(j-2i) + (2t-g) {+0, +1} (rows g) and the same
+  // shifted by -8 (rows g+8), so they accumulate in registers in slots indexed by j (+1) that rotate by two per query
+  // tile; only the two slots that leave the window are flushed (shared-memory atomics) per tile row.
+  float A0[NT + 1], A1[NT + 1];
+#pragma unroll
+  for (int sl = 0; sl <= NT; ++sl) { A0[sl] = 0.f; A1[sl] = 0.f; }
+  float* dbt = dbias + Kp + 2 * t - g;
+  const uint32_t* qT32 = reinterpret_cast<const uint32_t*>(qT + (h * 8 + g) * TS);
+  const uint32_t* doT32 = reinterpret_cast<const uint32_t*>(doT + (h * 8 + g) * TS);
+#pragma unroll 1
+  for (int i = 0; i < MT; ++i) {
+    const int qa = 16 * i + g, qb = qa + 8;
+    uint32_t aq[4], ad[4];
+    ta_load_afrag(aq, base, 3 * TA_D, qa, qb, K, h * 8 + t, scale);
+    ta_load_afrag(ad, dob, TA_D, qa, qb, K, h * 8 + t, 1.f);
+    // B fragments (k = 16 queries of this tile, n = head dim g) of the bf16 m16n8k16 MMAs
+    const uint32_t bq0 = qT32[8 * i + t], bq1 = qT32[8 * i + t + 4], bd0 = doT32[8 * i + t], bd1 = doT32[8 * i + t + 4];
+    const float La = lses[h * Kp + qa], Lb = lses[h * Kp + qb], Da = dsum[h * Kp + qa], Db = dsum[h * Kp + qb];
+    const int qac = min(qa, K - 1), qbc = min(qb, K - 1);
+    const float* ba = bias + (K - 1) - qac;
+    const float* bb = bias + (K - 1) - qbc;
+    const uint32_t keya = dctx.on ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qa) : 0u;
+    const uint32_t keyb = dctx.on ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qb) : 0u;
+    float dq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int jb = 0; jb < NB; ++jb) {
+      uint32_t pd_lo[2], pd_hi[2], ds_lo[2], ds_hi[2];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int j = 2 * jb + hf;
+        const int kc = 8 * j + 2 * t;
+        const uint32_t kb0 = ks[(8 * j + g) * TA_RS + h * 8 + t], kb1 = ks[(8 * j + g) * TA_RS + h * 8 + t + 4];
+        const uint32_t vb0 = vs[(8 * j + g) * TA_RS + h * 8 + t], vb1 = vs[(8 * j + g) * TA_RS + h * 8 + t + 4];
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_tf32(s, aq, kb0, kb1);
+        mma_tf32(dp, ad, vb0, vb1);
+        const bool v0 = kc < K, v1 = kc + 1 < K;
+        const float p0 = v0 ? __expf(s[0] + ba[kc] - La) : 0.f, p1 = v1 ? __expf(s[1] + ba[kc + 1] - La) : 0.f;
+        const float p2 = v0 ? __expf(s[2] + bb[kc] - Lb) : 0.f, p3 = v1 ? __expf(s[3] + bb[kc + 1] - Lb) : 0.f;
+        float c0 = 1.f, c1 = 1.f, c2 = 1.f, c3 = 1.f;
+        if (dctx.on) {
+          drop_pair(dctx, keya, (uint32_t)(4 * j + t), c0, c1);
+          drop_pair(dctx, keyb, (uint32_t)(4 * j + t), c2, c3);
+        }
+        const float ds0 = p0 * (dp[0] * c0 - Da), ds1 = p1 * (dp[1] * c1 - Da);
+        const float ds2 = p2 * (dp[2] * c2 - Db), ds3 = p3 * (dp[3] * c3 - Db);
+        A0[j + 1] += ds0; A1[j + 1] += ds1; A0[j] += ds2; A1[j] += ds3;      // padded rows / keys contribute exact zeros
+        const uint32_t pa[4] = {to_tf32(ds0), to_tf32(ds2), to_tf32(ds1), to_tf32(ds3)};
+        mma_tf32(dq, pa, ks[(8 * j + 2 * t) * TA_RS + h * 8 + g], ks[(8 * j + 2 * t + 1) * TA_RS + h * 8 + g]);
+        pd_lo[hf] = pack_bf16x2(p0 * c0, p1 * c1); pd_hi[hf] = pack_bf16x2(p2 * c2, p3 * c3);
+        ds_lo[hf] = pack_bf16x2(ds0, ds1); ds_hi[hf] = pack_bf16x2(ds2, ds3);
+      }
+      // A = tile^T: rows = 16 keys of block jb (tile 2jb -> rows 0-7, tile 2jb+1 -> rows 8-15), k = 16 queries
+      const uint32_t apd[4] = {movmatrix_t(pd_lo[0]), movmatrix_t(pd_lo[1]), movmatrix_t(pd_hi[0]), movmatrix_t(pd_hi[1])};
+      const uint32_t ads[4] = {movmatrix_t(ds_lo[0]), movmatrix_t(ds_lo[1]), movmatrix_t(ds_hi[0]), movmatrix_t(ds_hi[1])};
+      mma_bf16_16816(dv[jb], apd, bd0, bd1);
+      mma_bf16_16816(dk[jb], ads, bq0, bq1);
+    }
+    if (qa < K) *reinterpret_cast<float2*>(dqkv + (b * K + qa) * (int64_t)(3 * TA_D) + h * 8 + 2 * t) = make_float2(dq[0] * scale, dq[1] * scale);
+    if (qb < K) *reinterpret_cast<float2*>(dqkv + (b * K + qb) * (int64_t)(3 * TA_D) + h * 8 + 2 * t) = make_float2(dq[2] * scale, dq[3] * scale);
+    if (drelmean) {
+      // slot sl holds the diagonal block u = sl - 1 - 2i
+      if (i + 1 < MT) {
+        atomicAdd(dbt + 8 * (NT - 1 - 2 * i), A0[NT]); atomicAdd(dbt + 8 * (NT - 1 - 2 * i) + 1, A1[NT]);
+        atomicAdd(dbt + 8 * (NT - 2 - 2 * i), A0[NT - 1]); atomicAdd(dbt + 8 * (NT - 2 - 2 * i) + 1, A1[NT - 1]);
+#pragma unroll
+        for (int sl = NT; sl >= 2; --sl) { A0[sl] = A0[sl - 2]; A1[sl] = A1[sl - 2]; }
+        A0[0] = A0[1] = A1[0] = A1[1] = 0.f;
+      } else {
+#pragma unroll
+        for (int sl = 0; sl <= NT; ++sl) {
+          atomicAdd(dbt + 8 * (sl - 1 - 2 * i), A0[sl]); atomicAdd(dbt + 8 * (sl - 1 - 2 * i) + 1, A1[sl]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int jb = 0; jb < NB; ++jb) {
+    const int ka = 16 * jb + g, kb = ka + 8;
+    if (ka < K) {
+      *reinterpret_cast<float2*>(dqkv + (b * K + ka) * (int64_t)(3 * TA_D) + TA_D + h * 8 + 2 * t) = make_float2(dk[jb][0], dk[jb][1]);
+      *reinterpret_cast<float2*>(dqkv + (b * K + ka) * (int64_t)(3 * TA_D) + 2 * TA_D + h * 8 + 2 * t) = make_float2(dv[jb][0], dv[jb][1]);
+    }
+    if (kb < K) {
+      *reinterpret_cast<float2*>(dqkv + (b * K + kb) * (int64_t)(3 * TA_D) + TA_D + h * 8 + 2 * t) = make_float2(dk[jb][2], dk[jb][3]);
+      *reinterpret_cast<float2*>(dqkv + (b * K + kb) * (int64_t)(3 * TA_D) + 2 * TA_D + h * 8 + 2 * t) = make_float2(dv[jb][2], dv[jb][3]);
+    }
+  }
+  if (drelmean) {
+    __syncthreads();
+    for (int tt = threadIdx.x; tt < 2 * K - 1; tt += TA_THREADS) {
+      const int d = tt - (K - 1);
+      atomicAdd(drelmean + min(max(d, -max_len), max_len) + max_len, dbias[d + Kp]);
+    }
+  }
+}
+
+static int ta_set_smem(const void* fn, size_t bytes) {
+  if (bytes > 227 * 1024) {
+    set_error("attention (tensor-core path): K too large for one CTA's shared memory (%zu bytes)", bytes);
+    return B200CTR_E_UNSUPPORTED_SHAPE;
+  }
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attn_tc smem)");
+  }
+  return B200CTR_OK;
+}
+
+template <int NT>
+static int ta_launch_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, float* o, float* lse,
+                         b200ctr_dropout_t drop, cudaStream_t st) {
+  const size_t smem = ((size_t)2 * NT * 8 * TA_RS + 2 * K) * 4;
+  int rc = ta_set_smem((const void*)attn_tc_fwd_kernel<NT>, smem);
+  if (rc) return rc;
+  attn_tc_fwd_kernel<NT><<<(unsigned)B, TA_THREADS, smem, st>>>(qkv, relmean, max_len, K, o, lse, drop);
+  return B200CTR_OK;
+}
+template <int NT>
+static int ta_launch_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse, const float* d_o,
+                         int64_t B, int K, float* dqkv, float* drelmean, b200ctr_dropout_t drop, cudaStream_t st) {
+  const size_t smem = ((size_t)2 * NT * 8 * TA_RS + 2 * TA_H * NT * 8 + 2 * K + 2 * NT * 8 + 2) * 4 + (size_t)2 * 64 * (NT * 8 + 8) * 2;
+  int rc = ta_set_smem((const void*)attn_tc_bwd_kernel<NT>, smem);
+  if (rc) return rc;
+  attn_tc_bwd_kernel<NT><<<(unsigned)B, TA_THREADS, smem, st>>>(qkv, relmean, max_len, o, lse, d_o, K, dqkv, drelmean, drop);
+  return B200CTR_OK;
+}
+
+}  // namespace b200ctr
+
+using namespace b200ctr;
+
+#define TA_DISPATCH(CALL)                                                            \
+  switch ((K + 15) / 16) {                                                           \
+    case 1: rc = CALL(2); break;   case 2: rc = CALL(4); break;   case 3: rc = CALL(6); break;   \
+    case 4: rc = CALL(8); break;   case 5: rc = CALL(10); break;  case 6: rc = CALL(12); break;  \
+    case 7: rc = CALL(14); break;  case 8: rc = CALL(16); break;  case 9: rc = CALL(18); break;  \
+    case 10: rc = CALL(20); break;                                                   \
+    default:                                                                         \
+      set_error("attention (tensor-core path): top_k=%d > 160 is not built", K);     \
+      return B200CTR_E_UNSUPPORTED_SHAPE;                                            \
+  }
+
+extern "C" int b200ctr_attn_tc_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D, float* o,
+                                   float* lse, b200ctr_dropout_t drop, void* stream) {
+  B200_REQUIRE(qkv && o && lse, B200CTR_E_INVALID_ARG, "attn_tc_fwd: null pointer");
+  B200_REQUIRE(D == TA_D && H == TA_H, B200CTR_E_UNSUPPORTED_SHAPE,
+               "attn_tc_fwd: only emb_dim=64 with 8 heads of head_dim=8 is built (got D=%d, H=%d)", D, H);
+  if (B == 0 || K == 0) return B200CTR_OK;
+  int rc;
+#define CALL(NT_) ta_launch_fwd<NT_>(qkv, relmean, max_len, B, K, o, lse, drop, as_stream(stream))
+  TA_DISPATCH(CALL)
+#undef CALL
+  if (rc) return rc;
+  B200_LAUNCH_CHECK("attn_tc_fwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_attn_tc_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
+                                   const float* d_o, int64_t B, int K, int H, int D, float* dqkv, float* drelmean,
+                                   b200ctr_dropout_t drop, void* stream) {
+  B200_REQUIRE(qkv && o && lse && d_o && dqkv, B200CTR_E_INVALID_ARG, "attn_tc_bwd: null pointer");
+  B200_REQUIRE(D == TA_D && H == TA_H, B200CTR_E_UNSUPPORTED_SHAPE,
+               "attn_tc_bwd: only emb_dim=64 with 8 heads of head_dim=8 is built (got D=%d, H=%d)", D, H);
+  if (B == 0 || K == 0) return B200CTR_OK;
+  int rc;
+#define CALL(NT_) ta_launch_bwd<NT_>(qkv, relmean, max_len, o, lse, d_o, B, K, dqkv, drelmean, drop, as_stream(stream))
+  TA_DISPATCH(CALL)
+#undef CALL
+  if (rc) return rc;
+  B200_LAUNCH_CHECK("attn_tc_bwd_kernel");
+  return B200CTR_OK;
+}

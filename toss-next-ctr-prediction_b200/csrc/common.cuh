@@ -45,10 +45,48 @@ __device__ __forceinline__ uint32_t rng_u32(const b200ctr_dropout_t& d, uint64_t
   return x;
 }
 // keep-scale: 1/(1-p) if kept, 0 if dropped.  p == 0 short-circuits (exact identity).
+// One 32-bit hash serves the two elements of an aligned pair (idx >> 1): 16 bits each against a 16-bit threshold
+// (p is honoured to 2^-16), which halves the hash work in the kernels that walk adjacent elements (drop_scale2).
+__device__ __forceinline__ uint32_t drop_thr16(const b200ctr_dropout_t& d) { return __float2uint_rn(d.p * 65536.f); }
 __device__ __forceinline__ float drop_scale(const b200ctr_dropout_t& d, uint64_t idx) {
   if (d.p <= 0.f) return 1.f;
-  float u = (float)(rng_u32(d, idx) >> 8) * (1.0f / 16777216.0f);   // [0,1)
-  return u >= d.p ? 1.f / (1.f - d.p) : 0.f;
+  const uint32_t h = rng_u32(d, idx >> 1);
+  const uint32_t bits = (idx & 1) ? (h >> 16) : (h & 0xffffu);
+  return bits >= drop_thr16(d) ? 1.f / (1.f - d.p) : 0.f;
+}
+// both elements of the pair starting at the EVEN index idx0 (same values as two drop_scale calls)
+__device__ __forceinline__ void drop_scale2(const b200ctr_dropout_t& d, uint64_t idx0, float& s0, float& s1) {
+  const uint32_t h = rng_u32(d, idx0 >> 1), thr = drop_thr16(d);
+  const float inv = 1.f / (1.f - d.p);
+  s0 = (h & 0xffffu) >= thr ? inv : 0.f;
+  s1 = (h >> 16) >= thr ? inv : 0.f;
+}
+
+// Row/column form used by the 2-D hot loops (attention probabilities, FFN / MLP activations): a full-strength
+// key per row (rng_u32 of the 64-bit row id, computed once per row) and ONE mixer round per aligned column pair.
+struct DropCtx {
+  uint32_t thr;     // 16-bit keep threshold
+  float inv;        // 1/(1-p)
+  bool on;
+};
+__device__ __forceinline__ DropCtx drop_ctx(const b200ctr_dropout_t& d) {
+  DropCtx c;
+  c.on = d.p > 0.f;
+  c.thr = c.on ? drop_thr16(d) : 0u;
+  c.inv = c.on ? 1.f / (1.f - d.p) : 1.f;
+  return c;
+}
+__device__ __forceinline__ uint32_t drop_row_key(const b200ctr_dropout_t& d, uint64_t row) { return rng_u32(d, row); }
+// keep-scales of columns 2*colpair and 2*colpair+1 of the row with key `key`
+__device__ __forceinline__ void drop_pair(const DropCtx& c, uint32_t key, uint32_t colpair, float& s0, float& s1) {
+  const uint32_t h = mix32(key ^ (colpair * 0x9E3779B9U));
+  s0 = (h & 0xffffu) >= c.thr ? c.inv : 0.f;
+  s1 = (h >> 16) >= c.thr ? c.inv : 0.f;
+}
+__device__ __forceinline__ float drop_rc(const DropCtx& c, uint32_t key, uint32_t col) {
+  const uint32_t h = mix32(key ^ ((col >> 1) * 0x9E3779B9U));
+  const uint32_t bits = (col & 1) ? (h >> 16) : (h & 0xffffu);
+  return bits >= c.thr ? c.inv : 0.f;
 }
 
 // ---- math ------------------------------------------------------------------------------------------------

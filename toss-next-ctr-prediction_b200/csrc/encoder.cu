@@ -44,6 +44,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean
   }
   __syncthreads();
   const float scale = rsqrtf((float)AT_HD);
+  const DropCtx dctx = drop_ctx(drop);
   const int half = (K + 1) >> 1;
   for (int item = threadIdx.x; item < half * H; item += AT_THREADS) {
     const int h = item / half, ia = item % half;
@@ -74,7 +75,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean
     float aa[AT_HD], ab[AT_HD];
 #pragma unroll
     for (int d = 0; d < AT_HD; ++d) { aa[d] = 0.f; ab[d] = 0.f; }
-    const uint64_t ea0 = (((uint64_t)b * H + h) * K + ia) * K, eb0 = (((uint64_t)b * H + h) * K + ib) * K;
+    const uint32_t keya = drop_row_key(drop, ((uint64_t)b * H + h) * K + ia), keyb = drop_row_key(drop, ((uint64_t)b * H + h) * K + ib);
     for (int j = 0; j < K; ++j) {
       const float4* kp = reinterpret_cast<const float4*>(ks + (size_t)j * AT_D + h * AT_HD);
       const float4* vp = reinterpret_cast<const float4*>(vs + (size_t)j * AT_D + h * AT_HD);
@@ -82,7 +83,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean
       const float pa = expf(dot8(qa, k0, k1) + ba[j] - ma);
       const float pb = expf(dot8(qb, k0, k1) + bb[j] - mb);
       la += pa; lb += pb;
-      const float da = pa * drop_scale(drop, ea0 + j), db = pb * drop_scale(drop, eb0 + j);
+      const float da = pa * drop_rc(dctx, keya, (uint32_t)j), db = pb * drop_rc(dctx, keyb, (uint32_t)j);
       aa[0] = fmaf(da, v0.x, aa[0]); aa[1] = fmaf(da, v0.y, aa[1]); aa[2] = fmaf(da, v0.z, aa[2]); aa[3] = fmaf(da, v0.w, aa[3]);
       aa[4] = fmaf(da, v1.x, aa[4]); aa[5] = fmaf(da, v1.y, aa[5]); aa[6] = fmaf(da, v1.z, aa[6]); aa[7] = fmaf(da, v1.w, aa[7]);
       ab[0] = fmaf(db, v0.x, ab[0]); ab[1] = fmaf(db, v0.y, ab[1]); ab[2] = fmaf(db, v0.z, ab[2]); ab[3] = fmaf(db, v0.w, ab[3]);
@@ -152,6 +153,7 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean
   }
   __syncthreads();
   const int half = (K + 1) >> 1;
+  const DropCtx dctx = drop_ctx(drop);
   // phase 1: thread per (head, query rows ia/ib) -> dq, dbias
   for (int item = threadIdx.x; item < half * H; item += AT_THREADS) {
     const int h = item / half, ia = item % half;
@@ -170,15 +172,15 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean
     const float* bb = bias + (K - 1) - ib;
     float* dba = dbias + (K - 1) - ia;
     float* dbb = dbias + (K - 1) - ib;
-    const uint64_t ea0 = (((uint64_t)b * H + h) * K + ia) * K, eb0 = (((uint64_t)b * H + h) * K + ib) * K;
+    const uint32_t keya = drop_row_key(drop, ((uint64_t)b * H + h) * K + ia), keyb = drop_row_key(drop, ((uint64_t)b * H + h) * K + ib);
     for (int j = 0; j < K; ++j) {
       const float4* kp = reinterpret_cast<const float4*>(ks + (size_t)j * AT_D + h * AT_HD);
       const float4* vp = reinterpret_cast<const float4*>(vs + (size_t)j * AT_D + h * AT_HD);
       const float4 k0 = kp[0], k1 = kp[1], v0 = vp[0], v1 = vp[1];
       const float pa = expf(dot8(qa, k0, k1) + ba[j] - La);
       const float pb = expf(dot8(qb, k0, k1) + bb[j] - Lb);
-      const float dsa = pa * (dot8(da, v0, v1) * drop_scale(drop, ea0 + j) - Da);
-      const float dsb = pb * (dot8(db, v0, v1) * drop_scale(drop, eb0 + j) - Db);
+      const float dsa = pa * (dot8(da, v0, v1) * drop_rc(dctx, keya, (uint32_t)j) - Da);
+      const float dsb = pb * (dot8(db, v0, v1) * drop_rc(dctx, keyb, (uint32_t)j) - Db);
       axpy8(ga, dsa, k0, k1);
       axpy8(gb, dsb, k0, k1);
       if (drelmean) {
@@ -213,10 +215,10 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean
       const float4* dp4 = reinterpret_cast<const float4*>(dos + (size_t)i * AT_D + h * AT_HD);
       const float4 q0 = qp[0], q1 = qp[1], d0 = dp4[0], d1 = dp4[1];
       const float L = lses[h * K + i], Di = dsum[h * K + i];
-      const uint64_t e0 = (((uint64_t)b * H + h) * K + i) * K;
+      const uint32_t keyi = dctx.on ? drop_row_key(drop, ((uint64_t)b * H + h) * K + i) : 0u;
       const float pa = expf(dot8(ka, q0, q1) + bias[(ja - i) + K - 1] - L);
       const float pb = expf(dot8(kb, q0, q1) + bias[(jb - i) + K - 1] - L);
-      const float sa = drop_scale(drop, e0 + ja), sb = drop_scale(drop, e0 + jb);
+      const float sa = drop_rc(dctx, keyi, (uint32_t)ja), sb = drop_rc(dctx, keyi, (uint32_t)jb);
       axpy8(dva, pa * sa, d0, d1);
       axpy8(dvb, pb * sb, d0, d1);
       const float dsa = pa * (dot8(va, d0, d1) * sa - Di);

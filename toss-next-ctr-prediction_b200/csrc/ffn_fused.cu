@@ -195,8 +195,10 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
     const int ew = warp - 4, q = ew & 3, half = ew >> 2;
     const int r = q * 32 + lane;
     uint32_t g = 0;
+    const DropCtx dctx = drop_ctx(drop);
     for (int it = 0; it < n_it; ++it) {
       const int64_t m = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM + r;
+      const uint32_t rkey = dctx.on ? drop_row_key(drop, (uint64_t)m) : 0u;
       for (int c = 0; c < NC; ++c, ++g) {
         mbar_wait(smem_u32(&bars->p_full), g & 1);
         tc_fence_after();
@@ -206,13 +208,16 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->p_empty));
         const int n0 = c * FF_HC + half * 32;
-        const uint64_t e0 = (uint64_t)m * (uint64_t)hidden + (uint64_t)n0;
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float f0 = gelu_erf(__uint_as_float(v[j]) + b1s[n0 + j]);
           float f1 = gelu_erf(__uint_as_float(v[j + 1]) + b1s[n0 + j + 1]);
-          if (drop.p > 0.f) { f0 *= drop_scale(drop, e0 + j); f1 *= drop_scale(drop, e0 + j + 1); }
+          if (dctx.on) {
+            float d0, d1;
+            drop_pair(dctx, rkey, (uint32_t)(n0 + j) >> 1, d0, d1);
+            f0 *= d0; f1 *= d1;
+          }
           pk[j >> 1] = pack_bf16(f0, f1);
         }
         const int fb = g & 1;
@@ -408,9 +413,11 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
     const int r = q * 32 + lane;
     float db1_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     uint32_t g = 0;
+    const DropCtx dctx = drop_ctx(drop);
     for (int it = 0; it < n_it; ++it) {
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
       const int64_t m = tile * FF_TM + r;
+      const uint32_t rkey = dctx.on ? drop_row_key(drop, (uint64_t)m) : 0u;
       for (int c = 0; c < NC; ++c, ++g) {
         mbar_wait(smem_u32(&bars->pq_full), g & 1);
         tc_fence_after();
@@ -422,18 +429,21 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->pq_empty));
         const int n0 = c * FF_HC + half * 32;
-        const uint64_t e0 = (uint64_t)m * (uint64_t)hidden + (uint64_t)n0;
         uint32_t fpk[16], dpk[16];
         float dp[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float pre = __uint_as_float(pv[j]) + b1s[n0 + j];
-          float cdf, ex;
-          gelu_parts(pre, cdf, ex);
-          const float ds = (drop.p > 0.f) ? drop_scale(drop, e0 + j) : 1.f;
-          const float f = pre * cdf * ds;
-          dp[j] = __uint_as_float(qv[j]) * ds * fmaf(pre * 0.39894228040143268f, ex, cdf);
-          pv[j] = __float_as_uint(f);
+        for (int j = 0; j < 32; j += 2) {
+          float dsc[2] = {1.f, 1.f};
+          if (dctx.on) drop_pair(dctx, rkey, (uint32_t)(n0 + j) >> 1, dsc[0], dsc[1]);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float pre = __uint_as_float(pv[j + u]) + b1s[n0 + j + u];
+            float cdf, ex;
+            gelu_parts(pre, cdf, ex);
+            const float f = pre * cdf * dsc[u];
+            dp[j + u] = __uint_as_float(qv[j + u]) * dsc[u] * fmaf(pre * 0.39894228040143268f, ex, cdf);
+            pv[j + u] = __float_as_uint(f);
+          }
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {

@@ -22,7 +22,7 @@ __device__ __forceinline__ float apply_epi(float acc, int64_t m, int64_t n, int6
   if (e.pre_out) e.pre_out[m * e.ld_pre + n] = v;
   if (e.act == B200CTR_ACT_RELU) v = fmaxf(v, 0.f);
   else if (e.act == B200CTR_ACT_GELU) v = gelu_erf(v);
-  if (e.drop.p > 0.f) v *= drop_scale(e.drop, (uint64_t)(m * N + n));
+  if (e.drop.p > 0.f) v *= drop_rc(drop_ctx(e.drop), drop_row_key(e.drop, (uint64_t)m), (uint32_t)n);
   if (e.mask_mode == B200CTR_MASK_NONZERO) v = (e.mask_src[m * e.ld_mask + n] != 0.f) ? v * e.mask_scale : 0.f;
   else if (e.mask_mode == B200CTR_MASK_GELU_GRAD) v *= gelu_erf_grad(e.mask_src[m * e.ld_mask + n]);
   if (e.residual) v += e.residual[m * e.ld_res + n];
@@ -51,10 +51,13 @@ __device__ __forceinline__ float4 apply_epi4(float4 acc, const EpiAux4& a, int64
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
   }
-  if (e.drop.p > 0.f) {
-    const uint64_t id = (uint64_t)(m * N + n);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] *= drop_scale(e.drop, id + j);
+  if (e.drop.p > 0.f) {          // n % 4 == 0: two aligned column pairs of row m
+    const DropCtx dc = drop_ctx(e.drop);
+    const uint32_t key = drop_row_key(e.drop, (uint64_t)m);
+    float s0, s1, s2, s3;
+    drop_pair(dc, key, (uint32_t)n >> 1, s0, s1);
+    drop_pair(dc, key, ((uint32_t)n >> 1) + 1, s2, s3);
+    v[0] *= s0; v[1] *= s1; v[2] *= s2; v[3] *= s3;
   }
   if (e.mask_mode == B200CTR_MASK_NONZERO) {
     const float mk[4] = {a.mask.x, a.mask.y, a.mask.z, a.mask.w};
