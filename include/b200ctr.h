@@ -214,6 +214,12 @@ int b200ctr_rowrms_fwd(const float* x, int64_t ldx, const float* w, float eps, i
                        float* z, int64_t ld_z, float* r, void* stream);
 int b200ctr_rowrms_bwd(const float* dz, int64_t ld_dz, const float* x, int64_t ldx, const float* w, const float* r,
                        int64_t B, int64_t N, float* dx, int64_t ld_dx, float* dw_partial, int n_partials, void* stream);
+/* headproj: inter[b, h*P+p] = sum_r quad[b, h*R+r] * V[h][r][p] for all heads in one launch (qnn_alpha.py:96);
+ * bwd: dquad and dV (overwritten; deterministic two-stage batch reduction through `workspace`).              */
+int b200ctr_headproj_fwd(const float* quad, const float* V, int64_t B, int H, int R, int P, float* inter, void* stream);
+int64_t b200ctr_headproj_bwd_workspace_bytes(int H, int R, int P);
+int b200ctr_headproj_bwd(const float* quad, const float* dinter, const float* V, int64_t B, int H, int R, int P,
+                         float* dquad, float* dV, void* workspace, void* stream);
 int b200ctr_fm_reduce(const float* A, int64_t B, int F, int C, float* s, float* quad, void* stream);
 int b200ctr_fm_grad(float* A, const float* s, const float* dquad, int64_t B, int F, int C, void* stream);
 int b200ctr_se_gate_fwd(const float* colsum, float inv_B, const float* w1, const float* b1, const float* w2,

@@ -362,3 +362,18 @@ def test_attn_tc_matches_fp32_kernels(dev, B, K, p):
     for sl, name, tol in ((slice(0, 64), "dq", 5e-3), (slice(64, 128), "dk", 1.5e-2), (slice(128, 192), "dv", 1.5e-2)):
         assert float((dq[:, sl] - dq_ref[:, sl]).abs().max()) / gmax < tol, name
     assert float((drel - drel_ref).abs().max()) / (float(drel_ref.abs().max()) + gmax) < 5e-3
+
+
+@pytest.mark.parametrize("B,H,R,P", [(1000, 6, 16, 192), (7, 6, 16, 192), (300, 8, 32, 128), (64, 2, 4, 24)])
+def test_headproj_matches_einsum(dev, B, H, R, P):
+    from b200ctr import ops
+    assert ops.headproj_ok(H, R, P)
+    g = torch.Generator().manual_seed(B + H)
+    quad, V, dinter = _rand(g, B, H * R), _rand(g, H, R, P) * 0.1, _rand(g, B, H * P)
+    inter = ops.headproj_fwd(quad.to(dev), V.to(dev))
+    ref = torch.einsum("bhr,hrp->bhp", quad.view(B, H, R).double(), V.double()).reshape(B, H * P)
+    assert max_err_scaled(inter.cpu(), ref) < 1e-5
+    dV = torch.zeros(H, R, P, device=dev)
+    dquad = ops.headproj_bwd(quad.to(dev), dinter.to(dev), V.to(dev), dV)
+    assert max_err_scaled(dquad.cpu(), torch.einsum("bhp,hrp->bhr", dinter.view(B, H, P).double(), V.double()).reshape(B, H * R)) < 1e-5
+    assert max_err_scaled(dV.cpu(), torch.einsum("bhr,bhp->hrp", quad.view(B, H, R).double(), dinter.view(B, H, P).double())) < 1e-5

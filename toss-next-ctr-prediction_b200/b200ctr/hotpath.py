@@ -243,10 +243,13 @@ def qnn_fwd(P: Dict[str, Tensor], spec: ModelSpec, xF: Tensor, dc: DropCtl, B_to
     Ucat = P["qnn.U"].permute(1, 0, 2).reshape(D, C).contiguous()            # (D, H*r): layout plumbing only
     A = ops.gemm(z.view(B * F, D), Ucat)                                       # (B*F, C)
     s, quad = ops.fm_reduce(A, B, F, C)
-    inter = torch.empty((B, HP), device=xF.device, dtype=torch.float32)
     V = P["qnn.V"]
-    for h in range(H):
-        ops.gemm(quad[:, h * r:(h + 1) * r], V[h], out=inter[:, h * Pd:(h + 1) * Pd])
+    if ops.headproj_ok(H, r, Pd):
+        inter = ops.headproj_fwd(quad, V)
+    else:
+        inter = torch.empty((B, HP), device=xF.device, dtype=torch.float32)
+        for h in range(H):
+            ops.gemm(quad[:, h * r:(h + 1) * r], V[h], out=inter[:, h * Pd:(h + 1) * Pd])
     sv = dict(xF=xF, rz=rz, z=z, A=A, s=s, quad=quad, inter=inter, Ucat=Ucat)
     Bt = B_total or B
     if spec.use_se:
@@ -325,10 +328,13 @@ def qnn_bwd(P, spec: ModelSpec, sv: dict, dlogit: Tensor, dc: DropCtl, G: Callab
         dinter, _ = ops.se_apply_bwd(digd, inter, None, None, sv["B_total"], True, False, dcq)
     quad, V = sv["quad"], P["qnn.V"]
     gV = G("qnn.V")
-    dquad = torch.empty((B, C), device=xF.device, dtype=torch.float32)
-    for h in range(H):
-        ops.gemm(quad[:, h * r:(h + 1) * r], dinter[:, h * Pd:(h + 1) * Pd], trans_a=True, out=gV[h])
-        ops.gemm(dinter[:, h * Pd:(h + 1) * Pd], V[h], trans_b=True, out=dquad[:, h * r:(h + 1) * r])
+    if ops.headproj_ok(H, r, Pd):
+        dquad = ops.headproj_bwd(quad, dinter, V, gV)
+    else:
+        dquad = torch.empty((B, C), device=xF.device, dtype=torch.float32)
+        for h in range(H):
+            ops.gemm(quad[:, h * r:(h + 1) * r], dinter[:, h * Pd:(h + 1) * Pd], trans_a=True, out=gV[h])
+            ops.gemm(dinter[:, h * Pd:(h + 1) * Pd], V[h], trans_b=True, out=dquad[:, h * r:(h + 1) * r])
     dA = ops.fm_grad_(sv["A"], sv["s"], dquad, B, F, C)                       # in place over the saved A
     z3 = z.view(B * F, D)
     dUcat = ops.gemm(z3, dA, trans_a=True)                                    # (D, C)

@@ -486,6 +486,37 @@ def rowrms_bwd(dz, x, w, r, n_partials=296):
     return dx, colsum(part)
 
 
+def headproj_ok(H: int, R: int, P: int) -> bool:
+    C = H * R
+    if R > 32 or H * P > 1536 or C > 384 or C <= 0:
+        return False
+    return (C * (P + 1) + H * P + 5 * C) * 4 <= 200 * 1024
+
+
+def headproj_fwd(quad, V):
+    """inter (B, H*P) = per-head quad_h @ V_h, all heads in one launch."""
+    lib = _lib.load()
+    H, R, P = V.shape
+    B = quad.shape[0]
+    inter = torch.empty((B, H * P), device=quad.device, dtype=torch.float32)
+    _run("headproj_fwd", lib.b200ctr_headproj_fwd, _p(_f32(quad)), _p(V), B, H, R, P, _p(inter), _stream())
+    _count()
+    return inter
+
+
+def headproj_bwd(quad, dinter, V, dV):
+    """Returns dquad (B, H*R); overwrites dV (H, R, P)."""
+    lib = _lib.load()
+    H, R, P = V.shape
+    B = quad.shape[0]
+    assert dinter.is_contiguous() and quad.is_contiguous() and dV.is_contiguous()
+    dquad = torch.empty((B, H * R), device=quad.device, dtype=torch.float32)
+    ws = torch.empty((lib.b200ctr_headproj_bwd_workspace_bytes(H, R, P),), device=quad.device, dtype=torch.uint8)
+    _run("headproj_bwd", lib.b200ctr_headproj_bwd, _p(quad), _p(dinter), _p(V), B, H, R, P, _p(dquad), _p(dV), _p(ws), _stream())
+    _count(2)
+    return dquad
+
+
 def fm_reduce(A, B, F, C):
     lib = _lib.load()
     s = torch.empty((B, C), device=A.device, dtype=torch.float32)

@@ -183,6 +183,108 @@ __global__ void se_apply_bwd_kernel(const float* __restrict__ dout, int64_t ld_d
   if (dinter) dinter[i] = d * (gate ? gate[c] : 1.f) + (dmean ? dmean[c] * inv_B : 0.f);
 }
 
+
+// ---- per-head value projection of the quadratic term (qnn_alpha.py:96: out_h = quad_h @ V_h) --------------------
+// inter[b, h*P + p] = sum_r quad[b, h*R + r] * V[h][r][p].  Contraction depth R = 16: one launch for all heads on the
+// CUDA cores (exact fp32) instead of H skinny GEMMs; V stays in shared memory.
+constexpr int HP_THREADS = 384;
+constexpr int HP_MAXC = 4;           // output columns per thread => H*P <= 1536
+
+__global__ void __launch_bounds__(HP_THREADS)
+headproj_fwd_kernel(const float* __restrict__ quad, const float* __restrict__ V, int64_t B, int H, int R, int P,
+                    float* __restrict__ inter) {
+  extern __shared__ float hp_sm[];
+  float* Vs = hp_sm;                    // H*R*P
+  float* qs = Vs + H * R * P;           // 4 rows x H*R
+  const int C = H * R, HPd = H * P;
+  for (int i = threadIdx.x; i < C * P; i += HP_THREADS) Vs[i] = V[i];
+  for (int64_t b0 = (int64_t)blockIdx.x * 4; b0 < B; b0 += (int64_t)gridDim.x * 4) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * C; i += HP_THREADS) {
+      const int64_t b = b0 + i / C;
+      qs[i] = b < B ? quad[b * C + i % C] : 0.f;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < HPd; c += HP_THREADS) {
+      const int h = c / P, p = c % P;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int r = 0; r < R; ++r) {
+        const float v = Vs[(h * R + r) * P + p];
+        a0 = fmaf(qs[h * R + r], v, a0); a1 = fmaf(qs[C + h * R + r], v, a1);
+        a2 = fmaf(qs[2 * C + h * R + r], v, a2); a3 = fmaf(qs[3 * C + h * R + r], v, a3);
+      }
+      if (b0 < B) inter[b0 * HPd + c] = a0;
+      if (b0 + 1 < B) inter[(b0 + 1) * HPd + c] = a1;
+      if (b0 + 2 < B) inter[(b0 + 2) * HPd + c] = a2;
+      if (b0 + 3 < B) inter[(b0 + 3) * HPd + c] = a3;
+    }
+  }
+}
+
+// dquad[b, h*R + r] = sum_p dinter[b, h*P + p] * V[h][r][p] ;  dV partial[cta][h][r][p] = sum_{b in cta} quad * dinter
+template <int RMAX>
+__global__ void __launch_bounds__(HP_THREADS)
+headproj_bwd_kernel(const float* __restrict__ quad, const float* __restrict__ dinter, const float* __restrict__ V, int64_t B,
+                    int H, int R, int P, float* __restrict__ dquad, float* __restrict__ dv_partial) {
+  extern __shared__ float hp_sm[];
+  const int C = H * R, HPd = H * P, PS = P + 1;
+  float* Vs = hp_sm;                    // C x (P+1)
+  float* ds = Vs + C * PS;              // H*P : dinter row
+  float* qs = ds + HPd;                 // C   : quad row
+  for (int i = threadIdx.x; i < C * P; i += HP_THREADS) Vs[(i / P) * PS + i % P] = V[i];
+  float acc[HP_MAXC][RMAX];
+#pragma unroll
+  for (int k = 0; k < HP_MAXC; ++k)
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) acc[k][r] = 0.f;
+  int parts = 1;                        // threads cooperating on one dquad element: largest power of two <= min(32, threads/C)
+  while (parts * 2 <= 32 && parts * 2 * C <= HP_THREADS) parts *= 2;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < HPd; i += HP_THREADS) ds[i] = dinter[b * HPd + i];
+    for (int i = threadIdx.x; i < C; i += HP_THREADS) qs[i] = quad[b * C + i];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < HP_MAXC; ++k) {
+      const int c = threadIdx.x + k * HP_THREADS;
+      if (c < HPd) {
+        const int h = c / P;
+        const float d = ds[c];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r)
+          if (r < R) acc[k][r] = fmaf(qs[h * R + r], d, acc[k][r]);
+      }
+    }
+    if (threadIdx.x < C * parts) {
+      const int cc = threadIdx.x / parts, part = threadIdx.x % parts, h = cc / R;
+      const int span = (P + parts - 1) / parts, p0 = part * span, p1 = min(P, p0 + span);
+      float a = 0.f;
+      for (int pp = p0; pp < p1; ++pp) a = fmaf(ds[h * P + pp], Vs[cc * PS + pp], a);
+      for (int o = parts >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (part == 0) dquad[b * C + cc] = a;
+    }
+  }
+  float* out = dv_partial + (int64_t)blockIdx.x * C * P;
+#pragma unroll
+  for (int k = 0; k < HP_MAXC; ++k) {
+    const int c = threadIdx.x + k * HP_THREADS;
+    if (c < HPd) {
+      const int h = c / P, p = c % P;
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r)
+        if (r < R) out[(h * R + r) * P + p] = acc[k][r];
+    }
+  }
+}
+
+__global__ void headproj_reduce_kernel(const float* __restrict__ partial, int n_part, int n, float* __restrict__ dV) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int c = 0; c < n_part; ++c) a += partial[(int64_t)c * n + i];
+  dV[i] = a;
+}
+
 }  // namespace b200ctr
 
 using namespace b200ctr;
@@ -260,5 +362,50 @@ extern "C" int b200ctr_se_apply_bwd(const float* dout, int64_t ld_dout, const fl
   if (B * C == 0) return B200CTR_OK;
   se_apply_bwd_kernel<<<(unsigned)ceil_div(B * C, 256), 256, 0, as_stream(stream)>>>(dout, ld_dout, inter, gate, dmean, inv_B, B, C, dinter, gprod, drop);
   B200_LAUNCH_CHECK("se_apply_bwd_kernel");
+  return B200CTR_OK;
+}
+
+static bool headproj_ok(int H, int R, int P) {
+  const int C = H * R;
+  if (H <= 0 || R <= 0 || P <= 0 || R > 32 || H * P > HP_MAXC * HP_THREADS || C > HP_THREADS) return false;
+  return ((size_t)C * (P + 1) + (size_t)H * P + 5 * C) * 4 <= 200 * 1024;
+}
+
+extern "C" int b200ctr_headproj_fwd(const float* quad, const float* V, int64_t B, int H, int R, int P, float* inter, void* stream) {
+  B200_REQUIRE(quad && V && inter, B200CTR_E_INVALID_ARG, "headproj_fwd: null pointer");
+  B200_REQUIRE(headproj_ok(H, R, P), B200CTR_E_UNSUPPORTED_SHAPE, "headproj_fwd: heads=%d rank=%d proj=%d unsupported", H, R, P);
+  if (B == 0) return B200CTR_OK;
+  const size_t smem = ((size_t)H * R * P + 4 * H * R) * 4;
+  cudaError_t e = cudaFuncSetAttribute(headproj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(headproj_fwd smem)");
+  const int grid = (int)std::min<int64_t>(ceil_div(B, 4), (int64_t)num_sms() * 2);
+  headproj_fwd_kernel<<<grid, HP_THREADS, smem, as_stream(stream)>>>(quad, V, B, H, R, P, inter);
+  B200_LAUNCH_CHECK("headproj_fwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int64_t b200ctr_headproj_bwd_workspace_bytes(int H, int R, int P) { return (int64_t)num_sms() * H * R * P * 4; }
+
+extern "C" int b200ctr_headproj_bwd(const float* quad, const float* dinter, const float* V, int64_t B, int H, int R, int P,
+                                    float* dquad, float* dV, void* workspace, void* stream) {
+  B200_REQUIRE(quad && dinter && V && dquad && dV && workspace, B200CTR_E_INVALID_ARG, "headproj_bwd: null pointer");
+  B200_REQUIRE(headproj_ok(H, R, P), B200CTR_E_UNSUPPORTED_SHAPE, "headproj_bwd: heads=%d rank=%d proj=%d unsupported", H, R, P);
+  B200_REQUIRE(B > 0, B200CTR_E_INVALID_ARG, "headproj_bwd: empty batch");
+  const int C = H * R;
+  const size_t smem = ((size_t)C * (P + 1) + (size_t)H * P + C) * 4;
+  const int grid = (int)std::min<int64_t>(B, (int64_t)num_sms());
+  cudaStream_t st = as_stream(stream);
+#define HP_LAUNCH(RM)                                                                                              \
+  do {                                                                                                             \
+    cudaError_t e = cudaFuncSetAttribute(headproj_bwd_kernel<RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(headproj_bwd smem)");                          \
+    headproj_bwd_kernel<RM><<<grid, HP_THREADS, smem, st>>>(quad, dinter, V, B, H, R, P, dquad, (float*)workspace); \
+  } while (0)
+  if (R <= 8) HP_LAUNCH(8); else if (R <= 16) HP_LAUNCH(16); else HP_LAUNCH(32);
+#undef HP_LAUNCH
+  B200_LAUNCH_CHECK("headproj_bwd_kernel");
+  const int n = C * P;
+  headproj_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, n, dV);
+  B200_LAUNCH_CHECK("headproj_reduce_kernel");
   return B200CTR_OK;
 }
