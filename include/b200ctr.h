@@ -150,6 +150,18 @@ int b200ctr_retrieve_bwd(const int32_t* tok, const float* q, const float* emb_at
                          const float* dsel_rep, const float* dvals, int64_t B, int K, int D, int pad_id,
                          float* dq, float* datt_dense, float* drep_dense, void* stream);
 
+/* Row-sharded form (data parallel, one process per GPU): row r of a table lives on shard r % n_shards at local row
+ * r / n_shards.  att_shards / rep_shards / d*_shards are HOST arrays of n_shards device pointers (peer-mapped over
+ * NVLink for the remote shards), so the gather and the gradient scatter cross GPUs inside the kernel.
+ * n_shards is a power of two <= 8; n_shards == 1 is the plain layout above.                                  */
+int b200ctr_retrieve_fwd_sharded(const void* seq, int idx_is_64, const float* q, const float* const* att_shards,
+                                 const float* const* rep_shards, int n_shards, const float* rec, int64_t B, int L, int K,
+                                 int D, int pad_id, int64_t vocab, float* sel_rep, float* vals, int32_t* idx, int32_t* tok,
+                                 void* stream);
+int b200ctr_retrieve_bwd_sharded(const int32_t* tok, const float* q, const float* const* att_shards, int n_shards,
+                                 const float* dsel_rep, const float* dvals, int64_t B, int K, int D, int pad_id,
+                                 float* dq, float* const* datt_shards, float* const* drep_shards, void* stream);
+
 /* ---- DARE encoder layer pieces  (dare.py:29-37, 53-70) ---------------------------------------------------
  * attention: qkv (M=B*K, 3D) packed [q|k|v]; bias[i,j] = relmean[j-i+max_len] (relmean = mean over heads of
  *   pbias.rel.weight, length 2*max_len+1, may be NULL); softmax(q k^T/sqrt(hd) + bias); dropout on probabilities;

@@ -1,25 +1,40 @@
 // K2: DARE target-aware retrieval (reference src/models/dare.py:116-138).
 //
-// forward, one CTA per sample:
-//   1. the (L,) token row is staged in shared memory (coalesced);
+// forward (retrieve_fwd_warp_kernel), ONE WARP per sample, no CTA-wide barrier anywhere:
+//   1. the (L,) token row is staged in the warp's slice of shared memory (coalesced);
 //   2. every non-pad position's emb_att row (D=64 fp32 = 256 B) is fetched by one half-warp as 16 x 128-bit
-//      no-allocate loads, 4 rows in flight per half-warp (64 rows / 16 KB in flight per CTA); pad positions
-//      are never fetched (their score is the constant -1e9);
+//      no-allocate loads, 8 rows in flight per half-warp; pad positions are never fetched (score = -1e9);
 //   3. score = dot(row, q) in a FIXED order (per-lane 4-term fma chain, then xor-tree 8,4,2,1) + rec[p];
-//   4. scores and positions are packed into 64-bit keys (~orderable(score) << 32 | position) and sorted by a
-//      CTA bitonic network => sorted top-K directly in the canonical order (score desc, position asc);
+//   4. scores and positions become 64-bit keys (~orderable(score) << 32 | position), ceil(L/32) per lane in
+//      registers; the K-th smallest key is found by an MSB-first 8-bit radix select (warp-private histogram),
+//      the K selected keys are compacted and sorted by a register/shuffle bitonic network => the canonical
+//      order (score desc, position asc).  While one warp selects, the other warps of the SM keep gathering, so
+//      the kernel stays on the HBM roofline instead of the old CTA-wide 512-key bitonic sort's issue limit;
 //   5. only the K selected emb_rep rows are gathered and written with vals / idx / tok.
+// (retrieve_fwd_kernel, one CTA per sample with a full bitonic sort, remains for max_len > 640 or top_k > 256.)
 // Algorithmic bytes per sample: 8L (ids) + 4D*l (att rows) + 4D*Kv (rep rows) + 4D (q) + 4D*K + 12K (outputs).
 //
+// Row-sharded tables (data parallel, one process per GPU): row r lives on shard r % n at local row r / n; the
+// shard base pointers may be PEER memory (NVLink), so the gather and the gradient scatter cross GPUs inside
+// these kernels -- no staging copy, no collective (n is a power of two; n = 1 is the single-GPU layout).
+//
 // backward, one CTA per sample: dq = sum_k dvals_k * emb_att[tok_k]; table gradients are row-sparse
-// (K rows per table per sample) and accumulated with 128-bit vector atomics.
+// (K rows per table per sample) and accumulated with 128-bit vector atomics (into the owner's shard).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b200ctr {
 
 constexpr int RT_D = 64;
 constexpr int RT_THREADS = 256;
 constexpr float RT_PAD_SCORE = -1e9f;
+constexpr int RT_MAX_SHARDS = 8;
+
+struct RtShards {
+  float* p[RT_MAX_SHARDS];
+  int mask, shift;                       // shard = row & mask ; local row = row >> shift
+  __device__ __forceinline__ float4* row4(int t) const { return reinterpret_cast<float4*>(p[t & mask]) + (int64_t)(t >> shift) * (RT_D / 4); }
+};
 
 __device__ __forceinline__ uint32_t orderable(float s) {
   uint32_t u = __float_as_uint(s);
@@ -28,8 +43,8 @@ __device__ __forceinline__ uint32_t orderable(float s) {
 
 template <typename IT>
 __global__ void __launch_bounds__(RT_THREADS)
-retrieve_fwd_kernel(const IT* __restrict__ seq, const float* __restrict__ q, const float* __restrict__ emb_att,
-                    const float* __restrict__ emb_rep, const float* __restrict__ rec, int L, int LP, int K, int pad_id,
+retrieve_fwd_kernel(const IT* __restrict__ seq, const float* __restrict__ q, const __grid_constant__ RtShards emb_att,
+                    const __grid_constant__ RtShards emb_rep, const float* __restrict__ rec, int L, int LP, int K, int pad_id,
                     int64_t vocab, float* __restrict__ sel_rep, float* __restrict__ vals, int32_t* __restrict__ idx,
                     int32_t* __restrict__ tok_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -51,7 +66,6 @@ retrieve_fwd_kernel(const IT* __restrict__ seq, const float* __restrict__ q, con
   const float4 qv = *reinterpret_cast<const float4*>(q + b * RT_D + hl * 4);
   __syncthreads();
 
-  const float4* att4 = reinterpret_cast<const float4*>(emb_att);
   // loop bounds are warp-uniform (both half-warps of a warp run the same trip count) so the full-mask
   // shuffles below are always executed by all 32 lanes
   for (int base = 0; base < L; base += NHW * 4) {
@@ -62,7 +76,7 @@ retrieve_fwd_kernel(const IT* __restrict__ seq, const float* __restrict__ q, con
       int p = base + hw + u * NHW;
       t[u] = (p < L) ? toks[p] : pad_id;
       r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t[u] != pad_id) r[u] = ldg_nc_f4(att4 + (int64_t)t[u] * (RT_D / 4) + hl);
+      if (t[u] != pad_id) r[u] = ldg_nc_f4(emb_att.row4(t[u]) + hl);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -106,7 +120,6 @@ retrieve_fwd_kernel(const IT* __restrict__ seq, const float* __restrict__ q, con
     idx[b * K + k] = p;
     tok_out[b * K + k] = toks[p];
   }
-  const float4* rep4 = reinterpret_cast<const float4*>(emb_rep);
   float4* out4 = reinterpret_cast<float4*>(sel_rep + b * (int64_t)K * RT_D);
   for (int k0 = hw; k0 < K; k0 += NHW * 4) {
     float4 r[4];
@@ -116,7 +129,7 @@ retrieve_fwd_kernel(const IT* __restrict__ seq, const float* __restrict__ q, con
       r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (k < K) {
         int t = toks[(int)(keys[k] & 0xffffffffu)];
-        if (t != pad_id) r[u] = ldg_nc_f4(rep4 + (int64_t)t * (RT_D / 4) + hl);
+        if (t != pad_id) r[u] = ldg_nc_f4(emb_rep.row4(t) + hl);
       }
     }
 #pragma unroll
@@ -127,30 +140,216 @@ retrieve_fwd_kernel(const IT* __restrict__ seq, const float* __restrict__ q, con
   }
 }
 
+
+__device__ __forceinline__ float unorderable(uint32_t v) {      // inverse of orderable()
+  return __uint_as_float((v >> 31) ? (v ^ 0x80000000u) : ~v);
+}
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+  const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+// NKEYS = ceil(L / 32) keys per lane; R = sorted output slots per lane (32 * R >= K)
+template <typename IT, int NKEYS, int R>
+__global__ void __launch_bounds__(RT_THREADS)
+retrieve_fwd_warp_kernel(const IT* __restrict__ seq, const float* __restrict__ q, const __grid_constant__ RtShards emb_att,
+                         const __grid_constant__ RtShards emb_rep, const float* __restrict__ rec, int64_t B, int L, int K, int pad_id,
+                         int64_t vocab, float* __restrict__ sel_rep, float* __restrict__ vals, int32_t* __restrict__ idx,
+                         int32_t* __restrict__ tok_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int KP = 32 * R;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hl = lane & 15, hw = lane >> 4;
+  const int64_t b = (int64_t)blockIdx.x * (RT_THREADS / 32) + warp;
+  if (b >= B) return;                                           // warp-uniform; no CTA barrier is used below
+  const int LA = (L + 3) & ~3;
+  unsigned char* mine = smem_raw + (size_t)warp * ((size_t)LA * 8 + 1024 + (size_t)KP * 8);
+  int32_t* toks = reinterpret_cast<int32_t*>(mine);                                   // L
+  float* scores = reinterpret_cast<float*>(mine + (size_t)LA * 4);                    // L
+  int* hist = reinterpret_cast<int*>(mine + (size_t)LA * 8);                          // 256
+  unsigned long long* selk = reinterpret_cast<unsigned long long*>(mine + (size_t)LA * 8 + 1024);   // KP
+
+  for (int p = lane; p < L; p += 32) {
+    int64_t t = (int64_t)seq[b * L + p];
+    t = t < 0 ? 0 : (t >= vocab ? vocab - 1 : t);     // memory-safe clamp (reference would raise on OOB)
+    toks[p] = (int32_t)t;
+  }
+  const float4 qv = *reinterpret_cast<const float4*>(q + b * RT_D + hl * 4);
+  __syncwarp();
+
+  // ---- gather + score: each half-warp owns 8 consecutive positions per iteration, all 8 row loads in flight ----
+  for (int base = 0; base < L; base += 16) {
+    float4 r[8];
+    int t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int p = base + hw * 8 + u;
+      t[u] = (p < L) ? toks[p] : pad_id;
+      r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t[u] != pad_id) r[u] = ldg_nc_f4(emb_att.row4(t[u]) + hl);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int p = base + hw * 8 + u;
+      float d = r[u].x * qv.x;
+      d = fmaf(r[u].y, qv.y, d);
+      d = fmaf(r[u].z, qv.z, d);
+      d = fmaf(r[u].w, qv.w, d);
+      d += __shfl_xor_sync(0xffffffffu, d, 8);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      if (hl == 0 && p < L) scores[p] = (t[u] != pad_id) ? d + rec[p] : RT_PAD_SCORE;
+    }
+  }
+  __syncwarp();
+
+  // ---- keys: position p = r*32 + lane; smaller key = better (score desc, position asc) ----
+  unsigned long long key[NKEYS];
+#pragma unroll
+  for (int r = 0; r < NKEYS; ++r) {
+    const int p = r * 32 + lane;
+    key[r] = p < L ? (((unsigned long long)(~orderable(scores[p])) << 32) | (unsigned)p) : ~0ULL;
+  }
+  // ---- radix select of the K-th smallest key (MSB first, 8 bits per pass) ----
+  unsigned long long prefix = 0ULL, thr = ~0ULL;
+  int k_rem = K;
+#pragma unroll 1
+  for (int shift = 56; shift >= 0; shift -= 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < NKEYS; ++r) {
+      const bool match = (shift == 56) || ((key[r] >> (shift + 8)) == (prefix >> (shift + 8)));
+      if (match && key[r] != ~0ULL) atomicAdd(&hist[(int)((key[r] >> shift) & 255ULL)], 1);
+    }
+    __syncwarp();
+    int c[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; sum += c[i]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int excl = incl - sum;
+    const uint32_t hit = __ballot_sync(0xffffffffu, excl < k_rem && k_rem <= incl);
+    const int src = __ffs(hit) - 1;                  // exactly one lane (K <= number of real keys)
+    int bin = 0, below = excl, cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (cnt == 0) {
+        if (below + c[i] >= k_rem) { bin = lane * 8 + i; cnt = c[i]; }
+        else below += c[i];
+      }
+    }
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    below = __shfl_sync(0xffffffffu, below, src);
+    cnt = __shfl_sync(0xffffffffu, cnt, src);
+    k_rem -= below;
+    prefix |= (unsigned long long)bin << shift;
+    __syncwarp();
+    if (cnt == k_rem) {                              // every key of this bin is selected: threshold found
+      thr = shift ? (prefix | ((1ULL << shift) - 1ULL)) : prefix;
+      break;
+    }
+  }
+  // ---- compact the K selected keys, then sort them (ascending key) in registers ----
+  for (int i = lane; i < KP; i += 32) selk[i] = ~0ULL;
+  __syncwarp();
+  int basec = 0;
+#pragma unroll
+  for (int r = 0; r < NKEYS; ++r) {
+    const bool take = key[r] <= thr && key[r] != ~0ULL;
+    const uint32_t bal = __ballot_sync(0xffffffffu, take);
+    if (take) selk[basec + __popc(bal & ((1u << lane) - 1u))] = key[r];
+    basec += __popc(bal);
+  }
+  __syncwarp();
+  unsigned long long sk[R];                           // element index i = lane * R + r
+#pragma unroll
+  for (int r = 0; r < R; ++r) sk[r] = selk[lane * R + r];
+#pragma unroll
+  for (int k = 2; k <= KP; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= R) {                                   // partner in another lane
+        const int lm = j / R;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const unsigned long long other = shfl_xor_u64(sk[r], lm);
+          const int i = lane * R + r;
+          const bool up = (i & k) == 0, lower = (i & j) == 0;
+          const bool take_min = (up == lower);
+          sk[r] = take_min ? (other < sk[r] ? other : sk[r]) : (other > sk[r] ? other : sk[r]);
+        }
+      } else {                                        // partner in this lane's registers
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & j) == 0) {
+            const int i = lane * R + r;
+            const bool up = (i & k) == 0;
+            const unsigned long long a = sk[r], c2 = sk[r | j];
+            if ((a > c2) == up) { sk[r] = c2; sk[r | j] = a; }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) selk[lane * R + r] = sk[r];
+  __syncwarp();
+  for (int k = lane; k < K; k += 32) {
+    const unsigned long long kk = selk[k];
+    const int p = (int)(kk & 0xffffffffULL);
+    vals[b * K + k] = unorderable(~(uint32_t)(kk >> 32));
+    idx[b * K + k] = p;
+    tok_out[b * K + k] = toks[p];
+  }
+  float4* out4 = reinterpret_cast<float4*>(sel_rep + b * (int64_t)K * RT_D);
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    float4 r[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + hw * 8 + u;
+      r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K) {
+        const int t = toks[(int)(selk[k] & 0xffffffffULL)];
+        if (t != pad_id) r[u] = ldg_nc_f4(emb_rep.row4(t) + hl);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + hw * 8 + u;
+      if (k < K) out4[k * (RT_D / 4) + hl] = r[u];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128)
-retrieve_bwd_kernel(const int32_t* __restrict__ tok, const float* __restrict__ q, const float* __restrict__ emb_att,
+retrieve_bwd_kernel(const int32_t* __restrict__ tok, const float* __restrict__ q, const __grid_constant__ RtShards emb_att,
                     const float* __restrict__ dsel_rep, const float* __restrict__ dvals, int K, int pad_id,
-                    float* __restrict__ dq, float* __restrict__ datt, float* __restrict__ drep) {
+                    float* __restrict__ dq, const __grid_constant__ RtShards datt, const __grid_constant__ RtShards drep, int has_datt, int has_drep) {
   __shared__ float4 red[128];
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x, hl = tid & 15, hw = tid >> 4;
   constexpr int NHW = 8;
   const float4 qv = *reinterpret_cast<const float4*>(q + b * RT_D + hl * 4);
-  const float4* att4 = reinterpret_cast<const float4*>(emb_att);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = hw; k < K; k += NHW) {
     int t = tok[b * K + k];
     if (t == pad_id) continue;                      // masked_fill blocks the gradient; padding_idx row gets none
     float dv = dvals[b * K + k];
-    float4 a = ldg_nc_f4(att4 + (int64_t)t * (RT_D / 4) + hl);
+    float4 a = ldg_nc_f4(emb_att.row4(t) + hl);
     acc.x = fmaf(dv, a.x, acc.x); acc.y = fmaf(dv, a.y, acc.y); acc.z = fmaf(dv, a.z, acc.z); acc.w = fmaf(dv, a.w, acc.w);
-    if (datt) {
+    if (has_datt) {
       float4 g = make_float4(dv * qv.x, dv * qv.y, dv * qv.z, dv * qv.w);
-      atomicAdd(reinterpret_cast<float4*>(datt + (int64_t)t * RT_D) + hl, g);
+      atomicAdd(datt.row4(t) + hl, g);
     }
-    if (drep) {
+    if (has_drep) {
       float4 g = *reinterpret_cast<const float4*>(dsel_rep + (b * K + k) * (int64_t)RT_D + hl * 4);
-      atomicAdd(reinterpret_cast<float4*>(drep + (int64_t)t * RT_D) + hl, g);
+      atomicAdd(drep.row4(t) + hl, g);
     }
   }
   red[tid] = acc;
@@ -170,38 +369,110 @@ retrieve_bwd_kernel(const int32_t* __restrict__ tok, const float* __restrict__ q
 
 using namespace b200ctr;
 
-extern "C" int b200ctr_retrieve_fwd(const void* seq, int idx_is_64, const float* q, const float* emb_att,
-                                    const float* emb_rep, const float* rec, int64_t B, int L, int K, int D, int pad_id,
-                                    int64_t vocab, float* sel_rep, float* vals, int32_t* idx, int32_t* tok, void* stream) {
-  B200_REQUIRE(seq && q && emb_att && emb_rep && rec && sel_rep && vals && idx && tok, B200CTR_E_INVALID_ARG,
+static int make_shards(RtShards& out, const float* const* ptrs, int n, const char* what) {
+  if (n < 1 || n > RT_MAX_SHARDS || (n & (n - 1))) {
+    set_error("%s: n_shards=%d unsupported (power of two, 1..%d)", what, n, RT_MAX_SHARDS);
+    return B200CTR_E_UNSUPPORTED_SHAPE;
+  }
+  int shift = 0;
+  while ((1 << shift) < n) ++shift;
+  out.mask = n - 1; out.shift = shift;
+  for (int i = 0; i < RT_MAX_SHARDS; ++i) out.p[i] = const_cast<float*>(ptrs && i < n ? ptrs[i] : nullptr);
+  for (int i = 0; i < n; ++i)
+    if (!out.p[i]) { set_error("%s: shard %d is NULL", what, i); return B200CTR_E_INVALID_ARG; }
+  return B200CTR_OK;
+}
+
+template <typename IT>
+static int launch_retrieve_fwd(const IT* seq, const float* q, const RtShards& att, const RtShards& rep, const float* rec, int64_t B,
+                               int L, int K, int pad_id, int64_t vocab, float* sel_rep, float* vals, int32_t* idx, int32_t* tok,
+                               cudaStream_t st) {
+  const int nkeys = (L + 31) / 32;
+  static const bool force_cta = getenv("B200CTR_RETRIEVE_CTA") != nullptr;
+  if (nkeys <= 20 && K <= 256 && !force_cta) {
+    const int R = K <= 64 ? 2 : (K <= 128 ? 4 : 8);
+    const int LA = (L + 3) & ~3;
+    const size_t smem = (size_t)(RT_THREADS / 32) * ((size_t)LA * 8 + 1024 + (size_t)32 * R * 8);
+    const unsigned grid = (unsigned)ceil_div(B, (int64_t)(RT_THREADS / 32));
+#define RT_LAUNCH(NK_, R_)                                                                                           \
+    do {                                                                                                             \
+      auto fn = retrieve_fwd_warp_kernel<IT, NK_, R_>;                                                               \
+      if (smem > 48 * 1024) {                                                                                        \
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(retrieve_fwd smem)");                        \
+      }                                                                                                              \
+      fn<<<grid, RT_THREADS, smem, st>>>(seq, q, att, rep, rec, B, L, K, pad_id, vocab, sel_rep, vals, idx, tok);    \
+    } while (0)
+#define RT_LAUNCH_R(NK_) do { if (R == 2) RT_LAUNCH(NK_, 2); else if (R == 4) RT_LAUNCH(NK_, 4); else RT_LAUNCH(NK_, 8); } while (0)
+    if (nkeys <= 4) RT_LAUNCH_R(4);
+    else if (nkeys <= 8) RT_LAUNCH_R(8);
+    else if (nkeys <= 13) RT_LAUNCH_R(13);
+    else if (nkeys <= 16) RT_LAUNCH_R(16);
+    else RT_LAUNCH_R(20);
+#undef RT_LAUNCH_R
+#undef RT_LAUNCH
+    return B200CTR_OK;
+  }
+  int LP = 2;
+  while (LP < L) LP <<= 1;
+  size_t smem = (size_t)LP * 8 + (size_t)L * 8;
+  retrieve_fwd_kernel<IT><<<(unsigned)B, RT_THREADS, smem, st>>>(seq, q, att, rep, rec, L, LP, K, pad_id, vocab, sel_rep, vals, idx, tok);
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_retrieve_fwd_sharded(const void* seq, int idx_is_64, const float* q, const float* const* att_shards,
+                                            const float* const* rep_shards, int n_shards, const float* rec, int64_t B, int L,
+                                            int K, int D, int pad_id, int64_t vocab, float* sel_rep, float* vals, int32_t* idx,
+                                            int32_t* tok, void* stream) {
+  B200_REQUIRE(seq && q && att_shards && rep_shards && rec && sel_rep && vals && idx && tok, B200CTR_E_INVALID_ARG,
                "retrieve_fwd: null pointer");
   B200_REQUIRE(D == RT_D, B200CTR_E_UNSUPPORTED_SHAPE, "retrieve_fwd: emb_dim=%d unsupported (kernel is specialised for 64)", D);
   B200_REQUIRE(L >= 1 && L <= 4096, B200CTR_E_UNSUPPORTED_SHAPE, "retrieve_fwd: max_len=%d unsupported (1..4096)", L);
   B200_REQUIRE(K >= 1 && K <= L, B200CTR_E_INVALID_ARG, "retrieve_fwd: need 1 <= K <= L (K=%d, L=%d)", K, L);
+  RtShards att, rep;
+  int rc = make_shards(att, att_shards, n_shards, "retrieve_fwd(emb_att)");
+  if (rc) return rc;
+  rc = make_shards(rep, rep_shards, n_shards, "retrieve_fwd(emb_rep)");
+  if (rc) return rc;
   if (B == 0) return B200CTR_OK;
-  int LP = 2;
-  while (LP < L) LP <<= 1;
-  size_t smem = (size_t)LP * 8 + (size_t)L * 8;
   cudaStream_t st = as_stream(stream);
-  if (idx_is_64)
-    retrieve_fwd_kernel<int64_t><<<(unsigned)B, RT_THREADS, smem, st>>>((const int64_t*)seq, q, emb_att, emb_rep, rec, L, LP, K,
-                                                                          pad_id, vocab, sel_rep, vals, idx, tok);
-  else
-    retrieve_fwd_kernel<int32_t><<<(unsigned)B, RT_THREADS, smem, st>>>((const int32_t*)seq, q, emb_att, emb_rep, rec, L, LP, K,
-                                                                          pad_id, vocab, sel_rep, vals, idx, tok);
+  rc = idx_is_64 ? launch_retrieve_fwd<int64_t>((const int64_t*)seq, q, att, rep, rec, B, L, K, pad_id, vocab, sel_rep, vals, idx, tok, st)
+                 : launch_retrieve_fwd<int32_t>((const int32_t*)seq, q, att, rep, rec, B, L, K, pad_id, vocab, sel_rep, vals, idx, tok, st);
+  if (rc) return rc;
   B200_LAUNCH_CHECK("retrieve_fwd_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_retrieve_fwd(const void* seq, int idx_is_64, const float* q, const float* emb_att,
+                                    const float* emb_rep, const float* rec, int64_t B, int L, int K, int D, int pad_id,
+                                    int64_t vocab, float* sel_rep, float* vals, int32_t* idx, int32_t* tok, void* stream) {
+  B200_REQUIRE(emb_att && emb_rep, B200CTR_E_INVALID_ARG, "retrieve_fwd: null pointer");
+  return b200ctr_retrieve_fwd_sharded(seq, idx_is_64, q, &emb_att, &emb_rep, 1, rec, B, L, K, D, pad_id, vocab, sel_rep, vals, idx,
+                                      tok, stream);
+}
+
+extern "C" int b200ctr_retrieve_bwd_sharded(const int32_t* tok, const float* q, const float* const* att_shards, int n_shards,
+                                            const float* dsel_rep, const float* dvals, int64_t B, int K, int D, int pad_id,
+                                            float* dq, float* const* datt_shards, float* const* drep_shards, void* stream) {
+  B200_REQUIRE(tok && q && att_shards && dvals && dq, B200CTR_E_INVALID_ARG, "retrieve_bwd: null pointer");
+  B200_REQUIRE(!drep_shards || dsel_rep, B200CTR_E_INVALID_ARG, "retrieve_bwd: drep without dsel_rep");
+  B200_REQUIRE(D == RT_D, B200CTR_E_UNSUPPORTED_SHAPE, "retrieve_bwd: emb_dim=%d unsupported", D);
+  RtShards att, datt{}, drep{};
+  int rc = make_shards(att, att_shards, n_shards, "retrieve_bwd(emb_att)");
+  if (rc) return rc;
+  if (datt_shards) { rc = make_shards(datt, datt_shards, n_shards, "retrieve_bwd(datt)"); if (rc) return rc; }
+  if (drep_shards) { rc = make_shards(drep, drep_shards, n_shards, "retrieve_bwd(drep)"); if (rc) return rc; }
+  if (B == 0) return B200CTR_OK;
+  retrieve_bwd_kernel<<<(unsigned)B, 128, 0, as_stream(stream)>>>(tok, q, att, dsel_rep, dvals, K, pad_id, dq, datt, drep,
+                                                                   datt_shards ? 1 : 0, drep_shards ? 1 : 0);
+  B200_LAUNCH_CHECK("retrieve_bwd_kernel");
   return B200CTR_OK;
 }
 
 extern "C" int b200ctr_retrieve_bwd(const int32_t* tok, const float* q, const float* emb_att, const float* dsel_rep,
                                     const float* dvals, int64_t B, int K, int D, int pad_id, float* dq, float* datt_dense,
                                     float* drep_dense, void* stream) {
-  B200_REQUIRE(tok && q && emb_att && dvals && dq, B200CTR_E_INVALID_ARG, "retrieve_bwd: null pointer");
-  B200_REQUIRE(!drep_dense || dsel_rep, B200CTR_E_INVALID_ARG, "retrieve_bwd: drep without dsel_rep");
-  B200_REQUIRE(D == RT_D, B200CTR_E_UNSUPPORTED_SHAPE, "retrieve_bwd: emb_dim=%d unsupported", D);
-  if (B == 0) return B200CTR_OK;
-  retrieve_bwd_kernel<<<(unsigned)B, 128, 0, as_stream(stream)>>>(tok, q, emb_att, dsel_rep, dvals, K, pad_id, dq, datt_dense,
-                                                                   drep_dense);
-  B200_LAUNCH_CHECK("retrieve_bwd_kernel");
-  return B200CTR_OK;
+  B200_REQUIRE(emb_att, B200CTR_E_INVALID_ARG, "retrieve_bwd: null pointer");
+  return b200ctr_retrieve_bwd_sharded(tok, q, &emb_att, 1, dsel_rep, dvals, B, K, D, pad_id, dq, datt_dense ? &datt_dense : nullptr,
+                                      drep_dense ? &drep_dense : nullptr, stream);
 }
