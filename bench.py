@@ -226,7 +226,8 @@ def run_cuda(args):
         model = b200ctr.CTRModel(cfg, vocab, configs.N_NUM, configs.N_NUM, configs.cardinals(cfg), cols)
     model.train()
     steps_per_epoch = 1000
-    trainer = b200ctr.FusedTrainer(model, cfg, steps_per_epoch=steps_per_epoch, process_group=pg)
+    trainer = b200ctr.FusedTrainer(model, cfg, steps_per_epoch=steps_per_epoch, process_group=pg,
+                                   shard_tables=(world > 1 and not args.replicate_tables))
     schema = synth.ToySchema(cfg, configs.N_NUM, configs.N_NUM, seed=cfg["seed"])
     NB = 4
     host, dev_b = [], []
@@ -327,7 +328,9 @@ def run_cuda(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.amp == "bf16" else "fp32", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, B), "global_batch": B * world, "parallelism": f"dp{world}",
+            "config": {"workload": workload_name(cfg, B), "global_batch": B * world, "parallelism": (f"dp{world}" if world == 1 else
+                                       f"dp{world} over the batch; seq tables " + ("replicated" if args.replicate_tables else
+                                       f"row-sharded {world}-way, gathered/scattered through NVLink peer memory inside the kernels")),
                        "l2_policy": f"{NB} distinct batches rotate; each step touches >10 GB (two 2.56 GB tables + optimizer state "
                                     f"+ activations), far above the 126 MB L2",
                        "seq_vocab": vocab},
@@ -362,6 +365,9 @@ def main():
     ap.add_argument("--vocab", type=int, default=10_000_000)
     ap.add_argument("--ref-batch", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicate-tables", action="store_true",
+                    help="N > 1: keep full replicas of the two sequence tables on every GPU (all-gather of gradient rows) "
+                         "instead of the default row-sharded tables gathered / scattered through peer memory")
     ap.add_argument("--amp", default="bf16", choices=["none", "bf16"],
                     help="matmul precision of the training step: bf16 = the reference's `amp: bf16` autocast mode on the "
                          "tcgen05 tensor cores (fp32 accumulate, fp32 master weights/optimizer); none = exact fp32 CUDA cores")

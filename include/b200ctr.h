@@ -42,6 +42,14 @@ int b200ctr_version(void);
 const char* b200ctr_last_error(void);
 /* 0 if the current device is sm_100 (B200); B200CTR_E_ARCH otherwise. */
 int b200ctr_check_device(void);
+/* Enable loads / stores / atomics from the current device into `peer_device`'s memory (row-sharded tables whose remote
+ * shards are mapped through CUDA IPC).  Idempotent.                                                            */
+int b200ctr_enable_peer_access(int peer_device);
+/* CUDA IPC plumbing for the row-sharded tables: export = 64-byte handle of the allocation containing `ptr` + the byte
+ * offset of `ptr` in it; import (on the consumer's current device) = base address of that allocation mapped into this
+ * process with peer access enabled.  An allocation must be imported only once per process (cache by handle).       */
+int b200ctr_ipc_export(const void* ptr, void* handle_out64, int64_t* offset_out);
+int b200ctr_ipc_import(const void* handle64, void** base_out);
 
 /* ---- dropout descriptor ------------------------------------------------------------------------- */
 typedef struct {
@@ -279,6 +287,10 @@ int b200ctr_rows_zero(const int32_t* tok, int64_t n_slots, int pad_id, const int
 int b200ctr_rowopt_push(void* hist4, float* C, float* S, float* logD, int64_t capacity, int64_t t,
                         float decay_mul, float step_size, float bc2_sqrt, float ema_d, float C_t, float S_t, float logD_t,
                         void* stream);
+/* Row-sharded tables: out[i] = local row (tok / n_shards) if tok is owned by `rank` (tok % n_shards == rank) and is
+ * not pad_id, else -1; the owner-side row kernels are then called with pad_id = -1 on the local shard.           */
+int b200ctr_rows_localize(const void* tok, int idx_is_64, int64_t n_slots, int pad_id, int n_shards, int rank,
+                          int32_t* out, void* stream);
 int b200ctr_rows_claim_any(const void* tok, int idx_is_64, int64_t n_slots, int pad_id, int64_t vocab, int32_t* owner,
                            void* stream);
 int b200ctr_rowopt_catchup(const void* tok, int idx_is_64, int64_t n_slots, int pad_id, int64_t vocab, const int32_t* owner,

@@ -21,7 +21,7 @@ def _build(cfg, z, dev):
     return m.to(dev).train()
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, shard):
     import torch.distributed as dist
     import b200ctr
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -31,27 +31,36 @@ def _worker(rank, world, port, out_path):
     try:
         z, cfg = load_case("qnn_concat")
         m = _build(cfg, z, dev)
-        tr = b200ctr.FusedTrainer(m, cfg, steps_per_epoch=cfg["golden"]["steps_per_epoch"], process_group=dist.group.WORLD)
+        tr = b200ctr.FusedTrainer(m, cfg, steps_per_epoch=cfg["golden"]["steps_per_epoch"], process_group=dist.group.WORLD,
+                                  shard_tables=shard)
+        assert tr.shard == shard
+        if shard:       # the full replicas are gone: each rank holds every other row
+            assert m.dare.emb_att.weight.numel() == 0 and tr.tables["dare.emb_att.weight"]["p"].shape[0] == (g_vocab(cfg) + world - 1) // world
         for s in range(3):
             batch, y = batch_of(z, s)
             B = y.shape[0]
             lo, hi = rank * B // world, (rank + 1) * B // world
             tr.step({k: v[lo:hi] for k, v in batch.items()}, y[lo:hi])
-        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}       # sharded: re-assembles the tables (collective)
         if rank == 0:
             torch.save(sd, out_path)
     finally:
         dist.destroy_process_group()
 
 
+def g_vocab(cfg):
+    return cfg["golden"]["seq_vocab"]
+
+
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_data_parallel_matches_single_gpu_global_batch(tmp_path):
+@pytest.mark.parametrize("shard", [False, True], ids=["replicated_tables", "row_sharded_tables_p2p"])
+def test_two_rank_data_parallel_matches_single_gpu_global_batch(tmp_path, shard):
     import torch.multiprocessing as mp
     import b200ctr
     z, cfg = load_case("qnn_concat")
     out = str(tmp_path / "dp.pt")
-    port = 29600 + (os.getpid() % 1000)
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    port = 29600 + (os.getpid() % 1000) + (500 if shard else 0)
+    mp.spawn(_worker, args=(2, port, out, shard), nprocs=2, join=True)
     dp = torch.load(out)
     dev = torch.device("cuda:0")
     m = _build(cfg, z, dev)

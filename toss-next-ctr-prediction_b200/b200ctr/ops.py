@@ -312,18 +312,73 @@ def add2d_(dst, src):
 
 
 # ---- DARE ------------------------------------------------------------------------------------------------------
+def enable_peer_access(peer_device: int):
+    """Let kernels on the current device dereference memory of `peer_device` (NVLink P2P)."""
+    check(_lib.load().b200ctr_enable_peer_access(int(peer_device)), "enable_peer_access")
+
+
+def ipc_export(t: torch.Tensor):
+    """(handle bytes, offset) of a CUDA tensor's memory for another process on this node."""
+    lib = _lib.load()
+    h = ctypes.create_string_buffer(64)
+    off = ctypes.c_int64(0)
+    check(lib.b200ctr_ipc_export(_p(t), h, ctypes.byref(off)), "ipc_export")
+    return bytes(h.raw), int(off.value)
+
+
+_IPC_BASES: dict = {}
+
+
+def ipc_import(handle: bytes, offset: int) -> int:
+    """Device address (valid on the current device, peer access enabled) of memory exported by another process."""
+    base = _IPC_BASES.get(handle)
+    if base is None:
+        lib = _lib.load()
+        out = ctypes.c_void_p(0)
+        check(lib.b200ctr_ipc_import(ctypes.create_string_buffer(handle, 64), ctypes.byref(out)), "ipc_import")
+        base = int(out.value)
+        _IPC_BASES[handle] = base            # an allocation may be opened only once per process
+    return base + offset
+
+
+class ShardedTable:
+    """A (vocab, D) table stored as n row-interleaved shards: row r lives in shard r % n at local row r // n.  `shards`
+    holds this rank's tensor and, for the other ranks, raw device addresses of their shards mapped through CUDA IPC
+    (peer memory over NVLink); the kernels dereference them directly."""
+
+    def __init__(self, shards: Sequence, vocab: int, D: int = 64):
+        n = len(shards)
+        if n < 1 or n > 8 or (n & (n - 1)):
+            raise _lib.B200CtrError(f"row-sharded tables need a power-of-two shard count <= 8, got {n}")
+        addrs = []
+        for t in shards:
+            if isinstance(t, torch.Tensor):
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 2
+                addrs.append(t.data_ptr())
+            else:
+                addrs.append(int(t))
+        self.shards, self.n, self.vocab, self.D = list(shards), n, int(vocab), D
+        self.ptrs = (ctypes.c_void_p * n)(*addrs)
+
+
 def retrieve_fwd(seq, q, emb_att, emb_rep, rec, K, pad_id):
     lib = _lib.load()
     B, L = seq.shape
     D = q.shape[1]
     dev = q.device
-    assert seq.is_contiguous() and q.is_contiguous() and emb_att.is_contiguous() and emb_rep.is_contiguous()
+    assert seq.is_contiguous() and q.is_contiguous()
     sel = torch.empty((B, K, D), device=dev, dtype=torch.float32)
     vals = torch.empty((B, K), device=dev, dtype=torch.float32)
     idx = torch.empty((B, K), device=dev, dtype=torch.int32)
     tok = torch.empty((B, K), device=dev, dtype=torch.int32)
-    _run("retrieve_fwd", lib.b200ctr_retrieve_fwd, _p(seq), _idx64(seq), _p(q), _p(emb_att), _p(emb_rep), _p(rec), B, L, K, D, pad_id,
-                                   emb_att.shape[0], _p(sel), _p(vals), _p(idx), _p(tok), _stream())
+    if isinstance(emb_att, ShardedTable):
+        assert isinstance(emb_rep, ShardedTable) and emb_rep.n == emb_att.n
+        _run("retrieve_fwd", lib.b200ctr_retrieve_fwd_sharded, _p(seq), _idx64(seq), _p(q), emb_att.ptrs, emb_rep.ptrs, emb_att.n,
+             _p(rec), B, L, K, D, pad_id, emb_att.vocab, _p(sel), _p(vals), _p(idx), _p(tok), _stream())
+    else:
+        assert emb_att.is_contiguous() and emb_rep.is_contiguous()
+        _run("retrieve_fwd", lib.b200ctr_retrieve_fwd, _p(seq), _idx64(seq), _p(q), _p(emb_att), _p(emb_rep), _p(rec), B, L, K, D,
+             pad_id, emb_att.shape[0], _p(sel), _p(vals), _p(idx), _p(tok), _stream())
     _count()
     return sel, vals, idx, tok
 
@@ -333,10 +388,23 @@ def retrieve_bwd(tok, q, emb_att, dsel_rep, dvals, pad_id, datt_dense=None, drep
     B, K = tok.shape
     D = q.shape[1]
     dq = torch.empty_like(q)
-    _run("retrieve_bwd", lib.b200ctr_retrieve_bwd, _p(tok), _p(q), _p(emb_att), _p(dsel_rep), _p(dvals), B, K, D, pad_id, _p(dq),
-                                   _p(datt_dense), _p(drep_dense), _stream())
+    if isinstance(emb_att, ShardedTable):
+        _run("retrieve_bwd", lib.b200ctr_retrieve_bwd_sharded, _p(tok), _p(q), emb_att.ptrs, emb_att.n, _p(dsel_rep), _p(dvals), B, K,
+             D, pad_id, _p(dq), datt_dense.ptrs if datt_dense is not None else None,
+             drep_dense.ptrs if drep_dense is not None else None, _stream())
+    else:
+        _run("retrieve_bwd", lib.b200ctr_retrieve_bwd, _p(tok), _p(q), _p(emb_att), _p(dsel_rep), _p(dvals), B, K, D, pad_id, _p(dq),
+             _p(datt_dense), _p(drep_dense), _stream())
     _count()
     return dq
+
+
+def rows_localize(tok, pad_id, n_shards, rank):
+    lib = _lib.load()
+    out = torch.empty(tok.shape, device=tok.device, dtype=torch.int32)
+    _run("rows_localize", lib.b200ctr_rows_localize, _p(tok), _idx64(tok), tok.numel(), pad_id, n_shards, rank, _p(out), _stream())
+    _count()
+    return out
 
 
 def _attn_tc(tc: Optional[bool], K: int, H: int, D: int) -> bool:

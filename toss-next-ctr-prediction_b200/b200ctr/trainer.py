@@ -22,6 +22,15 @@ optimizer that avoids the dense passes is the planned next step; see DESIGN.md.)
 
 Data parallel (one process per GPU): dense grads are all-reduced (NCCL), class counts (C3), the SE squeeze (C4)
 and the table-row gradients are exchanged so that N ranks with B/N samples each reproduce the 1-GPU global batch.
+
+Row-sharded sequence tables (shard_tables=True, the default for world > 1): row r of emb_att / emb_rep -- and its
+Adam moments, EMA shadow, gradient row and lazy-optimizer state -- lives only on rank r % N at local row r // N.
+Every rank maps the other ranks' parameter and gradient shards through CUDA IPC (peer memory over NVLink), so the
+retrieval kernel gathers remote rows and the backward kernel scatters gradient rows straight into the owner's shard:
+the exchange happens inside the kernels, tile by tile, with no staging buffer.  Per step the owners need to know which
+of their rows are read / touched: one all-gather of the token ids (before the forward) and one of the K selected
+tokens (after the backward); those two collectives double as the device-side barriers that order "owner caught the
+rows up" -> "peers read them" and "peers scattered gradients" -> "owner applies AdamW".
 """
 from __future__ import annotations
 
@@ -66,7 +75,7 @@ BIG_TABLES = ("dare.emb_att.weight", "dare.emb_rep.weight")
 
 class FusedTrainer:
     def __init__(self, model: CTRModel, cfg: dict, steps_per_epoch: int = 1, seed: Optional[int] = None,
-                 process_group=None, lazy_tables: bool = True):
+                 process_group=None, lazy_tables: bool = True, shard_tables: Optional[bool] = None):
         self.model, self.cfg = model, cfg
         self.spec: hp.ModelSpec = model._spec
         spec = self.spec
@@ -124,29 +133,97 @@ class FusedTrainer:
             self.Gv[n] = self.flat_g[o:o + p.numel()].view(p.shape)
         self.flat_ema = self.flat_p.clone() if self.ema_on else None
         self.tables: Dict[str, dict] = {}
-        for n in BIG_TABLES:
-            p = params[n].data
-            self.P[n] = p
-            t = dict(p=p, m=torch.zeros_like(p), v=torch.zeros_like(p), g=torch.zeros_like(p),
-                     ema=p.clone() if self.ema_on else None)
-            self.tables[n] = t
-            self.Gv[n] = t["g"]
-        self.vocab = params[BIG_TABLES[0]].shape[0]
+        self.vocab_global = params[BIG_TABLES[0]].shape[0]
+        self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
+        self.shard = (self.world > 1) if shard_tables is None else (bool(shard_tables) and self.world > 1)
         self.lazy = bool(lazy_tables)
+        if self.shard:
+            if not self.lazy:
+                raise ValueError("row-sharded tables use the row-lazy optimizer (lazy_tables=True)")
+            self._init_sharded_tables(params)
+        else:
+            for n in BIG_TABLES:
+                p = params[n].data
+                self.P[n] = p
+                t = dict(p=p, m=torch.zeros_like(p), v=torch.zeros_like(p), g=torch.zeros_like(p),
+                         ema=p.clone() if self.ema_on else None)
+                self.tables[n] = t
+                self.Gv[n] = t["g"]
+        self.vocab = self.tables[BIG_TABLES[0]]["p"].shape[0]          # rows held by this rank
         if self.lazy:
             cap = min(max(self.epochs * self.steps_per_epoch + 64, 4096), 1 << 22)
             self.hist = ops.RowHistory(dev, cap)
             for n in BIG_TABLES:
                 self.tables[n]["state"] = torch.zeros(self.vocab, device=dev, dtype=torch.int32)
-            # state_dict()/checkpointing through the nn.Module sees fully-updated tables
-            model.register_state_dict_pre_hook(lambda *a, **k: self.sync_tables())
+            # state_dict()/checkpointing through the nn.Module sees fully-updated (and, if sharded, re-assembled) tables
+            model.register_state_dict_pre_hook(lambda *a, **k: self.materialize_tables())
         self.owner = torch.empty(max(self.vocab, 1), device=dev, dtype=torch.int32)
         self.acc = torch.zeros(1, device=dev, dtype=torch.float64)
         self.coef = torch.ones(1, device=dev, dtype=torch.float32)
+        self._bar = torch.zeros(1, device=dev, dtype=torch.float32)      # payload of the barrier all-reduces
         self.total_norm = torch.zeros(1, device=dev, dtype=torch.float32)
         self.global_step = 0
         self.n_ema = 0
         self.cache: dict = {}
+
+    # ---- row-sharded tables ----------------------------------------------------------------------------------
+    def _init_sharded_tables(self, params):
+        """Keep rows rank::world of each big table (+ optimizer state) and map every peer's parameter / gradient
+        shard (cudaIpcOpenMemHandle with lazy peer access => NVLink loads / atomics from inside the kernels)."""
+        import torch.distributed as dist
+        N, rank, dev = self.world, self.rank, self.dev
+        if N & (N - 1) or N > 8:
+            raise ValueError(f"row-sharded tables need a power-of-two world size <= 8, got {N}")
+        rows_local = (self.vocab_global + N - 1) // N
+        for n in BIG_TABLES:
+            full = params[n].data
+            D = full.shape[1]
+            p = torch.zeros((rows_local, D), device=dev, dtype=torch.float32)
+            mine = full[rank::N]
+            p[:mine.shape[0]].copy_(mine)
+            g = torch.zeros_like(p)
+            t = dict(p=p, m=torch.zeros_like(p), v=torch.zeros_like(p), g=g, ema=p.clone() if self.ema_on else None)
+            self.tables[n] = t
+            params[n].data = torch.empty((0, D), device=dev, dtype=torch.float32)     # the full replica is released
+            del full, mine
+            shards = {}
+            for kind, tens in (("p", p), ("g", g)):
+                handles = [None] * N
+                dist.all_gather_object(handles, ops.ipc_export(tens), group=self.pg)
+                lst = [tens if r == rank else ops.ipc_import(*handles[r]) for r in range(N)]
+                shards[kind] = ops.ShardedTable(lst, self.vocab_global, D)
+            self.P[n] = shards["p"]
+            self.Gv[n] = shards["g"]
+        torch.cuda.empty_cache()
+        dist.barrier(group=self.pg)
+
+    def _all_gather_ids(self, ids: torch.Tensor) -> torch.Tensor:
+        """(n,) or (B, L) int ids of this rank -> the concatenation over ranks, int32 (device-side barrier as a side effect)."""
+        flat = ids.reshape(-1).to(torch.int32)
+        out = torch.empty((self.world * flat.numel(),), device=self.dev, dtype=torch.int32)
+        torch.distributed.all_gather_into_tensor(out, flat, group=self.pg)
+        return out
+
+    def materialize_tables(self):
+        """Fully-updated tables behind the nn.Module's parameters (state_dict / checkpoint / plain-module eval).
+        Sharded mode: COLLECTIVE -- every rank re-assembles the full (vocab, D) tables from the shards."""
+        self.sync_tables()
+        if not self.shard:
+            return
+        params = dict(self.model.named_parameters())
+        N = self.world
+        for n in BIG_TABLES:
+            p = self.tables[n]["p"]
+            buf = torch.empty((N,) + tuple(p.shape), device=self.dev, dtype=torch.float32)
+            torch.distributed.all_gather_into_tensor(buf, p, group=self.pg)
+            params[n].data = buf.permute(1, 0, 2).reshape(N * p.shape[0], p.shape[1])[:self.vocab_global].contiguous()
+
+    def release_tables(self):
+        """Drop the re-assembled replicas again (sharded mode)."""
+        if self.shard:
+            params = dict(self.model.named_parameters())
+            for n in BIG_TABLES:
+                params[n].data = torch.empty((0, self.spec.D), device=self.dev, dtype=torch.float32)
 
     # ---- helpers ---------------------------------------------------------------------------------------------
     def _G(self, name: str) -> torch.Tensor:
@@ -195,13 +272,21 @@ class FusedTrainer:
         if self.lazy:
             # rows this batch is about to read are brought to step t-1 (exactly what dense AdamW/EMA would hold)
             self.hist.push(self.global_step, lr, self.wd, d if self.ema_on else 1.0)
+            if self.shard:
+                # owners catch up the rows ANY rank is about to read; the all-gather is also the barrier that orders the
+                # previous step's owner-side AdamW before this step's peer reads
+                seq_l = ops.rows_localize(self._all_gather_ids(dbatch["seq"]), spec.pad_id, self.world, self.rank)
+                pad_l = -1
+            else:
+                seq_l, pad_l = dbatch["seq"], spec.pad_id
             if self.global_step > 1:
-                seq = dbatch["seq"]
-                ops.rows_claim_any(seq, spec.pad_id, self.vocab, self.owner)
+                ops.rows_claim_any(seq_l, pad_l, self.vocab, self.owner)
                 for n in BIG_TABLES:
                     t = self.tables[n]
-                    ops.rowopt_catchup(seq, spec.pad_id, self.owner, t["state"], t["p"], t["m"], t["v"], t["ema"],
+                    ops.rowopt_catchup(seq_l, pad_l, self.owner, t["state"], t["p"], t["m"], t["v"], t["ema"],
                                        self.global_step - 1, self.hist)
+            if self.shard:
+                self._allreduce(self._bar)          # barrier: every shard is caught up before any peer gathers from it
         hook = (lambda t: self._allreduce(t)) if self.world > 1 else None
         logits, aux, sv = hp.model_fwd(self.P, spec, dbatch, dc, self.cache, B_total=B_local * self.world, colsum_hook=hook)
         counts_override = None
@@ -219,14 +304,23 @@ class FusedTrainer:
                     g = self.Gv[n].view(-1)
                     ops.axpby(g, None, 1.0 / self.world, 0.0, out=g)
             self._allreduce(self.flat_g[:self.n_active])                                            # C2
-            tok = self._exchange_table_grads(tok)                                                   # C1
+            if not self.shard:
+                tok = self._exchange_table_grads(tok)                                               # C1 (replicated tables)
             self._allreduce(loss)
+        pad_t = spec.pad_id
+        if self.shard:
+            # C1 already happened inside retrieve_bwd (gradient rows scattered into the owners' shards over NVLink); the
+            # owners only need the touched row ids.  This all-gather also orders every peer's scatter before the update.
+            tok = ops.rows_localize(self._all_gather_ids(tok), spec.pad_id, self.world, self.rank)
+            pad_t = -1
         # ---- global-norm clip (coef stays on the device) ----
         self.acc.zero_()
-        ops.sqnorm_(self.flat_g[:self.n_active], self.acc)
-        ops.rows_claim(tok, spec.pad_id, self.owner)
+        ops.rows_claim(tok, pad_t, self.owner)
         for n in BIG_TABLES:
-            ops.rows_sqnorm(tok, spec.pad_id, self.owner, self.tables[n]["g"], self.acc)
+            ops.rows_sqnorm(tok, pad_t, self.owner, self.tables[n]["g"], self.acc)
+        if self.shard:
+            self._allreduce(self.acc)               # C5: each owner contributes the squared norm of its rows
+        ops.sqnorm_(self.flat_g[:self.n_active], self.acc)
         ops.clip_coef(self.acc, self.clip, self.coef, self.total_norm)
         # ---- AdamW (+EMA) ----
         ops.adamw_ema_(self.flat_p[:self.n_active], self.flat_g[:self.n_active], self.flat_m, self.flat_v,
@@ -234,11 +328,11 @@ class FusedTrainer:
         for n in BIG_TABLES:
             t = self.tables[n]
             if self.lazy:
-                ops.rowopt_update(tok, spec.pad_id, self.owner, t["state"], t["p"], t["g"], t["m"], t["v"], t["ema"],
+                ops.rowopt_update(tok, pad_t, self.owner, t["state"], t["p"], t["g"], t["m"], t["v"], t["ema"],
                                   self.global_step, self.coef, self.hist)
             else:
                 ops.adamw_ema_(t["p"], t["g"], t["m"], t["v"], t["ema"], lr, self.wd, self.global_step, self.coef, d)
-                ops.rows_zero(tok, spec.pad_id, self.owner, t["g"])
+                ops.rows_zero(tok, pad_t, self.owner, t["g"])
         if self.ema_on:
             self.n_ema += 1
         self.last_logits = logits
@@ -277,7 +371,10 @@ class FusedTrainer:
 
     @torch.no_grad()
     def predict(self, batch: Dict[str, torch.Tensor]):
+        """Eval-mode forward on the trainer's own storage (sharded mode: collective, every rank calls it)."""
         self.sync_tables()
+        if self.shard:
+            self._allreduce(self._bar)                   # barrier: all shards flushed before peers read them
         dbatch, _ = self.to_device(batch, None)
         dc = hp.DropCtl(False)
         logits, aux, _ = hp.model_fwd(self.P, self.spec, dbatch, dc, self.cache)

@@ -169,6 +169,17 @@ static RowHist make_hist(const void* h, const float* C, const float* S, const fl
   return H;
 }
 
+
+// global row id -> local row of this rank's shard (row r lives on rank r % n at local row r / n), -1 for pad / foreign rows
+template <typename IT>
+__global__ void rows_localize_kernel(const IT* __restrict__ tok, int64_t n, int pad_id, int mask, int shift, int rank,
+                                     int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t t = (int64_t)tok[i];
+  out[i] = (t == pad_id || t < 0 || (int)(t & mask) != rank) ? -1 : (int32_t)(t >> shift);
+}
+
 }  // namespace b200ctr
 
 using namespace b200ctr;
@@ -235,5 +246,20 @@ extern "C" int b200ctr_rowopt_flush(int32_t* state, float* p, float* m, float* v
   int grid = (int)std::min<int64_t>(ceil_div(n_rows, 8), (int64_t)num_sms() * 32);
   rowopt_flush_kernel<<<grid, 256, 0, as_stream(stream)>>>(state, p, m, v, ema, n_rows, (int)target_step, H);
   B200_LAUNCH_CHECK("rowopt_flush_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_rows_localize(const void* tok, int idx_is_64, int64_t n_slots, int pad_id, int n_shards, int rank,
+                                     int32_t* out, void* stream) {
+  B200_REQUIRE(tok && out, B200CTR_E_INVALID_ARG, "rows_localize: null pointer");
+  B200_REQUIRE(n_shards >= 1 && n_shards <= 8 && !(n_shards & (n_shards - 1)) && rank >= 0 && rank < n_shards,
+               B200CTR_E_INVALID_ARG, "rows_localize: n_shards=%d rank=%d", n_shards, rank);
+  if (n_slots == 0) return B200CTR_OK;
+  int shift = 0;
+  while ((1 << shift) < n_shards) ++shift;
+  const unsigned grid = (unsigned)ceil_div(n_slots, 256);
+  if (idx_is_64) rows_localize_kernel<int64_t><<<grid, 256, 0, as_stream(stream)>>>((const int64_t*)tok, n_slots, pad_id, n_shards - 1, shift, rank, out);
+  else rows_localize_kernel<int32_t><<<grid, 256, 0, as_stream(stream)>>>((const int32_t*)tok, n_slots, pad_id, n_shards - 1, shift, rank, out);
+  B200_LAUNCH_CHECK("rows_localize_kernel");
   return B200CTR_OK;
 }
