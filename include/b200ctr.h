@@ -287,6 +287,22 @@ int b200ctr_rows_zero(const int32_t* tok, int64_t n_slots, int pad_id, const int
 int b200ctr_rowopt_push(void* hist4, float* C, float* S, float* logD, int64_t capacity, int64_t t,
                         float decay_mul, float step_size, float bc2_sqrt, float ema_d, float C_t, float S_t, float logD_t,
                         void* stream);
+/* Bitmap-driven row sets (one bit per GLOBAL row; `bitmaps` = n_maps maps of `words` 32-bit words, e.g. one per
+ * data-parallel rank after an all-gather).  The *_bm kernels visit every row owned by `rank` (row % n_shards == rank,
+ * local row = row / n_shards) whose bit is set in any map, each exactly once: catch-up before the forward reads it,
+ * squared gradient norm, AdamW/EMA step t (+ re-zeroing of the gradient row).  n_shards in {1,2,4,8}.          */
+int b200ctr_bitmap_mark(const void* tok, int idx_is_64, int64_t n_slots, int pad_id, int64_t vocab, uint32_t* bitmap,
+                        void* stream);
+int b200ctr_rowopt_catchup_bm(const uint32_t* bitmaps, int n_maps, int64_t words, int n_shards, int rank, int32_t* state,
+                              float* p, float* m, float* v, float* ema, int D, int64_t target_step, const void* hist4,
+                              const float* C, const float* S, const float* logD, float beta1, float beta2, float eps,
+                              void* stream);
+int b200ctr_rows_sqnorm_bm(const uint32_t* bitmaps, int n_maps, int64_t words, int n_shards, int rank, const float* g,
+                           int D, double* acc, void* stream);
+int b200ctr_rowopt_update_bm(const uint32_t* bitmaps, int n_maps, int64_t words, int n_shards, int rank, int32_t* state,
+                             float* p, float* g, float* m, float* v, float* ema, int D, int64_t step, const float* coef,
+                             const void* hist4, const float* C, const float* S, const float* logD, float beta1,
+                             float beta2, float eps, void* stream);
 /* Row-sharded tables: out[i] = local row (tok / n_shards) if tok is owned by `rank` (tok % n_shards == rank) and is
  * not pad_id, else -1; the owner-side row kernels are then called with pad_id = -1 on the local shard.           */
 int b200ctr_rows_localize(const void* tok, int idx_is_64, int64_t n_slots, int pad_id, int n_shards, int rank,

@@ -749,6 +749,38 @@ class RowHistory:
         return (_p(self.h4), _p(self.C), _p(self.S), _p(self.logD), self.b1, self.b2, self.eps)
 
 
+# ---- bitmap-driven row sets (see csrc/rowopt.cu) -------------------------------------------------------------------
+def bitmap_words(vocab: int) -> int:
+    return (int(vocab) + 31) // 32
+
+
+def bitmap_mark(tok, pad_id, vocab, bitmap):
+    """bitmap (int32 tensor of bitmap_words(vocab) words, zeroed by the caller) |= {rows listed in tok}."""
+    lib = _lib.load()
+    _run("bitmap_mark", lib.b200ctr_bitmap_mark, _p(tok), _idx64(tok), tok.numel(), pad_id, vocab, _p(bitmap), _stream())
+    _count()
+
+
+def rowopt_catchup_bm(bitmaps, n_maps, words, n_shards, rank, state, p, m, v, ema, target, hist: "RowHistory"):
+    lib = _lib.load()
+    _run("rowopt_catchup", lib.b200ctr_rowopt_catchup_bm, _p(bitmaps), n_maps, words, n_shards, rank, _p(state), _p(p), _p(m), _p(v),
+         _p(ema), p.shape[1], target, *hist.args(), _stream())
+    _count()
+
+
+def rows_sqnorm_bm(bitmaps, n_maps, words, n_shards, rank, g, acc):
+    lib = _lib.load()
+    _run("rows_sqnorm", lib.b200ctr_rows_sqnorm_bm, _p(bitmaps), n_maps, words, n_shards, rank, _p(g), g.shape[1], _p(acc), _stream())
+    _count()
+
+
+def rowopt_update_bm(bitmaps, n_maps, words, n_shards, rank, state, p, g, m, v, ema, step, coef, hist: "RowHistory"):
+    lib = _lib.load()
+    _run("rowopt_update", lib.b200ctr_rowopt_update_bm, _p(bitmaps), n_maps, words, n_shards, rank, _p(state), _p(p), _p(g), _p(m),
+         _p(v), _p(ema), p.shape[1], step, _p(coef), *hist.args(), _stream())
+    _count()
+
+
 def rows_claim_any(tok, pad_id, vocab, owner):
     lib = _lib.load()
     _run("rows_claim_any", lib.b200ctr_rows_claim_any, _p(tok), _idx64(tok), tok.numel(), pad_id, vocab, _p(owner), _stream())

@@ -158,6 +158,14 @@ class FusedTrainer:
             # state_dict()/checkpointing through the nn.Module sees fully-updated (and, if sharded, re-assembled) tables
             model.register_state_dict_pre_hook(lambda *a, **k: self.materialize_tables())
         self.owner = torch.empty(max(self.vocab, 1), device=dev, dtype=torch.int32)
+        # row sets as bitmaps (one bit per global row) unless the tables are replicated under DP (legacy all-gather path)
+        self.bitmaps = self.lazy and (self.world == 1 or self.shard)
+        self.n_shards = self.world if self.shard else 1
+        self.shard_rank = self.rank if self.shard else 0
+        self.bm_words = ops.bitmap_words(self.vocab_global)
+        if self.bitmaps:
+            self.bm_mine = torch.zeros(self.bm_words, device=dev, dtype=torch.int32)
+            self.bm_all = torch.zeros(self.n_shards * self.bm_words, device=dev, dtype=torch.int32) if self.shard else None
         self.acc = torch.zeros(1, device=dev, dtype=torch.float64)
         self.coef = torch.ones(1, device=dev, dtype=torch.float32)
         self._bar = torch.zeros(1, device=dev, dtype=torch.float32)      # payload of the barrier all-reduces
@@ -197,12 +205,15 @@ class FusedTrainer:
         torch.cuda.empty_cache()
         dist.barrier(group=self.pg)
 
-    def _all_gather_ids(self, ids: torch.Tensor) -> torch.Tensor:
-        """(n,) or (B, L) int ids of this rank -> the concatenation over ranks, int32 (device-side barrier as a side effect)."""
-        flat = ids.reshape(-1).to(torch.int32)
-        out = torch.empty((self.world * flat.numel(),), device=self.dev, dtype=torch.int32)
-        torch.distributed.all_gather_into_tensor(out, flat, group=self.pg)
-        return out
+    def _row_set(self, ids: torch.Tensor):
+        """Bitmap(s) of the global rows listed in `ids`: (maps, n_maps).  Sharded mode: all ranks' bitmaps, all-gathered
+        (1.25 MB per rank at 10 M rows; the collective doubles as a device-side barrier)."""
+        self.bm_mine.zero_()
+        ops.bitmap_mark(ids, self.spec.pad_id, self.vocab_global, self.bm_mine)
+        if not self.shard:
+            return self.bm_mine, 1
+        torch.distributed.all_gather_into_tensor(self.bm_all, self.bm_mine, group=self.pg)
+        return self.bm_all, self.world
 
     def materialize_tables(self):
         """Fully-updated tables behind the nn.Module's parameters (state_dict / checkpoint / plain-module eval).
@@ -272,21 +283,25 @@ class FusedTrainer:
         if self.lazy:
             # rows this batch is about to read are brought to step t-1 (exactly what dense AdamW/EMA would hold)
             self.hist.push(self.global_step, lr, self.wd, d if self.ema_on else 1.0)
-            if self.shard:
-                # owners catch up the rows ANY rank is about to read; the all-gather is also the barrier that orders the
-                # previous step's owner-side AdamW before this step's peer reads
-                seq_l = ops.rows_localize(self._all_gather_ids(dbatch["seq"]), spec.pad_id, self.world, self.rank)
-                pad_l = -1
-            else:
-                seq_l, pad_l = dbatch["seq"], spec.pad_id
-            if self.global_step > 1:
-                ops.rows_claim_any(seq_l, pad_l, self.vocab, self.owner)
+            if self.bitmaps:
+                # the set of rows this step reads, one bit per global row; sharded: the all-gather of the ranks' bitmaps
+                # tells every owner which of ITS rows any rank will read (and is the barrier that orders the previous
+                # step's owner-side AdamW before this step's peer reads)
+                maps, n_maps = self._row_set(dbatch["seq"])
+                if self.global_step > 1:
+                    for n in BIG_TABLES:
+                        t = self.tables[n]
+                        ops.rowopt_catchup_bm(maps, n_maps, self.bm_words, self.n_shards, self.shard_rank, t["state"], t["p"],
+                                              t["m"], t["v"], t["ema"], self.global_step - 1, self.hist)
+                if self.shard:
+                    self._allreduce(self._bar)      # barrier: every shard is caught up before any peer gathers from it
+            elif self.global_step > 1:
+                seq = dbatch["seq"]
+                ops.rows_claim_any(seq, spec.pad_id, self.vocab, self.owner)
                 for n in BIG_TABLES:
                     t = self.tables[n]
-                    ops.rowopt_catchup(seq_l, pad_l, self.owner, t["state"], t["p"], t["m"], t["v"], t["ema"],
+                    ops.rowopt_catchup(seq, spec.pad_id, self.owner, t["state"], t["p"], t["m"], t["v"], t["ema"],
                                        self.global_step - 1, self.hist)
-            if self.shard:
-                self._allreduce(self._bar)          # barrier: every shard is caught up before any peer gathers from it
         hook = (lambda t: self._allreduce(t)) if self.world > 1 else None
         logits, aux, sv = hp.model_fwd(self.P, spec, dbatch, dc, self.cache, B_total=B_local * self.world, colsum_hook=hook)
         counts_override = None
@@ -307,19 +322,20 @@ class FusedTrainer:
             if not self.shard:
                 tok = self._exchange_table_grads(tok)                                               # C1 (replicated tables)
             self._allreduce(loss)
-        pad_t = spec.pad_id
-        if self.shard:
-            # C1 already happened inside retrieve_bwd (gradient rows scattered into the owners' shards over NVLink); the
-            # owners only need the touched row ids.  This all-gather also orders every peer's scatter before the update.
-            tok = ops.rows_localize(self._all_gather_ids(tok), spec.pad_id, self.world, self.rank)
-            pad_t = -1
         # ---- global-norm clip (coef stays on the device) ----
         self.acc.zero_()
-        ops.rows_claim(tok, pad_t, self.owner)
-        for n in BIG_TABLES:
-            ops.rows_sqnorm(tok, pad_t, self.owner, self.tables[n]["g"], self.acc)
-        if self.shard:
-            self._allreduce(self.acc)               # C5: each owner contributes the squared norm of its rows
+        if self.lazy and self.bitmaps:
+            # sharded: C1 already happened inside retrieve_bwd (gradient rows scattered into the owners' shards over NVLink);
+            # the owners only need the set of touched rows.  Its all-gather also orders every peer's scatter before the update.
+            maps, n_maps = self._row_set(tok)
+            for n in BIG_TABLES:
+                ops.rows_sqnorm_bm(maps, n_maps, self.bm_words, self.n_shards, self.shard_rank, self.tables[n]["g"], self.acc)
+            if self.shard:
+                self._allreduce(self.acc)           # C5: each owner contributes the squared norm of its rows
+        else:
+            ops.rows_claim(tok, spec.pad_id, self.owner)
+            for n in BIG_TABLES:
+                ops.rows_sqnorm(tok, spec.pad_id, self.owner, self.tables[n]["g"], self.acc)
         ops.sqnorm_(self.flat_g[:self.n_active], self.acc)
         ops.clip_coef(self.acc, self.clip, self.coef, self.total_norm)
         # ---- AdamW (+EMA) ----
@@ -327,12 +343,15 @@ class FusedTrainer:
                        self.flat_ema[:self.n_active] if self.ema_on else None, lr, self.wd, self.global_step, self.coef, d)
         for n in BIG_TABLES:
             t = self.tables[n]
-            if self.lazy:
-                ops.rowopt_update(tok, pad_t, self.owner, t["state"], t["p"], t["g"], t["m"], t["v"], t["ema"],
+            if self.lazy and self.bitmaps:
+                ops.rowopt_update_bm(maps, n_maps, self.bm_words, self.n_shards, self.shard_rank, t["state"], t["p"], t["g"],
+                                     t["m"], t["v"], t["ema"], self.global_step, self.coef, self.hist)
+            elif self.lazy:
+                ops.rowopt_update(tok, spec.pad_id, self.owner, t["state"], t["p"], t["g"], t["m"], t["v"], t["ema"],
                                   self.global_step, self.coef, self.hist)
             else:
                 ops.adamw_ema_(t["p"], t["g"], t["m"], t["v"], t["ema"], lr, self.wd, self.global_step, self.coef, d)
-                ops.rows_zero(tok, pad_t, self.owner, t["g"])
+                ops.rows_zero(tok, spec.pad_id, self.owner, t["g"])
         if self.ema_on:
             self.n_ema += 1
         self.last_logits = logits

@@ -170,6 +170,141 @@ static RowHist make_hist(const void* h, const float* C, const float* S, const fl
 }
 
 
+// =============================================================================================================
+// Bitmap-driven row sets.  "Rows the batch reads" and "rows that received a gradient" are kept as one bit per GLOBAL
+// row (10 M rows = 1.25 MB, L2 resident): marking is one atomicOr per slot, the sets of all data-parallel ranks are
+// exchanged as bitmaps (n_maps x words), and the owner of a row walks only ITS bits -- the cost no longer grows with
+// the number of (duplicate-heavy) token slots of the whole job, and no per-row owner-slot election is needed.
+// Row r lives on rank r % n_shards at local row r / n_shards (n_shards in {1,2,4,8}, so the owner of bit b of a word is
+// b % n_shards).
+// =============================================================================================================
+template <typename IT>
+__global__ void bitmap_mark_kernel(const IT* __restrict__ tok, int64_t n, int pad_id, int64_t vocab, uint32_t* __restrict__ bm) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t t = (int64_t)tok[i];
+  if (t == pad_id || t < 0 || t >= vocab) return;
+  const uint32_t bit = 1u << (t & 31);
+  uint32_t* w = bm + (t >> 5);
+  if (!(*w & bit)) atomicOr(w, bit);              // hot rows are marked thousands of times: test first
+}
+
+__device__ __forceinline__ uint32_t own_mask(int n_shards, int rank) {
+  uint32_t m = 0;
+  for (int b = rank; b < 32; b += n_shards) m |= 1u << b;
+  return m;
+}
+
+// calls f(local_row) with the whole warp converged for every owned row whose bit is set in any of the n_maps bitmaps
+template <typename F>
+__device__ __forceinline__ void for_each_owned_row(const uint32_t* __restrict__ bm, int n_maps, int64_t words, int n_shards,
+                                                   int rank, F f) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t om = own_mask(n_shards, rank);
+  int shift = 0;
+  while ((1 << shift) < n_shards) ++shift;
+  for (int64_t w0 = warp * 32; w0 < words; w0 += nw * 32) {
+    const int64_t wi = w0 + lane;
+    uint32_t bits = 0;
+    if (wi < words)
+      for (int k = 0; k < n_maps; ++k) bits |= bm[(int64_t)k * words + wi];
+    bits &= om;
+    uint32_t active = __ballot_sync(0xffffffffu, bits != 0);
+    while (active) {
+      const int src = __ffs(active) - 1;
+      active &= active - 1;
+      uint32_t wb = __shfl_sync(0xffffffffu, bits, src);
+      const int64_t base_row = (w0 + src) * 32;
+      while (wb) {
+        const int b = __ffs(wb) - 1;
+        wb &= wb - 1;
+        f((base_row + b) >> shift);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rowopt_catchup_bm_kernel(const uint32_t* __restrict__ bm, int n_maps, int64_t words, int n_shards, int rank,
+                         int32_t* __restrict__ state, float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ V,
+                         float* __restrict__ E, int target, RowHist H) {
+  const int lane = threadIdx.x & 31;
+  for_each_owned_row(bm, n_maps, words, n_shards, rank, [&](int64_t t) {
+    const int32_t st = state[t];
+    const int last = st >> 1;
+    if (last >= target) return;
+    const bool has_mom = st & 1;
+    float2* p2 = reinterpret_cast<float2*>(P + t * RO_D) + lane;
+    float2 p = *p2, m = make_float2(0.f, 0.f), v = m, e = m;
+    if (has_mom) { m = reinterpret_cast<float2*>(Mo + t * RO_D)[lane]; v = reinterpret_cast<float2*>(V + t * RO_D)[lane]; }
+    if (E) e = reinterpret_cast<float2*>(E + t * RO_D)[lane];
+    row_catchup(p, m, v, e, E != nullptr, has_mom, last, target, H);
+    *p2 = p;
+    if (has_mom) { reinterpret_cast<float2*>(Mo + t * RO_D)[lane] = m; reinterpret_cast<float2*>(V + t * RO_D)[lane] = v; }
+    if (E) reinterpret_cast<float2*>(E + t * RO_D)[lane] = e;
+    __syncwarp();
+    if (lane == 0) state[t] = (target << 1) | (st & 1);
+  });
+}
+
+__global__ void __launch_bounds__(256)
+rows_sqnorm_bm_kernel(const uint32_t* __restrict__ bm, int n_maps, int64_t words, int n_shards, int rank,
+                      const float* __restrict__ G, double* __restrict__ acc) {
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for_each_owned_row(bm, n_maps, words, n_shards, rank, [&](int64_t t) {
+    const float2 g = reinterpret_cast<const float2*>(G + t * RO_D)[lane];
+    s += (double)(g.x * g.x + g.y * g.y);
+  });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    atomicAdd(acc, t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rowopt_update_bm_kernel(const uint32_t* __restrict__ bm, int n_maps, int64_t words, int n_shards, int rank,
+                        int32_t* __restrict__ state, float* __restrict__ P, float* __restrict__ G, float* __restrict__ Mo,
+                        float* __restrict__ V, float* __restrict__ E, int t_step, const float* __restrict__ coef, RowHist H) {
+  const int lane = threadIdx.x & 31;
+  const float c = coef ? coef[0] : 1.f;
+  const float4 hc = __ldg(H.h + t_step);
+  for_each_owned_row(bm, n_maps, words, n_shards, rank, [&](int64_t t) {
+    const int32_t st = state[t];
+    const bool has_mom = st & 1;
+    float2* p2 = reinterpret_cast<float2*>(P + t * RO_D) + lane;
+    float2* g2 = reinterpret_cast<float2*>(G + t * RO_D) + lane;
+    float2* m2 = reinterpret_cast<float2*>(Mo + t * RO_D) + lane;
+    float2* v2 = reinterpret_cast<float2*>(V + t * RO_D) + lane;
+    float2 p = *p2, g = *g2, m = make_float2(0.f, 0.f), v = m, e = m;
+    if (has_mom) { m = *m2; v = *v2; }
+    if (E) e = reinterpret_cast<float2*>(E + t * RO_D)[lane];
+    row_catchup(p, m, v, e, E != nullptr, has_mom, st >> 1, t_step - 1, H);
+    g.x *= c; g.y *= c;
+    p.x *= hc.x; p.y *= hc.x;
+    m.x = m.x + (g.x - m.x) * (1.f - H.beta1); m.y = m.y + (g.y - m.y) * (1.f - H.beta1);
+    v.x = v.x * H.beta2 + (1.f - H.beta2) * g.x * g.x; v.y = v.y * H.beta2 + (1.f - H.beta2) * g.y * g.y;
+    p.x -= hc.y * (m.x / (sqrtf(v.x) / hc.z + H.eps));
+    p.y -= hc.y * (m.y / (sqrtf(v.y) / hc.z + H.eps));
+    *p2 = p; *m2 = m; *v2 = v;
+    *g2 = make_float2(0.f, 0.f);
+    if (E) {
+      e.x = e.x * hc.w + p.x * (1.f - hc.w); e.y = e.y * hc.w + p.y * (1.f - hc.w);
+      reinterpret_cast<float2*>(E + t * RO_D)[lane] = e;
+    }
+    __syncwarp();
+    if (lane == 0) state[t] = (t_step << 1) | 1;
+  });
+}
+
 // global row id -> local row of this rank's shard (row r lives on rank r % n at local row r / n), -1 for pad / foreign rows
 template <typename IT>
 __global__ void rows_localize_kernel(const IT* __restrict__ tok, int64_t n, int pad_id, int mask, int shift, int rank,
@@ -261,5 +396,64 @@ extern "C" int b200ctr_rows_localize(const void* tok, int idx_is_64, int64_t n_s
   if (idx_is_64) rows_localize_kernel<int64_t><<<grid, 256, 0, as_stream(stream)>>>((const int64_t*)tok, n_slots, pad_id, n_shards - 1, shift, rank, out);
   else rows_localize_kernel<int32_t><<<grid, 256, 0, as_stream(stream)>>>((const int32_t*)tok, n_slots, pad_id, n_shards - 1, shift, rank, out);
   B200_LAUNCH_CHECK("rows_localize_kernel");
+  return B200CTR_OK;
+}
+
+static int bm_check(const void* bm, int n_maps, int64_t words, int n_shards, int rank, const char* what) {
+  if (!bm || n_maps < 1 || words < 1 || n_shards < 1 || n_shards > 8 || (n_shards & (n_shards - 1)) || rank < 0 || rank >= n_shards) {
+    set_error("%s: bad bitmap arguments (n_maps=%d words=%lld n_shards=%d rank=%d)", what, n_maps, (long long)words, n_shards, rank);
+    return B200CTR_E_INVALID_ARG;
+  }
+  return B200CTR_OK;
+}
+static int bm_grid(int64_t words) { return (int)std::min<int64_t>(ceil_div(words, 32 * 8), (int64_t)num_sms() * 8); }
+
+extern "C" int b200ctr_bitmap_mark(const void* tok, int idx_is_64, int64_t n_slots, int pad_id, int64_t vocab, uint32_t* bitmap,
+                                   void* stream) {
+  B200_REQUIRE(tok && bitmap, B200CTR_E_INVALID_ARG, "bitmap_mark: null pointer");
+  if (n_slots == 0) return B200CTR_OK;
+  const unsigned grid = (unsigned)ceil_div(n_slots, 256);
+  if (idx_is_64) bitmap_mark_kernel<int64_t><<<grid, 256, 0, as_stream(stream)>>>((const int64_t*)tok, n_slots, pad_id, vocab, bitmap);
+  else bitmap_mark_kernel<int32_t><<<grid, 256, 0, as_stream(stream)>>>((const int32_t*)tok, n_slots, pad_id, vocab, bitmap);
+  B200_LAUNCH_CHECK("bitmap_mark_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_rowopt_catchup_bm(const uint32_t* bitmaps, int n_maps, int64_t words, int n_shards, int rank, int32_t* state,
+                                         float* p, float* m, float* v, float* ema, int D, int64_t target_step, const void* hist4,
+                                         const float* C, const float* S, const float* logD, float beta1, float beta2, float eps,
+                                         void* stream) {
+  int rc = bm_check(bitmaps, n_maps, words, n_shards, rank, "rowopt_catchup_bm");
+  if (rc) return rc;
+  B200_REQUIRE(state && p && m && v && hist4 && C && S && logD, B200CTR_E_INVALID_ARG, "rowopt_catchup_bm: null pointer");
+  B200_REQUIRE(D == RO_D, B200CTR_E_UNSUPPORTED_SHAPE, "rowopt_catchup_bm: D=%d unsupported", D);
+  rowopt_catchup_bm_kernel<<<bm_grid(words), 256, 0, as_stream(stream)>>>(bitmaps, n_maps, words, n_shards, rank, state, p, m, v, ema,
+                                                                           (int)target_step, make_hist(hist4, C, S, logD, beta1, beta2, eps));
+  B200_LAUNCH_CHECK("rowopt_catchup_bm_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_rows_sqnorm_bm(const uint32_t* bitmaps, int n_maps, int64_t words, int n_shards, int rank, const float* g,
+                                      int D, double* acc, void* stream) {
+  int rc = bm_check(bitmaps, n_maps, words, n_shards, rank, "rows_sqnorm_bm");
+  if (rc) return rc;
+  B200_REQUIRE(g && acc, B200CTR_E_INVALID_ARG, "rows_sqnorm_bm: null pointer");
+  B200_REQUIRE(D == RO_D, B200CTR_E_UNSUPPORTED_SHAPE, "rows_sqnorm_bm: D=%d unsupported", D);
+  rows_sqnorm_bm_kernel<<<bm_grid(words), 256, 0, as_stream(stream)>>>(bitmaps, n_maps, words, n_shards, rank, g, acc);
+  B200_LAUNCH_CHECK("rows_sqnorm_bm_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_rowopt_update_bm(const uint32_t* bitmaps, int n_maps, int64_t words, int n_shards, int rank, int32_t* state,
+                                        float* p, float* g, float* m, float* v, float* ema, int D, int64_t step, const float* coef,
+                                        const void* hist4, const float* C, const float* S, const float* logD, float beta1,
+                                        float beta2, float eps, void* stream) {
+  int rc = bm_check(bitmaps, n_maps, words, n_shards, rank, "rowopt_update_bm");
+  if (rc) return rc;
+  B200_REQUIRE(state && p && g && m && v && hist4 && C && S && logD, B200CTR_E_INVALID_ARG, "rowopt_update_bm: null pointer");
+  B200_REQUIRE(D == RO_D, B200CTR_E_UNSUPPORTED_SHAPE, "rowopt_update_bm: D=%d unsupported", D);
+  rowopt_update_bm_kernel<<<bm_grid(words), 256, 0, as_stream(stream)>>>(bitmaps, n_maps, words, n_shards, rank, state, p, g, m, v, ema,
+                                                                          (int)step, coef, make_hist(hist4, C, S, logD, beta1, beta2, eps));
+  B200_LAUNCH_CHECK("rowopt_update_bm_kernel");
   return B200CTR_OK;
 }
