@@ -104,6 +104,13 @@ int b200ctr_gemm_bf16(int transA, int transB, int64_t M, int64_t N, int64_t K,
                       const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                       const b200ctr_epilogue_t* epi_host, int split_k, void* workspace, void* stream);
 /* out[n] = sum_m X[m,n]  (bias gradients; deterministic two-pass).  workspace >= 4*N*1184 bytes. */
+/* Same contraction with operands ALREADY in bf16 (row-major, leading dimensions in elements): activations that their
+ * producer kernel also emitted in bf16 (b200ctr_rowrms_fwd_bf16) and weights converted once per step (b200ctr_to_bf16);
+ * staging is then a pure 16-byte copy into the UMMA core-matrix layout.  Persistent warp-specialised kernel.       */
+int b200ctr_gemm_bf16in(int transA, int transB, int64_t M, int64_t N, int64_t K,
+                        const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
+                        const b200ctr_epilogue_t* epi_host, int split_k, void* workspace, void* stream);
+int b200ctr_to_bf16(const float* x, int64_t n, void* out_bf16, void* stream);
 int b200ctr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* workspace, void* stream);
 
 /* ---- numeric / binary feature embedding  (feature_embed.py:19-27, 42-48) ------------------------------
@@ -230,6 +237,8 @@ int b200ctr_pool_bwd(const float* x, const float* vals, const float* w, const fl
  * fm_grad:   dA[b,f,c] = dquad[b,c] * 2 * (s[b,c] - A[b,f,c])  (in place over A).
  * se_gate:   m = colsum/B; gate = sigmoid(W2 relu(W1 m + b1) + b2) (single CTA); bwd gives dm and weight grads.
  * se_apply:  out = inter * gate * dropout ; bwd: dinter = dout*drop*gate + dm/B ; gprod = dout*drop*inter.     */
+int b200ctr_rowrms_fwd_bf16(const float* x, int64_t ldx, const float* w, float eps, int64_t B, int64_t N,
+                            float* z, int64_t ld_z, float* r, void* z_bf16, void* stream);   /* + bf16 copy of z (B, N) */
 int b200ctr_rowrms_fwd(const float* x, int64_t ldx, const float* w, float eps, int64_t B, int64_t N,
                        float* z, int64_t ld_z, float* r, void* stream);
 int b200ctr_rowrms_bwd(const float* dz, int64_t ld_dz, const float* x, int64_t ldx, const float* w, const float* r,

@@ -377,3 +377,22 @@ def test_headproj_matches_einsum(dev, B, H, R, P):
     dquad = ops.headproj_bwd(quad.to(dev), dinter.to(dev), V.to(dev), dV)
     assert max_err_scaled(dquad.cpu(), torch.einsum("bhp,hrp->bhr", dinter.view(B, H, P).double(), V.double()).reshape(B, H * R)) < 1e-5
     assert max_err_scaled(dV.cpu(), torch.einsum("bhr,bhp->hrp", quad.view(B, H, R).double(), dinter.view(B, H, P).double())) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(256, 512, 1280, False, True), (512, 1280, 256, True, False), (300, 1288, 512, False, False),
+                                         (128, 64, 64, False, True)])
+def test_gemm_bf16_operands(dev, M, N, K, ta, tb):
+    """Operands already in bf16 (pure-copy staging) == the same contraction with fp32 operands rounded on load."""
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = _rand(g, K, M) if ta else _rand(g, M, K)
+    b = _rand(g, N, K) if tb else _rand(g, K, N)
+    ad, bd = a.to(dev), b.to(dev)
+    ref = (_bf(a).t() if ta else _bf(a)).double() @ (_bf(b).t() if tb else _bf(b)).double()
+    out = ops.gemm(ops.to_bf16(ad), ops.to_bf16(bd), trans_a=ta, trans_b=tb)
+    assert max_err_scaled(out.cpu(), ref) < 1e-5
+    # strided bf16 views (the W0[:, :N] / W0[:, N:] split of the first MLP layer)
+    if not ta and tb:
+        big = ops.to_bf16(torch.cat([bd, bd], dim=1).contiguous())
+        out2 = ops.gemm(ops.to_bf16(ad), big[:, K:], trans_b=True)
+        assert max_err_scaled(out2.cpu(), ref) < 1e-5

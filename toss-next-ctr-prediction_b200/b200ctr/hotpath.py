@@ -239,7 +239,14 @@ def qnn_fwd(P: Dict[str, Tensor], spec: ModelSpec, xF: Tensor, dc: DropCtl, B_to
     H, r, Pd = spec.heads, spec.rank, spec.proj
     C, HP = H * r, H * Pd
     flat = xF.view(B, N)
-    z, rz = ops.rowrms_fwd(flat, P["qnn.pre_norm.w"])
+    # amp: bf16 -- the deep (K = F*D) first-layer contractions read bf16 copies of z (emitted by the norm kernel itself)
+    # and of W0 (converted once per step) instead of converting fp32 operands inside the GEMM's load path
+    bf16_ops = ops.get_precision() == "bf16" and N % 8 == 0 and B >= 128
+    z16 = W0_16 = None
+    if bf16_ops:
+        z, rz, z16 = ops.rowrms_fwd(flat, P["qnn.pre_norm.w"], want_bf16=True)
+    else:
+        z, rz = ops.rowrms_fwd(flat, P["qnn.pre_norm.w"])
     Ucat = P["qnn.U"].permute(1, 0, 2).reshape(D, C).contiguous()            # (D, H*r): layout plumbing only
     A = ops.gemm(z.view(B * F, D), Ucat)                                       # (B*F, C)
     s, quad = ops.fm_reduce(A, B, F, C)
@@ -265,11 +272,14 @@ def qnn_fwd(P: Dict[str, Tensor], spec: ModelSpec, xF: Tensor, dc: DropCtl, B_to
     mlp = _qnn_mlp_names(P)
     acts = []
     W0 = P[f"qnn.mlp.{mlp[0]}.weight"]
+    if bf16_ops and W0.shape[1] % 8 == 0 and W0.is_contiguous():
+        W0_16 = ops.to_bf16(W0)
+    zin, W0z = (z16, W0_16[:, :N]) if W0_16 is not None else (z, W0[:, :N])
     if len(mlp) == 1:
-        hcur = ops.gemm(z, W0[:, :N], trans_b=True)
+        hcur = ops.gemm(zin, W0z, trans_b=True)
         logit = ops.gemm(igd, W0[:, N:], trans_b=True, accum=hcur, bias=P[f"qnn.mlp.{mlp[0]}.bias"])
     else:
-        hcur = ops.gemm(z, W0[:, :N], trans_b=True)
+        hcur = ops.gemm(zin, W0z, trans_b=True)
         hcur = ops.gemm(igd, W0[:, N:], trans_b=True, accum=hcur, bias=P[f"qnn.mlp.{mlp[0]}.bias"], act=ops.ACT_RELU,
                         dropout=dc(spec.p_qnn, SITE_MLP0), out=hcur)
         acts.append(hcur)
@@ -278,7 +288,7 @@ def qnn_fwd(P: Dict[str, Tensor], spec: ModelSpec, xF: Tensor, dc: DropCtl, B_to
                             act=ops.ACT_RELU, dropout=dc(spec.p_qnn, SITE_MLP0 + li))
             acts.append(hcur)
         logit = ops.gemm(hcur, P[f"qnn.mlp.{mlp[-1]}.weight"], trans_b=True, bias=P[f"qnn.mlp.{mlp[-1]}.bias"])
-    sv.update(igd=igd, acts=acts, mlp=mlp, B_total=Bt)
+    sv.update(igd=igd, acts=acts, mlp=mlp, B_total=Bt, z16=z16 if W0_16 is not None else None, W0_16=W0_16)
     return logit.view(B), sv
 
 
@@ -308,7 +318,12 @@ def qnn_bwd(P, spec: ModelSpec, sv: dict, dlogit: Tensor, dc: DropCtl, G: Callab
     # first layer: input = cat([z, igd])
     W0 = P[f"qnn.mlp.{mlp[0]}.weight"]
     gW0 = G(f"qnn.mlp.{mlp[0]}.weight")
-    ops.gemm(dh, z, trans_a=True, out=gW0[:, :N])
+    z16, W0_16 = sv.get("z16"), sv.get("W0_16")
+    dh16 = ops.to_bf16(dh) if (z16 is not None and dh.is_contiguous() and dh.shape[1] % 8 == 0) else None
+    if dh16 is not None:
+        ops.gemm(dh16, z16, trans_a=True, out=gW0[:, :N])
+    else:
+        ops.gemm(dh, z, trans_a=True, out=gW0[:, :N])
     ops.gemm(dh, igd, trans_a=True, out=gW0[:, N:])
     ops.colsum(dh, out=G(f"qnn.mlp.{mlp[0]}.bias"))
     digd = ops.gemm(dh, W0[:, N:])
@@ -340,7 +355,7 @@ def qnn_bwd(P, spec: ModelSpec, sv: dict, dlogit: Tensor, dc: DropCtl, G: Callab
     dUcat = ops.gemm(z3, dA, trans_a=True)                                    # (D, C)
     G("qnn.U").copy_(dUcat.view(D, H, r).permute(1, 0, 2))
     if spec.use_residual:
-        dz = ops.gemm(dh, W0[:, :N])                                          # (B, N)
+        dz = ops.gemm(dh16, W0_16[:, :N]) if dh16 is not None else ops.gemm(dh, W0[:, :N])      # (B, N)
         ops.gemm(dA, sv["Ucat"], trans_b=True, residual=dz.view(B * F, D), out=dz.view(B * F, D))
     else:
         dz = ops.gemm(dA, sv["Ucat"], trans_b=True).view(B, N)

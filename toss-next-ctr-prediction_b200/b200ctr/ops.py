@@ -131,7 +131,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, out:
          tc: Optional[bool] = None) -> torch.Tensor:
     """out[M,N] = epilogue(alpha * op(a) @ op(b)); see include/b200ctr.h:b200ctr_gemm."""
     lib = _lib.load()
-    _f32(a, "a"); _f32(b, "b")
+    bf16_in = a.dtype == torch.bfloat16
+    if bf16_in:
+        if b.dtype != torch.bfloat16 or (trans_a and trans_b):
+            raise TypeError("gemm: bf16 operands must both be bf16 (and not transA && transB)")
+    else:
+        _f32(a, "a"); _f32(b, "b")
     M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
     Kb, N = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
     assert K == Kb, (a.shape, b.shape, trans_a, trans_b)
@@ -161,8 +166,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, out:
         use_tc = bool(tc)
     if _PROF is not None:
         _TAG = f"[{M}x{N}x{K}{'T' if trans_a else 'N'}{'T' if trans_b else 'N'}]"
-    _run("gemm_bf16" if use_tc else "gemm", lib.b200ctr_gemm_bf16 if use_tc else lib.b200ctr_gemm, int(trans_a), int(trans_b), M, N, K, _p(a), _ld(a), _p(b), _ld(b), _p(out), _ld(out),
-                           ctypes.byref(e), split_k, _p(ws), _stream())
+    fn = lib.b200ctr_gemm_bf16in if bf16_in else (lib.b200ctr_gemm_bf16 if use_tc else lib.b200ctr_gemm)
+    _run("gemm_bf16" if (use_tc or bf16_in) else "gemm", fn, int(trans_a), int(trans_b), M, N, K, _p(a), _ld(a), _p(b), _ld(b),
+         _p(out), _ld(out), ctypes.byref(e), split_k, _p(ws), _stream())
     _count(2 if split_k > 1 else 1)
     return out
 
@@ -532,14 +538,26 @@ def pool_bwd(x, vals, w, aux_w, u, ld_u, du, ld_du, daux, gating_relu, daux_w, d
 
 
 # ---- QNN-alpha -------------------------------------------------------------------------------------------------
-def rowrms_fwd(x, w, eps=1e-6):
+def rowrms_fwd(x, w, eps=1e-6, want_bf16=False):
+    """z = w * x * rsqrt(mean(x^2) + eps) per row; want_bf16 also returns a bf16 copy of z for the tensor-core GEMMs."""
     lib = _lib.load()
     B, N = x.shape
     z = torch.empty((B, N), device=x.device, dtype=torch.float32)
     r = torch.empty((B,), device=x.device, dtype=torch.float32)
-    _run("rowrms_fwd", lib.b200ctr_rowrms_fwd, _p(x), _ld(x), _p(w), eps, B, N, _p(z), N, _p(r), _stream())
+    z16 = torch.empty((B, N), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    _run("rowrms_fwd", lib.b200ctr_rowrms_fwd_bf16, _p(x), _ld(x), _p(w), eps, B, N, _p(z), N, _p(r), _p(z16), _stream())
     _count()
-    return z, r
+    return (z, r, z16) if want_bf16 else (z, r)
+
+
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of a contiguous fp32 tensor (GEMM operand staging: weights once per step, small activations)."""
+    lib = _lib.load()
+    assert x.is_contiguous() and x.dtype == torch.float32
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _run("to_bf16", lib.b200ctr_to_bf16, _p(x), x.numel(), _p(out), _stream())
+    _count()
+    return out
 
 
 def rowrms_bwd(dz, x, w, r, n_partials=296):

@@ -16,6 +16,8 @@
 //   split-K: grid.z slices of K write raw partials; the shared reduce kernel applies the epilogue.
 #include "gemm_common.cuh"
 #include "tc_common.cuh"
+#include <cuda_bf16.h>
+#include <type_traits>
 #include <algorithm>
 #include <stdlib.h>
 
@@ -269,9 +271,53 @@ __device__ __forceinline__ void stage_operand_ws(unsigned char* smem, const floa
   }
 }
 
-template <int BN, bool TA, bool TB, int STAGES, int WS_PROD_WARPS, int WS_EPI_WARPS>
+// Same layout, operands already bf16 in global memory (one 16-byte load == one core-matrix row, no conversion)
+template <int R, bool KMAJOR, int WS_PROD_THREADS>
+__device__ __forceinline__ void stage_operand_ws(unsigned char* smem, const __nv_bfloat16* __restrict__ g, int64_t ld, int64_t mn0,
+                                                 int64_t mn_end, int64_t k0, int64_t k_end, bool vec_ok, int ptid) {
+  constexpr int UNITS = R * 8;
+  static_assert(UNITS % WS_PROD_THREADS == 0, "tile/threads mismatch");
+  constexpr int ITERS = UNITS / WS_PROD_THREADS;
+  // 16-byte loads in flight per thread: the operands mostly come from L2 (tiles are re-read by many CTAs), ~1 us away
+  constexpr int UNR = (ITERS % 8 == 0) ? 8 : ((ITERS % 6 == 0) ? 6 : ((ITERS % 4 == 0) ? 4 : ((ITERS % 3 == 0) ? 3 : ((ITERS % 2 == 0) ? 2 : 1))));
+#pragma unroll 1
+  for (int it0 = 0; it0 < ITERS; it0 += UNR) {
+    uint4 v[UNR];
+    uint32_t off[UNR];
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const int u = ptid + (it0 + q) * WS_PROD_THREADS;
+      v[q] = make_uint4(0u, 0u, 0u, 0u);
+      int64_t row, col, row_end, col_end;          // 8 consecutive elements [row][col .. col+7] of the global matrix
+      if (KMAJOR) {
+        const int r = u % R, c = u / R;
+        off[q] = (uint32_t)((c * (R / 8) + (r >> 3)) * 128 + (r & 7) * 16);
+        row = mn0 + r; col = k0 + c * 8; row_end = mn_end; col_end = k_end;
+      } else {
+        const int kk = u % TC_BK, gidx = u / TC_BK;
+        off[q] = (uint32_t)(((kk >> 3) * (R / 8) + gidx) * 128 + (kk & 7) * 16);
+        row = k0 + kk; col = mn0 + gidx * 8; row_end = k_end; col_end = mn_end;
+      }
+      if (row < row_end) {
+        const __nv_bfloat16* p = g + row * ld + col;
+        if (vec_ok && col + 7 < col_end) v[q] = __ldg(reinterpret_cast<const uint4*>(p));
+        else {
+          unsigned short t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = (col + j < col_end) ? __bfloat16_as_ushort(p[j]) : (unsigned short)0;
+          v[q] = make_uint4((uint32_t)t[0] | ((uint32_t)t[1] << 16), (uint32_t)t[2] | ((uint32_t)t[3] << 16),
+                            (uint32_t)t[4] | ((uint32_t)t[5] << 16), (uint32_t)t[6] | ((uint32_t)t[7] << 16));
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) *reinterpret_cast<uint4*>(smem + off[q]) = v[q];
+  }
+}
+
+template <int BN, bool TA, bool TB, int STAGES, int WS_PROD_WARPS, int WS_EPI_WARPS, typename TIn>
 __global__ void __launch_bounds__(WS_NT, 1)
-gemm_tc_ws_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+gemm_tc_ws_kernel(int64_t M, int64_t N, int64_t K, const TIn* __restrict__ A, int64_t lda, const TIn* __restrict__ B,
                   int64_t ldb, float* __restrict__ C, int64_t ldc, EpiDev epi, int split_k, int64_t k_chunk,
                   float* __restrict__ partial, int vec_epi, int tiles_m, int tiles_n) {
   constexpr int A_BYTES = TC_BM * TC_BK * 2;
@@ -306,8 +352,9 @@ gemm_tc_ws_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, 
 
   if (warp < WS_PROD_WARPS) {
     // ------------------------------------------------ producers ------------------------------------------------
-    const bool a_vec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-    const bool b_vec = ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    constexpr int64_t VEC_LD = std::is_same<TIn, float>::value ? 3 : 7;         // 16-byte rows: ld % 4 (fp32) / % 8 (bf16)
+    const bool a_vec = ((lda & VEC_LD) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const bool b_vec = ((ldb & VEC_LD) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
     uint32_t g = 0;                                       // ring position across all tiles of this CTA
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t % tiles_n, mt = (t / tiles_n) % tiles_m, z = t / (tiles_n * tiles_m);
@@ -447,21 +494,22 @@ gemm_tc_ws_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, 
   }
 }
 
-template <int BN>
-static int launch_tc_ws(int tA, int tB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+template <int BN, typename TIn = float>
+static int launch_tc_ws(int tA, int tB, int64_t M, int64_t N, int64_t K, const TIn* A, int64_t lda, const TIn* B,
                         int64_t ldb, float* C, int64_t ldc, const EpiDev& e, int split_k, float* ws, cudaStream_t st) {
   int64_t k_chunk = ceil_div(ceil_div(K, (int64_t)split_k), (int64_t)TC_BK) * TC_BK;
   if (k_chunk <= 0) k_chunk = TC_BK;
   const int tiles_m = (int)ceil_div(M, (int64_t)TC_BM), tiles_n = (int)ceil_div(N, (int64_t)BN);
   const int64_t total = (int64_t)tiles_m * tiles_n * split_k;
   constexpr int STAGES = BN <= 128 ? 5 : (BN <= 192 ? 4 : 3);
-  const bool deep_k = k_chunk > 512;                     // deep-K: loads dominate -> 8 producer warps; else 8 epilogue warps
+  // deep-K: loads dominate -> 8 producer warps; else 8 epilogue warps
+  const bool deep_k = std::is_same<TIn, float>::value ? (k_chunk > 512) : (k_chunk >= 256);
   size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + (size_t)8 * 32 * 36 * 4;
   const int vec = epi_vec_ok(e, C, ldc, N) ? 1 : 0;
   const int grid = (int)std::min<int64_t>(total, (int64_t)num_sms());
 #define WS_LAUNCH1(TA_, TB_, PW_, EW_)                                                                            \
   do {                                                                                                            \
-    auto fn = gemm_tc_ws_kernel<BN, TA_, TB_, STAGES, PW_, EW_>;                                                  \
+    auto fn = gemm_tc_ws_kernel<BN, TA_, TB_, STAGES, PW_, EW_, TIn>;                                             \
     cudaError_t ee = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     if (ee != cudaSuccess) return cuda_fail(ee, "cudaFuncSetAttribute(gemm_tc_ws smem)");                         \
     fn<<<grid, WS_NT, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e, split_k, k_chunk, ws, vec, tiles_m, tiles_n); \
@@ -549,6 +597,62 @@ extern "C" int b200ctr_gemm_bf16(int transA, int transB, int64_t M, int64_t N, i
 #undef TC_DISPATCH
   if (rc) return rc;
   B200_LAUNCH_CHECK("gemm_tc_kernel");
+  if (split_k > 1) {
+    rc = launch_splitk_reduce((const float*)workspace, split_k, M, N, C, ldc, e, st);
+    if (rc) return rc;
+  }
+  return B200CTR_OK;
+}
+
+// ---- operands already in bf16 (activations the producer kernel emitted in bf16, weights converted once per step) ----
+__global__ void to_bf16_kernel(const float* __restrict__ x, int64_t n8, int64_t n, __nv_bfloat16* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n8) {
+    const float4 a = reinterpret_cast<const float4*>(x)[2 * i], b = reinterpret_cast<const float4*>(x)[2 * i + 1];
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(b200ctr::pack_bf16(a.x, a.y), b200ctr::pack_bf16(a.z, a.w),
+                                                  b200ctr::pack_bf16(b.x, b.y), b200ctr::pack_bf16(b.z, b.w));
+  } else if (i == n8) {
+    for (int64_t j = n8 * 8; j < n; ++j) out[j] = __float2bfloat16(x[j]);
+  }
+}
+
+extern "C" int b200ctr_to_bf16(const float* x, int64_t n, void* out_bf16, void* stream) {
+  B200_REQUIRE(x && out_bf16, B200CTR_E_INVALID_ARG, "to_bf16: null pointer");
+  B200_REQUIRE((((uintptr_t)x | (uintptr_t)out_bf16) & 15) == 0, B200CTR_E_INVALID_ARG, "to_bf16: pointers must be 16-byte aligned");
+  if (n == 0) return B200CTR_OK;
+  const int64_t n8 = n / 8;
+  to_bf16_kernel<<<(unsigned)ceil_div(n8 + 1, 256), 256, 0, as_stream(stream)>>>(x, n8, n, (__nv_bfloat16*)out_bf16);
+  B200_LAUNCH_CHECK("to_bf16_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_gemm_bf16in(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                                   const void* B, int64_t ldb, float* C, int64_t ldc, const b200ctr_epilogue_t* eh,
+                                   int split_k, void* workspace, void* stream) {
+  B200_REQUIRE(M >= 0 && N >= 0 && K >= 0, B200CTR_E_INVALID_ARG, "gemm_bf16in: negative dimension");
+  if (M == 0 || N == 0) return B200CTR_OK;
+  B200_REQUIRE(A && B && C, B200CTR_E_INVALID_ARG, "gemm_bf16in: null operand");
+  B200_REQUIRE(split_k >= 1 && split_k <= 1024, B200CTR_E_INVALID_ARG, "gemm_bf16in: split_k out of range");
+  B200_REQUIRE(split_k == 1 || workspace, B200CTR_E_INVALID_ARG, "gemm_bf16in: split_k > 1 needs a workspace");
+  EpiDev e{};
+  e.alpha = 1.f;
+  if (eh) {
+    e.alpha = eh->alpha; e.bias = eh->bias; e.act = eh->act; e.pre_out = eh->pre_out; e.ld_pre = eh->ld_pre;
+    e.drop = eh->drop; e.mask_mode = eh->mask_mode; e.mask_src = eh->mask_src; e.ld_mask = eh->ld_mask;
+    e.mask_scale = eh->mask_scale; e.residual = eh->residual; e.ld_res = eh->ld_res;
+    e.accum = eh->accum; e.ld_accum = eh->ld_accum;
+    B200_REQUIRE(e.mask_mode == B200CTR_MASK_NONE || e.mask_src, B200CTR_E_INVALID_ARG, "gemm_bf16in: mask_mode without mask_src");
+  }
+  cudaStream_t st = as_stream(stream);
+  const __nv_bfloat16* a = (const __nv_bfloat16*)A;
+  const __nv_bfloat16* b = (const __nv_bfloat16*)B;
+  float* ws = (float*)workspace;
+  int rc;
+  if (N <= 64) rc = launch_tc_ws<64, __nv_bfloat16>(transA, transB, M, N, K, a, lda, b, ldb, C, ldc, e, split_k, ws, st);
+  else if (N <= 128) rc = launch_tc_ws<128, __nv_bfloat16>(transA, transB, M, N, K, a, lda, b, ldb, C, ldc, e, split_k, ws, st);
+  else rc = launch_tc_ws<256, __nv_bfloat16>(transA, transB, M, N, K, a, lda, b, ldb, C, ldc, e, split_k, ws, st);
+  if (rc) return rc;
+  B200_LAUNCH_CHECK("gemm_tc_ws_kernel(bf16 operands)");
   if (split_k > 1) {
     rc = launch_splitk_reduce((const float*)workspace, split_k, M, N, C, ldc, e, st);
     if (rc) return rc;

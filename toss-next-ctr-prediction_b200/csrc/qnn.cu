@@ -2,6 +2,7 @@
 // quadratic interaction, the batch-statistic SE gate and its application.
 // Reference: src/models/qnn_alpha.py:6-12 (RMSNorm), 24-26 (SEBlock), 86-97 (_pair_interaction_all), 109-130.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <algorithm>
 
 namespace b200ctr {
@@ -11,7 +12,7 @@ constexpr int RR_MAXV = 16;          // float4 slots per thread => N <= 16*4*256
 
 __global__ void __launch_bounds__(RR_THREADS)
 rowrms_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, float eps, int64_t N,
-                  float* __restrict__ z, int64_t ld_z, float* __restrict__ r) {
+                  float* __restrict__ z, int64_t ld_z, float* __restrict__ r, __nv_bfloat16* __restrict__ z16) {
   __shared__ float red[32];
   const int64_t b = blockIdx.x;
   const float4* xr = reinterpret_cast<const float4*>(x + b * ldx);
@@ -27,7 +28,12 @@ rowrms_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
   const float rr = rsqrtf(ss / (float)N + eps);
   for (int i = threadIdx.x; i < n4; i += RR_THREADS) {
     float4 v = xr[i], ww = __ldg(w4 + i);
-    zr[i] = make_float4(ww.x * v.x * rr, ww.y * v.y * rr, ww.z * v.z * rr, ww.w * v.w * rr);
+    const float4 o = make_float4(ww.x * v.x * rr, ww.y * v.y * rr, ww.z * v.z * rr, ww.w * v.w * rr);
+    zr[i] = o;
+    if (z16) {          // bf16 copy for the tensor-core contractions that consume z (row stride N)
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      reinterpret_cast<uint2*>(z16 + b * N)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
   }
   if (threadIdx.x == 0) r[b] = rr;
 }
@@ -289,14 +295,18 @@ __global__ void headproj_reduce_kernel(const float* __restrict__ partial, int n_
 
 using namespace b200ctr;
 
-extern "C" int b200ctr_rowrms_fwd(const float* x, int64_t ldx, const float* w, float eps, int64_t B, int64_t N, float* z,
-                                  int64_t ld_z, float* r, void* stream) {
+extern "C" int b200ctr_rowrms_fwd_bf16(const float* x, int64_t ldx, const float* w, float eps, int64_t B, int64_t N, float* z,
+                                       int64_t ld_z, float* r, void* z_bf16, void* stream) {
   B200_REQUIRE(x && w && z && r, B200CTR_E_INVALID_ARG, "rowrms_fwd: null pointer");
   B200_REQUIRE(N % 4 == 0 && ldx % 4 == 0 && ld_z % 4 == 0, B200CTR_E_UNSUPPORTED_SHAPE, "rowrms_fwd: N and leading dims must be multiples of 4");
   if (B == 0) return B200CTR_OK;
-  rowrms_fwd_kernel<<<(unsigned)B, RR_THREADS, 0, as_stream(stream)>>>(x, ldx, w, eps, N, z, ld_z, r);
+  rowrms_fwd_kernel<<<(unsigned)B, RR_THREADS, 0, as_stream(stream)>>>(x, ldx, w, eps, N, z, ld_z, r, (__nv_bfloat16*)z_bf16);
   B200_LAUNCH_CHECK("rowrms_fwd_kernel");
   return B200CTR_OK;
+}
+extern "C" int b200ctr_rowrms_fwd(const float* x, int64_t ldx, const float* w, float eps, int64_t B, int64_t N, float* z,
+                                  int64_t ld_z, float* r, void* stream) {
+  return b200ctr_rowrms_fwd_bf16(x, ldx, w, eps, B, N, z, ld_z, r, nullptr, stream);
 }
 
 extern "C" int b200ctr_rowrms_bwd(const float* dz, int64_t ld_dz, const float* x, int64_t ldx, const float* w, const float* r,
