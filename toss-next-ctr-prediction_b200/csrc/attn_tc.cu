@@ -166,12 +166,19 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int NT>
-__global__ void __launch_bounds__(TA_THREADS, (NT <= 10 ? 2 : 1))
+// KS = key split: the warps (head h, part) with part in [0, KS) own disjoint 16-key blocks of head h, so dK / dV / dbias
+// accumulators stay small (no spills at top_k = 148) and an SM holds 4x more warps than with one warp per head; only dQ
+// needs a cross-warp sum (global fp32 reductions into this sample's zero-initialised dQ rows).
+template <int NT, int KS>
+__global__ void __launch_bounds__(TA_THREADS * KS, (NT <= 10 ? 2 : 1))
 attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, const float* __restrict__ o,
                    const float* __restrict__ lse, const float* __restrict__ d_o, int K, float* __restrict__ dqkv,
                    float* __restrict__ drelmean, b200ctr_dropout_t drop) {
   constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2;
+  constexpr int NTH = TA_THREADS * KS;
+  constexpr int NBW = (NB + KS - 1) / KS;                     // 16-key blocks per warp
+  constexpr int NTW = 2 * NBW;                                 // 8-key tiles per warp
+  constexpr int KPA = 16 * NBW * KS;                           // padded key extent covered by the dbias slots (>= Kp)
   constexpr int TS = Kp + 8;                                   // bf16 row stride of the transposed copies
   extern __shared__ __align__(16) uint32_t sm_u[];
   uint32_t* ks = sm_u;
@@ -181,26 +188,46 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
   float* lses = reinterpret_cast<float*>(doT + 64 * TS);        // [H][Kp]  (+inf on padded rows -> P = 0)
   float* dsum = lses + TA_H * Kp;                               // [H][Kp]
   float* bias = dsum + TA_H * Kp;                               // 2K-1
-  float* dbias = bias + (2 * K - 1);                            // 2Kp+1 : dbias[(key - query) + Kp]
+  long long* dbias = reinterpret_cast<long long*>(bias + ((2 * K - 1 + 1) & ~1));   // 2*KPA+1 : dbias[(key - query) + KPA]
+  // dbias is accumulated in 32.32 fixed point: 64-bit integer shared-memory atomics are native (fp32 ones are CAS
+  // loops) and the sum becomes order-independent, i.e. deterministic
   const int64_t b = blockIdx.x;
   const float* base = qkv + b * (int64_t)K * 3 * TA_D;
   const float* dob = d_o + b * (int64_t)K * TA_D;
   const float scale = rsqrtf((float)TA_HD);
-  ta_stage(ks, base + TA_D, 3 * TA_D, K, Kp, 1.f);
-  ta_stage(vs, base + 2 * TA_D, 3 * TA_D, K, Kp, 1.f);
-  for (int i = threadIdx.x; i < Kp * 64; i += TA_THREADS) {
-    const int r = i >> 6, c = i & 63;                           // coalesced global reads; transposed smem writes
-    float qv = 0.f, dv = 0.f;
-    if (r < K) { qv = base[(int64_t)r * 3 * TA_D + c] * scale; dv = dob[(int64_t)r * TA_D + c]; }
-    qT[c * TS + r] = __float2bfloat16(qv);
-    doT[c * TS + r] = __float2bfloat16(dv);
+  for (int i = threadIdx.x; i < Kp * 16; i += NTH) {
+    const int r = i >> 4, c = i & 15;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (r < K) {
+      kv = *reinterpret_cast<const float4*>(base + (int64_t)r * 3 * TA_D + TA_D + c * 4);
+      vv = *reinterpret_cast<const float4*>(base + (int64_t)r * 3 * TA_D + 2 * TA_D + c * 4);
+    }
+    *reinterpret_cast<uint4*>(ks + r * TA_RS + c * 4) = make_uint4(to_tf32(kv.x), to_tf32(kv.y), to_tf32(kv.z), to_tf32(kv.w));
+    *reinterpret_cast<uint4*>(vs + r * TA_RS + c * 4) = make_uint4(to_tf32(vv.x), to_tf32(vv.y), to_tf32(vv.z), to_tf32(vv.w));
+    // dQ is summed over the key parts with global reductions (RED.ADD.F32 is native at L2): zero this sample's rows first
+    if (r < K) *reinterpret_cast<float4*>(dqkv + (b * K + r) * (int64_t)(3 * TA_D) + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int tt = threadIdx.x; tt < 2 * K - 1; tt += TA_THREADS) {
+  {
+    constexpr int TOT = Kp * 64, PER = (TOT + NTH - 1) / NTH;   // coalesced global reads (all in flight), transposed smem writes
+    float qv[PER], dv[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int i = threadIdx.x + u * NTH, r = i >> 6, c = i & 63;
+      qv[u] = 0.f; dv[u] = 0.f;
+      if (i < TOT && r < K) { qv[u] = base[(int64_t)r * 3 * TA_D + c]; dv[u] = dob[(int64_t)r * TA_D + c]; }
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int i = threadIdx.x + u * NTH, r = i >> 6, c = i & 63;
+      if (i < TOT) { qT[c * TS + r] = __float2bfloat16(qv[u] * scale); doT[c * TS + r] = __float2bfloat16(dv[u]); }
+    }
+  }
+  for (int tt = threadIdx.x; tt < 2 * K - 1; tt += NTH) {
     const int d = tt - (K - 1);
     bias[tt] = relmean ? relmean[min(max(d, -max_len), max_len) + max_len] : 0.f;
   }
-  for (int tt = threadIdx.x; tt < 2 * Kp + 1; tt += TA_THREADS) dbias[tt] = 0.f;
-  for (int item = threadIdx.x; item < Kp * TA_H; item += TA_THREADS) {
+  for (int tt = threadIdx.x; tt < 2 * KPA + 1; tt += NTH) dbias[tt] = 0LL;
+  for (int item = threadIdx.x; item < Kp * TA_H; item += NTH) {
     const int h = item / Kp, i = item % Kp;
     float L = INFINITY, dsv = 0.f;
     if (i < K) {
@@ -213,18 +240,23 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
     lses[item] = L; dsum[item] = dsv;
   }
   __syncthreads();
-  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;      // warp == head
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int h = warp & 7, part = warp >> 3;                     // (head, key part)
+  const int jb0 = part * NBW;                                   // first 16-key block of this warp
   const DropCtx dctx = drop_ctx(drop);
-  float dk[NB][4], dv[NB][4];
+  float dk[NBW][4], dv[NBW][4];
 #pragma unroll
-  for (int jb = 0; jb < NB; ++jb) { dk[jb][0] = dk[jb][1] = dk[jb][2] = dk[jb][3] = 0.f; dv[jb][0] = dv[jb][1] = dv[jb][2] = dv[jb][3] = 0.f; }
+  for (int jl = 0; jl < NBW; ++jl) { dk[jl][0] = dk[jl][1] = dk[jl][2] = dk[jl][3] = 0.f; dv[jl][0] = dv[jl][1] = dv[jl][2] = dv[jl][3] = 0.f; }
   // dbias: a thread's four dS values of tile (i, j) lie on the diagonals 8(j-2i) + (2t-g) {+0, +1} (rows g) and the same
-  // shifted by -8 (rows g+8), so they accumulate in registers in slots indexed by j (+1) that rotate by two per query
-  // tile; only the two slots that leave the window are flushed (shared-memory atomics) per tile row.
-  float A0[NT + 1], A1[NT + 1];
+  // shifted by -8 (rows g+8), so they accumulate in registers in slots indexed by the local tile (+1) that rotate by two
+  // per query tile; only the two slots that leave the window are flushed (shared-memory atomics) per query tile.
+  float A0[NTW + 1], A1[NTW + 1];
 #pragma unroll
-  for (int sl = 0; sl <= NT; ++sl) { A0[sl] = 0.f; A1[sl] = 0.f; }
-  float* dbt = dbias + Kp + 2 * t - g;
+  for (int sl = 0; sl <= NTW; ++sl) { A0[sl] = 0.f; A1[sl] = 0.f; }
+  long long* dbt = dbias + KPA + 2 * t - g + 8 * (2 * jb0);    // + 8 * (local slot - 1 - 2i)
+  auto dbias_add = [](long long* p, float v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__float2ll_rn(v * 4294967296.f));
+  };
   const uint32_t* qT32 = reinterpret_cast<const uint32_t*>(qT + (h * 8 + g) * TS);
   const uint32_t* doT32 = reinterpret_cast<const uint32_t*>(doT + (h * 8 + g) * TS);
 #pragma unroll 1
@@ -243,74 +275,83 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
     const uint32_t keyb = dctx.on ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qb) : 0u;
     float dq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int jb = 0; jb < NB; ++jb) {
-      uint32_t pd_lo[2], pd_hi[2], ds_lo[2], ds_hi[2];
+    for (int jl = 0; jl < NBW; ++jl) {
+      if (jb0 + jl < NB) {                                      // warp-uniform
+        uint32_t pd_lo[2], pd_hi[2], ds_lo[2], ds_hi[2];
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const int j = 2 * jb + hf;
-        const int kc = 8 * j + 2 * t;
-        const uint32_t kb0 = ks[(8 * j + g) * TA_RS + h * 8 + t], kb1 = ks[(8 * j + g) * TA_RS + h * 8 + t + 4];
-        const uint32_t vb0 = vs[(8 * j + g) * TA_RS + h * 8 + t], vb1 = vs[(8 * j + g) * TA_RS + h * 8 + t + 4];
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_tf32(s, aq, kb0, kb1);
-        mma_tf32(dp, ad, vb0, vb1);
-        const bool v0 = kc < K, v1 = kc + 1 < K;
-        const float p0 = v0 ? __expf(s[0] + ba[kc] - La) : 0.f, p1 = v1 ? __expf(s[1] + ba[kc + 1] - La) : 0.f;
-        const float p2 = v0 ? __expf(s[2] + bb[kc] - Lb) : 0.f, p3 = v1 ? __expf(s[3] + bb[kc + 1] - Lb) : 0.f;
-        float c0 = 1.f, c1 = 1.f, c2 = 1.f, c3 = 1.f;
-        if (dctx.on) {
-          drop_pair(dctx, keya, (uint32_t)(4 * j + t), c0, c1);
-          drop_pair(dctx, keyb, (uint32_t)(4 * j + t), c2, c3);
+        for (int hf = 0; hf < 2; ++hf) {
+          const int jt = 2 * jl + hf;                           // local tile
+          const int j = 2 * jb0 + jt;                           // global tile
+          const int kc = 8 * j + 2 * t;
+          const uint32_t kb0 = ks[(8 * j + g) * TA_RS + h * 8 + t], kb1 = ks[(8 * j + g) * TA_RS + h * 8 + t + 4];
+          const uint32_t vb0 = vs[(8 * j + g) * TA_RS + h * 8 + t], vb1 = vs[(8 * j + g) * TA_RS + h * 8 + t + 4];
+          float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_tf32(s, aq, kb0, kb1);
+          mma_tf32(dp, ad, vb0, vb1);
+          const bool v0 = kc < K, v1 = kc + 1 < K;
+          const float p0 = v0 ? __expf(s[0] + ba[kc] - La) : 0.f, p1 = v1 ? __expf(s[1] + ba[kc + 1] - La) : 0.f;
+          const float p2 = v0 ? __expf(s[2] + bb[kc] - Lb) : 0.f, p3 = v1 ? __expf(s[3] + bb[kc + 1] - Lb) : 0.f;
+          float c0 = 1.f, c1 = 1.f, c2 = 1.f, c3 = 1.f;
+          if (dctx.on) {
+            drop_pair(dctx, keya, (uint32_t)(4 * j + t), c0, c1);
+            drop_pair(dctx, keyb, (uint32_t)(4 * j + t), c2, c3);
+          }
+          const float ds0 = p0 * (dp[0] * c0 - Da), ds1 = p1 * (dp[1] * c1 - Da);
+          const float ds2 = p2 * (dp[2] * c2 - Db), ds3 = p3 * (dp[3] * c3 - Db);
+          A0[jt + 1] += ds0; A1[jt + 1] += ds1; A0[jt] += ds2; A1[jt] += ds3;    // padded rows / keys contribute exact zeros
+          const uint32_t pa[4] = {to_tf32(ds0), to_tf32(ds2), to_tf32(ds1), to_tf32(ds3)};
+          mma_tf32(dq, pa, ks[(8 * j + 2 * t) * TA_RS + h * 8 + g], ks[(8 * j + 2 * t + 1) * TA_RS + h * 8 + g]);
+          pd_lo[hf] = pack_bf16x2(p0 * c0, p1 * c1); pd_hi[hf] = pack_bf16x2(p2 * c2, p3 * c3);
+          ds_lo[hf] = pack_bf16x2(ds0, ds1); ds_hi[hf] = pack_bf16x2(ds2, ds3);
         }
-        const float ds0 = p0 * (dp[0] * c0 - Da), ds1 = p1 * (dp[1] * c1 - Da);
-        const float ds2 = p2 * (dp[2] * c2 - Db), ds3 = p3 * (dp[3] * c3 - Db);
-        A0[j + 1] += ds0; A1[j + 1] += ds1; A0[j] += ds2; A1[j] += ds3;      // padded rows / keys contribute exact zeros
-        const uint32_t pa[4] = {to_tf32(ds0), to_tf32(ds2), to_tf32(ds1), to_tf32(ds3)};
-        mma_tf32(dq, pa, ks[(8 * j + 2 * t) * TA_RS + h * 8 + g], ks[(8 * j + 2 * t + 1) * TA_RS + h * 8 + g]);
-        pd_lo[hf] = pack_bf16x2(p0 * c0, p1 * c1); pd_hi[hf] = pack_bf16x2(p2 * c2, p3 * c3);
-        ds_lo[hf] = pack_bf16x2(ds0, ds1); ds_hi[hf] = pack_bf16x2(ds2, ds3);
+        // A = tile^T: rows = 16 keys of the block (even tile -> rows 0-7, odd tile -> rows 8-15), k = 16 queries
+        const uint32_t apd[4] = {movmatrix_t(pd_lo[0]), movmatrix_t(pd_lo[1]), movmatrix_t(pd_hi[0]), movmatrix_t(pd_hi[1])};
+        const uint32_t ads[4] = {movmatrix_t(ds_lo[0]), movmatrix_t(ds_lo[1]), movmatrix_t(ds_hi[0]), movmatrix_t(ds_hi[1])};
+        mma_bf16_16816(dv[jl], apd, bd0, bd1);
+        mma_bf16_16816(dk[jl], ads, bq0, bq1);
       }
-      // A = tile^T: rows = 16 keys of block jb (tile 2jb -> rows 0-7, tile 2jb+1 -> rows 8-15), k = 16 queries
-      const uint32_t apd[4] = {movmatrix_t(pd_lo[0]), movmatrix_t(pd_lo[1]), movmatrix_t(pd_hi[0]), movmatrix_t(pd_hi[1])};
-      const uint32_t ads[4] = {movmatrix_t(ds_lo[0]), movmatrix_t(ds_lo[1]), movmatrix_t(ds_hi[0]), movmatrix_t(ds_hi[1])};
-      mma_bf16_16816(dv[jb], apd, bd0, bd1);
-      mma_bf16_16816(dk[jb], ads, bq0, bq1);
     }
-    if (qa < K) *reinterpret_cast<float2*>(dqkv + (b * K + qa) * (int64_t)(3 * TA_D) + h * 8 + 2 * t) = make_float2(dq[0] * scale, dq[1] * scale);
-    if (qb < K) *reinterpret_cast<float2*>(dqkv + (b * K + qb) * (int64_t)(3 * TA_D) + h * 8 + 2 * t) = make_float2(dq[2] * scale, dq[3] * scale);
+    if (qa < K) {
+      float* dst = dqkv + (b * K + qa) * (int64_t)(3 * TA_D) + h * 8 + 2 * t;
+      atomicAdd(dst, dq[0] * scale); atomicAdd(dst + 1, dq[1] * scale);
+    }
+    if (qb < K) {
+      float* dst = dqkv + (b * K + qb) * (int64_t)(3 * TA_D) + h * 8 + 2 * t;
+      atomicAdd(dst, dq[2] * scale); atomicAdd(dst + 1, dq[3] * scale);
+    }
     if (drelmean) {
-      // slot sl holds the diagonal block u = sl - 1 - 2i
+      // local slot sl holds the diagonal block u = 2*jb0 + sl - 1 - 2i
       if (i + 1 < MT) {
-        atomicAdd(dbt + 8 * (NT - 1 - 2 * i), A0[NT]); atomicAdd(dbt + 8 * (NT - 1 - 2 * i) + 1, A1[NT]);
-        atomicAdd(dbt + 8 * (NT - 2 - 2 * i), A0[NT - 1]); atomicAdd(dbt + 8 * (NT - 2 - 2 * i) + 1, A1[NT - 1]);
+        dbias_add(dbt + 8 * (NTW - 1 - 2 * i), A0[NTW]); dbias_add(dbt + 8 * (NTW - 1 - 2 * i) + 1, A1[NTW]);
+        dbias_add(dbt + 8 * (NTW - 2 - 2 * i), A0[NTW - 1]); dbias_add(dbt + 8 * (NTW - 2 - 2 * i) + 1, A1[NTW - 1]);
 #pragma unroll
-        for (int sl = NT; sl >= 2; --sl) { A0[sl] = A0[sl - 2]; A1[sl] = A1[sl - 2]; }
+        for (int sl = NTW; sl >= 2; --sl) { A0[sl] = A0[sl - 2]; A1[sl] = A1[sl - 2]; }
         A0[0] = A0[1] = A1[0] = A1[1] = 0.f;
       } else {
 #pragma unroll
-        for (int sl = 0; sl <= NT; ++sl) {
-          atomicAdd(dbt + 8 * (sl - 1 - 2 * i), A0[sl]); atomicAdd(dbt + 8 * (sl - 1 - 2 * i) + 1, A1[sl]);
+        for (int sl = 0; sl <= NTW; ++sl) {
+          dbias_add(dbt + 8 * (sl - 1 - 2 * i), A0[sl]); dbias_add(dbt + 8 * (sl - 1 - 2 * i) + 1, A1[sl]);
         }
       }
     }
   }
 #pragma unroll
-  for (int jb = 0; jb < NB; ++jb) {
-    const int ka = 16 * jb + g, kb = ka + 8;
+  for (int jl = 0; jl < NBW; ++jl) {
+    const int ka = 16 * (jb0 + jl) + g, kb = ka + 8;
     if (ka < K) {
-      *reinterpret_cast<float2*>(dqkv + (b * K + ka) * (int64_t)(3 * TA_D) + TA_D + h * 8 + 2 * t) = make_float2(dk[jb][0], dk[jb][1]);
-      *reinterpret_cast<float2*>(dqkv + (b * K + ka) * (int64_t)(3 * TA_D) + 2 * TA_D + h * 8 + 2 * t) = make_float2(dv[jb][0], dv[jb][1]);
+      *reinterpret_cast<float2*>(dqkv + (b * K + ka) * (int64_t)(3 * TA_D) + TA_D + h * 8 + 2 * t) = make_float2(dk[jl][0], dk[jl][1]);
+      *reinterpret_cast<float2*>(dqkv + (b * K + ka) * (int64_t)(3 * TA_D) + 2 * TA_D + h * 8 + 2 * t) = make_float2(dv[jl][0], dv[jl][1]);
     }
     if (kb < K) {
-      *reinterpret_cast<float2*>(dqkv + (b * K + kb) * (int64_t)(3 * TA_D) + TA_D + h * 8 + 2 * t) = make_float2(dk[jb][2], dk[jb][3]);
-      *reinterpret_cast<float2*>(dqkv + (b * K + kb) * (int64_t)(3 * TA_D) + 2 * TA_D + h * 8 + 2 * t) = make_float2(dv[jb][2], dv[jb][3]);
+      *reinterpret_cast<float2*>(dqkv + (b * K + kb) * (int64_t)(3 * TA_D) + TA_D + h * 8 + 2 * t) = make_float2(dk[jl][2], dk[jl][3]);
+      *reinterpret_cast<float2*>(dqkv + (b * K + kb) * (int64_t)(3 * TA_D) + 2 * TA_D + h * 8 + 2 * t) = make_float2(dv[jl][2], dv[jl][3]);
     }
   }
   if (drelmean) {
     __syncthreads();
-    for (int tt = threadIdx.x; tt < 2 * K - 1; tt += TA_THREADS) {
+    for (int tt = threadIdx.x; tt < 2 * K - 1; tt += NTH) {
       const int d = tt - (K - 1);
-      atomicAdd(drelmean + min(max(d, -max_len), max_len) + max_len, dbias[d + Kp]);
+      atomicAdd(drelmean + min(max(d, -max_len), max_len) + max_len, (float)((double)dbias[d + KPA] * (1.0 / 4294967296.0)));
     }
   }
 }
@@ -339,10 +380,12 @@ static int ta_launch_fwd(const float* qkv, const float* relmean, int max_len, in
 template <int NT>
 static int ta_launch_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse, const float* d_o,
                          int64_t B, int K, float* dqkv, float* drelmean, b200ctr_dropout_t drop, cudaStream_t st) {
-  const size_t smem = ((size_t)2 * NT * 8 * TA_RS + 2 * TA_H * NT * 8 + 2 * K + 2 * NT * 8 + 2) * 4 + (size_t)2 * 64 * (NT * 8 + 8) * 2;
-  int rc = ta_set_smem((const void*)attn_tc_bwd_kernel<NT>, smem);
+  constexpr int KS = NT <= 10 ? 2 : 4;
+  constexpr int NBW = (NT / 2 + KS - 1) / KS, KPA = 16 * NBW * KS, Kp = NT * 8;
+  const size_t smem = ((size_t)2 * Kp * TA_RS + 2 * TA_H * Kp + 2 * K + 2) * 4 + (size_t)(2 * KPA + 2) * 8 + (size_t)2 * 64 * (Kp + 8) * 2;
+  int rc = ta_set_smem((const void*)attn_tc_bwd_kernel<NT, KS>, smem);
   if (rc) return rc;
-  attn_tc_bwd_kernel<NT><<<(unsigned)B, TA_THREADS, smem, st>>>(qkv, relmean, max_len, o, lse, d_o, K, dqkv, drelmean, drop);
+  attn_tc_bwd_kernel<NT, KS><<<(unsigned)B, TA_THREADS * KS, smem, st>>>(qkv, relmean, max_len, o, lse, d_o, K, dqkv, drelmean, drop);
   return B200CTR_OK;
 }
 
