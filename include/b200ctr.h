@@ -223,6 +223,25 @@ int b200ctr_ffn_bwd(const float* dy, const float* s2, const float* r2, const flo
                     float* dx1, float* dw1, float* db1, float* dw2, float* db2, float* dn2,
                     void* workspace, b200ctr_dropout_t drop, void* stream);
 
+/* ---- fused attention-side projections on tcgen05 (dare.py:64-66; the `amp: bf16` path) ---------------------------
+ * inproj_fwd:        qkv (T,192) = x . w_in^T + b_in                              (w_in (192,64) = mha.in_proj_weight)
+ * outproj_norm_fwd:  s1 = x_resid + o . w_out^T + b_out ; r1 = rsqrt(mean(s1^2)+eps) ; x1 = n1w * s1 * r1
+ * outproj_norm_bwd:  ds1 = RMSNorm'(dx1; s1, r1, n1w) ; d_o = ds1 . w_out ; dw_out, db_out, dn1 (overwritten)
+ * inproj_bwd:        dx = dqkv . w_in + d_resid (may be NULL) ; dw_in, db_in (overwritten)
+ * Persistent kernels, weights resident in shared memory, weight AND bias gradients accumulated in TMEM (the bias
+ * gradient is the 65th accumulator column: the activation operand carries a ones column), deterministic cross-CTA
+ * reduction.  workspace >= b200ctr_proj_bwd_workspace_bytes().  D == 64 (8 heads x head_dim 8).                  */
+int b200ctr_inproj_fwd(const float* x, const float* w_in, const float* b_in, int64_t T, int D, float* qkv, void* stream);
+int b200ctr_outproj_norm_fwd(const float* o, const float* w_out, const float* b_out, const float* x_resid,
+                             const float* n1w, float eps, int64_t T, int D, float* s1_out, float* r1_out,
+                             float* x1_out, void* stream);
+int64_t b200ctr_proj_bwd_workspace_bytes(void);
+int b200ctr_outproj_norm_bwd(const float* dx1, const float* s1, const float* r1, const float* n1w, const float* o,
+                             const float* w_out, int64_t T, int D, float* ds1_out, float* d_o, float* dw_out,
+                             float* db_out, float* dn1, void* workspace, void* stream);
+int b200ctr_inproj_bwd(const float* dqkv, const float* x, const float* w_in, const float* d_resid, int64_t T, int D,
+                       float* dx, float* dw_in, float* db_in, void* workspace, void* stream);
+
 /* ---- gated pooling + aux head  (dare.py:151-161) ------------------------------------------------------- */
 int b200ctr_pool_fwd(const float* x, const float* vals, const float* aux_w, const float* aux_b, int gating_relu,
                      int64_t B, int K, int D, float* u, int64_t ld_u, float* aux, float* w_out,

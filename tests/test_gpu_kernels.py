@@ -396,3 +396,38 @@ def test_gemm_bf16_operands(dev, M, N, K, ta, tb):
         big = ops.to_bf16(torch.cat([bd, bd], dim=1).contiguous())
         out2 = ops.gemm(ops.to_bf16(ad), big[:, K:], trans_b=True)
         assert max_err_scaled(out2.cpu(), ref) < 1e-5
+
+
+# ---- fused attention-side projections (csrc/proj_fused.cu) vs their unfused bf16 compositions --------------------------
+@pytest.mark.parametrize("T", [128, 1000, 128 * 300 + 17, 5])
+def test_fused_projections_match_unfused(dev, T):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(77 + T)
+    x, o = _rand(g, T, 64).to(dev), _rand(g, T, 64).to(dev)
+    w_in, b_in = (_rand(g, 192, 64) * 0.125).to(dev), (_rand(g, 192) * 0.1).to(dev)
+    w_out, b_out = (_rand(g, 64, 64) * 0.125).to(dev), (_rand(g, 64) * 0.1).to(dev)
+    n1 = (1.0 + 0.1 * _rand(g, 64)).to(dev)
+    dqkv, dx1 = _rand(g, T, 192).to(dev), _rand(g, T, 64).to(dev)
+    z = lambda *s: torch.zeros(*s, device=dev)
+    with ops.precision("bf16"):
+        qkv_u = ops.gemm(x, w_in, trans_b=True, bias=b_in, tc=True)
+        h_u = ops.gemm(o, w_out, trans_b=True, bias=b_out, tc=True)
+        s1_u, x1_u, r1_u = ops.add_rmsnorm_fwd(x, h_u, n1)
+        dn1_u = z(64)
+        ds1_u = ops.rmsnorm_bwd(dx1, s1_u, n1, r1_u, dn1_u)
+        dwo_u = ops.gemm(ds1_u, o, trans_a=True, tc=True)
+        dbo_u = ops.colsum(ds1_u)
+        do_u = ops.gemm(ds1_u, w_out, tc=True)
+        dwi_u = ops.gemm(dqkv, x, trans_a=True, tc=True)
+        dbi_u = ops.colsum(dqkv)
+        dx_u = ops.gemm(dqkv, w_in, residual=ds1_u, tc=True)
+    qkv = ops.inproj_fwd(x, w_in, b_in)
+    s1, x1, r1 = ops.outproj_norm_fwd(o, w_out, b_out, x, n1)
+    dwo, dbo, dn1, dwi, dbi = z(64, 64), z(64), z(64), z(192, 64), z(192)
+    ds1, d_o = ops.outproj_norm_bwd(dx1, s1_u, r1_u, n1, o, w_out, dwo, dbo, dn1)
+    dx = ops.inproj_bwd(dqkv, x, w_in, ds1_u, dwi, dbi)
+    for name, a, b, tol in (("qkv", qkv, qkv_u, 2e-3), ("s1", s1, s1_u, 2e-3), ("x1", x1, x1_u, 2e-3), ("r1", r1, r1_u, 2e-3),
+                            ("ds1", ds1, ds1_u, 1e-4), ("d_o", d_o, do_u, 3e-3), ("dw_out", dwo, dwo_u, 5e-3),
+                            ("db_out", dbo, dbo_u, 5e-3), ("dn1", dn1, dn1_u, 1e-3), ("dx", dx, dx_u, 3e-3),
+                            ("dw_in", dwi, dwi_u, 5e-3), ("db_in", dbi, dbi_u, 5e-3)):
+        assert max_err_scaled(a.cpu(), b.cpu()) < tol, name

@@ -131,10 +131,16 @@ def encoder_layer_fwd(x: Tensor, P: Dict[str, Tensor], i: int, spec: ModelSpec, 
     n = _layer_names(i)
     D, H = spec.D, spec.n_heads
     relmean = ops.relmean_fwd(P[n["rel"]]) if spec.pos_bias else None
-    qkv = ops.gemm(x, P[n["in_w"]], trans_b=True, bias=P[n["in_b"]])
-    o, lse = ops.attn_fwd(qkv, relmean, spec.top_k, B, K, H, D, dc(spec.p_mha, SITE_LAYER0 + 2 * i))
-    h = ops.gemm(o, P[n["out_w"]], trans_b=True, bias=P[n["out_b"]])
-    s1, x1, r1 = ops.add_rmsnorm_fwd(x, h, P[n["n1"]])
+    fused_proj = ops.get_precision() == "bf16" and D == 64 and H == 8
+    if fused_proj:        # persistent tcgen05 kernels with resident weights (csrc/proj_fused.cu)
+        qkv = ops.inproj_fwd(x, P[n["in_w"]], P[n["in_b"]])
+        o, lse = ops.attn_fwd(qkv, relmean, spec.top_k, B, K, H, D, dc(spec.p_mha, SITE_LAYER0 + 2 * i))
+        s1, x1, r1 = ops.outproj_norm_fwd(o, P[n["out_w"]], P[n["out_b"]], x, P[n["n1"]])
+    else:
+        qkv = ops.gemm(x, P[n["in_w"]], trans_b=True, bias=P[n["in_b"]])
+        o, lse = ops.attn_fwd(qkv, relmean, spec.top_k, B, K, H, D, dc(spec.p_mha, SITE_LAYER0 + 2 * i))
+        h = ops.gemm(o, P[n["out_w"]], trans_b=True, bias=P[n["out_b"]])
+        s1, x1, r1 = ops.add_rmsnorm_fwd(x, h, P[n["n1"]])
     if ops.get_precision() == "bf16" and ops.ffn_fused_ok(spec.ffn_hidden, D):
         # one tcgen05 kernel: the (tokens, ffn_hidden) activation stays on the SM; the backward recomputes it from x1
         x2, s2, r2 = ops.ffn_fwd(x1, P[n["f1_w"]], P[n["f1_b"]], P[n["f2_w"]], P[n["f2_b"]], P[n["n2"]],
@@ -146,7 +152,8 @@ def encoder_layer_fwd(x: Tensor, P: Dict[str, Tensor], i: int, spec: ModelSpec, 
                       dropout=dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1))
         h2 = ops.gemm(fd, P[n["f2_w"]], trans_b=True, bias=P[n["f2_b"]])
         s2, x2, r2 = ops.add_rmsnorm_fwd(x1, h2, P[n["n2"]])
-    return x2, dict(x=x, relmean=relmean, qkv=qkv, o=o, lse=lse, s1=s1, x1=x1, r1=r1, pre=pre, fd=fd, s2=s2, r2=r2)
+    return x2, dict(x=x, relmean=relmean, qkv=qkv, o=o, lse=lse, s1=s1, x1=x1, r1=r1, pre=pre, fd=fd, s2=s2, r2=r2,
+                    fused_proj=fused_proj)
 
 
 def encoder_layer_bwd(dy: Tensor, sv: dict, P: Dict[str, Tensor], i: int, spec: ModelSpec, B: int, K: int, dc: DropCtl,
@@ -168,10 +175,15 @@ def encoder_layer_bwd(dy: Tensor, sv: dict, P: Dict[str, Tensor], i: int, spec: 
         ops.gemm(dpre, sv["x1"], trans_a=True, out=G(n["f1_w"]))
         ops.colsum(dpre, out=G(n["f1_b"]))
         dx1 = ops.gemm(dpre, P[n["f1_w"]], residual=d_s2)
-    d_s1 = ops.rmsnorm_bwd(dx1, sv["s1"], P[n["n1"]], sv["r1"], G(n["n1"]))
-    ops.gemm(d_s1, sv["o"], trans_a=True, out=G(n["out_w"]))
-    ops.colsum(d_s1, out=G(n["out_b"]))
-    d_o = ops.gemm(d_s1, P[n["out_w"]])
+    fused_proj = sv.get("fused_proj", False)
+    if fused_proj:
+        d_s1, d_o = ops.outproj_norm_bwd(dx1, sv["s1"], sv["r1"], P[n["n1"]], sv["o"], P[n["out_w"]], G(n["out_w"]),
+                                         G(n["out_b"]), G(n["n1"]))
+    else:
+        d_s1 = ops.rmsnorm_bwd(dx1, sv["s1"], P[n["n1"]], sv["r1"], G(n["n1"]))
+        ops.gemm(d_s1, sv["o"], trans_a=True, out=G(n["out_w"]))
+        ops.colsum(d_s1, out=G(n["out_b"]))
+        d_o = ops.gemm(d_s1, P[n["out_w"]])
     drelmean = None
     if spec.pos_bias:
         drelmean = torch.zeros_like(sv["relmean"])
@@ -179,6 +191,8 @@ def encoder_layer_bwd(dy: Tensor, sv: dict, P: Dict[str, Tensor], i: int, spec: 
                         dc(spec.p_mha, SITE_LAYER0 + 2 * i))
     if spec.pos_bias:
         G(n["rel"]).copy_(ops.relmean_bwd(drelmean, H))
+    if fused_proj:
+        return ops.inproj_bwd(dqkv, sv["x"], P[n["in_w"]], d_s1, G(n["in_w"]), G(n["in_b"]))
     ops.gemm(dqkv, sv["x"], trans_a=True, out=G(n["in_w"]))
     ops.colsum(dqkv, out=G(n["in_b"]))
     dx = ops.gemm(dqkv, P[n["in_w"]], residual=d_s1)

@@ -452,6 +452,56 @@ def add_rmsnorm_fwd(a, b, w, eps=1e-6, save_sum=True):
     return s, y, r
 
 
+# ---- fused attention-side projections (csrc/proj_fused.cu) ---------------------------------------------------------
+def inproj_fwd(x, w_in, b_in):
+    lib = _lib.load()
+    T, D = x.shape
+    qkv = torch.empty((T, 3 * D), device=x.device, dtype=torch.float32)
+    _run("inproj_fwd", lib.b200ctr_inproj_fwd, _p(_f32(x)), _p(w_in), _p(b_in), T, D, _p(qkv), _stream())
+    _count()
+    return qkv
+
+
+def outproj_norm_fwd(o, w_out, b_out, x_resid, n1w, eps=1e-6):
+    """Returns (s1, x1, r1) like add_rmsnorm_fwd(x_resid, o @ w_out^T + b_out, n1w)."""
+    lib = _lib.load()
+    T, D = o.shape
+    s1, x1 = torch.empty_like(o), torch.empty_like(o)
+    r1 = torch.empty((T,), device=o.device, dtype=torch.float32)
+    _run("outproj_norm_fwd", lib.b200ctr_outproj_norm_fwd, _p(_f32(o)), _p(w_out), _p(b_out), _p(x_resid), _p(n1w), eps, T, D,
+         _p(s1), _p(r1), _p(x1), _stream())
+    _count()
+    return s1, x1, r1
+
+
+def _proj_ws(dev):
+    return torch.empty((_lib.load().b200ctr_proj_bwd_workspace_bytes(),), device=dev, dtype=torch.uint8)
+
+
+def outproj_norm_bwd(dx1, s1, r1, n1w, o, w_out, dw_out, db_out, dn1):
+    """Returns (d_s1, d_o); overwrites dw_out, db_out, dn1."""
+    lib = _lib.load()
+    T, D = o.shape
+    ds1, d_o = torch.empty_like(o), torch.empty_like(o)
+    ws = _proj_ws(o.device)
+    _run("outproj_norm_bwd", lib.b200ctr_outproj_norm_bwd, _p(_f32(dx1)), _p(s1), _p(r1), _p(n1w), _p(o), _p(w_out), T, D, _p(ds1),
+         _p(d_o), _p(dw_out), _p(db_out), _p(dn1), _p(ws), _stream())
+    _count(2)
+    return ds1, d_o
+
+
+def inproj_bwd(dqkv, x, w_in, d_resid, dw_in, db_in):
+    """Returns dx = dqkv @ w_in + d_resid; overwrites dw_in, db_in."""
+    lib = _lib.load()
+    T, D = x.shape
+    dx = torch.empty_like(x)
+    ws = _proj_ws(x.device)
+    _run("inproj_bwd", lib.b200ctr_inproj_bwd, _p(_f32(dqkv)), _p(x), _p(w_in), _p(d_resid), T, D, _p(dx), _p(dw_in), _p(db_in),
+         _p(ws), _stream())
+    _count(2)
+    return dx
+
+
 def ffn_fused_ok(hidden: int, D: int = 64) -> bool:
     """Shapes the fused tcgen05 FFN kernels are built for (else: the unfused gemm composition)."""
     return D == 64 and hidden % 128 == 0 and 0 < hidden <= 384
