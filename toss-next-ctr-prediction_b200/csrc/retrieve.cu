@@ -33,8 +33,17 @@ constexpr int RT_MAX_SHARDS = 8;
 struct RtShards {
   float* p[RT_MAX_SHARDS];
   int mask, shift;                       // shard = row & mask ; local row = row >> shift
+  int ld_mode;                           // 0: ld.global.nc.L1::no_allocate (streaming), 1: plain ld.global (peer shards)
   __device__ __forceinline__ float4* row4(int t) const { return reinterpret_cast<float4*>(p[t & mask]) + (int64_t)(t >> shift) * (RT_D / 4); }
 };
+
+__device__ __forceinline__ float4 rt_load_row(const RtShards& sh, int t, int hl) {
+  const float4* p = sh.row4(t) + hl;
+  if (sh.ld_mode == 0) return ldg_nc_f4(p);
+  float4 r;
+  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
 
 __device__ __forceinline__ uint32_t orderable(float s) {
   uint32_t u = __float_as_uint(s);
@@ -76,7 +85,7 @@ retrieve_fwd_kernel(const IT* __restrict__ seq, const float* __restrict__ q, con
       int p = base + hw + u * NHW;
       t[u] = (p < L) ? toks[p] : pad_id;
       r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t[u] != pad_id) r[u] = ldg_nc_f4(emb_att.row4(t[u]) + hl);
+      if (t[u] != pad_id) r[u] = rt_load_row(emb_att, t[u], hl);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -129,7 +138,7 @@ retrieve_fwd_kernel(const IT* __restrict__ seq, const float* __restrict__ q, con
       r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (k < K) {
         int t = toks[(int)(keys[k] & 0xffffffffu)];
-        if (t != pad_id) r[u] = ldg_nc_f4(emb_rep.row4(t) + hl);
+        if (t != pad_id) r[u] = rt_load_row(emb_rep, t, hl);
       }
     }
 #pragma unroll
@@ -185,7 +194,7 @@ retrieve_fwd_warp_kernel(const IT* __restrict__ seq, const float* __restrict__ q
       const int p = base + hw * 8 + u;
       t[u] = (p < L) ? toks[p] : pad_id;
       r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t[u] != pad_id) r[u] = ldg_nc_f4(emb_att.row4(t[u]) + hl);
+      if (t[u] != pad_id) r[u] = rt_load_row(emb_att, t[u], hl);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -316,7 +325,7 @@ retrieve_fwd_warp_kernel(const IT* __restrict__ seq, const float* __restrict__ q
       r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (k < K) {
         const int t = toks[(int)(selk[k] & 0xffffffffULL)];
-        if (t != pad_id) r[u] = ldg_nc_f4(emb_rep.row4(t) + hl);
+        if (t != pad_id) r[u] = rt_load_row(emb_rep, t, hl);
       }
     }
 #pragma unroll
@@ -341,7 +350,7 @@ retrieve_bwd_kernel(const int32_t* __restrict__ tok, const float* __restrict__ q
     int t = tok[b * K + k];
     if (t == pad_id) continue;                      // masked_fill blocks the gradient; padding_idx row gets none
     float dv = dvals[b * K + k];
-    float4 a = ldg_nc_f4(emb_att.row4(t) + hl);
+    float4 a = rt_load_row(emb_att, t, hl);
     acc.x = fmaf(dv, a.x, acc.x); acc.y = fmaf(dv, a.y, acc.y); acc.z = fmaf(dv, a.z, acc.z); acc.w = fmaf(dv, a.w, acc.w);
     if (has_datt) {
       float4 g = make_float4(dv * qv.x, dv * qv.y, dv * qv.z, dv * qv.w);
@@ -377,6 +386,10 @@ static int make_shards(RtShards& out, const float* const* ptrs, int n, const cha
   int shift = 0;
   while ((1 << shift) < n) ++shift;
   out.mask = n - 1; out.shift = shift;
+  static const int env_mode = getenv("B200CTR_RT_LDMODE") ? atoi(getenv("B200CTR_RT_LDMODE")) : -1;
+  // measured on 2 x B200 (profiles/README.md): the non-coherent no-allocate path reaches only ~175 GB/s on PEER memory,
+  // plain ld.global ~800 GB/s; locally the streaming path is the faster one
+  out.ld_mode = env_mode >= 0 ? env_mode : (n > 1 ? 1 : 0);
   for (int i = 0; i < RT_MAX_SHARDS; ++i) out.p[i] = const_cast<float*>(ptrs && i < n ? ptrs[i] : nullptr);
   for (int i = 0; i < n; ++i)
     if (!out.p[i]) { set_error("%s: shard %d is NULL", what, i); return B200CTR_E_INVALID_ARG; }
