@@ -262,6 +262,17 @@ int b200ctr_rowrms_fwd(const float* x, int64_t ldx, const float* w, float eps, i
                        float* z, int64_t ld_z, float* r, void* stream);
 int b200ctr_rowrms_bwd(const float* dz, int64_t ld_dz, const float* x, int64_t ldx, const float* w, const float* r,
                        int64_t B, int64_t N, float* dx, int64_t ld_dx, float* dw_partial, int n_partials, void* stream);
+/* Fused quadratic interaction on tcgen05 (qnn_alpha.py:86-97; `amp: bf16` path): z_bf16 = the bf16 copy of the normed
+ * features (B*F, 64) from b200ctr_rowrms_fwd_bf16, Ucat (64, C) = qnn.U laid out [d][head*rank].
+ *   fwd: s[b,c] = sum_f (z.Ucat), quad = s^2 - sum_f (z.Ucat)^2          -- the (B*F, C) product never reaches HBM
+ *   bwd: dz (B*F, 64) = (dquad * 2 (s - z.Ucat)) . Ucat^T + dz_resid (may be NULL / may alias dz) ; dUcat (64, C) overwritten
+ * F <= 256, C % 32 == 0, C <= 128, D == 64.  workspace >= b200ctr_fm_fused_bwd_workspace_bytes().                */
+int b200ctr_fm_fused_fwd(const void* z_bf16, const float* Ucat, int64_t B, int F, int C, int D, float* s_out,
+                         float* quad_out, void* stream);
+int64_t b200ctr_fm_fused_bwd_workspace_bytes(void);
+int b200ctr_fm_fused_bwd(const void* z_bf16, const float* Ucat, const float* s, const float* dquad,
+                         const float* dz_resid, int64_t B, int F, int C, int D, float* dz, float* dUcat,
+                         void* workspace, void* stream);
 /* headproj: inter[b, h*P+p] = sum_r quad[b, h*R+r] * V[h][r][p] for all heads in one launch (qnn_alpha.py:96);
  * bwd: dquad and dV (overwritten; deterministic two-stage batch reduction through `workspace`).              */
 int b200ctr_headproj_fwd(const float* quad, const float* V, int64_t B, int H, int R, int P, float* inter, void* stream);

@@ -431,3 +431,31 @@ def test_fused_projections_match_unfused(dev, T):
                             ("db_out", dbo, dbo_u, 5e-3), ("dn1", dn1, dn1_u, 1e-3), ("dx", dx, dx_u, 3e-3),
                             ("dw_in", dwi, dwi_u, 5e-3), ("db_in", dbi, dbi_u, 5e-3)):
         assert max_err_scaled(a.cpu(), b.cpu()) < tol, name
+
+
+@pytest.mark.parametrize("B,F,C", [(300, 200, 96), (7, 200, 96), (200, 128, 64), (150, 256, 128), (33, 37, 32)])
+def test_fm_fused_matches_unfused(dev, B, F, C):
+    """Fused tcgen05 quadratic interaction == gemm + fm_reduce / fm_grad + gemms on the same bf16-rounded operands."""
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(B + F + C)
+    z = (_rand(g, B, F * 64) * 0.5).to(dev)
+    U = (_rand(g, 64, C) * 0.2).to(dev)
+    dquad = _rand(g, B, C).to(dev)
+    dzm = _rand(g, B, F * 64).to(dev)
+    z16 = ops.to_bf16(z)
+    zb = z16.float()
+    s, quad = ops.fm_fused_fwd(z16, U, B, F)
+    A = (zb.view(B * F, 64).double() @ _bf(U).double()).view(B, F, C)
+    s_ref = A.sum(1)
+    quad_ref = s_ref * s_ref - (A * A).sum(1)
+    assert max_err_scaled(s.cpu(), s_ref.cpu()) < 1e-4
+    assert max_err_scaled(quad.cpu(), quad_ref.cpu()) < 1e-4
+    dz, dU = ops.fm_fused_bwd(z16, U, s, dquad, dzm, B, F)
+    dA = (dquad.double().unsqueeze(1) * 2.0 * (s.double().unsqueeze(1) - A)).float()          # (B,F,C)
+    dAb = _bf(dA).double().view(B * F, C)
+    dz_ref = dAb @ _bf(U).double().t() + dzm.double().view(B * F, 64)
+    dU_ref = zb.view(B * F, 64).double().t() @ dAb
+    # dA is rounded to bf16 as a tensor-core operand: fp32-vs-fp64 noise in (s - A) occasionally flips one rounding
+    # (1 bf16 ulp of a |dA| ~ 100 element), hence 3e-3 rather than accumulation-order tolerance
+    assert max_err_scaled(dz.view(B * F, 64).cpu(), dz_ref.cpu()) < 3e-3
+    assert max_err_scaled(dU.cpu(), dU_ref.cpu()) < 2e-3

@@ -262,8 +262,13 @@ def qnn_fwd(P: Dict[str, Tensor], spec: ModelSpec, xF: Tensor, dc: DropCtl, B_to
     else:
         z, rz = ops.rowrms_fwd(flat, P["qnn.pre_norm.w"])
     Ucat = P["qnn.U"].permute(1, 0, 2).reshape(D, C).contiguous()            # (D, H*r): layout plumbing only
-    A = ops.gemm(z.view(B * F, D), Ucat)                                       # (B*F, C)
-    s, quad = ops.fm_reduce(A, B, F, C)
+    fm_fused = z16 is not None and ops.fm_fused_ok(F, C, D)
+    if fm_fused:          # one tcgen05 kernel; the (B*F, C) product z.Ucat stays in TMEM
+        A = None
+        s, quad = ops.fm_fused_fwd(z16, Ucat, B, F)
+    else:
+        A = ops.gemm(z.view(B * F, D), Ucat)                                   # (B*F, C)
+        s, quad = ops.fm_reduce(A, B, F, C)
     V = P["qnn.V"]
     if ops.headproj_ok(H, r, Pd):
         inter = ops.headproj_fwd(quad, V)
@@ -302,7 +307,8 @@ def qnn_fwd(P: Dict[str, Tensor], spec: ModelSpec, xF: Tensor, dc: DropCtl, B_to
                             act=ops.ACT_RELU, dropout=dc(spec.p_qnn, SITE_MLP0 + li))
             acts.append(hcur)
         logit = ops.gemm(hcur, P[f"qnn.mlp.{mlp[-1]}.weight"], trans_b=True, bias=P[f"qnn.mlp.{mlp[-1]}.bias"])
-    sv.update(igd=igd, acts=acts, mlp=mlp, B_total=Bt, z16=z16 if W0_16 is not None else None, W0_16=W0_16)
+    sv.update(igd=igd, acts=acts, mlp=mlp, B_total=Bt, z16=z16 if W0_16 is not None else None, W0_16=W0_16,
+              z16_fm=z16 if fm_fused else None)
     return logit.view(B), sv
 
 
@@ -364,15 +370,23 @@ def qnn_bwd(P, spec: ModelSpec, sv: dict, dlogit: Tensor, dc: DropCtl, G: Callab
         for h in range(H):
             ops.gemm(quad[:, h * r:(h + 1) * r], dinter[:, h * Pd:(h + 1) * Pd], trans_a=True, out=gV[h])
             ops.gemm(dinter[:, h * Pd:(h + 1) * Pd], V[h], trans_b=True, out=dquad[:, h * r:(h + 1) * r])
-    dA = ops.fm_grad_(sv["A"], sv["s"], dquad, B, F, C)                       # in place over the saved A
-    z3 = z.view(B * F, D)
-    dUcat = ops.gemm(z3, dA, trans_a=True)                                    # (D, C)
-    G("qnn.U").copy_(dUcat.view(D, H, r).permute(1, 0, 2))
+    dz_mlp = None
     if spec.use_residual:
-        dz = ops.gemm(dh16, W0_16[:, :N]) if dh16 is not None else ops.gemm(dh, W0[:, :N])      # (B, N)
-        ops.gemm(dA, sv["Ucat"], trans_b=True, residual=dz.view(B * F, D), out=dz.view(B * F, D))
+        dz_mlp = ops.gemm(dh16, W0_16[:, :N]) if dh16 is not None else ops.gemm(dh, W0[:, :N])  # (B, N)
+    if sv.get("z16_fm") is not None:
+        # recompute z.Ucat in TMEM, dA as a bf16 operand tile, dz (+ the MLP branch) and dUcat in one kernel
+        dz, dUcat = ops.fm_fused_bwd(sv["z16_fm"], sv["Ucat"], sv["s"], dquad, dz_mlp, B, F, dz_out=dz_mlp)
+        G("qnn.U").copy_(dUcat.view(D, H, r).permute(1, 0, 2))
     else:
-        dz = ops.gemm(dA, sv["Ucat"], trans_b=True).view(B, N)
+        dA = ops.fm_grad_(sv["A"], sv["s"], dquad, B, F, C)                   # in place over the saved A
+        z3 = z.view(B * F, D)
+        dUcat = ops.gemm(z3, dA, trans_a=True)                                # (D, C)
+        G("qnn.U").copy_(dUcat.view(D, H, r).permute(1, 0, 2))
+        if spec.use_residual:
+            dz = dz_mlp
+            ops.gemm(dA, sv["Ucat"], trans_b=True, residual=dz.view(B * F, D), out=dz.view(B * F, D))
+        else:
+            dz = ops.gemm(dA, sv["Ucat"], trans_b=True).view(B, N)
     dflat, dpw = ops.rowrms_bwd(dz, xF.view(B, N), P["qnn.pre_norm.w"], sv["rz"])
     G("qnn.pre_norm.w").copy_(dpw)
     return dflat.view(B, F, D)

@@ -622,6 +622,36 @@ def rowrms_bwd(dz, x, w, r, n_partials=296):
     return dx, colsum(part)
 
 
+def fm_fused_ok(F: int, C: int, D: int) -> bool:
+    return D == 64 and 1 <= F <= 256 and 16 <= C <= 128 and C % 32 == 0
+
+
+def fm_fused_fwd(z16, Ucat, B, F):
+    """(s, quad), each (B, C), from the bf16 normed features z16 (B, F*D) and Ucat (D, C)."""
+    lib = _lib.load()
+    D, C = Ucat.shape
+    assert z16.dtype == torch.bfloat16 and z16.is_contiguous() and Ucat.is_contiguous()
+    s = torch.empty((B, C), device=z16.device, dtype=torch.float32)
+    quad = torch.empty((B, C), device=z16.device, dtype=torch.float32)
+    _run("fm_fused_fwd", lib.b200ctr_fm_fused_fwd, _p(z16), _p(Ucat), B, F, C, D, _p(s), _p(quad), _stream())
+    _count()
+    return s, quad
+
+
+def fm_fused_bwd(z16, Ucat, s, dquad, dz_resid, B, F, dz_out=None):
+    """Returns (dz (B, F*D), dUcat (D, C)); dz_resid (B, F*D) or None is added; dz_out may alias dz_resid."""
+    lib = _lib.load()
+    D, C = Ucat.shape
+    dz = dz_out if dz_out is not None else torch.empty((B, F * D), device=z16.device, dtype=torch.float32)
+    dU = torch.empty((D, C), device=z16.device, dtype=torch.float32)
+    ws = torch.empty((lib.b200ctr_fm_fused_bwd_workspace_bytes(),), device=z16.device, dtype=torch.uint8)
+    assert dz.is_contiguous() and (dz_resid is None or dz_resid.is_contiguous())
+    _run("fm_fused_bwd", lib.b200ctr_fm_fused_bwd, _p(z16), _p(Ucat), _p(s), _p(dquad), _p(dz_resid), B, F, C, D, _p(dz), _p(dU),
+         _p(ws), _stream())
+    _count(2)
+    return dz, dU
+
+
 def headproj_ok(H: int, R: int, P: int) -> bool:
     C = H * R
     if R > 32 or H * P > 1536 or C > 384 or C <= 0:
