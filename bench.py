@@ -6,8 +6,9 @@
 
 Workload (BASELINE.json configs[1]): cfgs/dare_qnn_next.yaml — B=8192, L=400, K=60, 3 encoder layers, QNN-alpha
 (6 heads, rank 16, proj 192, MLP 512-256), 35 hashed-categorical tables, 82 numeric + 82 mask features, two
-10,000,000 x 64 sequence tables, fp32 (the cfg's `amp: none`), dropout ON (train mode), EMA 0.999 — on synthetic
-Toss-shaped data (b200ctr.synth).  One process per GPU; N > 1 = data parallel, B per GPU fixed (weak scaling).
+10,000,000 x 64 sequence tables, `amp: bf16` (BASELINE configs[1] names fp32/bf16; `--amp none` = the exact-fp32 CUDA-core
+path), dropout ON (train mode), EMA 0.999 — on synthetic Toss-shaped data (b200ctr.synth).  One process per GPU; N > 1 =
+data parallel over the batch with the two sequence tables row-sharded across the GPUs, B per GPU fixed (weak scaling).
 
 Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM; `e2e` = the same step
 through FusedTrainer.step() with pinned HOST batches (H2D inside the timed region) and a D2H read of the loss every
@@ -292,43 +293,79 @@ def run_cuda(args):
             a = fam.setdefault(f, [0, 0.0])
             a[0] += n; a[1] += t
         top = sorted(fam.items(), key=lambda kv: -kv[1][1])
-        flops = {"gemm": 0.0, "gemm_bf16": 0.0}
-        for tag, (n, t) in prof.items():
-            for famname in flops:
-                if tag.startswith(famname + "["):
-                    M, N, K = tag[len(famname) + 1:-3].split("x")
-                    flops[famname] += 2.0 * int(M) * int(N) * int(K) * n
-        roof = None
-        famname = "gemm_bf16" if fam.get("gemm_bf16", [0, 0.0])[1] >= fam.get("gemm", [0, 0.0])[1] else "gemm"
-        gemm_n, gemm_ms = fam.get(famname, [0, 0.0])
-        if gemm_n:
-            ach = flops[famname] / (gemm_ms * 1e-3) / 1e12
-            kname = ("gemm_tc_kernel (tcgen05.mma kind::f16, bf16 operands converted on load, fp32 TMEM accumulators)"
-                     if famname == "gemm_bf16" else "gemm_kernel (fp32 CUDA-core contraction)")
-            roof = {"kernel": kname + "; every dense projection of the step", "bound": "tensor",
-                    "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"], "traffic": None,
-                    "peak_source": f"{pk['src']} bf16 sustained", "launches": gemm_n, "avg_launch_ms": gemm_ms / gemm_n,
-                    "share_of_step": gemm_ms / tot_ms}
-        # gather kernel (north_star: gather GB/s vs HBM peak): algorithmic bytes of retrieve_fwd on these batches
-        L, Kk, D = cfg["sequence"]["max_len"], cfg["sequence"]["top_k"], 64
+        # ---- algorithmic work per launch of every modelled kernel family ----
+        sq = cfg["sequence"]
+        L, Kk, D = sq["max_len"], sq["top_k"], 64
+        hid = sq.get("tfm", {}).get("ffn_hidden", 0) if sq["transformer_block"] else 0
+        T = B * Kk
+        qa = cfg["model"]["qnn_alpha"]
+        F_all = 1 + 2 * configs.N_NUM + len(cols)
         gbytes = 0.0
         for i in range(args.steps):
             seq = host[i % NB][0]["seq"]
             ell = (seq != 0).sum(1).double()
             kv = torch.clamp(ell, max=Kk)
             gbytes += float((8 * L + 4 * D * ell + 4 * D * kv + 4 * D + 4 * D * Kk + 12 * Kk).sum())
-        gather = None
-        if "retrieve_fwd" in prof:
-            n, t = prof["retrieve_fwd"]
-            ach = gbytes / (t * 1e-3) / 1e9
-            gather = {"kernel": "retrieve_fwd_kernel", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                      "frac": ach / pk["hbm"], "frac_of_nominal_8TBs": ach / 8000.0, "traffic": None, "avg_launch_ms": t / n,
-                      "bytes_convention": "8L + 4D*l + 4D*min(K,l) + 4D + 4D*K + 12K per sample; every logical row use counted once"}
+        gemm_flops = {"gemm": 0.0, "gemm_bf16": 0.0}
+        for tag, (n, t) in prof.items():
+            for fn_ in gemm_flops:
+                if tag.startswith(fn_ + "["):
+                    M_, N_, K_ = tag[len(fn_) + 1:-3].split("x")
+                    gemm_flops[fn_] += 2.0 * int(M_) * int(N_) * int(K_) * n
+        models = {   # family -> (bound, work per launch [FLOP or byte], description)
+            "attn_tc_bwd": ("tensor", 10.0 * Kk * Kk * D * B, "attn_tc_bwd_kernel (mma.sync TF32/bf16, head_dim 8; one pass: S, dP, dQ, dK, dV = 10 K^2 D FLOP/sample)"),
+            "attn_tc_fwd": ("tensor", 4.0 * Kk * Kk * D * B, "attn_tc_fwd_kernel (mma.sync TF32: QK^T and PV = 4 K^2 D FLOP/sample)"),
+            "ffn_fwd": ("tensor", 4.0 * T * D * hid, "ffn_fwd_kernel (tcgen05 fused FFN block: 2 contractions of T x 64 x ffn_hidden)"),
+            "ffn_bwd": ("tensor", 8.0 * T * D * hid, "ffn_bwd1/ffn_bwd2 (tcgen05 fused FFN backward: 4 algorithmic contractions; the recompute is not counted)"),
+            "inproj_fwd": ("hbm", 4.0 * T * (D + 3 * D), "lin_fwd_kernel<192> (x in, qkv out)"),
+            "outproj_norm_fwd": ("hbm", 4.0 * T * D * 4 + 4.0 * T, "lin_fwd_kernel<64,norm> (o, x in; s1, x1, r1 out)"),
+            "outproj_norm_bwd": ("hbm", 4.0 * T * D * 5, "lin_bwd_kernel<64,norm> (dx1, s1, o in; d_s1, d_o out)"),
+            "inproj_bwd": ("hbm", 4.0 * T * (3 * D + 3 * D), "lin_bwd_kernel<192> (dqkv, x, d_s1 in; dx out)"),
+            "fm_fused_fwd": ("hbm", 2.0 * B * F_all * D, "fm_fwd_kernel (bf16 z in)"),
+            "fm_fused_bwd": ("hbm", B * F_all * D * (2.0 + 4.0 + 4.0), "fm_bwd_kernel (bf16 z, fp32 dz in / out)"),
+            "retrieve_fwd": ("hbm", gbytes / max(1, args.steps), "retrieve_fwd_warp_kernel (8L + 4D*l + 4D*min(K,l) + 4D + 4D*K + 12K bytes/sample; every logical row use counted once)"),
+        }
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "r01d_traffic.json")
+        if os.path.exists(tpath) and args.cfg == "dare_qnn_next" and B == 8192:
+            traffic = json.load(open(tpath))
+
+        def roof_of(name):
+            n, t = fam[name]
+            if name in ("gemm", "gemm_bf16"):
+                ach = gemm_flops[name] / (t * 1e-3) / 1e12
+                desc = ("gemm_tc_kernel / gemm_tc_ws_kernel (tcgen05.mma kind::f16, fp32 TMEM accumulators); every remaining dense "
+                        "projection of the step" if name == "gemm_bf16" else "gemm_kernel (fp32 CUDA-core contraction)")
+                return {"kernel": desc, "bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
+                        "traffic": None, "peak_source": f"{pk['src']} bf16 sustained", "launches": n, "avg_launch_ms": t / n,
+                        "share_of_step": t / tot_ms}
+            bound, work, desc = models[name]
+            tr = traffic.get("ffn_bwd1" if name == "ffn_bwd" else name, {}).get("traffic_bytes_per_launch")
+            if name == "ffn_bwd" and tr is not None:
+                tr += traffic.get("ffn_bwd2", {}).get("traffic_bytes_per_launch", 0)
+            if bound == "tensor":
+                ach = work * n / (t * 1e-3) / 1e12
+                return {"kernel": desc, "bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
+                        "traffic": tr, "peak_source": f"{pk['src']} bf16 sustained", "launches": n, "avg_launch_ms": t / n,
+                        "share_of_step": t / tot_ms}
+            ach = work * n / (t * 1e-3) / 1e9
+            return {"kernel": desc, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                    "frac_of_nominal_8TBs": ach / 8000.0, "traffic": tr, "peak_source": f"{pk['src']} HBM copy", "launches": n,
+                    "avg_launch_ms": t / n, "share_of_step": t / tot_ms}
+
+        modelled = [k for k, _ in top if k in models or k in ("gemm", "gemm_bf16")]
+        roof = roof_of(modelled[0]) if modelled else None
+        if roof is not None and modelled[0].startswith("attn_tc"):
+            roof["note"] = ("issue-bound on the exp / dropout-hash work per score (ncu: SM throughput 51-73 %, tensor pipe 6-9 %), "
+                            "not on the tensor pipe: head_dim 8 gives 2 MMAs per 128 scores")
+        kernels = [dict(roof_of(k), family=k) for k in modelled[:10]]
+        gather = roof_of("retrieve_fwd") if "retrieve_fwd" in fam else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.amp == "bf16" else "fp32", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, B), "global_batch": B * world, "parallelism": (f"dp{world}" if world == 1 else
+            "config": {"workload": workload_name(cfg, B), "global_batch": B * world,
+                       "parallelism": (f"dp{world}" if world == 1 else
                                        f"dp{world} over the batch; seq tables " + ("replicated" if args.replicate_tables else
                                        f"row-sharded {world}-way, gathered/scattered through NVLink peer memory inside the kernels")),
                        "l2_policy": f"{NB} distinct batches rotate; each step touches >10 GB (two 2.56 GB tables + optimizer state "
@@ -340,11 +377,12 @@ def run_cuda(args):
             "gpu_launches": int(launches),
             "roofline": roof,
             "gather_roofline": gather,
-            "kernel_time_share": {k: round(v[1] / tot_ms, 4) for k, v in top[:12]},
-            "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in top[:12]},
+            "kernel_rooflines": kernels,
+            "kernel_time_share": {k: round(v[1] / tot_ms, 4) for k, v in top[:14]},
+            "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in top[:14]},
             "gemm_shapes_ms_per_step": {k: [v[0] // args.steps, round(v[1] / args.steps, 4)] for k, v in
                                         sorted(((t, v) for t, v in prof.items() if t.startswith("gemm")),
-                                               key=lambda kv: -kv[1][1])[:16]},
+                                               key=lambda kv: -kv[1][1])[:10]},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference(args.cfg, 2, 1, sample_B=args.ref_batch)
