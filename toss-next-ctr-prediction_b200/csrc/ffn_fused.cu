@@ -12,8 +12,9 @@
 //   persistent CTA (one per SM), 13 warps:
 //     warps 0-3   stream x1 tiles (fp32 -> bf16 K-major core matrices, double buffered), then run the final
 //                 residual + RMSNorm epilogue of the previous tile (thread == token row == TMEM lane)
-//     warps 4-11  GELU epilogue: TMEM chunk -> +b1 -> erf-GELU -> dropout -> bf16 -> smem A operand of GEMM2
-//     warp  12    one thread issues every tcgen05.mma; tcgen05.commit -> mbarriers hand buffers back
+//     warps 4-19  GELU epilogue: TMEM chunk -> +b1 -> erf-GELU -> dropout -> bf16 -> smem A operand of GEMM2
+//                 (16 warps = 4 TMEM lane groups x 4 column quarters: the epilogue is the bottleneck, see profiles/)
+//     warp  20    one thread issues every tcgen05.mma; tcgen05.commit -> mbarriers hand buffers back
 //
 // Shared-memory operand layout is the canonical SWIZZLE_NONE one of gemm_tc.cu: 8 x 16-byte core matrices,
 // k-group stride R*16 bytes ("LBO"), mn-group stride 128 bytes ("SBO").
@@ -26,6 +27,9 @@ constexpr int FF_D = 64;          // emb_dim
 constexpr int FF_TM = 128;        // tokens per tile (UMMA M)
 constexpr int FF_HC = 64;         // hidden chunk (UMMA N of GEMM1, K of GEMM2)
 constexpr int FF_NT = 13 * 32;
+constexpr int FFW_EPI_WARPS = 16;                 // forward kernel: 4 loader/RMSNorm + 16 GELU-epilogue + 1 MMA warp
+constexpr int FFW_MMA_WARP = 4 + FFW_EPI_WARPS;
+constexpr int FFW_NT = (FFW_MMA_WARP + 1) * 32;
 constexpr int FF_A_BYTES = FF_TM * FF_D * 2;        // 16 KB: x1 tile, bf16
 constexpr int FF_FD_BYTES = FF_TM * FF_HC * 2;      // 16 KB: activation chunk, bf16
 constexpr int FF_WCHUNK = FF_HC * FF_D * 2;         // 8 KB of W1 or W2 per hidden chunk
@@ -92,7 +96,7 @@ __device__ __forceinline__ void ffn_mma_kk(uint32_t tmem_d, uint32_t a_base, uin
   }
 }
 
-__global__ void __launch_bounds__(FF_NT, 1)
+__global__ void __launch_bounds__(FFW_NT, 1)
 ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const float* __restrict__ b1,
                const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ n2w, float eps,
                int64_t T, int hidden, float* __restrict__ s2_out, float* __restrict__ r2_out, float* __restrict__ x2_out,
@@ -112,19 +116,19 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
   const int64_t tiles = (T + FF_TM - 1) / FF_TM;
   const int n_it = (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);      // tiles of this CTA
 
-  if (warp == 12) tmem_alloc(&bars->tmem_base, 256);
+  if (warp == FFW_MMA_WARP) tmem_alloc(&bars->tmem_base, 256);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bars->a_full[s]), 4); mbar_init(smem_u32(&bars->a_empty[s]), 1);
-      mbar_init(smem_u32(&bars->fd_full[s]), 8); mbar_init(smem_u32(&bars->fd_empty[s]), 1);
+      mbar_init(smem_u32(&bars->fd_full[s]), FFW_EPI_WARPS); mbar_init(smem_u32(&bars->fd_empty[s]), 1);
       mbar_init(smem_u32(&bars->h2_full[s]), 1); mbar_init(smem_u32(&bars->h2_empty[s]), 4);
     }
-    mbar_init(smem_u32(&bars->p_full), 1); mbar_init(smem_u32(&bars->p_empty), 8);
+    mbar_init(smem_u32(&bars->p_full), 1); mbar_init(smem_u32(&bars->p_empty), FFW_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  ffn_stage_w1(w1s, w1, hidden, tid, FF_NT);
-  ffn_stage_w2(w2s, w2, hidden, tid, FF_NT);
-  for (int i = tid; i < hidden; i += FF_NT) b1s[i] = b1[i];
+  ffn_stage_w1(w1s, w1, hidden, tid, FFW_NT);
+  ffn_stage_w2(w2s, w2, hidden, tid, FFW_NT);
+  for (int i = tid; i < hidden; i += FFW_NT) b1s[i] = b1[i];
   if (tid < FF_D) { b2s[tid] = b2[tid]; n2s[tid] = n2w[tid]; }
   fence_async_smem();
   tc_fence_before();
@@ -190,9 +194,9 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
                               n2s[4 * j + 2] * __uint_as_float(v[4 * j + 2]) * r, n2s[4 * j + 3] * __uint_as_float(v[4 * j + 3]) * r);
       }
     }
-  } else if (warp < 12) {
+  } else if (warp < FFW_MMA_WARP) {
     // ---------------------------------------- GELU epilogue -----------------------------------------------------
-    const int ew = warp - 4, q = ew & 3, half = ew >> 2;
+    const int ew = warp - 4, q = ew & 3, part = ew >> 2;          // 16 warps: TMEM lane group x 16-column quarter of the chunk
     const int r = q * 32 + lane;
     uint32_t g = 0;
     const DropCtx dctx = drop_ctx(drop);
@@ -202,15 +206,15 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
       for (int c = 0; c < NC; ++c, ++g) {
         mbar_wait(smem_u32(&bars->p_full), g & 1);
         tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(tmem + P_COL + half * 32 + ((uint32_t)(q * 32) << 16), v);
+        uint32_t v[16];
+        tmem_ld16(tmem + P_COL + part * 16 + ((uint32_t)(q * 32) << 16), v);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->p_empty));
-        const int n0 = c * FF_HC + half * 32;
-        uint32_t pk[16];
+        const int n0 = c * FF_HC + part * 16;
+        uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
+        for (int j = 0; j < 16; j += 2) {
           float f0 = gelu_erf(__uint_as_float(v[j]) + b1s[n0 + j]);
           float f1 = gelu_erf(__uint_as_float(v[j + 1]) + b1s[n0 + j + 1]);
           if (dctx.on) {
@@ -224,8 +228,8 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
         if (g >= 2) mbar_wait(smem_u32(&bars->fd_empty[fb]), ((g >> 1) - 1) & 1);
         unsigned char* dst = fds + fb * FF_FD_BYTES;
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const int kg = half * 4 + j4;
+        for (int j4 = 0; j4 < 2; ++j4) {
+          const int kg = part * 2 + j4;
           *reinterpret_cast<uint4*>(dst + (kg * 16 + (r >> 3)) * 128 + (r & 7) * 16) =
               make_uint4(pk[4 * j4], pk[4 * j4 + 1], pk[4 * j4 + 2], pk[4 * j4 + 3]);
         }
@@ -263,7 +267,7 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == FFW_MMA_WARP) {
     __syncwarp();
     tmem_dealloc(tmem, 256);
   }
@@ -697,7 +701,7 @@ extern "C" int b200ctr_ffn_fwd(const float* x1, const float* w1, const float* b1
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ffn_fwd smem)");
   const int64_t tiles = ceil_div(T, (int64_t)FF_TM);
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)num_sms());
-  ffn_fwd_kernel<<<grid, FF_NT, smem, as_stream(stream)>>>(x1, w1, b1, w2, b2, n2w, eps, T, hidden, s2_out, r2_out, x2_out, drop);
+  ffn_fwd_kernel<<<grid, FFW_NT, smem, as_stream(stream)>>>(x1, w1, b1, w2, b2, n2w, eps, T, hidden, s2_out, r2_out, x2_out, drop);
   B200_LAUNCH_CHECK("ffn_fwd_kernel");
   return B200CTR_OK;
 }

@@ -38,24 +38,24 @@ __device__ __forceinline__ float fm_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-// z16 rows of sample b (F x 64 bf16, contiguous) -> K-major core matrices, 128-row blocks; rows >= F stay zero (static)
+// z16 rows of sample b (F x 64 bf16, contiguous) -> K-major core matrices, 128-row blocks; rows >= F stay zero (static).
+// Thread t of the 128 loaders owns rows t and t + 128 (no division by the runtime F); the 8 16-byte chunks of a row go
+// to the 8 k-groups.  All loads of a thread are issued before the first store.
 __device__ __forceinline__ void fm_stage_z(unsigned char* dst, const __nv_bfloat16* __restrict__ z16, int64_t b, int F, int ptid) {
   const uint4* src = reinterpret_cast<const uint4*>(z16 + b * (int64_t)F * FM_D);
-  for (int u0 = ptid; u0 < F * 8; u0 += 128 * 4) {
-    uint4 v[4];
+  uint4 v[2][8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int u = u0 + k * 128;
-      v[k] = make_uint4(0u, 0u, 0u, 0u);
-      if (u < F * 8) { const int r = u % F, c = u / F; v[k] = __ldg(src + r * 8 + c); }
-    }
+  for (int blk = 0; blk < 2; ++blk) {
+    const int r = blk * 128 + ptid;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int u = u0 + k * 128;
-      if (u < F * 8) {
-        const int r = u % F, c = u / F, blk = r >> 7, rr = r & 127;
-        *reinterpret_cast<uint4*>(dst + blk * FM_ZBLK + (c * 16 + (rr >> 3)) * 128 + (rr & 7) * 16) = v[k];
-      }
+    for (int c = 0; c < 8; ++c) v[blk][c] = r < F ? __ldg(src + r * 8 + c) : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 2; ++blk) {
+    if (blk * 128 < F) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(dst + blk * FM_ZBLK + (c * 16 + (ptid >> 3)) * 128 + (ptid & 7) * 16) = v[blk][c];
     }
   }
 }

@@ -23,15 +23,6 @@ constexpr int PJ_NT = 13 * 32;
 constexpr int PJ_X_BYTES = PJ_TM * PJ_D * 2;          // 16 KB bf16 activation tile
 constexpr int PJ_ONES_BYTES = 2 * PJ_TM * 16;         // 4 KB: two extra 8-column groups (ones column + zeros)
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 // [128 tokens x 64] fp32 rows (stride ld floats) -> bf16 K-major core matrices (R = 128); NTHR cooperating threads
 template <int NTHR>
 __device__ __forceinline__ void pj_stage_x(unsigned char* dst, const float* __restrict__ x, int64_t ld, int64_t m0, int64_t T, int ptid) {
