@@ -26,7 +26,6 @@ namespace b200ctr {
 constexpr int FF_D = 64;          // emb_dim
 constexpr int FF_TM = 128;        // tokens per tile (UMMA M)
 constexpr int FF_HC = 64;         // hidden chunk (UMMA N of GEMM1, K of GEMM2)
-constexpr int FF_NT = 13 * 32;
 constexpr int FFW_EPI_WARPS = 16;                 // forward kernel: 4 loader/RMSNorm + 16 GELU-epilogue + 1 MMA warp
 constexpr int FFW_MMA_WARP = 4 + FFW_EPI_WARPS;
 constexpr int FFW_NT = (FFW_MMA_WARP + 1) * 32;
@@ -321,7 +320,24 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-__global__ void __launch_bounds__(FF_NT, 1)
+// 16 columns: fold the two half-warps, then the same halving network; lanes j and j + 16 <- column j
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(FFW_NT, 1)
 ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, const float* __restrict__ r2,
                 const float* __restrict__ n2w, const float* __restrict__ x1, const float* __restrict__ w1,
                 const float* __restrict__ b1, const float* __restrict__ w2, int64_t T, int hidden,
@@ -347,17 +363,17 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
   float* ws_db2 = ws_db1 + (size_t)4 * hidden;
   float* ws_dn2 = ws_db2 + 4 * FF_D;
 
-  if (warp == 12) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == FFW_MMA_WARP) tmem_alloc(&bars->tmem_base, 512);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->in_full[s]), 4); mbar_init(smem_u32(&bars->in_empty[s]), 1); }
-    mbar_init(smem_u32(&bars->pq_full), 1); mbar_init(smem_u32(&bars->pq_empty), 8);
-    mbar_init(smem_u32(&bars->blk_full), 8); mbar_init(smem_u32(&bars->blk_empty), 1);
+    mbar_init(smem_u32(&bars->pq_full), 1); mbar_init(smem_u32(&bars->pq_empty), FFW_EPI_WARPS);
+    mbar_init(smem_u32(&bars->blk_full), FFW_EPI_WARPS); mbar_init(smem_u32(&bars->blk_empty), 1);
     mbar_init(smem_u32(&bars->done), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  ffn_stage_w1(w1s, w1, hidden, tid, FF_NT);
-  ffn_stage_w2_mn(w2s, w2, hidden, tid, FF_NT);
-  for (int i = tid; i < hidden; i += FF_NT) b1s[i] = b1[i];
+  ffn_stage_w1(w1s, w1, hidden, tid, FFW_NT);
+  ffn_stage_w2_mn(w2s, w2, hidden, tid, FFW_NT);
+  for (int i = tid; i < hidden; i += FFW_NT) b1s[i] = b1[i];
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -377,11 +393,11 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
       unsigned char* dss = xs + FF_A_BYTES;
       ffn_stage_tile(xs, x1, m0, T, tid);
 #pragma unroll 1
-      for (int rr = 0; rr < 32; rr += 4) {
-        float2 d[4], s[4];
-        float r[4];
+      for (int rr = 0; rr < 32; rr += 8) {      // 8 rows (24 loads) in flight per lane: the loader is latency-bound
+        float2 d[8], s[8];
+        float r[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int64_t m = m0 + warp * 32 + rr + u;
           d[u] = make_float2(0.f, 0.f); s[u] = d[u]; r[u] = 0.f;
           if (m < T) {
@@ -391,7 +407,7 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int row = warp * 32 + rr + u;
           const int64_t m = m0 + row;
           const float2 g = make_float2(d[u].x * nw.x, d[u].y * nw.y);
@@ -411,9 +427,9 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
     }
     reinterpret_cast<float2*>(ws_db2 + warp * FF_D)[lane] = db_acc;
     reinterpret_cast<float2*>(ws_dn2 + warp * FF_D)[lane] = dn_acc;
-  } else if (warp < 12) {
+  } else if (warp < FFW_MMA_WARP) {
     // ------------------------------- epilogue: fd, dpre, db1 ---------------------------------------------------
-    const int ew = warp - 4, q = ew & 3, half = ew >> 2;
+    const int ew = warp - 4, q = ew & 3, part = ew >> 2;          // 16 warps: TMEM lane group x 16-column quarter of the chunk
     const int r = q * 32 + lane;
     float db1_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     uint32_t g = 0;
@@ -425,18 +441,18 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
       for (int c = 0; c < NC; ++c, ++g) {
         mbar_wait(smem_u32(&bars->pq_full), g & 1);
         tc_fence_after();
-        uint32_t pv[32], qv[32];
+        uint32_t pv[16], qv[16];
         const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
-        tmem_ld32(tmem + P_COL + half * 32 + lane_bits, pv);
-        tmem_ld32(tmem + Q_COL + half * 32 + lane_bits, qv);
+        tmem_ld16(tmem + P_COL + part * 16 + lane_bits, pv);
+        tmem_ld16(tmem + Q_COL + part * 16 + lane_bits, qv);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->pq_empty));
-        const int n0 = c * FF_HC + half * 32;
-        uint32_t fpk[16], dpk[16];
-        float dp[32];
+        const int n0 = c * FF_HC + part * 16;
+        uint32_t fpk[8], dpk[8];
+        float dp[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
+        for (int j = 0; j < 16; j += 2) {
           float dsc[2] = {1.f, 1.f};
           if (dctx.on) drop_pair(dctx, rkey, (uint32_t)(n0 + j) >> 1, dsc[0], dsc[1]);
 #pragma unroll
@@ -450,7 +466,7 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
           }
         }
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
+        for (int j = 0; j < 16; j += 2) {
           fpk[j >> 1] = pack_bf16(__uint_as_float(pv[j]), __uint_as_float(pv[j + 1]));
           dpk[j >> 1] = pack_bf16(dp[j], dp[j + 1]);
         }
@@ -458,8 +474,8 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
         if ((c & 1) == 0 && bk >= 1) mbar_wait(smem_u32(&bars->blk_empty), (bk - 1) & 1);
         unsigned char* spill = dpre_spill + ((size_t)tile * NB + (c >> 1)) * FF_BLK_BYTES;
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const int kg = (c & 1) * 8 + half * 4 + j4;
+        for (int j4 = 0; j4 < 2; ++j4) {
+          const int kg = (c & 1) * 8 + part * 2 + j4;
           const uint32_t off = (uint32_t)((kg * 16 + (r >> 3)) * 128 + (r & 7) * 16);
           const uint4 dv = make_uint4(dpk[4 * j4], dpk[4 * j4 + 1], dpk[4 * j4 + 2], dpk[4 * j4 + 3]);
           *reinterpret_cast<uint4*>(fdb + off) = make_uint4(fpk[4 * j4], fpk[4 * j4 + 1], fpk[4 * j4 + 2], fpk[4 * j4 + 3]);
@@ -471,7 +487,7 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->blk_full));
         }
-        const float cs = warp_colsum32(dp, lane);
+        const float cs = warp_colsum16(dp, lane);          // lane j (and j + 16) <- column j summed over the warp's 32 rows
 #pragma unroll
         for (int k = 0; k < 6; ++k) db1_acc[k] += (k == c) ? cs : 0.f;
       }
@@ -481,19 +497,21 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
     tc_fence_after();
     for (int which = 0; which < 2; ++which) {
       for (int b = 0; b < NB; ++b) {
-        uint32_t v[32];
-        tmem_ld32(tmem + (which ? DW2_COL : DW1_COL) + b * 64 + half * 32 + ((uint32_t)(q * 32) << 16), v);
-        float4* dst = reinterpret_cast<float4*>(wsc + ((size_t)which * hidden + b * 128 + r) * FF_D + half * 32);
+        uint32_t v[16];
+        tmem_ld16(tmem + (which ? DW2_COL : DW1_COL) + b * 64 + part * 16 + ((uint32_t)(q * 32) << 16), v);
+        float4* dst = reinterpret_cast<float4*>(wsc + ((size_t)which * hidden + b * 128 + r) * FF_D + part * 16);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 4; ++j)
           dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
       }
     }
-    for (int c = 0; c < NC; ++c) {
-      float vsel = 0.f;
+    if (lane < 16) {
+      for (int c = 0; c < NC; ++c) {
+        float vsel = 0.f;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) vsel = (k == c) ? db1_acc[k] : vsel;
-      ws_db1[(size_t)q * hidden + c * FF_HC + half * 32 + lane] = vsel;
+        for (int k = 0; k < 6; ++k) vsel = (k == c) ? db1_acc[k] : vsel;
+        ws_db1[(size_t)q * hidden + c * FF_HC + part * 16 + lane] = vsel;
+      }
     }
   } else if (lane == 0) {
     // ------------------------------- MMA issuer ---------------------------------------------------------------------
@@ -532,7 +550,7 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == FFW_MMA_WARP) {
     __syncwarp();
     tmem_dealloc(tmem, 512);
   }
@@ -735,7 +753,7 @@ extern "C" int b200ctr_ffn_bwd(const float* dy, const float* s2, const float* r2
   const size_t smem1 = (size_t)2 * (hidden / FF_HC) * FF_WCHUNK + 2 * FF_IN_BYTES + 2 * FF_BLK_BYTES + (size_t)hidden * 4 + sizeof(FfnBwdBars) + 16;
   cudaError_t e = cudaFuncSetAttribute(ffn_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ffn_bwd1 smem)");
-  ffn_bwd1_kernel<<<grid, FF_NT, smem1, st>>>(dy, s2, r2, n2w, x1, w1, b1, w2, T, hidden, ds2, spill, ws, drop);
+  ffn_bwd1_kernel<<<grid, FFW_NT, smem1, st>>>(dy, s2, r2, n2w, x1, w1, b1, w2, T, hidden, ds2, spill, ws, drop);
   B200_LAUNCH_CHECK("ffn_bwd1_kernel");
   const int n_out = 2 * hidden * FF_D + hidden + 2 * FF_D;
   ffn_bwd_reduce_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(ws, grid, hidden, dw1, db1, dw2, db2, dn2);
