@@ -177,6 +177,20 @@ int b200ctr_retrieve_bwd_sharded(const int32_t* tok, const float* q, const float
                                  const float* dsel_rep, const float* dvals, int64_t B, int K, int D, int pad_id,
                                  float* dq, float* const* datt_shards, float* const* drep_shards, void* stream);
 
+/* Staged scatter for row-sharded tables: gradient rows of tokens owned by another rank are written with plain stores
+ * into that owner's staging buffer stage[owner][my_rank][slot] (slot = b*K + k; stage_* = HOST arrays of n_shards device
+ * pointers to each rank's (n_shards, stage_cap, D) buffer, peer-mapped), rows owned by this rank are reduced locally.
+ * After a cross-rank barrier the owner runs b200ctr_stage_apply over the all-gathered token ids gtok (n_src, n_slots)
+ * to add the staged rows into its local gradient shard.                                                        */
+int b200ctr_retrieve_bwd_staged(const int32_t* tok, const float* q, const float* const* att_shards, int n_shards,
+                                const float* dsel_rep, const float* dvals, int64_t B, int K, int D, int pad_id,
+                                float* dq, float* const* datt_shards, float* const* drep_shards,
+                                float* const* stage_att, float* const* stage_rep, int my_rank, int64_t stage_cap,
+                                void* stream);
+int b200ctr_stage_apply(const int32_t* gtok, int n_src, int64_t n_slots, int64_t stage_cap, int pad_id, int n_shards,
+                        int rank, const float* stage_att, const float* stage_rep, float* g_att, float* g_rep, int D,
+                        void* stream);
+
 /* ---- DARE encoder layer pieces  (dare.py:29-37, 53-70) ---------------------------------------------------
  * attention: qkv (M=B*K, 3D) packed [q|k|v]; bias[i,j] = relmean[j-i+max_len] (relmean = mean over heads of
  *   pbias.rel.weight, length 2*max_len+1, may be NULL); softmax(q k^T/sqrt(hd) + bias); dropout on probabilities;

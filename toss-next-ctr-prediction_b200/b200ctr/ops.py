@@ -395,14 +395,26 @@ def retrieve_bwd(tok, q, emb_att, dsel_rep, dvals, pad_id, datt_dense=None, drep
     D = q.shape[1]
     dq = torch.empty_like(q)
     if isinstance(emb_att, ShardedTable):
-        _run("retrieve_bwd", lib.b200ctr_retrieve_bwd_sharded, _p(tok), _p(q), emb_att.ptrs, emb_att.n, _p(dsel_rep), _p(dvals), B, K,
+        sa = getattr(datt_dense, "stage_ptrs", None) if datt_dense is not None else None
+        sr = getattr(drep_dense, "stage_ptrs", None) if drep_dense is not None else None
+        ref = datt_dense if datt_dense is not None else drep_dense
+        _run("retrieve_bwd", lib.b200ctr_retrieve_bwd_staged, _p(tok), _p(q), emb_att.ptrs, emb_att.n, _p(dsel_rep), _p(dvals), B, K,
              D, pad_id, _p(dq), datt_dense.ptrs if datt_dense is not None else None,
-             drep_dense.ptrs if drep_dense is not None else None, _stream())
+             drep_dense.ptrs if drep_dense is not None else None, sa, sr,
+             getattr(ref, "stage_rank", 0) if ref is not None else 0, getattr(ref, "stage_cap", 0) if ref is not None else 0, _stream())
     else:
         _run("retrieve_bwd", lib.b200ctr_retrieve_bwd, _p(tok), _p(q), _p(emb_att), _p(dsel_rep), _p(dvals), B, K, D, pad_id, _p(dq),
              _p(datt_dense), _p(drep_dense), _stream())
     _count()
     return dq
+
+
+def stage_apply(gtok, n_src, n_slots, stage_cap, pad_id, n_shards, rank, stage_att, stage_rep, g_att, g_rep):
+    """Owner side of the staged scatter: add the rows other ranks staged for tokens this rank owns."""
+    lib = _lib.load()
+    _run("stage_apply", lib.b200ctr_stage_apply, _p(gtok), n_src, n_slots, stage_cap, pad_id, n_shards, rank, _p(stage_att),
+         _p(stage_rep), _p(g_att), _p(g_rep), g_att.shape[1] if g_att is not None else g_rep.shape[1], _stream())
+    _count()
 
 
 def rows_localize(tok, pad_id, n_shards, rank):

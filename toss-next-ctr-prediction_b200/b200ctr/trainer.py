@@ -34,6 +34,7 @@ rows up" -> "peers read them" and "peers scattered gradients" -> "owner applies 
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Dict, List, Optional
 
@@ -205,6 +206,25 @@ class FusedTrainer:
         torch.cuda.empty_cache()
         dist.barrier(group=self.pg)
 
+    def _ensure_staging(self, n_slots: int):
+        """Receive buffers of the staged gradient scatter: stage[n][src_rank, slot, :] on every rank, peer-mapped.  COLLECTIVE
+        on first use (and if a later batch is larger than any seen before)."""
+        import torch.distributed as dist
+        if getattr(self, "stage_cap", 0) >= n_slots:
+            return
+        N, D = self.world, self.spec.D
+        self.stage_cap = int(n_slots)
+        for n in BIG_TABLES:
+            buf = torch.empty((N, self.stage_cap, D), device=self.dev, dtype=torch.float32)
+            self.tables[n]["stage"] = buf
+            handles = [None] * N
+            dist.all_gather_object(handles, ops.ipc_export(buf), group=self.pg)
+            addrs = [buf.data_ptr() if r == self.rank else ops.ipc_import(*handles[r]) for r in range(N)]
+            gsh = self.Gv[n]
+            gsh.stage_ptrs = (ctypes.c_void_p * N)(*addrs)
+            gsh.stage_rank, gsh.stage_cap = self.rank, self.stage_cap
+        dist.barrier(group=self.pg)
+
     def _row_set(self, ids: torch.Tensor):
         """Bitmap(s) of the global rows listed in `ids`: (maps, n_maps).  Sharded mode: all ranks' bitmaps, all-gathered
         (1.25 MB per rank at 10 M rows; the collective doubles as a device-side barrier)."""
@@ -302,6 +322,8 @@ class FusedTrainer:
                     t = self.tables[n]
                     ops.rowopt_catchup(seq, spec.pad_id, self.owner, t["state"], t["p"], t["m"], t["v"], t["ema"],
                                        self.global_step - 1, self.hist)
+        if self.shard:
+            self._ensure_staging(B_local * min(spec.top_k, dbatch["seq"].shape[1]))
         hook = (lambda t: self._allreduce(t)) if self.world > 1 else None
         logits, aux, sv = hp.model_fwd(self.P, spec, dbatch, dc, self.cache, B_total=B_local * self.world, colsum_hook=hook)
         counts_override = None
@@ -325,9 +347,21 @@ class FusedTrainer:
         # ---- global-norm clip (coef stays on the device) ----
         self.acc.zero_()
         if self.lazy and self.bitmaps:
-            # sharded: C1 already happened inside retrieve_bwd (gradient rows scattered into the owners' shards over NVLink);
-            # the owners only need the set of touched rows.  Its all-gather also orders every peer's scatter before the update.
-            maps, n_maps = self._row_set(tok)
+            if self.shard:
+                # C1 happened inside retrieve_bwd: rows owned by other ranks were stored into the owners' staging buffers over
+                # NVLink.  The all-gather of the selected token ids tells every owner which staged rows are its own (and is the
+                # barrier that orders every peer's stores before the owner-side reduction).
+                n_slots = tok.numel()
+                gtok = torch.empty((self.world * n_slots,), device=self.dev, dtype=torch.int32)
+                torch.distributed.all_gather_into_tensor(gtok, tok.reshape(-1), group=self.pg)
+                ops.stage_apply(gtok, self.world, n_slots, self.stage_cap, spec.pad_id, self.world, self.rank,
+                                self.tables[BIG_TABLES[0]]["stage"], self.tables[BIG_TABLES[1]]["stage"],
+                                self.tables[BIG_TABLES[0]]["g"], self.tables[BIG_TABLES[1]]["g"])
+                self.bm_mine.zero_()
+                ops.bitmap_mark(gtok, spec.pad_id, self.vocab_global, self.bm_mine)
+                maps, n_maps = self.bm_mine, 1
+            else:
+                maps, n_maps = self._row_set(tok)
             for n in BIG_TABLES:
                 ops.rows_sqnorm_bm(maps, n_maps, self.bm_words, self.n_shards, self.shard_rank, self.tables[n]["g"], self.acc)
             if self.shard:
