@@ -271,47 +271,45 @@ __device__ __forceinline__ void stage_operand_ws(unsigned char* smem, const floa
   }
 }
 
-// Same layout, operands already bf16 in global memory (one 16-byte load == one core-matrix row, no conversion)
+// Same layout, operands already bf16 in global memory: one 16-byte cp.async (LDGSTS) == one core-matrix row, no
+// registers in between, so a producer thread can keep several ring stages of loads in flight (the operand tiles mostly
+// come from L2, ~1 us away; with register staging only ~32 KB per SM were in flight and the tensor pipe starved).
+// Partially valid rows use the src-size form (zero fill); rows out of range are zeroed with a plain store.
 template <int R, bool KMAJOR, int WS_PROD_THREADS>
 __device__ __forceinline__ void stage_operand_ws(unsigned char* smem, const __nv_bfloat16* __restrict__ g, int64_t ld, int64_t mn0,
                                                  int64_t mn_end, int64_t k0, int64_t k_end, bool vec_ok, int ptid) {
   constexpr int UNITS = R * 8;
   static_assert(UNITS % WS_PROD_THREADS == 0, "tile/threads mismatch");
   constexpr int ITERS = UNITS / WS_PROD_THREADS;
-  // 16-byte loads in flight per thread: the operands mostly come from L2 (tiles are re-read by many CTAs), ~1 us away
-  constexpr int UNR = (ITERS % 8 == 0) ? 8 : ((ITERS % 6 == 0) ? 6 : ((ITERS % 4 == 0) ? 4 : ((ITERS % 3 == 0) ? 3 : ((ITERS % 2 == 0) ? 2 : 1))));
-#pragma unroll 1
-  for (int it0 = 0; it0 < ITERS; it0 += UNR) {
-    uint4 v[UNR];
-    uint32_t off[UNR];
-#pragma unroll
-    for (int q = 0; q < UNR; ++q) {
-      const int u = ptid + (it0 + q) * WS_PROD_THREADS;
-      v[q] = make_uint4(0u, 0u, 0u, 0u);
-      int64_t row, col, row_end, col_end;          // 8 consecutive elements [row][col .. col+7] of the global matrix
-      if (KMAJOR) {
-        const int r = u % R, c = u / R;
-        off[q] = (uint32_t)((c * (R / 8) + (r >> 3)) * 128 + (r & 7) * 16);
-        row = mn0 + r; col = k0 + c * 8; row_end = mn_end; col_end = k_end;
-      } else {
-        const int kk = u % TC_BK, gidx = u / TC_BK;
-        off[q] = (uint32_t)(((kk >> 3) * (R / 8) + gidx) * 128 + (kk & 7) * 16);
-        row = k0 + kk; col = mn0 + gidx * 8; row_end = k_end; col_end = mn_end;
-      }
-      if (row < row_end) {
-        const __nv_bfloat16* p = g + row * ld + col;
-        if (vec_ok && col + 7 < col_end) v[q] = __ldg(reinterpret_cast<const uint4*>(p));
-        else {
-          unsigned short t[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) t[j] = (col + j < col_end) ? __bfloat16_as_ushort(p[j]) : (unsigned short)0;
-          v[q] = make_uint4((uint32_t)t[0] | ((uint32_t)t[1] << 16), (uint32_t)t[2] | ((uint32_t)t[3] << 16),
-                            (uint32_t)t[4] | ((uint32_t)t[5] << 16), (uint32_t)t[6] | ((uint32_t)t[7] << 16));
-        }
-      }
+#pragma unroll 4
+  for (int it = 0; it < ITERS; ++it) {
+    const int u = ptid + it * WS_PROD_THREADS;
+    uint32_t off;
+    int64_t row, col, row_end, col_end;          // 8 consecutive elements [row][col .. col+7] of the global matrix
+    // MN-major operands: a warp copies 8 k-rows x 4 adjacent 16-byte chunks, so every 32-byte sector it touches in global
+    // memory is fully used (64 contiguous bytes per row) and every quarter-warp writes one whole 128-byte core matrix
+    const int r8 = u & 7, c4 = (u >> 3) & 3, rest = u >> 5;
+    if (KMAJOR) {        // measured: for K-major operands consecutive threads on consecutive rows is the faster mapping
+      const int r = u % R, c = u / R;
+      off = (uint32_t)((c * (R / 8) + (r >> 3)) * 128 + (r & 7) * 16);
+      row = mn0 + r; col = k0 + c * 8; row_end = mn_end; col_end = k_end;
+    } else {
+      const int gq = rest % (R / 32), kg = rest / (R / 32);
+      const int gidx = gq * 4 + c4, kk = kg * 8 + r8;
+      off = (uint32_t)((kg * (R / 8) + gidx) * 128 + r8 * 16);
+      row = k0 + kk; col = mn0 + gidx * 8; row_end = k_end; col_end = mn_end;
     }
+    const __nv_bfloat16* p = g + row * ld + col;
+    if (row < row_end && col < col_end && vec_ok) {
+      const int valid = (int)min((int64_t)8, col_end - col) * 2;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem + off)), "l"(p), "r"(valid) : "memory");
+    } else {
+      unsigned short t[8];
 #pragma unroll
-    for (int q = 0; q < UNR; ++q) *reinterpret_cast<uint4*>(smem + off[q]) = v[q];
+      for (int j = 0; j < 8; ++j) t[j] = (row < row_end && col + j < col_end) ? __bfloat16_as_ushort(p[j]) : (unsigned short)0;
+      *reinterpret_cast<uint4*>(smem + off) = make_uint4((uint32_t)t[0] | ((uint32_t)t[1] << 16), (uint32_t)t[2] | ((uint32_t)t[3] << 16),
+                                                         (uint32_t)t[4] | ((uint32_t)t[5] << 16), (uint32_t)t[6] | ((uint32_t)t[7] << 16));
+    }
   }
 }
 
@@ -355,7 +353,9 @@ gemm_tc_ws_kernel(int64_t M, int64_t N, int64_t K, const TIn* __restrict__ A, in
     constexpr int64_t VEC_LD = std::is_same<TIn, float>::value ? 3 : 7;         // 16-byte rows: ld % 4 (fp32) / % 8 (bf16)
     const bool a_vec = ((lda & VEC_LD) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     const bool b_vec = ((ldb & VEC_LD) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
-    uint32_t g = 0;                                       // ring position across all tiles of this CTA
+    constexpr bool ASYNC_STAGING = !std::is_same<TIn, float>::value;           // bf16 operands: cp.async straight into the ring
+    constexpr uint32_t LAG = STAGES - 1;
+    uint32_t g = 0, done = 0;                             // ring position across all tiles of this CTA; published stages
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t % tiles_n, mt = (t / tiles_n) % tiles_m, z = t / (tiles_n * tiles_m);
       const int64_t m0 = (int64_t)mt * TC_BM, n0 = (int64_t)nt * BN;
@@ -370,10 +370,31 @@ gemm_tc_ws_kernel(int64_t M, int64_t N, int64_t K, const TIn* __restrict__ A, in
         const int64_t k0 = kbeg + (int64_t)kt * TC_BK;
         stage_operand_ws<TC_BM, !TA, WS_PROD_WARPS * 32>(sa, A, lda, m0, M, k0, kend, a_vec, tid);
         stage_operand_ws<BN, TB, WS_PROD_WARPS * 32>(sb, B, ldb, n0, N, k0, kend, b_vec, tid);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+        if (ASYNC_STAGING) {
+          // stage g is in flight; publish stage g - LAG once this thread's (and, after the warp sync, this warp's) copies of
+          // it have landed.  LAG = STAGES - 1 keeps the whole ring in flight without ever waiting on a slot the MMA warp
+          // cannot free yet.
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          if (g + 1 - done > LAG) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(LAG) : "memory");
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&full_bar[done % STAGES]));
+            ++done;
+          }
+        } else {
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+        }
       }
+    }
+    if (ASYNC_STAGING) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fence_async_smem();
+      __syncwarp();
+      for (; done < g; ++done)
+        if (lane == 0) mbar_arrive(smem_u32(&full_bar[done % STAGES]));
     }
   } else if (warp == WS_PROD_WARPS + WS_EPI_WARPS) {
     // ------------------------------------------------ MMA issuer -----------------------------------------------
@@ -503,7 +524,7 @@ static int launch_tc_ws(int tA, int tB, int64_t M, int64_t N, int64_t K, const T
   const int64_t total = (int64_t)tiles_m * tiles_n * split_k;
   constexpr int STAGES = BN <= 128 ? 5 : (BN <= 192 ? 4 : 3);
   // deep-K: loads dominate -> 8 producer warps; else 8 epilogue warps
-  const bool deep_k = std::is_same<TIn, float>::value ? (k_chunk > 512) : (k_chunk >= 256);
+  const bool deep_k = k_chunk > 512;
   size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + (size_t)8 * 32 * 36 * 4;
   const int vec = epi_vec_ok(e, C, ldc, N) ? 1 : 0;
   const int grid = (int)std::min<int64_t>(total, (int64_t)num_sms());
