@@ -162,3 +162,24 @@ def test_data_parallel_recipe_reproduces_global_batch_gloo():
         p.join(timeout=180)
         assert p.exitcode == 0
     assert q.get(timeout=5) < 1e-4
+
+
+def test_shape_predicates_and_shard_layout_helpers():
+    """Host-side dispatch predicates of the fused tensor-core kernels and the row-shard index math (no GPU needed)."""
+    from b200ctr import ops
+    assert ops.ffn_fused_ok(384) and ops.ffn_fused_ok(256) and not ops.ffn_fused_ok(512) and not ops.ffn_fused_ok(100)
+    assert ops.fm_fused_ok(200, 96, 64) and not ops.fm_fused_ok(300, 96, 64) and not ops.fm_fused_ok(200, 100, 64)
+    assert ops.headproj_ok(6, 16, 192) and not ops.headproj_ok(6, 64, 192)
+    assert ops.bitmap_words(10_000_000) == 312_500 and ops.bitmap_words(33) == 2
+    # row r lives on rank r % N at local row r // N: the shards of a table partition its rows exactly once
+    V, N = 1003, 4
+    rows_local = (V + N - 1) // N
+    seen = np.zeros(V, dtype=np.int64)
+    for rank in range(N):
+        mine = np.arange(V)[rank::N]
+        assert mine.shape[0] <= rows_local
+        assert np.array_equal(mine // N, np.arange(mine.shape[0])) and np.all(mine % N == rank)
+        seen[mine] += 1
+    assert np.all(seen == 1)
+    with pytest.raises(Exception):
+        ops.ShardedTable([0, 0, 0], 10)          # 3 shards: not a power of two
