@@ -37,6 +37,12 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// exp(x) for x <= 0 (softmax numerators): one FMUL + one MUFU, flush-to-zero (no range fix-up code around the MUFU)
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -103,10 +109,14 @@ attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const int kc = 8 * j + 2 * t;
-      s[j][0] = kc < K ? s[j][0] + ba[kc] : -INFINITY;
-      s[j][1] = kc + 1 < K ? s[j][1] + ba[kc + 1] : -INFINITY;
-      s[j][2] = kc < K ? s[j][2] + bb[kc] : -INFINITY;
-      s[j][3] = kc + 1 < K ? s[j][3] + bb[kc + 1] : -INFINITY;
+      if (NT <= 10 && 8 * j + 8 <= K) {          // warp-uniform: whole tile valid, no per-score mask (small kernels only: code size)
+        s[j][0] += ba[kc]; s[j][1] += ba[kc + 1]; s[j][2] += bb[kc]; s[j][3] += bb[kc + 1];
+      } else {
+        s[j][0] = kc < K ? s[j][0] + ba[kc] : -INFINITY;
+        s[j][1] = kc + 1 < K ? s[j][1] + ba[kc + 1] : -INFINITY;
+        s[j][2] = kc < K ? s[j][2] + bb[kc] : -INFINITY;
+        s[j][3] = kc + 1 < K ? s[j][3] + bb[kc + 1] : -INFINITY;
+      }
       ma = fmaxf(ma, fmaxf(s[j][0], s[j][1]));
       mb = fmaxf(mb, fmaxf(s[j][2], s[j][3]));
     }
@@ -118,7 +128,7 @@ attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
     const uint32_t keyb = dctx.on ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qb) : 0u;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      float p0 = __expf(s[j][0] - ma), p1 = __expf(s[j][1] - ma), p2 = __expf(s[j][2] - mb), p3 = __expf(s[j][3] - mb);
+      float p0 = fast_exp(s[j][0] - ma), p1 = fast_exp(s[j][1] - ma), p2 = fast_exp(s[j][2] - mb), p3 = fast_exp(s[j][3] - mb);
       la += p0 + p1; lb += p2 + p3;
       if (dctx.on) {
         float c0, c1, c2, c3;
@@ -288,9 +298,15 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
           float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
           mma_tf32(s, aq, kb0, kb1);
           mma_tf32(dp, ad, vb0, vb1);
-          const bool v0 = kc < K, v1 = kc + 1 < K;
-          const float p0 = v0 ? __expf(s[0] + ba[kc] - La) : 0.f, p1 = v1 ? __expf(s[1] + ba[kc + 1] - La) : 0.f;
-          const float p2 = v0 ? __expf(s[2] + bb[kc] - Lb) : 0.f, p3 = v1 ? __expf(s[3] + bb[kc + 1] - Lb) : 0.f;
+          float p0, p1, p2, p3;
+          if (NT <= 10 && 8 * j + 8 <= K) {       // warp-uniform: whole tile valid (small kernels only: code size)
+            p0 = fast_exp(s[0] + ba[kc] - La); p1 = fast_exp(s[1] + ba[kc + 1] - La);
+            p2 = fast_exp(s[2] + bb[kc] - Lb); p3 = fast_exp(s[3] + bb[kc + 1] - Lb);
+          } else {
+            const bool v0 = kc < K, v1 = kc + 1 < K;
+            p0 = v0 ? fast_exp(s[0] + ba[kc] - La) : 0.f; p1 = v1 ? fast_exp(s[1] + ba[kc + 1] - La) : 0.f;
+            p2 = v0 ? fast_exp(s[2] + bb[kc] - Lb) : 0.f; p3 = v1 ? fast_exp(s[3] + bb[kc + 1] - Lb) : 0.f;
+          }
           float c0 = 1.f, c1 = 1.f, c2 = 1.f, c3 = 1.f;
           if (dctx.on) {
             drop_pair(dctx, keya, (uint32_t)(4 * j + t), c0, c1);
