@@ -109,7 +109,8 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
   float* b1s = reinterpret_cast<float*>(fds + 2 * FF_FD_BYTES);
   float* b2s = b1s + hidden;
   float* n2s = b2s + FF_D;
-  FfnBars* bars = reinterpret_cast<FfnBars*>(n2s + FF_D);
+  float* scr_all = n2s + FF_D;                                 // 4 final-epilogue warps x 32 x 68 floats (store transpose)
+  FfnBars* bars = reinterpret_cast<FfnBars*>(scr_all + 4 * 32 * 68);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t tiles = (T + FF_TM - 1) / FF_TM;
@@ -163,10 +164,12 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->h2_empty[hb]));
-      const int64_t m = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM + warp * 32 + lane;
+      const int64_t m_w = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM + warp * 32;
+      const int64_t m = m_w + lane;
+      const int rows_valid = (int)max((int64_t)0, min((int64_t)32, T - m_w));
+      float ss = 0.f;
       if (m < T) {
         const float4* xr = reinterpret_cast<const float4*>(x1 + m * FF_D);
-        float ss = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float4 xv = __ldg(xr + j);
@@ -178,20 +181,14 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
           v[4 * j] = __float_as_uint(s0); v[4 * j + 1] = __float_as_uint(s1);
           v[4 * j + 2] = __float_as_uint(s2); v[4 * j + 3] = __float_as_uint(s3);
         }
-        const float r = rsqrtf(ss * (1.f / FF_D) + eps);
-        if (r2_out) r2_out[m] = r;
-        if (s2_out) {
-          float4* sp = reinterpret_cast<float4*>(s2_out + m * FF_D);
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            sp[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        }
-        float4* yp = reinterpret_cast<float4*>(x2_out + m * FF_D);
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          yp[j] = make_float4(n2s[4 * j] * __uint_as_float(v[4 * j]) * r, n2s[4 * j + 1] * __uint_as_float(v[4 * j + 1]) * r,
-                              n2s[4 * j + 2] * __uint_as_float(v[4 * j + 2]) * r, n2s[4 * j + 3] * __uint_as_float(v[4 * j + 3]) * r);
       }
+      const float r = rsqrtf(ss * (1.f / FF_D) + eps);
+      if (r2_out && m < T) r2_out[m] = r;
+      float* scr = scr_all + warp * (32 * 68);
+      if (s2_out) warp_store_rows<64>(scr, v, s2_out + m_w * FF_D, FF_D, rows_valid, lane);
+#pragma unroll
+      for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(n2s[j] * __uint_as_float(v[j]) * r);
+      warp_store_rows<64>(scr, v, x2_out + m_w * FF_D, FF_D, rows_valid, lane);
     }
   } else if (warp < FFW_MMA_WARP) {
     // ---------------------------------------- GELU epilogue -----------------------------------------------------
@@ -601,7 +598,8 @@ ffn_bwd2_kernel(const unsigned char* __restrict__ dpre_spill, const float* __res
   const int NB = hidden / 128;
   unsigned char* w1s = smem;                                   // NB x 16 KB: MN-major B operand (N = d, K = hidden)
   unsigned char* ring = w1s + (size_t)NB * 16384;              // FF2_STAGES x 32 KB
-  Ffn2Bars* bars = reinterpret_cast<Ffn2Bars*>(ring + (size_t)FF2_STAGES * FF_BLK_BYTES);
+  float* scr_all = reinterpret_cast<float*>(ring + (size_t)FF2_STAGES * FF_BLK_BYTES);       // 4 epilogue warps x 32 x 68 floats
+  Ffn2Bars* bars = reinterpret_cast<Ffn2Bars*>(scr_all + 4 * 32 * 68);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t tiles = (T + FF_TM - 1) / FF_TM;
   const int n_it = (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
@@ -677,17 +675,19 @@ ffn_bwd2_kernel(const unsigned char* __restrict__ dpre_spill, const float* __res
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[ab]));
-      const int64_t m = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM + q * 32 + lane;
+      const int64_t m_w = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM + q * 32;
+      const int64_t m = m_w + lane;
+      const int rows_valid = (int)max((int64_t)0, min((int64_t)32, T - m_w));
       if (m < T) {
         const float4* rp = reinterpret_cast<const float4*>(ds2 + m * FF_D);
-        float4* op = reinterpret_cast<float4*>(dx1 + m * FF_D);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float4 a = __ldg(rp + j);
-          op[j] = make_float4(__uint_as_float(v[4 * j]) + a.x, __uint_as_float(v[4 * j + 1]) + a.y,
-                              __uint_as_float(v[4 * j + 2]) + a.z, __uint_as_float(v[4 * j + 3]) + a.w);
+          v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + a.x); v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + a.y);
+          v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + a.z); v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + a.w);
         }
       }
+      warp_store_rows<64>(scr_all + (warp - 2) * (32 * 68), v, dx1 + m_w * FF_D, FF_D, rows_valid, lane);
     }
   }
   tc_fence_before();
@@ -699,7 +699,8 @@ ffn_bwd2_kernel(const unsigned char* __restrict__ dpre_spill, const float* __res
 }
 
 static size_t ffn_fwd_smem(int hidden) {
-  return (size_t)2 * (hidden / FF_HC) * FF_WCHUNK + 2 * FF_A_BYTES + 2 * FF_FD_BYTES + ((size_t)hidden + 2 * FF_D) * 4 + sizeof(FfnBars) + 16;
+  return (size_t)2 * (hidden / FF_HC) * FF_WCHUNK + 2 * FF_A_BYTES + 2 * FF_FD_BYTES + ((size_t)hidden + 2 * FF_D) * 4 +
+         (size_t)4 * 32 * 68 * 4 + sizeof(FfnBars) + 16;
 }
 
 }  // namespace b200ctr
@@ -758,7 +759,7 @@ extern "C" int b200ctr_ffn_bwd(const float* dy, const float* s2, const float* r2
   const int n_out = 2 * hidden * FF_D + hidden + 2 * FF_D;
   ffn_bwd_reduce_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(ws, grid, hidden, dw1, db1, dw2, db2, dn2);
   B200_LAUNCH_CHECK("ffn_bwd_reduce_kernel");
-  const size_t smem2 = (size_t)NB * 16384 + (size_t)FF2_STAGES * FF_BLK_BYTES + sizeof(Ffn2Bars) + 16;
+  const size_t smem2 = (size_t)NB * 16384 + (size_t)FF2_STAGES * FF_BLK_BYTES + (size_t)4 * 32 * 68 * 4 + sizeof(Ffn2Bars) + 16;
   e = cudaFuncSetAttribute(ffn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ffn_bwd2 smem)");
   ffn_bwd2_kernel<<<grid, FF2_NT, smem2, st>>>(spill, w1, ds2, T, hidden, dx1);

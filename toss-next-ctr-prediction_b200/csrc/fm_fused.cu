@@ -197,7 +197,8 @@ fm_bwd_kernel(const __nv_bfloat16* __restrict__ z16, const float* __restrict__ U
   unsigned char* zs = us_k + FM_D * FM_CP * 2;                   // [2][32 KB]
   unsigned char* das = zs + 2 * FM_ZTILE;                        // dA tile: 2 blocks x [128 rows][128 cols] bf16 = 64 KB
   float* vecs = reinterpret_cast<float*>(das + 2 * 128 * FM_CP * 2);     // [2 parity][2][C]: s, 2*dquad
-  FmBwdBars* bars = reinterpret_cast<FmBwdBars*>(vecs + 2 * 2 * FM_CP);
+  float* scr_all = vecs + 2 * 2 * FM_CP;                                  // 8 epilogue warps x 32 x 36 floats (store transpose)
+  FmBwdBars* bars = reinterpret_cast<FmBwdBars*>(scr_all + 8 * 32 * 36);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nblk = (F + 127) >> 7;
   const int n_it = (int)((B - blockIdx.x + gridDim.x - 1) / gridDim.x);
@@ -282,23 +283,21 @@ fm_bwd_kernel(const __nv_bfloat16* __restrict__ z16, const float* __restrict__ U
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->dz_empty));
-      if (row_ok) {
-        const int64_t row = b * F + blk * 128 + r;
-        float4* op = reinterpret_cast<float4*>(dz + row * FM_D);
-        if (dz_resid) {
-          const float4* rp = reinterpret_cast<const float4*>(dz_resid + row * FM_D);
+      const int64_t row_w = b * F + blk * 128 + q * 32;                 // first row of this warp
+      const int rows_valid = max(0, min(32, F - (blk * 128 + q * 32)));
+      if (dz_resid && row_ok) {
+        const float4* rp = reinterpret_cast<const float4*>(dz_resid + (row_w + lane) * FM_D);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 a = rp[j];
-            op[j] = make_float4(__uint_as_float(w[4 * j]) + a.x, __uint_as_float(w[4 * j + 1]) + a.y,
-                                __uint_as_float(w[4 * j + 2]) + a.z, __uint_as_float(w[4 * j + 3]) + a.w);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            op[j] = make_float4(__uint_as_float(w[4 * j]), __uint_as_float(w[4 * j + 1]), __uint_as_float(w[4 * j + 2]), __uint_as_float(w[4 * j + 3]));
+        for (int j = 0; j < 16; ++j) {
+          const float4 a = rp[j];
+          w[4 * j] = __float_as_uint(__uint_as_float(w[4 * j]) + a.x); w[4 * j + 1] = __float_as_uint(__uint_as_float(w[4 * j + 1]) + a.y);
+          w[4 * j + 2] = __float_as_uint(__uint_as_float(w[4 * j + 2]) + a.z); w[4 * j + 3] = __float_as_uint(__uint_as_float(w[4 * j + 3]) + a.w);
         }
       }
+      __syncwarp();        // in-place use (dz == dz_resid): every lane has read its residual row before any row is overwritten
+      float* scr = scr_all + ew * (32 * 36);
+      warp_store_rows<32>(scr, w, dz + row_w * FM_D, FM_D, rows_valid, lane);
+      warp_store_rows<32>(scr, w + 32, dz + row_w * FM_D + 32, FM_D, rows_valid, lane);
     }
     // ---- dUcat^T accumulator (rows = c, 64 columns = d) -> this CTA's partial slab ----
     mbar_wait(smem_u32(&bars->done), 0);
@@ -403,7 +402,8 @@ extern "C" int b200ctr_fm_fused_bwd(const void* z_bf16, const float* Ucat, const
   B200_REQUIRE(fm_shape_ok(F, C, D), B200CTR_E_UNSUPPORTED_SHAPE, "fm_fused_bwd: F=%d C=%d D=%d unsupported", F, C, D);
   B200_REQUIRE(B > 0, B200CTR_E_INVALID_ARG, "fm_fused_bwd: empty batch");
   cudaStream_t st = as_stream(stream);
-  const size_t smem = (size_t)2 * FM_D * FM_CP * 2 + 2 * FM_ZTILE + (size_t)2 * 128 * FM_CP * 2 + (size_t)2 * 2 * FM_CP * 4 + sizeof(FmBwdBars) + 16;
+  const size_t smem = (size_t)2 * FM_D * FM_CP * 2 + 2 * FM_ZTILE + (size_t)2 * 128 * FM_CP * 2 + (size_t)2 * 2 * FM_CP * 4 +
+                      (size_t)8 * 32 * 36 * 4 + sizeof(FmBwdBars) + 16;
   cudaError_t e = cudaFuncSetAttribute(fm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fm_bwd smem)");
   const int grid = (int)std::min<int64_t>(B, (int64_t)num_sms());

@@ -66,7 +66,9 @@ lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
   unsigned char* as = ws + NOUT * 128;                          // [2][16 KB]
   float* bs = reinterpret_cast<float*>(as + 2 * PJ_X_BYTES);    // NOUT
   float* ns = bs + NOUT;                                        // 64
-  PjFwdBars* bars = reinterpret_cast<PjFwdBars*>(ns + PJ_D);
+  constexpr int SCR = 32 * ((POST_NORM ? 64 : 32) + 4);         // per-epilogue-warp transpose scratch (floats)
+  float* scr_all = ns + PJ_D;                                   // 8 warps x SCR
+  PjFwdBars* bars = reinterpret_cast<PjFwdBars*>(scr_all + 8 * SCR);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t tiles = (T + PJ_TM - 1) / PJ_TM;
   const int n_it = (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
@@ -110,7 +112,10 @@ lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
     for (int it = eg; it < n_it; it += 2) {
       mbar_wait(smem_u32(&bars->acc_full[eg]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const int64_t m = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * PJ_TM + q * 32 + lane;
+      const int64_t m_w = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * PJ_TM + q * 32;      // first row of this warp
+      const int64_t m = m_w + lane;
+      const int rows_valid = (int)max((int64_t)0, min((int64_t)32, T - m_w));
+      float* scr = scr_all + ew * SCR;
       const uint32_t taddr = tmem + eg * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
       if (POST_NORM) {
         uint32_t v[64];
@@ -119,9 +124,9 @@ lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[eg]));
+        float ss = 0.f;
         if (m < T) {
           const float4* xr = reinterpret_cast<const float4*>(resid + m * PJ_D);
-          float ss = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float4 xv = __ldg(xr + j);
@@ -130,20 +135,13 @@ lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
             ss = fmaf(s0, s0, ss); ss = fmaf(s1, s1, ss); ss = fmaf(s2, s2, ss); ss = fmaf(s3, s3, ss);
             v[4 * j] = __float_as_uint(s0); v[4 * j + 1] = __float_as_uint(s1); v[4 * j + 2] = __float_as_uint(s2); v[4 * j + 3] = __float_as_uint(s3);
           }
-          const float r = rsqrtf(ss * (1.f / PJ_D) + eps);
-          if (r_out) r_out[m] = r;
-          if (s_out) {
-            float4* sp = reinterpret_cast<float4*>(s_out + m * PJ_D);
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              sp[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          }
-          float4* yp = reinterpret_cast<float4*>(y + m * PJ_D);
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            yp[j] = make_float4(ns[4 * j] * __uint_as_float(v[4 * j]) * r, ns[4 * j + 1] * __uint_as_float(v[4 * j + 1]) * r,
-                                ns[4 * j + 2] * __uint_as_float(v[4 * j + 2]) * r, ns[4 * j + 3] * __uint_as_float(v[4 * j + 3]) * r);
         }
+        const float r = rsqrtf(ss * (1.f / PJ_D) + eps);
+        if (r_out && m < T) r_out[m] = r;
+        if (s_out) warp_store_rows<64>(scr, v, s_out + m_w * PJ_D, PJ_D, rows_valid, lane);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(ns[j] * __uint_as_float(v[j]) * r);
+        warp_store_rows<64>(scr, v, y + m_w * PJ_D, PJ_D, rows_valid, lane);
       } else {
 #pragma unroll 1
         for (int cc = 0; cc < NOUT / 32; ++cc) {
@@ -154,13 +152,9 @@ lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[eg]));
           }
-          if (m < T) {
-            float4* yp = reinterpret_cast<float4*>(y + m * NOUT + cc * 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              yp[j] = make_float4(__uint_as_float(v[4 * j]) + bs[cc * 32 + 4 * j], __uint_as_float(v[4 * j + 1]) + bs[cc * 32 + 4 * j + 1],
-                                  __uint_as_float(v[4 * j + 2]) + bs[cc * 32 + 4 * j + 2], __uint_as_float(v[4 * j + 3]) + bs[cc * 32 + 4 * j + 3]);
-          }
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + bs[cc * 32 + j]);
+          warp_store_rows<32>(scr, v, y + m_w * NOUT + cc * 32, NOUT, rows_valid, lane);
         }
       }
     }
@@ -216,7 +210,11 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
   unsigned char* wsm = smem;                                    // W as MN-major B operand (N = d_in, K = NOUT)
   unsigned char* ins = wsm + NOUT * 128;                        // [2][x 16 KB | ones 4 KB | dY]
   float* red = reinterpret_cast<float*>(ins + 2 * IN_BYTES);    // 8 warps x 64 (dn partials)
-  PjBwdBars* bars = reinterpret_cast<PjBwdBars*>(red + 8 * PJ_D);
+  // store-transpose scratch of the 4 epilogue warps (64-wide kernel only: at NOUT = 192 the extra 18 KB would push the
+  // shared-memory carve-out to 228 KB and the 28 KB of L1 left no longer hold the loader's row lines -- measured slower)
+  constexpr int SCR_FLOATS = NOUT <= 64 ? 4 * 32 * 36 : 0;
+  float* scr_all = red + 8 * PJ_D;
+  PjBwdBars* bars = reinterpret_cast<PjBwdBars*>(scr_all + SCR_FLOATS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t tiles = (T + PJ_TM - 1) / PJ_TM;
   const int n_it = (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
@@ -338,22 +336,27 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->dx_empty[ib]));
-      const int64_t m = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * PJ_TM + q * 32 + lane;
-      if (m < T) {
-        float4* op = reinterpret_cast<float4*>(dx + m * PJ_D);
-        if (resid) {
-          const float4* rp = reinterpret_cast<const float4*>(resid + m * PJ_D);
+      const int64_t m_w = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * PJ_TM + q * 32;
+      const int64_t m = m_w + lane;
+      const int rows_valid = (int)max((int64_t)0, min((int64_t)32, T - m_w));
+      if (resid && m < T) {
+        const float4* rp = reinterpret_cast<const float4*>(resid + m * PJ_D);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 a = __ldg(rp + j);
-            op[j] = make_float4(__uint_as_float(v[4 * j]) + a.x, __uint_as_float(v[4 * j + 1]) + a.y,
-                                __uint_as_float(v[4 * j + 2]) + a.z, __uint_as_float(v[4 * j + 3]) + a.w);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            op[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        for (int j = 0; j < 16; ++j) {
+          const float4 a = __ldg(rp + j);
+          v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + a.x); v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + a.y);
+          v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + a.z); v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + a.w);
         }
+      }
+      if (NOUT <= 64) {          // measured: the transposed store pays off for the 64-wide kernel, not for the 192-wide one
+        float* scr = scr_all + (warp - 8) * (32 * 36);
+        warp_store_rows<32>(scr, v, dx + m_w * PJ_D, PJ_D, rows_valid, lane);
+        warp_store_rows<32>(scr, v + 32, dx + m_w * PJ_D + 32, PJ_D, rows_valid, lane);
+      } else if (m < T) {
+        float4* op = reinterpret_cast<float4*>(dx + m * PJ_D);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          op[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
       }
     }
     mbar_wait(smem_u32(&bars->done), 0);
@@ -430,7 +433,8 @@ __global__ void lin_bwd_reduce_kernel(const float* __restrict__ wsp, int n_cta, 
 template <int NOUT, bool POST_NORM>
 static int launch_lin_fwd(const float* x, const float* w, const float* bias, const float* resid, const float* nw, float eps,
                           int64_t T, float* y, float* s_out, float* r_out, cudaStream_t st) {
-  const size_t smem = (size_t)NOUT * 128 + 2 * PJ_X_BYTES + ((size_t)NOUT + PJ_D) * 4 + sizeof(PjFwdBars) + 16;
+  const size_t smem = (size_t)NOUT * 128 + 2 * PJ_X_BYTES + ((size_t)NOUT + PJ_D) * 4 +
+                      (size_t)8 * 32 * ((POST_NORM ? 64 : 32) + 4) * 4 + sizeof(PjFwdBars) + 16;
   auto fn = lin_fwd_kernel<NOUT, POST_NORM>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(lin_fwd smem)");
@@ -444,7 +448,8 @@ static int launch_lin_bwd(const float* gin, const float* s, const float* r, cons
                           const float* resid, int64_t T, float* dy_out, float* dx, float* dw, float* db, float* dn, float* wsp,
                           cudaStream_t st) {
   constexpr int NP = NOUT <= 128 ? 128 : 256;
-  const size_t smem = (size_t)NOUT * 128 + 2 * (size_t)(PJ_X_BYTES + PJ_ONES_BYTES + PJ_TM * NP * 2) + 8 * PJ_D * 4 + sizeof(PjBwdBars) + 16;
+  const size_t smem = (size_t)NOUT * 128 + 2 * (size_t)(PJ_X_BYTES + PJ_ONES_BYTES + PJ_TM * NP * 2) + 8 * PJ_D * 4 + (size_t)(NOUT <= 64 ? 4 * 32 * 36 * 4 : 0) +
+                      sizeof(PjBwdBars) + 16;
   auto fn = lin_bwd_kernel<NOUT, PRE_NORM>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(lin_bwd smem)");

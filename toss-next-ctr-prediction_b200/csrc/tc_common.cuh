@@ -91,4 +91,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+
+// Row-per-lane epilogues hold one output row per thread; storing it directly makes every STG.128 of a warp hit 32
+// different rows (32 half-used sectors per instruction).  warp_store_rows transposes a 32-row x NC-column fp32 block
+// through a warp-private shared-memory scratch (32 x (NC+4) floats, conflict-free both ways) so that the global stores
+// cover whole rows: NC/4 lanes x 16 bytes contiguous.  v = this lane's NC values; rows_valid = rows of the block to write.
+template <int NC>
+__device__ __forceinline__ void warp_store_rows(float* scratch, const uint32_t* v, float* gbase, int64_t ld, int rows_valid, int lane) {
+  constexpr int SR = NC + 4, LPR = NC / 4, RPI = 32 / LPR;
+#pragma unroll
+  for (int j = 0; j < NC / 4; ++j)
+    *reinterpret_cast<uint4*>(scratch + lane * SR + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int rsub = lane / LPR, c = lane % LPR;
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += RPI) {
+    const int row = r0 + rsub;
+    if (row < rows_valid)
+      *reinterpret_cast<uint4*>(gbase + (int64_t)row * ld + c * 4) = *reinterpret_cast<const uint4*>(scratch + row * SR + c * 4);
+  }
+  __syncwarp();
+}
+
 }  // namespace b200ctr
