@@ -111,6 +111,14 @@ int b200ctr_gemm_bf16in(int transA, int transB, int64_t M, int64_t N, int64_t K,
                         const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc,
                         const b200ctr_epilogue_t* epi_host, int split_k, void* workspace, void* stream);
 int b200ctr_to_bf16(const float* x, int64_t n, void* out_bf16, void* stream);
+/* Deep-K contraction fed by TMA: C (M,N) fp32 = A (M,K) . B (N,K)^T with BOTH operands bf16 and K contiguous
+ * (cp.async.bulk.tensor 128-byte-swizzled tiles -> tcgen05.mma, persistent, double-buffered TMEM accumulators).
+ * N % 32 == 0; K, lda, ldb % 8 == 0; 16-byte aligned bases.  Helpers to put operands into that form:
+ * to_bf16_transposed: fp32 (R,C) row stride ld_in -> bf16 (C,R) contiguous;  transpose_bf16: bf16 (R,C) -> bf16 (C,R).   */
+int b200ctr_gemm_bf16_kk(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                         int64_t N, int64_t K, void* stream);
+int b200ctr_to_bf16_transposed(const float* in, int64_t R, int64_t C, int64_t ld_in, void* out_bf16, void* stream);
+int b200ctr_transpose_bf16(const void* in_bf16, int64_t R, int64_t C, void* out_bf16, void* stream);
 int b200ctr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* workspace, void* stream);
 
 /* ---- numeric / binary feature embedding  (feature_embed.py:19-27, 42-48) ------------------------------

@@ -459,3 +459,21 @@ def test_fm_fused_matches_unfused(dev, B, F, C):
     # (1 bf16 ulp of a |dA| ~ 100 element), hence 3e-3 rather than accumulation-order tolerance
     assert max_err_scaled(dz.view(B * F, 64).cpu(), dz_ref.cpu()) < 3e-3
     assert max_err_scaled(dU.cpu(), dU_ref.cpu()) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 1280), (8192, 512, 1024), (512, 1280, 4096), (300, 96, 264), (128, 32, 256)])
+def test_gemm_tma_kmajor(dev, M, N, K):
+    """TMA-fed tcgen05 contraction (both operands bf16, K contiguous) incl. ragged M / N / K tiles and strided views."""
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    a, b = _rand(g, M, K).to(dev), _rand(g, N, K + 64).to(dev)
+    a16, b16 = ops.to_bf16(a), ops.to_bf16(b)[:, 32:32 + K]            # row-strided bf16 view (like W0[:, :N])
+    ref = _bf(a).double() @ _bf(b)[:, 32:32 + K].double().t()
+    out = ops.gemm_kk(a16, b16)
+    assert max_err_scaled(out.cpu(), ref.cpu()) < 1e-5
+    # the transposing staging helpers
+    t1 = ops.to_bf16_t(b[:, 32:32 + K])
+    assert torch.equal(t1.float().cpu(), _bf(b)[:, 32:32 + K].t().contiguous().cpu())
+    if M % 2 == 0 and K % 2 == 0:
+        t2 = ops.transpose_bf16(a16)
+        assert torch.equal(t2.cpu(), a16.t().contiguous().cpu())

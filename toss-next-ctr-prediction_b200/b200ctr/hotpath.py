@@ -294,11 +294,13 @@ def qnn_fwd(P: Dict[str, Tensor], spec: ModelSpec, xF: Tensor, dc: DropCtl, B_to
     if bf16_ops and W0.shape[1] % 8 == 0 and W0.is_contiguous():
         W0_16 = ops.to_bf16(W0)
     zin, W0z = (z16, W0_16[:, :N]) if W0_16 is not None else (z, W0[:, :N])
+    # the deep (K = F*D) contraction: TMA-fed tcgen05 kernel when both operands are bf16 with K contiguous
+    use_kk = W0_16 is not None and ops.gemm_kk_ok(B, W0.shape[0], N)
     if len(mlp) == 1:
-        hcur = ops.gemm(zin, W0z, trans_b=True)
+        hcur = ops.gemm_kk(zin, W0z) if use_kk else ops.gemm(zin, W0z, trans_b=True)
         logit = ops.gemm(igd, W0[:, N:], trans_b=True, accum=hcur, bias=P[f"qnn.mlp.{mlp[0]}.bias"])
     else:
-        hcur = ops.gemm(zin, W0z, trans_b=True)
+        hcur = ops.gemm_kk(zin, W0z) if use_kk else ops.gemm(zin, W0z, trans_b=True)
         hcur = ops.gemm(igd, W0[:, N:], trans_b=True, accum=hcur, bias=P[f"qnn.mlp.{mlp[0]}.bias"], act=ops.ACT_RELU,
                         dropout=dc(spec.p_qnn, SITE_MLP0), out=hcur)
         acts.append(hcur)
@@ -340,7 +342,12 @@ def qnn_bwd(P, spec: ModelSpec, sv: dict, dlogit: Tensor, dc: DropCtl, G: Callab
     gW0 = G(f"qnn.mlp.{mlp[0]}.weight")
     z16, W0_16 = sv.get("z16"), sv.get("W0_16")
     dh16 = ops.to_bf16(dh) if (z16 is not None and dh.is_contiguous() and dh.shape[1] % 8 == 0) else None
-    if dh16 is not None:
+    H0 = W0.shape[0]
+    use_kk = dh16 is not None and ops.gemm_kk_ok(H0, N, B) and ops.gemm_kk_ok(B, N, H0) and B % 2 == 0 and N % 2 == 0
+    if use_kk:
+        # K-major forms for the TMA kernel: dW0z = dh^T . z as (dh^T)(z^T)^T, dz = dh . W0z as dh (W0z^T)^T
+        ops.gemm_kk(ops.to_bf16_t(dh), ops.transpose_bf16(z16), out=gW0[:, :N])
+    elif dh16 is not None:
         ops.gemm(dh16, z16, trans_a=True, out=gW0[:, :N])
     else:
         ops.gemm(dh, z, trans_a=True, out=gW0[:, :N])
@@ -372,7 +379,10 @@ def qnn_bwd(P, spec: ModelSpec, sv: dict, dlogit: Tensor, dc: DropCtl, G: Callab
             ops.gemm(dinter[:, h * Pd:(h + 1) * Pd], V[h], trans_b=True, out=dquad[:, h * r:(h + 1) * r])
     dz_mlp = None
     if spec.use_residual:
-        dz_mlp = ops.gemm(dh16, W0_16[:, :N]) if dh16 is not None else ops.gemm(dh, W0[:, :N])  # (B, N)
+        if use_kk:
+            dz_mlp = ops.gemm_kk(dh16, ops.to_bf16_t(W0[:, :N]))                               # (B, N)
+        else:
+            dz_mlp = ops.gemm(dh16, W0_16[:, :N]) if dh16 is not None else ops.gemm(dh, W0[:, :N])
     if sv.get("z16_fm") is not None:
         # recompute z.Ucat in TMEM, dA as a bf16 operand tile, dz (+ the MLP branch) and dUcat in one kernel
         dz, dUcat = ops.fm_fused_bwd(sv["z16_fm"], sv["Ucat"], sv["s"], dquad, dz_mlp, B, F, dz_out=dz_mlp)

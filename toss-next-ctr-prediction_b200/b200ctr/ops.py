@@ -173,6 +173,48 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, out:
     return out
 
 
+def gemm_kk(a16: torch.Tensor, b16: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out (M,N) fp32 = a16 (M,K) @ b16 (N,K)^T, both bf16 with unit inner stride (row-strided views allowed): TMA-fed tcgen05."""
+    lib = _lib.load()
+    assert a16.dtype == torch.bfloat16 and b16.dtype == torch.bfloat16
+    M, K = a16.shape
+    N, Kb = b16.shape
+    assert K == Kb
+    if out is None:
+        out = torch.empty((M, N), device=a16.device, dtype=torch.float32)
+    assert out.shape == (M, N)
+    global _TAG
+    if _PROF is not None:
+        _TAG = f"[{M}x{N}x{K}NT]"
+    _run("gemm_tma", lib.b200ctr_gemm_bf16_kk, _p(a16), _ld(a16), _p(b16), _ld(b16), _p(out), _ld(out), M, N, K, _stream())
+    _count()
+    return out
+
+
+def gemm_kk_ok(M: int, N: int, K: int) -> bool:
+    return N % 32 == 0 and K % 8 == 0 and M >= 128 and K >= 256
+
+
+def to_bf16_t(x: torch.Tensor) -> torch.Tensor:
+    """bf16 transpose (C, R) of a row-strided fp32 (R, C) view."""
+    lib = _lib.load()
+    R, C = x.shape
+    out = torch.empty((C, R), device=x.device, dtype=torch.bfloat16)
+    _run("to_bf16_t", lib.b200ctr_to_bf16_transposed, _p(_f32(x)), R, C, _ld(x), _p(out), _stream())
+    _count()
+    return out
+
+
+def transpose_bf16(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    R, C = x.shape
+    out = torch.empty((C, R), device=x.device, dtype=torch.bfloat16)
+    _run("transpose_bf16", lib.b200ctr_transpose_bf16, _p(x), R, C, _p(out), _stream())
+    _count()
+    return out
+
+
 def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     M, N = x.shape
