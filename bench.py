@@ -306,7 +306,7 @@ def run_cuda(args):
             ell = (seq != 0).sum(1).double()
             kv = torch.clamp(ell, max=Kk)
             gbytes += float((8 * L + 4 * D * ell + 4 * D * kv + 4 * D + 4 * D * Kk + 12 * Kk).sum())
-        gemm_flops = {"gemm": 0.0, "gemm_bf16": 0.0}
+        gemm_flops = {"gemm": 0.0, "gemm_bf16": 0.0, "gemm_tma": 0.0}
         for tag, (n, t) in prof.items():
             for fn_ in gemm_flops:
                 if tag.startswith(fn_ + "["):
@@ -332,10 +332,13 @@ def run_cuda(args):
 
         def roof_of(name):
             n, t = fam[name]
-            if name in ("gemm", "gemm_bf16"):
+            if name in ("gemm", "gemm_bf16", "gemm_tma"):
                 ach = gemm_flops[name] / (t * 1e-3) / 1e12
-                desc = ("gemm_tc_kernel / gemm_tc_ws_kernel (tcgen05.mma kind::f16, fp32 TMEM accumulators); every remaining dense "
-                        "projection of the step" if name == "gemm_bf16" else "gemm_kernel (fp32 CUDA-core contraction)")
+                desc = {"gemm_bf16": "gemm_tc_kernel / gemm_tc_ws_kernel (tcgen05.mma kind::f16, fp32 TMEM accumulators); the remaining "
+                                     "small dense projections of the step",
+                        "gemm_tma": "gemm_tma_kernel (cp.async.bulk.tensor SWIZZLE_128B ring -> tcgen05.mma, double-buffered TMEM): the "
+                                    "deep-K first QNN MLP layer, forward and both backward products",
+                        "gemm": "gemm_kernel (fp32 CUDA-core contraction)"}[name]
                 return {"kernel": desc, "bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
                         "traffic": None, "peak_source": f"{pk['src']} bf16 sustained", "launches": n, "avg_launch_ms": t / n,
                         "share_of_step": t / tot_ms}
@@ -353,12 +356,12 @@ def run_cuda(args):
                     "frac_of_nominal_8TBs": ach / 8000.0, "traffic": tr, "peak_source": f"{pk['src']} HBM copy", "launches": n,
                     "avg_launch_ms": t / n, "share_of_step": t / tot_ms}
 
-        modelled = [k for k, _ in top if k in models or k in ("gemm", "gemm_bf16")]
+        modelled = [k for k, _ in top if k in models or k in ("gemm", "gemm_bf16", "gemm_tma")]
         roof = roof_of(modelled[0]) if modelled else None
         if roof is not None and modelled[0].startswith("attn_tc"):
             roof["note"] = ("issue-bound on the exp / dropout-hash work per score (ncu: SM throughput 51-73 %, tensor pipe 6-9 %), "
                             "not on the tensor pipe: head_dim 8 gives 2 MMAs per 128 scores")
-        kernels = [dict(roof_of(k), family=k) for k in modelled[:10]]
+        kernels = [dict(roof_of(k), family=k) for k in modelled[:14]]
         gather = roof_of("retrieve_fwd") if "retrieve_fwd" in fam else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),

@@ -344,16 +344,22 @@ def qnn_bwd(P, spec: ModelSpec, sv: dict, dlogit: Tensor, dc: DropCtl, G: Callab
     dh16 = ops.to_bf16(dh) if (z16 is not None and dh.is_contiguous() and dh.shape[1] % 8 == 0) else None
     H0 = W0.shape[0]
     use_kk = dh16 is not None and ops.gemm_kk_ok(H0, N, B) and ops.gemm_kk_ok(B, N, H0) and B % 2 == 0 and N % 2 == 0
+    HPc = W0.shape[1] - N
+    kk_inter = use_kk and ops.gemm_kk_ok(H0, HPc, B) and ops.gemm_kk_ok(B, HPc, H0)
     if use_kk:
         # K-major forms for the TMA kernel: dW0z = dh^T . z as (dh^T)(z^T)^T, dz = dh . W0z as dh (W0z^T)^T
-        ops.gemm_kk(ops.to_bf16_t(dh), ops.transpose_bf16(z16), out=gW0[:, :N])
+        dh16t = ops.to_bf16_t(dh)
+        ops.gemm_kk(dh16t, ops.transpose_bf16(z16), out=gW0[:, :N])
     elif dh16 is not None:
         ops.gemm(dh16, z16, trans_a=True, out=gW0[:, :N])
     else:
         ops.gemm(dh, z, trans_a=True, out=gW0[:, :N])
-    ops.gemm(dh, igd, trans_a=True, out=gW0[:, N:])
+    if kk_inter:
+        ops.gemm_kk(dh16t, ops.to_bf16_t(igd), out=gW0[:, N:])
+    else:
+        ops.gemm(dh, igd, trans_a=True, out=gW0[:, N:])
     ops.colsum(dh, out=G(f"qnn.mlp.{mlp[0]}.bias"))
-    digd = ops.gemm(dh, W0[:, N:])
+    digd = ops.gemm_kk(dh16, ops.to_bf16_t(W0[:, N:])) if kk_inter else ops.gemm(dh, W0[:, N:])
     inter = sv["inter"]
     dcq = dc(spec.p_qnn, SITE_QNN_INTER)
     if spec.use_se:
