@@ -710,7 +710,7 @@ def headproj_ok(H: int, R: int, P: int) -> bool:
     C = H * R
     if R > 32 or H * P > 1536 or C > 384 or C <= 0:
         return False
-    return (C * (P + 1) + H * P + 5 * C) * 4 <= 200 * 1024
+    return (C * (P + 1) + 4 * (H * P + C) + 4 * C) * 4 <= 200 * 1024
 
 
 def headproj_fwd(quad, V):

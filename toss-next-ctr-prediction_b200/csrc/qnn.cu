@@ -38,8 +38,9 @@ rowrms_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
   if (threadIdx.x == 0) r[b] = rr;
 }
 
-// grid = n_partials CTAs; CTA p handles rows p, p+P, ...; per-thread register accumulators for dw.
-__global__ void __launch_bounds__(RR_THREADS)
+// grid = n_partials CTAs; CTA p handles rows p, p+P, ...; per-thread register accumulators for dw.  The row's dz and x
+// stay in registers between the dot-product pass and the output pass (one HBM read of each, 25 loads in flight per lane).
+__global__ void __launch_bounds__(RR_THREADS, 1)
 rowrms_bwd_kernel(const float* __restrict__ dz, int64_t ld_dz, const float* __restrict__ x, int64_t ldx,
                   const float* __restrict__ w, const float* __restrict__ r, int64_t B, int64_t N, float* __restrict__ dx,
                   int64_t ld_dx, float* __restrict__ dw_partial) {
@@ -54,22 +55,29 @@ rowrms_bwd_kernel(const float* __restrict__ dz, int64_t ld_dz, const float* __re
     const float4* xr = reinterpret_cast<const float4*>(x + b * ldx);
     float4* dxr = reinterpret_cast<float4*>(dx + b * ld_dx);
     const float rr = r[b];
+    float4 dreg[RR_MAXV], xreg[RR_MAXV];
+#pragma unroll
+    for (int s = 0; s < RR_MAXV; ++s) {
+      const int i = threadIdx.x + s * RR_THREADS;
+      dreg[s] = make_float4(0.f, 0.f, 0.f, 0.f); xreg[s] = dreg[s];
+      if (i < n4) { dreg[s] = dzr[i]; xreg[s] = xr[i]; }
+    }
     float dot = 0.f;
 #pragma unroll
     for (int s = 0; s < RR_MAXV; ++s) {
-      int i = threadIdx.x + s * RR_THREADS;
+      const int i = threadIdx.x + s * RR_THREADS;
       if (i < n4) {
-        float4 d = dzr[i], v = xr[i], ww = __ldg(w4 + i);
-        dot += d.x * ww.x * v.x + d.y * ww.y * v.y + d.z * ww.z * v.z + d.w * ww.w * v.w;
+        const float4 ww = __ldg(w4 + i);
+        dot += dreg[s].x * ww.x * xreg[s].x + dreg[s].y * ww.y * xreg[s].y + dreg[s].z * ww.z * xreg[s].z + dreg[s].w * ww.w * xreg[s].w;
       }
     }
     dot = block_sum(dot, red) / (float)N;
     const float c = rr * rr * rr * dot;
 #pragma unroll
     for (int s = 0; s < RR_MAXV; ++s) {
-      int i = threadIdx.x + s * RR_THREADS;
+      const int i = threadIdx.x + s * RR_THREADS;
       if (i < n4) {
-        float4 d = dzr[i], v = xr[i], ww = __ldg(w4 + i);
+        const float4 d = dreg[s], v = xreg[s], ww = __ldg(w4 + i);   // w (51 KB, shared by every row) is an L1/L2 hit
         dxr[i] = make_float4(rr * d.x * ww.x - v.x * c, rr * d.y * ww.y - v.y * c, rr * d.z * ww.z - v.z * c, rr * d.w * ww.w - v.w * c);
         acc[s].x = fmaf(d.x * v.x, rr, acc[s].x); acc[s].y = fmaf(d.y * v.y, rr, acc[s].y);
         acc[s].z = fmaf(d.z * v.z, rr, acc[s].z); acc[s].w = fmaf(d.w * v.w, rr, acc[s].w);
@@ -234,6 +242,8 @@ headproj_fwd_kernel(const float* __restrict__ quad, const float* __restrict__ V,
 }
 
 // dquad[b, h*R + r] = sum_p dinter[b, h*P + p] * V[h][r][p] ;  dV partial[cta][h][r][p] = sum_{b in cta} quad * dinter
+// HP_RB batch rows per iteration share the two block barriers and the V reads.
+constexpr int HP_RB = 4;
 template <int RMAX>
 __global__ void __launch_bounds__(HP_THREADS)
 headproj_bwd_kernel(const float* __restrict__ quad, const float* __restrict__ dinter, const float* __restrict__ V, int64_t B,
@@ -241,8 +251,8 @@ headproj_bwd_kernel(const float* __restrict__ quad, const float* __restrict__ di
   extern __shared__ float hp_sm[];
   const int C = H * R, HPd = H * P, PS = P + 1;
   float* Vs = hp_sm;                    // C x (P+1)
-  float* ds = Vs + C * PS;              // H*P : dinter row
-  float* qs = ds + HPd;                 // C   : quad row
+  float* ds = Vs + C * PS;              // HP_RB x H*P : dinter rows
+  float* qs = ds + HP_RB * HPd;         // HP_RB x C   : quad rows
   for (int i = threadIdx.x; i < C * P; i += HP_THREADS) Vs[(i / P) * PS + i % P] = V[i];
   float acc[HP_MAXC][RMAX];
 #pragma unroll
@@ -251,29 +261,48 @@ headproj_bwd_kernel(const float* __restrict__ quad, const float* __restrict__ di
     for (int r = 0; r < RMAX; ++r) acc[k][r] = 0.f;
   int parts = 1;                        // threads cooperating on one dquad element: largest power of two <= min(32, threads/C)
   while (parts * 2 <= 32 && parts * 2 * C <= HP_THREADS) parts *= 2;
-  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+  for (int64_t b0 = (int64_t)blockIdx.x * HP_RB; b0 < B; b0 += (int64_t)gridDim.x * HP_RB) {
     __syncthreads();
-    for (int i = threadIdx.x; i < HPd; i += HP_THREADS) ds[i] = dinter[b * HPd + i];
-    for (int i = threadIdx.x; i < C; i += HP_THREADS) qs[i] = quad[b * C + i];
+    for (int i = threadIdx.x; i < HP_RB * HPd; i += HP_THREADS) {
+      const int64_t b = b0 + i / HPd;
+      ds[i] = b < B ? dinter[b * HPd + i % HPd] : 0.f;
+    }
+    for (int i = threadIdx.x; i < HP_RB * C; i += HP_THREADS) {
+      const int64_t b = b0 + i / C;
+      qs[i] = b < B ? quad[b * C + i % C] : 0.f;
+    }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < HP_MAXC; ++k) {
       const int c = threadIdx.x + k * HP_THREADS;
       if (c < HPd) {
         const int h = c / P;
-        const float d = ds[c];
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r)
-          if (r < R) acc[k][r] = fmaf(qs[h * R + r], d, acc[k][r]);
+        for (int rb = 0; rb < HP_RB; ++rb) {
+          const float d = ds[rb * HPd + c];
+#pragma unroll
+          for (int r = 0; r < RMAX; ++r)
+            if (r < R) acc[k][r] = fmaf(qs[rb * C + h * R + r], d, acc[k][r]);
+        }
       }
     }
     if (threadIdx.x < C * parts) {
       const int cc = threadIdx.x / parts, part = threadIdx.x % parts, h = cc / R;
       const int span = (P + parts - 1) / parts, p0 = part * span, p1 = min(P, p0 + span);
-      float a = 0.f;
-      for (int pp = p0; pp < p1; ++pp) a = fmaf(ds[h * P + pp], Vs[cc * PS + pp], a);
-      for (int o = parts >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (part == 0) dquad[b * C + cc] = a;
+      float a[HP_RB];
+#pragma unroll
+      for (int rb = 0; rb < HP_RB; ++rb) a[rb] = 0.f;
+      for (int pp = p0; pp < p1; ++pp) {
+        const float v = Vs[cc * PS + pp];
+#pragma unroll
+        for (int rb = 0; rb < HP_RB; ++rb) a[rb] = fmaf(ds[rb * HPd + h * P + pp], v, a[rb]);
+      }
+#pragma unroll
+      for (int rb = 0; rb < HP_RB; ++rb) {
+        float t = a[rb];
+        for (int o = parts >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (part == 0 && b0 + rb < B) dquad[(b0 + rb) * C + cc] = t;
+      }
     }
   }
   float* out = dv_partial + (int64_t)blockIdx.x * C * P;
@@ -387,7 +416,7 @@ extern "C" int b200ctr_se_apply_bwd(const float* dout, int64_t ld_dout, const fl
 static bool headproj_ok(int H, int R, int P) {
   const int C = H * R;
   if (H <= 0 || R <= 0 || P <= 0 || R > 32 || H * P > HP_MAXC * HP_THREADS || C > HP_THREADS) return false;
-  return ((size_t)C * (P + 1) + (size_t)H * P + 5 * C) * 4 <= 200 * 1024;
+  return ((size_t)C * (P + 1) + (size_t)HP_RB * (H * P + C) + 4 * C) * 4 <= 200 * 1024;
 }
 
 extern "C" int b200ctr_headproj_fwd(const float* quad, const float* V, int64_t B, int H, int R, int P, float* inter, void* stream) {
@@ -411,8 +440,8 @@ extern "C" int b200ctr_headproj_bwd(const float* quad, const float* dinter, cons
   B200_REQUIRE(headproj_ok(H, R, P), B200CTR_E_UNSUPPORTED_SHAPE, "headproj_bwd: heads=%d rank=%d proj=%d unsupported", H, R, P);
   B200_REQUIRE(B > 0, B200CTR_E_INVALID_ARG, "headproj_bwd: empty batch");
   const int C = H * R;
-  const size_t smem = ((size_t)C * (P + 1) + (size_t)H * P + C) * 4;
-  const int grid = (int)std::min<int64_t>(B, (int64_t)num_sms());
+  const size_t smem = ((size_t)C * (P + 1) + (size_t)HP_RB * (H * P + C)) * 4;
+  const int grid = (int)std::min<int64_t>(ceil_div(B, (int64_t)HP_RB), (int64_t)num_sms());
   cudaStream_t st = as_stream(stream);
 #define HP_LAUNCH(RM)                                                                                              \
   do {                                                                                                             \
