@@ -394,7 +394,7 @@ extern "C" int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* co
   B200_REQUIRE(x_cat && tables && projs && dims && cards && dtables && dprojs, B200CTR_E_INVALID_ARG, "cat_bwd: null pointer");
   B200_REQUIRE(D == CAT_D, B200CTR_E_UNSUPPORTED_SHAPE, "cat_bwd: emb_dim=%d unsupported (kernel is specialised for 64)", D);
   if (B == 0 || Fc == 0) return B200CTR_OK;
-  dim3 grid((unsigned)std::min<int64_t>(ceil_div(B, (int64_t)CATB_TS), 16), (unsigned)Fc);
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(B, (int64_t)CATB_TS), 64), (unsigned)Fc);     // wide columns (d_c up to 64) set the tail: many short CTAs
   cudaStream_t st = as_stream(stream);
   if (idx_is_64)
     cat_bwd_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)x_cat, tables, projs, dims, cards, dout, ld_b, dmean,

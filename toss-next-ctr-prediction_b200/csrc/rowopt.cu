@@ -195,11 +195,13 @@ __device__ __forceinline__ uint32_t own_mask(int n_shards, int rank) {
   return m;
 }
 
-// calls f(local_row) with the whole warp converged for every owned row whose bit is set in any of the n_maps bitmaps
+// Calls f(local_row, hl) for every owned row whose bit is set in any of the n_maps bitmaps.  Each HALF-warp gets its own
+// row (hl = lane within the half-warp, 16 lanes x float4 = one 256-byte row), so a warp keeps two rows' dependent
+// load chains (state -> p/m/v/ema) in flight; local_row < 0 = this half-warp has no row in this round.
 template <typename F>
 __device__ __forceinline__ void for_each_owned_row(const uint32_t* __restrict__ bm, int n_maps, int64_t words, int n_shards,
                                                    int rank, F f) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const uint32_t om = own_mask(n_shards, rank);
@@ -218,34 +220,50 @@ __device__ __forceinline__ void for_each_owned_row(const uint32_t* __restrict__ 
       uint32_t wb = __shfl_sync(0xffffffffu, bits, src);
       const int64_t base_row = (w0 + src) * 32;
       while (wb) {
-        const int b = __ffs(wb) - 1;
+        const int b0 = __ffs(wb) - 1;
         wb &= wb - 1;
-        f((base_row + b) >> shift);
+        int b1 = -1;
+        if (wb) { b1 = __ffs(wb) - 1; wb &= wb - 1; }
+        const int bsel = half ? b1 : b0;
+        f(bsel >= 0 ? ((base_row + bsel) >> shift) : (int64_t)-1, hl);
       }
     }
   }
+}
+
+// 4 elements per lane = two of the 2-element catch-up updates (identical per-element arithmetic)
+__device__ __forceinline__ void row_catchup4(float4& p, float4& m, float4& v, float4& e, bool has_ema, bool has_mom, int last,
+                                             int target, const RowHist& H) {
+  float2 p0 = make_float2(p.x, p.y), p1 = make_float2(p.z, p.w), m0 = make_float2(m.x, m.y), m1 = make_float2(m.z, m.w);
+  float2 v0 = make_float2(v.x, v.y), v1 = make_float2(v.z, v.w), e0 = make_float2(e.x, e.y), e1 = make_float2(e.z, e.w);
+  row_catchup(p0, m0, v0, e0, has_ema, has_mom, last, target, H);
+  row_catchup(p1, m1, v1, e1, has_ema, has_mom, last, target, H);
+  p = make_float4(p0.x, p0.y, p1.x, p1.y); m = make_float4(m0.x, m0.y, m1.x, m1.y);
+  v = make_float4(v0.x, v0.y, v1.x, v1.y); e = make_float4(e0.x, e0.y, e1.x, e1.y);
 }
 
 __global__ void __launch_bounds__(256)
 rowopt_catchup_bm_kernel(const uint32_t* __restrict__ bm, int n_maps, int64_t words, int n_shards, int rank,
                          int32_t* __restrict__ state, float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ V,
                          float* __restrict__ E, int target, RowHist H) {
-  const int lane = threadIdx.x & 31;
-  for_each_owned_row(bm, n_maps, words, n_shards, rank, [&](int64_t t) {
+  for_each_owned_row(bm, n_maps, words, n_shards, rank, [&](int64_t t, int hl) {
+    if (t < 0) return;
     const int32_t st = state[t];
     const int last = st >> 1;
     if (last >= target) return;
     const bool has_mom = st & 1;
-    float2* p2 = reinterpret_cast<float2*>(P + t * RO_D) + lane;
-    float2 p = *p2, m = make_float2(0.f, 0.f), v = m, e = m;
-    if (has_mom) { m = reinterpret_cast<float2*>(Mo + t * RO_D)[lane]; v = reinterpret_cast<float2*>(V + t * RO_D)[lane]; }
-    if (E) e = reinterpret_cast<float2*>(E + t * RO_D)[lane];
-    row_catchup(p, m, v, e, E != nullptr, has_mom, last, target, H);
-    *p2 = p;
-    if (has_mom) { reinterpret_cast<float2*>(Mo + t * RO_D)[lane] = m; reinterpret_cast<float2*>(V + t * RO_D)[lane] = v; }
-    if (E) reinterpret_cast<float2*>(E + t * RO_D)[lane] = e;
-    __syncwarp();
-    if (lane == 0) state[t] = (target << 1) | (st & 1);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* p4 = reinterpret_cast<float4*>(P + t * RO_D) + hl;
+    float4 p = *p4, m = z4, v = z4, e = z4;
+    if (has_mom) { m = reinterpret_cast<float4*>(Mo + t * RO_D)[hl]; v = reinterpret_cast<float4*>(V + t * RO_D)[hl]; }
+    if (E) e = reinterpret_cast<float4*>(E + t * RO_D)[hl];
+    row_catchup4(p, m, v, e, E != nullptr, has_mom, last, target, H);
+    *p4 = p;
+    if (has_mom) { reinterpret_cast<float4*>(Mo + t * RO_D)[hl] = m; reinterpret_cast<float4*>(V + t * RO_D)[hl] = v; }
+    if (E) reinterpret_cast<float4*>(E + t * RO_D)[hl] = e;
+    // every lane of the half-warp read state[t] before this point (program order within the lane; the 16 lanes only
+    // read it); lane 0 of the half publishes the new step
+    if (hl == 0) state[t] = (target << 1) | (st & 1);
   });
 }
 
@@ -255,9 +273,10 @@ rows_sqnorm_bm_kernel(const uint32_t* __restrict__ bm, int n_maps, int64_t words
   __shared__ double red[8];
   const int lane = threadIdx.x & 31;
   double s = 0.0;
-  for_each_owned_row(bm, n_maps, words, n_shards, rank, [&](int64_t t) {
-    const float2 g = reinterpret_cast<const float2*>(G + t * RO_D)[lane];
-    s += (double)(g.x * g.x + g.y * g.y);
+  for_each_owned_row(bm, n_maps, words, n_shards, rank, [&](int64_t t, int hl) {
+    if (t < 0) return;
+    const float4 g = reinterpret_cast<const float4*>(G + t * RO_D)[hl];
+    s += (double)(g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w);
   });
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -274,34 +293,38 @@ __global__ void __launch_bounds__(256)
 rowopt_update_bm_kernel(const uint32_t* __restrict__ bm, int n_maps, int64_t words, int n_shards, int rank,
                         int32_t* __restrict__ state, float* __restrict__ P, float* __restrict__ G, float* __restrict__ Mo,
                         float* __restrict__ V, float* __restrict__ E, int t_step, const float* __restrict__ coef, RowHist H) {
-  const int lane = threadIdx.x & 31;
   const float c = coef ? coef[0] : 1.f;
   const float4 hc = __ldg(H.h + t_step);
-  for_each_owned_row(bm, n_maps, words, n_shards, rank, [&](int64_t t) {
+  for_each_owned_row(bm, n_maps, words, n_shards, rank, [&](int64_t t, int hl) {
+    if (t < 0) return;
     const int32_t st = state[t];
     const bool has_mom = st & 1;
-    float2* p2 = reinterpret_cast<float2*>(P + t * RO_D) + lane;
-    float2* g2 = reinterpret_cast<float2*>(G + t * RO_D) + lane;
-    float2* m2 = reinterpret_cast<float2*>(Mo + t * RO_D) + lane;
-    float2* v2 = reinterpret_cast<float2*>(V + t * RO_D) + lane;
-    float2 p = *p2, g = *g2, m = make_float2(0.f, 0.f), v = m, e = m;
-    if (has_mom) { m = *m2; v = *v2; }
-    if (E) e = reinterpret_cast<float2*>(E + t * RO_D)[lane];
-    row_catchup(p, m, v, e, E != nullptr, has_mom, st >> 1, t_step - 1, H);
-    g.x *= c; g.y *= c;
-    p.x *= hc.x; p.y *= hc.x;
-    m.x = m.x + (g.x - m.x) * (1.f - H.beta1); m.y = m.y + (g.y - m.y) * (1.f - H.beta1);
-    v.x = v.x * H.beta2 + (1.f - H.beta2) * g.x * g.x; v.y = v.y * H.beta2 + (1.f - H.beta2) * g.y * g.y;
-    p.x -= hc.y * (m.x / (sqrtf(v.x) / hc.z + H.eps));
-    p.y -= hc.y * (m.y / (sqrtf(v.y) / hc.z + H.eps));
-    *p2 = p; *m2 = m; *v2 = v;
-    *g2 = make_float2(0.f, 0.f);
-    if (E) {
-      e.x = e.x * hc.w + p.x * (1.f - hc.w); e.y = e.y * hc.w + p.y * (1.f - hc.w);
-      reinterpret_cast<float2*>(E + t * RO_D)[lane] = e;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* p4 = reinterpret_cast<float4*>(P + t * RO_D) + hl;
+    float4* g4 = reinterpret_cast<float4*>(G + t * RO_D) + hl;
+    float4* m4 = reinterpret_cast<float4*>(Mo + t * RO_D) + hl;
+    float4* v4 = reinterpret_cast<float4*>(V + t * RO_D) + hl;
+    float4 p = *p4, g = *g4, m = z4, v = z4, e = z4;
+    if (has_mom) { m = *m4; v = *v4; }
+    if (E) e = reinterpret_cast<float4*>(E + t * RO_D)[hl];
+    row_catchup4(p, m, v, e, E != nullptr, has_mom, st >> 1, t_step - 1, H);
+    float pp[4] = {p.x, p.y, p.z, p.w}, gg[4] = {g.x, g.y, g.z, g.w}, mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w},
+          ee[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = gg[k] * c;
+      pp[k] *= hc.x;
+      mm[k] = mm[k] + (gk - mm[k]) * (1.f - H.beta1);
+      vv[k] = vv[k] * H.beta2 + (1.f - H.beta2) * gk * gk;
+      pp[k] -= hc.y * (mm[k] / (sqrtf(vv[k]) / hc.z + H.eps));
+      ee[k] = ee[k] * hc.w + pp[k] * (1.f - hc.w);
     }
-    __syncwarp();
-    if (lane == 0) state[t] = (t_step << 1) | 1;
+    *p4 = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    *m4 = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *v4 = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    *g4 = z4;
+    if (E) reinterpret_cast<float4*>(E + t * RO_D)[hl] = make_float4(ee[0], ee[1], ee[2], ee[3]);
+    if (hl == 0) state[t] = (t_step << 1) | 1;
   });
 }
 
