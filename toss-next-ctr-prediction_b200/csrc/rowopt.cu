@@ -207,8 +207,11 @@ __device__ __forceinline__ void for_each_owned_row(const uint32_t* __restrict__ 
   const uint32_t om = own_mask(n_shards, rank);
   int shift = 0;
   while ((1 << shift) < n_shards) ++shift;
-  for (int64_t w0 = warp * 32; w0 < words; w0 += nw * 32) {
-    const int64_t wi = w0 + lane;
+  // word (j * nw + warp) belongs to this warp: consecutive bitmap words go to different warps, so a dense run of ids
+  // (frequency-sorted vocabularies put all the hot rows together) is spread over the whole grid instead of
+  // serialising inside a few warps
+  for (int64_t j0 = 0; j0 * nw < words; j0 += 32) {
+    const int64_t wi = (j0 + lane) * nw + warp;
     uint32_t bits = 0;
     if (wi < words)
       for (int k = 0; k < n_maps; ++k) bits |= bm[(int64_t)k * words + wi];
@@ -218,7 +221,7 @@ __device__ __forceinline__ void for_each_owned_row(const uint32_t* __restrict__ 
       const int src = __ffs(active) - 1;
       active &= active - 1;
       uint32_t wb = __shfl_sync(0xffffffffu, bits, src);
-      const int64_t base_row = (w0 + src) * 32;
+      const int64_t base_row = ((j0 + src) * nw + warp) * 32;
       while (wb) {
         const int b0 = __ffs(wb) - 1;
         wb &= wb - 1;
