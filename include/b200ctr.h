@@ -210,12 +210,15 @@ int b200ctr_attn_bwd(const float* qkv, const float* relmean, int max_len, const 
                      const float* d_o, int64_t B, int K, int H, int D, float* dqkv, float* drelmean,
                      b200ctr_dropout_t drop, void* stream);
 /* Same contracts on the warp-level tensor cores (mma.sync m16n8k8, TF32 operands, fp32 accumulation): the
- * `amp: bf16` path.  head_dim 8 == the k extent of the instruction; dropout masks are identical to the fp32 kernels'. */
+ * `amp: bf16` path.  head_dim 8 == the k extent of the instruction; dropout masks are identical to the fp32 kernels'.
+ * keep (optional, b200ctr_attn_tc_keep_words(B, K) 32-bit words): the forward stores one keep flag per probability,
+ * the backward reads them instead of re-hashing; NULL = the backward recomputes the mask (same result).            */
+int64_t b200ctr_attn_tc_keep_words(int64_t B, int K);
 int b200ctr_attn_tc_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D,
-                        float* o, float* lse, b200ctr_dropout_t drop, void* stream);
+                        float* o, float* lse, uint32_t* keep, b200ctr_dropout_t drop, void* stream);
 int b200ctr_attn_tc_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
                         const float* d_o, int64_t B, int K, int H, int D, float* dqkv, float* drelmean,
-                        b200ctr_dropout_t drop, void* stream);
+                        const uint32_t* keep, b200ctr_dropout_t drop, void* stream);
 int b200ctr_add_rmsnorm_fwd(const float* a, const float* b, const float* w, float eps, int64_t M, int D,
                             float* s_out, float* y_out, float* r_out, void* stream);
 /* dx = rmsnorm'(dy) (+ dx_add) ; dw[D] += sum_m dy*s*r (atomic; caller zeroes dw) */

@@ -349,7 +349,8 @@ def test_attn_tc_matches_fp32_kernels(dev, B, K, p):
     d_o = _rand(g, B * K, 64).to(dev)
     dr = ops.drop(p, 99, 3)
     o_ref, lse_ref = ops.attn_fwd(qkv, relmean, K, B, K, 8, 64, dr, tc=False)
-    o, lse = ops.attn_fwd(qkv, relmean, K, B, K, 8, 64, dr, tc=True)
+    o, lse, keep = ops.attn_fwd(qkv, relmean, K, B, K, 8, 64, dr, tc=True, save_keep=True)
+    assert (keep is not None) == (p > 0)
     assert max_err_scaled(o.cpu(), o_ref.cpu()) < 3e-3
     assert max_err_scaled(lse.cpu(), lse_ref.cpu()) < 3e-3
     drel_ref = torch.zeros_like(relmean)
@@ -362,6 +363,13 @@ def test_attn_tc_matches_fp32_kernels(dev, B, K, p):
     for sl, name, tol in ((slice(0, 64), "dq", 5e-3), (slice(64, 128), "dk", 1.5e-2), (slice(128, 192), "dv", 1.5e-2)):
         assert float((dq[:, sl] - dq_ref[:, sl]).abs().max()) / gmax < tol, name
     assert float((drel - drel_ref).abs().max()) / (float(drel_ref.abs().max()) + gmax) < 5e-3
+    if keep is not None:
+        # the stored keep flags must reproduce the re-hashed mask exactly: same kernel arithmetic, same result
+        drel_k = torch.zeros_like(relmean)
+        dq_k = ops.attn_bwd(qkv, relmean, K, o_ref, lse_ref, d_o, B, K, 8, 64, drel_k, dr, tc=True, keep=keep)
+        assert torch.equal(dq_k[:, 64:], dq[:, 64:])                                  # dk, dv: no atomics, bit-identical
+        assert float((dq_k[:, :64] - dq[:, :64]).abs().max()) / gmax < 1e-5             # dq: fp32 RED order only
+        assert float((drel_k - drel).abs().max()) / (float(drel.abs().max()) + gmax) < 1e-5
 
 
 @pytest.mark.parametrize("B,H,R,P", [(1000, 6, 16, 192), (7, 6, 16, 192), (300, 8, 32, 128), (64, 2, 4, 24)])

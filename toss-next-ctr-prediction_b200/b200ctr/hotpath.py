@@ -134,11 +134,11 @@ def encoder_layer_fwd(x: Tensor, P: Dict[str, Tensor], i: int, spec: ModelSpec, 
     fused_proj = ops.get_precision() == "bf16" and D == 64 and H == 8
     if fused_proj:        # persistent tcgen05 kernels with resident weights (csrc/proj_fused.cu)
         qkv = ops.inproj_fwd(x, P[n["in_w"]], P[n["in_b"]])
-        o, lse = ops.attn_fwd(qkv, relmean, spec.top_k, B, K, H, D, dc(spec.p_mha, SITE_LAYER0 + 2 * i))
+        o, lse, keep = ops.attn_fwd(qkv, relmean, spec.top_k, B, K, H, D, dc(spec.p_mha, SITE_LAYER0 + 2 * i), save_keep=True)
         s1, x1, r1 = ops.outproj_norm_fwd(o, P[n["out_w"]], P[n["out_b"]], x, P[n["n1"]])
     else:
         qkv = ops.gemm(x, P[n["in_w"]], trans_b=True, bias=P[n["in_b"]])
-        o, lse = ops.attn_fwd(qkv, relmean, spec.top_k, B, K, H, D, dc(spec.p_mha, SITE_LAYER0 + 2 * i))
+        o, lse, keep = ops.attn_fwd(qkv, relmean, spec.top_k, B, K, H, D, dc(spec.p_mha, SITE_LAYER0 + 2 * i), save_keep=True)
         h = ops.gemm(o, P[n["out_w"]], trans_b=True, bias=P[n["out_b"]])
         s1, x1, r1 = ops.add_rmsnorm_fwd(x, h, P[n["n1"]])
     if ops.get_precision() == "bf16" and ops.ffn_fused_ok(spec.ffn_hidden, D):
@@ -152,7 +152,7 @@ def encoder_layer_fwd(x: Tensor, P: Dict[str, Tensor], i: int, spec: ModelSpec, 
                       dropout=dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1))
         h2 = ops.gemm(fd, P[n["f2_w"]], trans_b=True, bias=P[n["f2_b"]])
         s2, x2, r2 = ops.add_rmsnorm_fwd(x1, h2, P[n["n2"]])
-    return x2, dict(x=x, relmean=relmean, qkv=qkv, o=o, lse=lse, s1=s1, x1=x1, r1=r1, pre=pre, fd=fd, s2=s2, r2=r2,
+    return x2, dict(x=x, relmean=relmean, qkv=qkv, o=o, lse=lse, keep=keep, s1=s1, x1=x1, r1=r1, pre=pre, fd=fd, s2=s2, r2=r2,
                     fused_proj=fused_proj)
 
 
@@ -188,7 +188,7 @@ def encoder_layer_bwd(dy: Tensor, sv: dict, P: Dict[str, Tensor], i: int, spec: 
     if spec.pos_bias:
         drelmean = torch.zeros_like(sv["relmean"])
     dqkv = ops.attn_bwd(sv["qkv"], sv["relmean"], spec.top_k, sv["o"], sv["lse"], d_o, B, K, H, D, drelmean,
-                        dc(spec.p_mha, SITE_LAYER0 + 2 * i))
+                        dc(spec.p_mha, SITE_LAYER0 + 2 * i), keep=sv.get("keep"))
     if spec.pos_bias:
         G(n["rel"]).copy_(ops.relmean_bwd(drelmean, H))
     if fused_proj:

@@ -474,23 +474,35 @@ def _attn_tc(tc: Optional[bool], K: int, H: int, D: int) -> bool:
     return bool(tc) and D == 64 and H == 8 and K <= 160
 
 
-def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP, tc: Optional[bool] = None):
+def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP, tc: Optional[bool] = None, save_keep: bool = False):
+    """Returns (o, lse), or (o, lse, keep) with save_keep: keep = the dropout keep-flag words the tensor-core backward reads
+    instead of re-hashing (None when dropout is off or the fp32 kernels run)."""
     lib = _lib.load()
     o = torch.empty((B * K, D), device=qkv.device, dtype=torch.float32)
     lse = torch.empty((B, H, K), device=qkv.device, dtype=torch.float32)
     use_tc = _attn_tc(tc, K, H, D)
-    _run("attn_tc_fwd" if use_tc else "attn_fwd", lib.b200ctr_attn_tc_fwd if use_tc else lib.b200ctr_attn_fwd,
-         _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), dropout, _stream())
+    keep = None
+    if use_tc:
+        if save_keep and dropout.p > 0.0:
+            keep = torch.empty((int(lib.b200ctr_attn_tc_keep_words(B, K)),), device=qkv.device, dtype=torch.int32)
+        _run("attn_tc_fwd", lib.b200ctr_attn_tc_fwd, _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), _p(keep), dropout,
+             _stream())
+    else:
+        _run("attn_fwd", lib.b200ctr_attn_fwd, _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), dropout, _stream())
     _count()
-    return o, lse
+    return (o, lse, keep) if save_keep else (o, lse)
 
 
-def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=NO_DROP, tc: Optional[bool] = None):
+def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=NO_DROP, tc: Optional[bool] = None, keep=None):
     lib = _lib.load()
     dqkv = torch.empty_like(qkv)
     use_tc = _attn_tc(tc, K, H, D)
-    _run("attn_tc_bwd" if use_tc else "attn_bwd", lib.b200ctr_attn_tc_bwd if use_tc else lib.b200ctr_attn_bwd,
-         _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv), _p(drelmean), dropout, _stream())
+    if use_tc:
+        _run("attn_tc_bwd", lib.b200ctr_attn_tc_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
+             _p(drelmean), _p(keep), dropout, _stream())
+    else:
+        _run("attn_bwd", lib.b200ctr_attn_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
+             _p(drelmean), dropout, _stream())
     _count()
     return dqkv
 

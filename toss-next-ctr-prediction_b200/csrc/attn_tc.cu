@@ -37,11 +37,18 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// exp(x) for x <= 0 (softmax numerators): one FMUL + one MUFU, flush-to-zero (no range fix-up code around the MUFU)
-__device__ __forceinline__ float fast_exp(float x) {
+// 2^x for x <= 0: the scores are kept in log2 units (q and the bias carry a log2(e) factor), so a softmax numerator is
+// one MUFU with no multiply in front of it
+__device__ __forceinline__ float fast_exp2(float x) {
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+constexpr float TA_LOG2E = 1.4426950408889634f, TA_LN2 = 0.6931471805599453f;
+// keep-bit words of one (sample, head, 16-query tile): word w, lane l holds the 4 keep flags (rows g / g+8, key pair t)
+// of the 8-key tiles 8w .. 8w+7 -- written by the forward pass, read by the backward pass instead of re-hashing
+__device__ __forceinline__ int64_t ta_keep_index(int64_t b, int h, int mt, int i, int nw, int w, int lane) {
+  return ((((b * TA_H + h) * mt + i) * nw + w) << 5) + lane;
 }
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -75,8 +82,8 @@ __device__ __forceinline__ void ta_load_afrag(uint32_t (&a)[4], const float* __r
 template <int NT>
 __global__ void __launch_bounds__(TA_THREADS)
 attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, int K,
-                   float* __restrict__ o, float* __restrict__ lse, b200ctr_dropout_t drop) {
-  constexpr int Kp = NT * 8, MT = NT / 2;
+                   float* __restrict__ o, float* __restrict__ lse, uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
+  constexpr int Kp = NT * 8, MT = NT / 2, NW = (NT + 7) / 8;
   extern __shared__ __align__(16) uint32_t sm_u[];
   uint32_t* ks = sm_u;
   uint32_t* vs = ks + Kp * TA_RS;
@@ -87,7 +94,7 @@ attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
   ta_stage(vs, base + 2 * TA_D, 3 * TA_D, K, Kp, 1.f);
   for (int t = threadIdx.x; t < 2 * K - 1; t += TA_THREADS) {
     const int d = t - (K - 1);
-    bias[t] = relmean ? relmean[min(max(d, -max_len), max_len) + max_len] : 0.f;
+    bias[t] = relmean ? relmean[min(max(d, -max_len), max_len) + max_len] * TA_LOG2E : 0.f;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -96,7 +103,7 @@ attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
     const int h = item / MT, i = item % MT;
     const int qa = 16 * i + g, qb = qa + 8;
     uint32_t a[4];
-    ta_load_afrag(a, base, 3 * TA_D, qa, qb, K, h * 8 + t, rsqrtf((float)TA_HD));
+    ta_load_afrag(a, base, 3 * TA_D, qa, qb, K, h * 8 + t, rsqrtf((float)TA_HD) * TA_LOG2E);   // scores in log2 units
     float s[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -126,29 +133,39 @@ attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
     // dropout: row id = (b, h, query), column = key
     const uint32_t keya = dctx.on ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qa) : 0u;
     const uint32_t keyb = dctx.on ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qb) : 0u;
+    uint32_t kw[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) kw[w] = 0u;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      float p0 = fast_exp(s[j][0] - ma), p1 = fast_exp(s[j][1] - ma), p2 = fast_exp(s[j][2] - mb), p3 = fast_exp(s[j][3] - mb);
+      float p0 = fast_exp2(s[j][0] - ma), p1 = fast_exp2(s[j][1] - ma), p2 = fast_exp2(s[j][2] - mb), p3 = fast_exp2(s[j][3] - mb);
       la += p0 + p1; lb += p2 + p3;
       if (dctx.on) {
-        float c0, c1, c2, c3;
-        drop_pair(dctx, keya, (uint32_t)(4 * j + t), c0, c1);
-        drop_pair(dctx, keyb, (uint32_t)(4 * j + t), c2, c3);
-        p0 *= c0; p1 *= c1; p2 *= c2; p3 *= c3;
+        const uint32_t ha = drop_pair_hash(keya, (uint32_t)(4 * j + t)), hb = drop_pair_hash(keyb, (uint32_t)(4 * j + t));
+        const bool k0 = (ha & 0xffffu) >= dctx.thr, k1 = (ha >> 16) >= dctx.thr;
+        const bool k2 = (hb & 0xffffu) >= dctx.thr, k3 = (hb >> 16) >= dctx.thr;
+        p0 = k0 ? p0 * dctx.inv : 0.f; p1 = k1 ? p1 * dctx.inv : 0.f;
+        p2 = k2 ? p2 * dctx.inv : 0.f; p3 = k3 ? p3 * dctx.inv : 0.f;
+        const uint32_t sh = 4 * (j & 7);
+        kw[j >> 3] |= (k0 ? 1u << sh : 0u) | (k1 ? 2u << sh : 0u) | (k2 ? 4u << sh : 0u) | (k3 ? 8u << sh : 0u);
       }
       const uint32_t pa[4] = {to_tf32(p0), to_tf32(p2), to_tf32(p1), to_tf32(p3)};
       mma_tf32(oc, pa, vs[(8 * j + 2 * t) * TA_RS + h * 8 + g], vs[(8 * j + 2 * t + 1) * TA_RS + h * 8 + g]);
     }
     la = quad_sum(la); lb = quad_sum(lb);
+    if (keep && dctx.on) {
+#pragma unroll
+      for (int w = 0; w < NW; ++w) keep[ta_keep_index(b, h, MT, i, NW, w, lane)] = kw[w];
+    }
     if (qa < K) {
       const float inv = 1.f / la;
       *reinterpret_cast<float2*>(o + (b * K + qa) * (int64_t)TA_D + h * 8 + 2 * t) = make_float2(oc[0] * inv, oc[1] * inv);
-      if (t == 0) lse[(b * TA_H + h) * (int64_t)K + qa] = ma + logf(la);
+      if (t == 0) lse[(b * TA_H + h) * (int64_t)K + qa] = (ma + log2f(la)) * TA_LN2;       // natural-log units
     }
     if (qb < K) {
       const float inv = 1.f / lb;
       *reinterpret_cast<float2*>(o + (b * K + qb) * (int64_t)TA_D + h * 8 + 2 * t) = make_float2(oc[2] * inv, oc[3] * inv);
-      if (t == 0) lse[(b * TA_H + h) * (int64_t)K + qb] = mb + logf(lb);
+      if (t == 0) lse[(b * TA_H + h) * (int64_t)K + qb] = (mb + log2f(lb)) * TA_LN2;
     }
   }
 }
@@ -179,12 +196,13 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 // KS = key split: the warps (head h, part) with part in [0, KS) own disjoint 16-key blocks of head h, so dK / dV / dbias
 // accumulators stay small (no spills at top_k = 148) and an SM holds 4x more warps than with one warp per head; only dQ
 // needs a cross-warp sum (global fp32 reductions into this sample's zero-initialised dQ rows).
-template <int NT, int KS>
+// KEEP: the dropout keep flags come from the words the forward pass stored (2 instructions per score instead of a hash)
+template <int NT, int KS, bool KEEP>
 __global__ void __launch_bounds__(TA_THREADS * KS, (NT <= 10 ? 2 : 1))
 attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, const float* __restrict__ o,
                    const float* __restrict__ lse, const float* __restrict__ d_o, int K, float* __restrict__ dqkv,
-                   float* __restrict__ drelmean, b200ctr_dropout_t drop) {
-  constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2;
+                   float* __restrict__ drelmean, const uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
+  constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2, NW = (NT + 7) / 8;
   constexpr int NTH = TA_THREADS * KS;
   constexpr int NBW = (NB + KS - 1) / KS;                     // 16-key blocks per warp
   constexpr int NTW = 2 * NBW;                                 // 8-key tiles per warp
@@ -197,10 +215,12 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
   __nv_bfloat16* doT = qT + 64 * TS;                                          // [64][TS]  dO^T
   float* lses = reinterpret_cast<float*>(doT + 64 * TS);        // [H][Kp]  (+inf on padded rows -> P = 0)
   float* dsum = lses + TA_H * Kp;                               // [H][Kp]
-  float* bias = dsum + TA_H * Kp;                               // 2K-1
-  long long* dbias = reinterpret_cast<long long*>(bias + ((2 * K - 1 + 1) & ~1));   // 2*KPA+1 : dbias[(key - query) + KPA]
-  // dbias is accumulated in 32.32 fixed point: 64-bit integer shared-memory atomics are native (fp32 ones are CAS
-  // loops) and the sum becomes order-independent, i.e. deterministic
+  float* bias = dsum + TA_H * Kp;                               // 2K-1 (log2 units)
+  // dbias[(key - query) + KPA], one private copy per warp: shared-memory float AND 64-bit integer atomic adds are
+  // CAS loops (ATOMS.CAST.SPIN), so each warp sums the lanes that share a diagonal with two shuffles and does a plain
+  // read-modify-write on its own copy; the copies are added in warp order at the end (deterministic)
+  constexpr int DBS = 2 * KPA + 2;
+  float* dbias = bias + 2 * K;                                  // [8 * KS][DBS]
   const int64_t b = blockIdx.x;
   const float* base = qkv + b * (int64_t)K * 3 * TA_D;
   const float* dob = d_o + b * (int64_t)K * TA_D;
@@ -234,14 +254,15 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
   }
   for (int tt = threadIdx.x; tt < 2 * K - 1; tt += NTH) {
     const int d = tt - (K - 1);
-    bias[tt] = relmean ? relmean[min(max(d, -max_len), max_len) + max_len] : 0.f;
+    bias[tt] = relmean ? relmean[min(max(d, -max_len), max_len) + max_len] * TA_LOG2E : 0.f;
   }
-  for (int tt = threadIdx.x; tt < 2 * KPA + 1; tt += NTH) dbias[tt] = 0LL;
+  if (drelmean)
+    for (int tt = threadIdx.x; tt < 8 * KS * DBS; tt += NTH) dbias[tt] = 0.f;
   for (int item = threadIdx.x; item < Kp * TA_H; item += NTH) {
     const int h = item / Kp, i = item % Kp;
     float L = INFINITY, dsv = 0.f;
     if (i < K) {
-      L = lse[(b * TA_H + h) * (int64_t)K + i];
+      L = lse[(b * TA_H + h) * (int64_t)K + i] * TA_LOG2E;
       const float4* op = reinterpret_cast<const float4*>(o + (b * K + i) * (int64_t)TA_D + h * TA_HD);
       const float4* dp = reinterpret_cast<const float4*>(dob + (int64_t)i * TA_D + h * TA_HD);
       const float4 o0 = op[0], o1 = op[1], d0 = dp[0], d1 = dp[1];
@@ -263,9 +284,17 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
   float A0[NTW + 1], A1[NTW + 1];
 #pragma unroll
   for (int sl = 0; sl <= NTW; ++sl) { A0[sl] = 0.f; A1[sl] = 0.f; }
-  long long* dbt = dbias + KPA + 2 * t - g + 8 * (2 * jb0);    // + 8 * (local slot - 1 - 2i)
-  auto dbias_add = [](long long* p, float v) {
-    atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__float2ll_rn(v * 4294967296.f));
+  float* dbt = dbias + warp * DBS + KPA + 2 * t - g + 8 * (2 * jb0);    // + 8 * (local slot - 1 - 2i)
+  // lanes (g, t), (g+2, t+1), (g+4, t+2), (g+6, t+3) = lane, lane+9, lane+18, lane+27 lie on the same diagonal 2t-g:
+  // two shuffle steps leave the chain sum in its first lane (t == 0 or g < 2); those 14 lanes hit 14 distinct words
+  const bool ch1 = t < 3 && g < 6, ch2 = t < 2 && g < 4, chead = t == 0 || g < 2;
+  auto dbias_add = [&](float* p, float v) {
+    float x = __shfl_down_sync(0xffffffffu, v, 9);
+    if (ch1) v += x;
+    x = __shfl_down_sync(0xffffffffu, v, 18);
+    if (ch2) v += x;
+    if (chead) *p += v;
+    __syncwarp();
   };
   const uint32_t* qT32 = reinterpret_cast<const uint32_t*>(qT + (h * 8 + g) * TS);
   const uint32_t* doT32 = reinterpret_cast<const uint32_t*>(doT + (h * 8 + g) * TS);
@@ -273,16 +302,21 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
   for (int i = 0; i < MT; ++i) {
     const int qa = 16 * i + g, qb = qa + 8;
     uint32_t aq[4], ad[4];
-    ta_load_afrag(aq, base, 3 * TA_D, qa, qb, K, h * 8 + t, scale);
+    ta_load_afrag(aq, base, 3 * TA_D, qa, qb, K, h * 8 + t, scale * TA_LOG2E);     // scores in log2 units
     ta_load_afrag(ad, dob, TA_D, qa, qb, K, h * 8 + t, 1.f);
+    uint32_t kw[NW];
+    if (KEEP) {
+#pragma unroll
+      for (int w = 0; w < NW; ++w) kw[w] = __ldg(keep + ta_keep_index(b, h, MT, i, NW, w, lane));
+    }
     // B fragments (k = 16 queries of this tile, n = head dim g) of the bf16 m16n8k16 MMAs
     const uint32_t bq0 = qT32[8 * i + t], bq1 = qT32[8 * i + t + 4], bd0 = doT32[8 * i + t], bd1 = doT32[8 * i + t + 4];
     const float La = lses[h * Kp + qa], Lb = lses[h * Kp + qb], Da = dsum[h * Kp + qa], Db = dsum[h * Kp + qb];
     const int qac = min(qa, K - 1), qbc = min(qb, K - 1);
     const float* ba = bias + (K - 1) - qac;
     const float* bb = bias + (K - 1) - qbc;
-    const uint32_t keya = dctx.on ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qa) : 0u;
-    const uint32_t keyb = dctx.on ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qb) : 0u;
+    const uint32_t keya = (!KEEP && dctx.on) ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qa) : 0u;
+    const uint32_t keyb = (!KEEP && dctx.on) ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qb) : 0u;
     float dq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int jl = 0; jl < NBW; ++jl) {
@@ -300,15 +334,21 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
           mma_tf32(dp, ad, vb0, vb1);
           float p0, p1, p2, p3;
           if (NT <= 10 && 8 * j + 8 <= K) {       // warp-uniform: whole tile valid (small kernels only: code size)
-            p0 = fast_exp(s[0] + ba[kc] - La); p1 = fast_exp(s[1] + ba[kc + 1] - La);
-            p2 = fast_exp(s[2] + bb[kc] - Lb); p3 = fast_exp(s[3] + bb[kc + 1] - Lb);
+            p0 = fast_exp2(s[0] + ba[kc] - La); p1 = fast_exp2(s[1] + ba[kc + 1] - La);
+            p2 = fast_exp2(s[2] + bb[kc] - Lb); p3 = fast_exp2(s[3] + bb[kc + 1] - Lb);
           } else {
             const bool v0 = kc < K, v1 = kc + 1 < K;
-            p0 = v0 ? fast_exp(s[0] + ba[kc] - La) : 0.f; p1 = v1 ? fast_exp(s[1] + ba[kc + 1] - La) : 0.f;
-            p2 = v0 ? fast_exp(s[2] + bb[kc] - Lb) : 0.f; p3 = v1 ? fast_exp(s[3] + bb[kc + 1] - Lb) : 0.f;
+            p0 = v0 ? fast_exp2(s[0] + ba[kc] - La) : 0.f; p1 = v1 ? fast_exp2(s[1] + ba[kc + 1] - La) : 0.f;
+            p2 = v0 ? fast_exp2(s[2] + bb[kc] - Lb) : 0.f; p3 = v1 ? fast_exp2(s[3] + bb[kc + 1] - Lb) : 0.f;
           }
           float c0 = 1.f, c1 = 1.f, c2 = 1.f, c3 = 1.f;
-          if (dctx.on) {
+          if (KEEP) {
+            const int w = j >> 3;
+            const uint32_t word = NW == 1 ? kw[0] : (w == 0 ? kw[0] : (w == 1 ? kw[NW > 1 ? 1 : 0] : kw[NW > 2 ? 2 : 0]));
+            const uint32_t nib = word >> (4 * (j & 7));
+            c0 = (nib & 1u) ? dctx.inv : 0.f; c1 = (nib & 2u) ? dctx.inv : 0.f;
+            c2 = (nib & 4u) ? dctx.inv : 0.f; c3 = (nib & 8u) ? dctx.inv : 0.f;
+          } else if (dctx.on) {
             drop_pair(dctx, keya, (uint32_t)(4 * j + t), c0, c1);
             drop_pair(dctx, keyb, (uint32_t)(4 * j + t), c2, c3);
           }
@@ -367,7 +407,9 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
     __syncthreads();
     for (int tt = threadIdx.x; tt < 2 * K - 1; tt += NTH) {
       const int d = tt - (K - 1);
-      atomicAdd(drelmean + min(max(d, -max_len), max_len) + max_len, (float)((double)dbias[d + KPA] * (1.0 / 4294967296.0)));
+      float acc = 0.f;
+      for (int w = 0; w < 8 * KS; ++w) acc += dbias[w * DBS + d + KPA];
+      atomicAdd(drelmean + min(max(d, -max_len), max_len) + max_len, acc);
     }
   }
 }
@@ -386,22 +428,31 @@ static int ta_set_smem(const void* fn, size_t bytes) {
 
 template <int NT>
 static int ta_launch_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, float* o, float* lse,
-                         b200ctr_dropout_t drop, cudaStream_t st) {
+                         uint32_t* keep, b200ctr_dropout_t drop, cudaStream_t st) {
   const size_t smem = ((size_t)2 * NT * 8 * TA_RS + 2 * K) * 4;
   int rc = ta_set_smem((const void*)attn_tc_fwd_kernel<NT>, smem);
   if (rc) return rc;
-  attn_tc_fwd_kernel<NT><<<(unsigned)B, TA_THREADS, smem, st>>>(qkv, relmean, max_len, K, o, lse, drop);
+  attn_tc_fwd_kernel<NT><<<(unsigned)B, TA_THREADS, smem, st>>>(qkv, relmean, max_len, K, o, lse, keep, drop);
   return B200CTR_OK;
 }
 template <int NT>
 static int ta_launch_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse, const float* d_o,
-                         int64_t B, int K, float* dqkv, float* drelmean, b200ctr_dropout_t drop, cudaStream_t st) {
+                         int64_t B, int K, float* dqkv, float* drelmean, const uint32_t* keep, b200ctr_dropout_t drop,
+                         cudaStream_t st) {
   constexpr int KS = NT <= 10 ? 2 : 4;
   constexpr int NBW = (NT / 2 + KS - 1) / KS, KPA = 16 * NBW * KS, Kp = NT * 8;
-  const size_t smem = ((size_t)2 * Kp * TA_RS + 2 * TA_H * Kp + 2 * K + 2) * 4 + (size_t)(2 * KPA + 2) * 8 + (size_t)2 * 64 * (Kp + 8) * 2;
-  int rc = ta_set_smem((const void*)attn_tc_bwd_kernel<NT, KS>, smem);
+  const size_t smem = ((size_t)2 * Kp * TA_RS + 2 * TA_H * Kp + 2 * K) * 4 + (size_t)(8 * KS) * (2 * KPA + 2) * 4 +
+                      (size_t)2 * 64 * (Kp + 8) * 2;
+  const bool use_keep = keep != nullptr && drop.p > 0.f;
+  int rc = use_keep ? ta_set_smem((const void*)attn_tc_bwd_kernel<NT, KS, true>, smem)
+                    : ta_set_smem((const void*)attn_tc_bwd_kernel<NT, KS, false>, smem);
   if (rc) return rc;
-  attn_tc_bwd_kernel<NT, KS><<<(unsigned)B, TA_THREADS * KS, smem, st>>>(qkv, relmean, max_len, o, lse, d_o, K, dqkv, drelmean, drop);
+  if (use_keep)
+    attn_tc_bwd_kernel<NT, KS, true><<<(unsigned)B, TA_THREADS * KS, smem, st>>>(qkv, relmean, max_len, o, lse, d_o, K, dqkv, drelmean,
+                                                                                 keep, drop);
+  else
+    attn_tc_bwd_kernel<NT, KS, false><<<(unsigned)B, TA_THREADS * KS, smem, st>>>(qkv, relmean, max_len, o, lse, d_o, K, dqkv, drelmean,
+                                                                                  nullptr, drop);
   return B200CTR_OK;
 }
 
@@ -420,14 +471,19 @@ using namespace b200ctr;
       return B200CTR_E_UNSUPPORTED_SHAPE;                                            \
   }
 
+extern "C" int64_t b200ctr_attn_tc_keep_words(int64_t B, int K) {
+  const int64_t nt = 2 * (((int64_t)K + 15) / 16);
+  return B * TA_H * (nt / 2) * ((nt + 7) / 8) * 32;
+}
+
 extern "C" int b200ctr_attn_tc_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D, float* o,
-                                   float* lse, b200ctr_dropout_t drop, void* stream) {
+                                   float* lse, uint32_t* keep, b200ctr_dropout_t drop, void* stream) {
   B200_REQUIRE(qkv && o && lse, B200CTR_E_INVALID_ARG, "attn_tc_fwd: null pointer");
   B200_REQUIRE(D == TA_D && H == TA_H, B200CTR_E_UNSUPPORTED_SHAPE,
                "attn_tc_fwd: only emb_dim=64 with 8 heads of head_dim=8 is built (got D=%d, H=%d)", D, H);
   if (B == 0 || K == 0) return B200CTR_OK;
   int rc;
-#define CALL(NT_) ta_launch_fwd<NT_>(qkv, relmean, max_len, B, K, o, lse, drop, as_stream(stream))
+#define CALL(NT_) ta_launch_fwd<NT_>(qkv, relmean, max_len, B, K, o, lse, keep, drop, as_stream(stream))
   TA_DISPATCH(CALL)
 #undef CALL
   if (rc) return rc;
@@ -437,13 +493,13 @@ extern "C" int b200ctr_attn_tc_fwd(const float* qkv, const float* relmean, int m
 
 extern "C" int b200ctr_attn_tc_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
                                    const float* d_o, int64_t B, int K, int H, int D, float* dqkv, float* drelmean,
-                                   b200ctr_dropout_t drop, void* stream) {
+                                   const uint32_t* keep, b200ctr_dropout_t drop, void* stream) {
   B200_REQUIRE(qkv && o && lse && d_o && dqkv, B200CTR_E_INVALID_ARG, "attn_tc_bwd: null pointer");
   B200_REQUIRE(D == TA_D && H == TA_H, B200CTR_E_UNSUPPORTED_SHAPE,
                "attn_tc_bwd: only emb_dim=64 with 8 heads of head_dim=8 is built (got D=%d, H=%d)", D, H);
   if (B == 0 || K == 0) return B200CTR_OK;
   int rc;
-#define CALL(NT_) ta_launch_bwd<NT_>(qkv, relmean, max_len, o, lse, d_o, B, K, dqkv, drelmean, drop, as_stream(stream))
+#define CALL(NT_) ta_launch_bwd<NT_>(qkv, relmean, max_len, o, lse, d_o, B, K, dqkv, drelmean, keep, drop, as_stream(stream))
   TA_DISPATCH(CALL)
 #undef CALL
   if (rc) return rc;

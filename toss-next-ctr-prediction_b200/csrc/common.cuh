@@ -77,9 +77,11 @@ __device__ __forceinline__ DropCtx drop_ctx(const b200ctr_dropout_t& d) {
   return c;
 }
 __device__ __forceinline__ uint32_t drop_row_key(const b200ctr_dropout_t& d, uint64_t row) { return rng_u32(d, row); }
+// the 32 random bits of one aligned column pair: low half -> column 2*colpair, high half -> column 2*colpair+1
+__device__ __forceinline__ uint32_t drop_pair_hash(uint32_t key, uint32_t colpair) { return mix32(key ^ (colpair * 0x9E3779B9U)); }
 // keep-scales of columns 2*colpair and 2*colpair+1 of the row with key `key`
 __device__ __forceinline__ void drop_pair(const DropCtx& c, uint32_t key, uint32_t colpair, float& s0, float& s1) {
-  const uint32_t h = mix32(key ^ (colpair * 0x9E3779B9U));
+  const uint32_t h = drop_pair_hash(key, colpair);
   s0 = (h & 0xffffu) >= c.thr ? c.inv : 0.f;
   s1 = (h >> 16) >= c.thr ? c.inv : 0.f;
 }
