@@ -232,9 +232,11 @@ def test_row_lazy_optimizer_equals_dense(kind):
         finals[lazy] = (sd, {k: v.clone() for k, v in tr.ema_state().items()},
                         {n: (tr.tables[n]["m"].clone(), tr.tables[n]["v"].clone()) for n in tr.tables})
     for k in finals[False][0]:
-        assert max_err_scaled(finals[True][0][k].cpu(), finals[False][0][k].cpu()) < 3e-4, k   # ulp-level differences (closed-form vs sequential decay) fed back through 8 Adam steps
+        # ulp-level differences (closed-form vs sequential decay, and the order of the fp32 gradient atomics, which differs
+        # between the two runs) fed back through 8 Adam steps: the observed spread between runs is 1e-4 .. 3.4e-4
+        assert max_err_scaled(finals[True][0][k].cpu(), finals[False][0][k].cpu()) < 1e-3, k
     for k in finals[False][1]:
-        assert max_err_scaled(finals[True][1][k].cpu(), finals[False][1][k].cpu()) < 3e-4, k
+        assert max_err_scaled(finals[True][1][k].cpu(), finals[False][1][k].cpu()) < 1e-3, k
     for n in finals[False][2]:
         for a, b in zip(finals[True][2][n], finals[False][2][n]):
             assert max_err_scaled(a.cpu(), b.cpu()) < 2e-3, n

@@ -84,6 +84,31 @@ __device__ __forceinline__ void ffn_stage_tile(unsigned char* dst, const float* 
   }
 }
 
+// Normal CDF for the bf16 path: Phi(x) ~= sigmoid(x * (a + b u + c u^2)), u = min(x^2, 64)  (minimax fit of the three
+// coefficients: |error| < 2.1e-5 in Phi and < 4.2e-5 in x * Phi(x), two orders below bf16 resolution; 9 instructions
+// with 2 MUFU instead of the 18 of the erf formula in common.cuh, which stays the fp32 path's GELU).  The
+// coefficients carry the -log2(e) of the exponential.  x -> -inf gives rcp(inf) = 0, x -> +inf gives rcp(1) = 1.
+__device__ __forceinline__ float ffn_cdf(float x, float& u) {
+  u = fminf(x * x, 64.f);
+  float q = fmaf(u, 9.4134924e-4f, -0.10628247f);           // -log2e * (c u + b)
+  q = fmaf(u, q, -2.3016721f);                               // -log2e * a
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * q));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
+__device__ __forceinline__ float ffn_gelu(float x) {
+  float u;
+  return x * ffn_cdf(x, u);
+}
+// cdf = Phi(x); returns GELU'(x) = Phi(x) + x * phi(x), phi = exp(-x^2/2) / sqrt(2 pi)
+__device__ __forceinline__ float ffn_gelu_grad(float x, float& cdf) {
+  float u, e;
+  cdf = ffn_cdf(x, u);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(u, -0.72134752f, -1.3257480f)));   // phi(x), log2(1/sqrt(2 pi)) folded
+  return fmaf(x, e, cdf);
+}
+
 // D[tmem] (+)= A[smem, K-major, R_A rows] . B[smem, K-major, R_B rows]^T over `ksteps` K=16 steps
 __device__ __forceinline__ void ffn_mma_kk(uint32_t tmem_d, uint32_t a_base, uint32_t lbo_a, uint32_t b_base, uint32_t lbo_b,
                                            uint32_t idesc, int ksteps, bool accumulate) {
@@ -211,8 +236,8 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          float f0 = gelu_erf(__uint_as_float(v[j]) + b1s[n0 + j]);
-          float f1 = gelu_erf(__uint_as_float(v[j + 1]) + b1s[n0 + j + 1]);
+          float f0 = ffn_gelu(__uint_as_float(v[j]) + b1s[n0 + j]);
+          float f1 = ffn_gelu(__uint_as_float(v[j + 1]) + b1s[n0 + j + 1]);
           if (dctx.on) {
             float d0, d1;
             drop_pair(dctx, rkey, (uint32_t)(n0 + j) >> 1, d0, d1);
@@ -455,10 +480,10 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const float pre = __uint_as_float(pv[j + u]) + b1s[n0 + j + u];
-            float cdf, ex;
-            gelu_parts(pre, cdf, ex);
+            float cdf;
+            const float gg = ffn_gelu_grad(pre, cdf);
             const float f = pre * cdf * dsc[u];
-            dp[j + u] = __uint_as_float(qv[j + u]) * dsc[u] * fmaf(pre * 0.39894228040143268f, ex, cdf);
+            dp[j + u] = __uint_as_float(qv[j + u]) * dsc[u] * gg;
             pv[j + u] = __float_as_uint(f);
           }
         }
