@@ -20,12 +20,50 @@ namespace b200ctr {
 constexpr int PJ_D = 64;
 constexpr int PJ_TM = 128;
 constexpr int PJ_NT = 13 * 32;
-constexpr int PJ_X_BYTES = PJ_TM * PJ_D * 2;          // 16 KB bf16 activation tile
-constexpr int PJ_ONES_BYTES = 2 * PJ_TM * 16;         // 4 KB: two extra 8-column groups (ones column + zeros)
+// K-direction stride of the 8-column core-matrix groups of a staged tile: 128 rows x 16 bytes + 16 bytes of padding, so
+// that the column groups of one token row fall into different shared-memory banks (the coalesced loaders below write
+// consecutive column groups of the same row from neighbouring lanes)
+constexpr int PJ_LBO = PJ_TM * 16 + 16;
+constexpr int PJ_X_BYTES = 8 * PJ_LBO;                // bf16 activation tile (64 columns)
+constexpr int PJ_ONES_BYTES = 2 * PJ_LBO;             // two extra 8-column groups (ones column + zeros)
 
-// [128 tokens x 64] fp32 rows (stride ld floats) -> bf16 K-major core matrices (R = 128); NTHR cooperating threads
+// Coalesced staging of a [128 tokens x W] fp32 tile as a bf16 K-major UMMA operand.  The tile is a flat list of 16-byte
+// chunks; one pass = NTHR consecutive chunks, i.e. every LDG.128 of a warp reads 512 contiguous bytes (4 L1 wavefronts;
+// the row-per-lane pattern this replaces cost 32, and the kernels were bound by exactly that).  Two passes (A, B) are
+// converted together: 4 fp32 -> 8 bytes of bf16, neighbouring lanes hold the two halves of one 16-byte core-matrix row,
+// so even lanes collect the A halves and odd lanes the B halves with one exchange and every lane stores 16 bytes.
+template <int W, int NTHR>
+__device__ __forceinline__ void pj_load_pairs(float4 (&va)[4], float4 (&vb)[4], const float* __restrict__ src, int64_t m0,
+                                              int64_t T, int pair0, int tid) {
+  constexpr int C4 = W / 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int qa = 2 * (pair0 + k) * NTHR + tid, qb = qa + NTHR;
+    const int ra = qa / C4, rb = qb / C4;
+    va[k] = make_float4(0.f, 0.f, 0.f, 0.f); vb[k] = va[k];
+    if (m0 + ra < T) va[k] = __ldg(reinterpret_cast<const float4*>(src + (m0 + ra) * W) + (qa - ra * C4));
+    if (m0 + rb < T) vb[k] = __ldg(reinterpret_cast<const float4*>(src + (m0 + rb) * W) + (qb - rb * C4));
+  }
+}
+template <int W, int NTHR>
+__device__ __forceinline__ void pj_store_pairs(unsigned char* dst, const float4 (&va)[4], const float4 (&vb)[4], int pair0, int tid) {
+  constexpr int C4 = W / 4;
+  const bool odd = tid & 1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t a0 = pack_bf16(va[k].x, va[k].y), a1 = pack_bf16(va[k].z, va[k].w);
+    const uint32_t b0 = pack_bf16(vb[k].x, vb[k].y), b1 = pack_bf16(vb[k].z, vb[k].w);
+    const uint32_t r0 = __shfl_xor_sync(0xffffffffu, odd ? a0 : b0, 1), r1 = __shfl_xor_sync(0xffffffffu, odd ? a1 : b1, 1);
+    const int q = (2 * (pair0 + k) + (odd ? 1 : 0)) * NTHR + tid;          // the chunk whose 16-byte group this lane stores
+    const int row = q / C4, c8 = (q - row * C4) >> 1;
+    *reinterpret_cast<uint4*>(dst + c8 * PJ_LBO + (row >> 3) * 128 + (row & 7) * 16) =
+        odd ? make_uint4(r0, r1, b0, b1) : make_uint4(a0, a1, r0, r1);
+  }
+}
+
+// row-per-lane variant (each thread reads 32 contiguous bytes of its own row; 32 L1 wavefronts per LDG.128)
 template <int NTHR>
-__device__ __forceinline__ void pj_stage_x(unsigned char* dst, const float* __restrict__ x, int64_t ld, int64_t m0, int64_t T, int ptid) {
+__device__ __forceinline__ void pj_stage_x_rows(unsigned char* dst, const float* __restrict__ x, int64_t ld, int64_t m0, int64_t T, int ptid) {
   constexpr int ITERS = 1024 / NTHR;
   float4 va[ITERS], vb[ITERS];
 #pragma unroll
@@ -41,7 +79,7 @@ __device__ __forceinline__ void pj_stage_x(unsigned char* dst, const float* __re
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int u = ptid + it * NTHR, r = u & 127, c = u >> 7;
-    *reinterpret_cast<uint4*>(dst + (c * 16 + (r >> 3)) * 128 + (r & 7) * 16) =
+    *reinterpret_cast<uint4*>(dst + c * PJ_LBO + (r >> 3) * 128 + (r & 7) * 16) =
         make_uint4(pack_bf16(va[it].x, va[it].y), pack_bf16(va[it].z, va[it].w), pack_bf16(vb[it].x, vb[it].y), pack_bf16(vb[it].z, vb[it].w));
   }
 }
@@ -54,7 +92,7 @@ struct PjFwdBars {
   uint32_t tmem_base;
 };
 
-template <int NOUT, bool POST_NORM>
+template <int NOUT, bool POST_NORM, bool COAL>
 __global__ void __launch_bounds__(PJ_NT, 1)
 lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                const float* __restrict__ resid, const float* __restrict__ nw, float eps, int64_t T,
@@ -97,11 +135,22 @@ lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
   const uint32_t tmem = bars->tmem_base;
 
   if (warp < 4) {
-    // ---- loaders ----
+    // ---- loaders: two batches of 4 pass pairs per tile; the next batch's loads are in flight while one is stored ----
+    auto tile_m0 = [&](int it) { return ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * PJ_TM; };
+    float4 ra[2][4], rb[2][4];
+    if (COAL && n_it > 0) pj_load_pairs<PJ_D, 128>(ra[0], rb[0], x, tile_m0(0), T, 0, tid);
     for (int it = 0; it < n_it; ++it) {
       const int ab = it & 1;
       if (it >= 2) mbar_wait(smem_u32(&bars->a_empty[ab]), (uint32_t)(((it >> 1) - 1) & 1));
-      pj_stage_x<128>(as + ab * PJ_X_BYTES, x, PJ_D, ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * PJ_TM, T, tid);
+      unsigned char* dst = as + ab * PJ_X_BYTES;
+      if (COAL) {
+        pj_load_pairs<PJ_D, 128>(ra[1], rb[1], x, tile_m0(it), T, 4, tid);
+        pj_store_pairs<PJ_D, 128>(dst, ra[0], rb[0], 0, tid);
+        if (it + 1 < n_it) pj_load_pairs<PJ_D, 128>(ra[0], rb[0], x, tile_m0(it + 1), T, 0, tid);
+        pj_store_pairs<PJ_D, 128>(dst, ra[1], rb[1], 4, tid);
+      } else {
+        pj_stage_x_rows<128>(dst, x, PJ_D, tile_m0(it), T, tid);
+      }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[ab]));
@@ -113,7 +162,6 @@ lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
       mbar_wait(smem_u32(&bars->acc_full[eg]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       const int64_t m_w = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * PJ_TM + q * 32;      // first row of this warp
-      const int64_t m = m_w + lane;
       const int rows_valid = (int)max((int64_t)0, min((int64_t)32, T - m_w));
       float* scr = scr_all + ew * SCR;
       const uint32_t taddr = tmem + eg * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
@@ -124,24 +172,43 @@ lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[eg]));
-        float ss = 0.f;
-        if (m < T) {
-          const float4* xr = reinterpret_cast<const float4*>(resid + m * PJ_D);
+        // bias in the row-per-lane domain, then through the scratch: 16 lanes x 16 bytes cover one row, so the residual
+        // load and both stores are whole-row accesses and the row's sum of squares is a 16-lane shuffle reduction
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 xv = __ldg(xr + j);
-            const float s0 = __uint_as_float(v[4 * j]) + bs[4 * j] + xv.x, s1 = __uint_as_float(v[4 * j + 1]) + bs[4 * j + 1] + xv.y;
-            const float s2 = __uint_as_float(v[4 * j + 2]) + bs[4 * j + 2] + xv.z, s3 = __uint_as_float(v[4 * j + 3]) + bs[4 * j + 3] + xv.w;
-            ss = fmaf(s0, s0, ss); ss = fmaf(s1, s1, ss); ss = fmaf(s2, s2, ss); ss = fmaf(s3, s3, ss);
-            v[4 * j] = __float_as_uint(s0); v[4 * j + 1] = __float_as_uint(s1); v[4 * j + 2] = __float_as_uint(s2); v[4 * j + 3] = __float_as_uint(s3);
+        for (int j = 0; j < 16; ++j)
+          *reinterpret_cast<float4*>(scr + lane * 68 + 4 * j) =
+              make_float4(__uint_as_float(v[4 * j]) + bs[4 * j], __uint_as_float(v[4 * j + 1]) + bs[4 * j + 1],
+                          __uint_as_float(v[4 * j + 2]) + bs[4 * j + 2], __uint_as_float(v[4 * j + 3]) + bs[4 * j + 3]);
+        __syncwarp();
+        const int rsub = lane >> 4, c = lane & 15;
+        const float4 nv = *reinterpret_cast<const float4*>(ns + c * 4);
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+          float4 xv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int row = r0 + 2 * u + rsub;
+            xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows_valid) xv[u] = __ldg(reinterpret_cast<const float4*>(resid + (m_w + row) * PJ_D) + c);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int row = r0 + 2 * u + rsub;
+            const float4 a = *reinterpret_cast<const float4*>(scr + row * 68 + c * 4);
+            const float4 sv = make_float4(a.x + xv[u].x, a.y + xv[u].y, a.z + xv[u].z, a.w + xv[u].w);
+            float ss = sv.x * sv.x + sv.y * sv.y + sv.z * sv.z + sv.w * sv.w;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            const float r = rsqrtf(ss * (1.f / PJ_D) + eps);
+            if (row < rows_valid) {
+              const int64_t mr = m_w + row;
+              if (s_out) *reinterpret_cast<float4*>(s_out + mr * PJ_D + c * 4) = sv;
+              *reinterpret_cast<float4*>(y + mr * PJ_D + c * 4) = make_float4(nv.x * sv.x * r, nv.y * sv.y * r, nv.z * sv.z * r, nv.w * sv.w * r);
+              if (r_out && c == 0) r_out[mr] = r;
+            }
           }
         }
-        const float r = rsqrtf(ss * (1.f / PJ_D) + eps);
-        if (r_out && m < T) r_out[m] = r;
-        if (s_out) warp_store_rows<64>(scr, v, s_out + m_w * PJ_D, PJ_D, rows_valid, lane);
-#pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(ns[j] * __uint_as_float(v[j]) * r);
-        warp_store_rows<64>(scr, v, y + m_w * PJ_D, PJ_D, rows_valid, lane);
+        __syncwarp();
       } else {
 #pragma unroll 1
         for (int cc = 0; cc < NOUT / 32; ++cc) {
@@ -169,7 +236,7 @@ lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
       tc_fence_after();
 #pragma unroll 1
       for (int ks = 0; ks < PJ_D / 16; ++ks)
-        umma_bf16(tmem + ab * ACC_STRIDE, make_desc(as_u + ab * PJ_X_BYTES + ks * 2 * (PJ_TM * 16), PJ_TM * 16, 128),
+        umma_bf16(tmem + ab * ACC_STRIDE, make_desc(as_u + ab * PJ_X_BYTES + ks * 2 * PJ_LBO, PJ_LBO, 128),
                   make_desc(ws_u + ks * 2 * (NOUT * 16), NOUT * 16, 128), idesc, ks > 0 ? 1u : 0u);
       umma_commit(smem_u32(&bars->acc_full[ab]));
       umma_commit(smem_u32(&bars->a_empty[ab]));
@@ -192,7 +259,7 @@ struct PjBwdBars {
 };
 
 template <int NOUT, bool PRE_NORM>
-__global__ void __launch_bounds__(PJ_NT, 1)
+__global__ void __launch_bounds__(PJ_NT, 1)      // 13 warps: 4 on one SM sub-partition (16K registers) -> 128 registers per thread at most
 lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gradient of the norm's output ; else dY (T,NOUT)
                const float* __restrict__ s, const float* __restrict__ r, const float* __restrict__ nw,   // PRE_NORM only
                const float* __restrict__ xin,      // (T,64) forward input of the linear layer
@@ -202,7 +269,7 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
                float* __restrict__ wsp /* per-CTA partials */) {
   constexpr int NP = NOUT <= 128 ? 128 : 256;                   // dY columns padded to whole 128-row weight-gradient blocks
   constexpr int NBLK = NP / 128;
-  constexpr int DY_BYTES = PJ_TM * NP * 2;
+  constexpr int DY_BYTES = (NP / 8) * PJ_LBO;
   constexpr int IN_BYTES = PJ_X_BYTES + PJ_ONES_BYTES + DY_BYTES;
   constexpr int TMEM_COLS = NBLK == 1 ? 256 : 512;
   constexpr int DW_COL = 128, DW_STRIDE = 128;
@@ -210,9 +277,9 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
   unsigned char* wsm = smem;                                    // W as MN-major B operand (N = d_in, K = NOUT)
   unsigned char* ins = wsm + NOUT * 128;                        // [2][x 16 KB | ones 4 KB | dY]
   float* red = reinterpret_cast<float*>(ins + 2 * IN_BYTES);    // 8 warps x 64 (dn partials)
-  // store-transpose scratch of the 4 epilogue warps (64-wide kernel only: at NOUT = 192 the extra 18 KB would push the
-  // shared-memory carve-out to 228 KB and the 28 KB of L1 left no longer hold the loader's row lines -- measured slower)
-  constexpr int SCR_FLOATS = NOUT <= 64 ? 4 * 32 * 36 : 0;
+  // store-transpose scratch of the 4 epilogue warps (the loaders read whole lines once, so the small L1 left by the
+  // 228 KB carve-out at NOUT = 192 no longer matters)
+  constexpr int SCR_FLOATS = 4 * 32 * 36;
   float* scr_all = red + 8 * PJ_D;
   PjBwdBars* bars = reinterpret_cast<PjBwdBars*>(scr_all + SCR_FLOATS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -242,10 +309,10 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
   for (int bsel = 0; bsel < 2; ++bsel) {
     unsigned char* ones = ins + bsel * IN_BYTES + PJ_X_BYTES;
     for (int i = tid; i < 2 * PJ_TM; i += PJ_NT)        // group 8: column 64 == 1.0 (bf16 0x3F80), group 9: zeros
-      *reinterpret_cast<uint4*>(ones + i * 16) = make_uint4(i < PJ_TM ? 0x00003F80u : 0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(ones + (i >> 7) * PJ_LBO + (i & 127) * 16) = make_uint4(i < PJ_TM ? 0x00003F80u : 0u, 0u, 0u, 0u);
     unsigned char* dyb = ones + PJ_ONES_BYTES;
     for (int i = tid; i < (NP - NOUT) / 8 * PJ_TM; i += PJ_NT)
-      *reinterpret_cast<uint4*>(dyb + (NOUT / 8) * (PJ_TM * 16) + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(dyb + (NOUT / 8 + (i >> 7)) * PJ_LBO + (i & 127) * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
   fence_async_smem();
   tc_fence_before();
@@ -258,20 +325,34 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
     float2 dn_acc = make_float2(0.f, 0.f);
     float2 nwv = make_float2(0.f, 0.f);
     if (PRE_NORM) nwv = reinterpret_cast<const float2*>(nw)[lane];
+    // Batch 0 = the x tile (4 pass pairs of 256 chunks), batches 1.. = the dY tile.  The loads of batch b+1 (and of the
+    // next tile's first batch) are issued before batch b is converted and stored: 32 KB per SM stay in flight.
+    constexpr int NBATCH = 1 + (PRE_NORM ? 0 : PJ_TM * (NOUT / 4) / 256 / 8);
+    static_assert(NBATCH % 2 == 0 || NBATCH == 1, "register sets alternate with a static parity");
+    auto tile_m0 = [&](int it) { return ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * PJ_TM; };
+    auto load_batch = [&](int it, int bi, float4 (&va)[4], float4 (&vb)[4]) {
+      if (bi == 0) pj_load_pairs<PJ_D, 256>(va, vb, xin, tile_m0(it), T, 0, tid);
+      else pj_load_pairs<NOUT, 256>(va, vb, gin, tile_m0(it), T, (bi - 1) * 4, tid);
+    };
+    auto store_batch = [&](unsigned char* xs, unsigned char* dys, int bi, const float4 (&va)[4], const float4 (&vb)[4]) {
+      if (bi == 0) pj_store_pairs<PJ_D, 256>(xs, va, vb, 0, tid);
+      else pj_store_pairs<NOUT, 256>(dys, va, vb, (bi - 1) * 4, tid);
+    };
+    float4 ra[2][4], rb[2][4];
+    if (n_it > 0) load_batch(0, 0, ra[0], rb[0]);
     for (int it = 0; it < n_it; ++it) {
       const int ib = it & 1;
       if (it >= 2) mbar_wait(smem_u32(&bars->in_empty[ib]), (uint32_t)(((it >> 1) - 1) & 1));
-      const int64_t m0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * PJ_TM;
+      const int64_t m0 = tile_m0(it);
       unsigned char* xs = ins + ib * IN_BYTES;
       unsigned char* dys = xs + PJ_X_BYTES + PJ_ONES_BYTES;
-      pj_stage_x<256>(xs, xin, PJ_D, m0, T, tid);
       if (PRE_NORM) {
-#pragma unroll 1
-        for (int rr = 0; rr < 16; rr += 4) {
-          float2 d[4], sv[4];
-          float rv[4];
+        // rows of this warp, 8 at a time: gradient of the norm's output, saved sum and 1/rms -> dY = RMSNorm'(dOut)
+        float2 d[8], sv[8];
+        float rv[8];
+        auto load_rows = [&](int rr) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int64_t m = m0 + warp * 16 + rr + u;
             d[u] = make_float2(0.f, 0.f); sv[u] = d[u]; rv[u] = 0.f;
             if (m < T) {
@@ -280,8 +361,10 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
               rv[u] = __ldg(r + m);
             }
           }
+        };
+        auto norm_rows = [&](int rr) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int row = warp * 16 + rr + u;
             const int64_t m = m0 + row;
             const float2 g = make_float2(d[u].x * nwv.x, d[u].y * nwv.y);
@@ -291,30 +374,21 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
             dn_acc.x = fmaf(d[u].x * sv[u].x, rv[u], dn_acc.x);
             dn_acc.y = fmaf(d[u].y * sv[u].y, rv[u], dn_acc.y);
             if (m < T) reinterpret_cast<float2*>(dy_out + m * PJ_D)[lane] = o;
-            *reinterpret_cast<uint32_t*>(dys + ((lane >> 2) * 16 + (row >> 3)) * 128 + (row & 7) * 16 + (lane & 3) * 4) = pack_bf16(o.x, o.y);
+            *reinterpret_cast<uint32_t*>(dys + (lane >> 2) * PJ_LBO + (row >> 3) * 128 + (row & 7) * 16 + (lane & 3) * 4) = pack_bf16(o.x, o.y);
           }
-        }
+        };
+        load_rows(0);                                  // in flight together with the x tile (batch 0)
+        store_batch(xs, dys, 0, ra[0], rb[0]);
+        norm_rows(0);
+        load_rows(8);
+        if (it + 1 < n_it) load_batch(it + 1, 0, ra[0], rb[0]);
+        norm_rows(8);
       } else {
-        constexpr int UNITS = PJ_TM * (NOUT / 8), ITERS = UNITS / 256;
-#pragma unroll 1
-        for (int it0 = 0; it0 < ITERS; it0 += 4) {
-          float4 va[4], vb[4];
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int u = tid + (it0 + q4) * 256, rrow = u & 127, c = u >> 7;
-            const int64_t m = m0 + rrow;
-            va[q4] = make_float4(0.f, 0.f, 0.f, 0.f); vb[q4] = va[q4];
-            if (m < T) {
-              const float4* p = reinterpret_cast<const float4*>(gin + m * NOUT + c * 8);
-              va[q4] = __ldg(p); vb[q4] = __ldg(p + 1);
-            }
-          }
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int u = tid + (it0 + q4) * 256, rrow = u & 127, c = u >> 7;
-            *reinterpret_cast<uint4*>(dys + (c * 16 + (rrow >> 3)) * 128 + (rrow & 7) * 16) =
-                make_uint4(pack_bf16(va[q4].x, va[q4].y), pack_bf16(va[q4].z, va[q4].w), pack_bf16(vb[q4].x, vb[q4].y), pack_bf16(vb[q4].z, vb[q4].w));
-          }
+        for (int bi = 0; bi < NBATCH; ++bi) {
+          if (bi + 1 < NBATCH) load_batch(it, bi + 1, ra[(bi + 1) & 1], rb[(bi + 1) & 1]);
+          else if (it + 1 < n_it) load_batch(it + 1, 0, ra[0], rb[0]);
+          store_batch(xs, dys, bi, ra[bi & 1], rb[bi & 1]);
         }
       }
       fence_async_smem();
@@ -339,25 +413,10 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
       const int64_t m_w = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * PJ_TM + q * 32;
       const int64_t m = m_w + lane;
       const int rows_valid = (int)max((int64_t)0, min((int64_t)32, T - m_w));
-      if (resid && m < T) {
-        const float4* rp = reinterpret_cast<const float4*>(resid + m * PJ_D);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 a = __ldg(rp + j);
-          v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + a.x); v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + a.y);
-          v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + a.z); v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + a.w);
-        }
-      }
-      if (NOUT <= 64) {          // measured: the transposed store pays off for the 64-wide kernel, not for the 192-wide one
-        float* scr = scr_all + (warp - 8) * (32 * 36);
-        warp_store_rows<32>(scr, v, dx + m_w * PJ_D, PJ_D, rows_valid, lane);
-        warp_store_rows<32>(scr, v + 32, dx + m_w * PJ_D + 32, PJ_D, rows_valid, lane);
-      } else if (m < T) {
-        float4* op = reinterpret_cast<float4*>(dx + m * PJ_D);
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          op[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-      }
+      float* scr = scr_all + (warp - 8) * (32 * 36);
+      warp_store_rows_add<32>(scr, v, dx + m_w * PJ_D, PJ_D, resid ? resid + m_w * PJ_D : nullptr, PJ_D, rows_valid, lane);
+      warp_store_rows_add<32>(scr, v + 32, dx + m_w * PJ_D + 32, PJ_D, resid ? resid + m_w * PJ_D + 32 : nullptr, PJ_D, rows_valid, lane);
+      (void)m;
     }
     mbar_wait(smem_u32(&bars->done), 0);
     tc_fence_after();
@@ -385,14 +444,14 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
       const uint32_t xs_u = in_u + ib * IN_BYTES, dy_u = xs_u + PJ_X_BYTES + PJ_ONES_BYTES;
 #pragma unroll 1
       for (int ks = 0; ks < NOUT / 16; ++ks)
-        umma_bf16(tmem + ib * 64, make_desc(dy_u + ks * 2 * (PJ_TM * 16), PJ_TM * 16, 128), make_desc(w_u + ks * 2 * 1024, 1024, 128),
+        umma_bf16(tmem + ib * 64, make_desc(dy_u + ks * 2 * PJ_LBO, PJ_LBO, 128), make_desc(w_u + ks * 2 * 1024, 1024, 128),
                   idesc_dx, ks > 0 ? 1u : 0u);
       umma_commit(smem_u32(&bars->dx_full[ib]));
       for (int b = 0; b < NBLK; ++b) {
 #pragma unroll 1
-        for (int ks = 0; ks < 8; ++ks)      // K = 128 tokens; MN-major views: k-group (8 tokens) stride 128 B, mn-group stride 2048 B
-          umma_bf16(tmem + DW_COL + b * DW_STRIDE, make_desc(dy_u + b * 16 * (PJ_TM * 16) + ks * 256, 128, 2048),
-                    make_desc(xs_u + ks * 256, 128, 2048), idesc_dw, (it > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < 8; ++ks)      // K = 128 tokens; MN-major views: k-group (8 tokens) stride 128 B, mn-group stride PJ_LBO
+          umma_bf16(tmem + DW_COL + b * DW_STRIDE, make_desc(dy_u + b * 16 * PJ_LBO + ks * 256, 128, PJ_LBO),
+                    make_desc(xs_u + ks * 256, 128, PJ_LBO), idesc_dw, (it > 0 || ks > 0) ? 1u : 0u);
       }
       umma_commit(smem_u32(&bars->in_empty[ib]));
     }
@@ -435,7 +494,9 @@ static int launch_lin_fwd(const float* x, const float* w, const float* bias, con
                           int64_t T, float* y, float* s_out, float* r_out, cudaStream_t st) {
   const size_t smem = (size_t)NOUT * 128 + 2 * PJ_X_BYTES + ((size_t)NOUT + PJ_D) * 4 +
                       (size_t)8 * 32 * ((POST_NORM ? 64 : 32) + 4) * 4 + sizeof(PjFwdBars) + 16;
-  auto fn = lin_fwd_kernel<NOUT, POST_NORM>;
+  // measured on B200: the coalesced loader wins for the 64-wide kernel (0.103 vs 0.117 ms per launch), the row-per-lane
+  // loader for the 192-wide one (0.102 vs 0.112 ms), whose epilogue already keeps the L1 data pipe busy with 96 KB of stores per tile
+  auto fn = lin_fwd_kernel<NOUT, POST_NORM, POST_NORM>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(lin_fwd smem)");
   const int grid = (int)std::min<int64_t>(ceil_div(T, (int64_t)PJ_TM), (int64_t)num_sms());
@@ -448,7 +509,7 @@ static int launch_lin_bwd(const float* gin, const float* s, const float* r, cons
                           const float* resid, int64_t T, float* dy_out, float* dx, float* dw, float* db, float* dn, float* wsp,
                           cudaStream_t st) {
   constexpr int NP = NOUT <= 128 ? 128 : 256;
-  const size_t smem = (size_t)NOUT * 128 + 2 * (size_t)(PJ_X_BYTES + PJ_ONES_BYTES + PJ_TM * NP * 2) + 8 * PJ_D * 4 + (size_t)(NOUT <= 64 ? 4 * 32 * 36 * 4 : 0) +
+  const size_t smem = (size_t)NOUT * 128 + 2 * (size_t)(PJ_X_BYTES + PJ_ONES_BYTES + (NP / 8) * PJ_LBO) + 8 * PJ_D * 4 + (size_t)(4 * 32 * 36 * 4) +
                       sizeof(PjBwdBars) + 16;
   auto fn = lin_bwd_kernel<NOUT, PRE_NORM>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -113,4 +113,32 @@ __device__ __forceinline__ void warp_store_rows(float* scratch, const uint32_t* 
   __syncwarp();
 }
 
+// warp_store_rows with a residual: gbase[row] = v[row] + addbase[row], the residual read in the same coalesced pattern
+// as the store (row-per-lane 16-byte loads cost one L1 wavefront per lane, whole-row loads one per 128 bytes)
+template <int NC>
+__device__ __forceinline__ void warp_store_rows_add(float* scratch, const uint32_t* v, float* gbase, int64_t ld,
+                                                    const float* __restrict__ addbase, int64_t ld_add, int rows_valid, int lane) {
+  constexpr int SR = NC + 4, LPR = NC / 4, RPI = 32 / LPR;
+#pragma unroll
+  for (int j = 0; j < NC / 4; ++j)
+    *reinterpret_cast<uint4*>(scratch + lane * SR + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int rsub = lane / LPR, c = lane % LPR;
+  float4 x[32 / RPI];
+#pragma unroll
+  for (int i = 0; i < 32 / RPI; ++i) {
+    const int row = i * RPI + rsub;
+    x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (addbase && row < rows_valid) x[i] = __ldg(reinterpret_cast<const float4*>(addbase + (int64_t)row * ld_add + c * 4));
+  }
+#pragma unroll
+  for (int i = 0; i < 32 / RPI; ++i) {
+    const int row = i * RPI + rsub;
+    const float4 a = *reinterpret_cast<const float4*>(scratch + row * SR + c * 4);
+    if (row < rows_valid)
+      *reinterpret_cast<float4*>(gbase + (int64_t)row * ld + c * 4) = make_float4(a.x + x[i].x, a.y + x[i].y, a.z + x[i].z, a.w + x[i].w);
+  }
+  __syncwarp();
+}
+
 }  // namespace b200ctr
