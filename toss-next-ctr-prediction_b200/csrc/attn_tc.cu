@@ -195,14 +195,17 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 
 // KS = key split: the warps (head h, part) with part in [0, KS) own disjoint 16-key blocks of head h, so dK / dV / dbias
 // accumulators stay small (no spills at top_k = 148) and an SM holds 4x more warps than with one warp per head; only dQ
-// needs a cross-warp sum (global fp32 reductions into this sample's zero-initialised dQ rows).
+// needs a cross-warp sum.
 // KEEP: the dropout keep flags come from the words the forward pass stored (2 instructions per score instead of a hash)
 template <int NT, int KS, bool KEEP>
-__global__ void __launch_bounds__(TA_THREADS * KS, (NT <= 10 ? 2 : 1))
+// One CTA per SM: ~120 registers, no spills (two CTAs at 64 registers spilled the dK / dV / dbias accumulators: 2.28 vs
+// 1.83 ms per step).  dQ is summed over the key parts through a small shared-memory hand-off (one named barrier per head).
+__global__ void __launch_bounds__(TA_THREADS * KS, 1)
 attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, const float* __restrict__ o,
                    const float* __restrict__ lse, const float* __restrict__ d_o, int K, float* __restrict__ dqkv,
                    float* __restrict__ drelmean, const uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
   constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2, NW = (NT + 7) / 8;
+  constexpr bool SQD = NT <= 10;      // q / dO also staged as TF32 (A fragments from shared memory); does not fit for long sequences
   constexpr int NTH = TA_THREADS * KS;
   constexpr int NBW = (NB + KS - 1) / KS;                     // 16-key blocks per warp
   constexpr int NTW = 2 * NBW;                                 // 8-key tiles per warp
@@ -211,9 +214,11 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
   extern __shared__ __align__(16) uint32_t sm_u[];
   uint32_t* ks = sm_u;
   uint32_t* vs = ks + Kp * TA_RS;
-  __nv_bfloat16* qT = reinterpret_cast<__nv_bfloat16*>(vs + Kp * TA_RS);     // [64][TS]  (pre-scaled q)^T
+  uint32_t* qs = vs + Kp * TA_RS;                               // q * scale (TF32): A fragments of S = Q.K^T   (SQD only)
+  uint32_t* dos = qs + (SQD ? Kp * TA_RS : 0);                  // dO (TF32): A fragments of dP = dO.V^T         (SQD only)
+  __nv_bfloat16* qT = reinterpret_cast<__nv_bfloat16*>(dos + (SQD ? Kp * TA_RS : 0));     // [64][TS]  (q * scale)^T
   __nv_bfloat16* doT = qT + 64 * TS;                                          // [64][TS]  dO^T
-  float* lses = reinterpret_cast<float*>(doT + 64 * TS);        // [H][Kp]  (+inf on padded rows -> P = 0)
+  float* lses = reinterpret_cast<float*>(doT + 64 * TS);        // [H][Kp]  (+inf on padded rows -> P = 0), log2 units
   float* dsum = lses + TA_H * Kp;                               // [H][Kp]
   float* bias = dsum + TA_H * Kp;                               // 2K-1 (log2 units)
   // dbias[(key - query) + KPA], one private copy per warp: shared-memory float AND 64-bit integer atomic adds are
@@ -221,23 +226,30 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
   // read-modify-write on its own copy; the copies are added in warp order at the end (deterministic)
   constexpr int DBS = 2 * KPA + 2;
   float* dbias = bias + 2 * K;                                  // [8 * KS][DBS]
+  // dQ hand-off between the key parts of a head: parts 1.. write their 16 x 8 tile, part 0 adds and stores the rows
+  float* dqx = dbias + 8 * KS * DBS;                            // [H][2 (query-tile parity)][KS - 1][128]
   const int64_t b = blockIdx.x;
   const float* base = qkv + b * (int64_t)K * 3 * TA_D;
   const float* dob = d_o + b * (int64_t)K * TA_D;
   const float scale = rsqrtf((float)TA_HD);
+  // Everything the main loop reads comes from shared memory: the loop was bound by the L1 data pipe, a third of it
+  // fragment loads from global memory (8 rows = 8 tag lookups per LDG) and another tenth the dQ reductions.
   for (int i = threadIdx.x; i < Kp * 16; i += NTH) {
     const int r = i >> 4, c = i & 15;
-    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), kv = qv, vv = qv, dv = qv;
     if (r < K) {
-      kv = *reinterpret_cast<const float4*>(base + (int64_t)r * 3 * TA_D + TA_D + c * 4);
-      vv = *reinterpret_cast<const float4*>(base + (int64_t)r * 3 * TA_D + 2 * TA_D + c * 4);
+      const float4* row = reinterpret_cast<const float4*>(base + (int64_t)r * 3 * TA_D);
+      kv = row[16 + c]; vv = row[32 + c];
+      if (SQD) { qv = row[c]; dv = *reinterpret_cast<const float4*>(dob + (int64_t)r * TA_D + c * 4); }
     }
     *reinterpret_cast<uint4*>(ks + r * TA_RS + c * 4) = make_uint4(to_tf32(kv.x), to_tf32(kv.y), to_tf32(kv.z), to_tf32(kv.w));
     *reinterpret_cast<uint4*>(vs + r * TA_RS + c * 4) = make_uint4(to_tf32(vv.x), to_tf32(vv.y), to_tf32(vv.z), to_tf32(vv.w));
-    // dQ is summed over the key parts with global reductions (RED.ADD.F32 is native at L2): zero this sample's rows first
-    if (r < K) *reinterpret_cast<float4*>(dqkv + (b * K + r) * (int64_t)(3 * TA_D) + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (SQD) {
+      *reinterpret_cast<uint4*>(qs + r * TA_RS + c * 4) = make_uint4(to_tf32(qv.x * scale), to_tf32(qv.y * scale), to_tf32(qv.z * scale), to_tf32(qv.w * scale));
+      *reinterpret_cast<uint4*>(dos + r * TA_RS + c * 4) = make_uint4(to_tf32(dv.x), to_tf32(dv.y), to_tf32(dv.z), to_tf32(dv.w));
+    }
   }
-  {
+  if (!SQD) {
     constexpr int TOT = Kp * 64, PER = (TOT + NTH - 1) / NTH;   // coalesced global reads (all in flight), transposed smem writes
     float qv[PER], dv[PER];
 #pragma unroll
@@ -271,6 +283,17 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
     lses[item] = L; dsum[item] = dsv;
   }
   __syncthreads();
+  // bf16 transposes of the staged q / dO tiles (B operands of dK += dS^T.Q, dV += P^T.dO): a thread packs rows 2rp, 2rp+1
+  // of column c; lanes = 8 columns x 4 row pairs, which is bank-conflict free on both the reads and the writes
+  for (int u = threadIdx.x; SQD && u < (Kp / 2) * 64; u += NTH) {
+    const int lane_ = u & 31, blk = u >> 5;                     // blk -> (column group of 8, row-pair group of 4)
+    const int c = (blk & 7) * 8 + (lane_ & 7), rp = (blk >> 3) * 4 + (lane_ >> 3);
+    const uint32_t q0 = qs[(2 * rp) * TA_RS + c], q1 = qs[(2 * rp + 1) * TA_RS + c];
+    const uint32_t d0 = dos[(2 * rp) * TA_RS + c], d1 = dos[(2 * rp + 1) * TA_RS + c];
+    reinterpret_cast<uint32_t*>(qT + c * TS)[rp] = pack_bf16x2(__uint_as_float(q0), __uint_as_float(q1));
+    reinterpret_cast<uint32_t*>(doT + c * TS)[rp] = pack_bf16x2(__uint_as_float(d0), __uint_as_float(d1));
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int h = warp & 7, part = warp >> 3;                     // (head, key part)
   const int jb0 = part * NBW;                                   // first 16-key block of this warp
@@ -302,8 +325,14 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
   for (int i = 0; i < MT; ++i) {
     const int qa = 16 * i + g, qb = qa + 8;
     uint32_t aq[4], ad[4];
-    ta_load_afrag(aq, base, 3 * TA_D, qa, qb, K, h * 8 + t, scale * TA_LOG2E);     // scores in log2 units
-    ta_load_afrag(ad, dob, TA_D, qa, qb, K, h * 8 + t, 1.f);
+    if (SQD) {
+      const int oa = qa * TA_RS + h * 8 + t, ob = qb * TA_RS + h * 8 + t;      // rows >= K are zero in shared memory
+      aq[0] = qs[oa]; aq[1] = qs[ob]; aq[2] = qs[oa + 4]; aq[3] = qs[ob + 4];
+      ad[0] = dos[oa]; ad[1] = dos[ob]; ad[2] = dos[oa + 4]; ad[3] = dos[ob + 4];
+    } else {
+      ta_load_afrag(aq, base, 3 * TA_D, qa, qb, K, h * 8 + t, scale);
+      ta_load_afrag(ad, dob, TA_D, qa, qb, K, h * 8 + t, 1.f);
+    }
     uint32_t kw[NW];
     if (KEEP) {
 #pragma unroll
@@ -318,6 +347,8 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
     const uint32_t keya = (!KEEP && dctx.on) ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qa) : 0u;
     const uint32_t keyb = (!KEEP && dctx.on) ? drop_row_key(drop, ((uint64_t)b * TA_H + h) * K + qb) : 0u;
     float dq[4] = {0.f, 0.f, 0.f, 0.f};
+    // rows g+8 see the bias of rows g shifted by one 8-key tile: carry the previous tile's pair instead of reloading
+    float pb0 = bb[16 * jb0 + 2 * t], pb1 = bb[16 * jb0 + 2 * t + 1];
 #pragma unroll
     for (int jl = 0; jl < NBW; ++jl) {
       if (jb0 + jl < NB) {                                      // warp-uniform
@@ -332,15 +363,17 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
           float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
           mma_tf32(s, aq, kb0, kb1);
           mma_tf32(dp, ad, vb0, vb1);
+          const float a0 = ba[kc], a1 = ba[kc + 1];
           float p0, p1, p2, p3;
           if (NT <= 10 && 8 * j + 8 <= K) {       // warp-uniform: whole tile valid (small kernels only: code size)
-            p0 = fast_exp2(s[0] + ba[kc] - La); p1 = fast_exp2(s[1] + ba[kc + 1] - La);
-            p2 = fast_exp2(s[2] + bb[kc] - Lb); p3 = fast_exp2(s[3] + bb[kc + 1] - Lb);
+            p0 = fast_exp2(fmaf(s[0], TA_LOG2E, a0 - La)); p1 = fast_exp2(fmaf(s[1], TA_LOG2E, a1 - La));
+            p2 = fast_exp2(fmaf(s[2], TA_LOG2E, pb0 - Lb)); p3 = fast_exp2(fmaf(s[3], TA_LOG2E, pb1 - Lb));
           } else {
             const bool v0 = kc < K, v1 = kc + 1 < K;
-            p0 = v0 ? fast_exp2(s[0] + ba[kc] - La) : 0.f; p1 = v1 ? fast_exp2(s[1] + ba[kc + 1] - La) : 0.f;
-            p2 = v0 ? fast_exp2(s[2] + bb[kc] - Lb) : 0.f; p3 = v1 ? fast_exp2(s[3] + bb[kc + 1] - Lb) : 0.f;
+            p0 = v0 ? fast_exp2(fmaf(s[0], TA_LOG2E, a0 - La)) : 0.f; p1 = v1 ? fast_exp2(fmaf(s[1], TA_LOG2E, a1 - La)) : 0.f;
+            p2 = v0 ? fast_exp2(fmaf(s[2], TA_LOG2E, pb0 - Lb)) : 0.f; p3 = v1 ? fast_exp2(fmaf(s[3], TA_LOG2E, pb1 - Lb)) : 0.f;
           }
+          pb0 = a0; pb1 = a1;
           float c0 = 1.f, c1 = 1.f, c2 = 1.f, c3 = 1.f;
           if (KEEP) {
             const int w = j >> 3;
@@ -367,13 +400,24 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
         mma_bf16_16816(dk[jl], ads, bq0, bq1);
       }
     }
-    if (qa < K) {
-      float* dst = dqkv + (b * K + qa) * (int64_t)(3 * TA_D) + h * 8 + 2 * t;
-      atomicAdd(dst, dq[0] * scale); atomicAdd(dst + 1, dq[1] * scale);
-    }
-    if (qb < K) {
-      float* dst = dqkv + (b * K + qb) * (int64_t)(3 * TA_D) + h * 8 + 2 * t;
-      atomicAdd(dst, dq[2] * scale); atomicAdd(dst + 1, dq[3] * scale);
+    {
+      float2* xq = reinterpret_cast<float2*>(dqx + (size_t)((h * 2 + (i & 1)) * (KS - 1)) * 128);
+      if (part != 0) {
+        xq[(part - 1) * 64 + lane] = make_float2(dq[0], dq[1]);            // row g, dims 2t, 2t+1
+        xq[(part - 1) * 64 + 32 + lane] = make_float2(dq[2], dq[3]);       // row g + 8
+      }
+      asm volatile("bar.sync %0, %1;" :: "r"(h + 1), "r"(32 * KS) : "memory");   // the KS warps of head h
+      if (part == 0) {
+#pragma unroll
+        for (int pp = 0; pp < KS - 1; ++pp) {
+          const float2 x0 = xq[pp * 64 + lane], x1 = xq[pp * 64 + 32 + lane];
+          dq[0] += x0.x; dq[1] += x0.y; dq[2] += x1.x; dq[3] += x1.y;
+        }
+        if (qa < K)
+          *reinterpret_cast<float2*>(dqkv + (b * K + qa) * (int64_t)(3 * TA_D) + h * 8 + 2 * t) = make_float2(dq[0] * scale, dq[1] * scale);
+        if (qb < K)
+          *reinterpret_cast<float2*>(dqkv + (b * K + qb) * (int64_t)(3 * TA_D) + h * 8 + 2 * t) = make_float2(dq[2] * scale, dq[3] * scale);
+      }
     }
     if (drelmean) {
       // local slot sl holds the diagonal block u = 2*jb0 + sl - 1 - 2i
@@ -441,8 +485,8 @@ static int ta_launch_bwd(const float* qkv, const float* relmean, int max_len, co
                          cudaStream_t st) {
   constexpr int KS = NT <= 10 ? 2 : 4;
   constexpr int NBW = (NT / 2 + KS - 1) / KS, KPA = 16 * NBW * KS, Kp = NT * 8;
-  const size_t smem = ((size_t)2 * Kp * TA_RS + 2 * TA_H * Kp + 2 * K) * 4 + (size_t)(8 * KS) * (2 * KPA + 2) * 4 +
-                      (size_t)2 * 64 * (Kp + 8) * 2;
+  const size_t smem = ((size_t)(NT <= 10 ? 4 : 2) * Kp * TA_RS + 2 * TA_H * Kp + 2 * K) * 4 + (size_t)(8 * KS) * (2 * KPA + 2) * 4 +
+                      (size_t)TA_H * 2 * (KS - 1) * 128 * 4 + (size_t)2 * 64 * (Kp + 8) * 2;
   const bool use_keep = keep != nullptr && drop.p > 0.f;
   int rc = use_keep ? ta_set_smem((const void*)attn_tc_bwd_kernel<NT, KS, true>, smem)
                     : ta_set_smem((const void*)attn_tc_bwd_kernel<NT, KS, false>, smem);
