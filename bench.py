@@ -387,6 +387,11 @@ def run_cuda(args):
                                         sorted(((t, v) for t, v in prof.items() if t.startswith("gemm")),
                                                key=lambda kv: -kv[1][1])[:10]},
         }
+        if os.environ.get("B200CTR_BENCH_DUMP"):      # full per-op table (development aid): every family and GEMM shape
+            with open(os.environ["B200CTR_BENCH_DUMP"], "w") as fh:
+                json.dump({"families_ms_per_step": {k: [v[0] // args.steps, round(v[1] / args.steps, 4)] for k, v in top},
+                           "ops_ms_per_step": {k: [v[0] // args.steps, round(v[1] / args.steps, 4)]
+                                               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}, fh, indent=1)
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference(args.cfg, 2, 1, sample_B=args.ref_batch)
             line["cpu_baseline"] = cb

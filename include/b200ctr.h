@@ -216,8 +216,10 @@ int b200ctr_attn_bwd(const float* qkv, const float* relmean, int max_len, const 
 int64_t b200ctr_attn_tc_keep_words(int64_t B, int K);
 int b200ctr_attn_tc_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D,
                         float* o, float* lse, uint32_t* keep, b200ctr_dropout_t drop, void* stream);
+/* dqkv_bf16 != 0: dqkv is written as bf16 (same (M, 3D) layout) for b200ctr_inproj_bwd(dqkv_bf16 = 1), which rounds
+ * it to bf16 for its tensor-core products in any case (identical results, half the traffic).                       */
 int b200ctr_attn_tc_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
-                        const float* d_o, int64_t B, int K, int H, int D, float* dqkv, float* drelmean,
+                        const float* d_o, int64_t B, int K, int H, int D, void* dqkv, int dqkv_bf16, float* drelmean,
                         const uint32_t* keep, b200ctr_dropout_t drop, void* stream);
 int b200ctr_add_rmsnorm_fwd(const float* a, const float* b, const float* w, float eps, int64_t M, int D,
                             float* s_out, float* y_out, float* r_out, void* stream);
@@ -264,8 +266,8 @@ int64_t b200ctr_proj_bwd_workspace_bytes(void);
 int b200ctr_outproj_norm_bwd(const float* dx1, const float* s1, const float* r1, const float* n1w, const float* o,
                              const float* w_out, int64_t T, int D, float* ds1_out, float* d_o, float* dw_out,
                              float* db_out, float* dn1, void* workspace, void* stream);
-int b200ctr_inproj_bwd(const float* dqkv, const float* x, const float* w_in, const float* d_resid, int64_t T, int D,
-                       float* dx, float* dw_in, float* db_in, void* workspace, void* stream);
+int b200ctr_inproj_bwd(const void* dqkv, int dqkv_bf16, const float* x, const float* w_in, const float* d_resid, int64_t T,
+                       int D, float* dx, float* dw_in, float* db_in, void* workspace, void* stream);
 
 /* ---- gated pooling + aux head  (dare.py:151-161) ------------------------------------------------------- */
 int b200ctr_pool_fwd(const float* x, const float* vals, const float* aux_w, const float* aux_b, int gating_relu,
@@ -298,6 +300,14 @@ int64_t b200ctr_fm_fused_bwd_workspace_bytes(void);
 int b200ctr_fm_fused_bwd(const void* z_bf16, const float* Ucat, const float* s, const float* dquad,
                          const float* dz_resid, int64_t B, int F, int C, int D, float* dz, float* dUcat,
                          void* workspace, void* stream);
+/* The MLP's final Linear(K -> 1) (qnn_alpha.py:85-93) as row dot products instead of 1-wide GEMMs:
+ *   fwd: out[b] = h[b,:] . w + bias[0]
+ *   bwd: dh[b,n] = dl[b] * w[n] * (act[b,n] != 0 ? mask_scale : 0) ; dw[n] = sum_b dl[b] act[b,n] ; db[0] = sum_b dl[b]
+ *        (act = the layer's input after ReLU + dropout, whose mask it carries; K a multiple of 128, <= 512)          */
+int b200ctr_lin1_fwd(const float* h, int64_t ldh, const float* w, const float* bias, int64_t B, int K, float* out, void* stream);
+int64_t b200ctr_lin1_bwd_workspace_bytes(int K);
+int b200ctr_lin1_bwd(const float* dl, const float* act, int64_t ldact, const float* w, int64_t B, int K, float mask_scale,
+                     float* dh, int64_t lddh, float* dw, float* db, void* workspace, void* stream);
 /* headproj: inter[b, h*P+p] = sum_r quad[b, h*R+r] * V[h][r][p] for all heads in one launch (qnn_alpha.py:96);
  * bwd: dquad and dV (overwritten; deterministic two-stage batch reduction through `workspace`).              */
 int b200ctr_headproj_fwd(const float* quad, const float* V, int64_t B, int H, int R, int P, float* inter, void* stream);

@@ -367,9 +367,11 @@ def test_attn_tc_matches_fp32_kernels(dev, B, K, p):
         # the stored keep flags must reproduce the re-hashed mask exactly: same kernel arithmetic, same result
         drel_k = torch.zeros_like(relmean)
         dq_k = ops.attn_bwd(qkv, relmean, K, o_ref, lse_ref, d_o, B, K, 8, 64, drel_k, dr, tc=True, keep=keep)
-        assert torch.equal(dq_k[:, 64:], dq[:, 64:])                                  # dk, dv: no atomics, bit-identical
-        assert float((dq_k[:, :64] - dq[:, :64]).abs().max()) / gmax < 1e-5             # dq: fp32 RED order only
+        assert torch.equal(dq_k, dq)                                                  # no atomics anywhere: bit-identical
         assert float((drel_k - drel).abs().max()) / (float(drel.abs().max()) + gmax) < 1e-5
+    # bf16 output for the fused in-projection backward: the same values, rounded once
+    dq16 = ops.attn_bwd(qkv, relmean, K, o_ref, lse_ref, d_o, B, K, 8, 64, torch.zeros_like(relmean), dr, tc=True, keep=keep, out_bf16=True)
+    assert dq16.dtype == torch.bfloat16 and torch.equal(dq16, dq.to(torch.bfloat16))
 
 
 @pytest.mark.parametrize("B,H,R,P", [(1000, 6, 16, 192), (7, 6, 16, 192), (300, 8, 32, 128), (64, 2, 4, 24)])
@@ -434,6 +436,9 @@ def test_fused_projections_match_unfused(dev, T):
     dwo, dbo, dn1, dwi, dbi = z(64, 64), z(64), z(64), z(192, 64), z(192)
     ds1, d_o = ops.outproj_norm_bwd(dx1, s1_u, r1_u, n1, o, w_out, dwo, dbo, dn1)
     dx = ops.inproj_bwd(dqkv, x, w_in, ds1_u, dwi, dbi)
+    dwi16, dbi16 = torch.empty_like(dwi), torch.empty_like(dbi)
+    dx16 = ops.inproj_bwd(dqkv.to(torch.bfloat16), x, w_in, ds1_u, dwi16, dbi16)      # bf16 dqkv: the kernel rounds fp32 the same way
+    assert torch.equal(dx16, dx) and torch.equal(dwi16, dwi) and torch.equal(dbi16, dbi)
     for name, a, b, tol in (("qkv", qkv, qkv_u, 2e-3), ("s1", s1, s1_u, 2e-3), ("x1", x1, x1_u, 2e-3), ("r1", r1, r1_u, 2e-3),
                             ("ds1", ds1, ds1_u, 1e-4), ("d_o", d_o, do_u, 3e-3), ("dw_out", dwo, dwo_u, 5e-3),
                             ("db_out", dbo, dbo_u, 5e-3), ("dn1", dn1, dn1_u, 1e-3), ("dx", dx, dx_u, 3e-3),
@@ -485,3 +490,21 @@ def test_gemm_tma_kmajor(dev, M, N, K):
     if M % 2 == 0 and K % 2 == 0:
         t2 = ops.transpose_bf16(a16)
         assert torch.equal(t2.cpu(), a16.t().contiguous().cpu())
+
+
+# ---- Linear(K -> 1) as row dot products (csrc/qnn.cu lin1_*) vs torch ---------------------------------------------
+@pytest.mark.parametrize("B,K", [(1000, 256), (7, 128), (4096, 512)])
+def test_lin1_matches_torch(dev, B, K):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(B + K)
+    h = torch.relu(_rand(g, B, K))                       # ReLU output: exact zeros carry the mask
+    w, bias, dl = _rand(g, 1, K) * 0.1, _rand(g, 1), _rand(g, B, 1)
+    out = ops.lin1_fwd(h.to(dev), w.to(dev), bias.to(dev))
+    ref = h.double() @ w.double().t() + bias.double()
+    assert max_err_scaled(out.cpu(), ref) < 1e-5
+    dw, db = torch.empty(1, K, device=dev), torch.empty(1, device=dev)
+    dh = ops.lin1_bwd(dl.to(dev), h.to(dev), w.to(dev), 1.25, dw, db)
+    dh_ref = (dl.double() @ w.double()) * (h != 0).double() * 1.25
+    assert max_err_scaled(dh.cpu(), dh_ref) < 1e-5
+    assert max_err_scaled(dw.cpu(), dl.double().t() @ h.double()) < 1e-5
+    assert abs(float(db.cpu()) - float(dl.double().sum())) < 1e-4 * (1 + float(dl.abs().sum()))

@@ -188,7 +188,7 @@ def encoder_layer_bwd(dy: Tensor, sv: dict, P: Dict[str, Tensor], i: int, spec: 
     if spec.pos_bias:
         drelmean = torch.zeros_like(sv["relmean"])
     dqkv = ops.attn_bwd(sv["qkv"], sv["relmean"], spec.top_k, sv["o"], sv["lse"], d_o, B, K, H, D, drelmean,
-                        dc(spec.p_mha, SITE_LAYER0 + 2 * i), keep=sv.get("keep"))
+                        dc(spec.p_mha, SITE_LAYER0 + 2 * i), keep=sv.get("keep"), out_bf16=bool(sv.get("fused_proj")))
     if spec.pos_bias:
         G(n["rel"]).copy_(ops.relmean_bwd(drelmean, H))
     if fused_proj:
@@ -257,12 +257,16 @@ def qnn_fwd(P: Dict[str, Tensor], spec: ModelSpec, xF: Tensor, dc: DropCtl, B_to
     # and of W0 (converted once per step) instead of converting fp32 operands inside the GEMM's load path
     bf16_ops = ops.get_precision() == "bf16" and N % 8 == 0 and B >= 128
     z16 = W0_16 = None
+    fm_fused = bf16_ops and ops.fm_fused_ok(F, C, D)
     if bf16_ops:
-        z, rz, z16 = ops.rowrms_fwd(flat, P["qnn.pre_norm.w"], want_bf16=True)
+        # every consumer of z reads the bf16 copy when the fused interaction and the bf16 first-layer products run: the
+        # fp32 z (B x F*D) is then never written
+        W0_ = P[f"qnn.mlp.{_qnn_mlp_names(P)[0]}.weight"]
+        all_bf16 = fm_fused and W0_.shape[1] % 8 == 0 and W0_.is_contiguous() and W0_.shape[0] % 8 == 0
+        z, rz, z16 = ops.rowrms_fwd(flat, P["qnn.pre_norm.w"], want_bf16=True, want_f32=not all_bf16)
     else:
         z, rz = ops.rowrms_fwd(flat, P["qnn.pre_norm.w"])
     Ucat = P["qnn.U"].permute(1, 0, 2).reshape(D, C).contiguous()            # (D, H*r): layout plumbing only
-    fm_fused = z16 is not None and ops.fm_fused_ok(F, C, D)
     if fm_fused:          # one tcgen05 kernel; the (B*F, C) product z.Ucat stays in TMEM
         A = None
         s, quad = ops.fm_fused_fwd(z16, Ucat, B, F)
@@ -308,7 +312,11 @@ def qnn_fwd(P: Dict[str, Tensor], spec: ModelSpec, xF: Tensor, dc: DropCtl, B_to
             hcur = ops.gemm(hcur, P[f"qnn.mlp.{mlp[li]}.weight"], trans_b=True, bias=P[f"qnn.mlp.{mlp[li]}.bias"],
                             act=ops.ACT_RELU, dropout=dc(spec.p_qnn, SITE_MLP0 + li))
             acts.append(hcur)
-        logit = ops.gemm(hcur, P[f"qnn.mlp.{mlp[-1]}.weight"], trans_b=True, bias=P[f"qnn.mlp.{mlp[-1]}.bias"])
+        Wl = P[f"qnn.mlp.{mlp[-1]}.weight"]
+        if Wl.shape[0] == 1 and ops.lin1_ok(Wl.shape[1]) and hcur.is_contiguous():      # Linear(K -> 1): row dot products
+            logit = ops.lin1_fwd(hcur, Wl, P[f"qnn.mlp.{mlp[-1]}.bias"])
+        else:
+            logit = ops.gemm(hcur, Wl, trans_b=True, bias=P[f"qnn.mlp.{mlp[-1]}.bias"])
     sv.update(igd=igd, acts=acts, mlp=mlp, B_total=Bt, z16=z16 if W0_16 is not None else None, W0_16=W0_16,
               z16_fm=z16 if fm_fused else None)
     return logit.view(B), sv
@@ -330,9 +338,13 @@ def qnn_bwd(P, spec: ModelSpec, sv: dict, dlogit: Tensor, dc: DropCtl, G: Callab
     if len(mlp) == 1:
         dh = dl
     else:
-        ops.gemm(dl, acts[-1], trans_a=True, out=G(f"qnn.mlp.{last}.weight"))
-        ops.colsum(dl, out=G(f"qnn.mlp.{last}.bias"))
-        dh = ops.gemm(dl, P[f"qnn.mlp.{last}.weight"], mask_mode=ops.MASK_NONZERO, mask_src=acts[-1], mask_scale=ms)
+        Wl = P[f"qnn.mlp.{last}.weight"]
+        if Wl.shape[0] == 1 and ops.lin1_ok(Wl.shape[1]) and acts[-1].is_contiguous() and dl.is_contiguous():
+            dh = ops.lin1_bwd(dl, acts[-1], Wl, ms, G(f"qnn.mlp.{last}.weight"), G(f"qnn.mlp.{last}.bias"))
+        else:
+            ops.gemm(dl, acts[-1], trans_a=True, out=G(f"qnn.mlp.{last}.weight"))
+            ops.colsum(dl, out=G(f"qnn.mlp.{last}.bias"))
+            dh = ops.gemm(dl, Wl, mask_mode=ops.MASK_NONZERO, mask_src=acts[-1], mask_scale=ms)
         for li in range(len(mlp) - 2, 0, -1):
             ops.gemm(dh, acts[li - 1], trans_a=True, out=G(f"qnn.mlp.{mlp[li]}.weight"))
             ops.colsum(dh, out=G(f"qnn.mlp.{mlp[li]}.bias"))

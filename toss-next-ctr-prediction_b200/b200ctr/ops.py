@@ -493,13 +493,16 @@ def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP, tc: Optional[bo
     return (o, lse, keep) if save_keep else (o, lse)
 
 
-def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=NO_DROP, tc: Optional[bool] = None, keep=None):
+def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=NO_DROP, tc: Optional[bool] = None, keep=None,
+             out_bf16: bool = False):
+    """out_bf16 (tensor-core path only): dqkv comes back as bf16 for inproj_bwd, which consumes it as bf16 in any case."""
     lib = _lib.load()
-    dqkv = torch.empty_like(qkv)
     use_tc = _attn_tc(tc, K, H, D)
+    out_bf16 = bool(out_bf16 and use_tc)
+    dqkv = torch.empty(qkv.shape, device=qkv.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
     if use_tc:
         _run("attn_tc_bwd", lib.b200ctr_attn_tc_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
-             _p(drelmean), _p(keep), dropout, _stream())
+             int(out_bf16), _p(drelmean), _p(keep), dropout, _stream())
     else:
         _run("attn_bwd", lib.b200ctr_attn_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
              _p(drelmean), dropout, _stream())
@@ -562,8 +565,10 @@ def inproj_bwd(dqkv, x, w_in, d_resid, dw_in, db_in):
     T, D = x.shape
     dx = torch.empty_like(x)
     ws = _proj_ws(x.device)
-    _run("inproj_bwd", lib.b200ctr_inproj_bwd, _p(_f32(dqkv)), _p(x), _p(w_in), _p(d_resid), T, D, _p(dx), _p(dw_in), _p(db_in),
-         _p(ws), _stream())
+    if dqkv.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"inproj_bwd: dqkv must be float32 or bfloat16, got {dqkv.dtype}")
+    _run("inproj_bwd", lib.b200ctr_inproj_bwd, _p(dqkv), int(dqkv.dtype == torch.bfloat16), _p(x), _p(w_in), _p(d_resid), T, D, _p(dx),
+         _p(dw_in), _p(db_in), _p(ws), _stream())
     _count(2)
     return dx
 
@@ -654,16 +659,44 @@ def pool_bwd(x, vals, w, aux_w, u, ld_u, du, ld_du, daux, gating_relu, daux_w, d
 
 
 # ---- QNN-alpha -------------------------------------------------------------------------------------------------
-def rowrms_fwd(x, w, eps=1e-6, want_bf16=False):
-    """z = w * x * rsqrt(mean(x^2) + eps) per row; want_bf16 also returns a bf16 copy of z for the tensor-core GEMMs."""
+def rowrms_fwd(x, w, eps=1e-6, want_bf16=False, want_f32=True):
+    """z = w * x * rsqrt(mean(x^2) + eps) per row; want_bf16 also returns a bf16 copy of z for the tensor-core GEMMs
+    (want_f32=False with want_bf16: only the bf16 copy is written, z is None)."""
     lib = _lib.load()
     B, N = x.shape
-    z = torch.empty((B, N), device=x.device, dtype=torch.float32)
+    assert want_f32 or want_bf16
+    z = torch.empty((B, N), device=x.device, dtype=torch.float32) if want_f32 else None
     r = torch.empty((B,), device=x.device, dtype=torch.float32)
     z16 = torch.empty((B, N), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     _run("rowrms_fwd", lib.b200ctr_rowrms_fwd_bf16, _p(x), _ld(x), _p(w), eps, B, N, _p(z), N, _p(r), _p(z16), _stream())
     _count()
     return (z, r, z16) if want_bf16 else (z, r)
+
+
+def lin1_ok(K: int) -> bool:
+    return K % 128 == 0 and K <= 512
+
+
+def lin1_fwd(h: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """Linear(K -> 1): out (B, 1) = h @ w^T + bias, one warp per row."""
+    lib = _lib.load()
+    B, K = h.shape
+    out = torch.empty((B, 1), device=h.device, dtype=torch.float32)
+    _run("lin1_fwd", lib.b200ctr_lin1_fwd, _p(_f32(h)), _ld(h), _p(_f32(w)), _p(bias), B, K, _p(out), _stream())
+    _count()
+    return out
+
+
+def lin1_bwd(dl: torch.Tensor, act: torch.Tensor, w: torch.Tensor, mask_scale: float, dw: torch.Tensor, db: Optional[torch.Tensor]):
+    """Backward of Linear(K -> 1) behind ReLU + dropout: returns dh (B, K); writes dw (1, K) and db (1,)."""
+    lib = _lib.load()
+    B, K = act.shape
+    dh = torch.empty((B, K), device=act.device, dtype=torch.float32)
+    ws = torch.empty((int(lib.b200ctr_lin1_bwd_workspace_bytes(K)) // 4,), device=act.device, dtype=torch.float32)
+    _run("lin1_bwd", lib.b200ctr_lin1_bwd, _p(_f32(dl)), _p(_f32(act)), _ld(act), _p(_f32(w)), B, K, float(mask_scale), _p(dh), K,
+         _p(dw), _p(db), _p(ws), _stream())
+    _count(2)
+    return dh
 
 
 def to_bf16(x: torch.Tensor) -> torch.Tensor:
@@ -773,7 +806,7 @@ def se_gate_fwd(csum, B, w1, b1, w2, b2):
     gate = torch.empty((C,), device=csum.device, dtype=torch.float32)
     _run("se_gate_fwd", lib.b200ctr_se_gate_fwd, _p(csum), 1.0 / B, _p(w1), _p(b1), _p(w2), _p(b2), C, Cr, _p(mean), _p(h1), _p(gate),
                                   _stream())
-    _count()
+    _count(2)
     return mean, h1, gate
 
 

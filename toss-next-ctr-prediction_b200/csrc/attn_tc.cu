@@ -193,6 +193,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// two adjacent gradient elements at element offset `off` of the (M, 192) tensor: fp32 pair or one packed bf16 pair
+__device__ __forceinline__ void ta_store2(float* base, int as_bf16, int64_t off, float a, float b) {
+  if (as_bf16) reinterpret_cast<uint32_t*>(base)[off >> 1] = pack_bf16x2(a, b);
+  else *reinterpret_cast<float2*>(base + off) = make_float2(a, b);
+}
+
 // KS = key split: the warps (head h, part) with part in [0, KS) own disjoint 16-key blocks of head h, so dK / dV / dbias
 // accumulators stay small (no spills at top_k = 148) and an SM holds 4x more warps than with one warp per head; only dQ
 // needs a cross-warp sum.
@@ -202,8 +208,10 @@ template <int NT, int KS, bool KEEP>
 // 1.83 ms per step).  dQ is summed over the key parts through a small shared-memory hand-off (one named barrier per head).
 __global__ void __launch_bounds__(TA_THREADS * KS, 1)
 attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, const float* __restrict__ o,
-                   const float* __restrict__ lse, const float* __restrict__ d_o, int K, float* __restrict__ dqkv,
+                   const float* __restrict__ lse, const float* __restrict__ d_o, int K, float* __restrict__ dqkv, int dq16,
                    float* __restrict__ drelmean, const uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
+  // dq16: dqkv is written as bf16 (same (M, 192) layout) -- its only consumer, the fused in-projection backward, rounds
+  // it to bf16 for its tensor-core products anyway, so the results are identical and the tensor costs half the HBM traffic
   constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2, NW = (NT + 7) / 8;
   constexpr bool SQD = NT <= 10;      // q / dO also staged as TF32 (A fragments from shared memory); does not fit for long sequences
   constexpr int NTH = TA_THREADS * KS;
@@ -413,10 +421,8 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
           const float2 x0 = xq[pp * 64 + lane], x1 = xq[pp * 64 + 32 + lane];
           dq[0] += x0.x; dq[1] += x0.y; dq[2] += x1.x; dq[3] += x1.y;
         }
-        if (qa < K)
-          *reinterpret_cast<float2*>(dqkv + (b * K + qa) * (int64_t)(3 * TA_D) + h * 8 + 2 * t) = make_float2(dq[0] * scale, dq[1] * scale);
-        if (qb < K)
-          *reinterpret_cast<float2*>(dqkv + (b * K + qb) * (int64_t)(3 * TA_D) + h * 8 + 2 * t) = make_float2(dq[2] * scale, dq[3] * scale);
+        if (qa < K) ta_store2(dqkv, dq16, (b * K + qa) * (int64_t)(3 * TA_D) + h * 8 + 2 * t, dq[0] * scale, dq[1] * scale);
+        if (qb < K) ta_store2(dqkv, dq16, (b * K + qb) * (int64_t)(3 * TA_D) + h * 8 + 2 * t, dq[2] * scale, dq[3] * scale);
       }
     }
     if (drelmean) {
@@ -439,12 +445,12 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
   for (int jl = 0; jl < NBW; ++jl) {
     const int ka = 16 * (jb0 + jl) + g, kb = ka + 8;
     if (ka < K) {
-      *reinterpret_cast<float2*>(dqkv + (b * K + ka) * (int64_t)(3 * TA_D) + TA_D + h * 8 + 2 * t) = make_float2(dk[jl][0], dk[jl][1]);
-      *reinterpret_cast<float2*>(dqkv + (b * K + ka) * (int64_t)(3 * TA_D) + 2 * TA_D + h * 8 + 2 * t) = make_float2(dv[jl][0], dv[jl][1]);
+      ta_store2(dqkv, dq16, (b * K + ka) * (int64_t)(3 * TA_D) + TA_D + h * 8 + 2 * t, dk[jl][0], dk[jl][1]);
+      ta_store2(dqkv, dq16, (b * K + ka) * (int64_t)(3 * TA_D) + 2 * TA_D + h * 8 + 2 * t, dv[jl][0], dv[jl][1]);
     }
     if (kb < K) {
-      *reinterpret_cast<float2*>(dqkv + (b * K + kb) * (int64_t)(3 * TA_D) + TA_D + h * 8 + 2 * t) = make_float2(dk[jl][2], dk[jl][3]);
-      *reinterpret_cast<float2*>(dqkv + (b * K + kb) * (int64_t)(3 * TA_D) + 2 * TA_D + h * 8 + 2 * t) = make_float2(dv[jl][2], dv[jl][3]);
+      ta_store2(dqkv, dq16, (b * K + kb) * (int64_t)(3 * TA_D) + TA_D + h * 8 + 2 * t, dk[jl][2], dk[jl][3]);
+      ta_store2(dqkv, dq16, (b * K + kb) * (int64_t)(3 * TA_D) + 2 * TA_D + h * 8 + 2 * t, dv[jl][2], dv[jl][3]);
     }
   }
   if (drelmean) {
@@ -481,7 +487,7 @@ static int ta_launch_fwd(const float* qkv, const float* relmean, int max_len, in
 }
 template <int NT>
 static int ta_launch_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse, const float* d_o,
-                         int64_t B, int K, float* dqkv, float* drelmean, const uint32_t* keep, b200ctr_dropout_t drop,
+                         int64_t B, int K, float* dqkv, int dq16, float* drelmean, const uint32_t* keep, b200ctr_dropout_t drop,
                          cudaStream_t st) {
   constexpr int KS = NT <= 10 ? 2 : 4;
   constexpr int NBW = (NT / 2 + KS - 1) / KS, KPA = 16 * NBW * KS, Kp = NT * 8;
@@ -492,11 +498,11 @@ static int ta_launch_bwd(const float* qkv, const float* relmean, int max_len, co
                     : ta_set_smem((const void*)attn_tc_bwd_kernel<NT, KS, false>, smem);
   if (rc) return rc;
   if (use_keep)
-    attn_tc_bwd_kernel<NT, KS, true><<<(unsigned)B, TA_THREADS * KS, smem, st>>>(qkv, relmean, max_len, o, lse, d_o, K, dqkv, drelmean,
-                                                                                 keep, drop);
+    attn_tc_bwd_kernel<NT, KS, true><<<(unsigned)B, TA_THREADS * KS, smem, st>>>(qkv, relmean, max_len, o, lse, d_o, K, dqkv, dq16,
+                                                                                 drelmean, keep, drop);
   else
-    attn_tc_bwd_kernel<NT, KS, false><<<(unsigned)B, TA_THREADS * KS, smem, st>>>(qkv, relmean, max_len, o, lse, d_o, K, dqkv, drelmean,
-                                                                                  nullptr, drop);
+    attn_tc_bwd_kernel<NT, KS, false><<<(unsigned)B, TA_THREADS * KS, smem, st>>>(qkv, relmean, max_len, o, lse, d_o, K, dqkv, dq16,
+                                                                                  drelmean, nullptr, drop);
   return B200CTR_OK;
 }
 
@@ -536,14 +542,14 @@ extern "C" int b200ctr_attn_tc_fwd(const float* qkv, const float* relmean, int m
 }
 
 extern "C" int b200ctr_attn_tc_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
-                                   const float* d_o, int64_t B, int K, int H, int D, float* dqkv, float* drelmean,
+                                   const float* d_o, int64_t B, int K, int H, int D, void* dqkv, int dqkv_bf16, float* drelmean,
                                    const uint32_t* keep, b200ctr_dropout_t drop, void* stream) {
   B200_REQUIRE(qkv && o && lse && d_o && dqkv, B200CTR_E_INVALID_ARG, "attn_tc_bwd: null pointer");
   B200_REQUIRE(D == TA_D && H == TA_H, B200CTR_E_UNSUPPORTED_SHAPE,
                "attn_tc_bwd: only emb_dim=64 with 8 heads of head_dim=8 is built (got D=%d, H=%d)", D, H);
   if (B == 0 || K == 0) return B200CTR_OK;
   int rc;
-#define CALL(NT_) ta_launch_bwd<NT_>(qkv, relmean, max_len, o, lse, d_o, B, K, dqkv, drelmean, keep, drop, as_stream(stream))
+#define CALL(NT_) ta_launch_bwd<NT_>(qkv, relmean, max_len, o, lse, d_o, B, K, (float*)dqkv, dqkv_bf16, drelmean, keep, drop, as_stream(stream))
   TA_DISPATCH(CALL)
 #undef CALL
   if (rc) return rc;

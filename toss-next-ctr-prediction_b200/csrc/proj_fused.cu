@@ -13,6 +13,7 @@
 // of dY re-read MN-major) and gets the BIAS gradient from the same MMAs: the B operand (the activation tile viewed
 // MN-major, N = 64) is extended by 16 columns whose first one is all ones, so accumulator column 64 is colsum(dY).
 #include "tc_common.cuh"
+#include <cuda_bf16.h>
 #include <algorithm>
 
 namespace b200ctr {
@@ -266,7 +267,7 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
                const float* __restrict__ w,        // (NOUT,64)
                const float* __restrict__ resid,    // optional (T,64), added to dX
                int64_t T, float* __restrict__ dy_out /* PRE_NORM: d_s (T,64) */, float* __restrict__ dx,
-               float* __restrict__ wsp /* per-CTA partials */) {
+               float* __restrict__ wsp /* per-CTA partials */, int gin16 /* !PRE_NORM: dY is bf16 (T,NOUT) */) {
   constexpr int NP = NOUT <= 128 ? 128 : 256;                   // dY columns padded to whole 128-row weight-gradient blocks
   constexpr int NBLK = NP / 128;
   constexpr int DY_BYTES = (NP / 8) * PJ_LBO;
@@ -330,13 +331,32 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
     constexpr int NBATCH = 1 + (PRE_NORM ? 0 : PJ_TM * (NOUT / 4) / 256 / 8);
     static_assert(NBATCH % 2 == 0 || NBATCH == 1, "register sets alternate with a static parity");
     auto tile_m0 = [&](int it) { return ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * PJ_TM; };
+    // bf16 dY: a 16-byte chunk already is one core-matrix row (8 bf16), 128 * NOUT / 8 chunks = 4 passes per batch
+    constexpr int C8 = NOUT / 8;
     auto load_batch = [&](int it, int bi, float4 (&va)[4], float4 (&vb)[4]) {
       if (bi == 0) pj_load_pairs<PJ_D, 256>(va, vb, xin, tile_m0(it), T, 0, tid);
-      else pj_load_pairs<NOUT, 256>(va, vb, gin, tile_m0(it), T, (bi - 1) * 4, tid);
+      else if (!gin16) pj_load_pairs<NOUT, 256>(va, vb, gin, tile_m0(it), T, (bi - 1) * 4, tid);
+      else {
+        const int64_t m0 = tile_m0(it);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int q = ((bi - 1) * 4 + k) * 256 + tid, row = q / C8;
+          va[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m0 + row < T)
+            va[k] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const __nv_bfloat16*>(gin) + (m0 + row) * NOUT) + (q - row * C8));
+        }
+      }
     };
     auto store_batch = [&](unsigned char* xs, unsigned char* dys, int bi, const float4 (&va)[4], const float4 (&vb)[4]) {
       if (bi == 0) pj_store_pairs<PJ_D, 256>(xs, va, vb, 0, tid);
-      else pj_store_pairs<NOUT, 256>(dys, va, vb, (bi - 1) * 4, tid);
+      else if (!gin16) pj_store_pairs<NOUT, 256>(dys, va, vb, (bi - 1) * 4, tid);
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int q = ((bi - 1) * 4 + k) * 256 + tid, row = q / C8, c8 = q - row * C8;
+          *reinterpret_cast<float4*>(dys + c8 * PJ_LBO + (row >> 3) * 128 + (row & 7) * 16) = va[k];
+        }
+      }
     };
     float4 ra[2][4], rb[2][4];
     if (n_it > 0) load_batch(0, 0, ra[0], rb[0]);
@@ -507,7 +527,7 @@ static int launch_lin_fwd(const float* x, const float* w, const float* bias, con
 template <int NOUT, bool PRE_NORM>
 static int launch_lin_bwd(const float* gin, const float* s, const float* r, const float* nw, const float* xin, const float* w,
                           const float* resid, int64_t T, float* dy_out, float* dx, float* dw, float* db, float* dn, float* wsp,
-                          cudaStream_t st) {
+                          int gin16, cudaStream_t st) {
   constexpr int NP = NOUT <= 128 ? 128 : 256;
   const size_t smem = (size_t)NOUT * 128 + 2 * (size_t)(PJ_X_BYTES + PJ_ONES_BYTES + (NP / 8) * PJ_LBO) + 8 * PJ_D * 4 + (size_t)(4 * 32 * 36 * 4) +
                       sizeof(PjBwdBars) + 16;
@@ -515,7 +535,7 @@ static int launch_lin_bwd(const float* gin, const float* s, const float* r, cons
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(lin_bwd smem)");
   const int grid = (int)std::min<int64_t>(ceil_div(T, (int64_t)PJ_TM), (int64_t)num_sms());
-  fn<<<grid, PJ_NT, smem, st>>>(gin, s, r, nw, xin, w, resid, T, dy_out, dx, wsp);
+  fn<<<grid, PJ_NT, smem, st>>>(gin, s, r, nw, xin, w, resid, T, dy_out, dx, wsp, gin16);
   cudaError_t le = cudaPeekAtLastError();
   if (le != cudaSuccess) return cuda_fail(le, "lin_bwd_kernel");
   const int n_out = NOUT * 65 + PJ_D;
@@ -559,19 +579,19 @@ extern "C" int b200ctr_outproj_norm_bwd(const float* dx1, const float* s1, const
   B200_REQUIRE(D == PJ_D, B200CTR_E_UNSUPPORTED_SHAPE, "outproj_norm_bwd: D=%d unsupported (64 only)", D);
   B200_REQUIRE(T > 0, B200CTR_E_INVALID_ARG, "outproj_norm_bwd: empty input");
   int rc = launch_lin_bwd<64, true>(dx1, s1, r1, n1w, o, w_out, nullptr, T, ds1_out, d_o, dw_out, db_out, dn1, (float*)workspace,
-                                    as_stream(stream));
+                                    0, as_stream(stream));
   if (rc) return rc;
   B200_LAUNCH_CHECK("lin_bwd_kernel<64,norm>");
   return B200CTR_OK;
 }
 
-extern "C" int b200ctr_inproj_bwd(const float* dqkv, const float* x, const float* w_in, const float* d_resid, int64_t T, int D,
-                                  float* dx, float* dw_in, float* db_in, void* workspace, void* stream) {
+extern "C" int b200ctr_inproj_bwd(const void* dqkv, int dqkv_bf16, const float* x, const float* w_in, const float* d_resid, int64_t T,
+                                  int D, float* dx, float* dw_in, float* db_in, void* workspace, void* stream) {
   B200_REQUIRE(dqkv && x && w_in && dx && dw_in && db_in && workspace, B200CTR_E_INVALID_ARG, "inproj_bwd: null pointer");
   B200_REQUIRE(D == PJ_D, B200CTR_E_UNSUPPORTED_SHAPE, "inproj_bwd: D=%d unsupported (64 only)", D);
   B200_REQUIRE(T > 0, B200CTR_E_INVALID_ARG, "inproj_bwd: empty input");
-  int rc = launch_lin_bwd<192, false>(dqkv, nullptr, nullptr, nullptr, x, w_in, d_resid, T, nullptr, dx, dw_in, db_in, nullptr,
-                                      (float*)workspace, as_stream(stream));
+  int rc = launch_lin_bwd<192, false>((const float*)dqkv, nullptr, nullptr, nullptr, x, w_in, d_resid, T, nullptr, dx, dw_in, db_in,
+                                      nullptr, (float*)workspace, dqkv_bf16, as_stream(stream));
   if (rc) return rc;
   B200_LAUNCH_CHECK("lin_bwd_kernel<192>");
   return B200CTR_OK;

@@ -17,7 +17,7 @@ rowrms_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
   const int64_t b = blockIdx.x;
   const float4* xr = reinterpret_cast<const float4*>(x + b * ldx);
   const float4* w4 = reinterpret_cast<const float4*>(w);
-  float4* zr = reinterpret_cast<float4*>(z + b * ld_z);
+  float4* zr = reinterpret_cast<float4*>(z ? z + b * ld_z : nullptr);
   const int n4 = (int)(N >> 2);
   float ss = 0.f;
   for (int i = threadIdx.x; i < n4; i += RR_THREADS) {
@@ -29,7 +29,7 @@ rowrms_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
   for (int i = threadIdx.x; i < n4; i += RR_THREADS) {
     float4 v = xr[i], ww = __ldg(w4 + i);
     const float4 o = make_float4(ww.x * v.x * rr, ww.y * v.y * rr, ww.z * v.z * rr, ww.w * v.w * rr);
-    zr[i] = o;
+    if (z) zr[i] = o;
     if (z16) {          // bf16 copy for the tensor-core contractions that consume z (row stride N)
       __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
       reinterpret_cast<uint2*>(z16 + b * N)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
@@ -114,29 +114,33 @@ __global__ void fm_grad_kernel(float* __restrict__ A, const float* __restrict__ 
   A[i] = dquad[b * C + c] * 2.f * (s[b * C + c] - A[i]);
 }
 
-// single CTA: m = colsum/B ; h1 = relu(W1 m + b1) ; gate = sigmoid(W2 h1 + b2).  W1 (Cr,C), W2 (C,Cr).
-__global__ void __launch_bounds__(1024)
-se_gate_fwd_kernel(const float* __restrict__ colsum, float inv_B, const float* __restrict__ w1, const float* __restrict__ b1,
-                   const float* __restrict__ w2, const float* __restrict__ b2, int C, int Cr, float* __restrict__ mean,
-                   float* __restrict__ h1, float* __restrict__ gate) {
-  extern __shared__ float sm[];
-  float* ms = sm;            // C
-  float* hs = ms + C;        // Cr
-  for (int c = threadIdx.x; c < C; c += blockDim.x) { float m = colsum[c] * inv_B; ms[c] = m; mean[c] = m; }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int j = warp; j < Cr; j += nw) {
-    float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(w1[(int64_t)j * C + c], ms[c], a);
-    a = warp_sum(a);
-    if (lane == 0) { float h = fmaxf(a + b1[j], 0.f); hs[j] = h; h1[j] = h; }
+// m = colsum/B ; h1 = relu(W1 m + b1) ; gate = sigmoid(W2 h1 + b2).  W1 (Cr,C), W2 (C,Cr).  Two grid-wide launches (the
+// single-CTA version was 0.09 ms of pure latency): A = one warp per hidden unit j, B = one warp per output channel c.
+__global__ void __launch_bounds__(256)
+se_gate_fwd_a_kernel(const float* __restrict__ colsum, float inv_B, const float* __restrict__ w1, const float* __restrict__ b1,
+                     int C, int Cr, float* __restrict__ mean, float* __restrict__ h1) {
+  const int lane = threadIdx.x & 31;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= Cr) return;
+  float a = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float m = colsum[c] * inv_B;
+    if (j == 0) mean[c] = m;
+    a = fmaf(w1[(int64_t)j * C + c], m, a);
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = b2[c];
-    for (int j = 0; j < Cr; ++j) a = fmaf(w2[(int64_t)c * Cr + j], hs[j], a);
-    gate[c] = sigmoidf_(a);
-  }
+  a = warp_sum(a);
+  if (lane == 0) h1[j] = fmaxf(a + b1[j], 0.f);
+}
+__global__ void __launch_bounds__(256)
+se_gate_fwd_b_kernel(const float* __restrict__ h1, const float* __restrict__ w2, const float* __restrict__ b2, int C, int Cr,
+                     float* __restrict__ gate) {
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int j = lane; j < Cr; j += 32) a = fmaf(w2[(int64_t)c * Cr + j], h1[j], a);
+  a = warp_sum(a);
+  if (lane == 0) gate[c] = sigmoidf_(a + b2[c]);
 }
 
 // SE gate backward as two grid-wide launches (the single-CTA version took 0.22 ms of pure latency per step):
@@ -326,13 +330,110 @@ __global__ void headproj_reduce_kernel(const float* __restrict__ partial, int n_
   dV[i] = a;
 }
 
+// ---- the MLP's final Linear(K -> 1) (qnn_alpha.py:85-93): a per-row dot product, not a GEMM ---------------------------
+// forward: logit[b] = h[b, :] . w + bias ; one warp per row, float4 lanes
+__global__ void __launch_bounds__(256)
+lin1_fwd_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ w, const float* __restrict__ bias, int64_t B,
+                int K, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const float4* hr = reinterpret_cast<const float4*>(h + b * ldh);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  float acc = 0.f;
+  for (int i = lane; i < (K >> 2); i += 32) {
+    const float4 a = hr[i], ww = __ldg(w4 + i);
+    acc += a.x * ww.x + a.y * ww.y + a.z * ww.z + a.w * ww.w;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[b] = acc + (bias ? bias[0] : 0.f);
+}
+// backward: dh[b, n] = dl[b] * w[n] * (act[b, n] != 0 ? mask_scale : 0)   (ReLU + dropout mask of the layer's input)
+//           dw[n]   = sum_b dl[b] * act[b, n] ;  db = sum_b dl[b]           (per-CTA partials [K + 1], reduced afterwards)
+// CTA = 256 threads = 8 warps; a warp owns a row per iteration, lane owns K/128 float4 column groups
+constexpr int L1_MAXV = 4;      // K <= 512
+__global__ void __launch_bounds__(256)
+lin1_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ act, int64_t ldact, const float* __restrict__ w, int64_t B,
+                int K, float mask_scale, float* __restrict__ dh, int64_t lddh, float* __restrict__ partial) {
+  extern __shared__ float red[];              // [8][K + 1]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = K >> 7;                       // float4 groups per lane
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  float4 wv[L1_MAXV], acc[L1_MAXV];
+#pragma unroll
+  for (int v = 0; v < L1_MAXV; ++v) {
+    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    wv[v] = v < nv ? __ldg(w4 + v * 32 + lane) : acc[v];
+  }
+  float dsum = 0.f;
+  for (int64_t b = (int64_t)blockIdx.x * 8 + warp; b < B; b += (int64_t)gridDim.x * 8) {
+    const float d = dl[b];
+    const float4* ar = reinterpret_cast<const float4*>(act + b * ldact);
+    float4* dr = reinterpret_cast<float4*>(dh + b * lddh);
+    dsum += d;
+#pragma unroll
+    for (int v = 0; v < L1_MAXV; ++v) {
+      if (v < nv) {
+        const float4 a = ar[v * 32 + lane];
+        const float dm = d * mask_scale;
+        dr[v * 32 + lane] = make_float4(a.x != 0.f ? dm * wv[v].x : 0.f, a.y != 0.f ? dm * wv[v].y : 0.f,
+                                        a.z != 0.f ? dm * wv[v].z : 0.f, a.w != 0.f ? dm * wv[v].w : 0.f);
+        acc[v].x = fmaf(d, a.x, acc[v].x); acc[v].y = fmaf(d, a.y, acc[v].y);
+        acc[v].z = fmaf(d, a.z, acc[v].z); acc[v].w = fmaf(d, a.w, acc[v].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < L1_MAXV; ++v)
+    if (v < nv) *reinterpret_cast<float4*>(red + warp * (K + 4) + (v * 32 + lane) * 4) = acc[v];
+  if (lane == 0) red[8 * (K + 4) + warp] = dsum;
+  __syncthreads();
+  for (int n = threadIdx.x; n <= K; n += 256) {
+    float a = 0.f;
+    for (int wv_ = 0; wv_ < 8; ++wv_) a += n < K ? red[wv_ * (K + 4) + n] : red[8 * (K + 4) + wv_];
+    partial[(int64_t)blockIdx.x * (K + 1) + n] = a;
+  }
+}
+__global__ void lin1_reduce_kernel(const float* __restrict__ partial, int n_part, int K, float* __restrict__ dw, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > K) return;
+  float a = 0.f;
+  for (int c = 0; c < n_part; ++c) a += partial[(int64_t)c * (K + 1) + i];
+  if (i < K) dw[i] = a;
+  else if (db) db[0] = a;
+}
+
 }  // namespace b200ctr
 
 using namespace b200ctr;
 
+extern "C" int b200ctr_lin1_fwd(const float* h, int64_t ldh, const float* w, const float* bias, int64_t B, int K, float* out, void* stream) {
+  B200_REQUIRE(h && w && out, B200CTR_E_INVALID_ARG, "lin1_fwd: null pointer");
+  B200_REQUIRE(K % 4 == 0 && ldh % 4 == 0, B200CTR_E_UNSUPPORTED_SHAPE, "lin1_fwd: K and ldh must be multiples of 4");
+  if (B == 0) return B200CTR_OK;
+  lin1_fwd_kernel<<<(unsigned)ceil_div(B, (int64_t)8), 256, 0, as_stream(stream)>>>(h, ldh, w, bias, B, K, out);
+  B200_LAUNCH_CHECK("lin1_fwd_kernel");
+  return B200CTR_OK;
+}
+extern "C" int64_t b200ctr_lin1_bwd_workspace_bytes(int K) { return (int64_t)num_sms() * 2 * (K + 1) * 4; }
+extern "C" int b200ctr_lin1_bwd(const float* dl, const float* act, int64_t ldact, const float* w, int64_t B, int K, float mask_scale,
+                                float* dh, int64_t lddh, float* dw, float* db, void* workspace, void* stream) {
+  B200_REQUIRE(dl && act && w && dh && dw && workspace, B200CTR_E_INVALID_ARG, "lin1_bwd: null pointer");
+  B200_REQUIRE(K % 128 == 0 && K <= 128 * L1_MAXV && ldact % 4 == 0 && lddh % 4 == 0, B200CTR_E_UNSUPPORTED_SHAPE,
+               "lin1_bwd: K=%d must be a multiple of 128 up to %d", K, 128 * L1_MAXV);
+  B200_REQUIRE(B > 0, B200CTR_E_INVALID_ARG, "lin1_bwd: empty batch");
+  const int grid = (int)std::min<int64_t>(ceil_div(B, (int64_t)8), (int64_t)num_sms() * 2);
+  cudaStream_t st = as_stream(stream);
+  lin1_bwd_kernel<<<grid, 256, (size_t)(8 * (K + 4) + 8) * 4, st>>>(dl, act, ldact, w, B, K, mask_scale, dh, lddh, (float*)workspace);
+  B200_LAUNCH_CHECK("lin1_bwd_kernel");
+  lin1_reduce_kernel<<<(K + 256) / 256, 256, 0, st>>>((const float*)workspace, grid, K, dw, db);
+  B200_LAUNCH_CHECK("lin1_reduce_kernel");
+  return B200CTR_OK;
+}
+
 extern "C" int b200ctr_rowrms_fwd_bf16(const float* x, int64_t ldx, const float* w, float eps, int64_t B, int64_t N, float* z,
                                        int64_t ld_z, float* r, void* z_bf16, void* stream) {
-  B200_REQUIRE(x && w && z && r, B200CTR_E_INVALID_ARG, "rowrms_fwd: null pointer");
+  B200_REQUIRE(x && w && r && (z || z_bf16), B200CTR_E_INVALID_ARG, "rowrms_fwd: null pointer");   // z may be NULL when only the bf16 copy is wanted
   B200_REQUIRE(N % 4 == 0 && ldx % 4 == 0 && ld_z % 4 == 0, B200CTR_E_UNSUPPORTED_SHAPE, "rowrms_fwd: N and leading dims must be multiples of 4");
   if (B == 0) return B200CTR_OK;
   rowrms_fwd_kernel<<<(unsigned)B, RR_THREADS, 0, as_stream(stream)>>>(x, ldx, w, eps, N, z, ld_z, r, (__nv_bfloat16*)z_bf16);
@@ -376,9 +477,11 @@ extern "C" int b200ctr_fm_grad(float* A, const float* s, const float* dquad, int
 extern "C" int b200ctr_se_gate_fwd(const float* colsum, float inv_B, const float* w1, const float* b1, const float* w2,
                                    const float* b2, int C, int Cr, float* mean, float* h1, float* gate, void* stream) {
   B200_REQUIRE(colsum && w1 && b1 && w2 && b2 && mean && h1 && gate, B200CTR_E_INVALID_ARG, "se_gate_fwd: null pointer");
-  B200_REQUIRE((size_t)(C + Cr) * 4 <= 48 * 1024, B200CTR_E_UNSUPPORTED_SHAPE, "se_gate_fwd: C=%d too large", C);
-  se_gate_fwd_kernel<<<1, 1024, (size_t)(C + Cr) * 4, as_stream(stream)>>>(colsum, inv_B, w1, b1, w2, b2, C, Cr, mean, h1, gate);
-  B200_LAUNCH_CHECK("se_gate_fwd_kernel");
+  B200_REQUIRE(C > 0 && Cr > 0, B200CTR_E_INVALID_ARG, "se_gate_fwd: empty");
+  se_gate_fwd_a_kernel<<<(Cr + 7) / 8, 256, 0, as_stream(stream)>>>(colsum, inv_B, w1, b1, C, Cr, mean, h1);
+  B200_LAUNCH_CHECK("se_gate_fwd_a_kernel");
+  se_gate_fwd_b_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(h1, w2, b2, C, Cr, gate);
+  B200_LAUNCH_CHECK("se_gate_fwd_b_kernel");
   return B200CTR_OK;
 }
 
