@@ -326,7 +326,7 @@ def run_cuda(args):
             "retrieve_fwd": ("hbm", gbytes / max(1, args.steps), "retrieve_fwd_warp_kernel (8L + 4D*l + 4D*min(K,l) + 4D + 4D*K + 12K bytes/sample; every logical row use counted once)"),
         }
         traffic = {}
-        tpath = os.path.join(ROOT, "profiles", "r01e_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r01g_traffic.json")
         if os.path.exists(tpath) and args.cfg == "dare_qnn_next" and B == 8192:
             traffic = json.load(open(tpath))
 
