@@ -19,7 +19,10 @@ namespace b200ctr {
 
 constexpr int FM_D = 64;
 constexpr int FM_NT = 13 * 32;
-constexpr int FM_ZBLK = 128 * FM_D * 2;        // 16 KB: one 128-row block of z, bf16 K-major
+// K-direction stride of the 8-column core-matrix groups of a z block: 128 rows x 16 bytes + 16 bytes of padding, so that
+// the 8 chunks of one row (written by 8 neighbouring lanes of the coalesced loader) fall into different banks
+constexpr int FM_ZLBO = 128 * 16 + 16;
+constexpr int FM_ZBLK = 8 * FM_ZLBO;           // one 128-row block of z, bf16 K-major
 constexpr int FM_ZTILE = 2 * FM_ZBLK;          // up to 256 feature rows per sample
 constexpr int FM_CP = 128;                     // column stride of the A accumulators / dA tile
 
@@ -39,24 +42,22 @@ __device__ __forceinline__ float fm_colsum32(float (&v)[32], int lane) {
 }
 
 // z16 rows of sample b (F x 64 bf16, contiguous) -> K-major core matrices, 128-row blocks; rows >= F stay zero (static).
-// Thread t of the 128 loaders owns rows t and t + 128 (no division by the runtime F); the 8 16-byte chunks of a row go
-// to the 8 k-groups.  All loads of a thread are issued before the first store.
+// The sample is a flat list of F * 8 16-byte chunks read in passes of 128 consecutive chunks (512 contiguous bytes per
+// warp instruction = 4 L1 wavefronts; one row per lane cost 32).  All loads of a thread are issued before the first store.
 __device__ __forceinline__ void fm_stage_z(unsigned char* dst, const __nv_bfloat16* __restrict__ z16, int64_t b, int F, int ptid) {
   const uint4* src = reinterpret_cast<const uint4*>(z16 + b * (int64_t)F * FM_D);
-  uint4 v[2][8];
+  const int nq = F * 8;
+  uint4 v[16];
 #pragma unroll
-  for (int blk = 0; blk < 2; ++blk) {
-    const int r = blk * 128 + ptid;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) v[blk][c] = r < F ? __ldg(src + r * 8 + c) : make_uint4(0u, 0u, 0u, 0u);
+  for (int p = 0; p < 16; ++p) {
+    const int q = p * 128 + ptid;
+    v[p] = q < nq ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
   }
 #pragma unroll
-  for (int blk = 0; blk < 2; ++blk) {
-    if (blk * 128 < F) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(dst + blk * FM_ZBLK + (c * 16 + (ptid >> 3)) * 128 + (ptid & 7) * 16) = v[blk][c];
-    }
+  for (int p = 0; p < 16; ++p) {
+    const int q = p * 128 + ptid, row = q >> 3, c = q & 7;
+    if (q < nq)
+      *reinterpret_cast<uint4*>(dst + (row >> 7) * FM_ZBLK + c * FM_ZLBO + ((row & 127) >> 3) * 128 + (row & 7) * 16) = v[p];
   }
 }
 
@@ -168,7 +169,7 @@ fm_fwd_kernel(const __nv_bfloat16* __restrict__ z16, const float* __restrict__ U
       for (int blk = 0; blk < nblk; ++blk)
 #pragma unroll 1
         for (int ks = 0; ks < FM_D / 16; ++ks)
-          umma_bf16(tmem + ib * 256 + blk * FM_CP, make_desc(zs_u + ib * FM_ZTILE + blk * FM_ZBLK + ks * 2 * 2048, 2048, 128),
+          umma_bf16(tmem + ib * 256 + blk * FM_CP, make_desc(zs_u + ib * FM_ZTILE + blk * FM_ZBLK + ks * 2 * FM_ZLBO, FM_ZLBO, 128),
                     make_desc(us_u + ks * 2 * lbo_u, lbo_u, 128), idesc, ks > 0 ? 1u : 0u);
       umma_commit(smem_u32(&bars->acc_full[ib]));
       umma_commit(smem_u32(&bars->z_empty[ib]));
@@ -285,19 +286,14 @@ fm_bwd_kernel(const __nv_bfloat16* __restrict__ z16, const float* __restrict__ U
       if (lane == 0) mbar_arrive(smem_u32(&bars->dz_empty));
       const int64_t row_w = b * F + blk * 128 + q * 32;                 // first row of this warp
       const int rows_valid = max(0, min(32, F - (blk * 128 + q * 32)));
-      if (dz_resid && row_ok) {
-        const float4* rp = reinterpret_cast<const float4*>(dz_resid + (row_w + lane) * FM_D);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 a = rp[j];
-          w[4 * j] = __float_as_uint(__uint_as_float(w[4 * j]) + a.x); w[4 * j + 1] = __float_as_uint(__uint_as_float(w[4 * j + 1]) + a.y);
-          w[4 * j + 2] = __float_as_uint(__uint_as_float(w[4 * j + 2]) + a.z); w[4 * j + 3] = __float_as_uint(__uint_as_float(w[4 * j + 3]) + a.w);
-        }
-      }
-      __syncwarp();        // in-place use (dz == dz_resid): every lane has read its residual row before any row is overwritten
+      // the other branch's gradient is added in the coalesced domain of the store transpose (whole-row loads; a row-per-lane
+      // 16-byte load costs one L1 wavefront per lane).  In-place use (dz == dz_resid) is safe: a warp reads and writes only
+      // its own 32 rows, and each half's residual is loaded before that half is stored.
       float* scr = scr_all + ew * (32 * 36);
-      warp_store_rows<32>(scr, w, dz + row_w * FM_D, FM_D, rows_valid, lane);
-      warp_store_rows<32>(scr, w + 32, dz + row_w * FM_D + 32, FM_D, rows_valid, lane);
+      const float* rres = dz_resid ? dz_resid + row_w * FM_D : nullptr;
+      warp_store_rows_add<32>(scr, w, dz + row_w * FM_D, FM_D, rres, FM_D, rows_valid, lane);
+      warp_store_rows_add<32>(scr, w + 32, dz + row_w * FM_D + 32, FM_D, rres ? rres + 32 : nullptr, FM_D, rows_valid, lane);
+      (void)row_ok;
     }
     // ---- dUcat^T accumulator (rows = c, 64 columns = d) -> this CTA's partial slab ----
     mbar_wait(smem_u32(&bars->done), 0);
@@ -328,7 +324,7 @@ fm_bwd_kernel(const __nv_bfloat16* __restrict__ z16, const float* __restrict__ U
       for (int blk = 0; blk < nblk; ++blk)
 #pragma unroll 1
         for (int ks = 0; ks < FM_D / 16; ++ks)
-          umma_bf16(tmem + A_COL + blk * FM_CP, make_desc(zs_u + ib * FM_ZTILE + blk * FM_ZBLK + ks * 2 * 2048, 2048, 128),
+          umma_bf16(tmem + A_COL + blk * FM_CP, make_desc(zs_u + ib * FM_ZTILE + blk * FM_ZBLK + ks * 2 * FM_ZLBO, FM_ZLBO, 128),
                     make_desc(umn_u + ks * 2 * lbo_u, lbo_u, 128), idesc_a, ks > 0 ? 1u : 0u);
       umma_commit(smem_u32(&bars->a_full));
     };
@@ -348,7 +344,7 @@ fm_bwd_kernel(const __nv_bfloat16* __restrict__ z16, const float* __restrict__ U
 #pragma unroll 1
         for (int ks = 0; ks < 8; ++ks)            // K = 128 feature rows per block; MN views: k-group stride 128 B, mn-group 2048 B
           umma_bf16(tmem + DU_COL, make_desc(da_u + blk * (128 * FM_CP * 2) + ks * 256, 128, 2048),
-                    make_desc(zs_u + ib * FM_ZTILE + blk * FM_ZBLK + ks * 256, 128, 2048), idesc_du, (it > 0 || blk > 0 || ks > 0) ? 1u : 0u);
+                    make_desc(zs_u + ib * FM_ZTILE + blk * FM_ZBLK + ks * 256, 128, FM_ZLBO), idesc_du, (it > 0 || blk > 0 || ks > 0) ? 1u : 0u);
       umma_commit(smem_u32(&bars->da_empty));
       umma_commit(smem_u32(&bars->in_empty[ib]));
       if (it + 1 < n_it) gemm_a(it + 1);
