@@ -186,7 +186,7 @@ def run_reference(args):
             "config": {"workload": workload_name(cfg, cfg["train"]["batch_size"]), "reference_step_batch": args.ref_batch},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_name(cfg, B):
@@ -395,9 +395,18 @@ def run_cuda(args):
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference(args.cfg, 2, 1, sample_B=args.ref_batch)
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -418,6 +427,12 @@ def main():
                     help="matmul precision of the training step: bf16 = the reference's `amp: bf16` autocast mode on the "
                          "tcgen05 tensor cores (fp32 accumulate, fp32 master weights/optimizer); none = exact fp32 CUDA cores")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: libraries that write to fd 1 (NCCL prints its version banner there when
+    # NCCL_DEBUG is set) are sent to stderr, the JSON line goes to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
