@@ -584,25 +584,24 @@ __global__ void ffn_bwd_reduce_kernel(const float* __restrict__ ws, int n_cta, i
                                       float* __restrict__ dn2) {
   const size_t per = (size_t)2 * hidden * FF_D + (size_t)4 * hidden + 8 * FF_D;
   const int HD = hidden * FF_D;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * RED_TX + threadIdx.x, ty = threadIdx.y;
+  float acc = 0.f;
   if (i < 2 * HD) {
-    float acc = 0.f;
-    for (int c = 0; c < n_cta; ++c) acc += ws[(size_t)c * per + i];
-    if (i < HD) dw1[i] = acc;
-    else { const int j = i - HD, h = j / FF_D, d = j % FF_D; dw2[(size_t)d * hidden + h] = acc; }
+    for (int c = ty; c < n_cta; c += RED_TY) acc += ws[(size_t)c * per + i];
   } else if (i < 2 * HD + hidden) {
     const int h = i - 2 * HD;
-    float acc = 0.f;
-    for (int c = 0; c < n_cta; ++c)
-      for (int qq = 0; qq < 4; ++qq) acc += ws[(size_t)c * per + 2 * HD + (size_t)qq * hidden + h];
-    db1[h] = acc;
+    for (int p = ty; p < 4 * n_cta; p += RED_TY) acc += ws[(size_t)(p >> 2) * per + 2 * HD + (size_t)(p & 3) * hidden + h];
   } else if (i < 2 * HD + hidden + 2 * FF_D) {
     const int j = i - 2 * HD - hidden, which = j / FF_D, d = j % FF_D;
-    float acc = 0.f;
-    for (int c = 0; c < n_cta; ++c)
-      for (int w = 0; w < 4; ++w) acc += ws[(size_t)c * per + 2 * HD + (size_t)4 * hidden + which * 4 * FF_D + w * FF_D + d];
-    (which ? dn2 : db2)[d] = acc;
+    for (int p = ty; p < 4 * n_cta; p += RED_TY)
+      acc += ws[(size_t)(p >> 2) * per + 2 * HD + (size_t)4 * hidden + which * 4 * FF_D + (p & 3) * FF_D + d];
   }
+  acc = red_finish_32x8(acc);
+  if (ty != 0) return;
+  if (i < HD) dw1[i] = acc;
+  else if (i < 2 * HD) { const int j = i - HD, h = j / FF_D, d = j % FF_D; dw2[(size_t)d * hidden + h] = acc; }
+  else if (i < 2 * HD + hidden) db1[i - 2 * HD] = acc;
+  else if (i < 2 * HD + hidden + 2 * FF_D) { const int j = i - 2 * HD - hidden; (j / FF_D ? dn2 : db2)[j % FF_D] = acc; }
 }
 
 // =============================================================================================================
@@ -782,7 +781,7 @@ extern "C" int b200ctr_ffn_bwd(const float* dy, const float* s2, const float* r2
   ffn_bwd1_kernel<<<grid, FFW_NT, smem1, st>>>(dy, s2, r2, n2w, x1, w1, b1, w2, T, hidden, ds2, spill, ws, drop);
   B200_LAUNCH_CHECK("ffn_bwd1_kernel");
   const int n_out = 2 * hidden * FF_D + hidden + 2 * FF_D;
-  ffn_bwd_reduce_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(ws, grid, hidden, dw1, db1, dw2, db2, dn2);
+  ffn_bwd_reduce_kernel<<<(n_out + RED_TX - 1) / RED_TX, dim3(RED_TX, RED_TY), 0, st>>>(ws, grid, hidden, dw1, db1, dw2, db2, dn2);
   B200_LAUNCH_CHECK("ffn_bwd_reduce_kernel");
   const size_t smem2 = (size_t)NB * 16384 + (size_t)FF2_STAGES * FF_BLK_BYTES + (size_t)4 * 32 * 68 * 4 + sizeof(Ffn2Bars) + 16;
   e = cudaFuncSetAttribute(ffn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);

@@ -361,12 +361,14 @@ fm_bwd_kernel(const __nv_bfloat16* __restrict__ z16, const float* __restrict__ U
 
 // dUcat[d][c] = sum over CTAs of partial[cta][c][d]
 __global__ void fm_bwd_reduce_kernel(const float* __restrict__ wsp, int n_cta, int C, float* __restrict__ dU) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= FM_D * C) return;
-  const int d = i / C, c = i % C;
+  const int i = blockIdx.x * RED_TX + threadIdx.x, ty = threadIdx.y;       // i = c * 64 + d: coalesced partial reads
+  const bool valid = i < FM_D * C;
+  const int c = i / FM_D, d = i % FM_D;
   float acc = 0.f;
-  for (int k = 0; k < n_cta; ++k) acc += wsp[((size_t)k * FM_CP + c) * FM_D + d];
-  dU[i] = acc;
+  if (valid)
+    for (int k = ty; k < n_cta; k += RED_TY) acc += wsp[((size_t)k * FM_CP + c) * FM_D + d];
+  acc = red_finish_32x8(acc);
+  if (ty == 0 && valid) dU[d * C + c] = acc;
 }
 
 static bool fm_shape_ok(int F, int C, int D) { return D == FM_D && F >= 1 && F <= 256 && C >= 16 && C <= 128 && C % 32 == 0; }
@@ -405,7 +407,7 @@ extern "C" int b200ctr_fm_fused_bwd(const void* z_bf16, const float* Ucat, const
   const int grid = (int)std::min<int64_t>(B, (int64_t)num_sms());
   fm_bwd_kernel<<<grid, FM_NT, smem, st>>>((const __nv_bfloat16*)z_bf16, Ucat, s, dquad, dz_resid, B, F, C, dz, (float*)workspace);
   B200_LAUNCH_CHECK("fm_bwd_kernel");
-  fm_bwd_reduce_kernel<<<(FM_D * C + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, C, dUcat);
+  fm_bwd_reduce_kernel<<<(FM_D * C + RED_TX - 1) / RED_TX, dim3(RED_TX, RED_TY), 0, st>>>((const float*)workspace, grid, C, dUcat);
   B200_LAUNCH_CHECK("fm_bwd_reduce_kernel");
   return B200CTR_OK;
 }

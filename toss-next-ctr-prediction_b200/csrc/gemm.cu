@@ -257,11 +257,12 @@ __global__ void colsum_pass1(const float* __restrict__ X, int64_t ldx, int64_t M
   part[(int64_t)p * N + n] = s;
 }
 __global__ void colsum_pass2(const float* __restrict__ part, int P, int64_t N, float* __restrict__ out) {
-  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+  const int64_t n = (int64_t)blockIdx.x * RED_TX + threadIdx.x;
   float s = 0.f;
-  for (int p = 0; p < P; ++p) s += part[(int64_t)p * N + n];
-  out[n] = s;
+  if (n < N)
+    for (int p = threadIdx.y; p < P; p += RED_TY) s += part[(int64_t)p * N + n];
+  s = red_finish_32x8(s);
+  if (threadIdx.y == 0 && n < N) out[n] = s;
 }
 
 template <int BM, int BN>
@@ -347,12 +348,12 @@ extern "C" int b200ctr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N,
     int P = (int)std::min<int64_t>(std::max<int64_t>(1, ceil_div(M, (int64_t)rows_per_step * 8)), std::min<int64_t>(CS_MAXP, (int64_t)num_sms() * 8));
     colsum_pass1_v4<<<P, 256, 0, st>>>(X, ldx, M, (int)N, (float*)workspace);
     B200_LAUNCH_CHECK("colsum_pass1_v4");
-    colsum_pass2<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>((const float*)workspace, P, N, out);
+    colsum_pass2<<<(unsigned)ceil_div(N, (int64_t)RED_TX), dim3(RED_TX, RED_TY), 0, st>>>((const float*)workspace, P, N, out);
   } else {
     dim3 g1((unsigned)ceil_div(N, 128), CS_PARTS);
     colsum_pass1<<<g1, 128, 0, st>>>(X, ldx, M, N, (float*)workspace);
     B200_LAUNCH_CHECK("colsum_pass1");
-    colsum_pass2<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>((const float*)workspace, CS_PARTS, N, out);
+    colsum_pass2<<<(unsigned)ceil_div(N, (int64_t)RED_TX), dim3(RED_TX, RED_TY), 0, st>>>((const float*)workspace, CS_PARTS, N, out);
   }
   B200_LAUNCH_CHECK("colsum_pass2");
   return B200CTR_OK;

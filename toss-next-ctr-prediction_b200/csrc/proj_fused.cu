@@ -494,19 +494,21 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
 __global__ void lin_bwd_reduce_kernel(const float* __restrict__ wsp, int n_cta, int NP, int NOUT, float* __restrict__ dw,
                                       float* __restrict__ db, float* __restrict__ dn) {
   const size_t per = (size_t)NP * 80 + PJ_D;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * RED_TX + threadIdx.x, ty = threadIdx.y;
+  float acc = 0.f;
+  size_t off = 0;
+  bool valid = false;
+  if (i < NOUT * 65) { off = (size_t)(i / 65) * 80 + (i % 65); valid = true; }
+  else if (i < NOUT * 65 + PJ_D && dn) { off = (size_t)NP * 80 + (i - NOUT * 65); valid = true; }
+  if (valid)
+    for (int k = ty; k < n_cta; k += RED_TY) acc += wsp[(size_t)k * per + off];
+  acc = red_finish_32x8(acc);
+  if (ty != 0 || !valid) return;
   if (i < NOUT * 65) {
     const int n = i / 65, c = i % 65;
-    float acc = 0.f;
-    for (int k = 0; k < n_cta; ++k) acc += wsp[(size_t)k * per + (size_t)n * 80 + c];
     if (c < 64) dw[n * PJ_D + c] = acc;
     else if (db) db[n] = acc;
-  } else if (i < NOUT * 65 + PJ_D && dn) {
-    const int d = i - NOUT * 65;
-    float acc = 0.f;
-    for (int k = 0; k < n_cta; ++k) acc += wsp[(size_t)k * per + (size_t)NP * 80 + d];
-    dn[d] = acc;
-  }
+  } else dn[i - NOUT * 65] = acc;
 }
 
 template <int NOUT, bool POST_NORM>
@@ -539,7 +541,7 @@ static int launch_lin_bwd(const float* gin, const float* s, const float* r, cons
   cudaError_t le = cudaPeekAtLastError();
   if (le != cudaSuccess) return cuda_fail(le, "lin_bwd_kernel");
   const int n_out = NOUT * 65 + PJ_D;
-  lin_bwd_reduce_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(wsp, grid, NP, NOUT, dw, db, PRE_NORM ? dn : nullptr);
+  lin_bwd_reduce_kernel<<<(n_out + RED_TX - 1) / RED_TX, dim3(RED_TX, RED_TY), 0, st>>>(wsp, grid, NP, NOUT, dw, db, PRE_NORM ? dn : nullptr);
   return B200CTR_OK;
 }
 

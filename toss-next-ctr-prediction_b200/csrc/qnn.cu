@@ -323,11 +323,12 @@ headproj_bwd_kernel(const float* __restrict__ quad, const float* __restrict__ di
 }
 
 __global__ void headproj_reduce_kernel(const float* __restrict__ partial, int n_part, int n, float* __restrict__ dV) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const int i = blockIdx.x * RED_TX + threadIdx.x;
   float a = 0.f;
-  for (int c = 0; c < n_part; ++c) a += partial[(int64_t)c * n + i];
-  dV[i] = a;
+  if (i < n)
+    for (int c = threadIdx.y; c < n_part; c += RED_TY) a += partial[(int64_t)c * n + i];
+  a = red_finish_32x8(a);
+  if (threadIdx.y == 0 && i < n) dV[i] = a;
 }
 
 // ---- the MLP's final Linear(K -> 1) (qnn_alpha.py:85-93): a per-row dot product, not a GEMM ---------------------------
@@ -395,10 +396,12 @@ lin1_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ act, int
   }
 }
 __global__ void lin1_reduce_kernel(const float* __restrict__ partial, int n_part, int K, float* __restrict__ dw, float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > K) return;
+  const int i = blockIdx.x * RED_TX + threadIdx.x;
   float a = 0.f;
-  for (int c = 0; c < n_part; ++c) a += partial[(int64_t)c * (K + 1) + i];
+  if (i <= K)
+    for (int c = threadIdx.y; c < n_part; c += RED_TY) a += partial[(int64_t)c * (K + 1) + i];
+  a = red_finish_32x8(a);
+  if (threadIdx.y != 0 || i > K) return;
   if (i < K) dw[i] = a;
   else if (db) db[0] = a;
 }
@@ -426,7 +429,7 @@ extern "C" int b200ctr_lin1_bwd(const float* dl, const float* act, int64_t ldact
   cudaStream_t st = as_stream(stream);
   lin1_bwd_kernel<<<grid, 256, (size_t)(8 * (K + 4) + 8) * 4, st>>>(dl, act, ldact, w, B, K, mask_scale, dh, lddh, (float*)workspace);
   B200_LAUNCH_CHECK("lin1_bwd_kernel");
-  lin1_reduce_kernel<<<(K + 256) / 256, 256, 0, st>>>((const float*)workspace, grid, K, dw, db);
+  lin1_reduce_kernel<<<(K + RED_TX) / RED_TX, dim3(RED_TX, RED_TY), 0, st>>>((const float*)workspace, grid, K, dw, db);
   B200_LAUNCH_CHECK("lin1_reduce_kernel");
   return B200CTR_OK;
 }
@@ -556,7 +559,7 @@ extern "C" int b200ctr_headproj_bwd(const float* quad, const float* dinter, cons
 #undef HP_LAUNCH
   B200_LAUNCH_CHECK("headproj_bwd_kernel");
   const int n = C * P;
-  headproj_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, n, dV);
+  headproj_reduce_kernel<<<(n + RED_TX - 1) / RED_TX, dim3(RED_TX, RED_TY), 0, st>>>((const float*)workspace, grid, n, dV);
   B200_LAUNCH_CHECK("headproj_reduce_kernel");
   return B200CTR_OK;
 }
