@@ -236,9 +236,12 @@ int b200ctr_relmean_bwd(const float* drelmean, int T, int H, float* drel, void* 
  * reference's nn.Linear; dropout element = (row m, column n) (identical to the unfused gemm epilogue, so the
  * backward regenerates the same mask).  s2_out / r2_out (saved for the backward) may be NULL.
  * D == 64, hidden % 64 == 0, hidden <= 512.                                                                 */
+/* keep_bits (optional, b200ctr_ffn_keep_bytes(T, hidden) bytes): the forward stores one dropout keep flag per hidden
+ * activation, b200ctr_ffn_bwd reads them instead of re-hashing; NULL = the backward regenerates the same mask.        */
+int64_t b200ctr_ffn_keep_bytes(int64_t T, int hidden);
 int b200ctr_ffn_fwd(const float* x1, const float* w1, const float* b1, const float* w2, const float* b2,
                     const float* n2w, float eps, int64_t T, int D, int hidden, float* s2_out, float* r2_out,
-                    float* x2_out, b200ctr_dropout_t drop, void* stream);
+                    float* x2_out, void* keep_bits, b200ctr_dropout_t drop, void* stream);
 
 /* Backward of b200ctr_ffn_fwd: recomputes the hidden activation from x1 (dropout mask regenerated), accumulates
  * dW1 / dW2 in TMEM across a persistent loop (deterministic cross-CTA reduction afterwards) and returns
@@ -248,7 +251,7 @@ int64_t b200ctr_ffn_bwd_workspace_bytes(int64_t T, int hidden);
 int b200ctr_ffn_bwd(const float* dy, const float* s2, const float* r2, const float* n2w, const float* x1,
                     const float* w1, const float* b1, const float* w2, int64_t T, int D, int hidden,
                     float* dx1, float* dw1, float* db1, float* dw2, float* db2, float* dn2,
-                    void* workspace, b200ctr_dropout_t drop, void* stream);
+                    void* workspace, const void* keep_bits, b200ctr_dropout_t drop, void* stream);
 
 /* ---- fused attention-side projections on tcgen05 (dare.py:64-66; the `amp: bf16` path) ---------------------------
  * inproj_fwd:        qkv (T,192) = x . w_in^T + b_in                              (w_in (192,64) = mha.in_proj_weight)

@@ -318,10 +318,16 @@ def test_ffn_bwd_fused_matches_unfused(dev, T, hidden, p):
     x1, w1, b1, w2, b2, n2 = (t.to(dev) for t in _ffn_inputs(T, hidden, 9 + T))
     dy = torch.randn(T, 64, generator=torch.Generator().manual_seed(T)).to(dev)
     dr = ops.drop(p, 4321, 55)
-    x2, s2, r2 = ops.ffn_fwd(x1, w1, b1, w2, b2, n2, dr)
+    x2, s2, r2, fkeep = ops.ffn_fwd(x1, w1, b1, w2, b2, n2, dr, save_keep=True)
+    assert (fkeep is not None) == (p > 0)
     z = lambda *s: torch.zeros(*s, device=dev)
     dw1, db1, dw2, db2, dn2 = z(hidden, 64), z(hidden), z(64, hidden), z(64), z(64)
     dx1 = ops.ffn_bwd(dy, s2, r2, n2, x1, w1, b1, w2, dw1, db1, dw2, db2, dn2, dr)
+    if fkeep is not None:      # the stored keep flags reproduce the re-hashed mask: bit-identical gradients
+        k1, kb1, k2, kb2, kn2 = z(hidden, 64), z(hidden), z(64, hidden), z(64), z(64)
+        dx1k = ops.ffn_bwd(dy, s2, r2, n2, x1, w1, b1, w2, k1, kb1, k2, kb2, kn2, dr, keep=fkeep)
+        for a, b in ((dx1k, dx1), (k1, dw1), (kb1, db1), (k2, dw2), (kb2, db2), (kn2, dn2)):
+            assert torch.equal(a, b)
     # unfused composition (hotpath.encoder_layer_bwd before fusion), same dropout stream
     with ops.precision("bf16"):
         pre = torch.empty(T, hidden, device=dev)

@@ -143,16 +143,17 @@ def encoder_layer_fwd(x: Tensor, P: Dict[str, Tensor], i: int, spec: ModelSpec, 
         s1, x1, r1 = ops.add_rmsnorm_fwd(x, h, P[n["n1"]])
     if ops.get_precision() == "bf16" and ops.ffn_fused_ok(spec.ffn_hidden, D):
         # one tcgen05 kernel: the (tokens, ffn_hidden) activation stays on the SM; the backward recomputes it from x1
-        x2, s2, r2 = ops.ffn_fwd(x1, P[n["f1_w"]], P[n["f1_b"]], P[n["f2_w"]], P[n["f2_b"]], P[n["n2"]],
-                                 dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1))
+        x2, s2, r2, fkeep = ops.ffn_fwd(x1, P[n["f1_w"]], P[n["f1_b"]], P[n["f2_w"]], P[n["f2_b"]], P[n["n2"]],
+                                        dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1), save_keep=True)
         pre = fd = None
     else:
+        fkeep = None
         pre = torch.empty((x.shape[0], spec.ffn_hidden), device=x.device, dtype=torch.float32)
         fd = ops.gemm(x1, P[n["f1_w"]], trans_b=True, bias=P[n["f1_b"]], act=ops.ACT_GELU, pre_out=pre,
                       dropout=dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1))
         h2 = ops.gemm(fd, P[n["f2_w"]], trans_b=True, bias=P[n["f2_b"]])
         s2, x2, r2 = ops.add_rmsnorm_fwd(x1, h2, P[n["n2"]])
-    return x2, dict(x=x, relmean=relmean, qkv=qkv, o=o, lse=lse, keep=keep, s1=s1, x1=x1, r1=r1, pre=pre, fd=fd, s2=s2, r2=r2,
+    return x2, dict(x=x, relmean=relmean, qkv=qkv, o=o, lse=lse, keep=keep, fkeep=fkeep, s1=s1, x1=x1, r1=r1, pre=pre, fd=fd, s2=s2, r2=r2,
                     fused_proj=fused_proj)
 
 
@@ -163,7 +164,7 @@ def encoder_layer_bwd(dy: Tensor, sv: dict, P: Dict[str, Tensor], i: int, spec: 
     if sv["pre"] is None:         # fused tcgen05 FFN (forward saved only x1, s2, r2)
         dx1 = ops.ffn_bwd(dy, sv["s2"], sv["r2"], P[n["n2"]], sv["x1"], P[n["f1_w"]], P[n["f1_b"]], P[n["f2_w"]],
                           G(n["f1_w"]), G(n["f1_b"]), G(n["f2_w"]), G(n["f2_b"]), G(n["n2"]),
-                          dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1))
+                          dc(spec.p_ffn, SITE_LAYER0 + 2 * i + 1), keep=sv.get("fkeep"))
     else:
         d_s2 = ops.rmsnorm_bwd(dy, sv["s2"], P[n["n2"]], sv["r2"], G(n["n2"]))
         # FFN second linear
@@ -300,12 +301,17 @@ def qnn_fwd(P: Dict[str, Tensor], spec: ModelSpec, xF: Tensor, dc: DropCtl, B_to
     zin, W0z = (z16, W0_16[:, :N]) if W0_16 is not None else (z, W0[:, :N])
     # the deep (K = F*D) contraction: TMA-fed tcgen05 kernel when both operands are bf16 with K contiguous
     use_kk = W0_16 is not None and ops.gemm_kk_ok(B, W0.shape[0], N)
+    # the interaction part of the first layer: bf16 operands (16-byte async copies) when the bf16 weight copy exists --
+    # converting fp32 operands inside the GEMM's load path made this 1,152-deep product as slow as the 12,800-deep one
+    ig_op, Wi_op = igd, W0[:, N:]
+    if W0_16 is not None and igd.is_contiguous() and (W0.shape[1] - N) % 8 == 0 and N % 8 == 0:
+        ig_op, Wi_op = ops.to_bf16(igd), W0_16[:, N:]
     if len(mlp) == 1:
         hcur = ops.gemm_kk(zin, W0z) if use_kk else ops.gemm(zin, W0z, trans_b=True)
-        logit = ops.gemm(igd, W0[:, N:], trans_b=True, accum=hcur, bias=P[f"qnn.mlp.{mlp[0]}.bias"])
+        logit = ops.gemm(ig_op, Wi_op, trans_b=True, accum=hcur, bias=P[f"qnn.mlp.{mlp[0]}.bias"])
     else:
         hcur = ops.gemm_kk(zin, W0z) if use_kk else ops.gemm(zin, W0z, trans_b=True)
-        hcur = ops.gemm(igd, W0[:, N:], trans_b=True, accum=hcur, bias=P[f"qnn.mlp.{mlp[0]}.bias"], act=ops.ACT_RELU,
+        hcur = ops.gemm(ig_op, Wi_op, trans_b=True, accum=hcur, bias=P[f"qnn.mlp.{mlp[0]}.bias"], act=ops.ACT_RELU,
                         dropout=dc(spec.p_qnn, SITE_MLP0), out=hcur)
         acts.append(hcur)
         for li in range(1, len(mlp) - 1):

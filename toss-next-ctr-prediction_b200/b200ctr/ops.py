@@ -578,21 +578,25 @@ def ffn_fused_ok(hidden: int, D: int = 64) -> bool:
     return D == 64 and hidden % 128 == 0 and 0 < hidden <= 384
 
 
-def ffn_fwd(x1, w1, b1, w2, b2, n2w, dropout: Dropout = NO_DROP, eps=1e-6, save=True):
-    """Fused FFN block (bf16 tensor cores): returns (x2, s2, r2); s2/r2 are None when save=False."""
+def ffn_fwd(x1, w1, b1, w2, b2, n2w, dropout: Dropout = NO_DROP, eps=1e-6, save=True, save_keep=False):
+    """Fused FFN block (bf16 tensor cores): returns (x2, s2, r2) -- s2/r2 are None when save=False -- or, with save_keep,
+    (x2, s2, r2, keep): the dropout keep-flag bits ffn_bwd reads instead of re-hashing (None when dropout is off)."""
     lib = _lib.load()
     T, D = x1.shape
     hidden = w1.shape[0]
     x2 = torch.empty_like(x1)
     s2 = torch.empty_like(x1) if save else None
     r2 = torch.empty((T,), device=x1.device, dtype=torch.float32) if save else None
+    keep = None
+    if save_keep and dropout.p > 0.0:
+        keep = torch.empty((int(lib.b200ctr_ffn_keep_bytes(T, hidden)),), device=x1.device, dtype=torch.uint8)
     _run("ffn_fwd", lib.b200ctr_ffn_fwd, _p(_f32(x1)), _p(w1), _p(b1), _p(w2), _p(b2), _p(n2w), eps, T, D, hidden,
-         _p(s2), _p(r2), _p(x2), dropout, _stream())
+         _p(s2), _p(r2), _p(x2), _p(keep), dropout, _stream())
     _count()
-    return x2, s2, r2
+    return (x2, s2, r2, keep) if save_keep else (x2, s2, r2)
 
 
-def ffn_bwd(dy, s2, r2, n2w, x1, w1, b1, w2, dw1, db1, dw2, db2, dn2, dropout: Dropout = NO_DROP):
+def ffn_bwd(dy, s2, r2, n2w, x1, w1, b1, w2, dw1, db1, dw2, db2, dn2, dropout: Dropout = NO_DROP, keep=None):
     """Backward of ffn_fwd; returns dx1 and overwrites the five parameter-gradient tensors."""
     lib = _lib.load()
     T, D = x1.shape
@@ -603,7 +607,7 @@ def ffn_bwd(dy, s2, r2, n2w, x1, w1, b1, w2, dw1, db1, dw2, db2, dn2, dropout: D
     for t in (dw1, db1, dw2, db2, dn2):
         assert t.is_contiguous()
     _run("ffn_bwd", lib.b200ctr_ffn_bwd, _p(_f32(dy)), _p(s2), _p(r2), _p(n2w), _p(x1), _p(w1), _p(b1), _p(w2), T, D, hidden,
-         _p(dx1), _p(dw1), _p(db1), _p(dw2), _p(db2), _p(dn2), _p(ws), dropout, _stream())
+         _p(dx1), _p(dw1), _p(db1), _p(dw2), _p(db2), _p(dn2), _p(ws), _p(keep), dropout, _stream())
     _count(3)
     return dx1
 

@@ -113,17 +113,22 @@ attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
     const float* ba = bias + (K - 1) - min(qa, K - 1);
     const float* bb = bias + (K - 1) - min(qb, K - 1);
     float ma = -INFINITY, mb = -INFINITY;
+    float pb0 = 0.f, pb1 = 0.f;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const int kc = 8 * j + 2 * t;
+      // rows g+8 see the bias of rows g shifted by one 8-key tile: carry the previous tile's pair instead of reloading
+      const float a0 = ba[kc], a1 = ba[kc + 1];
+      if (j == 0) { pb0 = bb[kc]; pb1 = bb[kc + 1]; }
       if (NT <= 10 && 8 * j + 8 <= K) {          // warp-uniform: whole tile valid, no per-score mask (small kernels only: code size)
-        s[j][0] += ba[kc]; s[j][1] += ba[kc + 1]; s[j][2] += bb[kc]; s[j][3] += bb[kc + 1];
+        s[j][0] += a0; s[j][1] += a1; s[j][2] += pb0; s[j][3] += pb1;
       } else {
-        s[j][0] = kc < K ? s[j][0] + ba[kc] : -INFINITY;
-        s[j][1] = kc + 1 < K ? s[j][1] + ba[kc + 1] : -INFINITY;
-        s[j][2] = kc < K ? s[j][2] + bb[kc] : -INFINITY;
-        s[j][3] = kc + 1 < K ? s[j][3] + bb[kc + 1] : -INFINITY;
+        s[j][0] = kc < K ? s[j][0] + a0 : -INFINITY;
+        s[j][1] = kc + 1 < K ? s[j][1] + a1 : -INFINITY;
+        s[j][2] = kc < K ? s[j][2] + pb0 : -INFINITY;
+        s[j][3] = kc + 1 < K ? s[j][3] + pb1 : -INFINITY;
       }
+      pb0 = a0; pb1 = a1;
       ma = fmaxf(ma, fmaxf(s[j][0], s[j][1]));
       mb = fmaxf(mb, fmaxf(s[j][2], s[j][3]));
     }
@@ -144,8 +149,8 @@ attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
         const uint32_t ha = drop_pair_hash(keya, (uint32_t)(4 * j + t)), hb = drop_pair_hash(keyb, (uint32_t)(4 * j + t));
         const bool k0 = (ha & 0xffffu) >= dctx.thr, k1 = (ha >> 16) >= dctx.thr;
         const bool k2 = (hb & 0xffffu) >= dctx.thr, k3 = (hb >> 16) >= dctx.thr;
-        p0 = k0 ? p0 * dctx.inv : 0.f; p1 = k1 ? p1 * dctx.inv : 0.f;
-        p2 = k2 ? p2 * dctx.inv : 0.f; p3 = k3 ? p3 * dctx.inv : 0.f;
+        p0 = k0 ? p0 : 0.f; p1 = k1 ? p1 : 0.f;           // the 1/(1-p) scale is applied once, to the output row
+        p2 = k2 ? p2 : 0.f; p3 = k3 ? p3 : 0.f;
         const uint32_t sh = 4 * (j & 7);
         kw[j >> 3] |= (k0 ? 1u << sh : 0u) | (k1 ? 2u << sh : 0u) | (k2 ? 4u << sh : 0u) | (k3 ? 8u << sh : 0u);
       }
@@ -158,12 +163,12 @@ attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
       for (int w = 0; w < NW; ++w) keep[ta_keep_index(b, h, MT, i, NW, w, lane)] = kw[w];
     }
     if (qa < K) {
-      const float inv = 1.f / la;
+      const float inv = dctx.inv / la;
       *reinterpret_cast<float2*>(o + (b * K + qa) * (int64_t)TA_D + h * 8 + 2 * t) = make_float2(oc[0] * inv, oc[1] * inv);
       if (t == 0) lse[(b * TA_H + h) * (int64_t)K + qa] = (ma + log2f(la)) * TA_LN2;       // natural-log units
     }
     if (qb < K) {
-      const float inv = 1.f / lb;
+      const float inv = dctx.inv / lb;
       *reinterpret_cast<float2*>(o + (b * K + qb) * (int64_t)TA_D + h * 8 + 2 * t) = make_float2(oc[2] * inv, oc[3] * inv);
       if (t == 0) lse[(b * TA_H + h) * (int64_t)K + qb] = (mb + log2f(lb)) * TA_LN2;
     }
@@ -479,7 +484,7 @@ static int ta_set_smem(const void* fn, size_t bytes) {
 template <int NT>
 static int ta_launch_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, float* o, float* lse,
                          uint32_t* keep, b200ctr_dropout_t drop, cudaStream_t st) {
-  const size_t smem = ((size_t)2 * NT * 8 * TA_RS + 2 * K) * 4;
+  const size_t smem = ((size_t)2 * NT * 8 * TA_RS + K + NT * 8 + 8) * 4;   // bias: masked lanes read (unused) entries up to K - 1 + Kp
   int rc = ta_set_smem((const void*)attn_tc_fwd_kernel<NT>, smem);
   if (rc) return rc;
   attn_tc_fwd_kernel<NT><<<(unsigned)B, TA_THREADS, smem, st>>>(qkv, relmean, max_len, K, o, lse, keep, drop);

@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(FFW_NT, 1)
 ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const float* __restrict__ b1,
                const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ n2w, float eps,
                int64_t T, int hidden, float* __restrict__ s2_out, float* __restrict__ r2_out, float* __restrict__ x2_out,
-               b200ctr_dropout_t drop) {
+               uint16_t* __restrict__ keep, b200ctr_dropout_t drop) {
+  // keep (optional): one 16-bit word of dropout keep flags per (tile, 64-wide chunk, 16-column quarter, token row) --
+  // exactly what one epilogue lane produces -- so that the backward tests bits instead of re-hashing
   extern __shared__ __align__(128) unsigned char smem[];
   const int NC = hidden / FF_HC;
   unsigned char* w1s = smem;
@@ -222,7 +224,8 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
     uint32_t g = 0;
     const DropCtx dctx = drop_ctx(drop);
     for (int it = 0; it < n_it; ++it) {
-      const int64_t m = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM + r;
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+      const int64_t m = tile * FF_TM + r;
       const uint32_t rkey = dctx.on ? drop_row_key(drop, (uint64_t)m) : 0u;
       for (int c = 0; c < NC; ++c, ++g) {
         mbar_wait(smem_u32(&bars->p_full), g & 1);
@@ -234,17 +237,20 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
         if (lane == 0) mbar_arrive(smem_u32(&bars->p_empty));
         const int n0 = c * FF_HC + part * 16;
         uint32_t pk[8];
+        uint32_t kb = 0u;
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
           float f0 = ffn_gelu(__uint_as_float(v[j]) + b1s[n0 + j]);
           float f1 = ffn_gelu(__uint_as_float(v[j + 1]) + b1s[n0 + j + 1]);
           if (dctx.on) {
-            float d0, d1;
-            drop_pair(dctx, rkey, (uint32_t)(n0 + j) >> 1, d0, d1);
-            f0 *= d0; f1 *= d1;
+            const uint32_t h = drop_pair_hash(rkey, (uint32_t)(n0 + j) >> 1);
+            const bool k0 = (h & 0xffffu) >= dctx.thr, k1 = (h >> 16) >= dctx.thr;
+            f0 = k0 ? f0 * dctx.inv : 0.f; f1 = k1 ? f1 * dctx.inv : 0.f;
+            kb |= (k0 ? 1u << j : 0u) | (k1 ? 2u << j : 0u);
           }
           pk[j >> 1] = pack_bf16(f0, f1);
         }
+        if (keep && dctx.on) keep[((tile * NC + c) * 4 + part) * FF_TM + r] = (uint16_t)kb;
         const int fb = g & 1;
         if (g >= 2) mbar_wait(smem_u32(&bars->fd_empty[fb]), ((g >> 1) - 1) & 1);
         unsigned char* dst = fds + fb * FF_FD_BYTES;
@@ -359,12 +365,13 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
   return v[0];
 }
 
+template <bool KEEP>
 __global__ void __launch_bounds__(FFW_NT, 1)
 ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, const float* __restrict__ r2,
                 const float* __restrict__ n2w, const float* __restrict__ x1, const float* __restrict__ w1,
                 const float* __restrict__ b1, const float* __restrict__ w2, int64_t T, int hidden,
                 float* __restrict__ ds2_out, unsigned char* __restrict__ dpre_spill, float* __restrict__ ws,
-                b200ctr_dropout_t drop) {
+                const uint16_t* __restrict__ keep, b200ctr_dropout_t drop) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int NC = hidden / FF_HC, NB = hidden / 128;
   unsigned char* w1s = smem;
@@ -459,8 +466,10 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
     for (int it = 0; it < n_it; ++it) {
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
       const int64_t m = tile * FF_TM + r;
-      const uint32_t rkey = dctx.on ? drop_row_key(drop, (uint64_t)m) : 0u;
+      const uint32_t rkey = (!KEEP && dctx.on) ? drop_row_key(drop, (uint64_t)m) : 0u;
       for (int c = 0; c < NC; ++c, ++g) {
+        uint32_t kb = 0u;
+        if (KEEP) kb = keep[((tile * NC + c) * 4 + part) * FF_TM + r];      // issued before the wait: latency hidden
         mbar_wait(smem_u32(&bars->pq_full), g & 1);
         tc_fence_after();
         uint32_t pv[16], qv[16];
@@ -476,7 +485,8 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
           float dsc[2] = {1.f, 1.f};
-          if (dctx.on) drop_pair(dctx, rkey, (uint32_t)(n0 + j) >> 1, dsc[0], dsc[1]);
+          if (KEEP) { dsc[0] = (kb & (1u << j)) ? dctx.inv : 0.f; dsc[1] = (kb & (2u << j)) ? dctx.inv : 0.f; }
+          else if (dctx.on) drop_pair(dctx, rkey, (uint32_t)(n0 + j) >> 1, dsc[0], dsc[1]);
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const float pre = __uint_as_float(pv[j + u]) + b1s[n0 + j + u];
@@ -733,7 +743,7 @@ using namespace b200ctr;
 
 extern "C" int b200ctr_ffn_fwd(const float* x1, const float* w1, const float* b1, const float* w2, const float* b2,
                                const float* n2w, float eps, int64_t T, int D, int hidden, float* s2_out, float* r2_out,
-                               float* x2_out, b200ctr_dropout_t drop, void* stream) {
+                               float* x2_out, void* keep_bits, b200ctr_dropout_t drop, void* stream) {
   B200_REQUIRE(x1 && w1 && b1 && w2 && b2 && n2w && x2_out, B200CTR_E_INVALID_ARG, "ffn_fwd: null pointer");
   B200_REQUIRE(D == FF_D, B200CTR_E_UNSUPPORTED_SHAPE, "ffn_fwd: D=%d unsupported (64 only)", D);
   B200_REQUIRE(hidden > 0 && hidden % FF_HC == 0 && hidden <= 512, B200CTR_E_UNSUPPORTED_SHAPE,
@@ -744,9 +754,15 @@ extern "C" int b200ctr_ffn_fwd(const float* x1, const float* w1, const float* b1
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ffn_fwd smem)");
   const int64_t tiles = ceil_div(T, (int64_t)FF_TM);
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)num_sms());
-  ffn_fwd_kernel<<<grid, FFW_NT, smem, as_stream(stream)>>>(x1, w1, b1, w2, b2, n2w, eps, T, hidden, s2_out, r2_out, x2_out, drop);
+  ffn_fwd_kernel<<<grid, FFW_NT, smem, as_stream(stream)>>>(x1, w1, b1, w2, b2, n2w, eps, T, hidden, s2_out, r2_out, x2_out,
+                                                            (uint16_t*)keep_bits, drop);
   B200_LAUNCH_CHECK("ffn_fwd_kernel");
   return B200CTR_OK;
+}
+
+extern "C" int64_t b200ctr_ffn_keep_bytes(int64_t T, int hidden) {
+  if (T <= 0 || hidden <= 0) return 0;
+  return ceil_div(T, (int64_t)FF_TM) * FF_TM * (hidden / 16) * 2;
 }
 
 extern "C" int64_t b200ctr_ffn_bwd_workspace_bytes(int64_t T, int hidden) {
@@ -760,7 +776,7 @@ extern "C" int64_t b200ctr_ffn_bwd_workspace_bytes(int64_t T, int hidden) {
 extern "C" int b200ctr_ffn_bwd(const float* dy, const float* s2, const float* r2, const float* n2w, const float* x1,
                                const float* w1, const float* b1, const float* w2, int64_t T, int D, int hidden,
                                float* dx1, float* dw1, float* db1, float* dw2, float* db2, float* dn2,
-                               void* workspace, b200ctr_dropout_t drop, void* stream) {
+                               void* workspace, const void* keep_bits, b200ctr_dropout_t drop, void* stream) {
   B200_REQUIRE(dy && s2 && r2 && n2w && x1 && w1 && b1 && w2 && dx1 && dw1 && db1 && dw2 && db2 && dn2 && workspace,
                B200CTR_E_INVALID_ARG, "ffn_bwd: null pointer");
   B200_REQUIRE(D == FF_D, B200CTR_E_UNSUPPORTED_SHAPE, "ffn_bwd: D=%d unsupported (64 only)", D);
@@ -776,9 +792,12 @@ extern "C" int b200ctr_ffn_bwd(const float* dy, const float* s2, const float* r2
   const size_t per_cta = (size_t)2 * hidden * FF_D + (size_t)4 * hidden + 8 * FF_D;
   float* ds2 = ws + per_cta * (size_t)num_sms();
   const size_t smem1 = (size_t)2 * (hidden / FF_HC) * FF_WCHUNK + 2 * FF_IN_BYTES + 2 * FF_BLK_BYTES + (size_t)hidden * 4 + sizeof(FfnBwdBars) + 16;
-  cudaError_t e = cudaFuncSetAttribute(ffn_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+  const bool use_keep = keep_bits != nullptr && drop.p > 0.f;
+  auto fn1 = use_keep ? ffn_bwd1_kernel<true> : ffn_bwd1_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ffn_bwd1 smem)");
-  ffn_bwd1_kernel<<<grid, FFW_NT, smem1, st>>>(dy, s2, r2, n2w, x1, w1, b1, w2, T, hidden, ds2, spill, ws, drop);
+  fn1<<<grid, FFW_NT, smem1, st>>>(dy, s2, r2, n2w, x1, w1, b1, w2, T, hidden, ds2, spill, ws,
+                                   use_keep ? (const uint16_t*)keep_bits : nullptr, drop);
   B200_LAUNCH_CHECK("ffn_bwd1_kernel");
   const int n_out = 2 * hidden * FF_D + hidden + 2 * FF_D;
   ffn_bwd_reduce_kernel<<<(n_out + RED_TX - 1) / RED_TX, dim3(RED_TX, RED_TY), 0, st>>>(ws, grid, hidden, dw1, db1, dw2, db2, dn2);
