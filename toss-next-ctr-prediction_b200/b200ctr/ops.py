@@ -122,7 +122,7 @@ def _split_k_for(M: int, N: int, K: int) -> int:
     tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
     if tiles >= 148 or K < 2048:
         return 1
-    return int(max(1, min(296 // tiles, K // 512, 256)))
+    return int(max(1, min(296 // tiles, K // 256, 256)))
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, out: Optional[torch.Tensor] = None,
