@@ -208,7 +208,7 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   const float* T = tables[c];
   float* dT = dtables[c];
   float* dW = dprojs[c];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   for (int i = tid; i < CAT_D * dc; i += blockDim.x) Ws[i / dc][i % dc] = W[i];
   // this thread's dW elements: e = tid + k*256 < 64*dc  (<= 16 of them)
   float acc[16];
@@ -254,15 +254,15 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
         acc[k] = a;
       }
     }
-    // dE[id][j] += sum_n W[n][j] * g[n]   (warp per sample, lane per j)
-    for (int s = warp; s < CATB_TS; s += 8) {
+    // dE[id][j] += sum_n W[n][j] * g[s][n]   (thread per (sample, j) pair: with a warp per sample and a lane per j, 24 of the
+    // 32 lanes idled on the 8-wide tables -- 24 of the 35 columns -- and this loop was two thirds of the kernel's LDS traffic)
+    for (int pr = tid; pr < CATB_TS * dc; pr += blockDim.x) {
+      const int s = pr / dc, j = pr - s * dc;
       if (b0 + s >= B) continue;
-      for (int j = lane; j < dc; j += 32) {
-        float a = 0.f;
+      float a = 0.f;
 #pragma unroll 8
-        for (int n = 0; n < CAT_D; ++n) a = fmaf(Ws[n][j], gs[s][n], a);
-        atomicAdd(dT + ids[s] * dc + j, a);
-      }
+      for (int n = 0; n < CAT_D; ++n) a = fmaf(Ws[n][j], gs[s][n], a);
+      atomicAdd(dT + ids[s] * dc + j, a);
     }
   }
 #pragma unroll
