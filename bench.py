@@ -312,15 +312,23 @@ def run_cuda(args):
                 if tag.startswith(fn_ + "["):
                     M_, N_, K_ = tag[len(fn_) + 1:-3].split("x")
                     gemm_flops[fn_] += 2.0 * int(M_) * int(N_) * int(K_) * n
+        keep_b = 4.0 * B * 8 * ((Kk + 15) // 16) * ((2 * ((Kk + 15) // 16) + 7) // 8) * 32      # attention keep-bit words per launch
         models = {   # family -> (bound, work per launch [FLOP or byte], description)
-            "attn_tc_bwd": ("tensor", 10.0 * Kk * Kk * D * B, "attn_tc_bwd_kernel (mma.sync TF32/bf16, head_dim 8; one pass: S, dP, dQ, dK, dV = 10 K^2 D FLOP/sample)"),
-            "attn_tc_fwd": ("tensor", 4.0 * Kk * Kk * D * B, "attn_tc_fwd_kernel (mma.sync TF32: QK^T and PV = 4 K^2 D FLOP/sample)"),
-            "ffn_fwd": ("tensor", 4.0 * T * D * hid, "ffn_fwd_kernel (tcgen05 fused FFN block: 2 contractions of T x 64 x ffn_hidden)"),
-            "ffn_bwd": ("tensor", 8.0 * T * D * hid, "ffn_bwd1/ffn_bwd2 (tcgen05 fused FFN backward: 4 algorithmic contractions; the recompute is not counted)"),
+            # kernels with a FLOP and a byte model: (flops, bytes); the BINDING roof (the larger time floor) is reported
+            "attn_tc_bwd": ("both", (10.0 * Kk * Kk * D * B, T * (4.0 * 3 * D + 4.0 * D + 4.0 * D + 2.0 * 3 * D) + 4.0 * B * 8 * Kk + keep_b),
+                            "attn_tc_bwd_kernel (mma.sync TF32/bf16, head_dim 8; one pass: S, dP, dQ, dK, dV = 10 K^2 D FLOP/sample; "
+                            "qkv, o, d_o, lse, keep bits in, bf16 dqkv out)"),
+            "attn_tc_fwd": ("both", (4.0 * Kk * Kk * D * B, T * (4.0 * 3 * D + 4.0 * D) + 4.0 * B * 8 * Kk + keep_b),
+                            "attn_tc_fwd_kernel (mma.sync TF32: QK^T and PV = 4 K^2 D FLOP/sample; qkv in, o, lse, keep bits out)"),
+            "ffn_fwd": ("both", (4.0 * T * D * hid, T * (4.0 * D * 3 + 4.0 + hid / 8.0)),
+                        "ffn_fwd_kernel (tcgen05 fused FFN block: 2 contractions of T x 64 x ffn_hidden; x1 in, s2, x2, r2, keep bits out)"),
+            "ffn_bwd": ("both", (8.0 * T * D * hid, T * (4.0 * D * 4 + 4.0 + hid / 8.0)),
+                        "ffn_bwd1/ffn_bwd2 (tcgen05 fused FFN backward: 4 algorithmic contractions, the recompute and the internal bf16 "
+                        "dpre spill are not counted; dy, s2, x1, r2, keep bits in, dx1 out)"),
             "inproj_fwd": ("hbm", 4.0 * T * (D + 3 * D), "lin_fwd_kernel<192> (x in, qkv out)"),
             "outproj_norm_fwd": ("hbm", 4.0 * T * D * 4 + 4.0 * T, "lin_fwd_kernel<64,norm> (o, x in; s1, x1, r1 out)"),
             "outproj_norm_bwd": ("hbm", 4.0 * T * D * 5, "lin_bwd_kernel<64,norm> (dx1, s1, o in; d_s1, d_o out)"),
-            "inproj_bwd": ("hbm", 4.0 * T * (3 * D + 3 * D), "lin_bwd_kernel<192> (dqkv, x, d_s1 in; dx out)"),
+            "inproj_bwd": ("hbm", 2.0 * T * 3 * D + 4.0 * T * 3 * D, "lin_bwd_kernel<192> (bf16 dqkv, x, d_s1 in; dx out)"),
             "fm_fused_fwd": ("hbm", 2.0 * B * F_all * D, "fm_fwd_kernel (bf16 z in)"),
             "fm_fused_bwd": ("hbm", B * F_all * D * (2.0 + 4.0 + 4.0), "fm_bwd_kernel (bf16 z, fp32 dz in / out)"),
             "retrieve_fwd": ("hbm", gbytes / max(1, args.steps), "retrieve_fwd_warp_kernel (8L + 4D*l + 4D*min(K,l) + 4D + 4D*K + 12K bytes/sample; every logical row use counted once)"),
@@ -343,24 +351,39 @@ def run_cuda(args):
                         "traffic": None, "peak_source": f"{pk['src']} bf16 sustained", "launches": n, "avg_launch_ms": t / n,
                         "share_of_step": t / tot_ms}
             bound, work, desc = models[name]
+            other = None
+            if bound == "both":          # pick the binding roof: the one with the larger time floor
+                fl, by = work
+                t_fl, t_by = fl / (pk["tf_sus"] * 1e12), by / (pk["hbm"] * 1e9)
+                if t_by >= t_fl:
+                    bound, work = "hbm", by
+                    other = {"bound": "tensor", "frac": fl * n / (t * 1e-3) / 1e12 / pk["tf_sus"]}
+                else:
+                    bound, work = "tensor", fl
+                    other = {"bound": "hbm", "frac": by * n / (t * 1e-3) / 1e9 / pk["hbm"]}
             tr = traffic.get("ffn_bwd1" if name == "ffn_bwd" else name, {}).get("traffic_bytes_per_launch")
             if name == "ffn_bwd" and tr is not None:
                 tr += traffic.get("ffn_bwd2", {}).get("traffic_bytes_per_launch", 0)
             if bound == "tensor":
                 ach = work * n / (t * 1e-3) / 1e12
-                return {"kernel": desc, "bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
-                        "traffic": tr, "peak_source": f"{pk['src']} bf16 sustained", "launches": n, "avg_launch_ms": t / n,
-                        "share_of_step": t / tot_ms}
-            ach = work * n / (t * 1e-3) / 1e9
-            return {"kernel": desc, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                    "frac_of_nominal_8TBs": ach / 8000.0, "traffic": tr, "peak_source": f"{pk['src']} HBM copy", "launches": n,
-                    "avg_launch_ms": t / n, "share_of_step": t / tot_ms}
+                out = {"kernel": desc, "bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
+                       "traffic": tr, "peak_source": f"{pk['src']} bf16 sustained", "launches": n, "avg_launch_ms": t / n,
+                       "share_of_step": t / tot_ms}
+            else:
+                ach = work * n / (t * 1e-3) / 1e9
+                out = {"kernel": desc, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                       "frac_of_nominal_8TBs": ach / 8000.0, "traffic": tr, "peak_source": f"{pk['src']} HBM copy", "launches": n,
+                       "avg_launch_ms": t / n, "share_of_step": t / tot_ms}
+            if other is not None:
+                out["non_binding_roof"] = other
+            return out
 
         modelled = [k for k, _ in top if k in models or k in ("gemm", "gemm_bf16", "gemm_tma")]
         roof = roof_of(modelled[0]) if modelled else None
         if roof is not None and modelled[0].startswith("attn_tc"):
-            roof["note"] = ("issue-bound on the exp / dropout-hash work per score (ncu: SM throughput 51-73 %, tensor pipe 6-9 %), "
-                            "not on the tensor pipe: head_dim 8 gives 2 MMAs per 128 scores")
+            roof["note"] = ("HBM is the binding roof (head_dim 8: 2 MMAs per 128 scores, the tensor floor is 9x lower); the kernel itself is "
+                            "bound by instruction issue and the L1 data pipe on the exp / mask work per score (ncu: issue 49-74 %, "
+                            "L1 wavefronts 44-55 %)")
         kernels = [dict(roof_of(k), family=k) for k in modelled[:14]]
         gather = roof_of("retrieve_fwd") if "retrieve_fwd" in fam else None
         line = {
