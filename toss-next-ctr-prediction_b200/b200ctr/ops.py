@@ -757,9 +757,9 @@ def fm_fused_bwd(z16, Ucat, s, dquad, dz_resid, B, F, dz_out=None):
 
 def headproj_ok(H: int, R: int, P: int) -> bool:
     C = H * R
-    if R > 32 or H * P > 1536 or C > 384 or C <= 0:
+    if R > 32 or H * P > 1536 or C > 384 or C <= 0 or (H * P) % 4 or C % 4:
         return False
-    return (C * (P + 1) + 4 * (H * P + C) + 4 * C) * 4 <= 200 * 1024
+    return (C * (P + 1) + 4 + 2 * 4 * (H * P + C) + 4 * C) * 4 <= 200 * 1024
 
 
 def headproj_fwd(quad, V):

@@ -255,8 +255,9 @@ headproj_bwd_kernel(const float* __restrict__ quad, const float* __restrict__ di
   extern __shared__ float hp_sm[];
   const int C = H * R, HPd = H * P, PS = P + 1;
   float* Vs = hp_sm;                    // C x (P+1)
-  float* ds = Vs + C * PS;              // HP_RB x H*P : dinter rows
-  float* qs = ds + HP_RB * HPd;         // HP_RB x C   : quad rows
+  const int vs_floats = (C * PS + 3) & ~3;
+  float* ds_all = Vs + vs_floats;       // [2] x HP_RB x H*P : dinter rows (double-buffered, filled by cp.async)
+  float* qs_all = ds_all + 2 * HP_RB * HPd;   // [2] x HP_RB x C : quad rows
   for (int i = threadIdx.x; i < C * P; i += HP_THREADS) Vs[(i / P) * PS + i % P] = V[i];
   float acc[HP_MAXC][RMAX];
 #pragma unroll
@@ -265,17 +266,41 @@ headproj_bwd_kernel(const float* __restrict__ quad, const float* __restrict__ di
     for (int r = 0; r < RMAX; ++r) acc[k][r] = 0.f;
   int parts = 1;                        // threads cooperating on one dquad element: largest power of two <= min(32, threads/C)
   while (parts * 2 <= 32 && parts * 2 * C <= HP_THREADS) parts *= 2;
-  for (int64_t b0 = (int64_t)blockIdx.x * HP_RB; b0 < B; b0 += (int64_t)gridDim.x * HP_RB) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < HP_RB * HPd; i += HP_THREADS) {
-      const int64_t b = b0 + i / HPd;
-      ds[i] = b < B ? dinter[b * HPd + i % HPd] : 0.f;
+  // The rows of iteration i+1 are copied into the other buffer (16-byte cp.async, zero fill past the batch) while
+  // iteration i computes: with one CTA per SM the exposed load latency of every 4-row iteration was most of the kernel.
+  auto issue = [&](int64_t b0, int buf) {
+    float* dsb = ds_all + buf * HP_RB * HPd;
+    float* qsb = qs_all + buf * HP_RB * C;
+    const int d4 = HPd >> 2, c4n = C >> 2;
+    for (int i = threadIdx.x; i < HP_RB * d4; i += HP_THREADS) {
+      const int rb = i / d4, c4 = i - rb * d4;
+      const int64_t b = b0 + rb;
+      const float* src = dinter + (b < B ? b : 0) * HPd + c4 * 4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dsb + rb * HPd + c4 * 4)),
+                   "l"(src), "r"(b < B ? 16 : 0) : "memory");
     }
-    for (int i = threadIdx.x; i < HP_RB * C; i += HP_THREADS) {
-      const int64_t b = b0 + i / C;
-      qs[i] = b < B ? quad[b * C + i % C] : 0.f;
+    for (int i = threadIdx.x; i < HP_RB * c4n; i += HP_THREADS) {
+      const int rb = i / c4n, c4 = i - rb * c4n;
+      const int64_t b = b0 + rb;
+      const float* src = quad + (b < B ? b : 0) * C + c4 * 4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(qsb + rb * C + c4 * 4)),
+                   "l"(src), "r"(b < B ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int64_t bstep = (int64_t)gridDim.x * HP_RB;
+  int buf = 0;
+  if ((int64_t)blockIdx.x * HP_RB < B) issue((int64_t)blockIdx.x * HP_RB, 0);
+  for (int64_t b0 = (int64_t)blockIdx.x * HP_RB; b0 < B; b0 += bstep, buf ^= 1) {
+    if (b0 + bstep < B) {
+      issue(b0 + bstep, buf ^ 1);                                  // the buffer the previous iteration finished reading
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const float* ds = ds_all + buf * HP_RB * HPd;
+    const float* qs = qs_all + buf * HP_RB * C;
 #pragma unroll
     for (int k = 0; k < HP_MAXC; ++k) {
       const int c = threadIdx.x + k * HP_THREADS;
@@ -308,6 +333,7 @@ headproj_bwd_kernel(const float* __restrict__ quad, const float* __restrict__ di
         if (part == 0 && b0 + rb < B) dquad[(b0 + rb) * C + cc] = t;
       }
     }
+    __syncthreads();          // every thread is done with this buffer before the next iteration's copies overwrite it
   }
   float* out = dv_partial + (int64_t)blockIdx.x * C * P;
 #pragma unroll
@@ -522,7 +548,8 @@ extern "C" int b200ctr_se_apply_bwd(const float* dout, int64_t ld_dout, const fl
 static bool headproj_ok(int H, int R, int P) {
   const int C = H * R;
   if (H <= 0 || R <= 0 || P <= 0 || R > 32 || H * P > HP_MAXC * HP_THREADS || C > HP_THREADS) return false;
-  return ((size_t)C * (P + 1) + (size_t)HP_RB * (H * P + C) + 4 * C) * 4 <= 200 * 1024;
+  if ((H * P) % 4 != 0 || C % 4 != 0) return false;                       // 16-byte cp.async rows in the backward
+  return ((size_t)C * (P + 1) + 4 + (size_t)2 * HP_RB * (H * P + C) + 4 * C) * 4 <= 200 * 1024;
 }
 
 extern "C" int b200ctr_headproj_fwd(const float* quad, const float* V, int64_t B, int H, int R, int P, float* inter, void* stream) {
@@ -546,7 +573,7 @@ extern "C" int b200ctr_headproj_bwd(const float* quad, const float* dinter, cons
   B200_REQUIRE(headproj_ok(H, R, P), B200CTR_E_UNSUPPORTED_SHAPE, "headproj_bwd: heads=%d rank=%d proj=%d unsupported", H, R, P);
   B200_REQUIRE(B > 0, B200CTR_E_INVALID_ARG, "headproj_bwd: empty batch");
   const int C = H * R;
-  const size_t smem = ((size_t)C * (P + 1) + (size_t)HP_RB * (H * P + C)) * 4;
+  const size_t smem = ((size_t)((C * (P + 1) + 3) & ~3) + (size_t)2 * HP_RB * (H * P + C)) * 4;
   const int grid = (int)std::min<int64_t>(ceil_div(B, (int64_t)HP_RB), (int64_t)num_sms());
   cudaStream_t st = as_stream(stream);
 #define HP_LAUNCH(RM)                                                                                              \
