@@ -71,19 +71,30 @@ numbin_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, i
   const int npairs = F * D4;
   const int64_t b0 = (int64_t)blockIdx.x * chunk, b1 = min(B, b0 + chunk);
   const float invF = 1.f / (float)F;
-  for (int pr = threadIdx.x; pr < npairs; pr += blockDim.x) {
+  // grid.y slices the (f, d4) pairs, grid.x the samples: one pair per thread and 64 samples per CTA keep the serial
+  // chain short (it was 5 pairs x 32 samples per thread at 19 % occupancy) without adding atomics
+  for (int pr = blockIdx.y * blockDim.x + threadIdx.x; pr < npairs; pr += gridDim.y * blockDim.x) {
     int f = pr / D4, l = pr % D4;
     float4 ap = make_float4(0.f, 0.f, 0.f, 0.f), aq = ap;
-    for (int64_t b = b0; b < b1; ++b) {
+    auto grad = [&](int64_t b) {
       float4 g = dout ? *reinterpret_cast<const float4*>(dout + b * ld_b + (int64_t)f * D + l * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (dmean) {
         float4 m = *reinterpret_cast<const float4*>(dmean + b * ld_dmean + l * 4);
         g.x = fmaf(m.x, invF, g.x); g.y = fmaf(m.y, invF, g.y); g.z = fmaf(m.z, invF, g.z); g.w = fmaf(m.w, invF, g.w);
       }
-      float xv = x[b * F + f];
+      return g;
+    };
+    auto accum = [&](const float4& g, float xv) {
       ap.x = fmaf(xv, g.x, ap.x); ap.y = fmaf(xv, g.y, ap.y); ap.z = fmaf(xv, g.z, ap.z); ap.w = fmaf(xv, g.w, ap.w);
       aq.x += g.x; aq.y += g.y; aq.z += g.z; aq.w += g.w;
+    };
+    int64_t b = b0;
+    for (; b + 4 <= b1; b += 4) {                 // 4 samples' loads in flight
+      const float4 g0 = grad(b), g1 = grad(b + 1), g2 = grad(b + 2), g3 = grad(b + 3);
+      const float x0 = x[b * F + f], x1 = x[(b + 1) * F + f], x2 = x[(b + 2) * F + f], x3 = x[(b + 3) * F + f];
+      accum(g0, x0); accum(g1, x1); accum(g2, x2); accum(g3, x3);
     }
+    for (; b < b1; ++b) accum(grad(b), x[b * F + f]);
     float* p = dP + f * D + l * 4;
     float* q = dQ + f * D + l * 4;
     atomicAdd(p + 0, ap.x); atomicAdd(p + 1, ap.y); atomicAdd(p + 2, ap.z); atomicAdd(p + 3, ap.w);
@@ -352,8 +363,8 @@ extern "C" int b200ctr_numbin_bwd(const float* x, const float* dout, int64_t ld_
   if (e == cudaSuccess) e = cudaMemsetAsync(dQ, 0, sizeof(float) * F * D, st);
   if (e != cudaSuccess) return cuda_fail(e, "numbin_bwd memset");
   if (B == 0 || F == 0) return B200CTR_OK;
-  int64_t chunk = 32;
-  int grid = (int)ceil_div(B, chunk);
+  int64_t chunk = 64;
+  dim3 grid((unsigned)ceil_div(B, chunk), (unsigned)std::min<int64_t>(ceil_div((int64_t)F * (D / 4), (int64_t)256), 8));
   numbin_bwd_kernel<<<grid, 256, 0, st>>>(x, dout, ld_b, dmean, ld_dmean, dP, dQ, B, F, D, chunk);
   B200_LAUNCH_CHECK("numbin_bwd_kernel");
   return B200CTR_OK;
