@@ -80,7 +80,7 @@ __device__ __forceinline__ void ta_load_afrag(uint32_t (&a)[4], const float* __r
 
 // NT = number of 8-key tiles (keys padded to a multiple of 16); Kp = 8 * NT
 template <int NT>
-__global__ void __launch_bounds__(TA_THREADS, (NT <= 8 ? 4 : 1))
+__global__ void __launch_bounds__(TA_THREADS, (NT <= 8 ? 4 : 2))
 attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, int K,
                    float* __restrict__ o, float* __restrict__ lse, uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
   constexpr int Kp = NT * 8, MT = NT / 2, NW = (NT + 7) / 8;
