@@ -12,9 +12,12 @@
 //   forward : S = QK^T for all keys stays in registers -> exact two-pass softmax -> dropout -> O = P.V
 //             (the score tile's accumulator layout is fed back as the A operand by permuting the key index:
 //              k-slot t <-> key 2t, k-slot t+4 <-> key 2t+1, with V rows read in the same order; no shuffles)
-//   backward: one warp per head, one pass over the scores: recompute P, dP = dO.V^T, dS -> dQ += dS.K, dbias;
-//             P and dS tiles are transposed in registers (movmatrix on bf16 pairs) for dV += P^T.dO, dK += dS^T.Q
-// Probabilities are never stored (only the per-row log-sum-exp), exactly like the fp32 kernels.
+//   backward: warps = (head, key part); one pass over the scores: recompute P, dP = dO.V^T, dS -> dQ += dS.K, dbias;
+//             P and dS tiles are transposed in registers (movmatrix on bf16 pairs) for dV += P^T.dO, dK += dS^T.Q;
+//             q / dO fragments come from TF32 copies in shared memory (K <= 80), dQ is summed over the key parts
+//             through a shared-memory hand-off, dbias in per-warp copies (no shared-memory atomics: they are CAS loops)
+// Probabilities are never stored (only the per-row log-sum-exp, and -- with dropout -- one keep bit per probability
+// so that the backward does not re-hash the mask); dqkv can be emitted as bf16 for the fused in-projection backward.
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -181,7 +184,7 @@ attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
 // dK += dS^T.Q: the accumulator fragments are packed to bf16 pairs and transposed in registers with
 // movmatrix (8x8 b16), which yields exactly the A fragment of mma.m16n8k16 (16 keys x 16 queries); its B fragment
 // (queries x head dims) is read from bf16 copies of Q^T and dO^T in shared memory.  dK / dV for all keys of the
-// head live in the warp's registers, so nothing but dbias needs an atomic.
+// head live in the warp's registers; no atomics anywhere in the kernel except the final dbias -> drelmean reduction.
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
