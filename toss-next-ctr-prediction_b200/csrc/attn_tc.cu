@@ -497,7 +497,7 @@ template <int NT>
 static int ta_launch_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse, const float* d_o,
                          int64_t B, int K, float* dqkv, int dq16, float* drelmean, const uint32_t* keep, b200ctr_dropout_t drop,
                          cudaStream_t st) {
-  constexpr int KS = NT <= 10 ? 2 : 4;
+  constexpr int KS = NT <= 14 ? 2 : 4;      // 2 key parts (512 threads, ~128 registers, no spills) up to top_k = 112
   constexpr int NBW = (NT / 2 + KS - 1) / KS, KPA = 16 * NBW * KS, Kp = NT * 8;
   const size_t smem = ((size_t)(NT <= 10 ? 4 : 2) * Kp * TA_RS + 2 * TA_H * Kp + 2 * K) * 4 + (size_t)(8 * KS) * (2 * KPA + 2) * 4 +
                       (size_t)TA_H * 2 * (KS - 1) * 128 * 4 + (size_t)2 * 64 * (Kp + 8) * 2;
