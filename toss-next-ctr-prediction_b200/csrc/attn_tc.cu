@@ -208,7 +208,8 @@ __device__ __forceinline__ void ta_store2(float* base, int as_bf16, int64_t off,
 }
 
 // KS = key split: the warps (head h, part) with part in [0, KS) own disjoint 16-key blocks of head h, so dK / dV / dbias
-// accumulators stay small (no spills at top_k = 148) and an SM holds 4x more warps than with one warp per head; only dQ
+// accumulators stay small and an SM holds KS x more warps than with one warp per head (KS = 2 everywhere: 512 threads at
+// up to 128 registers; 4 parts = 1024 threads capped the kernel at 64 registers and spilled); only dQ
 // needs a cross-warp sum.
 // KEEP: the dropout keep flags come from the words the forward pass stored (2 instructions per score instead of a hash)
 template <int NT, int KS, bool KEEP>
@@ -497,7 +498,7 @@ template <int NT>
 static int ta_launch_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse, const float* d_o,
                          int64_t B, int K, float* dqkv, int dq16, float* drelmean, const uint32_t* keep, b200ctr_dropout_t drop,
                          cudaStream_t st) {
-  constexpr int KS = NT <= 14 ? 2 : 4;      // 2 key parts (512 threads, ~128 registers, no spills) up to top_k = 112
+  constexpr int KS = 2;      // 2 key parts: 512 threads at up to 128 registers (4 parts = 1024 threads at 64 registers spilled)
   constexpr int NBW = (NT / 2 + KS - 1) / KS, KPA = 16 * NBW * KS, Kp = NT * 8;
   const size_t smem = ((size_t)(NT <= 10 ? 4 : 2) * Kp * TA_RS + 2 * TA_H * Kp + 2 * K) * 4 + (size_t)(8 * KS) * (2 * KPA + 2) * 4 +
                       (size_t)TA_H * 2 * (KS - 1) * 128 * 4 + (size_t)2 * 64 * (Kp + 8) * 2;
