@@ -170,7 +170,7 @@ def test_shape_predicates_and_shard_layout_helpers():
     assert ops.ffn_fused_ok(384) and ops.ffn_fused_ok(256) and not ops.ffn_fused_ok(512) and not ops.ffn_fused_ok(100)
     assert ops.fm_fused_ok(200, 96, 64) and not ops.fm_fused_ok(300, 96, 64) and not ops.fm_fused_ok(200, 100, 64)
     assert ops.headproj_ok(6, 16, 192) and not ops.headproj_ok(6, 64, 192)
-    assert not ops.headproj_ok(6, 16, 190)          # rows of H*P floats are copied in 16-byte pieces
+    assert not ops.headproj_ok(6, 16, 191)          # rows of H*P floats are copied in 16-byte pieces
     assert ops.lin1_ok(256) and ops.lin1_ok(512) and not ops.lin1_ok(200) and not ops.lin1_ok(640)
     assert ops.bitmap_words(10_000_000) == 312_500 and ops.bitmap_words(33) == 2
     # row r lives on rank r % N at local row r // N: the shards of a table partition its rows exactly once
