@@ -185,3 +185,20 @@ def test_shape_predicates_and_shard_layout_helpers():
     assert np.all(seen == 1)
     with pytest.raises(Exception):
         ops.ShardedTable([0, 0, 0], 10)          # 3 shards: not a power of two
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: stdout carries ONE line, the JSON (library banners must go to stderr).  The reference arm is the
+    CPU oracle port, so this runs without a GPU; a tiny per-step sample keeps it to a few seconds."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ref-batch", "64"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:2000]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"] > 0
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
