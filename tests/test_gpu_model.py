@@ -240,3 +240,115 @@ def test_row_lazy_optimizer_equals_dense(kind):
     for n in finals[False][2]:
         for a, b in zip(finals[True][2][n], finals[False][2][n]):
             assert max_err_scaled(a.cpu(), b.cpu()) < 2e-3, n
+
+
+def _lazy_vs_dense(cfg, z, dev, n_steps, seq_of_step, small_hist=False):
+    import b200ctr
+    from b200ctr import ops
+    finals = {}
+    for lazy in (False, True):
+        m = _build(cfg, z, dev).train()
+        tr = b200ctr.FusedTrainer(m, cfg, steps_per_epoch=3, lazy_tables=lazy)
+        if lazy and small_hist:
+            tr.hist = ops.RowHistory(dev, 4)          # far below the number of steps: push() must grow it
+        for s in range(n_steps):
+            batch, y = batch_of(z, s % 3)
+            batch = dict(batch, seq=seq_of_step(s, batch["seq"].clone()))
+            tr.step(batch, y)
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        finals[lazy] = (sd, {k: v.clone() for k, v in tr.ema_state().items()})
+        if lazy and small_hist:
+            assert tr.hist.cap >= n_steps + 1
+    return finals
+
+
+def test_row_history_grows_past_its_initial_capacity():
+    """the row-lazy optimizer's per-step history had a fixed capacity and aborted mid-training when the run was
+    longer than estimated; it now grows geometrically.  12 steps through a history created with capacity 4 == dense."""
+    dev = torch.device("cuda:0")
+    z, cfg = load_case("qnn_concat")
+    V = cfg["golden"]["seq_vocab"]
+
+    def seq_of(s, seq):
+        nz = seq != 0
+        seq[nz] = (seq[nz] + 37 * (s % 4)) % (V - 1) + 1
+        return seq
+    f = _lazy_vs_dense(cfg, z, dev, 12, seq_of, small_hist=True)
+    for k in f[False][0]:
+        assert max_err_scaled(f[True][0][k].cpu(), f[False][0][k].cpu()) < 1e-3, k
+    for k in f[False][1]:
+        assert max_err_scaled(f[True][1][k].cpu(), f[False][1][k].cpu()) < 1e-3, k
+
+
+def test_row_lazy_long_gap_closed_form_tail_equals_dense():
+    """Rows with Adam moments that are not read for 300 steps (> the 256 skipped steps replayed exactly) and then come back:
+    the closed-form tail (weight-decay product, EMA prefix, geometric moment decay) against the dense optimizer that really
+    ran all 300 steps."""
+    dev = torch.device("cuda:0")
+    z, cfg = load_case("s2_relu")
+    V = cfg["golden"]["seq_vocab"]
+    half = (V - 1) // 2
+
+    def seq_of(s, seq):
+        nz = seq != 0
+        first = s == 0 or s >= 300
+        seq[nz] = (seq[nz] % half) + 1 + (0 if first else half)       # disjoint row sets: A at steps 0 and 300.., B in between
+        return seq
+    f = _lazy_vs_dense(cfg, z, dev, 302, seq_of)
+    for k in f[False][0]:
+        assert max_err_scaled(f[True][0][k].cpu(), f[False][0][k].cpu()) < 1e-3, k
+    for k in f[False][1]:
+        assert max_err_scaled(f[True][1][k].cpu(), f[False][1][k].cpu()) < 1e-3, k
+
+
+def test_plain_module_eval_sees_up_to_date_tables_under_a_lazy_trainer():
+    """the reference's validation pattern -- model.eval(); model(batch) (train.py:212-222) -- must not read rows whose
+    pending weight decay / momentum steps have not been applied: the trainer's forward pre-hook flushes them."""
+    import b200ctr
+    dev = torch.device("cuda:0")
+    z, cfg = load_case("qnn_concat")
+    V = cfg["golden"]["seq_vocab"]
+    m = _build(cfg, z, dev).train()
+    tr = b200ctr.FusedTrainer(m, cfg, steps_per_epoch=3)
+    for s in range(4):
+        batch, y = batch_of(z, s % 3)
+        seq = batch["seq"].clone()
+        nz = seq != 0
+        seq[nz] = (seq[nz] + 53 * s) % (V - 1) + 1
+        tr.step(dict(batch, seq=seq), y)
+    batch, _ = batch_of(z, 0)                      # rows last touched at step 1: three steps of decay are pending
+    m.eval()
+    with torch.no_grad():
+        logits, prob, aux = m(batch)
+    ref_logits, _, _ = tr.predict(batch)
+    assert max_err_scaled(logits.cpu(), ref_logits.cpu()) < 1e-6
+    # and the dense (non-lazy) trainer agrees on what those weights should be
+    m2 = _build(cfg, z, dev).train()
+    tr2 = b200ctr.FusedTrainer(m2, cfg, steps_per_epoch=3, lazy_tables=False)
+    for s in range(4):
+        b2, y = batch_of(z, s % 3)
+        seq = b2["seq"].clone()
+        nz = seq != 0
+        seq[nz] = (seq[nz] + 53 * s) % (V - 1) + 1
+        tr2.step(dict(b2, seq=seq), y)
+    m2.eval()
+    with torch.no_grad():
+        l2, _, _ = m2(batch)
+    assert max_err_scaled(logits.cpu(), l2.cpu()) < 1e-3
+
+
+def test_fc_head_sees_undropped_categorical_embeddings():
+    """embedding_dropout applies to cat_stack (QNN input) only; the FC head concatenates the un-dropped cat_embs
+    (wrapper.py:149-150 vs 167-171).  With p_emb = 0.5 in train mode the FC-head logits must equal the p_emb = 0 logits."""
+    import copy
+    dev = torch.device("cuda:0")
+    z, cfg = load_case("base_s1")
+    batch, _ = batch_of(z, 0)
+    outs = []
+    for p in (0.0, 0.5):
+        c = copy.deepcopy(cfg)
+        c["model"]["embedding_dropout"] = p
+        m = _build(c, z, dev).train()
+        with torch.no_grad():
+            outs.append(m(batch)[0].cpu())
+    assert torch.equal(outs[0], outs[1])

@@ -476,7 +476,10 @@ def model_fwd(P: Dict[str, Tensor], spec: ModelSpec, batch: Dict[str, Tensor], d
         o += D
     ct = _cat_tables(P, spec, cache)
     s1 = torch.empty((B, D), device=dev, dtype=torch.float32) if spec.q_idx >= 0 else None
-    ops.cat_fwd(X_cat, ct, cat_dst, ld, ctx[:, o:], nparts * D, spec.q_idx, s1, D, dc(spec.p_emb, SITE_EMB))
+    # embedding_dropout acts on cat_stack, which only the QNN head consumes; the FC head concatenates the un-dropped
+    # cat_embs (wrapper.py:149-150 vs 167-171)
+    emb_drop = dc(spec.p_emb, SITE_EMB) if spec.use_qnn else NO_DROP
+    ops.cat_fwd(X_cat, ct, cat_dst, ld, ctx[:, o:], nparts * D, spec.q_idx, s1, D, emb_drop)
     if not spec.use_qnn:
         # the FC head consumes the feature means: copy them next to u (device-to-device plumbing)
         k = 1
@@ -571,4 +574,4 @@ def model_bwd(P: Dict[str, Tensor], spec: ModelSpec, sv: dict, dlogits: Tensor, 
     dmean_cat = dctx[:, o:] if dctx is not None else None
     ops.cat_bwd(sv["X_cat"], sv["ct"], dcat, ld_d, dmean_cat, ldc, spec.q_idx if dq_cat is not None else -1, dq_cat,
                 [G(f"cat_embs.{c}.weight") for c in spec.cat_cols], [G(f"cat_proj.{c}.weight") for c in spec.cat_cols],
-                D, dc(spec.p_emb, SITE_EMB))
+                D, dc(spec.p_emb, SITE_EMB) if spec.use_qnn else NO_DROP)

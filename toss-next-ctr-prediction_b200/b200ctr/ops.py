@@ -931,6 +931,8 @@ class RowHistory:
         import math
         np = self.np
         assert t == self.t + 1, (t, self.t)
+        if t >= self.cap:
+            self._grow(max(2 * self.cap, t + 1))
         lib = _lib.load()
         lr32 = np.float32(lr)
         decay_mul = np.float32(1.0) - lr32 * np.float32(wd)                 # as adamw_ema_kernel: 1.f - lr*wd
@@ -945,6 +947,17 @@ class RowHistory:
              float(decay_mul), float(step_size), float(bc2s), float(d32), self.c, self.s, self.ld, _stream())
         self.t = t
         _count()
+
+    def _grow(self, cap: int):
+        """Geometric growth of the device-side history (the recurrences live on the host, the arrays are plain prefixes):
+        a run longer than the initial estimate -- more epochs, an underestimated steps_per_epoch, millions of steps -- keeps
+        going like the reference's loop does.  Stream-ordered copies; the kernels receive the pointers per call."""
+        def grown(old, fill):
+            new = torch.full((cap,) + tuple(old.shape[1:]), fill, device=old.device, dtype=old.dtype)
+            new[:old.shape[0]].copy_(old)
+            return new
+        self.h4, self.C, self.S, self.logD = grown(self.h4, 0.0), grown(self.C, 1.0), grown(self.S, 1.0), grown(self.logD, 0.0)
+        self.cap = int(cap)
 
     def args(self):
         return (_p(self.h4), _p(self.C), _p(self.S), _p(self.logD), self.b1, self.b2, self.eps)

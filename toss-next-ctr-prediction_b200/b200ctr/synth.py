@@ -64,3 +64,64 @@ class ToySchema:
         seq[valid] = toks
         y = (rng.random(B) < 0.019).astype(np.float32)
         return {"X_num": X_num, "X_mask": X_mask, "X_cat": X_cat, "seq": seq}, y
+
+
+def planted_labels(b: Dict[str, np.ndarray], cols, rng: np.random.Generator, query_key: str = "inventory_id") -> np.ndarray:
+    """Labels with a learnable signal (the default `batch()` labels are pure Bernoulli(0.019) noise, useless for AP / WLL):
+    a linear + one pairwise numeric term, a per-bucket effect of the query-key categorical, and a target-aware sequence
+    term -- the share of the 64 most recent tokens whose id is congruent to the query-key bucket mod 8 -- which is what
+    DARE's query . key retrieval can pick up.  Base rate ~ 7 %."""
+    x = b["X_num"]
+    qi = cols.index(query_key) if query_key in cols else 0
+    inv = b["X_cat"][:, qi]
+    eff = np.array([0.9, -0.6, 0.3, -0.2, 0.7, -0.8, 0.1, 0.4])[inv % 8]
+    recent = b["seq"][:, -64:]
+    nz = recent != 0
+    match = ((recent % 8) == (inv % 8)[:, None]) & nz
+    frac = match.sum(1) / np.maximum(1, nz.sum(1))
+    z = -3.3 + 0.9 * x[:, 0] - 0.6 * x[:, 1] + 0.5 * x[:, 2] * x[:, 3] + eff + 6.0 * (frac - 0.125)
+    return (rng.random(x.shape[0]) < 1.0 / (1.0 + np.exp(-z))).astype(np.float32)
+
+
+def write_cache(root: str, cfg: dict, n_train: int, n_test: int, n_num: int, shard_rows: int = 50_000, seed: int = 777,
+                planted: bool = True) -> Tuple[str, str]:
+    """Write a synthetic cache in the reference's on-disk format (build_cache_v1.py:158-177,223-306):
+    <root>/{train,test}/shard_%03d/{X_num f32, X_mask u8, X_cat i32, seq i32, y i8, groups i64, ids <U64}.npy + manifest.json.
+    Returns (manifest_train, manifest_test).  Deterministic in (cfg, sizes, seed)."""
+    import json
+    import os
+    schema = ToySchema(cfg, n_num, n_num, seed=seed)
+    cols = cfg["data"]["cat_cols"]
+    qk = cfg["sequence"].get("query_key", cols[0])
+    out = []
+    for split, n_rows, is_train in (("train", n_train, True), ("test", n_test, False)):
+        shards, start, si = [], 0, 0
+        while start < n_rows:
+            rows = min(shard_rows, n_rows - start)
+            b, y = schema.batch(rows, seed=seed + 1000 * (1 + is_train) + si)
+            if planted:
+                y = planted_labels(b, cols, np.random.default_rng(seed + 7 + si), qk)
+            d = os.path.join(root, split, f"shard_{si:03d}")
+            os.makedirs(d, exist_ok=True)
+            inv = b["X_cat"][:, cols.index(qk) if qk in cols else 0]
+            dow = b["X_cat"][:, cols.index("day_of_week")] if "day_of_week" in cols else 0
+            arrs = {"X_num": b["X_num"].astype(np.float32), "X_mask": b["X_mask"].astype(np.uint8),
+                    "X_cat": b["X_cat"].astype(np.int32), "seq": b["seq"].astype(np.int32),
+                    "y": (y if is_train else np.zeros_like(y)).astype(np.int8),
+                    "groups": (inv * 7 + dow).astype(np.int64) % (2 ** 31 - 1),
+                    "ids": np.array([f"{'TRAIN' if is_train else 'TEST'}_{start + i:07d}" for i in range(rows)], dtype="<U64")}
+            meta = {"rows": rows, "index": si, "start": start, "end": start + rows}
+            for k, a in arrs.items():
+                p = os.path.join(d, f"{k}.npy")
+                np.save(p, a)
+                meta[k] = {"path": p, "shape": list(a.shape), "dtype": str(a.dtype)}
+            shards.append(meta)
+            start += rows
+            si += 1
+        man = {"parquet": "synthetic", "is_train": is_train, "rows": n_rows, "num_cols": [f"num_{i}" for i in range(n_num)],
+               "cat_cols": list(cols), "group_key": qk, "seq_col": "seq", "shards": shards}
+        mp = os.path.join(root, split, "manifest.json")
+        with open(mp, "w") as fh:
+            json.dump(man, fh)
+        out.append(mp)
+    return out[0], out[1]

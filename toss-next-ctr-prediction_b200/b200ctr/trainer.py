@@ -15,10 +15,11 @@ checkpoints keep working on the same storage.  Parameters that never receive a g
 S1 mode, aux_head when aux_head_weight == 0) sit in a tail segment the optimizer skips: torch.optim.AdamW skips
 grad-less parameters entirely (no weight decay either), and this reproduces that.
 
-The two big tables keep separate p/m/v/ema buffers plus a persistent, all-zero dense gradient table: the backward
-kernel accumulates the K touched rows per sample into it, one representative slot per distinct row is elected
-(rows_claim) for the norm, the fused AdamW pass reads it, and the touched rows are re-zeroed afterwards.  (A row-lazy
-optimizer that avoids the dense passes is the planned next step; see DESIGN.md.)
+The two big tables keep separate p/m/v/ema buffers, a persistent all-zero gradient table and a per-row lazy state: the
+backward kernel accumulates the K touched rows per sample into the gradient table, the rows a batch reads / touches are
+kept as bitmaps (one bit per row), and the row-lazy optimizer (csrc/rowopt.cu) catches rows up before they are read, applies
+step t to the touched rows and re-zeroes their gradient rows.  Everything that reads the tables outside FusedTrainer.step
+(state_dict, plain-module forward for validation, EMA swap-in) flushes them first through module hooks.
 
 Data parallel (one process per GPU): dense grads are all-reduced (NCCL), class counts (C3), the SE squeeze (C4)
 and the table-row gradients are exchanged so that N ranks with B/N samples each reproduce the 1-GPU global batch.
@@ -26,11 +27,12 @@ and the table-row gradients are exchanged so that N ranks with B/N samples each 
 Row-sharded sequence tables (shard_tables=True, the default for world > 1): row r of emb_att / emb_rep -- and its
 Adam moments, EMA shadow, gradient row and lazy-optimizer state -- lives only on rank r % N at local row r // N.
 Every rank maps the other ranks' parameter and gradient shards through CUDA IPC (peer memory over NVLink), so the
-retrieval kernel gathers remote rows and the backward kernel scatters gradient rows straight into the owner's shard:
-the exchange happens inside the kernels, tile by tile, with no staging buffer.  Per step the owners need to know which
-of their rows are read / touched: one all-gather of the token ids (before the forward) and one of the K selected
-tokens (after the backward); those two collectives double as the device-side barriers that order "owner caught the
-rows up" -> "peers read them" and "peers scattered gradients" -> "owner applies AdamW".
+retrieval kernel gathers remote rows with plain loads; the backward kernel reduces locally-owned gradient rows in place and
+writes rows owned by other ranks into the owner's peer-mapped STAGING buffer (stage[owner][src_rank][slot]), which the owner
+adds into its shard after the step's second all-gather (remote fp32 atomics over NVLink were 7x slower).  Per step the owners
+need to know which of their rows are read / touched: one all-gather of the row bitmaps (before the forward) and one of the K
+selected tokens (after the backward); those two collectives double as the device-side barriers that order "owner caught the
+rows up" -> "peers read them" and "peers stored gradients" -> "owner applies AdamW".
 """
 from __future__ import annotations
 
@@ -83,7 +85,7 @@ class FusedTrainer:
         tr = cfg["train"]
         self.base_lr, self.wd = float(tr["lr"]), float(tr["weight_decay"])
         self.clip = float(tr.get("grad_clip_norm", 0.0))
-        self.warmup_epochs, self.epochs = int(tr.get("warmup_epochs", 1)), int(tr.get("epochs", 10))
+        self.warmup_epochs, self.epochs = tr.get("warmup_epochs", 1), int(tr.get("epochs", 10))      # fractional warm-up allowed, as in sched.py
         self.steps_per_epoch = int(steps_per_epoch)
         ema = cfg.get("ema") or {}
         self.ema_on = bool(ema.get("enabled", False))
@@ -152,12 +154,17 @@ class FusedTrainer:
                 self.Gv[n] = t["g"]
         self.vocab = self.tables[BIG_TABLES[0]]["p"].shape[0]          # rows held by this rank
         if self.lazy:
+            # initial capacity only: RowHistory grows geometrically when the run outlives the estimate
             cap = min(max(self.epochs * self.steps_per_epoch + 64, 4096), 1 << 22)
             self.hist = ops.RowHistory(dev, cap)
             for n in BIG_TABLES:
                 self.tables[n]["state"] = torch.zeros(self.vocab, device=dev, dtype=torch.int32)
             # state_dict()/checkpointing through the nn.Module sees fully-updated (and, if sharded, re-assembled) tables
             model.register_state_dict_pre_hook(lambda *a, **k: self.materialize_tables())
+            # the reference's validation pattern -- model.eval(); model(batch) (train.py:212-222), ema.store()/copy_to() --
+            # goes through the nn.Module: the lazily-updated rows must be brought to the current step first (sharded mode:
+            # the full tables are re-assembled, a collective every rank reaches because every rank validates)
+            model.register_forward_pre_hook(lambda *a, **k: self._before_module_forward())
         self.owner = torch.empty(max(self.vocab, 1), device=dev, dtype=torch.int32)
         # row sets as bitmaps (one bit per global row) unless the tables are replicated under DP (legacy all-gather path)
         self.bitmaps = self.lazy and (self.world == 1 or self.shard)
@@ -172,8 +179,16 @@ class FusedTrainer:
         self._bar = torch.zeros(1, device=dev, dtype=torch.float32)      # payload of the barrier all-reduces
         self.total_norm = torch.zeros(1, device=dev, dtype=torch.float32)
         self.global_step = 0
+        self._equal_batch = -1
+        self._flushed_at = 0             # global_step at which every table row was last brought up to date (sync_tables)
         self.n_ema = 0
         self.cache: dict = {}
+        defaults = {"update_after_step": 0, "update_interval": 1, "param_filter": [], "offload_to_cpu": False}
+        for k, dv in defaults.items():
+            v = ema.get(k, dv)
+            if self.ema_on and (list(v) if k == "param_filter" and v is not None else v) not in (dv, None):
+                raise ValueError(f"FusedTrainer: ema.{k}={v!r} is not supported by the fused AdamW+EMA kernels (only the default "
+                                 f"{dv!r}: update every step from step 0, all parameters, shadows on the device)")
 
     # ---- row-sharded tables ----------------------------------------------------------------------------------
     def _init_sharded_tables(self, params):
@@ -249,6 +264,12 @@ class FusedTrainer:
             torch.distributed.all_gather_into_tensor(buf, p, group=self.pg)
             params[n].data = buf.permute(1, 0, 2).reshape(N * p.shape[0], p.shape[1])[:self.vocab_global].contiguous()
 
+    def _before_module_forward(self):
+        """Plain-module forward while this trainer owns the tables lazily: flush pending decay / momentum / EMA steps (a no-op
+        pass when nothing is pending), and in sharded mode materialise the replicas the module parameters point at."""
+        if self._flushed_at != self.global_step or (self.shard and dict(self.model.named_parameters())[BIG_TABLES[0]].shape[0] == 0):
+            self.materialize_tables()
+
     def release_tables(self):
         """Drop the re-assembled replicas again (sharded mode)."""
         if self.shard:
@@ -282,6 +303,20 @@ class FusedTrainer:
             torch.distributed.all_reduce(t, group=self.pg)
         return t
 
+    def _check_equal_batch(self, B_local: int):
+        """Data parallel: staging slots, all_gather_into_tensor sizes and B_total = B_local * world all assume one batch size
+        per rank.  Verified collectively at first use and again whenever the local batch size changes (a ragged last batch
+        must change on every rank alike: pad or drop it otherwise)."""
+        if self.world == 1 or B_local == self._equal_batch:
+            return
+        mm = torch.tensor([B_local, -B_local], device=self.dev, dtype=torch.int64)
+        torch.distributed.all_reduce(mm, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+        lo, hi = -int(mm[1]), int(mm[0])
+        if lo != hi:
+            raise ValueError(f"FusedTrainer: per-rank batch sizes differ ({lo}..{hi}); every rank must step with the same B "
+                             f"(pad or drop the ragged last batch)")
+        self._equal_batch = B_local
+
     # ---- one optimisation step ---------------------------------------------------------------------------------
     def step(self, batch: Dict[str, torch.Tensor], y: torch.Tensor, lr: Optional[float] = None) -> torch.Tensor:
         """batch: collate_sharded dict (CPU pinned or device tensors).  Returns the loss as a 1-element device
@@ -293,11 +328,13 @@ class FusedTrainer:
         spec = self.spec
         if not spec.use_qnn:
             spec.p_fc = float(self.model.fc[2].p)
+        self._check_equal_batch(int(y.shape[0]))
         self.global_step += 1
         lr = self.lr_at(self.global_step) if lr is None else lr
         dbatch, yd = self.to_device(batch, y)
         B_local = yd.shape[0]
-        dc = hp.DropCtl(True, seed=self.seed, step=self.global_step)
+        # every rank draws its own masks (same seed on all ranks would give local row i identical masks on every rank)
+        dc = hp.DropCtl(True, seed=self.seed + 0x9E3779B1 * self.rank, step=self.global_step)
         self.flat_g.zero_()
         d = ema_decay_at(self.n_ema, self.ema_decay, self.ema_warm, self.ema_type) if self.ema_on else 0.0
         if self.lazy:
@@ -417,10 +454,11 @@ class FusedTrainer:
     def sync_tables(self):
         """Bring every row of the big tables (p, m, v, ema) to the current step.  Needed before anything other than
         FusedTrainer.step reads them (evaluation, state_dict, EMA swap-in); a dense pass, once per epoch in practice."""
-        if self.lazy and self.global_step > 0:
+        if self.lazy and self.global_step > 0 and self._flushed_at != self.global_step:
             for n in BIG_TABLES:
                 t = self.tables[n]
                 ops.rowopt_flush(t["state"], t["p"], t["m"], t["v"], t["ema"], self.global_step, self.hist)
+        self._flushed_at = self.global_step
 
     @torch.no_grad()
     def predict(self, batch: Dict[str, torch.Tensor]):

@@ -18,6 +18,7 @@
 namespace b200ctr {
 
 constexpr int RO_D = 64;
+constexpr int RO_REPLAY_MAX = 256;     // skipped steps replayed exactly before the closed-form tail (see row_catchup)
 
 struct RowHist {
   const float4* h;      // [steps+1]  per-step constants
@@ -43,7 +44,13 @@ __device__ __forceinline__ void row_catchup(float2& p, float2& m, float2& v, flo
     p.x *= ratio; p.y *= ratio;
     return;
   }
-  for (int s = last + 1; s <= target; ++s) {
+  // Replay is exact for the first RO_REPLAY_MAX skipped steps.  Beyond that the moments have decayed by beta1^k with the
+  // update ratio m/sqrt(v) shrinking as (beta1/sqrt(beta2))^k < 0.9005^k: the sum of ALL further updates is below
+  // 3e-11 * lr (k > 256), far under one fp32 ulp of any weight, so the tail is the zero-moment closed form (weight decay
+  // product + EMA prefix) plus the plain geometric decay of m and v.  Keeps a row that comes back after thousands of steps
+  // (the Zipf tail in real training) from serialising its warp on an O(gap) loop of sqrt + divide.
+  const int exact_to = (target - last > RO_REPLAY_MAX) ? last + RO_REPLAY_MAX : target;
+  for (int s = last + 1; s <= exact_to; ++s) {
     const float4 c = __ldg(H.h + s);
     p.x *= c.x; p.y *= c.x;
     m.x = m.x + (0.f - m.x) * (1.f - H.beta1);   // lerp_(g = 0, 1 - b1), written exactly as the dense kernel computes it
@@ -52,6 +59,20 @@ __device__ __forceinline__ void row_catchup(float2& p, float2& m, float2& v, flo
     p.x -= c.y * (m.x / (sqrtf(v.x) / c.z + H.eps));
     p.y -= c.y * (m.y / (sqrtf(v.y) / c.z + H.eps));
     if (has_ema) { e.x = e.x * c.w + p.x * (1.f - c.w); e.y = e.y * c.w + p.y * (1.f - c.w); }
+  }
+  if (exact_to < target) {
+    const int rest = target - exact_to;
+    const float ca = H.C[exact_to], cb = H.C[target];
+    const float ratio = cb / ca;
+    if (has_ema) {
+      const float Dm = expf(H.logD[target] - H.logD[exact_to]);
+      const float w = (H.S[target] - H.S[exact_to] * Dm) / ca;
+      e.x = e.x * Dm + p.x * w;
+      e.y = e.y * Dm + p.y * w;
+    }
+    p.x *= ratio; p.y *= ratio;
+    const float d1 = powf(H.beta1, (float)rest), d2 = powf(H.beta2, (float)rest);
+    m.x *= d1; m.y *= d1; v.x *= d2; v.y *= d2;
   }
 }
 
@@ -182,8 +203,10 @@ template <typename IT>
 __global__ void bitmap_mark_kernel(const IT* __restrict__ tok, int64_t n, int pad_id, int64_t vocab, uint32_t* __restrict__ bm) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int64_t t = (int64_t)tok[i];
-  if (t == pad_id || t < 0 || t >= vocab) return;
+  int64_t t = (int64_t)tok[i];
+  if (t == pad_id) return;
+  t = t < 0 ? 0 : (t >= vocab ? vocab - 1 : t);     // the same memory-safe clamp retrieve_fwd applies: the row it READS is the row marked
+  if (t == pad_id) return;
   const uint32_t bit = 1u << (t & 31);
   uint32_t* w = bm + (t >> 5);
   if (!(*w & bit)) atomicOr(w, bit);              // hot rows are marked thousands of times: test first
@@ -264,8 +287,9 @@ rowopt_catchup_bm_kernel(const uint32_t* __restrict__ bm, int n_maps, int64_t wo
     *p4 = p;
     if (has_mom) { reinterpret_cast<float4*>(Mo + t * RO_D)[hl] = m; reinterpret_cast<float4*>(V + t * RO_D)[hl] = v; }
     if (E) reinterpret_cast<float4*>(E + t * RO_D)[hl] = e;
-    // every lane of the half-warp read state[t] before this point (program order within the lane; the 16 lanes only
-    // read it); lane 0 of the half publishes the new step
+    // all 16 lanes of the half-warp must have READ state[t] before lane 0 of the half publishes the new step (independent
+    // thread scheduling gives no such order by itself; the two halves work on different rows and may have diverged)
+    __syncwarp(0xffffu << (threadIdx.x & 16));
     if (hl == 0) state[t] = (target << 1) | (st & 1);
   });
 }
@@ -327,6 +351,7 @@ rowopt_update_bm_kernel(const uint32_t* __restrict__ bm, int n_maps, int64_t wor
     *v4 = make_float4(vv[0], vv[1], vv[2], vv[3]);
     *g4 = z4;
     if (E) reinterpret_cast<float4*>(E + t * RO_D)[hl] = make_float4(ee[0], ee[1], ee[2], ee[3]);
+    __syncwarp(0xffffu << (threadIdx.x & 16));
     if (hl == 0) state[t] = (t_step << 1) | 1;
   });
 }
