@@ -82,8 +82,9 @@ def full_init(model_cls, cfg, z):
     return m
 
 
-def packed_err(z, key, t):
-    """(max-abs error of the stored subsample / max|ref|, relative error of the whole-tensor L2 norm)."""
+def packed_err(z, key, t, l2=False):
+    """(max-abs error of the stored subsample / max|ref|, relative error of the whole-tensor L2 norm[, relative L2 error of the
+    subsample])."""
     from oracle.make_golden_full import sample_stride
     ref = torch.from_numpy(np.array(z[key])).double()
     st = z[key + "#stats"]
@@ -93,6 +94,8 @@ def packed_err(z, key, t):
     e_sub = float((sub - ref).abs().max() / (ref.abs().max() + 1e-30))
     nref = float(st[1]) ** 0.5
     e_norm = abs(float(a.norm()) - nref) / (nref + 1e-30)
+    if l2:
+        return e_sub, e_norm, float((sub - ref).norm() / (ref.norm() + 1e-30))
     return e_sub, e_norm
 
 

@@ -514,3 +514,30 @@ def test_lin1_matches_torch(dev, B, K):
     assert max_err_scaled(dh.cpu(), dh_ref) < 1e-5
     assert max_err_scaled(dw.cpu(), dl.double().t() @ h.double()) < 1e-5
     assert abs(float(db.cpu()) - float(dl.double().sum())) < 1e-4 * (1 + float(dl.abs().sum()))
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(300, 192, 64, False, True), (1000, 96, 64, False, False), (257, 70, 136, True, False),
+                                          (512, 384, 2048, False, True), (130, 64, 5000, True, False), (4096, 512, 1088, False, True)])
+def test_gemm_x3_split_precision_is_fp32_grade(M, N, K, ta, tb):
+    """b200ctr_gemm_x3 (the `amp: none` tensor-core contraction: bf16 hi/lo split, 3 MMAs per product) against fp64 math:
+    error <= 3e-5 of max|C| (the bf16 kernel sits at ~3e-3), and the fused epilogue matches the CUDA-core kernel's."""
+    from b200ctr import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((K, M) if ta else (M, K), generator=g)
+    b = torch.randn((N, K) if tb else (K, N), generator=g)
+    ref = (a.double().t() if ta else a.double()) @ (b.double().t() if tb else b.double())
+    with ops.precision("fp32"):
+        ops.profile_start()
+        out = ops.gemm(a.to(dev), b.to(dev), trans_a=ta, trans_b=tb)
+        fams = {t.split("[")[0] for t in ops.profile_stop()}
+        assert fams == {"gemm_x3"}, fams
+        bias = torch.randn(N, generator=g).to(dev)
+        res = torch.randn(M, N, generator=g).to(dev)
+        o_x3 = ops.gemm(a.to(dev), b.to(dev), trans_a=ta, trans_b=tb, bias=bias, act=ops.ACT_RELU, residual=res)
+        o_fma = ops.gemm(a.to(dev), b.to(dev), trans_a=ta, trans_b=tb, bias=bias, act=ops.ACT_RELU, residual=res, tc=False)
+        o_sk = ops.gemm(a.to(dev), b.to(dev), trans_a=ta, trans_b=tb, split_k=3)
+    err = float((out.double().cpu() - ref).abs().max() / ref.abs().max())
+    assert err < 3e-5, err
+    assert float((o_sk.double().cpu() - ref).abs().max() / ref.abs().max()) < 3e-5
+    assert float((o_x3 - o_fma).abs().max() / o_fma.abs().max()) < 3e-5

@@ -509,8 +509,10 @@ def model_fwd(P: Dict[str, Tensor], spec: ModelSpec, batch: Dict[str, Tensor], d
 
 
 def model_bwd(P: Dict[str, Tensor], spec: ModelSpec, sv: dict, dlogits: Tensor, daux: Optional[Tensor], dc: DropCtl,
-              G: Callable[[str], Tensor], colsum_hook=None):
-    """Backward of model_fwd.  G(name) returns the (zero-initialised) gradient tensor of parameter `name`."""
+              G: Callable[[str], Tensor], colsum_hook=None, after_head: Optional[Callable[[], None]] = None):
+    """Backward of model_fwd.  G(name) returns the (zero-initialised) gradient tensor of parameter `name`.
+    after_head: called once the head's (QNN / FC) parameter gradients are final -- the data-parallel trainer starts their
+    all-reduce there, under the encoder / embedding backward."""
     B, D = sv["B"], spec.D
     Fn, Fm, Fc = spec.num_dim, spec.mask_dim, len(spec.cat_cols)
     nparts = (Fn > 0) + (Fm > 0) + 1
@@ -536,6 +538,8 @@ def model_bwd(P: Dict[str, Tensor], spec: ModelSpec, sv: dict, dlogits: Tensor, 
         dnum = dmask = None
         dcat = dfeat[:, D * (1 + (Fn > 0) + (Fm > 0)):]
         dmean_fc = dfeat[:, D:]                                                     # [dnum_mean | dmask_mean] slices
+    if after_head is not None:
+        after_head()
     dq = dare_bwd(P, spec, sv["dare"], du, ld_d, daux, dc, G, want_aux_grads=spec.aux_weight > 0)
     # query path
     dctx = None

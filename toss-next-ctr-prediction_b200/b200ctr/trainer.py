@@ -115,11 +115,24 @@ class FusedTrainer:
         off = 0
         n_active = 0
         for n in active:
+            if n in frozen:
+                continue
             self.offsets[n] = off
             off += (params[n].numel() + 3) // 4 * 4
-            if n not in frozen:
-                n_active = off
+        n_active = off
+        self.slot0 = off          # 4 reserved floats between the active and the frozen segment: the step's loss rides on the
+        off += 4                  # dense-gradient all-reduce there (one collective less per step)
+        for n in active:
+            if n in frozen:
+                self.offsets[n] = off
+                off += (params[n].numel() + 3) // 4 * 4
         self.n_flat, self.n_active = off, n_active
+        # head (qnn.* / fc.*) gradients are final first in the backward pass: if they form the tail of the active segment their
+        # all-reduce is launched asynchronously under the encoder / embedding backward
+        head = [n for n in active if n not in frozen and (n.startswith("qnn.") or n.startswith("fc."))]
+        self.head_off = min((self.offsets[n] for n in head), default=n_active)
+        if any(self.offsets[n] > self.head_off for n in active if n not in frozen and n not in head):
+            self.head_off = n_active                       # not a contiguous tail: single all-reduce
         self.flat_p = torch.zeros(off, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(off, device=dev, dtype=torch.float32)
         self.flat_m = torch.zeros(n_active, device=dev, dtype=torch.float32)
@@ -176,10 +189,11 @@ class FusedTrainer:
             self.bm_all = torch.zeros(self.n_shards * self.bm_words, device=dev, dtype=torch.int32) if self.shard else None
         self.acc = torch.zeros(1, device=dev, dtype=torch.float64)
         self.coef = torch.ones(1, device=dev, dtype=torch.float32)
-        self._bar = torch.zeros(1, device=dev, dtype=torch.float32)      # payload of the barrier all-reduces
+        self._bar = torch.zeros(4, device=dev, dtype=torch.float32)      # payload of the barrier all-reduces (+ class counts)
         self.total_norm = torch.zeros(1, device=dev, dtype=torch.float32)
         self.global_step = 0
         self._equal_batch = -1
+        self.comm_prof = None            # bench.py: list of (tag, start_event, end_event) per collective
         self._flushed_at = 0             # global_step at which every table row was last brought up to date (sync_tables)
         self.n_ema = 0
         self.cache: dict = {}
@@ -240,14 +254,14 @@ class FusedTrainer:
             gsh.stage_rank, gsh.stage_cap = self.rank, self.stage_cap
         dist.barrier(group=self.pg)
 
-    def _row_set(self, ids: torch.Tensor):
+    def _row_set(self, ids: torch.Tensor):  # noqa: D401
         """Bitmap(s) of the global rows listed in `ids`: (maps, n_maps).  Sharded mode: all ranks' bitmaps, all-gathered
         (1.25 MB per rank at 10 M rows; the collective doubles as a device-side barrier)."""
         self.bm_mine.zero_()
         ops.bitmap_mark(ids, self.spec.pad_id, self.vocab_global, self.bm_mine)
         if not self.shard:
             return self.bm_mine, 1
-        torch.distributed.all_gather_into_tensor(self.bm_all, self.bm_mine, group=self.pg)
+        self._allgather(self.bm_all, self.bm_mine, "C1_bitmaps_allgather")
         return self.bm_all, self.world
 
     def materialize_tables(self):
@@ -298,10 +312,24 @@ class FusedTrainer:
         epoch, step = divmod(g, max(1, self.steps_per_epoch))
         return cosine_warmup_lr(epoch, step, self.steps_per_epoch, self.base_lr, self.warmup_epochs, self.epochs)
 
-    def _allreduce(self, t: torch.Tensor):
+    def _comm(self, tag: str, fn):
+        """Run one collective; when bench.py switched `comm_prof` on, bracket it with CUDA events on the launch stream."""
+        if self.comm_prof is None:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        self.comm_prof.append((tag, a, b))
+        return out
+
+    def _allreduce(self, t: torch.Tensor, tag: str = "allreduce"):
         if self.pg is not None and self.world > 1:
-            torch.distributed.all_reduce(t, group=self.pg)
+            self._comm(tag, lambda: torch.distributed.all_reduce(t, group=self.pg))
         return t
+
+    def _allgather(self, out: torch.Tensor, inp: torch.Tensor, tag: str):
+        self._comm(tag, lambda: torch.distributed.all_gather_into_tensor(out, inp, group=self.pg))
 
     def _check_equal_batch(self, B_local: int):
         """Data parallel: staging slots, all_gather_into_tensor sizes and B_total = B_local * world all assume one batch size
@@ -335,6 +363,7 @@ class FusedTrainer:
         B_local = yd.shape[0]
         # every rank draws its own masks (same seed on all ranks would give local row i identical masks on every rank)
         dc = hp.DropCtl(True, seed=self.seed + 0x9E3779B1 * self.rank, step=self.global_step)
+        counts_ready = None
         self.flat_g.zero_()
         d = ema_decay_at(self.n_ema, self.ema_decay, self.ema_warm, self.ema_type) if self.ema_on else 0.0
         if self.lazy:
@@ -351,7 +380,13 @@ class FusedTrainer:
                         ops.rowopt_catchup_bm(maps, n_maps, self.bm_words, self.n_shards, self.shard_rank, t["state"], t["p"],
                                               t["m"], t["v"], t["ema"], self.global_step - 1, self.hist)
                 if self.shard:
-                    self._allreduce(self._bar)      # barrier: every shard is caught up before any peer gathers from it
+                    # barrier: every shard is caught up before any peer gathers from it.  Its payload carries the class counts
+                    # (C3) so they need no collective of their own (exact in fp32: counts <= 2^24)
+                    self._bar[0] = 0.0
+                    self._bar[1] = (yd > 0.5).sum()
+                    self._bar[2] = (yd <= 0.5).sum()
+                    self._allreduce(self._bar, "barrier+C3_counts")
+                    counts_ready = self._bar[1:3].to(torch.int32)
             elif self.global_step > 1:
                 seq = dbatch["seq"]
                 ops.rows_claim_any(seq, spec.pad_id, self.vocab, self.owner)
@@ -361,26 +396,49 @@ class FusedTrainer:
                                        self.global_step - 1, self.hist)
         if self.shard:
             self._ensure_staging(B_local * min(spec.top_k, dbatch["seq"].shape[1]))
-        hook = (lambda t: self._allreduce(t)) if self.world > 1 else None
+        hook = (lambda t: self._allreduce(t, "C4_se_squeeze")) if self.world > 1 else None
         logits, aux, sv = hp.model_fwd(self.P, spec, dbatch, dc, self.cache, B_total=B_local * self.world, colsum_hook=hook)
         counts_override = None
         if self.world > 1:
-            counts_override = torch.stack([(yd > 0.5).sum(), (yd <= 0.5).sum()]).to(torch.int32)   # 2 ints (C3)
-            self._allreduce(counts_override)
+            if counts_ready is not None:
+                counts_override = counts_ready
+            else:
+                counts_override = torch.stack([(yd > 0.5).sum(), (yd <= 0.5).sum()]).to(torch.int32)   # 2 ints (C3)
+                self._allreduce(counts_override, "C3_counts")
         loss, dz, daux, _, _ = ops.bce_wll(logits, aux, yd, spec.aux_weight, counts_override, want_prob=False)
-        hp.model_bwd(self.P, spec, sv, dz, daux if spec.aux_weight > 0 else None, dc, self._G, colsum_hook=hook)
-        tok = sv["dare"]["tok"]
-        if self.world > 1:
+        pending = []
+
+        def head_grads_final():
+            """C2, first part: the head's gradients (28 of the 37.6 MB: qnn.mlp.0.weight) + the loss slot, all-reduced on
+            NCCL's stream while the encoder / embedding backward keeps this stream busy."""
             # the SE gate's weight gradients are functions of batch-global sums (already all-reduced inside
             # qnn_bwd), hence identical on every rank: pre-divide so the dense all-reduce(sum) leaves them unchanged
             if spec.use_qnn and spec.use_se:
                 for n in ("qnn.se.fc.0.weight", "qnn.se.fc.0.bias", "qnn.se.fc.2.weight", "qnn.se.fc.2.bias"):
                     g = self.Gv[n].view(-1)
                     ops.axpby(g, None, 1.0 / self.world, 0.0, out=g)
-            self._allreduce(self.flat_g[:self.n_active])                                            # C2
+            self.flat_g[self.slot0:self.slot0 + 1].copy_(loss.view(1))
+            seg = self.flat_g[self.head_off:self.slot0 + 4]
+            pending.append(self._comm("C2_head_async", lambda: torch.distributed.all_reduce(seg, group=self.pg, async_op=True)))
+
+        overlap = self.world > 1 and self.head_off < self.n_active
+        hp.model_bwd(self.P, spec, sv, dz, daux if spec.aux_weight > 0 else None, dc, self._G, colsum_hook=hook,
+                     after_head=head_grads_final if overlap else None)
+        tok = sv["dare"]["tok"]
+        if self.world > 1:
+            if overlap:
+                self._allreduce(self.flat_g[:self.head_off], "C2_rest")                             # C2, second part
+                self._comm("C2_head_wait", lambda: pending[0].wait())
+            else:
+                if spec.use_qnn and spec.use_se:
+                    for n in ("qnn.se.fc.0.weight", "qnn.se.fc.0.bias", "qnn.se.fc.2.weight", "qnn.se.fc.2.bias"):
+                        g = self.Gv[n].view(-1)
+                        ops.axpby(g, None, 1.0 / self.world, 0.0, out=g)
+                self.flat_g[self.slot0:self.slot0 + 1].copy_(loss.view(1))
+                self._allreduce(self.flat_g[:self.slot0 + 4], "C2")                                 # C2 (+ loss slot)
+            loss = self.flat_g[self.slot0:self.slot0 + 1].clone()
             if not self.shard:
                 tok = self._exchange_table_grads(tok)                                               # C1 (replicated tables)
-            self._allreduce(loss)
         # ---- global-norm clip (coef stays on the device) ----
         self.acc.zero_()
         if self.lazy and self.bitmaps:
@@ -390,7 +448,7 @@ class FusedTrainer:
                 # barrier that orders every peer's stores before the owner-side reduction).
                 n_slots = tok.numel()
                 gtok = torch.empty((self.world * n_slots,), device=self.dev, dtype=torch.int32)
-                torch.distributed.all_gather_into_tensor(gtok, tok.reshape(-1), group=self.pg)
+                self._allgather(gtok, tok.reshape(-1), "C1_selected_tokens_allgather")
                 ops.stage_apply(gtok, self.world, n_slots, self.stage_cap, spec.pad_id, self.world, self.rank,
                                 self.tables[BIG_TABLES[0]]["stage"], self.tables[BIG_TABLES[1]]["stage"],
                                 self.tables[BIG_TABLES[0]]["g"], self.tables[BIG_TABLES[1]]["g"])
@@ -402,7 +460,7 @@ class FusedTrainer:
             for n in BIG_TABLES:
                 ops.rows_sqnorm_bm(maps, n_maps, self.bm_words, self.n_shards, self.shard_rank, self.tables[n]["g"], self.acc)
             if self.shard:
-                self._allreduce(self.acc)           # C5: each owner contributes the squared norm of its rows
+                self._allreduce(self.acc, "C5_sqnorm")           # C5: each owner contributes the squared norm of its rows
         else:
             ops.rows_claim(tok, spec.pad_id, self.owner)
             for n in BIG_TABLES:
