@@ -104,13 +104,14 @@ int b200ctr_gemm_bf16(int transA, int transB, int64_t M, int64_t N, int64_t K,
                       const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                       const b200ctr_epilogue_t* epi_host, int split_k, void* workspace, void* stream);
 /* Same contract as b200ctr_gemm on the tcgen05 tensor cores at fp32-grade accuracy (the `amp: none` mode, SURVEY hard
- * part 5): each fp32 operand is split into bf16(a) + bf16(a - bf16(a)) on its way into shared memory and the product is
- * accumulated as hi.hi + lo.hi + hi.lo in the fp32 TMEM accumulator (three MMAs per k-step; relative error ~2^-16 per
- * product term, against 2^-8 for b200ctr_gemm_bf16).  Replaces the reference's true-fp32 cuBLAS matmul (TF32 off):
- * src/models/dare.py:64-69, qnn_alpha.py:89-97,123-129 under `amp: none`.  transA && transB is not built.            */
-int b200ctr_gemm_x3(int transA, int transB, int64_t M, int64_t N, int64_t K,
-                    const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
-                    const b200ctr_epilogue_t* epi_host, int split_k, void* workspace, void* stream);
+ * part 5): each fp32 operand is split into `parts` bf16 pieces on its way into shared memory (a0 = bf16(a), a1 = bf16(a - a0),
+ * a2 = bf16(a - a0 - a1)) and the product is accumulated as the sum of a_i.b_j over i + j < parts in the fp32 TMEM accumulator:
+ * parts = 2 -> 3 MMAs per k-step, error ~2^-17 per product term; parts = 3 -> 6 MMAs, dropped terms ~2^-24 (fp32 rounding).
+ * Replaces the reference's true-fp32 cuBLAS matmul (TF32 off): src/models/dare.py:64-69, qnn_alpha.py:89-97,123-129 under
+ * `amp: none`.  transA && transB is not built.                                                                          */
+int b200ctr_gemm_split(int parts, int transA, int transB, int64_t M, int64_t N, int64_t K,
+                       const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                       const b200ctr_epilogue_t* epi_host, int split_k, void* workspace, void* stream);
 /* Same contraction with operands ALREADY in bf16 (row-major, leading dimensions in elements): activations that their
  * producer kernel also emitted in bf16 (b200ctr_rowrms_fwd_bf16) and weights converted once per step (b200ctr_to_bf16);
  * staging is then a pure 16-byte copy into the UMMA core-matrix layout.  Persistent warp-specialised kernel.       */

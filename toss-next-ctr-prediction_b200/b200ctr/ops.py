@@ -92,9 +92,10 @@ def drop(p: float, seed: int, stream_id: int) -> Dropout:
 # "fp32": CUDA-core contraction, exact fp32 (the reference's default `amp: none`, TF32 off).
 # "bf16": tcgen05 tensor-core contraction with bf16 operands / fp32 accumulation (the reference's `amp: bf16` autocast).
 _PRECISION = "fp32"
-# contraction kernel of the fp32 mode: "x3" = tcgen05 split precision (b200ctr_gemm_x3), "fma" = CUDA-core fp32 (b200ctr_gemm)
+# contraction kernel of the fp32 mode (b200ctr_gemm_split): "x6" = tcgen05 split precision with 3 bf16 parts per operand (6 MMAs
+# per product, fp32-grade), "x3" = 2 parts (3 MMAs, ~1e-5), "fma" = the CUDA-core fp32 kernel (b200ctr_gemm)
 import os as _os
-FP32_GEMM = _os.environ.get("B200CTR_FP32_GEMM", "x3")
+FP32_GEMM = _os.environ.get("B200CTR_FP32_GEMM", "x6")
 
 
 def get_precision() -> str:
@@ -169,13 +170,17 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, out:
         use_tc = bool(tc)
     # `amp: none`: the same tcgen05 kernels in split-precision mode (3 x bf16 per product, fp32-grade accuracy) instead of
     # the CUDA-core fp32 contraction; tc=False (tests) and tiny shapes keep the exact FMA kernel
-    use_x3 = (tc is None and not use_tc and not bf16_in and _PRECISION == "fp32" and FP32_GEMM == "x3"
-              and not (trans_a and trans_b) and (M * N * K >= (1 << 20)) and K >= 32)
+    use_split = (tc is None and not use_tc and not bf16_in and _PRECISION == "fp32" and FP32_GEMM in ("x3", "x6")
+                 and not (trans_a and trans_b) and (M * N * K >= (1 << 20)) and K >= 32)
     if _PROF is not None:
         _TAG = f"[{M}x{N}x{K}{'T' if trans_a else 'N'}{'T' if trans_b else 'N'}]"
-    fn = lib.b200ctr_gemm_bf16in if bf16_in else (lib.b200ctr_gemm_bf16 if use_tc else (lib.b200ctr_gemm_x3 if use_x3 else lib.b200ctr_gemm))
-    _run("gemm_bf16" if (use_tc or bf16_in) else ("gemm_x3" if use_x3 else "gemm"), fn, int(trans_a), int(trans_b), M, N, K, _p(a),
-         _ld(a), _p(b), _ld(b), _p(out), _ld(out), ctypes.byref(e), split_k, _p(ws), _stream())
+    if use_split:
+        _run("gemm_" + FP32_GEMM, lib.b200ctr_gemm_split, 2 if FP32_GEMM == "x3" else 3, int(trans_a), int(trans_b), M, N, K, _p(a),
+             _ld(a), _p(b), _ld(b), _p(out), _ld(out), ctypes.byref(e), split_k, _p(ws), _stream())
+    else:
+        fn = lib.b200ctr_gemm_bf16in if bf16_in else (lib.b200ctr_gemm_bf16 if use_tc else lib.b200ctr_gemm)
+        _run("gemm_bf16" if (use_tc or bf16_in) else "gemm", fn, int(trans_a), int(trans_b), M, N, K, _p(a), _ld(a), _p(b), _ld(b),
+             _p(out), _ld(out), ctypes.byref(e), split_k, _p(ws), _stream())
     _count(2 if split_k > 1 else 1)
     return out
 

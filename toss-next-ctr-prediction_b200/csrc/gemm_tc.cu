@@ -33,13 +33,17 @@ constexpr int TC_STAGES = 2;
 //   KMAJOR  (global [mn][k], k contiguous): unit = (row r, k-group c), 16-B smem row = 8 consecutive k of row r.
 //   MNMAJOR (global [k][mn], mn contiguous): unit = (k row, mn-group g), 16-B smem row = 8 consecutive mn at row k.
 // Consecutive threads take consecutive smem rows (16-B stride) => conflict-free STS.128, 32-B global sectors.
-// X3 (split-precision mode, see gemm_tc_kernel): the tile is written twice -- bf16(v) at `off` and bf16(v - bf16(v)) at
-// off + R*TC_BK*2 -- so that hi + lo carries 16 mantissa bits of every fp32 operand.
-__device__ __forceinline__ uint32_t pack_bf16_resid(float a, float b, uint32_t hi) {
-  return pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+// SPLIT > 1 (split-precision mode, see gemm_tc_kernel): the tile is written SPLIT times -- bf16(v) at `off`, then the bf16
+// of what is still missing at off + part * R*TC_BK*2 -- so that the parts together carry 16 (SPLIT = 2) or 24 (SPLIT = 3)
+// mantissa bits of every fp32 operand.
+__device__ __forceinline__ void resid8(float* v, const uint4& p) {       // v -= the bf16 values just packed (exact in fp32)
+  v[0] -= __uint_as_float(p.x << 16); v[1] -= __uint_as_float(p.x & 0xffff0000u);
+  v[2] -= __uint_as_float(p.y << 16); v[3] -= __uint_as_float(p.y & 0xffff0000u);
+  v[4] -= __uint_as_float(p.z << 16); v[5] -= __uint_as_float(p.z & 0xffff0000u);
+  v[6] -= __uint_as_float(p.w << 16); v[7] -= __uint_as_float(p.w & 0xffff0000u);
 }
 
-template <int R, bool KMAJOR, bool X3 = false>
+template <int R, bool KMAJOR, int SPLIT = 1>
 __device__ __forceinline__ void stage_operand(unsigned char* smem, const float* __restrict__ g, int64_t ld, int64_t mn0,
                                               int64_t mn_end, int64_t k0, int64_t k_end, bool vec_ok, int tid) {
   constexpr int UNITS = R * 8;
@@ -76,31 +80,34 @@ __device__ __forceinline__ void stage_operand(unsigned char* smem, const float* 
     }
     uint4 packed = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     *reinterpret_cast<uint4*>(smem + off) = packed;
-    if (X3) {
-      uint4 lo = make_uint4(pack_bf16_resid(v[0], v[1], packed.x), pack_bf16_resid(v[2], v[3], packed.y),
-                            pack_bf16_resid(v[4], v[5], packed.z), pack_bf16_resid(v[6], v[7], packed.w));
-      *reinterpret_cast<uint4*>(smem + off + R * TC_BK * 2) = lo;
+#pragma unroll
+    for (int part = 1; part < SPLIT; ++part) {          // residual tiles: bf16(v - hi), bf16(v - hi - mid)
+      resid8(v, packed);
+      packed = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      *reinterpret_cast<uint4*>(smem + off + part * (R * TC_BK * 2)) = packed;
     }
   }
 }
 
-// X3 = split-precision fp32 emulation for the `amp: none` mode (SURVEY hard part 5): every fp32 operand is split into
-// a_hi = bf16(a), a_lo = bf16(a - a_hi) and the product is accumulated as a_hi.b_hi + a_lo.b_hi + a_hi.b_lo (three
-// tcgen05.mma per k-step into the same fp32 TMEM accumulator; the dropped a_lo.b_lo term is ~2^-16 relative).  Operands are
-// fp32 in HBM either way, so the kernel stays bound by the operand loads and the two extra MMAs are nearly free.
-template <int BN, bool TA, bool TB, bool X3 = false>
+// SPLIT = split-precision fp32 emulation for the `amp: none` mode (SURVEY hard part 5): every fp32 operand is split into
+// bf16 parts a = a0 + a1 (+ a2) (each the bf16 rounding of what the previous parts miss) and the product is accumulated as
+// the sum of a_i.b_j over i + j < SPLIT in the same fp32 TMEM accumulator: SPLIT = 2 -> 3 MMAs per k-step, error ~2^-17 per
+// product term; SPLIT = 3 -> 6 MMAs, dropped terms ~2^-24 = fp32 rounding itself.  Operands are fp32 in HBM either way, so
+// the kernel stays bound by the operand loads / the epilogue stores and the extra MMAs are nearly free.
+// NST = ring depth actually needed (1 when the whole contraction depth fits one k-tile: K <= 64, the encoder projections).
+template <int BN, bool TA, bool TB, int SPLIT = 1, int NST = TC_STAGES>
 __global__ void __launch_bounds__(TC_NT, 2)
 gemm_tc_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
                int64_t ldb, float* __restrict__ C, int64_t ldc, EpiDev epi, int split_k, int64_t k_chunk,
                float* __restrict__ partial, int vec_epi) {
   constexpr int A_HALF = TC_BM * TC_BK * 2, B_HALF = BN * TC_BK * 2;      // one bf16 tile; X3 stores the residual tile behind it
-  constexpr int A_BYTES = A_HALF * (X3 ? 2 : 1);
-  constexpr int B_BYTES = B_HALF * (X3 ? 2 : 1);
+  constexpr int A_BYTES = A_HALF * SPLIT;
+  constexpr int B_BYTES = B_HALF * SPLIT;
   constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* sA = smem;                              // [STAGES][A_BYTES]
-  unsigned char* sB = smem + TC_STAGES * A_BYTES;        // [STAGES][B_BYTES]
-  __shared__ __align__(8) unsigned long long mbar[TC_STAGES];
+  unsigned char* sA = smem;                              // [NST][A_BYTES]
+  unsigned char* sB = smem + NST * A_BYTES;              // [NST][B_BYTES]
+  __shared__ __align__(8) unsigned long long mbar[NST];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -115,7 +122,7 @@ gemm_tc_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int
   }
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TC_STAGES; ++s) mbar_init(smem_u32(&mbar[s]), 1);
+    for (int s = 0; s < NST; ++s) mbar_init(smem_u32(&mbar[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -131,13 +138,13 @@ gemm_tc_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int
   constexpr uint32_t LBO_A = TC_BM * 16, LBO_B = BN * 16, SBO = 128;
 
   for (int kt = 0; kt < KT; ++kt) {
-    const int s = kt % TC_STAGES;
-    if (kt >= TC_STAGES) mbar_wait(smem_u32(&mbar[s]), (uint32_t)(((kt / TC_STAGES) - 1) & 1));   // stage free again
+    const int s = kt % NST;
+    if (kt >= NST) mbar_wait(smem_u32(&mbar[s]), (uint32_t)(((kt / NST) - 1) & 1));   // stage free again
     const int64_t k0 = kbeg + (int64_t)kt * TC_BK;
     // A operand: opA(A)[m,k].  !TA: stored [M,K] -> K-major.  TA: stored [K,M] -> MN-major.
-    stage_operand<TC_BM, !TA, X3>(sA + s * A_BYTES, A, lda, m0, M, k0, kend, a_vec, tid);
+    stage_operand<TC_BM, !TA, SPLIT>(sA + s * A_BYTES, A, lda, m0, M, k0, kend, a_vec, tid);
     // B operand: opB(B)[k,n] as the UMMA "B" (N x K).  TB: stored [N,K] -> K-major.  !TB: stored [K,N] -> MN-major.
-    stage_operand<BN, TB, X3>(sB + s * B_BYTES, B, ldb, n0, N, k0, kend, b_vec, tid);
+    stage_operand<BN, TB, SPLIT>(sB + s * B_BYTES, B, ldb, n0, N, k0, kend, b_vec, tid);
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -148,15 +155,18 @@ gemm_tc_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int
         const uint64_t da = make_desc(a_base + k4 * 2 * LBO_A, LBO_A, SBO);
         const uint64_t db = make_desc(b_base + k4 * 2 * LBO_B, LBO_B, SBO);
         umma_bf16(tmem_d, da, db, idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
-        if (X3) {
-          umma_bf16(tmem_d, make_desc(a_base + A_HALF + k4 * 2 * LBO_A, LBO_A, SBO), db, idesc, 1u);      // a_lo . b_hi
-          umma_bf16(tmem_d, da, make_desc(b_base + B_HALF + k4 * 2 * LBO_B, LBO_B, SBO), idesc, 1u);      // a_hi . b_lo
-        }
+#pragma unroll
+        for (int i = 0; i < SPLIT; ++i)
+#pragma unroll
+          for (int j = 0; j < SPLIT - i; ++j)
+            if (i + j > 0)                                   // the cross terms a_i . b_j, i + j < SPLIT
+              umma_bf16(tmem_d, make_desc(a_base + i * A_HALF + k4 * 2 * LBO_A, LBO_A, SBO),
+                        make_desc(b_base + j * B_HALF + k4 * 2 * LBO_B, LBO_B, SBO), idesc, 1u);
       }
       umma_commit(smem_u32(&mbar[s]));
     }
   }
-  if (KT > 0) mbar_wait(smem_u32(&mbar[(KT - 1) % TC_STAGES]), (uint32_t)(((KT - 1) / TC_STAGES) & 1));
+  if (KT > 0) mbar_wait(smem_u32(&mbar[(KT - 1) % NST]), (uint32_t)(((KT - 1) / NST) & 1));
   tc_fence_after();
   __syncthreads();     // every warp is past its last smem/MMA dependency: the stage buffers become epilogue scratch
 
@@ -238,7 +248,7 @@ gemm_tc_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int
 constexpr int WS_NT = 13 * 32;     // 416 threads in both splits
 
 
-template <int R, bool KMAJOR, int WS_PROD_THREADS, bool X3 = false>
+template <int R, bool KMAJOR, int WS_PROD_THREADS, int SPLIT = 1>
 __device__ __forceinline__ void stage_operand_ws(unsigned char* smem, const float* __restrict__ g, int64_t ld, int64_t mn0,
                                                  int64_t mn_end, int64_t k0, int64_t k_end, bool vec_ok, int ptid) {
   constexpr int UNITS = R * 8;
@@ -287,10 +297,14 @@ __device__ __forceinline__ void stage_operand_ws(unsigned char* smem, const floa
     for (int q = 0; q < UNR; ++q) {
       uint4 packed = make_uint4(pack_bf16(va[q].x, va[q].y), pack_bf16(va[q].z, va[q].w), pack_bf16(vb[q].x, vb[q].y), pack_bf16(vb[q].z, vb[q].w));
       *reinterpret_cast<uint4*>(smem + off[q]) = packed;
-      if (X3) {
-        uint4 lo = make_uint4(pack_bf16_resid(va[q].x, va[q].y, packed.x), pack_bf16_resid(va[q].z, va[q].w, packed.y),
-                              pack_bf16_resid(vb[q].x, vb[q].y, packed.z), pack_bf16_resid(vb[q].z, vb[q].w, packed.w));
-        *reinterpret_cast<uint4*>(smem + off[q] + R * TC_BK * 2) = lo;
+      if (SPLIT > 1) {
+        float v[8] = {va[q].x, va[q].y, va[q].z, va[q].w, vb[q].x, vb[q].y, vb[q].z, vb[q].w};
+#pragma unroll
+        for (int part = 1; part < SPLIT; ++part) {
+          resid8(v, packed);
+          packed = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          *reinterpret_cast<uint4*>(smem + off[q] + part * (R * TC_BK * 2)) = packed;
+        }
       }
     }
   }
@@ -300,7 +314,7 @@ __device__ __forceinline__ void stage_operand_ws(unsigned char* smem, const floa
 // registers in between, so a producer thread can keep several ring stages of loads in flight (the operand tiles mostly
 // come from L2, ~1 us away; with register staging only ~32 KB per SM were in flight and the tensor pipe starved).
 // Partially valid rows use the src-size form (zero fill); rows out of range are zeroed with a plain store.
-template <int R, bool KMAJOR, int WS_PROD_THREADS, bool X3 = false>
+template <int R, bool KMAJOR, int WS_PROD_THREADS, int SPLIT = 1>
 __device__ __forceinline__ void stage_operand_ws(unsigned char* smem, const __nv_bfloat16* __restrict__ g, int64_t ld, int64_t mn0,
                                                  int64_t mn_end, int64_t k0, int64_t k_end, bool vec_ok, int ptid) {
   constexpr int UNITS = R * 8;
@@ -338,15 +352,15 @@ __device__ __forceinline__ void stage_operand_ws(unsigned char* smem, const __nv
   }
 }
 
-template <int BN, bool TA, bool TB, int STAGES, int WS_PROD_WARPS, int WS_EPI_WARPS, typename TIn, bool X3 = false>
+template <int BN, bool TA, bool TB, int STAGES, int WS_PROD_WARPS, int WS_EPI_WARPS, typename TIn, int SPLIT = 1>
 __global__ void __launch_bounds__(WS_NT, 1)
 gemm_tc_ws_kernel(int64_t M, int64_t N, int64_t K, const TIn* __restrict__ A, int64_t lda, const TIn* __restrict__ B,
                   int64_t ldb, float* __restrict__ C, int64_t ldc, EpiDev epi, int split_k, int64_t k_chunk,
                   float* __restrict__ partial, int vec_epi, int tiles_m, int tiles_n) {
-  static_assert(!X3 || std::is_same<TIn, float>::value, "split precision applies to fp32 operands");
+  static_assert(SPLIT == 1 || std::is_same<TIn, float>::value, "split precision applies to fp32 operands");
   constexpr int A_HALF = TC_BM * TC_BK * 2, B_HALF = BN * TC_BK * 2;
-  constexpr int A_BYTES = A_HALF * (X3 ? 2 : 1);
-  constexpr int B_BYTES = B_HALF * (X3 ? 2 : 1);
+  constexpr int A_BYTES = A_HALF * SPLIT;
+  constexpr int B_BYTES = B_HALF * SPLIT;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int ACC_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);     // columns per accumulator buffer
   constexpr int TMEM_COLS = 2 * ACC_COLS;
@@ -395,8 +409,8 @@ gemm_tc_ws_kernel(int64_t M, int64_t N, int64_t K, const TIn* __restrict__ A, in
         unsigned char* sa = smem + s * STAGE_BYTES;
         unsigned char* sb = sa + A_BYTES;
         const int64_t k0 = kbeg + (int64_t)kt * TC_BK;
-        stage_operand_ws<TC_BM, !TA, WS_PROD_WARPS * 32, X3>(sa, A, lda, m0, M, k0, kend, a_vec, tid);
-        stage_operand_ws<BN, TB, WS_PROD_WARPS * 32, X3>(sb, B, ldb, n0, N, k0, kend, b_vec, tid);
+        stage_operand_ws<TC_BM, !TA, WS_PROD_WARPS * 32, SPLIT>(sa, A, lda, m0, M, k0, kend, a_vec, tid);
+        stage_operand_ws<BN, TB, WS_PROD_WARPS * 32, SPLIT>(sb, B, ldb, n0, N, k0, kend, b_vec, tid);
         if (ASYNC_STAGING) {
           // stage g is in flight; publish stage g - LAG once this thread's (and, after the warp sync, this warp's) copies of
           // it have landed.  LAG = STAGES - 1 keeps the whole ring in flight without ever waiting on a slot the MMA warp
@@ -448,10 +462,13 @@ gemm_tc_ws_kernel(int64_t M, int64_t N, int64_t K, const TIn* __restrict__ A, in
             const uint64_t da = make_desc(a_base + k4 * 2 * LBO_A, LBO_A, SBO);
             const uint64_t db = make_desc(b_base + k4 * 2 * LBO_B, LBO_B, SBO);
             umma_bf16(tmem_d, da, db, idesc, (kt > 0 || k4 > 0) ? 1u : 0u);
-            if (X3) {
-              umma_bf16(tmem_d, make_desc(a_base + A_HALF + k4 * 2 * LBO_A, LBO_A, SBO), db, idesc, 1u);
-              umma_bf16(tmem_d, da, make_desc(b_base + B_HALF + k4 * 2 * LBO_B, LBO_B, SBO), idesc, 1u);
-            }
+#pragma unroll
+            for (int i = 0; i < SPLIT; ++i)
+#pragma unroll
+              for (int j = 0; j < SPLIT - i; ++j)
+                if (i + j > 0)
+                  umma_bf16(tmem_d, make_desc(a_base + i * A_HALF + k4 * 2 * LBO_A, LBO_A, SBO),
+                            make_desc(b_base + j * B_HALF + k4 * 2 * LBO_B, LBO_B, SBO), idesc, 1u);
           }
           umma_commit(smem_u32(&empty_bar[s]));            // ring slot reusable once these MMAs have read it
         }
@@ -546,23 +563,25 @@ gemm_tc_ws_kernel(int64_t M, int64_t N, int64_t K, const TIn* __restrict__ A, in
   }
 }
 
-template <int BN, typename TIn = float, bool X3 = false>
+template <int BN, typename TIn = float, int SPLIT = 1>
 static int launch_tc_ws(int tA, int tB, int64_t M, int64_t N, int64_t K, const TIn* A, int64_t lda, const TIn* B,
                         int64_t ldb, float* C, int64_t ldc, const EpiDev& e, int split_k, float* ws, cudaStream_t st) {
   int64_t k_chunk = ceil_div(ceil_div(K, (int64_t)split_k), (int64_t)TC_BK) * TC_BK;
   if (k_chunk <= 0) k_chunk = TC_BK;
   const int tiles_m = (int)ceil_div(M, (int64_t)TC_BM), tiles_n = (int)ceil_div(N, (int64_t)BN);
   const int64_t total = (int64_t)tiles_m * tiles_n * split_k;
-  static_assert(!X3 || BN <= 128, "split precision: tiles up to 128 columns (two bf16 tiles per operand per stage)");
-  constexpr int STAGES = X3 ? (BN <= 64 ? 4 : 3) : (BN <= 128 ? 5 : (BN <= 192 ? 4 : 3));
+  constexpr bool X3 = SPLIT > 1;
+  static_assert(!X3 || BN <= 128, "split precision: tiles up to 128 columns (SPLIT bf16 tiles per operand per stage)");
+  // ring depth: what fits next to the epilogue scratch in 227 KB
+  constexpr int STAGES = SPLIT == 3 ? 2 : (SPLIT == 2 ? (BN <= 64 ? 4 : 3) : (BN <= 128 ? 5 : (BN <= 192 ? 4 : 3)));
   // deep-K: loads dominate -> 8 producer warps; else 8 epilogue warps (split precision: always 8 producers, 4 epilogue warps)
   const bool deep_k = X3 || k_chunk > 512;
-  size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) * (X3 ? 2 : 1) + (size_t)(X3 ? 4 : 8) * 32 * 36 * 4;
+  size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) * SPLIT + (size_t)(X3 ? 4 : 8) * 32 * 36 * 4;
   const int vec = epi_vec_ok(e, C, ldc, N) ? 1 : 0;
   const int grid = (int)std::min<int64_t>(total, (int64_t)num_sms());
 #define WS_LAUNCH1(TA_, TB_, PW_, EW_)                                                                            \
   do {                                                                                                            \
-    auto fn = gemm_tc_ws_kernel<BN, TA_, TB_, STAGES, PW_, EW_, TIn, X3>;                                         \
+    auto fn = gemm_tc_ws_kernel<BN, TA_, TB_, STAGES, PW_, EW_, TIn, SPLIT>;                                         \
     cudaError_t ee = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
     if (ee != cudaSuccess) return cuda_fail(ee, "cudaFuncSetAttribute(gemm_tc_ws smem)");                         \
     fn<<<grid, WS_NT, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e, split_k, k_chunk, ws, vec, tiles_m, tiles_n); \
@@ -584,18 +603,18 @@ static int launch_tc_ws(int tA, int tB, int64_t M, int64_t N, int64_t K, const T
   return B200CTR_OK;
 }
 
-template <int BN, bool X3 = false>
+template <int BN, int SPLIT = 1, int NST = TC_STAGES>
 static int launch_tc(int tA, int tB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                      int64_t ldb, float* C, int64_t ldc, const EpiDev& e, int split_k, float* ws, cudaStream_t st) {
   int64_t k_chunk = ceil_div(ceil_div(K, (int64_t)split_k), (int64_t)TC_BK) * TC_BK;
   if (k_chunk <= 0) k_chunk = TC_BK;
   dim3 grid((unsigned)ceil_div(N, (int64_t)BN), (unsigned)ceil_div(M, (int64_t)TC_BM), (unsigned)split_k);
-  size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) * (X3 ? 2 : 1);
+  size_t smem = (size_t)NST * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) * SPLIT;
   smem = std::max(smem, (size_t)8 * 32 * 36 * 4);
   const int vec = epi_vec_ok(e, C, ldc, N) ? 1 : 0;
 #define TC_LAUNCH(TA_, TB_)                                                                                       \
   do {                                                                                                            \
-    auto fn = gemm_tc_kernel<BN, TA_, TB_, X3>;                                                                   \
+    auto fn = gemm_tc_kernel<BN, TA_, TB_, SPLIT, NST>;                                                                  \
     if (smem + 1024 > 48 * 1024) {                                                                                \
       cudaError_t ee = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
       if (ee != cudaSuccess) return cuda_fail(ee, "cudaFuncSetAttribute(gemm_tc smem)");                          \
@@ -661,25 +680,42 @@ extern "C" int b200ctr_gemm_bf16(int transA, int transB, int64_t M, int64_t N, i
   return B200CTR_OK;
 }
 
-// ---- split-precision (3 x bf16) contraction of fp32 operands: the tensor-core path of the `amp: none` mode ----
-template <int BN> static int launch_tc_x3(int tA, int tB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
-                                          int64_t ldb, float* C, int64_t ldc, const EpiDev& e, int split_k, float* ws, cudaStream_t st) {
-  return b200ctr::launch_tc<BN, true>(tA, tB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
+// ---- split-precision contraction of fp32 operands: the tensor-core path of the `amp: none` mode ----
+namespace b200ctr {
+template <int SPLIT>
+static int gemm_split(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                      int64_t ldb, float* C, int64_t ldc, const EpiDev& e, int split_k, float* ws, cudaStream_t st) {
+  const int64_t k_per_split = ceil_div(K, (int64_t)split_k);
+#define SP_ARGS transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st
+  if (k_per_split <= TC_BK) {
+    // one k-tile: a single ring slot, so 2-3 CTAs stay resident per SM and one CTA's epilogue stores overlap the others' loads
+    if (N <= 64) return launch_tc<64, SPLIT, 1>(SP_ARGS);
+    if (N <= 96) return launch_tc<96, SPLIT, 1>(SP_ARGS);
+    return launch_tc<128, SPLIT, 1>(SP_ARGS);
+  }
+  if (k_per_split <= 512) {
+    if (N <= 64) return launch_tc<64, SPLIT, 2>(SP_ARGS);
+    if (N <= 96) return launch_tc<96, SPLIT, 2>(SP_ARGS);
+    return launch_tc<128, SPLIT, 2>(SP_ARGS);
+  }
+  if (N <= 64) return launch_tc_ws<64, float, SPLIT>(SP_ARGS);
+  if (N <= 96) return launch_tc_ws<96, float, SPLIT>(SP_ARGS);
+  return launch_tc_ws<128, float, SPLIT>(SP_ARGS);
+#undef SP_ARGS
 }
-template <int BN> static int launch_tc_ws_x3(int tA, int tB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
-                                             int64_t ldb, float* C, int64_t ldc, const EpiDev& e, int split_k, float* ws, cudaStream_t st) {
-  return b200ctr::launch_tc_ws<BN, float, true>(tA, tB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
-}
+}  // namespace b200ctr
 
-extern "C" int b200ctr_gemm_x3(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
-                               const float* B, int64_t ldb, float* C, int64_t ldc, const b200ctr_epilogue_t* eh,
-                               int split_k, void* workspace, void* stream) {
-  B200_REQUIRE(M >= 0 && N >= 0 && K >= 0, B200CTR_E_INVALID_ARG, "gemm_x3: negative dimension");
+extern "C" int b200ctr_gemm_split(int parts, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                                  const float* B, int64_t ldb, float* C, int64_t ldc, const b200ctr_epilogue_t* eh,
+                                  int split_k, void* workspace, void* stream) {
+  B200_REQUIRE(parts == 2 || parts == 3, B200CTR_E_INVALID_ARG, "gemm_split: parts must be 2 (3 MMAs per product) or 3 (6 MMAs)");
+  B200_REQUIRE(M >= 0 && N >= 0 && K >= 0, B200CTR_E_INVALID_ARG, "gemm_split: negative dimension");
   if (M == 0 || N == 0) return B200CTR_OK;
-  B200_REQUIRE(A && B && C, B200CTR_E_INVALID_ARG, "gemm_x3: null operand");
-  B200_REQUIRE(split_k >= 1 && split_k <= 1024, B200CTR_E_INVALID_ARG, "gemm_x3: split_k out of range");
-  B200_REQUIRE(split_k == 1 || workspace, B200CTR_E_INVALID_ARG, "gemm_x3: split_k > 1 needs a workspace");
-  B200_REQUIRE(ceil_div(M, (int64_t)TC_BM) <= 65535, B200CTR_E_UNSUPPORTED_SHAPE, "gemm_x3: M too large for one launch");
+  B200_REQUIRE(A && B && C, B200CTR_E_INVALID_ARG, "gemm_split: null operand");
+  B200_REQUIRE(split_k >= 1 && split_k <= 1024, B200CTR_E_INVALID_ARG, "gemm_split: split_k out of range");
+  B200_REQUIRE(split_k == 1 || workspace, B200CTR_E_INVALID_ARG, "gemm_split: split_k > 1 needs a workspace");
+  B200_REQUIRE(ceil_div(M, (int64_t)TC_BM) <= 65535, B200CTR_E_UNSUPPORTED_SHAPE, "gemm_split: M too large for one launch");
+  B200_REQUIRE(!(transA && transB), B200CTR_E_UNSUPPORTED_SHAPE, "gemm_split: transA && transB is not built");
   EpiDev e{};
   e.alpha = 1.f;
   if (eh) {
@@ -687,20 +723,14 @@ extern "C" int b200ctr_gemm_x3(int transA, int transB, int64_t M, int64_t N, int
     e.drop = eh->drop; e.mask_mode = eh->mask_mode; e.mask_src = eh->mask_src; e.ld_mask = eh->ld_mask;
     e.mask_scale = eh->mask_scale; e.residual = eh->residual; e.ld_res = eh->ld_res;
     e.accum = eh->accum; e.ld_accum = eh->ld_accum;
-    B200_REQUIRE(e.mask_mode == B200CTR_MASK_NONE || e.mask_src, B200CTR_E_INVALID_ARG, "gemm_x3: mask_mode without mask_src");
+    B200_REQUIRE(e.mask_mode == B200CTR_MASK_NONE || e.mask_src, B200CTR_E_INVALID_ARG, "gemm_split: mask_mode without mask_src");
   }
   cudaStream_t st = as_stream(stream);
   float* ws = (float*)workspace;
-  int rc;
-#define X3_DISPATCH(FN)                                                                                          \
-  if (N <= 64) rc = FN<64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);                 \
-  else if (N <= 96) rc = FN<96>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);            \
-  else rc = FN<128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
-  const int64_t k_per_split = ceil_div(K, (int64_t)split_k);
-  if (k_per_split <= 512) { X3_DISPATCH(launch_tc_x3) } else { X3_DISPATCH(launch_tc_ws_x3) }
-#undef X3_DISPATCH
+  int rc = parts == 2 ? b200ctr::gemm_split<2>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st)
+                      : b200ctr::gemm_split<3>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st);
   if (rc) return rc;
-  B200_LAUNCH_CHECK("gemm_tc_kernel(x3)");
+  B200_LAUNCH_CHECK("gemm_tc_kernel(split precision)");
   if (split_k > 1) {
     rc = launch_splitk_reduce((const float*)workspace, split_k, M, N, C, ldc, e, st);
     if (rc) return rc;
