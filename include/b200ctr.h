@@ -408,6 +408,21 @@ int b200ctr_rowopt_flush(int32_t* state, float* p, float* m, float* v, float* em
 
 /* ---- fold-ensemble  (infer.py:122-158, utils/metrics.py:68-71): p = sigmoid(mean_m logit(clamp(p_m))) ---- */
 int b200ctr_logit_mean(const float* probs, int n_models, int64_t B, float eps, float* out, void* stream);
+/* The whole per-batch tail of infer.py:108-158 for `ensemble.method: logit_mean` in one launch: for every fold m,
+ * p_m = sigmoid(z_m / T_m) (T_m = 1 when the fold has no temperature calibrator: utils/calibration.py:17-21,103-110),
+ * clipped to [eps, 1-eps] exactly where the reference clips (Calibrator.predict_proba and infer.py:122), then
+ * out = sigmoid(mean_m logit(p_m)) (utils/metrics.py:30-32,68-71).  logits (n_models, B) row-major; inv_T may be NULL. */
+int b200ctr_ensemble_logit_mean(const float* logits, const float* inv_T, int n_models, int64_t B, float eps, float* out,
+                                void* stream);
+
+/* ---- batched shard reader  (data/dataset.py:28-43,98-124): host row gather + device-side widening ---- */
+/* dst row (dst_idx ? dst_idx[i] : i) <- src row src_idx[i] for i < n, rows of row_bytes bytes; n_threads host threads.  Host
+ * memory only (memory-mapped .npy payload -> pinned staging buffer); makes no CUDA call.                              */
+int b200ctr_gather_rows(const void* src, int64_t row_bytes, const int64_t* src_idx, const int64_t* dst_idx, int64_t n,
+                        void* dst, int n_threads);
+/* On-disk dtypes -> the collate contract's, on the device: kind 0 uint8 -> float32 (X_mask), 1 int8 -> float32 (y),
+ * 2 int32 -> int64 (ids; the kernels also take int32 directly).                                                      */
+int b200ctr_widen(int kind, const void* in, int64_t n, void* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -922,6 +922,17 @@ def logit_mean(probs, eps=1e-7):
     return out
 
 
+def ensemble_logit_mean(logits, inv_T=None, eps=1e-7):
+    """(M, B) fold logits [+ per-fold 1/T] -> sigmoid(mean_m logit(clip(sigmoid(z_m / T_m)))): infer.py:108-158 in one launch."""
+    lib = _lib.load()
+    M, B = logits.shape
+    assert logits.is_contiguous() and (inv_T is None or (inv_T.numel() == M and inv_T.dtype == torch.float32))
+    out = torch.empty((B,), device=logits.device, dtype=torch.float32)
+    _run("ensemble_logit_mean", lib.b200ctr_ensemble_logit_mean, _p(_f32(logits)), _p(inv_T), M, B, eps, _p(out), _stream())
+    _count()
+    return out
+
+
 # ---- row-lazy table optimiser -------------------------------------------------------------------------------------
 class RowHistory:
     """Device-side per-step constants for the row-lazy AdamW/EMA (see csrc/rowopt.cu) + their host recurrences."""

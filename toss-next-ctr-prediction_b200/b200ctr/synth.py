@@ -54,6 +54,7 @@ class ToySchema:
         lens[u < 0.01] = 0
         short = (u >= 0.01) & (u < 0.02)
         lens[short] = rng.integers(1, max(2, K), size=int(short.sum()))
+        lens = np.minimum(lens, L)
         tot = int(lens.sum())
         r = np.searchsorted(self.tok_cdf, rng.random(tot), side="right")
         toks = self.tok_perm[np.minimum(r, TOKEN_RANGE - 1)]

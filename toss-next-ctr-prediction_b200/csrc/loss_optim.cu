@@ -144,9 +144,33 @@ __global__ void logit_mean_kernel(const float* __restrict__ probs, int n_models,
   out[i] = sigmoidf_(s / (float)n_models);
 }
 
+// infer.py:108-158 for logit_mean: calibrate (temperature), clip, logit, mean over folds, sigmoid -- one pass over (M, B)
+__global__ void ensemble_logit_mean_kernel(const float* __restrict__ logits, const float* __restrict__ inv_T, int n_models,
+                                           int64_t B, float eps, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  float s = 0.f;
+  for (int m = 0; m < n_models; ++m) {
+    float z = logits[(int64_t)m * B + i];
+    if (inv_T) z = fminf(fmaxf(z * inv_T[m], -50.f), 50.f);            // calibration._sigmoid_stable_numpy clips the scaled logit
+    float p = fminf(fmaxf(sigmoidf_(z), eps), 1.f - eps);
+    s += logf(p) - log1pf(-p);
+  }
+  out[i] = sigmoidf_(s / (float)n_models);
+}
+
 }  // namespace b200ctr
 
 using namespace b200ctr;
+
+extern "C" int b200ctr_ensemble_logit_mean(const float* logits, const float* inv_T, int n_models, int64_t B, float eps, float* out,
+                                           void* stream) {
+  B200_REQUIRE(logits && out && n_models >= 1, B200CTR_E_INVALID_ARG, "ensemble_logit_mean: bad argument");
+  if (B == 0) return B200CTR_OK;
+  ensemble_logit_mean_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, as_stream(stream)>>>(logits, inv_T, n_models, B, eps, out);
+  B200_LAUNCH_CHECK("ensemble_logit_mean_kernel");
+  return B200CTR_OK;
+}
 
 extern "C" int b200ctr_bce_wll(const float* logits, const float* aux, const float* y, float aux_w, int64_t B,
                                const int32_t* counts_override, float* loss, int32_t* counts, float* dlogits, float* daux,
