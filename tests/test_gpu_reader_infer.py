@@ -63,7 +63,7 @@ def test_fused_trainer_consumes_reader_batches(tmp_path):
             tr.step(b, y)
         finals.append({k: v.detach().cpu().clone() for k, v in m.state_dict().items() if not k.startswith("dare.emb_")})
     for k in finals[0]:
-        assert max_err_scaled(finals[1][k], finals[0][k]) < 1e-5, k          # only the table-gradient atomics' order differs
+        assert max_err_scaled(finals[1][k], finals[0][k]) < 1e-4, k          # only the table-gradient atomics' order differs (fed through 4 Adam steps)
 
 
 @pytest.mark.parametrize("with_T", [False, True])

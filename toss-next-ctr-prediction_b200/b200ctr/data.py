@@ -126,7 +126,7 @@ class BatchedShardReader:
                 out["y"] = y
             ev = torch.cuda.Event()
             ev.record(stream)
-        out["groups"] = narrow["groups"].long()
+        out["groups"] = narrow["groups"].long().clone()          # the staging slot is refilled two batches later
         if ids is not None:
             out["ids"] = ids
         out["_ready"] = ev
