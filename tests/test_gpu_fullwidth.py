@@ -8,7 +8,7 @@ dimension or hand-off in the full-size integration fails here.
 
 Stated tolerances (max-abs error / max-abs of the reference tensor, plus relative error of the whole-tensor L2 norm):
   fp32 path (`amp: none`)   : 1e-4 logits / prob / aux / every gradient; 2e-3 parameters + EMA after 2 AdamW steps at lr 3e-3
-                              (bf16: 1e-1 -- sign flips of near-zero gradients become full lr-sized steps under Adam)
+                              (bf16: 1.5e-1 -- sign flips of near-zero gradients become full lr-sized steps under Adam)
   bf16 path (`amp: bf16`)   : 2e-2 logits / aux, loss within 2e-3, whole-tensor gradient norms 3e-2; elementwise, every gradient's
                               stored subsample: relative L2 error 1.5e-1, max-abs error 3.5e-1 of max|ref| (measured: <= 0.13 /
                               0.28, largest on embedding-table rows that collect a handful of samples' gradients after they
@@ -141,7 +141,7 @@ def test_bf16_error_is_no_larger_than_the_reference_autocast_error():
     assert not worse, worse
 
 
-@pytest.mark.parametrize("prec,tol", [("none", 2e-3), ("bf16", 1e-1)])
+@pytest.mark.parametrize("prec,tol", [("none", 2e-3), ("bf16", 1.5e-1)])
 def test_fused_trainer_two_steps_at_full_width(prec, tol):
     """FusedTrainer (flat buffers, fused clip / AdamW / EMA, row-lazy table optimizer) on the K = 60 concat case: loss and
     global gradient norm of both steps, parameters and EMA shadows after the second step."""

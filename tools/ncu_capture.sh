@@ -19,6 +19,7 @@ rm -f $OUT/${TAG}_top.ncu-rep
 # (3) the fp32 mode's split-precision GEMMs (one step's worth), with source correlation for the dominant shape
 CMD32="python bench.py --amp none --quick --steps 2 --warmup 3 --no-cpu-baseline --batches 8"
 $CMD32 > $OUT/${TAG}_plain32.json 2> $OUT/${TAG}_plain32.err || { echo "fp32 plain run failed"; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:'gemm_tc' --launch-skip 200 -c 24 -o $OUT/${TAG}_gemm32 $CMD32 > $OUT/${TAG}_ncu3.log 2>&1
+ncu --set full --clock-control none -k regex:'gemm_tc' --launch-skip 200 -c 16 -o $OUT/${TAG}_gemm32 $CMD32 > $OUT/${TAG}_ncu3.log 2>&1
 ncu -i $OUT/${TAG}_gemm32.ncu-rep --page raw --csv > $OUT/${TAG}_gemm32_raw.csv 2>/dev/null
+rm -f $OUT/${TAG}_gemm32.ncu-rep          # gpurun merges at most 64 MiB back: only the CSV exports travel
 ls -la $OUT/${TAG}_*
