@@ -139,6 +139,9 @@ int b200ctr_numbin_fold(const float* w, const float* b, const float* w_out, floa
                         int F, int fe, int D, void* stream);
 int b200ctr_numbin_fwd(const float* x, const float* P, const float* Q, float* out, int64_t ld_b,
                        float* mean_out, int64_t ld_mean, int64_t B, int F, int D, void* stream);
+/* numbin_bwd writes PARTIAL sums: dP / dQ are (b200ctr_numbin_bwd_rows(B), F*D) matrices, one row per 64-sample chunk, every
+ * entry written (no atomics); the caller sums the rows in order (b200ctr_colsum) -> bit-identical runs.                 */
+int64_t b200ctr_numbin_bwd_rows(int64_t B);
 int b200ctr_numbin_bwd(const float* x, const float* dout, int64_t ld_b, const float* dmean, int64_t ld_dmean,
                        float* dP, float* dQ, int64_t B, int F, int D, void* stream);
 int b200ctr_numbin_unfold(const float* dP, const float* dQ, const float* w, const float* b, const float* w_out,
@@ -153,11 +156,16 @@ int b200ctr_cat_fwd(const void* x_cat, int idx_is_64, const float* const* tables
                     const int32_t* dims, const int32_t* cards, float* out, int64_t ld_b,
                     float* mean_out, int64_t ld_mean, int q_idx, float* q_out,
                     int64_t B, int Fc, int D, b200ctr_dropout_t drop, void* stream);
+/* cat_bwd is deterministic (no float atomics): kernel 1 writes every sample's contribution W_c^T g to a (B, sum_dims) workspace
+ * and per-CTA partials of dW_c; kernel 2 (thread per table row) adds the contributions of the samples that hit the row in
+ * ascending sample order; kernel 3 adds the dW_c partials in CTA order.  sum_dims = sum_c d_c, max_card = max_c card_c;
+ * dtables / dprojs are accumulated into (single writer per element).                                                  */
+int64_t b200ctr_cat_bwd_workspace_bytes(int64_t B, int sum_dims);
 int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
                     const int32_t* dims, const int32_t* cards, const float* dout, int64_t ld_b,
-                    const float* dmean, int64_t ld_dmean, int q_idx, const float* dq,
-                    float* const* dtables, float* const* dprojs,
-                    int64_t B, int Fc, int D, b200ctr_dropout_t drop, void* stream);
+                    const float* dmean, int64_t ld_dmean, int q_idx, const float* dq, float* const* dtables,
+                    float* const* dprojs, int64_t B, int Fc, int D, int sum_dims, int max_card,
+                    b200ctr_dropout_t drop, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- query mix  (wrapper.py:128-136): q = a*s1 + b*s2 ; bwd: ds2pre = b*dq*(s2>0) --------------------- */
 int b200ctr_axpby(const float* x, const float* y, float a, float b, float* out, int64_t n, void* stream);
@@ -201,7 +209,7 @@ int b200ctr_retrieve_bwd_sharded(const int32_t* tok, const float* q, const float
 int b200ctr_retrieve_bwd_staged(const int32_t* tok, const float* q, const float* const* att_shards, int n_shards,
                                 const float* dsel_rep, const float* dvals, int64_t B, int K, int D, int pad_id,
                                 float* dq, float* const* datt_shards, float* const* drep_shards,
-                                float* const* stage_att, float* const* stage_rep, int my_rank, int64_t stage_cap,
+                                float* const* stage_att, float* const* stage_rep, int my_rank, int64_t stage_cap, int stage_all,
                                 void* stream);
 int b200ctr_stage_apply(const int32_t* gtok, int n_src, int64_t n_slots, int64_t stage_cap, int pad_id, int n_shards,
                         int rank, const float* stage_att, const float* stage_rep, float* g_att, float* g_rep, int D,
@@ -214,6 +222,8 @@ int b200ctr_stage_apply(const int32_t* gtok, int n_src, int64_t n_slots, int64_t
  * add_rmsnorm: s = a + b ; y = w * s * rsqrt(mean(s^2)+eps) ; saves s and r.                                 */
 int b200ctr_attn_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D,
                      float* o, float* lse, b200ctr_dropout_t drop, void* stream);
+/* drelmean (both attention backward kernels): a ZEROED (B, 2*max_len+1) matrix of per-sample partial rows, written without
+ * atomics; d relmean = its column sum in sample order (b200ctr_colsum) -> bit-identical runs.  NULL = not wanted.        */
 int b200ctr_attn_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
                      const float* d_o, int64_t B, int K, int H, int D, float* dqkv, float* drelmean,
                      b200ctr_dropout_t drop, void* stream);
@@ -231,7 +241,9 @@ int b200ctr_attn_tc_bwd(const float* qkv, const float* relmean, int max_len, con
                         const uint32_t* keep, b200ctr_dropout_t drop, void* stream);
 int b200ctr_add_rmsnorm_fwd(const float* a, const float* b, const float* w, float eps, int64_t M, int D,
                             float* s_out, float* y_out, float* r_out, void* stream);
-/* dx = rmsnorm'(dy) (+ dx_add) ; dw[D] += sum_m dy*s*r (atomic; caller zeroes dw) */
+/* dx = rmsnorm'(dy) (+ dx_add) ; dw: (b200ctr_rmsnorm_bwd_rows(M), D) PARTIAL sums of dy*s*r, one row per CTA, every entry
+ * written (no atomics); the caller sums the rows in order (b200ctr_colsum).                                            */
+int64_t b200ctr_rmsnorm_bwd_rows(int64_t M);
 int b200ctr_rmsnorm_bwd(const float* dy, const float* s, const float* w, const float* r, int64_t M, int D,
                         const float* dx_add, float* dx, float* dw, void* stream);
 /* relmean[t] = mean_h rel[t,h] ; drel[t,h] = drelmean[t]/H */
@@ -284,6 +296,8 @@ int b200ctr_inproj_bwd(const void* dqkv, int dqkv_bf16, const float* x, const fl
 int b200ctr_pool_fwd(const float* x, const float* vals, const float* aux_w, const float* aux_b, int gating_relu,
                      int64_t B, int K, int D, float* u, int64_t ld_u, float* aux, float* w_out,
                      b200ctr_dropout_t drop, void* stream);
+/* daux_w / daux_b of pool_bwd are per-sample PARTIAL rows, (B, D) and (B), every entry written (no atomics); the aux-head
+ * gradients are their column sums in sample order (b200ctr_colsum).                                                      */
 int b200ctr_pool_bwd(const float* x, const float* vals, const float* w, const float* aux_w, const float* u, int64_t ld_u,
                      const float* du, int64_t ld_du, const float* daux, int gating_relu, int64_t B, int K, int D,
                      float* dx, float* dvals, float* daux_w, float* daux_b, b200ctr_dropout_t drop, void* stream);
@@ -346,7 +360,9 @@ int b200ctr_bce_wll(const float* logits, const float* aux, const float* y, float
                     float* prob, void* stream);
 
 /* ---- clip + AdamW + EMA  (train.py:193-199, utils/ema.py:91-131) -----------------------------------------
- * sqnorm: acc[0] += sum x^2 (double accumulation in-kernel, atomic across CTAs; caller zeroes acc).
+ * sqnorm: acc += sum x^2.  `acc` is an opaque 8-byte accumulator the caller zeroes (all-zero bits): every CTA adds its double
+ *   partial as a 2^-32 fixed-point 64-bit INTEGER, so the total does not depend on the order the CTAs retire (bit-identical
+ *   runs); only clip_coef reads it back.  Across ranks it is summed as int64.
  * clip_coef: coef[0] = min(1, max_norm / (sqrt(acc[0]) + 1e-6)) ; max_norm <= 0 => 1.
  * adamw_ema: torch.optim.AdamW step order (decay, lerp m, v, bias-corrected update) with g scaled by coef[0],
  *            then ema = decay*ema + (1-decay)*p when ema != NULL.                                             */
@@ -405,6 +421,20 @@ int b200ctr_rowopt_update(const int32_t* tok, int64_t n_slots, int pad_id, const
 int b200ctr_rowopt_flush(int32_t* state, float* p, float* m, float* v, float* ema, int64_t n_rows, int D,
                          int64_t target_step, const void* hist4, const float* C, const float* S, const float* logD,
                          float beta1, float beta2, float eps, void* stream);
+
+/* ---- deterministic scatter-add of the sequence-table gradients (csrc/scatter.cu) ----
+ * Replaces the dense `embedding_dense_backward` + top-k `scatter` of autograd (src/models/dare.py:122-123,135-137 under
+ * train.py:192) without atomics: the (token, slot) pairs are radix-sorted by token and every distinct row is reduced once,
+ * in slot order, so two runs are bit-identical.  tok: n_src * n_slots ids.  DIRECT form (n_src = 1): slot s adds
+ * dvals[s] * q[s / K] to g_att[tok_s] and rows_rep[s] to g_rep[tok_s].  STAGED form (row-sharded tables): the rows are read
+ * from the owner's staging buffers, stage[(src * stage_cap + slot)], written by b200ctr_retrieve_bwd_staged(stage_all = 1) on
+ * every rank.  Only tokens with (t & (n_shards-1)) == rank are reduced, into local row t >> log2(n_shards).  The target rows
+ * must be zero on entry: each touched row is written, not accumulated.                                                  */
+int64_t b200ctr_scatter_rows_workspace_bytes(int64_t n_total_slots, int64_t vocab);
+int b200ctr_scatter_rows(const int32_t* tok, int n_src, int64_t n_slots, int pad_id, int64_t vocab, int K,
+                         const float* q, const float* dvals, const float* rows_rep, const float* stage_att,
+                         const float* stage_rep, int64_t stage_cap, int n_shards, int rank, float* g_att,
+                         float* g_rep, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- fold-ensemble  (infer.py:122-158, utils/metrics.py:68-71): p = sigmoid(mean_m logit(clamp(p_m))) ---- */
 int b200ctr_logit_mean(const float* probs, int n_models, int64_t B, float eps, float* out, void* stream);

@@ -51,7 +51,10 @@ def main():
             i = ix[k]
             if i is None or r[i] == "":
                 return None
-            return float(r[i].replace(",", "")) * SCALE.get(units[i], 1.0)
+            try:
+                return float(r[i].replace(",", "")) * SCALE.get(units[i], 1.0)
+            except ValueError:                                   # "no data" for metrics a pass did not collect
+                return None
         fam.setdefault(f, []).append({k: val(k) for k in COLS})
     res = {}
     for f, ls in fam.items():
@@ -59,7 +62,7 @@ def main():
             v = [x[k] for x in ls if x[k] is not None]
             return sum(v) / len(v) if v else None
         rd, wr = mean("rd") or 0.0, mean("wr") or 0.0
-        res[f] = {"launches_captured": len(ls), "ncu_ms": round(mean("ms"), 4), "dram_read_MB": round(rd / 1e6, 1), "dram_write_MB": round(wr / 1e6, 1),
+        res[f] = {"launches_captured": len(ls), "ncu_ms": round(mean("ms") or 0.0, 4), "dram_read_MB": round(rd / 1e6, 1), "dram_write_MB": round(wr / 1e6, 1),
                   "traffic_bytes_per_launch": int(rd + wr), "sm_throughput_pct": mean("sm"), "issue_active_pct": mean("issue"),
                   "warps_active_pct": mean("warps"), "tensor_pipe_pct": mean("tensor"), "l1_lsu_wavefronts_pct": mean("lsu"),
                   "dram_throughput_pct": mean("dram"), "registers": mean("regs")}

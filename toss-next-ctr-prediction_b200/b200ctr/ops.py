@@ -262,10 +262,11 @@ def numbin_fwd(x, P, Q, out, ld_b, mean_out, ld_mean):
 def numbin_bwd(x, dout, ld_b, dmean, ld_dmean, D):
     lib = _lib.load()
     B, F = x.shape
-    dP = torch.empty((F, D), device=x.device, dtype=torch.float32)
-    dQ = torch.empty((F, D), device=x.device, dtype=torch.float32)
-    _run("numbin_bwd", lib.b200ctr_numbin_bwd, _p(x), _p(dout), ld_b, _p(dmean), ld_dmean, _p(dP), _p(dQ), B, F, D, _stream())
-    _count(3)
+    rows = int(lib.b200ctr_numbin_bwd_rows(B))
+    part = torch.empty((2, rows, F * D), device=x.device, dtype=torch.float32)       # per-chunk partial sums, no atomics
+    _run("numbin_bwd", lib.b200ctr_numbin_bwd, _p(x), _p(dout), ld_b, _p(dmean), ld_dmean, _p(part[0]), _p(part[1]), B, F, D, _stream())
+    _count()
+    dP, dQ = colsum(part[0]).view(F, D), colsum(part[1]).view(F, D)                  # summed in chunk order
     return dP, dQ
 
 
@@ -330,10 +331,14 @@ def cat_bwd(x_cat, ct: CatTables, dout, ld_b, dmean, ld_dmean, q_idx, dq, dtable
     lib = _lib.load()
     B, Fc = x_cat.shape
     dt_ptrs, dp_ptrs = _ptr_table(dtables), _ptr_table(dprojs)
+    sum_dims = int(sum(t.shape[1] for t in dtables))
+    max_card = int(max(t.shape[0] for t in dtables))
+    ws_bytes = int(lib.b200ctr_cat_bwd_workspace_bytes(B, sum_dims))
+    ws = torch.empty((ws_bytes,), device=x_cat.device, dtype=torch.uint8)
     _run("cat_bwd", lib.b200ctr_cat_bwd, _p(x_cat), _idx64(x_cat), _p(ct.t_ptrs), _p(ct.p_ptrs), _p(ct.dims), _p(ct.cards),
                               _p(dout), ld_b, _p(dmean), ld_dmean, q_idx, _p(dq), _p(dt_ptrs), _p(dp_ptrs),
-                              B, Fc, D, dropout, _stream())
-    _count()
+                              B, Fc, D, sum_dims, max_card, dropout, _p(ws), ws_bytes, _stream())
+    _count(3)
 
 
 def axpby(x, y, a, b, out=None):
@@ -443,11 +448,36 @@ def retrieve_fwd(seq, q, emb_att, emb_rep, rec, K, pad_id):
     return sel, vals, idx, tok
 
 
+# table-gradient scatter: "sorted" = radix sort by token + segmented reduction in slot order (deterministic, csrc/scatter.cu);
+# "atomic" = the first version's fp32 vector atomics (kept for A/B timing)
+SCATTER = _os.environ.get("B200CTR_SCATTER", "sorted")
+
+
+def scatter_rows(tok, n_src, n_slots, pad_id, vocab, K, q, dvals, rows_rep, stage_att, stage_rep, stage_cap, n_shards, rank, g_att, g_rep):
+    lib = _lib.load()
+    n = int(n_src) * int(n_slots)
+    ws_bytes = int(lib.b200ctr_scatter_rows_workspace_bytes(n, int(vocab)))
+    ws = torch.empty((ws_bytes,), device=tok.device, dtype=torch.uint8)
+    _run("scatter_rows", lib.b200ctr_scatter_rows, _p(tok), int(n_src), int(n_slots), pad_id, int(vocab), int(K), _p(q), _p(dvals),
+         _p(rows_rep), _p(stage_att), _p(stage_rep), int(stage_cap), int(n_shards), int(rank), _p(g_att), _p(g_rep), _p(ws), ws_bytes,
+         _stream())
+    _count(4)
+
+
 def retrieve_bwd(tok, q, emb_att, dsel_rep, dvals, pad_id, datt_dense=None, drep_dense=None):
     lib = _lib.load()
     B, K = tok.shape
     D = q.shape[1]
     dq = torch.empty_like(q)
+    if SCATTER == "sorted" and not isinstance(emb_att, ShardedTable):
+        # dq only; then every distinct gradient row is reduced once, in slot order
+        _run("retrieve_bwd", lib.b200ctr_retrieve_bwd, _p(tok), _p(q), _p(emb_att), _p(dsel_rep), _p(dvals), B, K, D, pad_id, _p(dq),
+             None, None, _stream())
+        _count()
+        if datt_dense is not None or drep_dense is not None:
+            scatter_rows(tok, 1, B * K, pad_id, emb_att.shape[0], K, q, dvals, dsel_rep.contiguous() if dsel_rep is not None else None,
+                         None, None, 0, 1, 0, datt_dense, drep_dense)
+        return dq
     if isinstance(emb_att, ShardedTable):
         sa = getattr(datt_dense, "stage_ptrs", None) if datt_dense is not None else None
         sr = getattr(drep_dense, "stage_ptrs", None) if drep_dense is not None else None
@@ -455,7 +485,8 @@ def retrieve_bwd(tok, q, emb_att, dsel_rep, dvals, pad_id, datt_dense=None, drep
         _run("retrieve_bwd", lib.b200ctr_retrieve_bwd_staged, _p(tok), _p(q), emb_att.ptrs, emb_att.n, _p(dsel_rep), _p(dvals), B, K,
              D, pad_id, _p(dq), datt_dense.ptrs if datt_dense is not None else None,
              drep_dense.ptrs if drep_dense is not None else None, sa, sr,
-             getattr(ref, "stage_rank", 0) if ref is not None else 0, getattr(ref, "stage_cap", 0) if ref is not None else 0, _stream())
+             getattr(ref, "stage_rank", 0) if ref is not None else 0, getattr(ref, "stage_cap", 0) if ref is not None else 0,
+             1 if (SCATTER == "sorted" and (sa is not None or sr is not None)) else 0, _stream())
     else:
         _run("retrieve_bwd", lib.b200ctr_retrieve_bwd, _p(tok), _p(q), _p(emb_att), _p(dsel_rep), _p(dvals), B, K, D, pad_id, _p(dq),
              _p(datt_dense), _p(drep_dense), _stream())
@@ -512,6 +543,9 @@ def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=N
     use_tc = _attn_tc(tc, K, H, D)
     out_bf16 = bool(out_bf16 and use_tc)
     dqkv = torch.empty(qkv.shape, device=qkv.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    drel_out = drelmean
+    if drelmean is not None:      # the kernels write one partial row per sample (no float atomics); summed in sample order below
+        drelmean = torch.zeros((B, 2 * max_len + 1), device=qkv.device, dtype=torch.float32)
     if use_tc:
         _run("attn_tc_bwd", lib.b200ctr_attn_tc_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
              int(out_bf16), _p(drelmean), _p(keep), dropout, _stream())
@@ -519,6 +553,8 @@ def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=N
         _run("attn_bwd", lib.b200ctr_attn_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
              _p(drelmean), dropout, _stream())
     _count()
+    if drel_out is not None:
+        colsum(drelmean, out=drel_out)
     return dqkv
 
 
@@ -625,12 +661,14 @@ def ffn_bwd(dy, s2, r2, n2w, x1, w1, b1, w2, dw1, db1, dw2, db2, dn2, dropout: D
 
 
 def rmsnorm_bwd(dy, s, w, r, dw, dx_add=None):
-    """dw: zeroed (D,) tensor, accumulated into."""
+    """dw: (D,) tensor, overwritten with sum_m dy*s*r."""
     lib = _lib.load()
     M, D = dy.shape
     dx = torch.empty_like(dy)
-    _run("rmsnorm_bwd", lib.b200ctr_rmsnorm_bwd, _p(dy), _p(s), _p(w), _p(r), M, D, _p(dx_add), _p(dx), _p(dw), _stream())
+    part = torch.empty((int(lib.b200ctr_rmsnorm_bwd_rows(M)), D), device=dy.device, dtype=torch.float32)   # one row per CTA
+    _run("rmsnorm_bwd", lib.b200ctr_rmsnorm_bwd, _p(dy), _p(s), _p(w), _p(r), M, D, _p(dx_add), _p(dx), _p(part), _stream())
     _count()
+    colsum(part, out=dw)                                                                  # summed in CTA order: no float atomics
     return dx
 
 
@@ -668,9 +706,16 @@ def pool_bwd(x, vals, w, aux_w, u, ld_u, du, ld_du, daux, gating_relu, daux_w, d
     B, K, D = x.shape
     dx = torch.empty_like(x)
     dvals = torch.empty_like(vals)
+    want = daux is not None and daux_w is not None
+    pw = torch.empty((B, D), device=x.device, dtype=torch.float32) if want else None      # per-sample partial rows, no atomics
+    pb = torch.empty((B, 1), device=x.device, dtype=torch.float32) if (want and daux_b is not None) else None
     _run("pool_bwd", lib.b200ctr_pool_bwd, _p(x), _p(vals), _p(w), _p(aux_w), _p(u), ld_u, _p(du), ld_du, _p(daux), int(gating_relu),
-                               B, K, D, _p(dx), _p(dvals), _p(daux_w), _p(daux_b), dropout, _stream())
+                               B, K, D, _p(dx), _p(dvals), _p(pw), _p(pb), dropout, _stream())
     _count()
+    if want:                                                                              # summed in sample order
+        colsum(pw, out=daux_w.view(-1))
+        if pb is not None:
+            colsum(pb, out=daux_b.view(-1))
     return dx, dvals
 
 

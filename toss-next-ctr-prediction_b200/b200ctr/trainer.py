@@ -449,9 +449,15 @@ class FusedTrainer:
                 n_slots = tok.numel()
                 gtok = torch.empty((self.world * n_slots,), device=self.dev, dtype=torch.int32)
                 self._allgather(gtok, tok.reshape(-1), "C1_selected_tokens_allgather")
-                ops.stage_apply(gtok, self.world, n_slots, self.stage_cap, spec.pad_id, self.world, self.rank,
-                                self.tables[BIG_TABLES[0]]["stage"], self.tables[BIG_TABLES[1]]["stage"],
-                                self.tables[BIG_TABLES[0]]["g"], self.tables[BIG_TABLES[1]]["g"])
+                if ops.SCATTER == "sorted":
+                    # every rank staged ALL its slots' rows at their owners: reduce each owned row once, in (rank, slot) order
+                    ops.scatter_rows(gtok, self.world, n_slots, spec.pad_id, self.vocab_global, tok.shape[1], None, None, None,
+                                     self.tables[BIG_TABLES[0]]["stage"], self.tables[BIG_TABLES[1]]["stage"], self.stage_cap,
+                                     self.world, self.rank, self.tables[BIG_TABLES[0]]["g"], self.tables[BIG_TABLES[1]]["g"])
+                else:
+                    ops.stage_apply(gtok, self.world, n_slots, self.stage_cap, spec.pad_id, self.world, self.rank,
+                                    self.tables[BIG_TABLES[0]]["stage"], self.tables[BIG_TABLES[1]]["stage"],
+                                    self.tables[BIG_TABLES[0]]["g"], self.tables[BIG_TABLES[1]]["g"])
                 self.bm_mine.zero_()
                 ops.bitmap_mark(gtok, spec.pad_id, self.vocab_global, self.bm_mine)
                 maps, n_maps = self.bm_mine, 1
@@ -460,7 +466,7 @@ class FusedTrainer:
             for n in BIG_TABLES:
                 ops.rows_sqnorm_bm(maps, n_maps, self.bm_words, self.n_shards, self.shard_rank, self.tables[n]["g"], self.acc)
             if self.shard:
-                self._allreduce(self.acc, "C5_sqnorm")           # C5: each owner contributes the squared norm of its rows
+                self._allreduce(self.acc.view(torch.int64), "C5_sqnorm")   # the accumulator is a fixed-point integer (order-independent)           # C5: each owner contributes the squared norm of its rows
         else:
             ops.rows_claim(tok, spec.pad_id, self.owner)
             for n in BIG_TABLES:

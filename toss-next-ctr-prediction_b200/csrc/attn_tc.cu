@@ -468,7 +468,9 @@ attn_tc_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
       const int d = tt - (K - 1);
       float acc = 0.f;
       for (int w = 0; w < 8 * KS; ++w) acc += dbias[w * DBS + d + KPA];
-      atomicAdd(drelmean + min(max(d, -max_len), max_len) + max_len, acc);
+      // per-sample partial row (zero-initialised by the caller; |d| <= K - 1 < max_len: one writer per slot), summed in sample
+      // order afterwards (b200ctr_colsum): no float atomics
+      drelmean[b * (int64_t)(2 * max_len + 1) + min(max(d, -max_len), max_len) + max_len] = acc;
     }
   }
 }

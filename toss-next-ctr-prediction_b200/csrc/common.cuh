@@ -169,6 +169,20 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return red[0];
 }
 
+// ---- order-independent accumulation ------------------------------------------------------------------------------
+// The squared-gradient-norm accumulator is an 8-byte slot that many blocks add to.  Floating-point atomics would make the sum
+// depend on the order in which the blocks retire; instead every block rounds its partial to a 2^-32 grid and adds it as a
+// 64-bit INTEGER (associative), so the global norm -- and with it the clip coefficient and every parameter after the step --
+// is bit-identical from run to run.  Range 2^31 (a squared norm of 2e9), resolution 2.3e-10.  The slot is read back with
+// norm_acc_value(); across ranks it is all-reduced as int64.
+constexpr double NORM_ACC_SCALE = 4294967296.0;
+__device__ __forceinline__ void norm_acc_add(double* acc, double partial) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)__double2ll_rn(partial * NORM_ACC_SCALE));
+}
+__device__ __forceinline__ double norm_acc_value(const double* acc) {
+  return (double)(*reinterpret_cast<const long long*>(acc)) * (1.0 / NORM_ACC_SCALE);
+}
+
 // 128-bit streaming loads (read-only path, no L1 allocation) for gather rows
 __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
   float4 r;

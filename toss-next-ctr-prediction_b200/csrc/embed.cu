@@ -95,10 +95,10 @@ numbin_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, i
       accum(g0, x0); accum(g1, x1); accum(g2, x2); accum(g3, x3);
     }
     for (; b < b1; ++b) accum(grad(b), x[b * F + f]);
-    float* p = dP + f * D + l * 4;
-    float* q = dQ + f * D + l * 4;
-    atomicAdd(p + 0, ap.x); atomicAdd(p + 1, ap.y); atomicAdd(p + 2, ap.z); atomicAdd(p + 3, ap.w);
-    atomicAdd(q + 0, aq.x); atomicAdd(q + 1, aq.y); atomicAdd(q + 2, aq.z); atomicAdd(q + 3, aq.w);
+    // one partial row per sample chunk (= blockIdx.x), summed in chunk order afterwards (b200ctr_colsum): no float atomics
+    const int64_t prow = (int64_t)blockIdx.x * F * D;
+    *reinterpret_cast<float4*>(dP + prow + f * D + l * 4) = ap;
+    *reinterpret_cast<float4*>(dQ + prow + f * D + l * 4) = aq;
   }
 }
 
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256)
 cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ tables, const float* const* __restrict__ projs,
                const int32_t* __restrict__ dims, const int32_t* __restrict__ cards, const float* __restrict__ dout, int64_t ld_b,
                const float* __restrict__ dmean, int64_t ld_dmean, int q_idx, const float* __restrict__ dq,
-               float* const* __restrict__ dtables, float* const* __restrict__ dprojs, int64_t B, int Fc,
+               float* __restrict__ rowg, float* __restrict__ dwpart, int sumdc, int64_t B, int Fc,
                b200ctr_dropout_t drop) {
   __shared__ float Ws[CAT_D][CAT_MAXDC + 1];           // natural layout W[n][j]
   __shared__ float gs[CATB_TS][CAT_D + 1];
@@ -217,8 +217,8 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   const int card = cards[c];
   const float* W = projs[c];
   const float* T = tables[c];
-  float* dT = dtables[c];
-  float* dW = dprojs[c];
+  int off_c = 0;                                          // column offset inside a sample's row of table-row gradients
+  for (int cc = 0; cc < c; ++cc) off_c += dims[cc];
   const int tid = threadIdx.x;
   for (int i = tid; i < CAT_D * dc; i += blockDim.x) Ws[i / dc][i % dc] = W[i];
   // this thread's dW elements: e = tid + k*256 < 64*dc  (<= 16 of them)
@@ -273,14 +273,72 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
       float a = 0.f;
 #pragma unroll 8
       for (int n = 0; n < CAT_D; ++n) a = fmaf(Ws[n][j], gs[s][n], a);
-      atomicAdd(dT + ids[s] * dc + j, a);
-    }
+      rowg[(b0 + s) * (int64_t)sumdc + off_c + j] = a;      // this sample's contribution to dE_c[id]; summed per table row in
+    }                                                       // sample order by cat_dtable_kernel (no float atomics)
   }
+  // this CTA's partial dW_c; the partials are added in CTA order by cat_dw_reduce_kernel
+  float* dwp = dwpart + (int64_t)blockIdx.x * CAT_D * sumdc + (int64_t)CAT_D * off_c;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     int e = tid + k * 256;
-    if (e < CAT_D * dc) atomicAdd(dW + e, acc[k]);
+    if (e < CAT_D * dc) dwp[e] = acc[k];
   }
+}
+
+// dE_c[row, :] += sum over the samples b with x_cat[b, c] == row, in ascending b, of rowg[b, off_c : off_c + d_c].
+// Thread per table row; the column's B ids are walked through shared memory (a broadcast read per comparison).
+constexpr int CATT_TILE = 2048;
+template <typename IT>
+__global__ void __launch_bounds__(256)
+cat_dtable_kernel(const IT* __restrict__ x_cat, const int32_t* __restrict__ dims, const int32_t* __restrict__ cards,
+                  const float* __restrict__ rowg, int sumdc, float* const* __restrict__ dtables, int64_t B, int Fc) {
+  __shared__ int32_t ids[CATT_TILE];
+  const int c = blockIdx.y, dc = dims[c], card = cards[c];
+  if ((int64_t)blockIdx.x * blockDim.x >= card) return;
+  int off_c = 0;
+  for (int cc = 0; cc < c; ++cc) off_c += dims[cc];
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc[CAT_MAXDC];
+#pragma unroll
+  for (int j = 0; j < CAT_MAXDC; ++j) acc[j] = 0.f;
+  bool any = false;
+  for (int64_t b0 = 0; b0 < B; b0 += CATT_TILE) {
+    const int nb = (int)min((int64_t)CATT_TILE, B - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+      int64_t id = (int64_t)x_cat[(b0 + i) * Fc + c];
+      ids[i] = (int32_t)(id < 0 ? 0 : (id >= card ? card - 1 : id));
+    }
+    __syncthreads();
+    for (int i = 0; i < nb; ++i) {
+      if (ids[i] == row) {
+        any = true;
+        const float* src = rowg + (b0 + i) * (int64_t)sumdc + off_c;
+#pragma unroll
+        for (int j = 0; j < CAT_MAXDC; ++j)
+          if (j < dc) acc[j] += src[j];
+      }
+    }
+  }
+  if (any && row < card) {
+    float* dT = dtables[c] + (int64_t)row * dc;
+#pragma unroll
+    for (int j = 0; j < CAT_MAXDC; ++j)
+      if (j < dc) dT[j] += acc[j];                          // single writer per row: plain read-modify-write
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cat_dw_reduce_kernel(const float* __restrict__ dwpart, int nparts, const int32_t* __restrict__ dims, int sumdc,
+                     float* const* __restrict__ dprojs) {
+  const int c = blockIdx.y, dc = dims[c];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= CAT_D * dc) return;
+  int off_c = 0;
+  for (int cc = 0; cc < c; ++cc) off_c += dims[cc];
+  float a = 0.f;
+  for (int p = 0; p < nparts; ++p) a += dwpart[(int64_t)p * CAT_D * sumdc + (int64_t)CAT_D * off_c + e];
+  dprojs[c][e] += a;
 }
 
 __global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float a, float b,
@@ -354,16 +412,16 @@ extern "C" int b200ctr_numbin_fwd(const float* x, const float* P, const float* Q
   return B200CTR_OK;
 }
 
+constexpr int64_t NUMBIN_CHUNK = 64;
+extern "C" int64_t b200ctr_numbin_bwd_rows(int64_t B) { return std::max<int64_t>(1, ceil_div(B, NUMBIN_CHUNK)); }
+
 extern "C" int b200ctr_numbin_bwd(const float* x, const float* dout, int64_t ld_b, const float* dmean, int64_t ld_dmean,
                                   float* dP, float* dQ, int64_t B, int F, int D, void* stream) {
   B200_REQUIRE(x && dP && dQ && (dout || dmean), B200CTR_E_INVALID_ARG, "numbin_bwd: null pointer");
   B200_REQUIRE(D % 4 == 0, B200CTR_E_UNSUPPORTED_SHAPE, "numbin_bwd: D=%d unsupported", D);
   cudaStream_t st = as_stream(stream);
-  cudaError_t e = cudaMemsetAsync(dP, 0, sizeof(float) * F * D, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(dQ, 0, sizeof(float) * F * D, st);
-  if (e != cudaSuccess) return cuda_fail(e, "numbin_bwd memset");
   if (B == 0 || F == 0) return B200CTR_OK;
-  int64_t chunk = 64;
+  int64_t chunk = NUMBIN_CHUNK;
   dim3 grid((unsigned)ceil_div(B, chunk), (unsigned)std::min<int64_t>(ceil_div((int64_t)F * (D / 4), (int64_t)256), 8));
   numbin_bwd_kernel<<<grid, 256, 0, st>>>(x, dout, ld_b, dmean, ld_dmean, dP, dQ, B, F, D, chunk);
   B200_LAUNCH_CHECK("numbin_bwd_kernel");
@@ -398,22 +456,39 @@ extern "C" int b200ctr_cat_fwd(const void* x_cat, int idx_is_64, const float* co
   return B200CTR_OK;
 }
 
+extern "C" int64_t b200ctr_cat_bwd_workspace_bytes(int64_t B, int sum_dims) {
+  // per-sample table-row gradients (B x sum d_c) + 64 per-CTA partials of all dW_c (64 x 64 x sum d_c)
+  return (int64_t)sizeof(float) * (std::max<int64_t>(B, 1) * sum_dims + (int64_t)64 * CAT_D * sum_dims);
+}
+
 extern "C" int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
                                const int32_t* dims, const int32_t* cards, const float* dout, int64_t ld_b,
                                const float* dmean, int64_t ld_dmean, int q_idx, const float* dq, float* const* dtables,
-                               float* const* dprojs, int64_t B, int Fc, int D, b200ctr_dropout_t drop, void* stream) {
-  B200_REQUIRE(x_cat && tables && projs && dims && cards && dtables && dprojs, B200CTR_E_INVALID_ARG, "cat_bwd: null pointer");
+                               float* const* dprojs, int64_t B, int Fc, int D, int sum_dims, int max_card,
+                               b200ctr_dropout_t drop, void* workspace, int64_t workspace_bytes, void* stream) {
+  B200_REQUIRE(x_cat && tables && projs && dims && cards && dtables && dprojs && workspace, B200CTR_E_INVALID_ARG, "cat_bwd: null pointer");
   B200_REQUIRE(D == CAT_D, B200CTR_E_UNSUPPORTED_SHAPE, "cat_bwd: emb_dim=%d unsupported (kernel is specialised for 64)", D);
+  B200_REQUIRE(sum_dims > 0 && max_card > 0 && workspace_bytes >= b200ctr_cat_bwd_workspace_bytes(B, sum_dims), B200CTR_E_INVALID_ARG,
+               "cat_bwd: workspace too small (sum_dims=%d)", sum_dims);
   if (B == 0 || Fc == 0) return B200CTR_OK;
   dim3 grid((unsigned)std::min<int64_t>(ceil_div(B, (int64_t)CATB_TS), 64), (unsigned)Fc);     // wide columns (d_c up to 64) set the tail: many short CTAs
   cudaStream_t st = as_stream(stream);
+  float* rowg = (float*)workspace;
+  float* dwpart = rowg + std::max<int64_t>(B, 1) * sum_dims;
   if (idx_is_64)
     cat_bwd_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)x_cat, tables, projs, dims, cards, dout, ld_b, dmean,
-                                                   ld_dmean, q_idx, dq, dtables, dprojs, B, Fc, drop);
+                                                   ld_dmean, q_idx, dq, rowg, dwpart, sum_dims, B, Fc, drop);
   else
     cat_bwd_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)x_cat, tables, projs, dims, cards, dout, ld_b, dmean,
-                                                   ld_dmean, q_idx, dq, dtables, dprojs, B, Fc, drop);
+                                                   ld_dmean, q_idx, dq, rowg, dwpart, sum_dims, B, Fc, drop);
   B200_LAUNCH_CHECK("cat_bwd_kernel");
+  dim3 tgrid((unsigned)ceil_div((int64_t)max_card, (int64_t)256), (unsigned)Fc);
+  if (idx_is_64) cat_dtable_kernel<int64_t><<<tgrid, 256, 0, st>>>((const int64_t*)x_cat, dims, cards, rowg, sum_dims, dtables, B, Fc);
+  else cat_dtable_kernel<int32_t><<<tgrid, 256, 0, st>>>((const int32_t*)x_cat, dims, cards, rowg, sum_dims, dtables, B, Fc);
+  B200_LAUNCH_CHECK("cat_dtable_kernel");
+  dim3 wgrid((unsigned)ceil_div((int64_t)CAT_D * CAT_MAXDC, (int64_t)256), (unsigned)Fc);
+  cat_dw_reduce_kernel<<<wgrid, 256, 0, st>>>(dwpart, (int)grid.x, dims, sum_dims, dprojs);
+  B200_LAUNCH_CHECK("cat_dw_reduce_kernel");
   return B200CTR_OK;
 }
 

@@ -242,7 +242,9 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean
     for (int t = threadIdx.x; t < 2 * K - 1; t += AT_THREADS) {
       int d = t - (K - 1);
       int di = min(max(d, -max_len), max_len) + max_len;
-      atomicAdd(drelmean + di, dbias[t]);
+      // per-sample partial row (zero-initialised by the caller, |d| <= K-1 <= max_len-1 so no two t share a slot); the rows
+      // are summed in sample order afterwards (b200ctr_colsum)
+      drelmean[b * (int64_t)(2 * max_len + 1) + di] = dbias[t];
     }
   }
 }
@@ -294,8 +296,8 @@ rmsnorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, co
   if (wid == 0) {
     float2 t = red[0][lane];
     for (int k = 1; k < 8; ++k) { t.x += red[k][lane].x; t.y += red[k][lane].y; }
-    atomicAdd(dw + 2 * lane, t.x);
-    atomicAdd(dw + 2 * lane + 1, t.y);
+    // one partial row per CTA, summed afterwards in row order (b200ctr_colsum): no float atomics, bit-identical runs
+    reinterpret_cast<float2*>(dw + (int64_t)blockIdx.x * AT_D)[lane] = t;
   }
 }
 
@@ -368,12 +370,16 @@ extern "C" int b200ctr_add_rmsnorm_fwd(const float* a, const float* b, const flo
   return B200CTR_OK;
 }
 
+extern "C" int64_t b200ctr_rmsnorm_bwd_rows(int64_t M) {
+  return std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, (int64_t)8), (int64_t)num_sms() * 8));
+}
+
 extern "C" int b200ctr_rmsnorm_bwd(const float* dy, const float* s, const float* w, const float* r, int64_t M, int D,
                                    const float* dx_add, float* dx, float* dw, void* stream) {
   B200_REQUIRE(dy && s && w && r && dx && dw, B200CTR_E_INVALID_ARG, "rmsnorm_bwd: null pointer");
   B200_REQUIRE(D == AT_D, B200CTR_E_UNSUPPORTED_SHAPE, "rmsnorm_bwd: D=%d unsupported (64 only)", D);
   if (M == 0) return B200CTR_OK;
-  int grid = (int)std::min<int64_t>(ceil_div(M, 8), (int64_t)num_sms() * 8);
+  int grid = (int)b200ctr_rmsnorm_bwd_rows(M);
   rmsnorm_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(dy, s, w, r, M, dx_add, dx, dw);
   B200_LAUNCH_CHECK("rmsnorm_bwd_kernel");
   return B200CTR_OK;

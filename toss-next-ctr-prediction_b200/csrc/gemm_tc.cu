@@ -574,9 +574,13 @@ static int launch_tc_ws(int tA, int tB, int64_t M, int64_t N, int64_t K, const T
   static_assert(!X3 || BN <= 128, "split precision: tiles up to 128 columns (SPLIT bf16 tiles per operand per stage)");
   // ring depth: what fits next to the epilogue scratch in 227 KB
   constexpr int STAGES = SPLIT == 3 ? 2 : (SPLIT == 2 ? (BN <= 64 ? 4 : 3) : (BN <= 128 ? 5 : (BN <= 192 ? 4 : 3)));
-  // deep-K: loads dominate -> 8 producer warps; else 8 epilogue warps (split precision: always 8 producers, 4 epilogue warps)
-  const bool deep_k = X3 || k_chunk > 512;
-  size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) * SPLIT + (size_t)(X3 ? 4 : 8) * 32 * 36 * 4;
+  // deep-K: loads dominate -> 8 producer warps; else 8 epilogue warps (output-heavy shapes: the epilogue is the long pole)
+  const bool deep_k = k_chunk > 512;
+  size_t smem = (size_t)STAGES * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) * SPLIT + (size_t)(deep_k ? 4 : 8) * 32 * 36 * 4;
+  if (smem > 232448) {
+    set_error("gemm_tc_ws: tile %d x %d parts needs %zu bytes of shared memory", BN, SPLIT, smem);
+    return B200CTR_E_UNSUPPORTED_SHAPE;
+  }
   const int vec = epi_vec_ok(e, C, ldc, N) ? 1 : 0;
   const int grid = (int)std::min<int64_t>(total, (int64_t)num_sms());
 #define WS_LAUNCH1(TA_, TB_, PW_, EW_)                                                                            \
@@ -588,8 +592,7 @@ static int launch_tc_ws(int tA, int tB, int64_t M, int64_t N, int64_t K, const T
   } while (0)
 #define WS_LAUNCH(TA_, TB_)                                                                                       \
   do {                                                                                                            \
-    if constexpr (X3) { WS_LAUNCH1(TA_, TB_, 8, 4); }                                                             \
-    else { if (deep_k) WS_LAUNCH1(TA_, TB_, 8, 4); else WS_LAUNCH1(TA_, TB_, 4, 8); }                             \
+    if (deep_k) WS_LAUNCH1(TA_, TB_, 8, 4); else WS_LAUNCH1(TA_, TB_, 4, 8);                                      \
   } while (0)
   if (!tA && !tB) WS_LAUNCH(false, false);
   else if (!tA && tB) WS_LAUNCH(false, true);
@@ -687,6 +690,13 @@ static int gemm_split(int transA, int transB, int64_t M, int64_t N, int64_t K, c
                       int64_t ldb, float* C, int64_t ldc, const EpiDev& e, int split_k, float* ws, cudaStream_t st) {
   const int64_t k_per_split = ceil_div(K, (int64_t)split_k);
 #define SP_ARGS transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st
+  // A/B switch (measured on B200, profiles/): the persistent warp-specialised pipeline also for the shallow-K shapes --
+  // 4 producer + 8 epilogue warps, double-buffered TMEM accumulators, tiles of at most 96 columns (shared-memory budget)
+  static const bool ws_all = getenv("B200CTR_SPLIT_WS") != nullptr;
+  if (ws_all && k_per_split <= 512 && M >= 4096) {
+    if (N <= 64) return launch_tc_ws<64, float, SPLIT>(SP_ARGS);
+    return launch_tc_ws<96, float, SPLIT>(SP_ARGS);
+  }
   if (k_per_split <= TC_BK) {
     // one k-tile: a single ring slot, so 2-3 CTAs stay resident per SM and one CTA's epilogue stores overlap the others' loads
     if (N <= 64) return launch_tc<64, SPLIT, 1>(SP_ARGS);

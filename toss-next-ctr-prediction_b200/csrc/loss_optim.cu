@@ -59,12 +59,12 @@ sqnorm_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ acc) 
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int k = 0; k < 8; ++k) t += red[k];
-    atomicAdd(acc, t);
+    norm_acc_add(acc, t);
   }
 }
 
 __global__ void clip_coef_kernel(const double* __restrict__ acc, float max_norm, float* __restrict__ coef, float* __restrict__ total) {
-  double tn = sqrt(acc[0]);
+  double tn = sqrt(norm_acc_value(acc));
   if (total) total[0] = (float)tn;
   float c = 1.f;
   if (max_norm > 0.f) { c = max_norm / ((float)tn + 1e-6f); c = fminf(c, 1.f); }
@@ -120,7 +120,7 @@ rows_sqnorm_kernel(const int32_t* __restrict__ tok, int64_t n, int pad_id, const
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int k = 0; k < 8; ++k) t += red[k];
-    atomicAdd(acc, t);
+    norm_acc_add(acc, t);
   }
 }
 __global__ void rows_zero_kernel(const int32_t* __restrict__ tok, int64_t n, int pad_id, const int32_t* __restrict__ owner,

@@ -66,9 +66,9 @@ pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ vals, con
   if (tid < PL_D) {
     float g = (du ? du[b * ld_du + tid] : 0.f) + da * aux_w[tid];
     du0[tid] = g * drop_scale(drop, (uint64_t)b * PL_D + tid);
-    if (daux_w && daux) atomicAdd(daux_w + tid, da * u[b * ld_u + tid]);
-  }
-  if (tid == 0 && daux_b && daux) atomicAdd(daux_b, da);
+    if (daux_w && daux) daux_w[b * PL_D + tid] = da * u[b * ld_u + tid];     // per-sample partial rows, summed in sample order
+  }                                                                          // afterwards (b200ctr_colsum): no float atomics
+  if (tid == 0 && daux_b && daux) daux_b[b] = da;
   __syncthreads();
   const float* xb = x + b * (int64_t)K * PL_D;
   float* dxb = dx + b * (int64_t)K * PL_D;

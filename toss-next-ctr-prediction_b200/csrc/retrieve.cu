@@ -359,17 +359,17 @@ retrieve_bwd_kernel(const int32_t* __restrict__ tok, const float* __restrict__ q
     float4 a = rt_load_row(emb_att, t, hl);
     acc.x = fmaf(dv, a.x, acc.x); acc.y = fmaf(dv, a.y, acc.y); acc.z = fmaf(dv, a.z, acc.z); acc.w = fmaf(dv, a.w, acc.w);
     const int owner = t & datt.mask;
-    const bool remote = staged && owner != my_rank;
+    const bool remote = staged && (staged == 2 || owner != my_rank);     // staged == 2: the owner's own slots are staged too
     const int64_t srow = ((int64_t)my_rank * stage_cap + (b * K + k)) * (RT_D / 4) + hl;
     if (has_datt) {
       float4 g = make_float4(dv * qv.x, dv * qv.y, dv * qv.z, dv * qv.w);
       if (remote) reinterpret_cast<float4*>(stage_att.p[owner])[srow] = g;
-      else atomicAdd(datt.row4(t) + hl, g);
+      else if (staged != 2) atomicAdd(datt.row4(t) + hl, g);
     }
     if (has_drep) {
       float4 g = *reinterpret_cast<const float4*>(dsel_rep + (b * K + k) * (int64_t)RT_D + hl * 4);
       if (remote) reinterpret_cast<float4*>(stage_rep.p[owner])[srow] = g;
-      else atomicAdd(drep.row4(t) + hl, g);
+      else if (staged != 2) atomicAdd(drep.row4(t) + hl, g);
     }
   }
   red[tid] = acc;
@@ -501,7 +501,7 @@ extern "C" int b200ctr_retrieve_bwd_staged(const int32_t* tok, const float* q, c
                                            const float* dsel_rep, const float* dvals, int64_t B, int K, int D, int pad_id,
                                            float* dq, float* const* datt_shards, float* const* drep_shards,
                                            float* const* stage_att, float* const* stage_rep, int my_rank, int64_t stage_cap,
-                                           void* stream) {
+                                           int stage_all, void* stream) {
   B200_REQUIRE(tok && q && att_shards && dvals && dq, B200CTR_E_INVALID_ARG, "retrieve_bwd: null pointer");
   B200_REQUIRE(!drep_shards || dsel_rep, B200CTR_E_INVALID_ARG, "retrieve_bwd: drep without dsel_rep");
   B200_REQUIRE(D == RT_D, B200CTR_E_UNSUPPORTED_SHAPE, "retrieve_bwd: emb_dim=%d unsupported", D);
@@ -511,7 +511,7 @@ extern "C" int b200ctr_retrieve_bwd_staged(const int32_t* tok, const float* q, c
   if (datt_shards) { rc = make_shards(datt, datt_shards, n_shards, "retrieve_bwd(datt)"); if (rc) return rc; }
   if (drep_shards) { rc = make_shards(drep, drep_shards, n_shards, "retrieve_bwd(drep)"); if (rc) return rc; }
   else { datt.mask = datt_shards ? datt.mask : n_shards - 1; }
-  const int staged = (stage_att || stage_rep) ? 1 : 0;
+  const int staged = (stage_att || stage_rep) ? (stage_all ? 2 : 1) : 0;
   if (staged) {
     B200_REQUIRE(n_shards > 1 && my_rank >= 0 && my_rank < n_shards && stage_cap >= B * K, B200CTR_E_INVALID_ARG,
                  "retrieve_bwd: staging needs n_shards > 1, a valid rank and stage_cap >= B*K");
@@ -533,7 +533,7 @@ extern "C" int b200ctr_retrieve_bwd_sharded(const int32_t* tok, const float* q, 
                                             const float* dsel_rep, const float* dvals, int64_t B, int K, int D, int pad_id,
                                             float* dq, float* const* datt_shards, float* const* drep_shards, void* stream) {
   return b200ctr_retrieve_bwd_staged(tok, q, att_shards, n_shards, dsel_rep, dvals, B, K, D, pad_id, dq, datt_shards, drep_shards,
-                                     nullptr, nullptr, 0, 0, stream);
+                                     nullptr, nullptr, 0, 0, 0, stream);
 }
 
 extern "C" int b200ctr_stage_apply(const int32_t* gtok, int n_src, int64_t n_slots, int64_t stage_cap, int pad_id, int n_shards,

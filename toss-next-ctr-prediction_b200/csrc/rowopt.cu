@@ -312,7 +312,7 @@ rows_sqnorm_bm_kernel(const uint32_t* __restrict__ bm, int n_maps, int64_t words
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int k = 0; k < 8; ++k) t += red[k];
-    atomicAdd(acc, t);
+    norm_acc_add(acc, t);
   }
 }
 
