@@ -156,15 +156,16 @@ int b200ctr_cat_fwd(const void* x_cat, int idx_is_64, const float* const* tables
                     const int32_t* dims, const int32_t* cards, float* out, int64_t ld_b,
                     float* mean_out, int64_t ld_mean, int q_idx, float* q_out,
                     int64_t B, int Fc, int D, b200ctr_dropout_t drop, void* stream);
-/* cat_bwd is deterministic (no float atomics): kernel 1 writes every sample's contribution W_c^T g to a (B, sum_dims) workspace
- * and per-CTA partials of dW_c; kernel 2 (thread per table row) adds the contributions of the samples that hit the row in
- * ascending sample order; kernel 3 adds the dW_c partials in CTA order.  sum_dims = sum_c d_c, max_card = max_c card_c;
- * dtables / dprojs are accumulated into (single writer per element).                                                  */
-int64_t b200ctr_cat_bwd_workspace_bytes(int64_t B, int sum_dims);
+/* cat_bwd is deterministic (no float atomics): kernel 1 writes every (sample, column) slot's contribution W_c^T g as a 64-wide
+ * row plus the slot's global table row id (row_base_c + id), and per-CTA partials of dW_c; b200ctr_scatter_rows sorts the slots
+ * by table row and reduces each distinct row once, in (sample, column) order; the reduced rows are added into dE_c and the
+ * dW_c partials are added in CTA order.  sum_dims = sum_c d_c, sum_cards = sum_c card_c, max_card = max_c card_c; dtables /
+ * dprojs are accumulated into (single writer per element).  The same path serves HBM-sized hashed tables (v4 cfgs).      */
+int64_t b200ctr_cat_bwd_workspace_bytes(int64_t B, int Fc, int sum_dims, int64_t sum_cards);
 int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
                     const int32_t* dims, const int32_t* cards, const float* dout, int64_t ld_b,
                     const float* dmean, int64_t ld_dmean, int q_idx, const float* dq, float* const* dtables,
-                    float* const* dprojs, int64_t B, int Fc, int D, int sum_dims, int max_card,
+                    float* const* dprojs, int64_t B, int Fc, int D, int sum_dims, int64_t sum_cards, int max_card,
                     b200ctr_dropout_t drop, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- query mix  (wrapper.py:128-136): q = a*s1 + b*s2 ; bwd: ds2pre = b*dq*(s2>0) --------------------- */

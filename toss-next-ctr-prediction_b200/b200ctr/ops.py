@@ -333,12 +333,13 @@ def cat_bwd(x_cat, ct: CatTables, dout, ld_b, dmean, ld_dmean, q_idx, dq, dtable
     dt_ptrs, dp_ptrs = _ptr_table(dtables), _ptr_table(dprojs)
     sum_dims = int(sum(t.shape[1] for t in dtables))
     max_card = int(max(t.shape[0] for t in dtables))
-    ws_bytes = int(lib.b200ctr_cat_bwd_workspace_bytes(B, sum_dims))
+    sum_cards = int(sum(t.shape[0] for t in dtables))
+    ws_bytes = int(lib.b200ctr_cat_bwd_workspace_bytes(B, Fc, sum_dims, sum_cards))
     ws = torch.empty((ws_bytes,), device=x_cat.device, dtype=torch.uint8)
     _run("cat_bwd", lib.b200ctr_cat_bwd, _p(x_cat), _idx64(x_cat), _p(ct.t_ptrs), _p(ct.p_ptrs), _p(ct.dims), _p(ct.cards),
                               _p(dout), ld_b, _p(dmean), ld_dmean, q_idx, _p(dq), _p(dt_ptrs), _p(dp_ptrs),
-                              B, Fc, D, sum_dims, max_card, dropout, _p(ws), ws_bytes, _stream())
-    _count(3)
+                              B, Fc, D, sum_dims, sum_cards, max_card, dropout, _p(ws), ws_bytes, _stream())
+    _count(7)
 
 
 def axpby(x, y, a, b, out=None):

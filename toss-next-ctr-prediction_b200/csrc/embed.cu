@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256)
 cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ tables, const float* const* __restrict__ projs,
                const int32_t* __restrict__ dims, const int32_t* __restrict__ cards, const float* __restrict__ dout, int64_t ld_b,
                const float* __restrict__ dmean, int64_t ld_dmean, int q_idx, const float* __restrict__ dq,
-               float* __restrict__ rowg, float* __restrict__ dwpart, int sumdc, int64_t B, int Fc,
+               float* __restrict__ rowg, int32_t* __restrict__ keys, float* __restrict__ dwpart, int sumdc, int64_t B, int Fc,
                b200ctr_dropout_t drop) {
   __shared__ float Ws[CAT_D][CAT_MAXDC + 1];           // natural layout W[n][j]
   __shared__ float gs[CATB_TS][CAT_D + 1];
@@ -217,8 +217,8 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   const int card = cards[c];
   const float* W = projs[c];
   const float* T = tables[c];
-  int off_c = 0;                                          // column offset inside a sample's row of table-row gradients
-  for (int cc = 0; cc < c; ++cc) off_c += dims[cc];
+  int off_c = 0, row_base = 0;                            // column offset of dW_c in a partial; first global row id of table c
+  for (int cc = 0; cc < c; ++cc) { off_c += dims[cc]; row_base += cards[cc]; }
   const int tid = threadIdx.x;
   for (int i = tid; i < CAT_D * dc; i += blockDim.x) Ws[i / dc][i % dc] = W[i];
   // this thread's dW elements: e = tid + k*256 < 64*dc  (<= 16 of them)
@@ -273,8 +273,11 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
       float a = 0.f;
 #pragma unroll 8
       for (int n = 0; n < CAT_D; ++n) a = fmaf(Ws[n][j], gs[s][n], a);
-      rowg[(b0 + s) * (int64_t)sumdc + off_c + j] = a;      // this sample's contribution to dE_c[id]; summed per table row in
-    }                                                       // sample order by cat_dtable_kernel (no float atomics)
+      // this sample's contribution to dE_c[id], as a 64-wide row (columns >= d_c stay zero) of slot (b, c): the slots are
+      // sorted by global table row and reduced in slot order by b200ctr_scatter_rows (no float atomics)
+      rowg[((b0 + s) * Fc + c) * (int64_t)CAT_D + j] = a;
+    }
+    if (tid < CATB_TS && b0 + tid < B) keys[(b0 + tid) * Fc + c] = row_base + (int32_t)ids[tid];
   }
   // this CTA's partial dW_c; the partials are added in CTA order by cat_dw_reduce_kernel
   float* dwp = dwpart + (int64_t)blockIdx.x * CAT_D * sumdc + (int64_t)CAT_D * off_c;
@@ -285,47 +288,18 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   }
 }
 
-// dE_c[row, :] += sum over the samples b with x_cat[b, c] == row, in ascending b, of rowg[b, off_c : off_c + d_c].
-// Thread per table row; the column's B ids are walked through shared memory (a broadcast read per comparison).
-constexpr int CATT_TILE = 2048;
-template <typename IT>
+// dE_c[r, 0:d_c] += temp[row_base_c + r, 0:d_c]  (temp: the 64-wide reduced rows of all tables, one global row id per table row)
 __global__ void __launch_bounds__(256)
-cat_dtable_kernel(const IT* __restrict__ x_cat, const int32_t* __restrict__ dims, const int32_t* __restrict__ cards,
-                  const float* __restrict__ rowg, int sumdc, float* const* __restrict__ dtables, int64_t B, int Fc) {
-  __shared__ int32_t ids[CATT_TILE];
+cat_unpad_kernel(const float* __restrict__ temp, const int32_t* __restrict__ dims, const int32_t* __restrict__ cards,
+                 float* const* __restrict__ dtables, int Fc) {
   const int c = blockIdx.y, dc = dims[c], card = cards[c];
-  if ((int64_t)blockIdx.x * blockDim.x >= card) return;
-  int off_c = 0;
-  for (int cc = 0; cc < c; ++cc) off_c += dims[cc];
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  float acc[CAT_MAXDC];
-#pragma unroll
-  for (int j = 0; j < CAT_MAXDC; ++j) acc[j] = 0.f;
-  bool any = false;
-  for (int64_t b0 = 0; b0 < B; b0 += CATT_TILE) {
-    const int nb = (int)min((int64_t)CATT_TILE, B - b0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-      int64_t id = (int64_t)x_cat[(b0 + i) * Fc + c];
-      ids[i] = (int32_t)(id < 0 ? 0 : (id >= card ? card - 1 : id));
-    }
-    __syncthreads();
-    for (int i = 0; i < nb; ++i) {
-      if (ids[i] == row) {
-        any = true;
-        const float* src = rowg + (b0 + i) * (int64_t)sumdc + off_c;
-#pragma unroll
-        for (int j = 0; j < CAT_MAXDC; ++j)
-          if (j < dc) acc[j] += src[j];
-      }
-    }
-  }
-  if (any && row < card) {
-    float* dT = dtables[c] + (int64_t)row * dc;
-#pragma unroll
-    for (int j = 0; j < CAT_MAXDC; ++j)
-      if (j < dc) dT[j] += acc[j];                          // single writer per row: plain read-modify-write
-  }
+  int row_base = 0;
+  for (int cc = 0; cc < c; ++cc) row_base += cards[cc];
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)card * dc) return;
+  const int r = (int)(e / dc), j = (int)(e - (int64_t)r * dc);
+  const float v = temp[(int64_t)(row_base + r) * CAT_D + j];
+  if (v != 0.f) dtables[c][e] += v;                       // single writer per element
 }
 
 __global__ void __launch_bounds__(256)
@@ -456,36 +430,52 @@ extern "C" int b200ctr_cat_fwd(const void* x_cat, int idx_is_64, const float* co
   return B200CTR_OK;
 }
 
-extern "C" int64_t b200ctr_cat_bwd_workspace_bytes(int64_t B, int sum_dims) {
-  // per-sample table-row gradients (B x sum d_c) + 64 per-CTA partials of all dW_c (64 x 64 x sum d_c)
-  return (int64_t)sizeof(float) * (std::max<int64_t>(B, 1) * sum_dims + (int64_t)64 * CAT_D * sum_dims);
+static size_t cat_al(size_t x) { return (x + 255) & ~(size_t)255; }
+extern "C" int64_t b200ctr_cat_bwd_workspace_bytes(int64_t B, int Fc, int sum_dims, int64_t sum_cards) {
+  const int64_t n = std::max<int64_t>(B, 1) * Fc;
+  size_t t = cat_al((size_t)n * 4);                                       // keys: global table row of slot (b, c)
+  t += cat_al((size_t)n * CAT_D * 4);                                     // 64-wide contribution rows of the slots
+  t += cat_al((size_t)sum_cards * CAT_D * 4);                             // reduced rows of all tables
+  t += cat_al((size_t)64 * CAT_D * sum_dims * 4);                         // per-CTA partials of all dW_c
+  t += (size_t)b200ctr_scatter_rows_workspace_bytes(n, sum_cards);
+  return (int64_t)t;
 }
 
 extern "C" int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
                                const int32_t* dims, const int32_t* cards, const float* dout, int64_t ld_b,
                                const float* dmean, int64_t ld_dmean, int q_idx, const float* dq, float* const* dtables,
-                               float* const* dprojs, int64_t B, int Fc, int D, int sum_dims, int max_card,
+                               float* const* dprojs, int64_t B, int Fc, int D, int sum_dims, int64_t sum_cards, int max_card,
                                b200ctr_dropout_t drop, void* workspace, int64_t workspace_bytes, void* stream) {
   B200_REQUIRE(x_cat && tables && projs && dims && cards && dtables && dprojs && workspace, B200CTR_E_INVALID_ARG, "cat_bwd: null pointer");
   B200_REQUIRE(D == CAT_D, B200CTR_E_UNSUPPORTED_SHAPE, "cat_bwd: emb_dim=%d unsupported (kernel is specialised for 64)", D);
-  B200_REQUIRE(sum_dims > 0 && max_card > 0 && workspace_bytes >= b200ctr_cat_bwd_workspace_bytes(B, sum_dims), B200CTR_E_INVALID_ARG,
-               "cat_bwd: workspace too small (sum_dims=%d)", sum_dims);
+  B200_REQUIRE(sum_dims > 0 && sum_cards > 0 && max_card > 0 && workspace_bytes >= b200ctr_cat_bwd_workspace_bytes(B, Fc, sum_dims, sum_cards),
+               B200CTR_E_INVALID_ARG, "cat_bwd: workspace too small (sum_dims=%d sum_cards=%lld)", sum_dims, (long long)sum_cards);
   if (B == 0 || Fc == 0) return B200CTR_OK;
   dim3 grid((unsigned)std::min<int64_t>(ceil_div(B, (int64_t)CATB_TS), 64), (unsigned)Fc);     // wide columns (d_c up to 64) set the tail: many short CTAs
   cudaStream_t st = as_stream(stream);
-  float* rowg = (float*)workspace;
-  float* dwpart = rowg + std::max<int64_t>(B, 1) * sum_dims;
+  const int64_t n = B * Fc;
+  char* w = (char*)workspace;
+  int32_t* keys = (int32_t*)w; w += cat_al((size_t)n * 4);
+  float* rowg = (float*)w; w += cat_al((size_t)n * CAT_D * 4);
+  float* temp = (float*)w; w += cat_al((size_t)sum_cards * CAT_D * 4);
+  float* dwpart = (float*)w; w += cat_al((size_t)64 * CAT_D * sum_dims * 4);
+  const int64_t sc_bytes = b200ctr_scatter_rows_workspace_bytes(n, sum_cards);
+  cudaError_t e = cudaMemsetAsync(rowg, 0, (size_t)n * CAT_D * 4, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(temp, 0, (size_t)sum_cards * CAT_D * 4, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cat_bwd memset");
   if (idx_is_64)
     cat_bwd_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)x_cat, tables, projs, dims, cards, dout, ld_b, dmean,
-                                                   ld_dmean, q_idx, dq, rowg, dwpart, sum_dims, B, Fc, drop);
+                                                   ld_dmean, q_idx, dq, rowg, keys, dwpart, sum_dims, B, Fc, drop);
   else
     cat_bwd_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)x_cat, tables, projs, dims, cards, dout, ld_b, dmean,
-                                                   ld_dmean, q_idx, dq, rowg, dwpart, sum_dims, B, Fc, drop);
+                                                   ld_dmean, q_idx, dq, rowg, keys, dwpart, sum_dims, B, Fc, drop);
   B200_LAUNCH_CHECK("cat_bwd_kernel");
-  dim3 tgrid((unsigned)ceil_div((int64_t)max_card, (int64_t)256), (unsigned)Fc);
-  if (idx_is_64) cat_dtable_kernel<int64_t><<<tgrid, 256, 0, st>>>((const int64_t*)x_cat, dims, cards, rowg, sum_dims, dtables, B, Fc);
-  else cat_dtable_kernel<int32_t><<<tgrid, 256, 0, st>>>((const int32_t*)x_cat, dims, cards, rowg, sum_dims, dtables, B, Fc);
-  B200_LAUNCH_CHECK("cat_dtable_kernel");
+  // every distinct table row is reduced once, its slots in (sample, column) order
+  int rc = b200ctr_scatter_rows(keys, 1, n, -1, sum_cards, 1, nullptr, nullptr, rowg, nullptr, nullptr, 0, 1, 0, nullptr, temp, w, sc_bytes, stream);
+  if (rc) return rc;
+  dim3 ugrid((unsigned)ceil_div((int64_t)max_card * CAT_MAXDC, (int64_t)256), (unsigned)Fc);
+  cat_unpad_kernel<<<ugrid, 256, 0, st>>>(temp, dims, cards, dtables, Fc);
+  B200_LAUNCH_CHECK("cat_unpad_kernel");
   dim3 wgrid((unsigned)ceil_div((int64_t)CAT_D * CAT_MAXDC, (int64_t)256), (unsigned)Fc);
   cat_dw_reduce_kernel<<<wgrid, 256, 0, st>>>(dwpart, (int)grid.x, dims, sum_dims, dprojs);
   B200_LAUNCH_CHECK("cat_dw_reduce_kernel");

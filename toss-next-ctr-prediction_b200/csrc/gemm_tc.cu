@@ -692,8 +692,10 @@ static int gemm_split(int transA, int transB, int64_t M, int64_t N, int64_t K, c
 #define SP_ARGS transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, split_k, ws, st
   // A/B switch (measured on B200, profiles/): the persistent warp-specialised pipeline also for the shallow-K shapes --
   // 4 producer + 8 epilogue warps, double-buffered TMEM accumulators, tiles of at most 96 columns (shared-memory budget)
-  static const bool ws_all = getenv("B200CTR_SPLIT_WS") != nullptr;
-  if (ws_all && k_per_split <= 512 && M >= 4096) {
+  // Measured on B200 (profiles/README.md, r02g): the persistent pipeline wins for the narrow-output / several-k-tile shapes
+  // (491,520 x 64 x 384: 0.57 vs 0.76 ms) and loses for the wide-output single-k-tile ones (x 384 x 64: 1.6 vs 1.2 ms).
+  static const bool ws_all = getenv("B200CTR_SPLIT_WS") != nullptr, ws_none = getenv("B200CTR_SPLIT_V1") != nullptr;
+  if (!ws_none && k_per_split <= 512 && M >= 4096 && (ws_all || (N <= 64 && k_per_split > TC_BK))) {
     if (N <= 64) return launch_tc_ws<64, float, SPLIT>(SP_ARGS);
     return launch_tc_ws<96, float, SPLIT>(SP_ARGS);
   }
