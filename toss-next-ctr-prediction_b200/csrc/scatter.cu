@@ -105,17 +105,34 @@ sc_reduce_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__
       if (which) m.y = (int)key; else { m.x = (int)key; m.z = ends ? 0 : 1; }
     }
   };
-  for (int i = 0; i < cnt; ++i) {
-    const uint32_t k = __shfl_sync(hmask, i < 16 ? k_lo : k_hi, hbase + (i & 15));
-    const uint32_t v = __shfl_sync(hmask, i < 16 ? v_lo : v_hi, hbase + (i & 15));
-    if (k != cur) {
-      flush(cur, run_start, i);
-      cur = k; run_start = i; aa = z4; ar = z4;
+  // The rows of SC_PF consecutive slots are fetched before any of them is added (independent loads in flight; the adds stay
+  // in slot order, so the association order -- and the result bits -- do not change).
+  constexpr int SC_PF = 4;
+  bool done = false;
+  for (int i0 = 0; i0 < cnt && !done; i0 += SC_PF) {
+    uint32_t kk[SC_PF];
+    float4 pa[SC_PF], pr[SC_PF];
+#pragma unroll
+    for (int u = 0; u < SC_PF; ++u) {
+      const int i = i0 + u;
+      kk[u] = __shfl_sync(hmask, i < 16 ? k_lo : k_hi, hbase + (i & 15));
+      const uint32_t v = __shfl_sync(hmask, i < 16 ? v_lo : v_hi, hbase + (i & 15));
+      if (i >= cnt) kk[u] = sentinel;
+      pa[u] = z4; pr[u] = z4;
+      if (kk[u] != sentinel) sc_load(S, v, hl, pa[u], pr[u], want_att, want_rep);
     }
-    if (k == sentinel) break;                           // sorted: only pad / foreign slots follow
-    float4 a = z4, r = z4;
-    sc_load(S, v, hl, a, r, want_att, want_rep);
-    f4_add(aa, a); f4_add(ar, r);
+#pragma unroll
+    for (int u = 0; u < SC_PF; ++u) {
+      const int i = i0 + u;
+      if (i >= cnt) break;
+      const uint32_t k = kk[u];
+      if (k != cur) {
+        flush(cur, run_start, i);
+        cur = k; run_start = i; aa = z4; ar = z4;
+      }
+      if (k == sentinel) { done = true; break; }        // sorted: only pad / foreign slots follow
+      f4_add(aa, pa[u]); f4_add(ar, pr[u]);
+    }
   }
   if (cur != sentinel) {
     int end = cnt;
