@@ -74,6 +74,8 @@ def ema_decay_at(n_updates: int, base: float, warmup_steps: int = 0, warmup_type
 
 
 BIG_TABLES = ("dare.emb_att.weight", "dare.emb_rep.weight")
+import os as _os
+C5_MODE = _os.environ.get("B200CTR_C5", "gather")        # "allreduce": NCCL int64 sum (A/B timing)
 
 
 class FusedTrainer:
@@ -188,6 +190,7 @@ class FusedTrainer:
             self.bm_mine = torch.zeros(self.bm_words, device=dev, dtype=torch.int32)
             self.bm_all = torch.zeros(self.n_shards * self.bm_words, device=dev, dtype=torch.int32) if self.shard else None
         self.acc = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.acc_all = torch.zeros(max(1, self.world), device=dev, dtype=torch.float64)
         self.coef = torch.ones(1, device=dev, dtype=torch.float32)
         self._bar = torch.zeros(4, device=dev, dtype=torch.float32)      # payload of the barrier all-reduces (+ class counts)
         self.total_norm = torch.zeros(1, device=dev, dtype=torch.float32)
@@ -466,7 +469,13 @@ class FusedTrainer:
             for n in BIG_TABLES:
                 ops.rows_sqnorm_bm(maps, n_maps, self.bm_words, self.n_shards, self.shard_rank, self.tables[n]["g"], self.acc)
             if self.shard:
-                self._allreduce(self.acc.view(torch.int64), "C5_sqnorm")   # the accumulator is a fixed-point integer (order-independent)           # C5: each owner contributes the squared norm of its rows
+                # C5: each owner contributes the squared norm of its rows.  The accumulator is a fixed-point 64-bit integer
+                # (order-independent sum); the ranks' 8-byte slots are all-gathered and added as integers
+                if C5_MODE == "gather":
+                    self._allgather(self.acc_all, self.acc, "C5_sqnorm")
+                    self.acc.view(torch.int64).copy_(self.acc_all.view(torch.int64).sum(0, keepdim=True))
+                else:
+                    self._allreduce(self.acc.view(torch.int64), "C5_sqnorm")
         else:
             ops.rows_claim(tok, spec.pad_id, self.owner)
             for n in BIG_TABLES:
