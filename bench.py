@@ -363,6 +363,19 @@ def measure(env, cfg, vocab, dev_b, host, steps, warmup, profile=False, e2e=Fals
     ms = env.timed(dev_loop, steps)
     if profile:
         out["prof"] = ops.profile_stop()
+        if env.world > 1:          # per-rank view: which rank's kernels make the others wait inside the collectives
+            fam = {}
+            for tag, (n, t) in out["prof"].items():
+                f = tag.split("[")[0]
+                fam[f] = fam.get(f, 0.0) + t / steps
+            mine = {k: round(v, 4) for k, v in fam.items() if v > 0.1}
+            per = {}
+            for tag, a, b in tr.comm_prof:
+                per[tag] = per.get(tag, 0.0) + a.elapsed_time(b) / steps
+            mine.update({"comm:" + k: round(v, 4) for k, v in per.items()})
+            allr = [None] * env.world
+            env.dist.all_gather_object(allr, mine)
+            out["per_rank_ms"] = allr
         out["comm_ms_per_step"] = sum(a.elapsed_time(b) for _, a, b in tr.comm_prof) / steps
         per = {}
         for tag, a, b in tr.comm_prof:
@@ -605,6 +618,7 @@ def run_cuda(args):
             line["comm_ms_per_step"] = round(r["comm_ms_per_step"], 4)
             line["comm_ms_by_call"] = r["comm_ms_by_call"]
             line["comm_calls_per_step"] = r["comm_calls_per_step"]
+            line["per_rank_ms"] = r["per_rank_ms"]
             line["dp_parity"] = parity
         if os.environ.get("B200CTR_BENCH_DUMP"):      # full per-op table (development aid): every family and GEMM shape
             with open(os.environ["B200CTR_BENCH_DUMP"], "w") as fh:
