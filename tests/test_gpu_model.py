@@ -401,6 +401,7 @@ def test_sorted_scatter_equals_atomic_scatter_and_the_oracle():
     tok = torch.randint(1, 40, (B, K), generator=g)                        # 39 hot rows
     tok[torch.rand(B, K, generator=g) < 0.3] = torch.randint(40, V, (1,), generator=g).item()
     tok[:, -3:] = torch.randint(1, V, (B, 3), generator=g)                 # + rows hit once
+    tok[:, :15] = 7                                                        # + one row with 4,500 slots: ~140 chunks, solid groups
     tok[torch.rand(B, K, generator=g) < 0.1] = 0                           # pad slots
     q = torch.randn(B, D, generator=g)
     dvals = torch.randn(B, K, generator=g)

@@ -102,7 +102,8 @@ sc_reduce_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__
       float4* dst = part + ((c * 2 + which) * 2) * (SC_D / 4) + hl;
       if (want_att) dst[0] = aa;
       if (want_rep) dst[SC_D / 4] = ar;
-      if (which) m.y = (int)key; else { m.x = (int)key; m.z = ends ? 0 : 1; }
+      if (which) m.y = (int)key;
+      else { m.x = (int)key; m.z = ends ? 0 : 1; m.w = (!ends && a == 0 && b == SC_CHUNK) ? 1 : 0; }   // w: the WHOLE chunk is one row that goes on
     }
   };
   // The rows of SC_PF consecutive slots are fetched before any of them is added (independent loads in flight; the adds stay
@@ -142,8 +143,44 @@ sc_reduce_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__
   if (hl == 0) meta[c] = m;
 }
 
+// Level 2: a row that collects thousands of slots (the hot tokens of a Zipf stream: 8 % of all slots for the hottest one) spans
+// hundreds of chunks, and stitching them one by one would serialise one half-warp for a millisecond.  One half-warp per GROUP of
+// 32 chunks: if all 32 are FULL chunks of the same row, their HEAD partials are added in chunk order into one group partial, and
+// the stitch below steps over the whole group at once.  The association order still depends on the sorted data only.
+constexpr int SC_GROUP = 32;
 __global__ void __launch_bounds__(256)
-sc_stitch_kernel(const float4* __restrict__ part, const int4* __restrict__ meta, int64_t n_chunks, int shift,
+sc_group_kernel(const float4* __restrict__ part, const int4* __restrict__ meta, int64_t n_chunks, int64_t n_groups, bool want_att,
+                bool want_rep, float4* __restrict__ gpart, int32_t* __restrict__ gmeta) {
+  const int hl = threadIdx.x & 15, hbase = threadIdx.x & 16;
+  const uint32_t hmask = 0xffffu << hbase;
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  if (g >= n_groups) return;
+  const int64_t c0 = g * SC_GROUP;
+  bool solid = c0 + SC_GROUP <= n_chunks;
+  int key = -1;
+  if (solid) {
+    const int4 m0 = meta[c0 + hl], m1 = meta[c0 + hl + 16];
+    key = __shfl_sync(hmask, m0.x, hbase);
+    const bool ok = m0.w && m1.w && m0.x == key && m1.x == key && key >= 0;
+    solid = __all_sync(hmask, ok);
+  }
+  if (!solid) { if (hl == 0) gmeta[g] = -1; return; }
+  float4 aa = make_float4(0.f, 0.f, 0.f, 0.f), ar = aa;
+#pragma unroll 8
+  for (int i = 0; i < SC_GROUP; ++i) {
+    const float4* h = part + (((c0 + i) * 2 + 0) * 2) * (SC_D / 4) + hl;
+    if (want_att) f4_add(aa, h[0]);
+    if (want_rep) f4_add(ar, h[SC_D / 4]);
+  }
+  float4* dst = gpart + (g * 2) * (SC_D / 4) + hl;
+  if (want_att) dst[0] = aa;
+  if (want_rep) dst[SC_D / 4] = ar;
+  if (hl == 0) gmeta[g] = key;
+}
+
+__global__ void __launch_bounds__(256)
+sc_stitch_kernel(const float4* __restrict__ part, const int4* __restrict__ meta, const float4* __restrict__ gpart,
+                 const int32_t* __restrict__ gmeta, int64_t n_chunks, int64_t n_groups, int shift,
                  float* __restrict__ g_att, float* __restrict__ g_rep) {
   const int hl = threadIdx.x & 15;
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
@@ -154,13 +191,22 @@ sc_stitch_kernel(const float4* __restrict__ part, const int4* __restrict__ meta,
   const bool want_att = g_att != nullptr, want_rep = g_rep != nullptr;
   const float4* src = part + ((c * 2 + 1) * 2) * (SC_D / 4) + hl;
   float4 aa = want_att ? src[0] : make_float4(0.f, 0.f, 0.f, 0.f), ar = want_rep ? src[SC_D / 4] : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t cc = c + 1; cc < n_chunks; ++cc) {
+  int64_t cc = c + 1;
+  while (cc < n_chunks) {
+    if ((cc % SC_GROUP) == 0 && cc / SC_GROUP < n_groups && gmeta[cc / SC_GROUP] == key) {
+      const float4* gp = gpart + ((cc / SC_GROUP) * 2) * (SC_D / 4) + hl;   // 32 full chunks of this row at once
+      if (want_att) f4_add(aa, gp[0]);
+      if (want_rep) f4_add(ar, gp[SC_D / 4]);
+      cc += SC_GROUP;                                    // a solid group always goes on into the next chunk
+      continue;
+    }
     const int4 mm = meta[cc];
     if (mm.x != key) break;
     const float4* h = part + ((cc * 2 + 0) * 2) * (SC_D / 4) + hl;
     if (want_att) f4_add(aa, h[0]);
     if (want_rep) f4_add(ar, h[SC_D / 4]);
     if (!mm.z) break;
+    ++cc;
   }
   const int64_t row = (int64_t)(key >> shift) * (SC_D / 4) + hl;
   if (want_att) reinterpret_cast<float4*>(g_att)[row] = aa;
@@ -193,6 +239,8 @@ extern "C" int64_t b200ctr_scatter_rows_workspace_bytes(int64_t n_total_slots, i
   total += align256(sort_temp_bytes(n_total_slots, key_bits(vocab)));
   total += align256((size_t)n_chunks * 2 * 2 * SC_D * 4);                                 // partial rows
   total += align256((size_t)n_chunks * sizeof(int4));
+  const int64_t n_groups = ceil_div(n_chunks, (int64_t)SC_GROUP);
+  total += align256((size_t)n_groups * 2 * SC_D * 4) + align256((size_t)n_groups * 4);      // group partials + group keys
   return (int64_t)total;
 }
 
@@ -225,7 +273,10 @@ extern "C" int b200ctr_scatter_rows(const int32_t* tok, int n_src, int64_t n_slo
   size_t tb = sort_temp_bytes(n, bits);
   void* temp = w; w += align256(tb);
   float4* part = (float4*)w; w += align256((size_t)n_chunks * 2 * 2 * SC_D * 4);
-  int4* meta = (int4*)w;
+  int4* meta = (int4*)w; w += align256((size_t)n_chunks * sizeof(int4));
+  const int64_t n_groups = ceil_div(n_chunks, (int64_t)SC_GROUP);
+  float4* gpart = (float4*)w; w += align256((size_t)n_groups * 2 * SC_D * 4);
+  int32_t* gmeta = (int32_t*)w;
   int shift = 0;
   while ((1 << shift) < n_shards) ++shift;
   sc_keys_kernel<<<(unsigned)ceil_div(n, (int64_t)256), 256, 0, st>>>(tok, n, pad_id, n_shards - 1, rank, (uint32_t)vocab, keys, vals);
@@ -239,7 +290,10 @@ extern "C" int b200ctr_scatter_rows(const int32_t* tok, int n_src, int64_t n_slo
   const unsigned grid = (unsigned)ceil_div(n_chunks * 16, (int64_t)256);
   sc_reduce_kernel<<<grid, 256, 0, st>>>(skeys, svals, n, (uint32_t)vocab, shift, S, g_att, g_rep, part, meta, n_chunks);
   B200_LAUNCH_CHECK("sc_reduce_kernel");
-  sc_stitch_kernel<<<grid, 256, 0, st>>>(part, meta, n_chunks, shift, g_att, g_rep);
+  sc_group_kernel<<<(unsigned)ceil_div(n_groups * 16, (int64_t)256), 256, 0, st>>>(part, meta, n_chunks, n_groups, g_att != nullptr,
+                                                                                    g_rep != nullptr, gpart, gmeta);
+  B200_LAUNCH_CHECK("sc_group_kernel");
+  sc_stitch_kernel<<<grid, 256, 0, st>>>(part, meta, gpart, gmeta, n_chunks, n_groups, shift, g_att, g_rep);
   B200_LAUNCH_CHECK("sc_stitch_kernel");
   return B200CTR_OK;
 }
