@@ -7,6 +7,7 @@ All wrappers raise if a tensor is not on a CUDA device (there is no fallback pat
 from __future__ import annotations
 
 import ctypes
+import os as _os
 from typing import Optional, Sequence
 
 import torch
@@ -43,8 +44,21 @@ def profile_stop():
     return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (prof or {}).items()}
 
 
+# NVTX range per C-ABI call (B200CTR_NVTX=1): the kernels of one op show up under the op's name in Nsight timelines
+_NVTX = _os.environ.get("B200CTR_NVTX", "0") not in ("", "0")
+
+
 def _run(what, fn, *args):
     global _TAG
+    if _NVTX:
+        torch.cuda.nvtx.range_push(what if _TAG is None else f"{what}{_TAG}")
+        try:
+            rc = fn(*args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+        _TAG = None
+        check(rc, what)
+        return
     if _PROF is None:
         rc = fn(*args)
     else:
