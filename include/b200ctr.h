@@ -152,21 +152,27 @@ int b200ctr_numbin_unfold(const float* dP, const float* dQ, const float* w, cons
  * fwd: e = E_c[x_cat[b,c]] @ W_c^T ; out[b,c,:] = dropout(e) at out + b*ld_b + c*D ; mean_out = mean_c e (pre-dropout);
  *      q_out[b,:] = e[b,q_idx,:] (pre-dropout, S1 query) when q_idx >= 0.
  * bwd: g = dropout'(dout[b,c,:]) + dmean[b,:]/Fc + (c==q_idx)*dq[b,:]; dE_c[idx] += W_c^T g ; dW_c += g (x) row.   */
+/* lds: device int32[Fc] row strides of the tables in elements (NULL = d_c, i.e. dense rows): tables kept under the row-lazy
+ * optimizer are stored 64 floats wide.                                                                                */
 int b200ctr_cat_fwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
-                    const int32_t* dims, const int32_t* cards, float* out, int64_t ld_b,
+                    const int32_t* dims, const int32_t* cards, const int32_t* lds, float* out, int64_t ld_b,
                     float* mean_out, int64_t ld_mean, int q_idx, float* q_out,
                     int64_t B, int Fc, int D, b200ctr_dropout_t drop, void* stream);
 /* cat_bwd is deterministic (no float atomics): kernel 1 writes every (sample, column) slot's contribution W_c^T g as a 64-wide
  * row plus the slot's global table row id (row_base_c + id), and per-CTA partials of dW_c; b200ctr_scatter_rows sorts the slots
  * by table row and reduces each distinct row once, in (sample, column) order; the reduced rows are added into dE_c and the
  * dW_c partials are added in CTA order.  sum_dims = sum_c d_c, sum_cards = sum_c card_c, max_card = max_c card_c; dtables /
- * dprojs are accumulated into (single writer per element).  The same path serves HBM-sized hashed tables (v4 cfgs).      */
+ * dprojs are accumulated into (single writer per element).  The same path serves HBM-sized hashed tables (v4 cfgs):
+ * rows_acc (optional) = a caller-owned ALL-ZERO (sum_cards, 64) buffer in global-row order that outlives the call, and
+ * keep_rows[c] != 0 leaves table c's reduced 64-wide rows there (they are the gradient rows the row-lazy optimizer
+ * consumes and re-zeroes) instead of adding them into dtables[c]; the other tables' rows are zeroed again.              */
 int64_t b200ctr_cat_bwd_workspace_bytes(int64_t B, int Fc, int sum_dims, int64_t sum_cards);
 int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
-                    const int32_t* dims, const int32_t* cards, const float* dout, int64_t ld_b,
+                    const int32_t* dims, const int32_t* cards, const int32_t* lds, const float* dout, int64_t ld_b,
                     const float* dmean, int64_t ld_dmean, int q_idx, const float* dq, float* const* dtables,
                     float* const* dprojs, int64_t B, int Fc, int D, int sum_dims, int64_t sum_cards, int max_card,
-                    b200ctr_dropout_t drop, void* workspace, int64_t workspace_bytes, void* stream);
+                    b200ctr_dropout_t drop, float* rows_acc, const int32_t* keep_rows, void* workspace,
+                    int64_t workspace_bytes, void* stream);
 
 /* ---- query mix  (wrapper.py:128-136): q = a*s1 + b*s2 ; bwd: ds2pre = b*dq*(s2>0) --------------------- */
 int b200ctr_axpby(const float* x, const float* y, float a, float b, float* out, int64_t n, void* stream);

@@ -418,3 +418,51 @@ def test_sorted_scatter_equals_atomic_scatter_and_the_oracle():
     g2a, g2r = torch.zeros(V, D, device=dev), torch.zeros(V, D, device=dev)
     ops.scatter_rows(tok.int().to(dev), 1, B * K, 0, V, K, q.to(dev), dvals.to(dev), drep.to(dev), None, None, 0, 1, 0, g2a, g2r)
     assert torch.equal(g_att, g2a) and torch.equal(g_rep, g2r)
+
+
+@pytest.mark.parametrize("kind", ["qnn_concat", "base_s1"])
+def test_row_lazy_categorical_tables_match_reference(kind):
+    """Enlarged hashed-categorical tables (cfgs/v4_k120_s1.yaml: 2,000,503 x 32 and 4,000,513 x 57 rows) take the sequence
+    tables' route in FusedTrainer: stored 64 wide outside the flat buffer, gradient rows from the sort + segmented reduction,
+    row-lazy AdamW + EMA.  Forced here on the small golden tables (threshold 100 rows: d_c = 33, 57 and 64 wide tables qualify)
+    and held to the reference's 3-step parameters and EMA shadows, and to the dense path over 8 steps with wandering ids."""
+    import copy
+    import b200ctr
+    dev = torch.device("cuda:0")
+    z, cfg = load_case(kind)
+    cfg = copy.deepcopy(cfg)
+    cfg["b200ctr"] = {"lazy_table_min_rows": 100}
+    m = _build(cfg, z, dev).train()
+    tr = b200ctr.FusedTrainer(m, cfg, steps_per_epoch=cfg["golden"]["steps_per_epoch"])
+    assert len(tr.cat_tables) >= 2 and not any(n in tr.offsets for n in tr.cat_tables)
+    for s in range(3):
+        batch, y = batch_of(z, s)
+        loss = tr.step(batch, y)
+        assert abs(float(loss.cpu()) - float(z[f"step{s}/loss"])) < 2e-4
+        if cfg["train"]["grad_clip_norm"] > 0:
+            assert abs(float(tr.total_norm.cpu()) - float(z[f"step{s}/total_norm"])) < 2e-4 * float(z[f"step{s}/total_norm"])
+    sd = m.state_dict()
+    for k, v in group(z, "final/").items():
+        assert max_err_scaled(sd[k].cpu(), v) < 1e-3, k
+    ema = tr.ema_state()
+    for k, v in group(z, "ema/").items():
+        assert max_err_scaled(ema[k].cpu(), v) < 1e-3, k
+    assert float(tr.cat_rows_acc.abs().max()) == 0.0                       # the row accumulator is back to all-zero
+    # lazy vs dense over 8 steps, ids wandering so that rows go stale and come back
+    finals = {}
+    cards = {c: cfg["data"]["hash_buckets"][c] + cfg["data"]["hash_buckets_margin"] for c in cfg["data"]["cat_cols"]}
+    cvec = torch.tensor([cards[c] for c in cfg["data"]["cat_cols"]])
+    for thr in (100, 10 ** 9):
+        c2 = copy.deepcopy(cfg)
+        c2["b200ctr"] = {"lazy_table_min_rows": thr}
+        m2 = _build(c2, z, dev).train()
+        t2 = b200ctr.FusedTrainer(m2, c2, steps_per_epoch=3)
+        for s in range(8):
+            batch, y = batch_of(z, s % 3)
+            xc = (batch["X_cat"] + 17 * (s % 4)) % cvec
+            t2.step(dict(batch, X_cat=xc), y)
+        finals[thr] = ({k: v.detach().clone() for k, v in m2.state_dict().items()}, {k: v.clone() for k, v in t2.ema_state().items()})
+    for k in finals[100][0]:
+        assert max_err_scaled(finals[100][0][k].cpu(), finals[10 ** 9][0][k].cpu()) < 1e-3, k
+    for k in finals[100][1]:
+        assert max_err_scaled(finals[100][1][k].cpu(), finals[10 ** 9][1][k].cpu()) < 1e-3, k

@@ -306,13 +306,15 @@ class CatTables:
         self.tables, self.projs = list(tables), list(projs)
         self.Fc = len(tables)
         for t, p in zip(tables, projs):
-            assert t.is_contiguous() and p.is_contiguous() and t.dtype == torch.float32
+            # a table is either dense (row stride d_c) or a [:, :d_c] view of a 64-wide store (row-lazy tables)
+            assert t.stride(1) == 1 and t.stride(0) in (t.shape[1], 64) and p.is_contiguous() and t.dtype == torch.float32
             if t.shape[1] > 64:
                 raise _lib.B200CtrError(f"categorical embedding dim {t.shape[1]} > 64 is not built")
         self.t_ptrs = torch.tensor([t.data_ptr() for t in tables], dtype=torch.int64, device=dev)
         self.p_ptrs = torch.tensor([p.data_ptr() for p in projs], dtype=torch.int64, device=dev)
         self.dims = torch.tensor([t.shape[1] for t in tables], dtype=torch.int32, device=dev)
         self.cards = torch.tensor([t.shape[0] for t in tables], dtype=torch.int32, device=dev)
+        self.lds = torch.tensor([t.stride(0) if t.shape[0] > 1 else t.shape[1] for t in tables], dtype=torch.int32, device=dev)
         self._key = tuple(t.data_ptr() for t in tables) + tuple(p.data_ptr() for p in projs)
 
     def matches(self, tables, projs) -> bool:
@@ -336,23 +338,26 @@ def cat_fwd(x_cat, ct: CatTables, out, ld_b, mean_out, ld_mean, q_idx, q_out, D,
     B, Fc = x_cat.shape
     assert Fc == ct.Fc and x_cat.is_contiguous()
     _run("cat_fwd", lib.b200ctr_cat_fwd, _p(x_cat), _idx64(x_cat), _p(ct.t_ptrs), _p(ct.p_ptrs), _p(ct.dims), _p(ct.cards),
-                              _p(out), ld_b, _p(mean_out), ld_mean, q_idx, _p(q_out), B, Fc, D, dropout, _stream())
+                              _p(ct.lds), _p(out), ld_b, _p(mean_out), ld_mean, q_idx, _p(q_out), B, Fc, D, dropout, _stream())
     _count()
 
 
-def cat_bwd(x_cat, ct: CatTables, dout, ld_b, dmean, ld_dmean, q_idx, dq, dtables, dprojs, D, dropout=NO_DROP):
-    """dtables/dprojs: lists of ZEROED gradient tensors (accumulated into)."""
+def cat_bwd(x_cat, ct: CatTables, dout, ld_b, dmean, ld_dmean, q_idx, dq, dtables, dprojs, D, dropout=NO_DROP, rows_acc=None,
+            keep_rows=None):
+    """dtables/dprojs: lists of ZEROED gradient tensors (accumulated into).  rows_acc / keep_rows: the trainer's persistent
+    all-zero (sum_cards, 64) row accumulator and the int32 per-table flags of its row-lazy tables (their reduced rows stay in
+    rows_acc; their dtables entry is ignored and may be any tensor of the right row count)."""
     lib = _lib.load()
     B, Fc = x_cat.shape
     dt_ptrs, dp_ptrs = _ptr_table(dtables), _ptr_table(dprojs)
-    sum_dims = int(sum(t.shape[1] for t in dtables))
-    max_card = int(max(t.shape[0] for t in dtables))
-    sum_cards = int(sum(t.shape[0] for t in dtables))
+    sum_dims = int(sum(t.shape[1] for t in ct.tables))
+    max_card = int(max(t.shape[0] for t in ct.tables))
+    sum_cards = int(sum(t.shape[0] for t in ct.tables))
     ws_bytes = int(lib.b200ctr_cat_bwd_workspace_bytes(B, Fc, sum_dims, sum_cards))
     ws = torch.empty((ws_bytes,), device=x_cat.device, dtype=torch.uint8)
     _run("cat_bwd", lib.b200ctr_cat_bwd, _p(x_cat), _idx64(x_cat), _p(ct.t_ptrs), _p(ct.p_ptrs), _p(ct.dims), _p(ct.cards),
-                              _p(dout), ld_b, _p(dmean), ld_dmean, q_idx, _p(dq), _p(dt_ptrs), _p(dp_ptrs),
-                              B, Fc, D, sum_dims, sum_cards, max_card, dropout, _p(ws), ws_bytes, _stream())
+                              _p(ct.lds), _p(dout), ld_b, _p(dmean), ld_dmean, q_idx, _p(dq), _p(dt_ptrs), _p(dp_ptrs),
+                              B, Fc, D, sum_dims, sum_cards, max_card, dropout, _p(rows_acc), _p(keep_rows), _p(ws), ws_bytes, _stream())
     _count(7)
 
 

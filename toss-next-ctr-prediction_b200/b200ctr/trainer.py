@@ -111,7 +111,15 @@ class FusedTrainer:
             frozen |= {n for n in params if n.startswith("ctx_mlp.")}
         if spec.aux_weight <= 0:
             frozen |= {n for n in params if n.startswith("dare.aux_head.")}
-        small = [n for n in params if n not in BIG_TABLES]
+        # Hashed-categorical tables with an HBM-sized bucket count (cfgs/v4_k120_s1.yaml: 2,000,503 x 32 and 4,000,513 x 57;
+        # dare_base: 2,000,000 x 64 and 1,000,000 x 64) are kept OUT of the flat dense buffer and updated by the row-lazy
+        # optimizer like the sequence tables (a dense AdamW + EMA pass over them would cost 36 B per parameter per step).  One
+        # process only: under data parallelism they stay dense and replicated.
+        thr = int((cfg.get("b200ctr") or {}).get("lazy_table_min_rows", 500_000))
+        self.cat_lazy = [c for c in spec.cat_cols
+                         if lazy_tables and self.world == 1 and params[f"cat_embs.{c}.weight"].shape[0] >= thr]
+        lazy_names = {f"cat_embs.{c}.weight" for c in self.cat_lazy}
+        small = [n for n in params if n not in BIG_TABLES and n not in lazy_names]
         active = [n for n in small if n not in frozen] + [n for n in small if n in frozen]
         self.offsets: Dict[str, int] = {}
         off = 0
@@ -168,6 +176,32 @@ class FusedTrainer:
                 self.tables[n] = t
                 self.Gv[n] = t["g"]
         self.vocab = self.tables[BIG_TABLES[0]]["p"].shape[0]          # rows held by this rank
+        self.cat_tables: Dict[str, dict] = {}
+        if self.cat_lazy:
+            cards = [params[f"cat_embs.{c}.weight"].shape[0] for c in spec.cat_cols]
+            # ONE persistent all-zero (sum of cards, 64) accumulator in global-row order: cat_bwd leaves the reduced 64-wide
+            # gradient rows of the row-lazy tables here (their `g`), the optimizer consumes and re-zeroes them
+            self.cat_rows_acc = torch.zeros((sum(cards), 64), device=dev, dtype=torch.float32)
+            keep = torch.zeros(len(cards), dtype=torch.int32)
+            base = 0
+            for ci, c in enumerate(spec.cat_cols):
+                if c in self.cat_lazy:
+                    n = f"cat_embs.{c}.weight"
+                    full = params[n].data
+                    card, dcw = full.shape
+                    p = torch.zeros((card, 64), device=dev, dtype=torch.float32)       # stored 64 wide: the row kernels' width
+                    p[:, :dcw].copy_(full)
+                    params[n].data = p[:, :dcw]                                        # the module sees the same storage
+                    self.P[n] = p[:, :dcw]
+                    t = dict(p=p, m=torch.zeros_like(p), v=torch.zeros_like(p), g=self.cat_rows_acc[base:base + card],
+                             ema=p.clone() if self.ema_on else None, state=torch.zeros(card, device=dev, dtype=torch.int32),
+                             words=ops.bitmap_words(card), col=ci, dc=dcw, card=card)
+                    t["bm"] = torch.zeros(t["words"], device=dev, dtype=torch.int32)
+                    self.cat_tables[n] = t
+                    self.Gv[n] = t["g"]
+                    keep[ci] = 1
+                base += cards[ci]
+            self.cat_keep_rows = keep.to(dev)
         if self.lazy:
             # initial capacity only: RowHistory grows geometrically when the run outlives the estimate
             cap = min(max(self.epochs * self.steps_per_epoch + 64, 4096), 1 << 22)
@@ -200,6 +234,8 @@ class FusedTrainer:
         self._flushed_at = 0             # global_step at which every table row was last brought up to date (sync_tables)
         self.n_ema = 0
         self.cache: dict = {}
+        if self.cat_lazy:
+            self.cache["cat_rows_acc"], self.cache["cat_keep_rows"] = self.cat_rows_acc, self.cat_keep_rows
         defaults = {"update_after_step": 0, "update_interval": 1, "param_filter": [], "offload_to_cpu": False}
         for k, dv in defaults.items():
             v = ema.get(k, dv)
@@ -397,6 +433,14 @@ class FusedTrainer:
                     t = self.tables[n]
                     ops.rowopt_catchup(seq, spec.pad_id, self.owner, t["state"], t["p"], t["m"], t["v"], t["ema"],
                                        self.global_step - 1, self.hist)
+        for n, t in self.cat_tables.items():
+            # rows of the row-lazy categorical tables this batch reads: mark, then bring them to step t-1
+            ids = dbatch["X_cat"][:, t["col"]].contiguous()
+            t["bm"].zero_()
+            ops.bitmap_mark(ids, -1, t["card"], t["bm"])
+            if self.global_step > 1:
+                ops.rowopt_catchup_bm(t["bm"], 1, t["words"], 1, 0, t["state"], t["p"], t["m"], t["v"], t["ema"], self.global_step - 1,
+                                      self.hist)
         if self.shard:
             self._ensure_staging(B_local * min(spec.top_k, dbatch["seq"].shape[1]))
         hook = (lambda t: self._allreduce(t, "C4_se_squeeze")) if self.world > 1 else None
@@ -480,6 +524,8 @@ class FusedTrainer:
             ops.rows_claim(tok, spec.pad_id, self.owner)
             for n in BIG_TABLES:
                 ops.rows_sqnorm(tok, spec.pad_id, self.owner, self.tables[n]["g"], self.acc)
+        for n, t in self.cat_tables.items():      # the rows a batch reads are the rows that received a gradient: same bitmap
+            ops.rows_sqnorm_bm(t["bm"], 1, t["words"], 1, 0, t["g"], self.acc)
         ops.sqnorm_(self.flat_g[:self.n_active], self.acc)
         ops.clip_coef(self.acc, self.clip, self.coef, self.total_norm)
         # ---- AdamW (+EMA) ----
@@ -496,6 +542,9 @@ class FusedTrainer:
             else:
                 ops.adamw_ema_(t["p"], t["g"], t["m"], t["v"], t["ema"], lr, self.wd, self.global_step, self.coef, d)
                 ops.rows_zero(tok, spec.pad_id, self.owner, t["g"])
+        for n, t in self.cat_tables.items():
+            ops.rowopt_update_bm(t["bm"], 1, t["words"], 1, 0, t["state"], t["p"], t["g"], t["m"], t["v"], t["ema"], self.global_step,
+                                 self.coef, self.hist)
         if self.ema_on:
             self.n_ema += 1
         self.last_logits = logits
@@ -528,8 +577,7 @@ class FusedTrainer:
         """Bring every row of the big tables (p, m, v, ema) to the current step.  Needed before anything other than
         FusedTrainer.step reads them (evaluation, state_dict, EMA swap-in); a dense pass, once per epoch in practice."""
         if self.lazy and self.global_step > 0 and self._flushed_at != self.global_step:
-            for n in BIG_TABLES:
-                t = self.tables[n]
+            for t in list(self.tables.values()) + list(self.cat_tables.values()):
                 ops.rowopt_flush(t["state"], t["p"], t["m"], t["v"], t["ema"], self.global_step, self.hist)
         self._flushed_at = self.global_step
 
@@ -555,4 +603,6 @@ class FusedTrainer:
             out[n] = self.flat_ema[o:o + p.numel()].view(p.shape)
         for n in BIG_TABLES:
             out[n] = self.tables[n]["ema"]
+        for n, t in self.cat_tables.items():
+            out[n] = t["ema"][:, :t["dc"]]
         return out

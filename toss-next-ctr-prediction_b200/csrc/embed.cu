@@ -140,7 +140,8 @@ constexpr int CAT_WARPS = 8;
 template <typename IT>
 __global__ void __launch_bounds__(CAT_WARPS * 32)
 cat_fwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ tables, const float* const* __restrict__ projs,
-               const int32_t* __restrict__ dims, const int32_t* __restrict__ cards, float* __restrict__ out, int64_t ld_b,
+               const int32_t* __restrict__ dims, const int32_t* __restrict__ cards, const int32_t* __restrict__ lds,
+               float* __restrict__ out, int64_t ld_b,
                float* __restrict__ mean_out, int64_t ld_mean, int q_idx, float* __restrict__ q_out,
                int64_t B, int Fc, b200ctr_dropout_t drop) {
   __shared__ float Wt[CAT_MAXDC][CAT_D + 1];               // W_c transposed: Wt[j][n]
@@ -155,6 +156,7 @@ cat_fwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
     const float* W = projs[c];
     const float* T = tables[c];
     const int card = cards[c];
+    const int64_t ldt = lds ? lds[c] : dc;                  // row stride of table c (row-lazy tables are stored 64 wide)
     __syncthreads();
     for (int i = threadIdx.x; i < CAT_D * dc; i += blockDim.x) {
       int n = i / dc, j = i % dc;
@@ -166,7 +168,7 @@ cat_fwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
       if (b < B) {
         int64_t id = (int64_t)x_cat[b * Fc + c];
         id = id < 0 ? 0 : (id >= card ? card - 1 : id);     // memory-safe clamp (reference would raise)
-        for (int j = lane; j < dc; j += 32) rows[warp][s][j] = T[id * dc + j];
+        for (int j = lane; j < dc; j += 32) rows[warp][s][j] = T[id * ldt + j];
       }
     }
     __syncthreads();
@@ -204,7 +206,8 @@ constexpr int CATB_TS = 32;
 template <typename IT>
 __global__ void __launch_bounds__(256)
 cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ tables, const float* const* __restrict__ projs,
-               const int32_t* __restrict__ dims, const int32_t* __restrict__ cards, const float* __restrict__ dout, int64_t ld_b,
+               const int32_t* __restrict__ dims, const int32_t* __restrict__ cards, const int32_t* __restrict__ lds,
+               const float* __restrict__ dout, int64_t ld_b,
                const float* __restrict__ dmean, int64_t ld_dmean, int q_idx, const float* __restrict__ dq,
                float* __restrict__ rowg, int32_t* __restrict__ keys, float* __restrict__ dwpart, int sumdc, int64_t B, int Fc,
                b200ctr_dropout_t drop) {
@@ -219,6 +222,7 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   const float* T = tables[c];
   int off_c = 0, row_base = 0;                            // column offset of dW_c in a partial; first global row id of table c
   for (int cc = 0; cc < c; ++cc) { off_c += dims[cc]; row_base += cards[cc]; }
+  const int64_t ldt = lds ? lds[c] : dc;
   const int tid = threadIdx.x;
   for (int i = tid; i < CAT_D * dc; i += blockDim.x) Ws[i / dc][i % dc] = W[i];
   // this thread's dW elements: e = tid + k*256 < 64*dc  (<= 16 of them)
@@ -250,7 +254,7 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
     __syncthreads();
     for (int i = tid; i < CATB_TS * dc; i += blockDim.x) {
       int s = i / dc, j = i % dc;
-      rs[s][j] = (b0 + s < B) ? T[ids[s] * dc + j] : 0.f;
+      rs[s][j] = (b0 + s < B) ? T[ids[s] * ldt + j] : 0.f;
     }
     __syncthreads();
     // dW[n][j] += sum_s g[s][n] * row[s][j]
@@ -290,16 +294,21 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
 
 // dE_c[r, 0:d_c] += temp[row_base_c + r, 0:d_c]  (temp: the 64-wide reduced rows of all tables, one global row id per table row)
 __global__ void __launch_bounds__(256)
-cat_unpad_kernel(const float* __restrict__ temp, const int32_t* __restrict__ dims, const int32_t* __restrict__ cards,
-                 float* const* __restrict__ dtables, int Fc) {
+cat_unpad_kernel(float* __restrict__ temp, const int32_t* __restrict__ dims, const int32_t* __restrict__ cards,
+                 const int32_t* __restrict__ keep_rows, int rezero, float* const* __restrict__ dtables, int Fc) {
   const int c = blockIdx.y, dc = dims[c], card = cards[c];
+  if (keep_rows && keep_rows[c]) return;                  // row-lazy table: its reduced 64-wide rows in `temp` ARE its gradient rows
   int row_base = 0;
   for (int cc = 0; cc < c; ++cc) row_base += cards[cc];
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (int64_t)card * dc) return;
   const int r = (int)(e / dc), j = (int)(e - (int64_t)r * dc);
-  const float v = temp[(int64_t)(row_base + r) * CAT_D + j];
-  if (v != 0.f) dtables[c][e] += v;                       // single writer per element
+  float* t = temp + (int64_t)(row_base + r) * CAT_D + j;
+  const float v = *t;
+  if (v != 0.f) {
+    dtables[c][e] += v;                                   // single writer per element
+    if (rezero) *t = 0.f;                                 // caller-owned buffer: back to all-zero for the next step
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -412,7 +421,7 @@ extern "C" int b200ctr_numbin_unfold(const float* dP, const float* dQ, const flo
 }
 
 extern "C" int b200ctr_cat_fwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
-                               const int32_t* dims, const int32_t* cards, float* out, int64_t ld_b, float* mean_out,
+                               const int32_t* dims, const int32_t* cards, const int32_t* lds, float* out, int64_t ld_b, float* mean_out,
                                int64_t ld_mean, int q_idx, float* q_out, int64_t B, int Fc, int D, b200ctr_dropout_t drop,
                                void* stream) {
   B200_REQUIRE(x_cat && tables && projs && dims && cards && out, B200CTR_E_INVALID_ARG, "cat_fwd: null pointer");
@@ -421,10 +430,10 @@ extern "C" int b200ctr_cat_fwd(const void* x_cat, int idx_is_64, const float* co
   int grid = (int)ceil_div(B, (int64_t)CAT_WARPS * CAT_SPW);
   cudaStream_t st = as_stream(stream);
   if (idx_is_64)
-    cat_fwd_kernel<int64_t><<<grid, CAT_WARPS * 32, 0, st>>>((const int64_t*)x_cat, tables, projs, dims, cards, out, ld_b,
+    cat_fwd_kernel<int64_t><<<grid, CAT_WARPS * 32, 0, st>>>((const int64_t*)x_cat, tables, projs, dims, cards, lds, out, ld_b,
                                                               mean_out, ld_mean, q_idx, q_out, B, Fc, drop);
   else
-    cat_fwd_kernel<int32_t><<<grid, CAT_WARPS * 32, 0, st>>>((const int32_t*)x_cat, tables, projs, dims, cards, out, ld_b,
+    cat_fwd_kernel<int32_t><<<grid, CAT_WARPS * 32, 0, st>>>((const int32_t*)x_cat, tables, projs, dims, cards, lds, out, ld_b,
                                                               mean_out, ld_mean, q_idx, q_out, B, Fc, drop);
   B200_LAUNCH_CHECK("cat_fwd_kernel");
   return B200CTR_OK;
@@ -442,10 +451,11 @@ extern "C" int64_t b200ctr_cat_bwd_workspace_bytes(int64_t B, int Fc, int sum_di
 }
 
 extern "C" int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
-                               const int32_t* dims, const int32_t* cards, const float* dout, int64_t ld_b,
+                               const int32_t* dims, const int32_t* cards, const int32_t* lds, const float* dout, int64_t ld_b,
                                const float* dmean, int64_t ld_dmean, int q_idx, const float* dq, float* const* dtables,
                                float* const* dprojs, int64_t B, int Fc, int D, int sum_dims, int64_t sum_cards, int max_card,
-                               b200ctr_dropout_t drop, void* workspace, int64_t workspace_bytes, void* stream) {
+                               b200ctr_dropout_t drop, float* rows_acc, const int32_t* keep_rows, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
   B200_REQUIRE(x_cat && tables && projs && dims && cards && dtables && dprojs && workspace, B200CTR_E_INVALID_ARG, "cat_bwd: null pointer");
   B200_REQUIRE(D == CAT_D, B200CTR_E_UNSUPPORTED_SHAPE, "cat_bwd: emb_dim=%d unsupported (kernel is specialised for 64)", D);
   B200_REQUIRE(sum_dims > 0 && sum_cards > 0 && max_card > 0 && workspace_bytes >= b200ctr_cat_bwd_workspace_bytes(B, Fc, sum_dims, sum_cards),
@@ -461,20 +471,24 @@ extern "C" int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* co
   float* dwpart = (float*)w; w += cat_al((size_t)64 * CAT_D * sum_dims * 4);
   const int64_t sc_bytes = b200ctr_scatter_rows_workspace_bytes(n, sum_cards);
   cudaError_t e = cudaMemsetAsync(rowg, 0, (size_t)n * CAT_D * 4, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(temp, 0, (size_t)sum_cards * CAT_D * 4, st);
+  // rows_acc: a caller-owned, ALL-ZERO (sum_cards, 64) buffer that outlives the call (the trainer's: the rows of its row-lazy
+  // tables are their gradient rows, the other tables' rows are zeroed again below); NULL: scratch from the workspace
+  const int rezero = rows_acc != nullptr;
+  if (rows_acc) temp = rows_acc;
+  else if (e == cudaSuccess) e = cudaMemsetAsync(temp, 0, (size_t)sum_cards * CAT_D * 4, st);
   if (e != cudaSuccess) return cuda_fail(e, "cat_bwd memset");
   if (idx_is_64)
-    cat_bwd_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)x_cat, tables, projs, dims, cards, dout, ld_b, dmean,
+    cat_bwd_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)x_cat, tables, projs, dims, cards, lds, dout, ld_b, dmean,
                                                    ld_dmean, q_idx, dq, rowg, keys, dwpart, sum_dims, B, Fc, drop);
   else
-    cat_bwd_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)x_cat, tables, projs, dims, cards, dout, ld_b, dmean,
+    cat_bwd_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)x_cat, tables, projs, dims, cards, lds, dout, ld_b, dmean,
                                                    ld_dmean, q_idx, dq, rowg, keys, dwpart, sum_dims, B, Fc, drop);
   B200_LAUNCH_CHECK("cat_bwd_kernel");
   // every distinct table row is reduced once, its slots in (sample, column) order
   int rc = b200ctr_scatter_rows(keys, 1, n, -1, sum_cards, 1, nullptr, nullptr, rowg, nullptr, nullptr, 0, 1, 0, nullptr, temp, w, sc_bytes, stream);
   if (rc) return rc;
   dim3 ugrid((unsigned)ceil_div((int64_t)max_card * CAT_MAXDC, (int64_t)256), (unsigned)Fc);
-  cat_unpad_kernel<<<ugrid, 256, 0, st>>>(temp, dims, cards, dtables, Fc);
+  cat_unpad_kernel<<<ugrid, 256, 0, st>>>(temp, dims, cards, keep_rows, rezero, dtables, Fc);
   B200_LAUNCH_CHECK("cat_unpad_kernel");
   dim3 wgrid((unsigned)ceil_div((int64_t)CAT_D * CAT_MAXDC, (int64_t)256), (unsigned)Fc);
   cat_dw_reduce_kernel<<<wgrid, 256, 0, st>>>(dwpart, (int)grid.x, dims, sum_dims, dprojs);
