@@ -165,13 +165,17 @@ int b200ctr_cat_fwd(const void* x_cat, int idx_is_64, const float* const* tables
  * dprojs are accumulated into (single writer per element).  The same path serves HBM-sized hashed tables (v4 cfgs):
  * rows_acc (optional) = a caller-owned ALL-ZERO (sum_cards, 64) buffer in global-row order that outlives the call, and
  * keep_rows[c] != 0 leaves table c's reduced 64-wide rows there (they are the gradient rows the row-lazy optimizer
- * consumes and re-zeroes) instead of adding them into dtables[c]; the other tables' rows are zeroed again.              */
+ * consumes and re-zeroes) instead of adding them into dtables[c]; the other tables' rows are zeroed again.
+ * defer_slot[c] >= 0 (data parallel, replicated row-lazy tables): column c's slots are NOT reduced here; sample b's 64-wide
+ * contribution row and its global row id are written to defer_rows[b, defer_slot[c]] / defer_keys[b, defer_slot[c]]
+ * (n_defer slots per sample) for the caller to all-gather and reduce with b200ctr_scatter_rows.                          */
 int64_t b200ctr_cat_bwd_workspace_bytes(int64_t B, int Fc, int sum_dims, int64_t sum_cards);
 int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* const* tables, const float* const* projs,
                     const int32_t* dims, const int32_t* cards, const int32_t* lds, const float* dout, int64_t ld_b,
                     const float* dmean, int64_t ld_dmean, int q_idx, const float* dq, float* const* dtables,
                     float* const* dprojs, int64_t B, int Fc, int D, int sum_dims, int64_t sum_cards, int max_card,
-                    b200ctr_dropout_t drop, float* rows_acc, const int32_t* keep_rows, void* workspace,
+                    b200ctr_dropout_t drop, float* rows_acc, const int32_t* keep_rows, const int32_t* defer_slot,
+                    int n_defer, float* defer_rows, int32_t* defer_keys, void* workspace,
                     int64_t workspace_bytes, void* stream);
 
 /* ---- query mix  (wrapper.py:128-136): q = a*s1 + b*s2 ; bwd: ds2pre = b*dq*(s2>0) --------------------- */

@@ -21,7 +21,7 @@ def _build(cfg, z, dev):
     return m.to(dev).train()
 
 
-def _worker(rank, world, port, out_path, shard):
+def _worker(rank, world, port, out_path, shard, lazy_cat=False):
     import torch.distributed as dist
     import b200ctr
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -30,10 +30,12 @@ def _worker(rank, world, port, out_path, shard):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         z, cfg = load_case("qnn_concat")
+        if lazy_cat:
+            cfg = dict(cfg, b200ctr={"lazy_table_min_rows": 100})
         m = _build(cfg, z, dev)
         tr = b200ctr.FusedTrainer(m, cfg, steps_per_epoch=cfg["golden"]["steps_per_epoch"], process_group=dist.group.WORLD,
                                   shard_tables=shard)
-        assert tr.shard == shard
+        assert tr.shard == shard and (len(tr.cat_tables) >= 2) == lazy_cat
         if shard:       # the full replicas are gone: each rank holds every other row
             assert m.dare.emb_att.weight.numel() == 0 and tr.tables["dare.emb_att.weight"]["p"].shape[0] == (g_vocab(cfg) + world - 1) // world
         for s in range(3):
@@ -53,14 +55,15 @@ def g_vocab(cfg):
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("shard", [False, True], ids=["replicated_tables", "row_sharded_tables_p2p"])
-def test_two_rank_data_parallel_matches_single_gpu_global_batch(tmp_path, shard):
+@pytest.mark.parametrize("shard,lazy_cat", [(False, False), (True, False), (True, True)],
+                         ids=["replicated_tables", "row_sharded_tables_p2p", "row_sharded_plus_row_lazy_categorical_tables"])
+def test_two_rank_data_parallel_matches_single_gpu_global_batch(tmp_path, shard, lazy_cat):
     import torch.multiprocessing as mp
     import b200ctr
     z, cfg = load_case("qnn_concat")
     out = str(tmp_path / "dp.pt")
-    port = 29600 + (os.getpid() % 1000) + (500 if shard else 0)
-    mp.spawn(_worker, args=(2, port, out, shard), nprocs=2, join=True)
+    port = 29600 + (os.getpid() % 1000) + (500 if shard else 0) + (250 if lazy_cat else 0)
+    mp.spawn(_worker, args=(2, port, out, shard, lazy_cat), nprocs=2, join=True)
     dp = torch.load(out)
     dev = torch.device("cuda:0")
     m = _build(cfg, z, dev)

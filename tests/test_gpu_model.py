@@ -434,7 +434,7 @@ def test_row_lazy_categorical_tables_match_reference(kind):
     cfg["b200ctr"] = {"lazy_table_min_rows": 100}
     m = _build(cfg, z, dev).train()
     tr = b200ctr.FusedTrainer(m, cfg, steps_per_epoch=cfg["golden"]["steps_per_epoch"])
-    assert len(tr.cat_tables) >= 2 and not any(n in tr.offsets for n in tr.cat_tables)
+    assert len(tr.cat_tables) >= (2 if kind == "qnn_concat" else 1) and not any(n in tr.offsets for n in tr.cat_tables)
     for s in range(3):
         batch, y = batch_of(z, s)
         loss = tr.step(batch, y)

@@ -494,6 +494,10 @@ def model_fwd(P: Dict[str, Tensor], spec: ModelSpec, batch: Dict[str, Tensor], d
         s2 = ops.gemm(ctx, P["ctx_mlp.0.weight"], trans_b=True, bias=P["ctx_mlp.0.bias"], act=ops.ACT_RELU)
         q = s2 if spec.query_mode == "S2" else ops.axpby(s1, s2, 0.5, 0.5)
     sv.update(s2=s2, ct=ct, cat_rows_acc=cache.get("cat_rows_acc"), cat_keep_rows=cache.get("cat_keep_rows"))
+    if cache.get("cat_defer_slot") is not None:        # data parallel: the row-lazy tables' slots are reduced by the trainer
+        nd = cache["cat_defer_n"]
+        sv["cat_defer"] = dict(slot=cache["cat_defer_slot"], n=nd, rows=torch.empty((B, nd, D), device=dev, dtype=torch.float32),
+                               keys=torch.empty((B, nd), device=dev, dtype=torch.int32))
     aux, dsv = dare_fwd(P, spec, seq, q, u_out, ld_u, dc)
     sv["dare"] = dsv
     if spec.use_qnn:
@@ -579,4 +583,4 @@ def model_bwd(P: Dict[str, Tensor], spec: ModelSpec, sv: dict, dlogits: Tensor, 
     ops.cat_bwd(sv["X_cat"], sv["ct"], dcat, ld_d, dmean_cat, ldc, spec.q_idx if dq_cat is not None else -1, dq_cat,
                 [G(f"cat_embs.{c}.weight") for c in spec.cat_cols], [G(f"cat_proj.{c}.weight") for c in spec.cat_cols],
                 D, dc(spec.p_emb, SITE_EMB) if spec.use_qnn else NO_DROP, rows_acc=sv.get("cat_rows_acc"),
-                keep_rows=sv.get("cat_keep_rows"))
+                keep_rows=sv.get("cat_keep_rows"), defer=sv.get("cat_defer"))

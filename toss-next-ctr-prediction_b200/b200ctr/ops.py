@@ -343,7 +343,7 @@ def cat_fwd(x_cat, ct: CatTables, out, ld_b, mean_out, ld_mean, q_idx, q_out, D,
 
 
 def cat_bwd(x_cat, ct: CatTables, dout, ld_b, dmean, ld_dmean, q_idx, dq, dtables, dprojs, D, dropout=NO_DROP, rows_acc=None,
-            keep_rows=None):
+            keep_rows=None, defer=None):
     """dtables/dprojs: lists of ZEROED gradient tensors (accumulated into).  rows_acc / keep_rows: the trainer's persistent
     all-zero (sum_cards, 64) row accumulator and the int32 per-table flags of its row-lazy tables (their reduced rows stay in
     rows_acc; their dtables entry is ignored and may be any tensor of the right row count)."""
@@ -357,7 +357,9 @@ def cat_bwd(x_cat, ct: CatTables, dout, ld_b, dmean, ld_dmean, q_idx, dq, dtable
     ws = torch.empty((ws_bytes,), device=x_cat.device, dtype=torch.uint8)
     _run("cat_bwd", lib.b200ctr_cat_bwd, _p(x_cat), _idx64(x_cat), _p(ct.t_ptrs), _p(ct.p_ptrs), _p(ct.dims), _p(ct.cards),
                               _p(ct.lds), _p(dout), ld_b, _p(dmean), ld_dmean, q_idx, _p(dq), _p(dt_ptrs), _p(dp_ptrs),
-                              B, Fc, D, sum_dims, sum_cards, max_card, dropout, _p(rows_acc), _p(keep_rows), _p(ws), ws_bytes, _stream())
+                              B, Fc, D, sum_dims, sum_cards, max_card, dropout, _p(rows_acc), _p(keep_rows),
+                              _p(defer["slot"]) if defer else None, defer["n"] if defer else 0, _p(defer["rows"]) if defer else None,
+                              _p(defer["keys"]) if defer else None, _p(ws), ws_bytes, _stream())
     _count(7)
 
 

@@ -113,11 +113,12 @@ class FusedTrainer:
             frozen |= {n for n in params if n.startswith("dare.aux_head.")}
         # Hashed-categorical tables with an HBM-sized bucket count (cfgs/v4_k120_s1.yaml: 2,000,503 x 32 and 4,000,513 x 57;
         # dare_base: 2,000,000 x 64 and 1,000,000 x 64) are kept OUT of the flat dense buffer and updated by the row-lazy
-        # optimizer like the sequence tables (a dense AdamW + EMA pass over them would cost 36 B per parameter per step).  One
-        # process only: under data parallelism they stay dense and replicated.
+        # optimizer like the sequence tables (a dense AdamW + EMA pass over them would cost 36 B per parameter per step, and a
+        # dense all-reduce under data parallelism).  Under DP they stay REPLICATED (1.2 GB at the v4 sizes) and exchange sparsely:
+        # every rank all-gathers its B slots per table (row id + 64-wide contribution row) and reduces all ranks' slots with
+        # the same sort + segmented reduction, so every replica applies bit-identical row updates.
         thr = int((cfg.get("b200ctr") or {}).get("lazy_table_min_rows", 500_000))
-        self.cat_lazy = [c for c in spec.cat_cols
-                         if lazy_tables and self.world == 1 and params[f"cat_embs.{c}.weight"].shape[0] >= thr]
+        self.cat_lazy = [c for c in spec.cat_cols if lazy_tables and params[f"cat_embs.{c}.weight"].shape[0] >= thr]
         lazy_names = {f"cat_embs.{c}.weight" for c in self.cat_lazy}
         small = [n for n in params if n not in BIG_TABLES and n not in lazy_names]
         active = [n for n in small if n not in frozen] + [n for n in small if n in frozen]
@@ -183,6 +184,7 @@ class FusedTrainer:
             # gradient rows of the row-lazy tables here (their `g`), the optimizer consumes and re-zeroes them
             self.cat_rows_acc = torch.zeros((sum(cards), 64), device=dev, dtype=torch.float32)
             keep = torch.zeros(len(cards), dtype=torch.int32)
+            dslot = torch.full((len(cards),), -1, dtype=torch.int32)
             base = 0
             for ci, c in enumerate(spec.cat_cols):
                 if c in self.cat_lazy:
@@ -195,13 +197,15 @@ class FusedTrainer:
                     self.P[n] = p[:, :dcw]
                     t = dict(p=p, m=torch.zeros_like(p), v=torch.zeros_like(p), g=self.cat_rows_acc[base:base + card],
                              ema=p.clone() if self.ema_on else None, state=torch.zeros(card, device=dev, dtype=torch.int32),
-                             words=ops.bitmap_words(card), col=ci, dc=dcw, card=card)
+                             words=ops.bitmap_words(card), col=ci, dc=dcw, card=card, base=base)
                     t["bm"] = torch.zeros(t["words"], device=dev, dtype=torch.int32)
                     self.cat_tables[n] = t
                     self.Gv[n] = t["g"]
                     keep[ci] = 1
+                    dslot[ci] = len(self.cat_tables) - 1
                 base += cards[ci]
             self.cat_keep_rows = keep.to(dev)
+            self.cat_defer_slot = dslot.to(dev) if self.world > 1 else None
         if self.lazy:
             # initial capacity only: RowHistory grows geometrically when the run outlives the estimate
             cap = min(max(self.epochs * self.steps_per_epoch + 64, 4096), 1 << 22)
@@ -236,6 +240,8 @@ class FusedTrainer:
         self.cache: dict = {}
         if self.cat_lazy:
             self.cache["cat_rows_acc"], self.cache["cat_keep_rows"] = self.cat_rows_acc, self.cat_keep_rows
+            if self.world > 1:
+                self.cache["cat_defer_slot"], self.cache["cat_defer_n"] = self.cat_defer_slot, len(self.cat_tables)
         defaults = {"update_after_step": 0, "update_interval": 1, "param_filter": [], "offload_to_cpu": False}
         for k, dv in defaults.items():
             v = ema.get(k, dv)
@@ -472,6 +478,21 @@ class FusedTrainer:
         hp.model_bwd(self.P, spec, sv, dz, daux if spec.aux_weight > 0 else None, dc, self._G, colsum_hook=hook,
                      after_head=head_grads_final if overlap else None)
         tok = sv["dare"]["tok"]
+        if self.world > 1 and self.cat_tables:
+            # replicated row-lazy categorical tables: gather every rank's slots, reduce them once -- in (rank, sample, table)
+            # order, the same on every replica -- into the row accumulator, and mark the union of the touched rows
+            df = sv["cat_defer"]
+            rows_all = torch.empty((self.world,) + tuple(df["rows"].shape), device=self.dev, dtype=torch.float32)
+            keys_all = torch.empty((self.world,) + tuple(df["keys"].shape), device=self.dev, dtype=torch.int32)
+            self._allgather(rows_all.view(-1), df["rows"].view(-1), "C1_cat_rows_allgather")
+            self._allgather(keys_all.view(-1), df["keys"].view(-1), "C1_cat_keys_allgather")
+            n_sl = keys_all.numel()
+            ops.scatter_rows(keys_all.view(-1), 1, n_sl, -1, self.cat_rows_acc.shape[0], 1, None, None, rows_all.view(n_sl, spec.D),
+                             None, None, 0, 1, 0, None, self.cat_rows_acc)
+            for k, t in enumerate(self.cat_tables.values()):
+                ids = (keys_all[:, :, k] - t["base"]).contiguous()
+                t["bm"].zero_()
+                ops.bitmap_mark(ids, -1, t["card"], t["bm"])
         if self.world > 1:
             if overlap:
                 self._allreduce(self.flat_g[:self.head_off], "C2_rest")                             # C2, second part

@@ -210,7 +210,8 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
                const float* __restrict__ dout, int64_t ld_b,
                const float* __restrict__ dmean, int64_t ld_dmean, int q_idx, const float* __restrict__ dq,
                float* __restrict__ rowg, int32_t* __restrict__ keys, float* __restrict__ dwpart, int sumdc, int64_t B, int Fc,
-               b200ctr_dropout_t drop) {
+               b200ctr_dropout_t drop, const int32_t* __restrict__ defer_slot, int n_defer, float* __restrict__ defer_rows,
+               int32_t* __restrict__ defer_keys, int32_t sentinel) {
   __shared__ float Ws[CAT_D][CAT_MAXDC + 1];           // natural layout W[n][j]
   __shared__ float gs[CATB_TS][CAT_D + 1];
   __shared__ float rs[CATB_TS][CAT_MAXDC + 1];
@@ -223,6 +224,7 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   int off_c = 0, row_base = 0;                            // column offset of dW_c in a partial; first global row id of table c
   for (int cc = 0; cc < c; ++cc) { off_c += dims[cc]; row_base += cards[cc]; }
   const int64_t ldt = lds ? lds[c] : dc;
+  const int dslot = defer_slot ? defer_slot[c] : -1;
   const int tid = threadIdx.x;
   for (int i = tid; i < CAT_D * dc; i += blockDim.x) Ws[i / dc][i % dc] = W[i];
   // this thread's dW elements: e = tid + k*256 < 64*dc  (<= 16 of them)
@@ -279,9 +281,16 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
       for (int n = 0; n < CAT_D; ++n) a = fmaf(Ws[n][j], gs[s][n], a);
       // this sample's contribution to dE_c[id], as a 64-wide row (columns >= d_c stay zero) of slot (b, c): the slots are
       // sorted by global table row and reduced in slot order by b200ctr_scatter_rows (no float atomics)
-      rowg[((b0 + s) * Fc + c) * (int64_t)CAT_D + j] = a;
+      if (dslot >= 0) defer_rows[((b0 + s) * n_defer + dslot) * (int64_t)CAT_D + j] = a;
+      else rowg[((b0 + s) * Fc + c) * (int64_t)CAT_D + j] = a;
     }
-    if (tid < CATB_TS && b0 + tid < B) keys[(b0 + tid) * Fc + c] = row_base + (int32_t)ids[tid];
+    if (tid < CATB_TS && b0 + tid < B) {
+      // deferred column (data parallel, replicated row-lazy table): the slot leaves this call unreduced -- the trainer gathers
+      // every rank's slots and reduces them once, identically on every replica; the local sort skips it (sentinel key)
+      const int32_t key = row_base + (int32_t)ids[tid];
+      keys[(b0 + tid) * Fc + c] = dslot >= 0 ? sentinel : key;
+      if (dslot >= 0) defer_keys[(b0 + tid) * n_defer + dslot] = key;
+    }
   }
   // this CTA's partial dW_c; the partials are added in CTA order by cat_dw_reduce_kernel
   float* dwp = dwpart + (int64_t)blockIdx.x * CAT_D * sumdc + (int64_t)CAT_D * off_c;
@@ -454,8 +463,10 @@ extern "C" int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* co
                                const int32_t* dims, const int32_t* cards, const int32_t* lds, const float* dout, int64_t ld_b,
                                const float* dmean, int64_t ld_dmean, int q_idx, const float* dq, float* const* dtables,
                                float* const* dprojs, int64_t B, int Fc, int D, int sum_dims, int64_t sum_cards, int max_card,
-                               b200ctr_dropout_t drop, float* rows_acc, const int32_t* keep_rows, void* workspace,
+                               b200ctr_dropout_t drop, float* rows_acc, const int32_t* keep_rows, const int32_t* defer_slot,
+                               int n_defer, float* defer_rows, int32_t* defer_keys, void* workspace,
                                int64_t workspace_bytes, void* stream) {
+  B200_REQUIRE(!defer_slot || (n_defer > 0 && defer_rows && defer_keys), B200CTR_E_INVALID_ARG, "cat_bwd: deferred columns need their output buffers");
   B200_REQUIRE(x_cat && tables && projs && dims && cards && dtables && dprojs && workspace, B200CTR_E_INVALID_ARG, "cat_bwd: null pointer");
   B200_REQUIRE(D == CAT_D, B200CTR_E_UNSUPPORTED_SHAPE, "cat_bwd: emb_dim=%d unsupported (kernel is specialised for 64)", D);
   B200_REQUIRE(sum_dims > 0 && sum_cards > 0 && max_card > 0 && workspace_bytes >= b200ctr_cat_bwd_workspace_bytes(B, Fc, sum_dims, sum_cards),
@@ -473,16 +484,19 @@ extern "C" int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* co
   cudaError_t e = cudaMemsetAsync(rowg, 0, (size_t)n * CAT_D * 4, st);
   // rows_acc: a caller-owned, ALL-ZERO (sum_cards, 64) buffer that outlives the call (the trainer's: the rows of its row-lazy
   // tables are their gradient rows, the other tables' rows are zeroed again below); NULL: scratch from the workspace
+  if (defer_slot && e == cudaSuccess) e = cudaMemsetAsync(defer_rows, 0, (size_t)B * n_defer * CAT_D * 4, st);
   const int rezero = rows_acc != nullptr;
   if (rows_acc) temp = rows_acc;
   else if (e == cudaSuccess) e = cudaMemsetAsync(temp, 0, (size_t)sum_cards * CAT_D * 4, st);
   if (e != cudaSuccess) return cuda_fail(e, "cat_bwd memset");
   if (idx_is_64)
     cat_bwd_kernel<int64_t><<<grid, 256, 0, st>>>((const int64_t*)x_cat, tables, projs, dims, cards, lds, dout, ld_b, dmean,
-                                                   ld_dmean, q_idx, dq, rowg, keys, dwpart, sum_dims, B, Fc, drop);
+                                                   ld_dmean, q_idx, dq, rowg, keys, dwpart, sum_dims, B, Fc, drop, defer_slot, n_defer, defer_rows, defer_keys,
+                                                   (int32_t)sum_cards);
   else
     cat_bwd_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)x_cat, tables, projs, dims, cards, lds, dout, ld_b, dmean,
-                                                   ld_dmean, q_idx, dq, rowg, keys, dwpart, sum_dims, B, Fc, drop);
+                                                   ld_dmean, q_idx, dq, rowg, keys, dwpart, sum_dims, B, Fc, drop, defer_slot, n_defer, defer_rows, defer_keys,
+                                                   (int32_t)sum_cards);
   B200_LAUNCH_CHECK("cat_bwd_kernel");
   // every distinct table row is reduced once, its slots in (sample, column) order
   int rc = b200ctr_scatter_rows(keys, 1, n, -1, sum_cards, 1, nullptr, nullptr, rowg, nullptr, nullptr, 0, 1, 0, nullptr, temp, w, sc_bytes, stream);
