@@ -59,8 +59,20 @@ def v3_k148_s1() -> dict:
     c["sequence"].update(top_k=148, query_mode="S1")
     c["sequence"]["tfm"].update(n_layers=4, ffn_dropout=0.15)
     c["model"]["dare_dropout"] = 0.25
+    c["model"]["cat_embedding_dims"]["inventory_id"] = 32          # cfgs/v3_k148_s1.yaml:206
     c["train"]["batch_size"] = 4096
     c["ema"] = {"enabled": False}
+    return c
+
+
+def v3_k148_s1_big() -> dict:
+    """BASELINE configs[3]: cfgs/v3_k148_s1.yaml with the enlarged hash_buckets of cfgs/v4_k120_s1.yaml:142,156,204,218
+    (inventory_id 2,000,003 x 32, l_feat_14 4,000,013 x 57; + the 500-row margin): 1.17 GB of hashed-categorical tables, kept
+    under the row-lazy optimizer (FusedTrainer: tables with >= 500,000 rows)."""
+    c = v3_k148_s1()
+    c["exp_name"] = "v3_k148_s1_big"
+    c["data"]["hash_buckets"].update(inventory_id=2_000_003, l_feat_14=4_000_013)
+    c["model"]["cat_embedding_dims"].update(inventory_id=32, l_feat_14=57)
     return c
 
 
