@@ -351,7 +351,10 @@ def cat_bwd(x_cat, ct: CatTables, dout, ld_b, dmean, ld_dmean, q_idx, dq, dtable
     B, Fc = x_cat.shape
     dt_ptrs, dp_ptrs = _ptr_table(dtables), _ptr_table(dprojs)
     sum_dims = int(sum(t.shape[1] for t in ct.tables))
-    max_card = int(max(t.shape[0] for t in ct.tables))
+    # rows of the widest table that is UNPADDED into its dense gradient (the row-lazy tables keep their rows in rows_acc): the
+    # unpad grid is sized by it, so HBM-sized row-lazy tables do not cost millions of idle blocks
+    kept = getattr(keep_rows, "_host", None) if keep_rows is not None else None
+    max_card = int(max([t.shape[0] for i, t in enumerate(ct.tables) if not (kept and kept[i])] or [1]))
     sum_cards = int(sum(t.shape[0] for t in ct.tables))
     ws_bytes = int(lib.b200ctr_cat_bwd_workspace_bytes(B, Fc, sum_dims, sum_cards))
     ws = torch.empty((ws_bytes,), device=x_cat.device, dtype=torch.uint8)

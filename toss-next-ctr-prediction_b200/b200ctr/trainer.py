@@ -117,7 +117,7 @@ class FusedTrainer:
         # dense all-reduce under data parallelism).  Under DP they stay REPLICATED (1.2 GB at the v4 sizes) and exchange sparsely:
         # every rank all-gathers its B slots per table (row id + 64-wide contribution row) and reduces all ranks' slots with
         # the same sort + segmented reduction, so every replica applies bit-identical row updates.
-        thr = int((cfg.get("b200ctr") or {}).get("lazy_table_min_rows", 500_000))
+        thr = int(_os.environ.get("B200CTR_LAZY_THR", (cfg.get("b200ctr") or {}).get("lazy_table_min_rows", 500_000)))
         self.cat_lazy = [c for c in spec.cat_cols if lazy_tables and params[f"cat_embs.{c}.weight"].shape[0] >= thr]
         lazy_names = {f"cat_embs.{c}.weight" for c in self.cat_lazy}
         small = [n for n in params if n not in BIG_TABLES and n not in lazy_names]
@@ -205,6 +205,7 @@ class FusedTrainer:
                     dslot[ci] = len(self.cat_tables) - 1
                 base += cards[ci]
             self.cat_keep_rows = keep.to(dev)
+            self.cat_keep_rows._host = [int(x) for x in keep]          # host copy for the launch geometry (ops.cat_bwd)
             self.cat_defer_slot = dslot.to(dev) if self.world > 1 else None
         if self.lazy:
             # initial capacity only: RowHistory grows geometrically when the run outlives the estimate
