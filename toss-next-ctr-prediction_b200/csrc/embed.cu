@@ -301,23 +301,39 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   }
 }
 
-// dE_c[r, 0:d_c] += temp[row_base_c + r, 0:d_c]  (temp: the 64-wide reduced rows of all tables, one global row id per table row)
+// dE_c[r, 0:d_c] += temp[row_base_c + r, 0:d_c]  (temp: the 64-wide reduced rows of all tables, one global row id per table row).
+// 1-D over the 16-byte quads of temp, so the cost follows the total row count (a (max_card, Fc) grid launched 35 M mostly idle
+// blocks with one 4 M-row table); the table of a global row is found by a search over the <= 64 row bases in shared memory.
+constexpr int CAT_MAXF = 64;
 __global__ void __launch_bounds__(256)
 cat_unpad_kernel(float* __restrict__ temp, const int32_t* __restrict__ dims, const int32_t* __restrict__ cards,
-                 const int32_t* __restrict__ keep_rows, int rezero, float* const* __restrict__ dtables, int Fc) {
-  const int c = blockIdx.y, dc = dims[c], card = cards[c];
-  if (keep_rows && keep_rows[c]) return;                  // row-lazy table: its reduced 64-wide rows in `temp` ARE its gradient rows
-  int row_base = 0;
-  for (int cc = 0; cc < c; ++cc) row_base += cards[cc];
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (int64_t)card * dc) return;
-  const int r = (int)(e / dc), j = (int)(e - (int64_t)r * dc);
-  float* t = temp + (int64_t)(row_base + r) * CAT_D + j;
-  const float v = *t;
-  if (v != 0.f) {
-    dtables[c][e] += v;                                   // single writer per element
-    if (rezero) *t = 0.f;                                 // caller-owned buffer: back to all-zero for the next step
+                 const int32_t* __restrict__ keep_rows, int rezero, float* const* __restrict__ dtables, int Fc, int64_t sum_cards) {
+  __shared__ int64_t base[CAT_MAXF + 1];
+  if (threadIdx.x == 0) {
+    int64_t b = 0;
+    for (int c = 0; c < Fc; ++c) { base[c] = b; b += cards[c]; }
+    base[Fc] = b;
   }
+  __syncthreads();
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // quad index: global row q / 16, columns 4 (q % 16) ..
+  if (q >= sum_cards * (CAT_D / 4)) return;
+  const int64_t g = q >> 4;
+  const int j0 = (int)(q & 15) * 4;
+  int lo = 0, hi = Fc - 1;                                                     // largest c with base[c] <= g
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (base[mid] <= g) lo = mid; else hi = mid - 1; }
+  const int c = lo;
+  if (keep_rows && keep_rows[c]) return;               // row-lazy table: its reduced 64-wide rows in `temp` ARE its gradient rows
+  const int dc = dims[c];
+  if (j0 >= dc) return;
+  float4* t4 = reinterpret_cast<float4*>(temp) + q;
+  const float4 v = *t4;
+  if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) return;
+  float* dst = dtables[c] + (g - base[c]) * dc + j0;                           // single writer per element
+  const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (j0 + k < dc && vv[k] != 0.f) dst[k] += vv[k];
+  if (rezero) *t4 = make_float4(0.f, 0.f, 0.f, 0.f);   // caller-owned buffer: back to all-zero for the next step
 }
 
 __global__ void __launch_bounds__(256)
@@ -501,8 +517,10 @@ extern "C" int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* co
   // every distinct table row is reduced once, its slots in (sample, column) order
   int rc = b200ctr_scatter_rows(keys, 1, n, -1, sum_cards, 1, nullptr, nullptr, rowg, nullptr, nullptr, 0, 1, 0, nullptr, temp, w, sc_bytes, stream);
   if (rc) return rc;
-  dim3 ugrid((unsigned)ceil_div((int64_t)max_card * CAT_MAXDC, (int64_t)256), (unsigned)Fc);
-  cat_unpad_kernel<<<ugrid, 256, 0, st>>>(temp, dims, cards, keep_rows, rezero, dtables, Fc);
+  B200_REQUIRE(Fc <= CAT_MAXF, B200CTR_E_UNSUPPORTED_SHAPE, "cat_bwd: more than %d categorical columns", CAT_MAXF);
+  (void)max_card;
+  cat_unpad_kernel<<<(unsigned)ceil_div(sum_cards * (CAT_D / 4), (int64_t)256), 256, 0, st>>>(temp, dims, cards, keep_rows, rezero,
+                                                                                              dtables, Fc, sum_cards);
   B200_LAUNCH_CHECK("cat_unpad_kernel");
   dim3 wgrid((unsigned)ceil_div((int64_t)CAT_D * CAT_MAXDC, (int64_t)256), (unsigned)Fc);
   cat_dw_reduce_kernel<<<wgrid, 256, 0, st>>>(dwpart, (int)grid.x, dims, sum_dims, dprojs);
