@@ -315,25 +315,31 @@ cat_unpad_kernel(float* __restrict__ temp, const int32_t* __restrict__ dims, con
     base[Fc] = b;
   }
   __syncthreads();
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // quad index: global row q / 16, columns 4 (q % 16) ..
-  if (q >= sum_cards * (CAT_D / 4)) return;
-  const int64_t g = q >> 4;
-  const int j0 = (int)(q & 15) * 4;
-  int lo = 0, hi = Fc - 1;                                                     // largest c with base[c] <= g
-  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (base[mid] <= g) lo = mid; else hi = mid - 1; }
-  const int c = lo;
-  if (keep_rows && keep_rows[c]) return;               // row-lazy table: its reduced 64-wide rows in `temp` ARE its gradient rows
-  const int dc = dims[c];
-  if (j0 >= dc) return;
-  float4* t4 = reinterpret_cast<float4*>(temp) + q;
-  const float4 v = *t4;
-  if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) return;
-  float* dst = dtables[c] + (g - base[c]) * dc + j0;                           // single writer per element
-  const float vv[4] = {v.x, v.y, v.z, v.w};
+  // grid-stride over the tables' quads; a row-lazy table's whole range is stepped over in one go
+  const int64_t nq = sum_cards * (CAT_D / 4), stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {   // quad: global row q / 16, columns 4 (q % 16) ..
+    const int64_t g = q >> 4;
+    const int j0 = (int)(q & 15) * 4;
+    int lo = 0, hi = Fc - 1;                                                     // largest c with base[c] <= g
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (base[mid] <= g) lo = mid; else hi = mid - 1; }
+    const int c = lo;
+    if (keep_rows && keep_rows[c]) {                     // row-lazy table: its reduced rows in `temp` ARE its gradient rows
+      const int64_t q_end = base[c + 1] * (CAT_D / 4);   // first quad after this table: jump there, keeping this thread's phase
+      q += ((q_end - q + stride - 1) / stride - 1) * stride;
+      continue;
+    }
+    const int dc = dims[c];
+    if (j0 >= dc) continue;
+    float4* t4 = reinterpret_cast<float4*>(temp) + q;
+    const float4 v = *t4;
+    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+    float* dst = dtables[c] + (g - base[c]) * dc + j0;                           // single writer per element
+    const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (j0 + k < dc && vv[k] != 0.f) dst[k] += vv[k];
-  if (rezero) *t4 = make_float4(0.f, 0.f, 0.f, 0.f);   // caller-owned buffer: back to all-zero for the next step
+    for (int k = 0; k < 4; ++k)
+      if (j0 + k < dc && vv[k] != 0.f) dst[k] += vv[k];
+    if (rezero) *t4 = make_float4(0.f, 0.f, 0.f, 0.f);   // caller-owned buffer: back to all-zero for the next step
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -519,8 +525,8 @@ extern "C" int b200ctr_cat_bwd(const void* x_cat, int idx_is_64, const float* co
   if (rc) return rc;
   B200_REQUIRE(Fc <= CAT_MAXF, B200CTR_E_UNSUPPORTED_SHAPE, "cat_bwd: more than %d categorical columns", CAT_MAXF);
   (void)max_card;
-  cat_unpad_kernel<<<(unsigned)ceil_div(sum_cards * (CAT_D / 4), (int64_t)256), 256, 0, st>>>(temp, dims, cards, keep_rows, rezero,
-                                                                                              dtables, Fc, sum_cards);
+  const int ublocks = (int)std::min<int64_t>(ceil_div(sum_cards * (CAT_D / 4), (int64_t)256), (int64_t)num_sms() * 16);
+  cat_unpad_kernel<<<ublocks, 256, 0, st>>>(temp, dims, cards, keep_rows, rezero, dtables, Fc, sum_cards);
   B200_LAUNCH_CHECK("cat_unpad_kernel");
   dim3 wgrid((unsigned)ceil_div((int64_t)CAT_D * CAT_MAXDC, (int64_t)256), (unsigned)Fc);
   cat_dw_reduce_kernel<<<wgrid, 256, 0, st>>>(dwpart, (int)grid.x, dims, sum_dims, dprojs);
