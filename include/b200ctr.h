@@ -250,6 +250,17 @@ int b200ctr_attn_tc_fwd(const float* qkv, const float* relmean, int max_len, int
 int b200ctr_attn_tc_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
                         const float* d_o, int64_t B, int K, int H, int D, void* dqkv, int dqkv_bf16, float* drelmean,
                         const uint32_t* keep, b200ctr_dropout_t drop, void* stream);
+/* Same contracts again in PACKED HALF arithmetic (csrc/attn_h16.cu; the default of the `amp: bf16` path): scores with
+ * the bias as the accumulator input of mma.m16n8k8.f16, max / exp2 / dropout mask on half2 pairs, probabilities straight
+ * into mma.m16n8k16 (fp32 accumulate), operand fragments by ldmatrix from transposed fp16 images; the backward rescales dO
+ * per sample by a power of two.  Under torch autocast the reference rounds scores and probabilities to bf16 (8 bits);
+ * fp16 keeps 11.  Same keep-word count (b200ctr_attn_tc_keep_words) but its own bit layout: pair the h16 forward with
+ * the h16 backward.  Dropout masks are identical to the other attention kernels'.                                     */
+int b200ctr_attn_h16_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D,
+                         float* o, float* lse, uint32_t* keep, b200ctr_dropout_t drop, void* stream);
+int b200ctr_attn_h16_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
+                         const float* d_o, int64_t B, int K, int H, int D, void* dqkv, int dqkv_bf16, float* drelmean,
+                         const uint32_t* keep, b200ctr_dropout_t drop, void* stream);
 int b200ctr_add_rmsnorm_fwd(const float* a, const float* b, const float* w, float eps, int64_t M, int D,
                             float* s_out, float* y_out, float* r_out, void* stream);
 /* dx = rmsnorm'(dy) (+ dx_add) ; dw: (b200ctr_rmsnorm_bwd_rows(M), D) PARTIAL sums of dy*s*r, one row per CTA, every entry

@@ -345,24 +345,31 @@ def test_ffn_bwd_fused_matches_unfused(dev, T, hidden, p):
         assert max_err_scaled(a.cpu(), b.cpu()) < 5e-3, name
 
 
-# ---- TF32 tensor-core attention (csrc/attn_tc.cu) vs the exact fp32 CUDA-core kernels (same dropout masks) ----------
-@pytest.mark.parametrize("B,K,p", [(3, 60, 0.0), (5, 60, 0.1), (2, 100, 0.1), (2, 148, 0.1), (4, 5, 0.0), (3, 16, 0.1), (2, 80, 0.0), (1, 1, 0.0)])
-def test_attn_tc_matches_fp32_kernels(dev, B, K, p):
+# ---- tensor-core attention (packed-half csrc/attn_h16.cu = the default, TF32 csrc/attn_tc.cu) vs the exact fp32 CUDA-core
+# kernels (same dropout masks).  do_scale: gradients of a mean-reduced loss are ~1e-7 -- far below fp16's range; the packed-half
+# backward rescales dO per sample by a power of two, and rows of very different size share that scale.
+@pytest.mark.parametrize("impl,do_scale", [("h16", 1.0), ("h16", 3e-8), ("tf32", 1.0)])
+@pytest.mark.parametrize("B,K,p", [(3, 60, 0.0), (5, 60, 0.1), (2, 100, 0.1), (2, 148, 0.1), (4, 5, 0.0), (3, 16, 0.1), (2, 80, 0.0), (1, 1, 0.0),
+                                   (2, 33, 0.2), (2, 112, 0.1), (2, 160, 0.0)])
+def test_attn_tc_matches_fp32_kernels(dev, B, K, p, impl, do_scale):
     from b200ctr import ops
     g = torch.Generator().manual_seed(100 * B + K)
     qkv = (_rand(g, B * K, 192) * 0.8).to(dev)
     relmean = (_rand(g, 2 * K + 1) * 0.5).to(dev)
-    d_o = _rand(g, B * K, 64).to(dev)
+    d_o = _rand(g, B * K, 64) * do_scale
+    if do_scale != 1.0:
+        d_o = d_o * torch.logspace(0, -3, B * K)[torch.randperm(B * K, generator=g)][:, None]   # token rows spanning 3 decades
+    d_o = d_o.to(dev)
     dr = ops.drop(p, 99, 3)
     o_ref, lse_ref = ops.attn_fwd(qkv, relmean, K, B, K, 8, 64, dr, tc=False)
-    o, lse, keep = ops.attn_fwd(qkv, relmean, K, B, K, 8, 64, dr, tc=True, save_keep=True)
+    o, lse, keep = ops.attn_fwd(qkv, relmean, K, B, K, 8, 64, dr, tc=True, save_keep=True, impl=impl)
     assert (keep is not None) == (p > 0)
     assert max_err_scaled(o.cpu(), o_ref.cpu()) < 3e-3
     assert max_err_scaled(lse.cpu(), lse_ref.cpu()) < 3e-3
     drel_ref = torch.zeros_like(relmean)
     drel = torch.zeros_like(relmean)
     dq_ref = ops.attn_bwd(qkv, relmean, K, o_ref, lse_ref, d_o, B, K, 8, 64, drel_ref, dr, tc=False)
-    dq = ops.attn_bwd(qkv, relmean, K, o_ref, lse_ref, d_o, B, K, 8, 64, drel, dr, tc=True)
+    dq = ops.attn_bwd(qkv, relmean, K, o_ref, lse_ref, d_o, B, K, 8, 64, drel, dr, tc=True, impl=impl)
     # dq: TF32 operands; dk / dv: bf16 P^T / dS^T operands (the amp: bf16 matmul policy).  Scale by the largest gradient
     # of the call so that exactly-zero reference blocks (K = 1: softmax over one key) compare in absolute terms.
     gmax = float(dq_ref.abs().max()) + 1e-30
@@ -372,11 +379,12 @@ def test_attn_tc_matches_fp32_kernels(dev, B, K, p):
     if keep is not None:
         # the stored keep flags must reproduce the re-hashed mask exactly: same kernel arithmetic, same result
         drel_k = torch.zeros_like(relmean)
-        dq_k = ops.attn_bwd(qkv, relmean, K, o_ref, lse_ref, d_o, B, K, 8, 64, drel_k, dr, tc=True, keep=keep)
+        dq_k = ops.attn_bwd(qkv, relmean, K, o_ref, lse_ref, d_o, B, K, 8, 64, drel_k, dr, tc=True, keep=keep, impl=impl)
         assert torch.equal(dq_k, dq)                                                  # no atomics anywhere: bit-identical
         assert float((drel_k - drel).abs().max()) / (float(drel.abs().max()) + gmax) < 1e-5
     # bf16 output for the fused in-projection backward: the same values, rounded once
-    dq16 = ops.attn_bwd(qkv, relmean, K, o_ref, lse_ref, d_o, B, K, 8, 64, torch.zeros_like(relmean), dr, tc=True, keep=keep, out_bf16=True)
+    dq16 = ops.attn_bwd(qkv, relmean, K, o_ref, lse_ref, d_o, B, K, 8, 64, torch.zeros_like(relmean), dr, tc=True, keep=keep, out_bf16=True,
+                        impl=impl)
     assert dq16.dtype == torch.bfloat16 and torch.equal(dq16, dq.to(torch.bfloat16))
 
 

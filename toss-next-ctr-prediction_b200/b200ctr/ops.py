@@ -542,7 +542,17 @@ def _attn_tc(tc: Optional[bool], K: int, H: int, D: int) -> bool:
     return bool(tc) and D == 64 and H == 8 and K <= 160
 
 
-def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP, tc: Optional[bool] = None, save_keep: bool = False):
+def _attn_impl(impl: Optional[str]) -> str:
+    """Tensor-core attention flavour: "h16" (packed-half kernels, csrc/attn_h16.cu; default) or "tf32" (csrc/attn_tc.cu).
+    B200CTR_ATTN overrides the default for A/B runs."""
+    impl = impl or _os.environ.get("B200CTR_ATTN", "h16")
+    if impl not in ("h16", "tf32"):
+        raise _lib.B200CtrError(f"attention implementation {impl!r}: expected 'h16' or 'tf32'")
+    return impl
+
+
+def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP, tc: Optional[bool] = None, save_keep: bool = False,
+             impl: Optional[str] = None):
     """Returns (o, lse), or (o, lse, keep) with save_keep: keep = the dropout keep-flag words the tensor-core backward reads
     instead of re-hashing (None when dropout is off or the fp32 kernels run)."""
     lib = _lib.load()
@@ -553,8 +563,8 @@ def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP, tc: Optional[bo
     if use_tc:
         if save_keep and dropout.p > 0.0:
             keep = torch.empty((int(lib.b200ctr_attn_tc_keep_words(B, K)),), device=qkv.device, dtype=torch.int32)
-        _run("attn_tc_fwd", lib.b200ctr_attn_tc_fwd, _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), _p(keep), dropout,
-             _stream())
+        fn = lib.b200ctr_attn_h16_fwd if _attn_impl(impl) == "h16" else lib.b200ctr_attn_tc_fwd
+        _run("attn_tc_fwd", fn, _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), _p(keep), dropout, _stream())
     else:
         _run("attn_fwd", lib.b200ctr_attn_fwd, _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), dropout, _stream())
     _count()
@@ -562,7 +572,7 @@ def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP, tc: Optional[bo
 
 
 def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=NO_DROP, tc: Optional[bool] = None, keep=None,
-             out_bf16: bool = False):
+             out_bf16: bool = False, impl: Optional[str] = None):
     """out_bf16 (tensor-core path only): dqkv comes back as bf16 for inproj_bwd, which consumes it as bf16 in any case."""
     lib = _lib.load()
     use_tc = _attn_tc(tc, K, H, D)
@@ -572,7 +582,8 @@ def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=N
     if drelmean is not None:      # the kernels write one partial row per sample (no float atomics); summed in sample order below
         drelmean = torch.zeros((B, 2 * max_len + 1), device=qkv.device, dtype=torch.float32)
     if use_tc:
-        _run("attn_tc_bwd", lib.b200ctr_attn_tc_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
+        fn = lib.b200ctr_attn_h16_bwd if _attn_impl(impl) == "h16" else lib.b200ctr_attn_tc_bwd
+        _run("attn_tc_bwd", fn, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
              int(out_bf16), _p(drelmean), _p(keep), dropout, _stream())
     else:
         _run("attn_bwd", lib.b200ctr_attn_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),

@@ -154,8 +154,8 @@ attn_tc_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relm
       la += p0 + p1; lb += p2 + p3;
       if (dctx.on) {
         const uint32_t ha = drop_pair_hash(keya, (uint32_t)(4 * j + t)), hb = drop_pair_hash(keyb, (uint32_t)(4 * j + t));
-        const bool k0 = (ha & 0xffffu) >= dctx.thr, k1 = (ha >> 16) >= dctx.thr;
-        const bool k2 = (hb & 0xffffu) >= dctx.thr, k3 = (hb >> 16) >= dctx.thr;
+        const bool k0 = drop_keep_lo(ha, dctx.thr), k1 = drop_keep_hi(ha, dctx.thr);
+        const bool k2 = drop_keep_lo(hb, dctx.thr), k3 = drop_keep_hi(hb, dctx.thr);
         p0 = k0 ? p0 : 0.f; p1 = k1 ? p1 : 0.f;           // the 1/(1-p) scale is applied once, to the output row
         p2 = k2 ? p2 : 0.f; p3 = k3 ? p3 : 0.f;
         const uint32_t sh = 4 * (j & 7);

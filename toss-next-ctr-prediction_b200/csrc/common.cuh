@@ -45,60 +45,71 @@ __device__ __forceinline__ uint32_t rng_u32(const b200ctr_dropout_t& d, uint64_t
   return x;
 }
 // keep-scale: 1/(1-p) if kept, 0 if dropped.  p == 0 short-circuits (exact identity).
-// One 32-bit hash serves the two elements of an aligned pair (idx >> 1): 16 bits each against a 16-bit threshold
-// (p is honoured to 2^-16), which halves the hash work in the kernels that walk adjacent elements (drop_scale2).
-__device__ __forceinline__ uint32_t drop_thr16(const b200ctr_dropout_t& d) { return __float2uint_rn(d.p * 65536.f); }
+// One 32-bit hash serves the two elements of an aligned pair (idx >> 1): bits 0-14 decide the even element, bits 16-30 the
+// odd one, each against a 15-bit threshold (p is honoured to 2^-15).  Bits 15 and 31 are unused on purpose: a 15-bit
+// field is a NON-NEGATIVE fp16 bit pattern, whose integer order is its float order, so the packed-half kernels
+// (attn_h16.cu) turn a pair of fields into a pair of keep masks with one AND and one HSET2 (drop_keep_mask2).
+__device__ __forceinline__ uint32_t drop_thr15(const b200ctr_dropout_t& d) { return min(__float2uint_rn(d.p * 32768.f), 0x7c00u); }
+__device__ __forceinline__ bool drop_keep_lo(uint32_t h, uint32_t thr) { return (h & 0x7fffu) >= thr; }
+__device__ __forceinline__ bool drop_keep_hi(uint32_t h, uint32_t thr) { return (h & 0x7fff0000u) >= (thr << 16); }
+// 0xffff in each half whose field is >= its threshold (thr2 = thr | thr << 16).  Fields 0x7c01..0x7fff are fp16 NaNs:
+// the unordered-or-greater compare keeps them (thr <= 0x7c00 always), exactly like the integer compare.
+__device__ __forceinline__ uint32_t drop_keep_mask2(uint32_t h, uint32_t thr2) {
+  uint32_t m;
+  asm("set.geu.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(h & 0x7fff7fffu), "r"(thr2));
+  return m;
+}
 __device__ __forceinline__ float drop_scale(const b200ctr_dropout_t& d, uint64_t idx) {
   if (d.p <= 0.f) return 1.f;
-  const uint32_t h = rng_u32(d, idx >> 1);
-  const uint32_t bits = (idx & 1) ? (h >> 16) : (h & 0xffffu);
-  return bits >= drop_thr16(d) ? 1.f / (1.f - d.p) : 0.f;
+  const uint32_t h = rng_u32(d, idx >> 1), thr = drop_thr15(d);
+  return ((idx & 1) ? drop_keep_hi(h, thr) : drop_keep_lo(h, thr)) ? 1.f / (1.f - d.p) : 0.f;
 }
 // both elements of the pair starting at the EVEN index idx0 (same values as two drop_scale calls)
 __device__ __forceinline__ void drop_scale2(const b200ctr_dropout_t& d, uint64_t idx0, float& s0, float& s1) {
-  const uint32_t h = rng_u32(d, idx0 >> 1), thr = drop_thr16(d);
+  const uint32_t h = rng_u32(d, idx0 >> 1), thr = drop_thr15(d);
   const float inv = 1.f / (1.f - d.p);
-  s0 = (h & 0xffffu) >= thr ? inv : 0.f;
-  s1 = (h >> 16) >= thr ? inv : 0.f;
+  s0 = drop_keep_lo(h, thr) ? inv : 0.f;
+  s1 = drop_keep_hi(h, thr) ? inv : 0.f;
 }
 
 // Row/column form used by the 2-D hot loops (attention probabilities, FFN / MLP activations): a full-strength
 // key per row (rng_u32 of the 64-bit row id, computed once per row) and ONE mixer round per aligned column pair.
 struct DropCtx {
-  uint32_t thr;     // 16-bit keep threshold
+  uint32_t thr;     // 15-bit keep threshold
   float inv;        // 1/(1-p)
   bool on;
 };
 __device__ __forceinline__ DropCtx drop_ctx(const b200ctr_dropout_t& d) {
   DropCtx c;
   c.on = d.p > 0.f;
-  c.thr = c.on ? drop_thr16(d) : 0u;
+  c.thr = c.on ? drop_thr15(d) : 0u;
   c.inv = c.on ? 1.f / (1.f - d.p) : 1.f;
   return c;
 }
 __device__ __forceinline__ uint32_t drop_row_key(const b200ctr_dropout_t& d, uint64_t row) { return rng_u32(d, row); }
-// the 32 random bits of one aligned column pair: low half -> column 2*colpair, high half -> column 2*colpair+1.
+// the random bits of one aligned column pair: bits 0-14 -> column 2*colpair, bits 16-30 -> column 2*colpair+1.
 // The row key already is a full-strength hash, so the per-pair step is ONE multiply-xorshift-multiply round of
 // key ^ (colpair * golden) instead of the full mix32 (6 instead of 10 instructions in every dropout hot loop).  Keep rates
 // and all pairwise column / half / row correlations of the masks were measured at the sampling-noise level (3e5 rows x
 // 384 columns, p = 0.1 / 0.2 / 0.5); a single multiply-xorshift or a Weyl ADD in front of the round is NOT enough
 // (1.5 - 7 % correlations between specific columns).
-__device__ __forceinline__ uint32_t drop_pair_hash(uint32_t key, uint32_t colpair) {
-  uint32_t x = key ^ (colpair * 0x9E3779B9U);
+// (_pre: the caller supplies colpair * golden, e.g. a per-thread term plus a compile-time constant per unrolled tile)
+__device__ __forceinline__ uint32_t drop_pair_hash_pre(uint32_t key, uint32_t colpair_golden) {
+  uint32_t x = key ^ colpair_golden;
   x *= 0x7feb352dU;
   x ^= x >> 15;
   return x * 0x846ca68bU;
 }
+__device__ __forceinline__ uint32_t drop_pair_hash(uint32_t key, uint32_t colpair) { return drop_pair_hash_pre(key, colpair * 0x9E3779B9U); }
 // keep-scales of columns 2*colpair and 2*colpair+1 of the row with key `key`
 __device__ __forceinline__ void drop_pair(const DropCtx& c, uint32_t key, uint32_t colpair, float& s0, float& s1) {
   const uint32_t h = drop_pair_hash(key, colpair);
-  s0 = (h & 0xffffu) >= c.thr ? c.inv : 0.f;
-  s1 = (h >> 16) >= c.thr ? c.inv : 0.f;
+  s0 = drop_keep_lo(h, c.thr) ? c.inv : 0.f;
+  s1 = drop_keep_hi(h, c.thr) ? c.inv : 0.f;
 }
 __device__ __forceinline__ float drop_rc(const DropCtx& c, uint32_t key, uint32_t col) {
   const uint32_t h = drop_pair_hash(key, col >> 1);
-  const uint32_t bits = (col & 1) ? (h >> 16) : (h & 0xffffu);
-  return bits >= c.thr ? c.inv : 0.f;
+  return ((col & 1) ? drop_keep_hi(h, c.thr) : drop_keep_lo(h, c.thr)) ? c.inv : 0.f;
 }
 
 // ---- math ------------------------------------------------------------------------------------------------

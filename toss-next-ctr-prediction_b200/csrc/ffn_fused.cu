@@ -244,7 +244,7 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
           float f1 = ffn_gelu(__uint_as_float(v[j + 1]) + b1s[n0 + j + 1]);
           if (dctx.on) {
             const uint32_t h = drop_pair_hash(rkey, (uint32_t)(n0 + j) >> 1);
-            const bool k0 = (h & 0xffffu) >= dctx.thr, k1 = (h >> 16) >= dctx.thr;
+            const bool k0 = drop_keep_lo(h, dctx.thr), k1 = drop_keep_hi(h, dctx.thr);
             f0 = k0 ? f0 * dctx.inv : 0.f; f1 = k1 ? f1 * dctx.inv : 0.f;
             kb |= (k0 ? 1u << j : 0u) | (k1 ? 2u << j : 0u);
           }
