@@ -317,7 +317,7 @@ __device__ __forceinline__ void ha_store2(float* base, int as_bf16, int64_t off,
 // dQ is summed over the parts through a shared-memory hand-off.  KS = 1 up to 64 keys, 2 above.
 // DROP: dropout on; KEEP: the keep flags come from the words the forward stored (otherwise re-hashed: same mask).
 template <int NT, int KS, bool DROP, bool KEEP>
-__global__ void __launch_bounds__(HA_THREADS * KS, (KS == 1 ? 2 : 1))
+__global__ void __launch_bounds__(HA_THREADS * KS, (KS == 1 ? 3 : 1))
 attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, const float* __restrict__ o,
                     const float* __restrict__ lse, const float* __restrict__ d_o, int K, float* __restrict__ dqkv, int dq16,
                     float* __restrict__ drelmean, const uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
@@ -345,10 +345,11 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
   const float* ob = o + b * (int64_t)K * HA_D;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const DropCtx dctx = drop_ctx(drop);
-  // dO and o of the thread's units stay in registers across the barrier that agrees on the sample's scale
+  // dO, the head-partial dot product dO . o (D = sum_j P_ij c_ij dP_ij = dO_i . o_i holds with the dropped-and-rescaled o the
+  // forward wrote) and the log-sum-exp of the thread's units stay in registers across the barrier that agrees on the scale
   constexpr int RG = (Kp / 2 + 15) / 16, UPT = (RG * 256 + NTH - 1) / NTH;
-  float4 xd[UPT][2], xo[UPT][2];
-  float Ls[UPT][2];
+  float4 xd[UPT][2];
+  float Ls[UPT][2], dro[UPT][2];
   float domax = 0.f;
 #pragma unroll
   for (int it = 0; it < UPT; ++it) {
@@ -357,11 +358,12 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
     for (int r = 0; r < 2; ++r) {
       const int row = 2 * un.rp + r;
       const bool ok = un.act && row < K;
-      xd[it][r] = make_float4(0.f, 0.f, 0.f, 0.f); xo[it][r] = xd[it][r]; Ls[it][r] = 0.f;
+      xd[it][r] = make_float4(0.f, 0.f, 0.f, 0.f); Ls[it][r] = 0.f; dro[it][r] = 0.f;
       if (ok) {
         xd[it][r] = *reinterpret_cast<const float4*>(dob + (int64_t)row * HA_D + 4 * un.c);
-        xo[it][r] = *reinterpret_cast<const float4*>(ob + (int64_t)row * HA_D + 4 * un.c);
+        const float4 oo = *reinterpret_cast<const float4*>(ob + (int64_t)row * HA_D + 4 * un.c);
         Ls[it][r] = lse[(b * HA_H + (un.c >> 1)) * (int64_t)K + row];
+        dro[it][r] = xd[it][r].x * oo.x + xd[it][r].y * oo.y + xd[it][r].z * oo.z + xd[it][r].w * oo.w;
       }
     }
   }
@@ -401,10 +403,8 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
       const float L = Ls[it][r] * HA_LOG2E;
       m[r] = ok ? __half2float(__float2half_rn(L)) : 100.f;      // padded rows: e = 2^(bias - 100) ~ 0 and dO' = D' = 0
       f[r] = ok ? exp2f(m[r] - L) * spow * dctx.inv : 0.f;
-      // D = sum_j P_ij (c_ij dP_ij) = dO_i . o_i holds with the dropped-and-rescaled o the forward wrote; dO' carries the extra
-      // 1/(1-p) of the mask scale, which D' must not: o already contains it
-      const float4 &x = xd[it][r], &oo = xo[it][r];
-      d[r] = (x.x * oo.x + x.y * oo.y + x.z * oo.z + x.w * oo.w) * f[r] * (1.f / dctx.inv);
+      // dO' carries the extra 1/(1-p) of the mask scale, which D' must not: o already contains it
+      d[r] = dro[it][r] * f[r] * (1.f / dctx.inv);
       d[r] += __shfl_xor_sync(0xffffffffu, d[r], 1);                // the other half of the head's 8 dims
     }
     if (un.act) {
@@ -452,6 +452,11 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
     if (chead) p[1] += h2_hi(v);
     __syncwarp();
   };
+  uint32_t kwn[NW];
+  if (DROP && KEEP) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) kwn[w] = __ldg(keep + ha_keep_index(b, h, MT, 0, NW, w, lane));
+  }
 #pragma unroll 1
   for (int i = 0; i < MT; ++i) {
     const int qa = 16 * i + g, qb = qa + 8;
@@ -460,9 +465,9 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
     ldsm_x4(bq0, bq1, bd0, bd1, ab_addr + 32 * i);               // B fragments (16 queries x head dim) of dK += dS^T.Q, dV += P^T.dO'
     const uint32_t mna = mneg[h * Kp + qa], mnb = mneg[h * Kp + qb], dna = dneg[h * Kp + qa], dnb = dneg[h * Kp + qb];
     uint32_t kw[NW];
-    if (DROP && KEEP) {
+    if (DROP && KEEP) {      // this query tile's keep words were requested one iteration ago: the loop never waits on global memory
 #pragma unroll
-      for (int w = 0; w < NW; ++w) kw[w] = __ldg(keep + ha_keep_index(b, h, MT, i, NW, w, lane));
+      for (int w = 0; w < NW; ++w) { kw[w] = kwn[w]; kwn[w] = __ldg(keep + ha_keep_index(b, h, MT, min(i + 1, MT - 1), NW, w, lane)); }
     }
     uint32_t keya = 0u, keyb = 0u;
     if (DROP && !KEEP) { keya = keys[h * Kp + qa]; keyb = keys[h * Kp + qb]; }
