@@ -20,8 +20,7 @@
 // 8 max|dO| max|V| below 2^9 (gradients of a mean-reduced loss are ~1e-6: below fp16's range), undone on the way out.
 // dS = e (dP' & keep - D'), dQ += dS.K straight from the registers, dK / dV through movmatrix transposes; all fp32 accumulate.
 // No atomics; dbias as in attn_tc.cu (register slots per diagonal block, per-warp shared copies, per-sample partial row).
-#include "common.cuh"
-#include <cuda_fp16.h>
+#include "h2_common.cuh"
 #include <cuda_bf16.h>
 #include <algorithm>
 
@@ -32,27 +31,6 @@ constexpr int HA_H = 8;
 constexpr int HA_THREADS = 256;
 constexpr float HA_LOG2E = 1.4426950408889634f, HA_LN2 = 0.6931471805599453f;
 constexpr uint32_t HA_ONES = 0x3c003c00u;       // half2(1, 1)
-
-__device__ __forceinline__ uint32_t h2_pack(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) { uint32_t r; asm("add.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-__device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) { uint32_t r; asm("mul.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-__device__ __forceinline__ uint32_t h2_max(uint32_t a, uint32_t b) { uint32_t r; asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-__device__ __forceinline__ uint32_t h2_ex2(uint32_t a) { uint32_t r; asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(a)); return r; }
-__device__ __forceinline__ float h2_lo(uint32_t a) { return __half2float(__ushort_as_half((unsigned short)(a & 0xffffu))); }
-__device__ __forceinline__ float h2_hi(uint32_t a) { return __half2float(__ushort_as_half((unsigned short)(a >> 16))); }
-__device__ __forceinline__ uint32_t h2_swap(uint32_t a) { return __byte_perm(a, a, 0x1032); }
-__device__ __forceinline__ uint32_t h2_dup_lo(uint32_t a) { return __byte_perm(a, a, 0x1010); }
-__device__ __forceinline__ uint32_t h2_dup_hi(uint32_t a) { return __byte_perm(a, a, 0x3232); }
-// 0xffff per half from the flags at bits 15 and 31
-__device__ __forceinline__ uint32_t h2_mask_from_signs(uint32_t y) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(y), "r"(0u), "r"(0xBB99u));
-  return r;
-}
 
 // D(16 x 8, fp16 pairs) = A(16 x 8) . B(8 x 8) + C
 __device__ __forceinline__ void mma_1688_h(uint32_t (&d)[2], const uint32_t (&a)[2], uint32_t b, uint32_t c0, uint32_t c1) {

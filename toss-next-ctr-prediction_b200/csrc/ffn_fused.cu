@@ -19,6 +19,7 @@
 // Shared-memory operand layout is the canonical SWIZZLE_NONE one of gemm_tc.cu: 8 x 16-byte core matrices,
 // k-group stride R*16 bytes ("LBO"), mn-group stride 128 bytes ("SBO").
 #include "tc_common.cuh"
+#include "h2_common.cuh"
 #include <algorithm>
 
 namespace b200ctr {
@@ -28,13 +29,14 @@ constexpr int FF_TM = 128;        // tokens per tile (UMMA M)
 constexpr int FF_HC = 64;         // hidden chunk (UMMA N of GEMM1, K of GEMM2)
 constexpr int FFW_EPI_WARPS = 16;                 // forward kernel: 4 loader/RMSNorm + 16 GELU-epilogue + 1 MMA warp
 constexpr int FFW_MMA_WARP = 4 + FFW_EPI_WARPS;
+constexpr int FFW_PB = 1;      // TMEM buffers of the pre-activation chunk (2 measured 12 % SLOWER than 1: see profiles/README.md)
 constexpr int FFW_NT = (FFW_MMA_WARP + 1) * 32;
 constexpr int FF_A_BYTES = FF_TM * FF_D * 2;        // 16 KB: x1 tile, bf16
 constexpr int FF_FD_BYTES = FF_TM * FF_HC * 2;      // 16 KB: activation chunk, bf16
 constexpr int FF_WCHUNK = FF_HC * FF_D * 2;         // 8 KB of W1 or W2 per hidden chunk
 
 struct FfnBars {
-  unsigned long long a_full[2], a_empty[2], p_full, p_empty, fd_full[2], fd_empty[2], h2_full[2], h2_empty[2];
+  unsigned long long a_full[2], a_empty[2], p_full[2], p_empty[2], fd_full[2], fd_empty[2], h2_full[2], h2_empty[2];
   uint32_t tmem_base;
 };
 
@@ -49,8 +51,10 @@ __device__ __forceinline__ void ffn_stage_w1(unsigned char* w1s, const float* __
         make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
   }
 }
-// W2 [64][hidden] fp32 -> per 64-column chunk a K-major B operand (N = d rows, K = hidden within the chunk)
-__device__ __forceinline__ void ffn_stage_w2(unsigned char* w2s, const float* __restrict__ w2, int hidden, int tid, int nt) {
+// W2 [64][hidden] fp32 -> per 64-column chunk a K-major B operand (N = d rows, K = hidden within the chunk);
+// the forward's copy: fp16, times the dropout keep scale 1/(1-p) (the GELU epilogue hands GEMM2 fp16 activations that are
+// masked but not rescaled)
+__device__ __forceinline__ void ffn_stage_w2_h(unsigned char* w2s, const float* __restrict__ w2, int hidden, float scale, int tid, int nt) {
   const int hg_per_row = hidden >> 3;
   for (int u = tid; u < FF_D * hg_per_row; u += nt) {
     const int d = u / hg_per_row, hg = u % hg_per_row;
@@ -58,7 +62,8 @@ __device__ __forceinline__ void ffn_stage_w2(unsigned char* w2s, const float* __
     const float4 a = __ldg(p), b = __ldg(p + 1);
     const int c = hg >> 3, kc = hg & 7;
     *reinterpret_cast<uint4*>(w2s + c * FF_WCHUNK + (kc * 8 + (d >> 3)) * 128 + (d & 7) * 16) =
-        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+        make_uint4(h2_pack(a.x * scale, a.y * scale), h2_pack(a.z * scale, a.w * scale), h2_pack(b.x * scale, b.y * scale),
+                   h2_pack(b.z * scale, b.w * scale));
   }
 }
 // one 128-token x 64 fp32 tile -> bf16 K-major A operand (R = 128); 128 threads, rows >= T are zero-filled
@@ -150,19 +155,22 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
       mbar_init(smem_u32(&bars->fd_full[s]), FFW_EPI_WARPS); mbar_init(smem_u32(&bars->fd_empty[s]), 1);
       mbar_init(smem_u32(&bars->h2_full[s]), 1); mbar_init(smem_u32(&bars->h2_empty[s]), 4);
     }
-    mbar_init(smem_u32(&bars->p_full), 1); mbar_init(smem_u32(&bars->p_empty), FFW_EPI_WARPS);
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->p_full[s]), 1); mbar_init(smem_u32(&bars->p_empty[s]), FFW_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   ffn_stage_w1(w1s, w1, hidden, tid, FFW_NT);
-  ffn_stage_w2(w2s, w2, hidden, tid, FFW_NT);
-  for (int i = tid; i < hidden; i += FFW_NT) b1s[i] = b1[i];
+  ffn_stage_w2_h(w2s, w2, hidden, drop.p > 0.f ? 1.f / (1.f - drop.p) : 1.f, tid, FFW_NT);
+  uint32_t* b1h = reinterpret_cast<uint32_t*>(b1s);                // bias as half2 pairs
+  for (int i = tid; i < hidden / 2; i += FFW_NT) b1h[i] = h2_pack(b1[2 * i], b1[2 * i + 1]);
   if (tid < FF_D) { b2s[tid] = b2[tid]; n2s[tid] = n2w[tid]; }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  const uint32_t P_COL = 0, H2_COL = 64;          // h2 buffers at columns 64 and 128
+  // TMEM: pre-activation chunk buffer(s) at columns 0 (/ 64); the x1 . W1^T product of chunk g + FFW_PB is issued the moment
+  // the epilogue has READ chunk g; h2 buffers at columns 128 and 192
+  const uint32_t P_COL = 0, H2_COL = 128;
 
   if (warp < 4) {
     // ---------------------------------------- tile loader + final epilogue ----------------------------------
@@ -223,33 +231,39 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
     const int r = q * 32 + lane;
     uint32_t g = 0;
     const DropCtx dctx = drop_ctx(drop);
+    const uint32_t thr2 = dctx.thr | (dctx.thr << 16);
     for (int it = 0; it < n_it; ++it) {
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
       const int64_t m = tile * FF_TM + r;
       const uint32_t rkey = dctx.on ? drop_row_key(drop, (uint64_t)m) : 0u;
       for (int c = 0; c < NC; ++c, ++g) {
-        mbar_wait(smem_u32(&bars->p_full), g & 1);
+        const uint32_t pb = g % FFW_PB;
+        mbar_wait(smem_u32(&bars->p_full[pb]), (g / FFW_PB) & 1);
         tc_fence_after();
         uint32_t v[16];
-        tmem_ld16(tmem + P_COL + part * 16 + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld16(tmem + P_COL + pb * 64 + part * 16 + ((uint32_t)(q * 32) << 16), v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->p_empty));
+        if (lane == 0) mbar_arrive(smem_u32(&bars->p_empty[pb]));
+        // per-element work on half2 pairs: pack, + b1, GELU (h2_common.cuh), keep mask = one AND + one HSET2 on the hash
+        // word; the activation goes to GEMM2 as fp16 (11 bits, against the 8 of bf16), masked but not rescaled (W2 carries
+        // the 1/(1-p)).  10 instructions per element instead of 27.
         const int n0 = c * FF_HC + part * 16;
+        const uint4 bq0 = *reinterpret_cast<const uint4*>(b1h + (n0 >> 1)), bq1 = *reinterpret_cast<const uint4*>(b1h + (n0 >> 1) + 4);
+        const uint32_t bh[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
         uint32_t pk[8];
         uint32_t kb = 0u;
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          float f0 = ffn_gelu(__uint_as_float(v[j]) + b1s[n0 + j]);
-          float f1 = ffn_gelu(__uint_as_float(v[j + 1]) + b1s[n0 + j + 1]);
+        for (int jp = 0; jp < 8; ++jp) {
+          uint32_t f = h2_gelu(h2_add(h2_pack(__uint_as_float(v[2 * jp]), __uint_as_float(v[2 * jp + 1])), bh[jp]));
           if (dctx.on) {
-            const uint32_t h = drop_pair_hash(rkey, (uint32_t)(n0 + j) >> 1);
-            const bool k0 = drop_keep_lo(h, dctx.thr), k1 = drop_keep_hi(h, dctx.thr);
-            f0 = k0 ? f0 * dctx.inv : 0.f; f1 = k1 ? f1 * dctx.inv : 0.f;
-            kb |= (k0 ? 1u << j : 0u) | (k1 ? 2u << j : 0u);
+            const uint32_t mk = drop_keep_mask2(drop_pair_hash(rkey, (uint32_t)(n0 >> 1) + jp), thr2);
+            f &= mk;
+            kb |= mk & ((1u << (2 * jp)) | (1u << (2 * jp + 17)));      // bit 2jp <- even column, bit 16 + 2jp + 1 <- odd column
           }
-          pk[j >> 1] = pack_bf16(f0, f1);
+          pk[jp] = f;
         }
+        kb |= kb >> 16;
         if (keep && dctx.on) keep[((tile * NC + c) * 4 + part) * FF_TM + r] = (uint16_t)kb;
         const int fb = g & 1;
         if (g >= 2) mbar_wait(smem_u32(&bars->fd_empty[fb]), ((g >> 1) - 1) & 1);
@@ -267,30 +281,53 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
     }
   } else if (lane == 0) {
     // ---------------------------------------- MMA issuer ---------------------------------------------------------
-    const uint32_t idesc = umma_idesc(FF_TM, FF_HC, false, false);       // M=128, N=64, both operands K-major
+    const uint32_t idesc = umma_idesc(FF_TM, FF_HC, false, false);       // M=128, N=64, both operands K-major (bf16: x1 . W1^T)
+    const uint32_t idesc2 = umma_idesc_f16(FF_TM, FF_HC, false, false);  // fp16: activation . W2^T
     const uint32_t as_u = smem_u32(as), fd_u = smem_u32(fds), w1_u = smem_u32(w1s), w2_u = smem_u32(w2s);
     const uint32_t total = (uint32_t)n_it * (uint32_t)NC;
-    auto gemm2 = [&](uint32_t gg) {
-      const uint32_t it2 = gg / NC, c2 = gg % NC, fb = gg & 1, hb = it2 & 1;
-      mbar_wait(smem_u32(&bars->fd_full[fb]), (gg >> 1) & 1);
+    // The issuer is ONE thread whose dependent scalar instructions compete with 20 busy warps for issue slots: at ~300
+    // instructions per chunk (runtime divisions, descriptor construction per MMA, predicate set-up) it, not the epilogue,
+    // set the pace of the kernel.  Descriptors are built once and advanced by an add; chunk / tile counters are carried.
+    const uint64_t dA[2] = {make_desc(as_u, FF_TM * 16, 128), make_desc(as_u + FF_A_BYTES, FF_TM * 16, 128)};
+    const uint64_t dF[2] = {make_desc(fd_u, FF_TM * 16, 128), make_desc(fd_u + FF_FD_BYTES, FF_TM * 16, 128)};
+    const uint64_t dW1 = make_desc(w1_u, FF_HC * 16, 128), dW2 = make_desc(w2_u, FF_D * 16, 128);
+    uint32_t g1 = 0, it1 = 0, c1 = 0, g2 = 0, it2 = 0, c2 = 0;
+    auto gemm1 = [&]() {                             // next chunk -> P buffer g1 % FFW_PB (free once the epilogue has read chunk g1 - FFW_PB)
+      const uint32_t ab = it1 & 1, pb = g1 % FFW_PB;
+      if (c1 == 0) mbar_wait(smem_u32(&bars->a_full[ab]), (it1 >> 1) & 1);
+      if (g1 >= FFW_PB) mbar_wait(smem_u32(&bars->p_empty[pb]), ((g1 / FFW_PB) - 1) & 1);
+      tc_fence_after();
+      const uint64_t da = dA[ab], db = desc_advance(dW1, c1 * FF_WCHUNK);
+      const uint32_t td = tmem + P_COL + pb * 64;
+      umma_bf16_c<false>(td, da, db, idesc);
+      umma_bf16_c<true>(td, desc_advance(da, 2 * FF_TM * 16), desc_advance(db, 2 * FF_HC * 16), idesc);
+      umma_bf16_c<true>(td, desc_advance(da, 4 * FF_TM * 16), desc_advance(db, 4 * FF_HC * 16), idesc);
+      umma_bf16_c<true>(td, desc_advance(da, 6 * FF_TM * 16), desc_advance(db, 6 * FF_HC * 16), idesc);
+      umma_commit(smem_u32(&bars->p_full[pb]));
+      ++g1;
+      if (++c1 == (uint32_t)NC) { umma_commit(smem_u32(&bars->a_empty[ab])); c1 = 0; ++it1; }
+    };
+    auto gemm2 = [&]() {
+      const uint32_t fb = g2 & 1, hb = it2 & 1;
+      mbar_wait(smem_u32(&bars->fd_full[fb]), (g2 >> 1) & 1);
       if (c2 == 0 && it2 >= 2) mbar_wait(smem_u32(&bars->h2_empty[hb]), ((it2 >> 1) - 1) & 1);
       tc_fence_after();
-      ffn_mma_kk(tmem + H2_COL + hb * 64, fd_u + fb * FF_FD_BYTES, FF_TM * 16, w2_u + c2 * FF_WCHUNK, FF_D * 16, idesc,
-                 FF_HC / 16, c2 > 0);
+      const uint64_t da = dF[fb], db = desc_advance(dW2, c2 * FF_WCHUNK);
+      const uint32_t td = tmem + H2_COL + hb * 64;
+      if (c2 == 0) umma_bf16_c<false>(td, da, db, idesc2); else umma_bf16_c<true>(td, da, db, idesc2);
+      umma_bf16_c<true>(td, desc_advance(da, 2 * FF_TM * 16), desc_advance(db, 2 * FF_D * 16), idesc2);
+      umma_bf16_c<true>(td, desc_advance(da, 4 * FF_TM * 16), desc_advance(db, 4 * FF_D * 16), idesc2);
+      umma_bf16_c<true>(td, desc_advance(da, 6 * FF_TM * 16), desc_advance(db, 6 * FF_D * 16), idesc2);
       umma_commit(smem_u32(&bars->fd_empty[fb]));
-      if (c2 == (uint32_t)NC - 1) umma_commit(smem_u32(&bars->h2_full[hb]));
+      ++g2;
+      if (++c2 == (uint32_t)NC) { umma_commit(smem_u32(&bars->h2_full[hb])); c2 = 0; ++it2; }
     };
+    for (int pre = 0; pre < FFW_PB; ++pre)
+      if (g1 < total) gemm1();
     for (uint32_t g = 0; g < total; ++g) {
-      const uint32_t it = g / NC, c = g % NC, ab = it & 1;
-      if (c == 0) mbar_wait(smem_u32(&bars->a_full[ab]), (it >> 1) & 1);
-      if (g > 0) mbar_wait(smem_u32(&bars->p_empty), (g - 1) & 1);
-      tc_fence_after();
-      ffn_mma_kk(tmem + P_COL, as_u + ab * FF_A_BYTES, FF_TM * 16, w1_u + c * FF_WCHUNK, FF_HC * 16, idesc, FF_D / 16, false);
-      umma_commit(smem_u32(&bars->p_full));
-      if (c == (uint32_t)NC - 1) umma_commit(smem_u32(&bars->a_empty[ab]));
-      if (g > 0) gemm2(g - 1);
+      if (g1 < total) gemm1();
+      gemm2();
     }
-    if (total > 0) gemm2(total - 1);
   }
   tc_fence_before();
   __syncthreads();
