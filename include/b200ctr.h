@@ -476,6 +476,33 @@ int b200ctr_gather_rows(const void* src, int64_t row_bytes, const int64_t* src_i
  * 2 int32 -> int64 (ids; the kernels also take int32 directly).                                                      */
 int b200ctr_widen(int kind, const void* in, int64_t n, void* out, void* stream);
 
+/* ---- on-GPU cache builder  (data/build_cache_v1.py:28-75 medians, 78-173 `_process_arrow_batch`) ----------
+ * Arrow column buffers in, App. D shard arrays out.  Strings are (bytes, offsets[rows+1]) with int32 (offsets64 = 0) or int64
+ * offsets; validity = Arrow validity bitmap at bit offset 0 (LSB first) or NULL.  The reference's categorical / group hash is
+ * polars.Series.hash (unpinned, absent here), so this builder pins its own (cache format v2):
+ *     h(bytes) = splitmix64_finalize(fnv1a64(bytes, basis 0xcbf29ce484222325 ^ seed)), nulls hash as "NA", integers as their
+ *     decimal string; out[r * out_stride] = h % mod as int32 (out_int32) or int64.
+ * b200ctr_cache_hash_bytes_host: the same hash of one byte string on the HOST (no GPU; returns the 64 bits as int64).
+ * parse_seq: "12,345,6789" -> last max_len tokens right-aligned in seq_out (rows, max_len), pad_id on the left; n_bad
+ *     (device uint64, caller-zeroed) counts bytes other than digits / ',' and tokens > INT32_MAX.
+ * col_to_f32: one numeric column buffer (dtype 0 f32, 1 f64, 2 i32, 3 i64, 4 u8) -> float32 with nulls as NaN.
+ * numeric: x = (Fn, ld) column-major float32, rows r0..r0+rows -> X_num (rows, Fn) float32 with NaN -> med[c], then
+ *     nan_to_num(nan 0, +-inf -> +-1e6), and X_mask (rows, Fn) uint8 = isnan.
+ * select_hist: one 8-bit digit pass of an exact radix select over order-preserving float keys: query q looks at column
+ *     q_col[q], elements whose key equals q_prefix[q] above bit shift + 8; hist (n_q, 256) uint64, caller-zeroed.            */
+int64_t b200ctr_cache_hash_bytes_host(const void* bytes, int64_t n, uint64_t seed);
+int b200ctr_cache_hash_strings(const void* bytes, const void* offsets, int offsets64, const void* validity, int64_t rows,
+                               uint64_t mod, uint64_t seed, void* out, int64_t out_stride, int out_int32, void* stream);
+int b200ctr_cache_hash_int64(const void* vals, const void* validity, int64_t rows, uint64_t mod, uint64_t seed, void* out,
+                             int64_t out_stride, int out_int32, void* stream);
+int b200ctr_cache_parse_seq(const void* bytes, const void* offsets, int offsets64, const void* validity, int64_t rows,
+                            int max_len, int pad_id, int32_t* seq_out, void* n_bad, void* stream);
+int b200ctr_cache_col_to_f32(const void* col, int dtype, const void* validity, int64_t rows, float* out, void* stream);
+int b200ctr_cache_numeric(const float* x, int64_t ld, int64_t r0, int64_t rows, int Fn, const float* med, float* X_num,
+                          void* X_mask, void* stream);
+int b200ctr_cache_select_hist(const float* x, int64_t ld, int64_t rows, const int* q_col, const uint32_t* q_prefix, int n_q,
+                              int shift, void* hist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,7 @@ class Epilogue(ctypes.Structure):
 NO_DROP = Dropout(0.0, 0, 0, 0)
 
 _SCALARS = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "double": ctypes.c_double,
-            "int32_t": ctypes.c_int32, "uint32_t": ctypes.c_uint32, "b200ctr_dropout_t": Dropout}
+            "int32_t": ctypes.c_int32, "uint32_t": ctypes.c_uint32, "uint64_t": ctypes.c_uint64, "b200ctr_dropout_t": Dropout}
 _RET = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "const char*": ctypes.c_char_p}
 
 
