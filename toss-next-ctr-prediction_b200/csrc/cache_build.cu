@@ -87,6 +87,7 @@ __global__ void cache_parse_seq_kernel(const uint8_t* __restrict__ bytes, const 
   const uint8_t* p = bytes + s;
   int n_tok = 0, bad = 0;
   bool carry = false;
+#pragma unroll 4
   for (int64_t base = 0; base < n; base += 32) {
     const int64_t i = base + lane;
     const uint8_t c = i < n ? p[i] : (uint8_t)',';
@@ -102,6 +103,7 @@ __global__ void cache_parse_seq_kernel(const uint8_t* __restrict__ bytes, const 
   for (int j = lane; j < max_len - keep; j += 32) orow[j] = pad_id;
   int seen = 0;
   carry = false;
+#pragma unroll 2
   for (int64_t base = 0; base < n && keep > 0; base += 32) {
     const int64_t i = base + lane;
     const uint8_t c = i < n ? p[i] : (uint8_t)',';

@@ -91,6 +91,34 @@ adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   }
 }
 
+// Multi-tensor form for the UNMODIFIED reference loop (Tier A: 138 separate parameter tensors, torch.optim.AdamW semantics,
+// utils/ema.py:91-131): one launch walks a chunk table instead of 3-4 launches per tensor.  A tensor record is six 64-bit
+// words {p, g, m, v, ema, n}; mode 0 = AdamW (+ EMA when the record has a shadow), mode 1 = EMA only (p is read).
+struct MtRec { float* p; const float* g; float* m; float* v; float* ema; int64_t n; };
+__global__ void __launch_bounds__(256)
+multi_adamw_ema_kernel(const MtRec* __restrict__ recs, const int32_t* __restrict__ chunk_tensor, const int64_t* __restrict__ chunk_off,
+                       int64_t n_chunks, int64_t chunk, float lr, float wd, float b1, float b2, float eps, float bc1, float bc2_sqrt,
+                       const float* __restrict__ coef, float ema_decay, int mode) {
+  const float c = coef ? coef[0] : 1.f;
+  const float step_size = lr / bc1;
+  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const MtRec r = recs[chunk_tensor[ch]];
+    const int64_t i0 = chunk_off[ch], i1 = min(i0 + chunk, r.n);
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+      float pi = r.p[i];
+      if (mode == 0) {
+        const float gi = r.g[i] * c;
+        pi *= (1.f - lr * wd);
+        const float mi = r.m[i] + (gi - r.m[i]) * (1.f - b1);
+        const float vi = r.v[i] * b2 + (1.f - b2) * gi * gi;
+        pi -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+        r.p[i] = pi; r.m[i] = mi; r.v[i] = vi;
+      }
+      if (r.ema) r.ema[i] = r.ema[i] * ema_decay + pi * (1.f - ema_decay);
+    }
+  }
+}
+
 // ---- row-sparse bookkeeping: one representative slot per distinct token ---------------------------------
 __global__ void rows_claim_kernel(const int32_t* __restrict__ tok, int64_t n, int pad_id, int32_t* __restrict__ owner) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,6 +238,22 @@ extern "C" int b200ctr_adamw_ema(float* p, const float* g, float* m, float* v, f
   adamw_ema_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, g, m, v, ema, n, lr, wd, beta1, beta2, eps, (float)bc1,
                                                         (float)sqrt(bc2), coef, ema_decay);
   B200_LAUNCH_CHECK("adamw_ema_kernel");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_multi_adamw_ema(const void* recs, const int32_t* chunk_tensor, const int64_t* chunk_off, int64_t n_chunks,
+                                       int64_t chunk, float lr, float wd, float beta1, float beta2, float eps, int64_t step,
+                                       const float* coef, float ema_decay, int mode, void* stream) {
+  B200_REQUIRE(recs && chunk_tensor && chunk_off && chunk > 0, B200CTR_E_INVALID_ARG, "multi_adamw_ema: null pointer");
+  B200_REQUIRE(mode == 0 || mode == 1, B200CTR_E_INVALID_ARG, "multi_adamw_ema: mode %d", mode);
+  B200_REQUIRE(mode == 1 || step >= 1, B200CTR_E_INVALID_ARG, "multi_adamw_ema: step must be >= 1");
+  if (n_chunks == 0) return B200CTR_OK;
+  const double bc1 = mode == 0 ? 1.0 - pow((double)beta1, (double)step) : 1.0;
+  const double bc2 = mode == 0 ? 1.0 - pow((double)beta2, (double)step) : 1.0;
+  const int grid = (int)std::min<int64_t>(n_chunks, (int64_t)num_sms() * 8);
+  multi_adamw_ema_kernel<<<grid, 256, 0, as_stream(stream)>>>((const MtRec*)recs, chunk_tensor, chunk_off, n_chunks, chunk, lr, wd, beta1,
+                                                              beta2, eps, (float)bc1, (float)sqrt(bc2), coef, ema_decay, mode);
+  B200_LAUNCH_CHECK("multi_adamw_ema_kernel");
   return B200CTR_OK;
 }
 
