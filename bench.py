@@ -499,12 +499,14 @@ def rooflines(cfg, B, steps, prof, host, used, args):
     keep_b = 4.0 * B * 8 * ((Kk + 15) // 16) * ((2 * ((Kk + 15) // 16) + 7) // 8) * 32      # attention keep-bit words per launch
     models = {   # family -> (bound, work per launch [FLOP or byte], description); "both": the BINDING roof is reported
         "attn_tc_bwd": ("both", (10.0 * Kk * Kk * D * B, T * (4.0 * 3 * D + 4.0 * D + 4.0 * D + 2.0 * 3 * D) + 4.0 * B * 8 * Kk + keep_b),
-                        "attn_tc_bwd_kernel (mma.sync TF32/bf16, head_dim 8; one pass: S, dP, dQ, dK, dV = 10 K^2 D FLOP/sample; "
-                        "qkv, o, d_o, lse, keep bits in, bf16 dqkv out)"),
+                        "attn_h16_bwd_kernel (packed-half attention backward, head_dim 8: fp16-accumulate score MMAs, half2 exp / mask / dS, "
+                        "fp32-accumulate dQ / dK / dV MMAs; one pass = 10 K^2 D FLOP/sample; qkv, o, d_o, lse, keep bits in, bf16 dqkv out)"),
         "attn_tc_fwd": ("both", (4.0 * Kk * Kk * D * B, T * (4.0 * 3 * D + 4.0 * D) + 4.0 * B * 8 * Kk + keep_b),
-                        "attn_tc_fwd_kernel (mma.sync TF32: QK^T and PV = 4 K^2 D FLOP/sample; qkv in, o, lse, keep bits out)"),
+                        "attn_h16_fwd_kernel (packed-half attention forward: QK^T + bias in one fp16-accumulate MMA, half2 softmax / dropout, "
+                        "PV and the row sums on fp32-accumulate MMAs = 4 K^2 D FLOP/sample; qkv in, o, lse, keep bits out)"),
         "ffn_fwd": ("both", (4.0 * T * D * hid, T * (4.0 * D * 3 + 4.0 + hid / 8.0)),
-                    "ffn_fwd_kernel (tcgen05 fused FFN block: 2 contractions of T x 64 x ffn_hidden; x1 in, s2, x2, r2, keep bits out)"),
+                    "ffn_fwd_kernel (tcgen05 fused FFN block: 2 contractions of T x 64 x ffn_hidden, half2 GELU / dropout epilogue, fp16 "
+                    "activation operand; x1 in, s2, x2, r2, keep bits out)"),
         "ffn_bwd": ("both", (8.0 * T * D * hid, T * (4.0 * D * 4 + 4.0 + hid / 8.0)),
                     "ffn_bwd1/ffn_bwd2 (tcgen05 fused FFN backward: 4 algorithmic contractions, the recompute and the internal bf16 "
                     "dpre spill are not counted; dy, s2, x1, r2, keep bits in, dx1 out)"),
@@ -566,8 +568,8 @@ def rooflines(cfg, B, steps, prof, host, used, args):
     modelled = [k for k, _ in top if k in models or k in gemm_flops]
     roof = roof_of(modelled[0]) if modelled else None
     if roof is not None and modelled[0].startswith("attn_tc"):
-        roof["note"] = ("HBM is the binding roof (head_dim 8: 2 MMAs per 128 scores, the tensor floor is 9x lower); the kernel itself is "
-                        "bound by instruction issue and the L1 data pipe on the exp / mask work per score (ncu: issue 49-74 %)")
+        roof["note"] = ("HBM is the binding roof (head_dim 8: the tensor floor is 9x lower); the kernel is bound by the per-score work "
+                        "and, since the packed-half rewrite, by the latency of its per-sample staging phase (ncu r02: issue 43-57 %)")
     return {"roofline": roof, "gather_roofline": roof_of("retrieve_fwd") if "retrieve_fwd" in fam else None,
             "kernel_rooflines": [dict(roof_of(k), family=k) for k in modelled[:14]],
             "kernel_time_share": {k: round(v[1] / tot_ms, 4) for k, v in top[:14]},

@@ -256,6 +256,9 @@ int b200ctr_attn_tc_bwd(const float* qkv, const float* relmean, int max_len, con
  * per sample by a power of two.  Under torch autocast the reference rounds scores and probabilities to bf16 (8 bits);
  * fp16 keeps 11.  Same keep-word count (b200ctr_attn_tc_keep_words) but its own bit layout: pair the h16 forward with
  * the h16 backward.  Dropout masks are identical to the other attention kernels'.                                     */
+/* the h16 backward runs two CTAs per sample (four heads each): its drelmean is a ZEROED (b200ctr_attn_h16_drel_rows(B),
+ * 2*max_len+1) matrix of per-CTA partial rows (column-summed in row order, like the others').                           */
+int64_t b200ctr_attn_h16_drel_rows(int64_t B);
 int b200ctr_attn_h16_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D,
                          float* o, float* lse, uint32_t* keep, b200ctr_dropout_t drop, void* stream);
 int b200ctr_attn_h16_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,

@@ -12,11 +12,12 @@ $CMD > $OUT/${TAG}_plain.json 2> $OUT/${TAG}_plain.err || { echo "plain run fail
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu1.log 2>&1
 # (2) full counter set on the 36 fused / retrieval launches of the 4th step (3 x [attn fwd, attn bwd, ffn fwd, ffn bwd1, ffn bwd2,
 #     2 lin_fwd, 2 lin_bwd] + 2 fm + 5 gemm_tma + retrieve fwd / bwd)
-ncu --set full --clock-control none -k regex:'attn_tc|attn_mma|ffn_|lin_fwd|lin_bwd|fm_fwd|fm_bwd|gemm_tma|retrieve_fwd|retrieve_bwd' \
+ncu --set full --clock-control none -k regex:'attn_tc|attn_h16|attn_mma|ffn_|lin_fwd|lin_bwd|fm_fwd|fm_bwd|gemm_tma|retrieve_fwd|retrieve_bwd' \
     --launch-skip 108 -c 36 -o $OUT/${TAG}_top $CMD > $OUT/${TAG}_ncu2.log 2>&1
 ncu -i $OUT/${TAG}_top.ncu-rep --page raw --csv > $OUT/${TAG}_top_raw.csv 2>/dev/null
 rm -f $OUT/${TAG}_top.ncu-rep
-# (3) the fp32 mode's split-precision GEMMs (one step's worth), with source correlation for the dominant shape
+# (3) the fp32 mode's split-precision GEMMs (one step's worth), with source correlation for the dominant shape (SKIP_FP32=1 skips)
+[ -n "$SKIP_FP32" ] && { ls -la $OUT/${TAG}_*; exit 0; }
 CMD32="python bench.py --amp none --quick --steps 2 --warmup 3 --no-cpu-baseline --batches 8"
 $CMD32 > $OUT/${TAG}_plain32.json 2> $OUT/${TAG}_plain32.err || { echo "fp32 plain run failed"; exit 1; }
 ncu --set full --clock-control none -k regex:'gemm_tc' --launch-skip 200 -c 16 -o $OUT/${TAG}_gemm32 $CMD32 > $OUT/${TAG}_ncu3.log 2>&1

@@ -13,7 +13,7 @@ import re
 import sys
 
 FAMILIES = [
-    (r"attn_tc_bwd_kernel", "attn_tc_bwd"), (r"attn_tc_fwd_kernel", "attn_tc_fwd"), (r"attn_mma_bwd", "attn_umma_bwd"),
+    (r"attn_(tc|h16)_bwd_kernel", "attn_tc_bwd"), (r"attn_(tc|h16)_fwd_kernel", "attn_tc_fwd"), (r"attn_mma_bwd", "attn_umma_bwd"),
     (r"attn_mma_fwd", "attn_umma_fwd"), (r"ffn_fwd_kernel", "ffn_fwd"), (r"ffn_bwd1_kernel", "ffn_bwd1"), (r"ffn_bwd2_kernel", "ffn_bwd2"),
     (r"ffn_bwd_kernel", "ffn_bwd"), (r"lin_fwd_kernel<192", "inproj_fwd"), (r"lin_fwd_kernel<64", "outproj_norm_fwd"),
     (r"lin_bwd_kernel<192", "inproj_bwd"), (r"lin_bwd_kernel<64", "outproj_norm_bwd"), (r"fm_fwd_kernel", "fm_fused_fwd"),

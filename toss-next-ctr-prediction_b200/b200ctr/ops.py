@@ -579,10 +579,12 @@ def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=N
     out_bf16 = bool(out_bf16 and use_tc)
     dqkv = torch.empty(qkv.shape, device=qkv.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
     drel_out = drelmean
-    if drelmean is not None:      # the kernels write one partial row per sample (no float atomics); summed in sample order below
-        drelmean = torch.zeros((B, 2 * max_len + 1), device=qkv.device, dtype=torch.float32)
+    h16 = use_tc and _attn_impl(impl) == "h16"
+    if drelmean is not None:      # the kernels write one partial row per CTA (no float atomics); summed in row order below
+        rows = int(lib.b200ctr_attn_h16_drel_rows(B)) if h16 else B
+        drelmean = torch.zeros((rows, 2 * max_len + 1), device=qkv.device, dtype=torch.float32)
     if use_tc:
-        fn = lib.b200ctr_attn_h16_bwd if _attn_impl(impl) == "h16" else lib.b200ctr_attn_tc_bwd
+        fn = lib.b200ctr_attn_h16_bwd if h16 else lib.b200ctr_attn_tc_bwd
         _run("attn_tc_bwd", fn, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
              int(out_bf16), _p(drelmean), _p(keep), dropout, _stream())
     else:

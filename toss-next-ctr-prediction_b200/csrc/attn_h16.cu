@@ -28,7 +28,7 @@ namespace b200ctr {
 
 constexpr int HA_D = 64;
 constexpr int HA_H = 8;
-constexpr int HA_THREADS = 256;
+constexpr int HA_HPC = 4;          // heads per CTA of the backward kernel (two CTAs per sample)
 constexpr float HA_LOG2E = 1.4426950408889634f, HA_LN2 = 0.6931471805599453f;
 constexpr uint32_t HA_ONES = 0x3c003c00u;       // half2(1, 1)
 
@@ -67,15 +67,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // 32-bit words = 2 TSW positions; TSW = 4 mod 8).  A unit = (row pair rp, 4 dims c): two float4 loads per image, four packed
 // stores; the lanes of a warp are 16 row pairs x 2 dim quads, which makes the stores bank-conflict free (16 * odd * cl + rp)
 // and the loads whole 32-byte sectors.  Rows >= K are zero.
+// QD = dim quads the CTA stages (16 = all 8 heads, 8 = the 4 heads of a head-split CTA)
 struct HaUnit { int c, rp; bool act; };
-template <int KP>
+template <int KP, int QD>
 __device__ __forceinline__ HaUnit ha_unit(int u) {
   constexpr int RG = (KP / 2 + 15) / 16;
   HaUnit r;
   const int cl = u & 1, rpl = (u >> 1) & 15, rest = u >> 5;
-  r.c = (rest & 7) * 2 + cl;
-  r.rp = (rest >> 3) * 16 + rpl;
-  r.act = u < RG * 256 && r.rp < KP / 2;
+  r.c = (rest % (QD / 2)) * 2 + cl;
+  r.rp = (rest / (QD / 2)) * 16 + rpl;
+  r.act = u < RG * 16 * QD && r.rp < KP / 2;
   return r;
 }
 __device__ __forceinline__ float ha_absmax4(float m, const float4& x) {
@@ -90,9 +91,9 @@ __device__ __forceinline__ void ha_store_T(uint32_t* dst, int TSW, int c, int rp
 }
 // q (scaled), k, v of the sample; the six 128-bit loads of a unit (twelve with two units per thread) are all in flight
 // before the first conversion: the staging phase is pure load latency.  Returns the thread's max |v|.
-template <int NTH, int KP>
+template <int NTH, int KP, int QD>
 __device__ __forceinline__ float ha_stage_qkv(uint32_t* qT, uint32_t* kT, uint32_t* vT, const float* __restrict__ base, int K, float qscale) {
-  constexpr int RG = (KP / 2 + 15) / 16, UPT = (RG * 256 + NTH - 1) / NTH, TSW = (KP + 8) / 2;
+  constexpr int RG = (KP / 2 + 15) / 16, UPT = (RG * 16 * QD + NTH - 1) / NTH, TSW = (KP + 8) / 2;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   float vmax = 0.f;
 #pragma unroll
@@ -100,7 +101,7 @@ __device__ __forceinline__ float ha_stage_qkv(uint32_t* qT, uint32_t* kT, uint32
     float4 x[2][3][2];
 #pragma unroll
     for (int ii = 0; ii < 2; ++ii) {
-      const HaUnit un = ha_unit<KP>(threadIdx.x + (it0 + ii) * NTH);
+      const HaUnit un = ha_unit<KP, QD>(threadIdx.x + (it0 + ii) * NTH);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int row = 2 * un.rp + r;
@@ -111,7 +112,7 @@ __device__ __forceinline__ float ha_stage_qkv(uint32_t* qT, uint32_t* kT, uint32
     }
 #pragma unroll
     for (int ii = 0; ii < 2; ++ii) {
-      const HaUnit un = ha_unit<KP>(threadIdx.x + (it0 + ii) * NTH);
+      const HaUnit un = ha_unit<KP, QD>(threadIdx.x + (it0 + ii) * NTH);
       if (it0 + ii < UPT && un.act) {
         ha_store_T(qT, TSW, un.c, un.rp, x[ii][0][0], x[ii][0][1], qscale, qscale);
         ha_store_T(kT, TSW, un.c, un.rp, x[ii][1][0], x[ii][1][1], 1.f, 1.f);
@@ -151,35 +152,38 @@ __device__ __forceinline__ void ha_key_masks(int kc, int K, uint32_t& andm, uint
   orm = (v0 ? 0u : 0xfc00u) | (v1 ? 0u : 0xfc000000u);
 }
 
-// NT = number of 8-key tiles (keys padded to a multiple of 16)
+// NT = number of 8-key tiles (keys padded to a multiple of 16).  Like the backward, two CTAs per sample with four heads each
+// (one warp per head): half the staging per CTA, twice as many CTAs to hide it behind.
 template <int NT, bool DROP>
-__global__ void __launch_bounds__(HA_THREADS, (NT <= 14 ? 4 : 3))
+__global__ void __launch_bounds__(32 * HA_HPC, (NT <= 14 ? 8 : 6))
 attn_h16_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, int K,
                     float* __restrict__ o, float* __restrict__ lse, uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
   constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2, NW = (NT + 7) / 8, TS = Kp + 8, TSW = TS / 2, NBP = 2 * Kp + 16;
   constexpr bool KEEP_S = NT <= 8;
   extern __shared__ __align__(16) uint32_t sm_u[];
-  uint32_t* qT = sm_u;                       // [64][TSW]  (q / sqrt(hd) * log2 e)^T
-  uint32_t* kT = qT + 64 * TSW;
-  uint32_t* vT = kT + 64 * TSW;
-  uint32_t* bp = vT + 64 * TSW;              // [NBP]
-  uint32_t* keys = bp + NBP;                 // [H][Kp] dropout row keys (DROP only)
-  const int64_t b = blockIdx.x;
-  const float* base = qkv + b * (int64_t)K * 3 * HA_D;
-  ha_stage_qkv<HA_THREADS, Kp>(qT, kT, vT, base, K, rsqrtf(8.f) * HA_LOG2E);
-  ha_fill_bias<HA_THREADS>(bp, NBP, relmean, max_len, K);
+  constexpr int HPC = HA_HPC, NTH = 32 * HA_HPC;
+  uint32_t* qT = sm_u;                       // [8 HPC][TSW]  (q / sqrt(hd) * log2 e)^T of this CTA's heads
+  uint32_t* kT = qT + 8 * HPC * TSW;
+  uint32_t* vT = kT + 8 * HPC * TSW;
+  uint32_t* bp = vT + 8 * HPC * TSW;         // [NBP]
+  uint32_t* keys = bp + NBP;                 // [HPC][Kp] dropout row keys (DROP only)
+  const int64_t b = blockIdx.x / (HA_H / HPC);
+  const int hbase = (int)(blockIdx.x % (HA_H / HPC)) * HPC;
+  const float* base = qkv + b * (int64_t)K * 3 * HA_D + hbase * 8;
+  ha_stage_qkv<NTH, Kp, 2 * HPC>(qT, kT, vT, base, K, rsqrtf(8.f) * HA_LOG2E);
+  ha_fill_bias<NTH>(bp, NBP, relmean, max_len, K);
   if (DROP)
-    for (int i = threadIdx.x; i < HA_H * Kp; i += HA_THREADS) {
-      const int h = i / Kp, r = i % Kp;
-      keys[i] = r < K ? drop_row_key(drop, ((uint64_t)b * HA_H + h) * K + r) : 0u;
+    for (int i = threadIdx.x; i < HPC * Kp; i += NTH) {
+      const int hl = i / Kp, r = i % Kp;
+      keys[i] = r < K ? drop_row_key(drop, ((uint64_t)b * HA_H + hbase + hl) * K + r) : 0u;
     }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int h = warp;
+  const int hl = warp, h = hbase + hl;
   const DropCtx dctx = drop_ctx(drop);
   const uint32_t thr2 = dctx.thr | (dctx.thr << 16);
   // ldmatrix lane addresses (bytes): row (h * 8 + (lane & 7)) of the image, position offset 8 * ((lane >> 3) & 1)
-  const uint32_t lrow = (uint32_t)(((h * 8 + (lane & 7)) * TS + 8 * ((lane >> 3) & 1)) * 2);
+  const uint32_t lrow = (uint32_t)(((hl * 8 + (lane & 7)) * TS + 8 * ((lane >> 3) & 1)) * 2);
   const uint32_t q_addr = smem_u32(qT) + lrow, k_addr = smem_u32(kT) + lrow, v_addr = smem_u32(vT) + lrow;
   uint32_t andm[2], orm[2];
   ha_key_masks(8 * (NT - 2) + 2 * t, K, andm[0], orm[0]);
@@ -229,7 +233,7 @@ attn_h16_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
     const uint32_t nma = h2_dup_lo(pk) ^ 0x80008000u, nmb = h2_dup_hi(pk) ^ 0x80008000u;      // -max, both halves
     float oc[4] = {0.f, 0.f, 0.f, 0.f}, ls[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t keya = 0u, keyb = 0u;
-    if (DROP) { keya = keys[h * Kp + qa]; keyb = keys[h * Kp + qb]; }
+    if (DROP) { keya = keys[hl * Kp + qa]; keyb = keys[hl * Kp + qb]; }
     uint32_t kw[NW];
 #pragma unroll
     for (int w = 0; w < NW; ++w) kw[w] = 0u;
@@ -291,47 +295,51 @@ __device__ __forceinline__ void ha_store2(float* base, int as_bf16, int64_t off,
 }
 
 // ---- backward ---------------------------------------------------------------------------------------------------------
-// warps = (head, key part): the KS parts of a head own disjoint runs of 16-key blocks (dK / dV accumulators in registers),
-// dQ is summed over the parts through a shared-memory hand-off.  KS = 1 up to 64 keys, 2 above.
+// TWO CTAs per sample, four heads each (HA_HPC): a CTA stages only its heads' 32 columns of q / k / v / dO / o, so the per-sample
+// staging phase (pure global-load latency) is half as long and twice as many, smaller CTAs interleave it with the others'
+// compute.  warps = (head, key part): the KS parts of a head own disjoint runs of 16-key blocks (dK / dV accumulators in
+// registers), dQ is summed over the parts through a shared-memory hand-off.  KS = 1 up to 64 keys, 2 above.
+// drelmean: one partial row per CTA = 2 B rows (b200ctr_attn_h16_drel_rows).
 // DROP: dropout on; KEEP: the keep flags come from the words the forward stored (otherwise re-hashed: same mask).
 template <int NT, int KS, bool DROP, bool KEEP>
-__global__ void __launch_bounds__(HA_THREADS * KS, (KS == 1 ? 3 : 1))
+__global__ void __launch_bounds__(32 * HA_HPC * KS, (KS == 1 ? 6 : 2))
 attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, const float* __restrict__ o,
                     const float* __restrict__ lse, const float* __restrict__ d_o, int K, float* __restrict__ dqkv, int dq16,
                     float* __restrict__ drelmean, const uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
   constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2, NW = (NT + 7) / 8, TS = Kp + 8, TSW = TS / 2, NBP = 2 * Kp + 16;
-  constexpr int NTH = HA_THREADS * KS;
+  constexpr int NTH = 32 * HA_HPC * KS, HPC = HA_HPC, QD = 2 * HA_HPC;
   constexpr int NBW = (NB + KS - 1) / KS;                     // 16-key blocks per warp
   constexpr int NTW = 2 * NBW;                                 // 8-key tiles per warp
   constexpr int KPA = 16 * NBW * KS;                           // padded key extent covered by the dbias slots (>= Kp)
   constexpr int DBS = 2 * KPA + 2;
   extern __shared__ __align__(16) uint32_t sm_u[];
-  uint32_t* qT = sm_u;                       // (q / sqrt(hd) * log2 e)^T
-  uint32_t* kT = qT + 64 * TSW;
-  uint32_t* vT = kT + 64 * TSW;
-  uint32_t* doT = vT + 64 * TSW;             // (dO * f / (1-p) * 2^e)^T
-  uint32_t* mneg = doT + 64 * TSW;           // [H][Kp] half2(-m', -m')
-  uint32_t* dneg = mneg + HA_H * Kp;         // [H][Kp] half2(-D', -D')
-  uint32_t* bp = dneg + HA_H * Kp;           // [NBP]
-  float* dbias = reinterpret_cast<float*>(bp + NBP);            // [8 * KS][DBS], index (key - query) + KPA
-  float* dqx = dbias + 8 * KS * DBS;                            // [H][2 (query-tile parity)][KS - 1][128]
-  float* red = dqx + (KS > 1 ? HA_H * 2 * (KS - 1) * 128 : 0);  // [64] block-reduction scratch
-  uint32_t* keys = reinterpret_cast<uint32_t*>(red + 64);       // [H][Kp] (DROP && !KEEP)
-  const int64_t b = blockIdx.x;
-  const float* base = qkv + b * (int64_t)K * 3 * HA_D;
-  const float* dob = d_o + b * (int64_t)K * HA_D;
-  const float* ob = o + b * (int64_t)K * HA_D;
+  uint32_t* qT = sm_u;                       // [8 HPC][TSW]  (q / sqrt(hd) * log2 e)^T of this CTA's heads
+  uint32_t* kT = qT + 8 * HPC * TSW;
+  uint32_t* vT = kT + 8 * HPC * TSW;
+  uint32_t* doT = vT + 8 * HPC * TSW;        // (dO * f / (1-p) * 2^e)^T
+  uint32_t* mneg = doT + 8 * HPC * TSW;      // [HPC][Kp] half2(-m', -m')
+  uint32_t* dneg = mneg + HPC * Kp;          // [HPC][Kp] half2(-D', -D')
+  uint32_t* bp = dneg + HPC * Kp;            // [NBP]
+  float* dbias = reinterpret_cast<float*>(bp + NBP);            // [HPC * KS][DBS], index (key - query) + KPA
+  float* dqx = dbias + HPC * KS * DBS;                          // [HPC][2 (query-tile parity)][KS - 1][128]
+  float* red = dqx + (KS > 1 ? HPC * 2 * (KS - 1) * 128 : 0);   // [64] block-reduction scratch
+  uint32_t* keys = reinterpret_cast<uint32_t*>(red + 64);       // [HPC][Kp] (DROP && !KEEP)
+  const int64_t b = blockIdx.x / (HA_H / HPC);
+  const int hbase = (int)(blockIdx.x % (HA_H / HPC)) * HPC, dim0 = hbase * 8;      // first head / first column of this CTA
+  const float* base = qkv + b * (int64_t)K * 3 * HA_D + dim0;
+  const float* dob = d_o + b * (int64_t)K * HA_D + dim0;
+  const float* ob = o + b * (int64_t)K * HA_D + dim0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const DropCtx dctx = drop_ctx(drop);
   // dO, the head-partial dot product dO . o (D = sum_j P_ij c_ij dP_ij = dO_i . o_i holds with the dropped-and-rescaled o the
   // forward wrote) and the log-sum-exp of the thread's units stay in registers across the barrier that agrees on the scale
-  constexpr int RG = (Kp / 2 + 15) / 16, UPT = (RG * 256 + NTH - 1) / NTH;
+  constexpr int RG = (Kp / 2 + 15) / 16, UPT = (RG * 16 * QD + NTH - 1) / NTH;
   float4 xd[UPT][2];
   float Ls[UPT][2], dro[UPT][2];
   float domax = 0.f;
 #pragma unroll
   for (int it = 0; it < UPT; ++it) {
-    const HaUnit un = ha_unit<Kp>(threadIdx.x + it * NTH);
+    const HaUnit un = ha_unit<Kp, QD>(threadIdx.x + it * NTH);
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int row = 2 * un.rp + r;
@@ -340,23 +348,23 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
       if (ok) {
         xd[it][r] = *reinterpret_cast<const float4*>(dob + (int64_t)row * HA_D + 4 * un.c);
         const float4 oo = *reinterpret_cast<const float4*>(ob + (int64_t)row * HA_D + 4 * un.c);
-        Ls[it][r] = lse[(b * HA_H + (un.c >> 1)) * (int64_t)K + row];
+        Ls[it][r] = lse[(b * HA_H + hbase + (un.c >> 1)) * (int64_t)K + row];
         dro[it][r] = xd[it][r].x * oo.x + xd[it][r].y * oo.y + xd[it][r].z * oo.z + xd[it][r].w * oo.w;
       }
     }
   }
-  float vmax = ha_stage_qkv<NTH, Kp>(qT, kT, vT, base, K, rsqrtf(8.f) * HA_LOG2E);
+  float vmax = ha_stage_qkv<NTH, Kp, QD>(qT, kT, vT, base, K, rsqrtf(8.f) * HA_LOG2E);
 #pragma unroll
   for (int it = 0; it < UPT; ++it) domax = ha_absmax4(ha_absmax4(domax, xd[it][0]), xd[it][1]);
   vmax = warp_max(vmax); domax = warp_max(domax);
   if (lane == 0) { red[warp] = vmax; red[32 + warp] = domax; }
   ha_fill_bias<NTH>(bp, NBP, relmean, max_len, K);
   if (drelmean)
-    for (int i = threadIdx.x; i < 8 * KS * DBS; i += NTH) dbias[i] = 0.f;
+    for (int i = threadIdx.x; i < HPC * KS * DBS; i += NTH) dbias[i] = 0.f;
   if (DROP && !KEEP)
-    for (int i = threadIdx.x; i < HA_H * Kp; i += NTH) {
-      const int h = i / Kp, r = i % Kp;
-      keys[i] = r < K ? drop_row_key(drop, ((uint64_t)b * HA_H + h) * K + r) : 0u;
+    for (int i = threadIdx.x; i < HPC * Kp; i += NTH) {
+      const int hl = i / Kp, r = i % Kp;
+      keys[i] = r < K ? drop_row_key(drop, ((uint64_t)b * HA_H + hbase + hl) * K + r) : 0u;
     }
   __syncthreads();
   // per-sample power of two: |dP'|, |D'| <= 8 max|dO'| max|V| are placed below 2^9, so |dS| < 2^10, a dbias slot (up to ten
@@ -373,7 +381,7 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
   // dO' = dO * f * spow / (1-p), f = 2^(m' - lse*log2e), m' = the log-sum-exp rounded to fp16;  D' = dO' . o over the head
 #pragma unroll
   for (int it = 0; it < UPT; ++it) {
-    const HaUnit un = ha_unit<Kp>(threadIdx.x + it * NTH);
+    const HaUnit un = ha_unit<Kp, QD>(threadIdx.x + it * NTH);
     float m[2], f[2], d[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -388,19 +396,19 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
     if (un.act) {
       ha_store_T(doT, TSW, un.c, un.rp, xd[it][0], xd[it][1], f[0], f[1]);
       if ((un.c & 1) == 0) {
-        const int hh = un.c >> 1, r0 = 2 * un.rp;
+        const int hh = un.c >> 1, r0 = 2 * un.rp;          // local head
         mneg[hh * Kp + r0] = h2_pack(-m[0], -m[0]); mneg[hh * Kp + r0 + 1] = h2_pack(-m[1], -m[1]);
         dneg[hh * Kp + r0] = h2_pack(-d[0], -d[0]); dneg[hh * Kp + r0 + 1] = h2_pack(-d[1], -d[1]);
       }
     }
   }
   __syncthreads();
-  const int h = warp & 7, part = warp >> 3;                     // (head, key part)
+  const int hl = warp % HPC, part = warp / HPC, h = hbase + hl;  // (local head, key part), global head
   const int jb0 = part * NBW;                                   // first 16-key block of this warp
   const uint32_t thr2 = dctx.thr | (dctx.thr << 16);
   const uint32_t tphi = (uint32_t)t * 0x9E3779B9U;
   // ldmatrix lane addresses (bytes).  "ab": matrices (qT pos +0, qT pos +8, doT pos +0, doT pos +8); "kv": same for (kT, vT)
-  const uint32_t lrow = (uint32_t)(((h * 8 + (lane & 7)) * TS + 8 * ((lane >> 3) & 1)) * 2);
+  const uint32_t lrow = (uint32_t)(((hl * 8 + (lane & 7)) * TS + 8 * ((lane >> 3) & 1)) * 2);
   const uint32_t ab_addr = (lane < 16 ? smem_u32(qT) : smem_u32(doT)) + lrow;
   const uint32_t kv_addr = (lane < 16 ? smem_u32(kT) : smem_u32(vT)) + lrow;
   uint32_t andm[2], orm_unused;
@@ -441,14 +449,14 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
     uint32_t aq[2], ad[2], bq0, bq1, bd0, bd1;
     ldsm_x4_t(aq[0], aq[1], ad[0], ad[1], ab_addr + 32 * i);     // A fragments of S = Q.K^T and dP = dO'.V^T
     ldsm_x4(bq0, bq1, bd0, bd1, ab_addr + 32 * i);               // B fragments (16 queries x head dim) of dK += dS^T.Q, dV += P^T.dO'
-    const uint32_t mna = mneg[h * Kp + qa], mnb = mneg[h * Kp + qb], dna = dneg[h * Kp + qa], dnb = dneg[h * Kp + qb];
+    const uint32_t mna = mneg[hl * Kp + qa], mnb = mneg[hl * Kp + qb], dna = dneg[hl * Kp + qa], dnb = dneg[hl * Kp + qb];
     uint32_t kw[NW];
     if (DROP && KEEP) {      // this query tile's keep words were requested one iteration ago: the loop never waits on global memory
 #pragma unroll
       for (int w = 0; w < NW; ++w) { kw[w] = kwn[w]; kwn[w] = __ldg(keep + ha_keep_index(b, h, MT, min(i + 1, MT - 1), NW, w, lane)); }
     }
     uint32_t keya = 0u, keyb = 0u;
-    if (DROP && !KEEP) { keya = keys[h * Kp + qa]; keyb = keys[h * Kp + qb]; }
+    if (DROP && !KEEP) { keya = keys[hl * Kp + qa]; keyb = keys[hl * Kp + qb]; }
     const uint32_t* bpa = bp + 8 + 2 * t + (K - 1) - min(qa, K - 1) + 16 * jb0;     // + 8 * local tile
     uint32_t cprev = bpa[-8];
     float dq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -505,12 +513,12 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
     {
       const float qs = rsqrtf(8.f) * rspow;
       if (KS > 1) {
-        float2* xq = reinterpret_cast<float2*>(dqx + (size_t)((h * 2 + (i & 1)) * (KS - 1)) * 128);
+        float2* xq = reinterpret_cast<float2*>(dqx + (size_t)((hl * 2 + (i & 1)) * (KS - 1)) * 128);
         if (part != 0) {
           xq[(part - 1) * 64 + lane] = make_float2(dq[0], dq[1]);            // row g, dims 2t, 2t+1
           xq[(part - 1) * 64 + 32 + lane] = make_float2(dq[2], dq[3]);       // row g + 8
         }
-        asm volatile("bar.sync %0, %1;" :: "r"(h + 1), "r"(32 * KS) : "memory");   // the KS warps of head h
+        asm volatile("bar.sync %0, %1;" :: "r"(hl + 1), "r"(32 * KS) : "memory");   // the KS warps of this head
         if (part == 0) {
 #pragma unroll
           for (int pp = 0; pp < KS - 1; ++pp) {
@@ -558,10 +566,10 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
     for (int tt = threadIdx.x; tt < 2 * K - 1; tt += NTH) {
       const int d = tt - (K - 1);
       float acc = 0.f;
-      for (int w = 0; w < 8 * KS; ++w) acc += dbias[w * DBS + d + KPA];
+      for (int w = 0; w < HPC * KS; ++w) acc += dbias[w * DBS + d + KPA];
       // per-sample partial row (zero-initialised by the caller; |d| <= K - 1 < max_len: one writer per slot), summed in sample
       // order afterwards (b200ctr_colsum): no float atomics
-      drelmean[b * (int64_t)(2 * max_len + 1) + min(max(d, -max_len), max_len) + max_len] = acc * rspow;
+      drelmean[blockIdx.x * (int64_t)(2 * max_len + 1) + min(max(d, -max_len), max_len) + max_len] = acc * rspow;
     }
   }
 }
@@ -583,11 +591,12 @@ static int ha_launch_fwd(const float* qkv, const float* relmean, int max_len, in
                          uint32_t* keep, b200ctr_dropout_t drop, cudaStream_t st) {
   constexpr int Kp = NT * 8, TSW = (Kp + 8) / 2;
   const bool on = drop.p > 0.f;
-  const size_t smem = ((size_t)3 * 64 * TSW + 2 * Kp + 16 + (on ? HA_H * Kp : 0)) * 4;
+  const size_t smem = ((size_t)3 * 8 * HA_HPC * TSW + 2 * Kp + 16 + (on ? HA_HPC * Kp : 0)) * 4;
   int rc = on ? ha_set_smem((const void*)attn_h16_fwd_kernel<NT, true>, smem) : ha_set_smem((const void*)attn_h16_fwd_kernel<NT, false>, smem);
   if (rc) return rc;
-  if (on) attn_h16_fwd_kernel<NT, true><<<(unsigned)B, HA_THREADS, smem, st>>>(qkv, relmean, max_len, K, o, lse, keep, drop);
-  else attn_h16_fwd_kernel<NT, false><<<(unsigned)B, HA_THREADS, smem, st>>>(qkv, relmean, max_len, K, o, lse, keep, drop);
+  const unsigned grid = (unsigned)(B * (HA_H / HA_HPC));
+  if (on) attn_h16_fwd_kernel<NT, true><<<grid, 32 * HA_HPC, smem, st>>>(qkv, relmean, max_len, K, o, lse, keep, drop);
+  else attn_h16_fwd_kernel<NT, false><<<grid, 32 * HA_HPC, smem, st>>>(qkv, relmean, max_len, K, o, lse, keep, drop);
   return B200CTR_OK;
 }
 
@@ -597,8 +606,8 @@ static int ha_launch_bwd_inst(size_t smem, const float* qkv, const float* relmea
                               b200ctr_dropout_t drop, cudaStream_t st) {
   int rc = ha_set_smem((const void*)attn_h16_bwd_kernel<NT, KS, DROP, KEEP>, smem);
   if (rc) return rc;
-  attn_h16_bwd_kernel<NT, KS, DROP, KEEP><<<(unsigned)B, HA_THREADS * KS, smem, st>>>(qkv, relmean, max_len, o, lse, d_o, K, dqkv,
-                                                                                      dq16, drelmean, keep, drop);
+  attn_h16_bwd_kernel<NT, KS, DROP, KEEP><<<(unsigned)(B * (HA_H / HA_HPC)), 32 * HA_HPC * KS, smem, st>>>(
+      qkv, relmean, max_len, o, lse, d_o, K, dqkv, dq16, drelmean, keep, drop);
   return B200CTR_OK;
 }
 
@@ -609,8 +618,8 @@ static int ha_launch_bwd(const float* qkv, const float* relmean, int max_len, co
   constexpr int KS = NT <= 8 ? 1 : 2;
   constexpr int Kp = NT * 8, TSW = (Kp + 8) / 2, NBW = (NT / 2 + KS - 1) / KS, KPA = 16 * NBW * KS;
   const bool on = drop.p > 0.f, use_keep = on && keep != nullptr;
-  const size_t smem = ((size_t)4 * 64 * TSW + 2 * HA_H * Kp + 2 * Kp + 16 + (size_t)(8 * KS) * (2 * KPA + 2) +
-                       (KS > 1 ? HA_H * 2 * (KS - 1) * 128 : 0) + 64 + (on && !use_keep ? HA_H * Kp : 0)) * 4;
+  const size_t smem = ((size_t)4 * 8 * HA_HPC * TSW + 2 * HA_HPC * Kp + 2 * Kp + 16 + (size_t)(HA_HPC * KS) * (2 * KPA + 2) +
+                       (KS > 1 ? HA_HPC * 2 * (KS - 1) * 128 : 0) + 64 + (on && !use_keep ? HA_HPC * Kp : 0)) * 4;
 #define HA_ARGS smem, qkv, relmean, max_len, o, lse, d_o, B, K, dqkv, dq16, drelmean, keep, drop, st
   if (!on) return ha_launch_bwd_inst<NT, KS, false, false>(HA_ARGS);
   if (use_keep) return ha_launch_bwd_inst<NT, KS, true, true>(HA_ARGS);
@@ -632,6 +641,8 @@ using namespace b200ctr;
       set_error("attention (packed-half path): top_k=%d > 160 is not built", K);     \
       return B200CTR_E_UNSUPPORTED_SHAPE;                                            \
   }
+
+extern "C" int64_t b200ctr_attn_h16_drel_rows(int64_t B) { return B * (HA_H / HA_HPC); }
 
 extern "C" int b200ctr_attn_h16_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D, float* o,
                                     float* lse, uint32_t* keep, b200ctr_dropout_t drop, void* stream) {
