@@ -155,7 +155,7 @@ __device__ __forceinline__ void ha_key_masks(int kc, int K, uint32_t& andm, uint
 // NT = number of 8-key tiles (keys padded to a multiple of 16).  Like the backward, two CTAs per sample with four heads each
 // (one warp per head): half the staging per CTA, twice as many CTAs to hide it behind.
 template <int NT, bool DROP>
-__global__ void __launch_bounds__(32 * HA_HPC, (NT <= 14 ? 8 : 6))
+__global__ void __launch_bounds__(32 * HA_HPC, (NT <= 14 ? 32 : 24) / HA_HPC)
 attn_h16_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, int K,
                     float* __restrict__ o, float* __restrict__ lse, uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
   constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2, NW = (NT + 7) / 8, TS = Kp + 8, TSW = TS / 2, NBP = 2 * Kp + 16;
@@ -302,7 +302,7 @@ __device__ __forceinline__ void ha_store2(float* base, int as_bf16, int64_t off,
 // drelmean: one partial row per CTA = 2 B rows (b200ctr_attn_h16_drel_rows).
 // DROP: dropout on; KEEP: the keep flags come from the words the forward stored (otherwise re-hashed: same mask).
 template <int NT, int KS, bool DROP, bool KEEP>
-__global__ void __launch_bounds__(32 * HA_HPC * KS, (KS == 1 ? 6 : 2))
+__global__ void __launch_bounds__(32 * HA_HPC * KS, (KS == 1 ? 24 : 8) / HA_HPC)
 attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, const float* __restrict__ o,
                     const float* __restrict__ lse, const float* __restrict__ d_o, int K, float* __restrict__ dqkv, int dq16,
                     float* __restrict__ drelmean, const uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
