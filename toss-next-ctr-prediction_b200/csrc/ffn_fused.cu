@@ -259,11 +259,11 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
           if (dctx.on) {
             const uint32_t mk = drop_keep_mask2(drop_pair_hash(rkey, (uint32_t)(n0 >> 1) + jp), thr2);
             f &= mk;
-            kb |= mk & ((1u << (2 * jp)) | (1u << (2 * jp + 17)));      // bit 2jp <- even column, bit 16 + 2jp + 1 <- odd column
+            kb |= mk & (0x00010001u << (2 * jp));      // bit 2jp <- even column, bit 16 + 2jp <- odd column
           }
           pk[jp] = f;
         }
-        kb |= kb >> 16;
+        kb = (kb & 0x5555u) | ((kb >> 15) & 0xAAAAu);      // stored word: bit j = keep flag of column j
         if (keep && dctx.on) keep[((tile * NC + c) * 4 + part) * FF_TM + r] = (uint16_t)kb;
         const int fb = g & 1;
         if (g >= 2) mbar_wait(smem_u32(&bars->fd_empty[fb]), ((g >> 1) - 1) & 1);
@@ -358,7 +358,7 @@ constexpr int FF_IN_BYTES = 2 * FF_A_BYTES;            // x1 tile + d_s2 tile (b
 constexpr int FF_BLK_BYTES = FF_TM * 128 * 2;          // 32 KB: 128 tokens x 128 hidden, bf16
 
 // W2 [64][hidden] fp32 -> per 64-column chunk an MN-major B operand (N = hidden within the chunk, K = d)
-__device__ __forceinline__ void ffn_stage_w2_mn(unsigned char* w2s, const float* __restrict__ w2, int hidden, int tid, int nt) {
+__device__ __forceinline__ void ffn_stage_w2_mn(unsigned char* w2s, const float* __restrict__ w2, int hidden, float scale, int tid, int nt) {
   const int hg_per_row = hidden >> 3;
   for (int u = tid; u < FF_D * hg_per_row; u += nt) {
     const int d = u / hg_per_row, hg = u % hg_per_row;
@@ -366,7 +366,8 @@ __device__ __forceinline__ void ffn_stage_w2_mn(unsigned char* w2s, const float*
     const float4 a = __ldg(p), b = __ldg(p + 1);
     const int c = hg >> 3, ng = hg & 7;
     *reinterpret_cast<uint4*>(w2s + c * FF_WCHUNK + ((d >> 3) * 8 + ng) * 128 + (d & 7) * 16) =
-        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+        make_uint4(pack_bf16(a.x * scale, a.y * scale), pack_bf16(a.z * scale, a.w * scale), pack_bf16(b.x * scale, b.y * scale),
+                   pack_bf16(b.z * scale, b.w * scale));
   }
 }
 
@@ -438,8 +439,9 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   ffn_stage_w1(w1s, w1, hidden, tid, FFW_NT);
-  ffn_stage_w2_mn(w2s, w2, hidden, tid, FFW_NT);
-  for (int i = tid; i < hidden; i += FFW_NT) b1s[i] = b1[i];
+  ffn_stage_w2_mn(w2s, w2, hidden, drop.p > 0.f ? 1.f / (1.f - drop.p) : 1.f, tid, FFW_NT);      // Q arrives times 1/(1-p)
+  uint32_t* b1h = reinterpret_cast<uint32_t*>(b1s);                // bias as half2 pairs
+  for (int i = tid; i < hidden / 2; i += FFW_NT) b1h[i] = h2_pack(b1[2 * i], b1[2 * i + 1]);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -500,13 +502,18 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
     float db1_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     uint32_t g = 0;
     const DropCtx dctx = drop_ctx(drop);
+    const uint32_t thr2 = dctx.thr | (dctx.thr << 16);
     for (int it = 0; it < n_it; ++it) {
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
       const int64_t m = tile * FF_TM + r;
       const uint32_t rkey = (!KEEP && dctx.on) ? drop_row_key(drop, (uint64_t)m) : 0u;
+      uint32_t kb_next = 0u;
+      if (KEEP) kb_next = keep[((tile * NC) * 4 + part) * FF_TM + r];
       for (int c = 0; c < NC; ++c, ++g) {
-        uint32_t kb = 0u;
-        if (KEEP) kb = keep[((tile * NC + c) * 4 + part) * FF_TM + r];      // issued before the wait: latency hidden
+        // keep flags of this chunk were requested one chunk ago (the load right before the wait was NOT hidden: 7 % of the
+        // kernel's stall samples sat on its first use)
+        const uint32_t kb16 = kb_next;
+        if (KEEP && c + 1 < NC) kb_next = keep[((tile * NC + c + 1) * 4 + part) * FF_TM + r];
         mbar_wait(smem_u32(&bars->pq_full), g & 1);
         tc_fence_after();
         uint32_t pv[16], qv[16];
@@ -517,27 +524,37 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->pq_empty));
         const int n0 = c * FF_HC + part * 16;
+        // GELU, GELU' and the mask on half2 pairs (h2_common.cuh; the forward's arithmetic), the products with Q -- gradient
+        // sized, outside fp16's range -- in fp32:  f = x Phi(x) & keep ;  dpre = Q (Phi(x) + x phi(x)) & keep
+        // (Q carries the 1/(1-p) through W2; f gets it below).  21 instructions per element instead of 36.
+        const uint4 bq0 = *reinterpret_cast<const uint4*>(b1h + (n0 >> 1)), bq1 = *reinterpret_cast<const uint4*>(b1h + (n0 >> 1) + 4);
+        const uint32_t bh[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
+        const uint32_t kb32 = (kb16 & 0x5555u) | ((kb16 & 0xAAAAu) << 15);      // pair jp: bits 2jp and 16 + 2jp
+        const uint32_t inv2 = h2_const_rt(dctx.inv);
         uint32_t fpk[8], dpk[8];
         float dp[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          float dsc[2] = {1.f, 1.f};
-          if (KEEP) { dsc[0] = (kb & (1u << j)) ? dctx.inv : 0.f; dsc[1] = (kb & (2u << j)) ? dctx.inv : 0.f; }
-          else if (dctx.on) drop_pair(dctx, rkey, (uint32_t)(n0 + j) >> 1, dsc[0], dsc[1]);
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float pre = __uint_as_float(pv[j + u]) + b1s[n0 + j + u];
-            float cdf;
-            const float gg = ffn_gelu_grad(pre, cdf);
-            const float f = pre * cdf * dsc[u];
-            dp[j + u] = __uint_as_float(qv[j + u]) * dsc[u] * gg;
-            pv[j + u] = __float_as_uint(f);
+        for (int jp = 0; jp < 8; ++jp) {
+          const uint32_t x = h2_add(h2_pack(__uint_as_float(pv[2 * jp]), __uint_as_float(pv[2 * jp + 1])), bh[jp]);
+          const uint32_t u = h2_min(h2_mul(x, x), h2_const(64.f));
+          uint32_t qq = h2_fma(u, h2_const(-3.2625e-4f), h2_const(0.036835f));
+          qq = h2_fma(u, qq, h2_const(0.797687f));
+          const uint32_t cdf = h2_fma(h2_tanh(h2_mul(x, qq)), h2_const(0.5f), h2_const(0.5f));
+          const uint32_t phi = h2_ex2(h2_fma(u, h2_const(-0.72134752f), h2_const(-1.3257480f)));      // exp(-x^2/2) / sqrt(2 pi)
+          uint32_t gg = h2_fma(x, phi, cdf), f = h2_mul(x, cdf);
+          if (KEEP) {
+            const uint32_t mk = h2_mask_from_signs(kb32 << (15 - 2 * jp));
+            gg &= mk;
+            f = h2_mul(f & mk, inv2);
+          } else if (dctx.on) {
+            const uint32_t mk = drop_keep_mask2(drop_pair_hash(rkey, (uint32_t)(n0 >> 1) + jp), thr2);
+            gg &= mk;
+            f = h2_mul(f & mk, inv2);
           }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          fpk[j >> 1] = pack_bf16(__uint_as_float(pv[j]), __uint_as_float(pv[j + 1]));
-          dpk[j >> 1] = pack_bf16(dp[j], dp[j + 1]);
+          dp[2 * jp] = __uint_as_float(qv[2 * jp]) * h2_lo(gg);
+          dp[2 * jp + 1] = __uint_as_float(qv[2 * jp + 1]) * h2_hi(gg);
+          fpk[jp] = pack_bf16(h2_lo(f), h2_hi(f));
+          dpk[jp] = pack_bf16(dp[2 * jp], dp[2 * jp + 1]);
         }
         const uint32_t bk = (uint32_t)it * NB + (uint32_t)(c >> 1);
         if ((c & 1) == 0 && bk >= 1) mbar_wait(smem_u32(&bars->blk_empty), (bk - 1) & 1);

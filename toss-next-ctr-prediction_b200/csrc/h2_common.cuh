@@ -35,6 +35,8 @@ __device__ __forceinline__ uint32_t h2_const(float c) {
   const __half2 v = __float2half2_rn(c);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
+// both halves = a run-time value
+__device__ __forceinline__ uint32_t h2_const_rt(float c) { return h2_pack(c, c); }
 // erf-GELU on a pair: x * Phi(x), Phi(x) ~= 0.5 + 0.5 tanh(x (a + b u + c u^2)), u = min(x^2, 64) -- the sigmoid fit of
 // ffn_fused.cu (|error| < 4.2e-5 in fp32) with its coefficients halved for the tanh form; in half arithmetic the result is
 // good to ~5e-4 relative for |f| > 0.1 and ~1e-3 absolute in the negative tail (bf16, its consumer's format, resolves 4e-3)
