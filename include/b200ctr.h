@@ -398,9 +398,10 @@ int b200ctr_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, 
                       const float* coef, float ema_decay, void* stream);
 /* multi-tensor form for the unmodified reference loop (separate parameter tensors): recs = device array of n_t records of six
  * 64-bit words {p, g, m, v, ema, n} (ema may be 0); chunk c covers elements [chunk_off[c], chunk_off[c] + chunk) of tensor
- * chunk_tensor[c].  mode 0 = AdamW as above (+ EMA where a record has a shadow), mode 1 = EMA only.                       */
+ * chunk_tensor[c].  mode 0 = AdamW as above (+ EMA where a record has a shadow), mode 1 = EMA only.  The betas are doubles:
+ * torch forms 1 - beta and the bias corrections from Python doubles, and float(0.999) is 1.3e-5 away in 1 - beta.           */
 int b200ctr_multi_adamw_ema(const void* recs, const int32_t* chunk_tensor, const int64_t* chunk_off, int64_t n_chunks,
-                            int64_t chunk, float lr, float wd, float beta1, float beta2, float eps, int64_t step,
+                            int64_t chunk, float lr, float wd, double beta1, double beta2, float eps, int64_t step,
                             const float* coef, float ema_decay, int mode, void* stream);
 /* sparse rows of a big table: rows listed in tok[n_slots] (duplicates + pad_id allowed).  owner[vocab] scratch. */
 int b200ctr_rows_claim(const int32_t* tok, int64_t n_slots, int pad_id, int32_t* owner, void* stream);

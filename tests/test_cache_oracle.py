@@ -59,3 +59,35 @@ def test_numeric_block_and_median():
     assert np.array_equal(M, np.array([[0, 1, 0], [1, 1, 0], [0, 1, 0], [0, 1, 1]], dtype=np.uint8))
     assert np.array_equal(X, np.array([[1, 0, 1e6], [2, 0, -1e6], [3, 0, 2], [2, 0, 2]], dtype=np.float32))
     assert co.median_ignore_missing(np.array([4, 1, 3, 2], np.float32)) == 2.5
+
+
+# ---- property tests (hypothesis): the parse rule and the two hash implementations on arbitrary inputs ------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.one_of(st.none(), st.lists(st.integers(0, 2 ** 31 - 1), max_size=40)), max_size=6), st.integers(1, 12),
+       st.integers(0, 5), st.integers(0, 3))
+def test_parse_seq_keeps_the_last_tokens_right_aligned(rows, L, pad, extra_commas):
+    strings = []
+    for toks in rows:
+        if toks is None:
+            strings.append(None)
+        else:
+            s = ",".join(map(str, toks))
+            strings.append("," * extra_commas + s.replace(",", "," * (1 + extra_commas % 2)) + "," * extra_commas)
+    got = co.parse_seq(strings, L, pad)
+    assert got.shape == (len(rows), L) and got.dtype == np.int32
+    for i, toks in enumerate(rows):
+        last = (toks or [])[-L:]
+        assert list(got[i, L - len(last):]) == last and all(v == pad for v in got[i, :L - len(last)])
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.binary(max_size=200), st.integers(0, 2 ** 32 - 1))
+def test_host_hash_equals_oracle_on_arbitrary_bytes(data, seed):
+    from b200ctr import _lib
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(data, max(len(data), 1))
+    got = lib.b200ctr_cache_hash_bytes_host(ctypes.cast(buf, ctypes.c_void_p), len(data), seed) & ((1 << 64) - 1)
+    assert got == co.hash_bytes(data, seed)

@@ -97,8 +97,8 @@ adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 struct MtRec { float* p; const float* g; float* m; float* v; float* ema; int64_t n; };
 __global__ void __launch_bounds__(256)
 multi_adamw_ema_kernel(const MtRec* __restrict__ recs, const int32_t* __restrict__ chunk_tensor, const int64_t* __restrict__ chunk_off,
-                       int64_t n_chunks, int64_t chunk, float lr, float wd, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-                       const float* __restrict__ coef, float ema_decay, int mode) {
+                       int64_t n_chunks, int64_t chunk, float lr, float wd, float omb1, float b2, float omb2, float eps, float bc1,
+                       float bc2_sqrt, const float* __restrict__ coef, float ema_decay, int mode) {
   const float c = coef ? coef[0] : 1.f;
   const float step_size = lr / bc1;
   for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
@@ -109,8 +109,10 @@ multi_adamw_ema_kernel(const MtRec* __restrict__ recs, const int32_t* __restrict
       if (mode == 0) {
         const float gi = r.g[i] * c;
         pi *= (1.f - lr * wd);
-        const float mi = r.m[i] + (gi - r.m[i]) * (1.f - b1);
-        const float vi = r.v[i] * b2 + (1.f - b2) * gi * gi;
+        // torch: exp_avg.lerp_(g, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2) with the weights formed in
+        // double on the host (1.f - 0.999f is 1.3e-5 away from float(1 - 0.999))
+        const float mi = r.m[i] + (gi - r.m[i]) * omb1;
+        const float vi = r.v[i] * b2 + omb2 * gi * gi;
         pi -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
         r.p[i] = pi; r.m[i] = mi; r.v[i] = vi;
       }
@@ -242,17 +244,18 @@ extern "C" int b200ctr_adamw_ema(float* p, const float* g, float* m, float* v, f
 }
 
 extern "C" int b200ctr_multi_adamw_ema(const void* recs, const int32_t* chunk_tensor, const int64_t* chunk_off, int64_t n_chunks,
-                                       int64_t chunk, float lr, float wd, float beta1, float beta2, float eps, int64_t step,
+                                       int64_t chunk, float lr, float wd, double beta1, double beta2, float eps, int64_t step,
                                        const float* coef, float ema_decay, int mode, void* stream) {
   B200_REQUIRE(recs && chunk_tensor && chunk_off && chunk > 0, B200CTR_E_INVALID_ARG, "multi_adamw_ema: null pointer");
   B200_REQUIRE(mode == 0 || mode == 1, B200CTR_E_INVALID_ARG, "multi_adamw_ema: mode %d", mode);
   B200_REQUIRE(mode == 1 || step >= 1, B200CTR_E_INVALID_ARG, "multi_adamw_ema: step must be >= 1");
   if (n_chunks == 0) return B200CTR_OK;
-  const double bc1 = mode == 0 ? 1.0 - pow((double)beta1, (double)step) : 1.0;
-  const double bc2 = mode == 0 ? 1.0 - pow((double)beta2, (double)step) : 1.0;
+  const double bc1 = mode == 0 ? 1.0 - pow(beta1, (double)step) : 1.0;
+  const double bc2 = mode == 0 ? 1.0 - pow(beta2, (double)step) : 1.0;
   const int grid = (int)std::min<int64_t>(n_chunks, (int64_t)num_sms() * 8);
-  multi_adamw_ema_kernel<<<grid, 256, 0, as_stream(stream)>>>((const MtRec*)recs, chunk_tensor, chunk_off, n_chunks, chunk, lr, wd, beta1,
-                                                              beta2, eps, (float)bc1, (float)sqrt(bc2), coef, ema_decay, mode);
+  multi_adamw_ema_kernel<<<grid, 256, 0, as_stream(stream)>>>((const MtRec*)recs, chunk_tensor, chunk_off, n_chunks, chunk, lr, wd,
+                                                              (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps,
+                                                              (float)bc1, (float)sqrt(bc2), coef, ema_decay, mode);
   B200_LAUNCH_CHECK("multi_adamw_ema_kernel");
   return B200CTR_OK;
 }
