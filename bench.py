@@ -687,10 +687,12 @@ def run_cuda(args):
                 line["scale_config"]["comm_ms_per_step"] = round(r2["comm_ms_per_step"], 4)
         keep.append((m2, t2))
     if rank == 0:
-        ad = os.path.join(ROOT, "profiles", "r02_amp_delta.json")
-        if os.path.exists(ad):
+        # newest record first: r02z was re-measured with the packed-half attention / half2 FFN epilogues (fp32 and bf16 arms; the
+        # CPU-reference arm is in r02_amp_delta.json)
+        ad = next((p_ for p_ in (os.path.join(ROOT, "profiles", f) for f in ("r02z_amp_delta.json", "r02_amp_delta.json")) if os.path.exists(p_)), None)
+        if ad is not None:
             d = json.load(open(ad))
-            line["amp_delta_one_epoch"] = {"source": "profiles/r02_amp_delta.json (tools/amp_delta.py)", "bf16_minus_fp32": d["delta"]["bf16_minus_fp32"],
+            line["amp_delta_one_epoch"] = {"source": f"profiles/{os.path.basename(ad)} (tools/amp_delta.py)", "bf16_minus_fp32": d["delta"]["bf16_minus_fp32"],
                                            "fp32_seed_noise": d["delta"]["fp32_seed_noise"], "stated_tolerance": d["stated_tolerance"],
                                            "within_tolerance": d["within_tolerance"]}
         if world == 1 and not args.no_cpu_baseline:
