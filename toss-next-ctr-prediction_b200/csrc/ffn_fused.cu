@@ -29,10 +29,11 @@ constexpr int FF_TM = 128;        // tokens per tile (UMMA M)
 constexpr int FF_HC = 64;         // hidden chunk (UMMA N of GEMM1, K of GEMM2)
 constexpr int FFW_EPI_WARPS = 16;                 // forward kernel: 4 loader/RMSNorm + 16 GELU-epilogue + 1 MMA warp
 constexpr int FFW_MMA_WARP = 4 + FFW_EPI_WARPS;
-constexpr int FFW_PB = 1;      // TMEM buffers of the pre-activation chunk (2 measured 12 % SLOWER than 1: see profiles/README.md)
 constexpr int FFW_NT = (FFW_MMA_WARP + 1) * 32;
+// forward kernel: 4 tile-producer + 4 final-epilogue + 16 GELU-epilogue + 1 MMA warp
+constexpr int FFF_MMA_WARP = 8 + FFW_EPI_WARPS;
+constexpr int FFF_NT = (FFF_MMA_WARP + 1) * 32;
 constexpr int FF_A_BYTES = FF_TM * FF_D * 2;        // 16 KB: x1 tile, bf16
-constexpr int FF_FD_BYTES = FF_TM * FF_HC * 2;      // 16 KB: activation chunk, bf16
 constexpr int FF_WCHUNK = FF_HC * FF_D * 2;         // 8 KB of W1 or W2 per hidden chunk
 
 struct FfnBars {
@@ -52,20 +53,6 @@ __device__ __forceinline__ void ffn_stage_w1(unsigned char* w1s, const float* __
   }
 }
 // W2 [64][hidden] fp32 -> per 64-column chunk a K-major B operand (N = d rows, K = hidden within the chunk);
-// the forward's copy: fp16, times the dropout keep scale 1/(1-p) (the GELU epilogue hands GEMM2 fp16 activations that are
-// masked but not rescaled)
-__device__ __forceinline__ void ffn_stage_w2_h(unsigned char* w2s, const float* __restrict__ w2, int hidden, float scale, int tid, int nt) {
-  const int hg_per_row = hidden >> 3;
-  for (int u = tid; u < FF_D * hg_per_row; u += nt) {
-    const int d = u / hg_per_row, hg = u % hg_per_row;
-    const float4* p = reinterpret_cast<const float4*>(w2 + (size_t)d * hidden + hg * 8);
-    const float4 a = __ldg(p), b = __ldg(p + 1);
-    const int c = hg >> 3, kc = hg & 7;
-    *reinterpret_cast<uint4*>(w2s + c * FF_WCHUNK + (kc * 8 + (d >> 3)) * 128 + (d & 7) * 16) =
-        make_uint4(h2_pack(a.x * scale, a.y * scale), h2_pack(a.z * scale, a.w * scale), h2_pack(b.x * scale, b.y * scale),
-                   h2_pack(b.z * scale, b.w * scale));
-  }
-}
 // one 128-token x 64 fp32 tile -> bf16 K-major A operand (R = 128); 128 threads, rows >= T are zero-filled
 __device__ __forceinline__ void ffn_stage_tile(unsigned char* dst, const float* __restrict__ x, int64_t m0, int64_t T, int ptid) {
   float4 va[8], vb[8];
@@ -125,81 +112,110 @@ __device__ __forceinline__ void ffn_mma_kk(uint32_t tmem_d, uint32_t a_base, uin
   }
 }
 
-__global__ void __launch_bounds__(FFW_NT, 1)
+// HC = hidden chunk width.  Every chunk costs one trip around the barrier ring (epilogue reads P -> issuer -> GEMM1 -> epilogue;
+// epilogue writes fd -> issuer -> GEMM2 -> fd buffer free), ~1.3 us whatever the chunk holds (measured by ablation: with the
+// GELU removed the kernel went 0.274 -> 0.262 ms, with the output stores removed too -> 0.21 ms).  128-wide chunks halve the
+// number of trips; HC = 64 remains for ffn_hidden not divisible by 128.
+template <int HC>
+__global__ void __launch_bounds__(FFF_NT, 1)
 ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const float* __restrict__ b1,
                const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ n2w, float eps,
                int64_t T, int hidden, float* __restrict__ s2_out, float* __restrict__ r2_out, float* __restrict__ x2_out,
                uint16_t* __restrict__ keep, b200ctr_dropout_t drop) {
   // keep (optional): one 16-bit word of dropout keep flags per (tile, 64-wide chunk, 16-column quarter, token row) --
-  // exactly what one epilogue lane produces -- so that the backward tests bits instead of re-hashing
+  // so that the backward tests bits instead of re-hashing
+  constexpr int WCH = HC * FF_D * 2;            // bytes of W1 or W2 per chunk
+  constexpr int FDB = FF_TM * HC * 2;           // bytes of one activation chunk buffer
+  constexpr int CW = HC / 4;                    // columns per epilogue warp and chunk (16 or 32)
   extern __shared__ __align__(128) unsigned char smem[];
-  const int NC = hidden / FF_HC;
+  const int NC = hidden / HC;
   unsigned char* w1s = smem;
-  unsigned char* w2s = w1s + (size_t)NC * FF_WCHUNK;
-  unsigned char* as = w2s + (size_t)NC * FF_WCHUNK;            // [2][16 KB]
-  unsigned char* fds = as + 2 * FF_A_BYTES;                    // [2][16 KB]
-  float* b1s = reinterpret_cast<float*>(fds + 2 * FF_FD_BYTES);
+  unsigned char* w2s = w1s + (size_t)NC * WCH;
+  unsigned char* as = w2s + (size_t)NC * WCH;                  // [2][16 KB]
+  unsigned char* fds = as + 2 * FF_A_BYTES;                    // [2][FDB]
+  float* b1s = reinterpret_cast<float*>(fds + 2 * FDB);
   float* b2s = b1s + hidden;
   float* n2s = b2s + FF_D;
-  float* scr_all = n2s + FF_D;                                 // 4 final-epilogue warps x 32 x 68 floats (store transpose)
-  FfnBars* bars = reinterpret_cast<FfnBars*>(scr_all + 4 * 32 * 68);
+  float* scr_all = n2s + FF_D;                                 // 4 final-epilogue warps x 32 x 36 floats (store transpose, 32 columns at a time)
+  FfnBars* bars = reinterpret_cast<FfnBars*>(scr_all + 4 * 32 * 36);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t tiles = (T + FF_TM - 1) / FF_TM;
   const int n_it = (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);      // tiles of this CTA
 
-  if (warp == FFW_MMA_WARP) tmem_alloc(&bars->tmem_base, 256);
+  if (warp == FFF_MMA_WARP) tmem_alloc(&bars->tmem_base, 256);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bars->a_full[s]), 4); mbar_init(smem_u32(&bars->a_empty[s]), 1);
       mbar_init(smem_u32(&bars->fd_full[s]), FFW_EPI_WARPS); mbar_init(smem_u32(&bars->fd_empty[s]), 1);
       mbar_init(smem_u32(&bars->h2_full[s]), 1); mbar_init(smem_u32(&bars->h2_empty[s]), 4);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->p_full[s]), 1); mbar_init(smem_u32(&bars->p_empty[s]), FFW_EPI_WARPS); }
+    mbar_init(smem_u32(&bars->p_full[0]), 1); mbar_init(smem_u32(&bars->p_empty[0]), FFW_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  ffn_stage_w1(w1s, w1, hidden, tid, FFW_NT);
-  ffn_stage_w2_h(w2s, w2, hidden, drop.p > 0.f ? 1.f / (1.f - drop.p) : 1.f, tid, FFW_NT);
+  // W1 [hidden][64] -> per chunk a K-major B operand (N = HC hidden rows, K = d): core (k-group kc, n-group r/8)
+  for (int u = tid; u < hidden * 8; u += FFF_NT) {
+    const int h = u >> 3, kc = u & 7;
+    const float4* p = reinterpret_cast<const float4*>(w1 + (size_t)h * FF_D + kc * 8);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    const int c = h / HC, r = h % HC;
+    *reinterpret_cast<uint4*>(w1s + c * WCH + (kc * (HC / 8) + (r >> 3)) * 128 + (r & 7) * 16) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+  // W2 [64][hidden] -> per chunk a K-major B operand (N = d rows, K = HC hidden within the chunk), fp16, times 1/(1-p)
+  {
+    const float scale = drop.p > 0.f ? 1.f / (1.f - drop.p) : 1.f;
+    const int hg_per_row = hidden >> 3;
+    for (int u = tid; u < FF_D * hg_per_row; u += FFF_NT) {
+      const int d = u / hg_per_row, hg = u % hg_per_row;
+      const float4* p = reinterpret_cast<const float4*>(w2 + (size_t)d * hidden + hg * 8);
+      const float4 a = __ldg(p), b = __ldg(p + 1);
+      const int c = hg / (HC / 8), kc = hg % (HC / 8);
+      *reinterpret_cast<uint4*>(w2s + c * WCH + (kc * 8 + (d >> 3)) * 128 + (d & 7) * 16) =
+          make_uint4(h2_pack(a.x * scale, a.y * scale), h2_pack(a.z * scale, a.w * scale), h2_pack(b.x * scale, b.y * scale),
+                     h2_pack(b.z * scale, b.w * scale));
+    }
+  }
   uint32_t* b1h = reinterpret_cast<uint32_t*>(b1s);                // bias as half2 pairs
-  for (int i = tid; i < hidden / 2; i += FFW_NT) b1h[i] = h2_pack(b1[2 * i], b1[2 * i + 1]);
+  for (int i = tid; i < hidden / 2; i += FFF_NT) b1h[i] = h2_pack(b1[2 * i], b1[2 * i + 1]);
   if (tid < FF_D) { b2s[tid] = b2[tid]; n2s[tid] = n2w[tid]; }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  // TMEM: pre-activation chunk buffer(s) at columns 0 (/ 64); the x1 . W1^T product of chunk g + FFW_PB is issued the moment
-  // the epilogue has READ chunk g; h2 buffers at columns 128 and 192
+  // TMEM: the pre-activation chunk at columns 0 .. HC-1 (one buffer: two measured slower, profiles/README.md); the x1 . W1^T
+  // product of chunk g + 1 is issued the moment the epilogue has READ chunk g; h2 buffers at columns 128 and 192
   const uint32_t P_COL = 0, H2_COL = 128;
 
   if (warp < 4) {
-    // ---------------------------------------- tile loader + final epilogue ----------------------------------
-    if (n_it > 0) {
-      ffn_stage_tile(as, x1, (int64_t)blockIdx.x * FF_TM, T, tid);
+    // ---------------------------------------- tile producer --------------------------------------------------------
+    // (its own four warps: with one set of warps doing "stage tile it + 1, then the final epilogue of tile it" the two
+    // phases' global-load latencies added up on the kernel's critical path -- removing the output stores alone moved the
+    // kernel by 15 %)
+    for (int it = 0; it < n_it; ++it) {
+      const int nb = it & 1;
+      if (it >= 2) mbar_wait(smem_u32(&bars->a_empty[nb]), (uint32_t)(((it >> 1) - 1) & 1));
+      ffn_stage_tile(as + nb * FF_A_BYTES, x1, ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM, T, tid);
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[0]));
+      if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[nb]));
     }
+  } else if (warp < 8) {
+    // ---------------------------------------- final epilogue: residual + RMSNorm on the h2 accumulator --------------
+    const int fw = warp - 4;                                      // TMEM lane group = warp % 4
     for (int it = 0; it < n_it; ++it) {
-      if (it + 1 < n_it) {
-        const int nb = (it + 1) & 1;
-        if (it + 1 >= 2) mbar_wait(smem_u32(&bars->a_empty[nb]), (uint32_t)((((it + 1) >> 1) - 1) & 1));
-        ffn_stage_tile(as + nb * FF_A_BYTES, x1, ((int64_t)blockIdx.x + (int64_t)(it + 1) * gridDim.x) * FF_TM, T, tid);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->a_full[nb]));
-      }
       const int hb = it & 1;
       mbar_wait(smem_u32(&bars->h2_full[hb]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       uint32_t v[64];
-      const uint32_t taddr = tmem + H2_COL + hb * 64 + ((uint32_t)(warp * 32) << 16);
+      const uint32_t taddr = tmem + H2_COL + hb * 64 + ((uint32_t)(fw * 32) << 16);
       tmem_ld32(taddr, v);
       tmem_ld32(taddr + 32, v + 32);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->h2_empty[hb]));
-      const int64_t m_w = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM + warp * 32;
+      const int64_t m_w = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FF_TM + fw * 32;
       const int64_t m = m_w + lane;
       const int rows_valid = (int)max((int64_t)0, min((int64_t)32, T - m_w));
       float ss = 0.f;
@@ -219,15 +235,19 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
       }
       const float r = rsqrtf(ss * (1.f / FF_D) + eps);
       if (r2_out && m < T) r2_out[m] = r;
-      float* scr = scr_all + warp * (32 * 68);
-      if (s2_out) warp_store_rows<64>(scr, v, s2_out + m_w * FF_D, FF_D, rows_valid, lane);
+      float* scr = scr_all + fw * (32 * 36);
+      if (s2_out) {
+        warp_store_rows<32>(scr, v, s2_out + m_w * FF_D, FF_D, rows_valid, lane);
+        warp_store_rows<32>(scr, v + 32, s2_out + m_w * FF_D + 32, FF_D, rows_valid, lane);
+      }
 #pragma unroll
       for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(n2s[j] * __uint_as_float(v[j]) * r);
-      warp_store_rows<64>(scr, v, x2_out + m_w * FF_D, FF_D, rows_valid, lane);
+      warp_store_rows<32>(scr, v, x2_out + m_w * FF_D, FF_D, rows_valid, lane);
+      warp_store_rows<32>(scr, v + 32, x2_out + m_w * FF_D + 32, FF_D, rows_valid, lane);
     }
-  } else if (warp < FFW_MMA_WARP) {
+  } else if (warp < FFF_MMA_WARP) {
     // ---------------------------------------- GELU epilogue -----------------------------------------------------
-    const int ew = warp - 4, q = ew & 3, part = ew >> 2;          // 16 warps: TMEM lane group x 16-column quarter of the chunk
+    const int ew = warp - 8, q = ew & 3, part = ew >> 2;          // 16 warps: TMEM lane group x CW-column quarter of the chunk
     const int r = q * 32 + lane;
     uint32_t g = 0;
     const DropCtx dctx = drop_ctx(drop);
@@ -237,40 +257,43 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
       const int64_t m = tile * FF_TM + r;
       const uint32_t rkey = dctx.on ? drop_row_key(drop, (uint64_t)m) : 0u;
       for (int c = 0; c < NC; ++c, ++g) {
-        const uint32_t pb = g % FFW_PB;
-        mbar_wait(smem_u32(&bars->p_full[pb]), (g / FFW_PB) & 1);
+        mbar_wait(smem_u32(&bars->p_full[0]), g & 1);
         tc_fence_after();
-        uint32_t v[16];
-        tmem_ld16(tmem + P_COL + pb * 64 + part * 16 + ((uint32_t)(q * 32) << 16), v);
+        uint32_t v[CW];
+        const uint32_t taddr = tmem + P_COL + part * CW + ((uint32_t)(q * 32) << 16);
+        if (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->p_empty[pb]));
+        if (lane == 0) mbar_arrive(smem_u32(&bars->p_empty[0]));
         // per-element work on half2 pairs: pack, + b1, GELU (h2_common.cuh), keep mask = one AND + one HSET2 on the hash
         // word; the activation goes to GEMM2 as fp16 (11 bits, against the 8 of bf16), masked but not rescaled (W2 carries
         // the 1/(1-p)).  10 instructions per element instead of 27.
-        const int n0 = c * FF_HC + part * 16;
-        const uint4 bq0 = *reinterpret_cast<const uint4*>(b1h + (n0 >> 1)), bq1 = *reinterpret_cast<const uint4*>(b1h + (n0 >> 1) + 4);
-        const uint32_t bh[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
-        uint32_t pk[8];
-        uint32_t kb = 0u;
+        uint32_t pk[CW / 2];
 #pragma unroll
-        for (int jp = 0; jp < 8; ++jp) {
-          uint32_t f = h2_gelu(h2_add(h2_pack(__uint_as_float(v[2 * jp]), __uint_as_float(v[2 * jp + 1])), bh[jp]));
-          if (dctx.on) {
-            const uint32_t mk = drop_keep_mask2(drop_pair_hash(rkey, (uint32_t)(n0 >> 1) + jp), thr2);
-            f &= mk;
-            kb |= mk & (0x00010001u << (2 * jp));      // bit 2jp <- even column, bit 16 + 2jp <- odd column
+        for (int sq = 0; sq < CW / 16; ++sq) {
+          const int n0 = c * HC + part * CW + 16 * sq;      // first hidden column of this 16-column quarter
+          const uint4 bq0 = *reinterpret_cast<const uint4*>(b1h + (n0 >> 1)), bq1 = *reinterpret_cast<const uint4*>(b1h + (n0 >> 1) + 4);
+          const uint32_t bh[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
+          uint32_t kb = 0u;
+#pragma unroll
+          for (int jp = 0; jp < 8; ++jp) {
+            uint32_t f = h2_gelu(h2_add(h2_pack(__uint_as_float(v[16 * sq + 2 * jp]), __uint_as_float(v[16 * sq + 2 * jp + 1])), bh[jp]));
+            if (dctx.on) {
+              const uint32_t mk = drop_keep_mask2(drop_pair_hash(rkey, (uint32_t)(n0 >> 1) + jp), thr2);
+              f &= mk;
+              kb |= mk & (0x00010001u << (2 * jp));      // bit 2jp <- even column, bit 16 + 2jp <- odd column
+            }
+            pk[8 * sq + jp] = f;
           }
-          pk[jp] = f;
+          kb = (kb & 0x5555u) | ((kb >> 15) & 0xAAAAu);      // stored word: bit j = keep flag of column j
+          if (keep && dctx.on) keep[((tile * (hidden / 64) + (n0 >> 6)) * 4 + ((n0 & 63) >> 4)) * FF_TM + r] = (uint16_t)kb;
         }
-        kb = (kb & 0x5555u) | ((kb >> 15) & 0xAAAAu);      // stored word: bit j = keep flag of column j
-        if (keep && dctx.on) keep[((tile * NC + c) * 4 + part) * FF_TM + r] = (uint16_t)kb;
         const int fb = g & 1;
         if (g >= 2) mbar_wait(smem_u32(&bars->fd_empty[fb]), ((g >> 1) - 1) & 1);
-        unsigned char* dst = fds + fb * FF_FD_BYTES;
+        unsigned char* dst = fds + fb * FDB;
 #pragma unroll
-        for (int j4 = 0; j4 < 2; ++j4) {
-          const int kg = part * 2 + j4;
+        for (int j4 = 0; j4 < CW / 8; ++j4) {
+          const int kg = part * (CW / 8) + j4;
           *reinterpret_cast<uint4*>(dst + (kg * 16 + (r >> 3)) * 128 + (r & 7) * 16) =
               make_uint4(pk[4 * j4], pk[4 * j4 + 1], pk[4 * j4 + 2], pk[4 * j4 + 3]);
         }
@@ -281,29 +304,27 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
     }
   } else if (lane == 0) {
     // ---------------------------------------- MMA issuer ---------------------------------------------------------
-    const uint32_t idesc = umma_idesc(FF_TM, FF_HC, false, false);       // M=128, N=64, both operands K-major (bf16: x1 . W1^T)
-    const uint32_t idesc2 = umma_idesc_f16(FF_TM, FF_HC, false, false);  // fp16: activation . W2^T
+    const uint32_t idesc = umma_idesc(FF_TM, HC, false, false);          // M=128, N=HC, both operands K-major (bf16: x1 . W1^T)
+    const uint32_t idesc2 = umma_idesc_f16(FF_TM, FF_D, false, false);   // fp16: activation . W2^T, N = 64
     const uint32_t as_u = smem_u32(as), fd_u = smem_u32(fds), w1_u = smem_u32(w1s), w2_u = smem_u32(w2s);
     const uint32_t total = (uint32_t)n_it * (uint32_t)NC;
-    // The issuer is ONE thread whose dependent scalar instructions compete with 20 busy warps for issue slots: at ~300
-    // instructions per chunk (runtime divisions, descriptor construction per MMA, predicate set-up) it, not the epilogue,
-    // set the pace of the kernel.  Descriptors are built once and advanced by an add; chunk / tile counters are carried.
+    // descriptors are built once and advanced by an add; chunk / tile counters are carried (no divisions)
     const uint64_t dA[2] = {make_desc(as_u, FF_TM * 16, 128), make_desc(as_u + FF_A_BYTES, FF_TM * 16, 128)};
-    const uint64_t dF[2] = {make_desc(fd_u, FF_TM * 16, 128), make_desc(fd_u + FF_FD_BYTES, FF_TM * 16, 128)};
-    const uint64_t dW1 = make_desc(w1_u, FF_HC * 16, 128), dW2 = make_desc(w2_u, FF_D * 16, 128);
+    const uint64_t dF[2] = {make_desc(fd_u, FF_TM * 16, 128), make_desc(fd_u + FDB, FF_TM * 16, 128)};
+    const uint64_t dW1 = make_desc(w1_u, HC * 16, 128), dW2 = make_desc(w2_u, FF_D * 16, 128);
     uint32_t g1 = 0, it1 = 0, c1 = 0, g2 = 0, it2 = 0, c2 = 0;
-    auto gemm1 = [&]() {                             // next chunk -> P buffer g1 % FFW_PB (free once the epilogue has read chunk g1 - FFW_PB)
-      const uint32_t ab = it1 & 1, pb = g1 % FFW_PB;
+    auto gemm1 = [&]() {                             // next chunk -> the P buffer (free once the epilogue has read the previous chunk)
+      const uint32_t ab = it1 & 1;
       if (c1 == 0) mbar_wait(smem_u32(&bars->a_full[ab]), (it1 >> 1) & 1);
-      if (g1 >= FFW_PB) mbar_wait(smem_u32(&bars->p_empty[pb]), ((g1 / FFW_PB) - 1) & 1);
+      if (g1 >= 1) mbar_wait(smem_u32(&bars->p_empty[0]), (g1 - 1) & 1);
       tc_fence_after();
-      const uint64_t da = dA[ab], db = desc_advance(dW1, c1 * FF_WCHUNK);
-      const uint32_t td = tmem + P_COL + pb * 64;
+      const uint64_t da = dA[ab], db = desc_advance(dW1, c1 * WCH);
+      const uint32_t td = tmem + P_COL;
       umma_bf16_c<false>(td, da, db, idesc);
-      umma_bf16_c<true>(td, desc_advance(da, 2 * FF_TM * 16), desc_advance(db, 2 * FF_HC * 16), idesc);
-      umma_bf16_c<true>(td, desc_advance(da, 4 * FF_TM * 16), desc_advance(db, 4 * FF_HC * 16), idesc);
-      umma_bf16_c<true>(td, desc_advance(da, 6 * FF_TM * 16), desc_advance(db, 6 * FF_HC * 16), idesc);
-      umma_commit(smem_u32(&bars->p_full[pb]));
+#pragma unroll
+      for (int ks = 1; ks < FF_D / 16; ++ks)
+        umma_bf16_c<true>(td, desc_advance(da, ks * 2 * FF_TM * 16), desc_advance(db, ks * 2 * HC * 16), idesc);
+      umma_commit(smem_u32(&bars->p_full[0]));
       ++g1;
       if (++c1 == (uint32_t)NC) { umma_commit(smem_u32(&bars->a_empty[ab])); c1 = 0; ++it1; }
     };
@@ -312,18 +333,17 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
       mbar_wait(smem_u32(&bars->fd_full[fb]), (g2 >> 1) & 1);
       if (c2 == 0 && it2 >= 2) mbar_wait(smem_u32(&bars->h2_empty[hb]), ((it2 >> 1) - 1) & 1);
       tc_fence_after();
-      const uint64_t da = dF[fb], db = desc_advance(dW2, c2 * FF_WCHUNK);
+      const uint64_t da = dF[fb], db = desc_advance(dW2, c2 * WCH);
       const uint32_t td = tmem + H2_COL + hb * 64;
       if (c2 == 0) umma_bf16_c<false>(td, da, db, idesc2); else umma_bf16_c<true>(td, da, db, idesc2);
-      umma_bf16_c<true>(td, desc_advance(da, 2 * FF_TM * 16), desc_advance(db, 2 * FF_D * 16), idesc2);
-      umma_bf16_c<true>(td, desc_advance(da, 4 * FF_TM * 16), desc_advance(db, 4 * FF_D * 16), idesc2);
-      umma_bf16_c<true>(td, desc_advance(da, 6 * FF_TM * 16), desc_advance(db, 6 * FF_D * 16), idesc2);
+#pragma unroll
+      for (int ks = 1; ks < HC / 16; ++ks)
+        umma_bf16_c<true>(td, desc_advance(da, ks * 2 * FF_TM * 16), desc_advance(db, ks * 2 * FF_D * 16), idesc2);
       umma_commit(smem_u32(&bars->fd_empty[fb]));
       ++g2;
       if (++c2 == (uint32_t)NC) { umma_commit(smem_u32(&bars->h2_full[hb])); c2 = 0; ++it2; }
     };
-    for (int pre = 0; pre < FFW_PB; ++pre)
-      if (g1 < total) gemm1();
+    if (g1 < total) gemm1();
     for (uint32_t g = 0; g < total; ++g) {
       if (g1 < total) gemm1();
       gemm2();
@@ -331,7 +351,7 @@ ffn_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ w1, const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == FFW_MMA_WARP) {
+  if (warp == FFF_MMA_WARP) {
     __syncwarp();
     tmem_dealloc(tmem, 256);
   }
@@ -786,9 +806,9 @@ ffn_bwd2_kernel(const unsigned char* __restrict__ dpre_spill, const float* __res
   }
 }
 
-static size_t ffn_fwd_smem(int hidden) {
-  return (size_t)2 * (hidden / FF_HC) * FF_WCHUNK + 2 * FF_A_BYTES + 2 * FF_FD_BYTES + ((size_t)hidden + 2 * FF_D) * 4 +
-         (size_t)4 * 32 * 68 * 4 + sizeof(FfnBars) + 16;
+static size_t ffn_fwd_smem(int hidden, int hc) {
+  return (size_t)2 * hidden * FF_D * 2 + 2 * FF_A_BYTES + (size_t)2 * FF_TM * hc * 2 + ((size_t)hidden + 2 * FF_D) * 4 +
+         (size_t)4 * 32 * 36 * 4 + sizeof(FfnBars) + 16;
 }
 
 }  // namespace b200ctr
@@ -803,13 +823,15 @@ extern "C" int b200ctr_ffn_fwd(const float* x1, const float* w1, const float* b1
   B200_REQUIRE(hidden > 0 && hidden % FF_HC == 0 && hidden <= 512, B200CTR_E_UNSUPPORTED_SHAPE,
                "ffn_fwd: ffn_hidden=%d unsupported (multiple of 64, <= 512)", hidden);
   if (T == 0) return B200CTR_OK;
-  const size_t smem = ffn_fwd_smem(hidden);
-  cudaError_t e = cudaFuncSetAttribute(ffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int hc = (hidden % 128 == 0 && hidden <= 384) ? 128 : 64;      // 128-wide chunks need 213 KB of shared memory at 384
+  const size_t smem = ffn_fwd_smem(hidden, hc);
+  auto fn = hc == 128 ? ffn_fwd_kernel<128> : ffn_fwd_kernel<64>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ffn_fwd smem)");
   const int64_t tiles = ceil_div(T, (int64_t)FF_TM);
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)num_sms());
-  ffn_fwd_kernel<<<grid, FFW_NT, smem, as_stream(stream)>>>(x1, w1, b1, w2, b2, n2w, eps, T, hidden, s2_out, r2_out, x2_out,
-                                                            (uint16_t*)keep_bits, drop);
+  fn<<<grid, FFF_NT, smem, as_stream(stream)>>>(x1, w1, b1, w2, b2, n2w, eps, T, hidden, s2_out, r2_out, x2_out,
+                                                (uint16_t*)keep_bits, drop);
   B200_LAUNCH_CHECK("ffn_fwd_kernel");
   return B200CTR_OK;
 }
