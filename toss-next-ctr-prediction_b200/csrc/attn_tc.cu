@@ -4,8 +4,11 @@
 // 1/sqrt(hd), additive Toeplitz bias from PositionalBias dare.py:29-37, dropout on the probabilities).
 //
 // head_dim = 8 is exactly the k extent of m16n8k8, so Q.K^T needs one MMA per 16 x 8 score tile and P.V one per
-// 8 keys; contraction depth 8 is far too shallow for tcgen05 (K = 16 per instruction, 128-row tiles), and the
-// kernel is bound by the exp / dropout-hash work per score anyway, so the legacy HMMA path is the right tool here.
+// 8 keys.  (tcgen05.mma kind::tf32 also has k = 8, so the contraction would map; what rules it out is that the MMAs are
+// 2 % of this kernel's issue slots -- the exp / mask / dropout work per score is the bound, on either tensor path.)
+// SUPERSEDED as the default of the `amp: bf16` path by the packed-half kernels of attn_h16.cu (1.6-1.9x faster: the per-score
+// work runs on half2 pairs there); kept selectable with B200CTR_ATTN=tf32 for A/B runs and as a second implementation the
+// tests hold to the same fp32 reference.
 //
 // One CTA per sample; q (pre-scaled), k, v [, dO] of all heads staged once in shared memory as TF32 with a row
 // stride of 68 words, which makes every fragment load bank-conflict free.  A warp owns (head, 16-query tile):
