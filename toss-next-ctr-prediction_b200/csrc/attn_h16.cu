@@ -89,6 +89,14 @@ __device__ __forceinline__ void ha_store_T(uint32_t* dst, int TSW, int c, int rp
   d[2 * TSW] = h2_pack(x0.z * s0, x1.z * s1);
   d[3 * TSW] = h2_pack(x0.w * s0, x1.w * s1);
 }
+// unscaled (k, v): no multiplies in the staging loop
+__device__ __forceinline__ void ha_store_T1(uint32_t* dst, int TSW, int c, int rp, const float4& x0, const float4& x1) {
+  uint32_t* d = dst + (4 * c) * TSW + rp;
+  d[0] = h2_pack(x0.x, x1.x);
+  d[TSW] = h2_pack(x0.y, x1.y);
+  d[2 * TSW] = h2_pack(x0.z, x1.z);
+  d[3 * TSW] = h2_pack(x0.w, x1.w);
+}
 // q (scaled), k, v of the sample; the six 128-bit loads of a unit (twelve with two units per thread) are all in flight
 // before the first conversion: the staging phase is pure load latency.  Returns the thread's max |v|.
 template <int NTH, int KP, int QD>
@@ -115,8 +123,8 @@ __device__ __forceinline__ float ha_stage_qkv(uint32_t* qT, uint32_t* kT, uint32
       const HaUnit un = ha_unit<KP, QD>(threadIdx.x + (it0 + ii) * NTH);
       if (it0 + ii < UPT && un.act) {
         ha_store_T(qT, TSW, un.c, un.rp, x[ii][0][0], x[ii][0][1], qscale, qscale);
-        ha_store_T(kT, TSW, un.c, un.rp, x[ii][1][0], x[ii][1][1], 1.f, 1.f);
-        ha_store_T(vT, TSW, un.c, un.rp, x[ii][2][0], x[ii][2][1], 1.f, 1.f);
+        ha_store_T1(kT, TSW, un.c, un.rp, x[ii][1][0], x[ii][1][1]);
+        ha_store_T1(vT, TSW, un.c, un.rp, x[ii][2][0], x[ii][2][1]);
         vmax = ha_absmax4(ha_absmax4(vmax, x[ii][2][0]), x[ii][2][1]);
       }
     }
