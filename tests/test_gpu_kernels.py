@@ -290,7 +290,9 @@ def _bf(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
-@pytest.mark.parametrize("T,hidden,p", [(128, 128, 0.0), (1000, 384, 0.0), (1000, 384, 0.1), (128 * 300 + 17, 384, 0.1), (5, 256, 0.0)])
+# hidden = 192 / 320 / 512 run the 64-wide-chunk instantiation of the forward kernel, the multiples of 128 up to 384 the 128-wide one
+@pytest.mark.parametrize("T,hidden,p", [(128, 128, 0.0), (1000, 384, 0.0), (1000, 384, 0.1), (128 * 300 + 17, 384, 0.1), (5, 256, 0.0),
+                                        (700, 192, 0.1), (300, 320, 0.0), (300, 512, 0.1)])
 def test_ffn_fwd_fused_matches_unfused(dev, T, hidden, p):
     from b200ctr import ops
     x1, w1, b1, w2, b2, n2 = (t.to(dev) for t in _ffn_inputs(T, hidden, 3 + T))
