@@ -538,8 +538,7 @@ ffn_bwd1_kernel(const float* __restrict__ dy, const float* __restrict__ s2, cons
         tc_fence_after();
         uint32_t pv[16], qv[16];
         const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
-        tmem_ld16(tmem + P_COL + part * 16 + lane_bits, pv);
-        tmem_ld16(tmem + Q_COL + part * 16 + lane_bits, qv);
+        tmem_ld16_pair(tmem + P_COL + part * 16 + lane_bits, pv, tmem + Q_COL + part * 16 + lane_bits, qv);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->pq_empty));
