@@ -259,9 +259,11 @@ int b200ctr_attn_tc_bwd(const float* qkv, const float* relmean, int max_len, con
 /* the h16 backward runs two CTAs per sample (four heads each): its drelmean is a ZEROED (b200ctr_attn_h16_drel_rows(B),
  * 2*max_len+1) matrix of per-CTA partial rows (column-summed in row order, like the others').                           */
 int64_t b200ctr_attn_h16_drel_rows(int64_t B);
-int b200ctr_attn_h16_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D,
+/* qkv_f16 != 0: qkv is the (M, 3D) fp16 tensor written by b200ctr_inproj_fwd_h16 (q already times log2(e) / sqrt(hd)): the
+ * kernels then stage their operands with plain copies -- same values, half the bytes; 0: the fp32 tensor of the other kernels. */
+int b200ctr_attn_h16_fwd(const void* qkv, int qkv_f16, const float* relmean, int max_len, int64_t B, int K, int H, int D,
                          float* o, float* lse, uint32_t* keep, b200ctr_dropout_t drop, void* stream);
-int b200ctr_attn_h16_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
+int b200ctr_attn_h16_bwd(const void* qkv, int qkv_f16, const float* relmean, int max_len, const float* o, const float* lse,
                          const float* d_o, int64_t B, int K, int H, int D, void* dqkv, int dqkv_bf16, float* drelmean,
                          const uint32_t* keep, b200ctr_dropout_t drop, void* stream);
 int b200ctr_add_rmsnorm_fwd(const float* a, const float* b, const float* w, float eps, int64_t M, int D,
@@ -307,6 +309,9 @@ int b200ctr_ffn_bwd(const float* dy, const float* s2, const float* r2, const flo
  * gradient is the 65th accumulator column: the activation operand carries a ones column), deterministic cross-CTA
  * reduction.  workspace >= b200ctr_proj_bwd_workspace_bytes().  D == 64 (8 heads x head_dim 8).                  */
 int b200ctr_inproj_fwd(const float* x, const float* w_in, const float* b_in, int64_t T, int D, float* qkv, void* stream);
+/* the same projection with qkv written as fp16 (T, 192), its q third times log2(e) / sqrt(head_dim = 8): the operand format of
+ * b200ctr_attn_h16_fwd/bwd(qkv_f16 = 1) -- bit-identical attention results, half the qkv traffic in three kernels            */
+int b200ctr_inproj_fwd_h16(const float* x, const float* w_in, const float* b_in, int64_t T, int D, void* qkv16, void* stream);
 int b200ctr_outproj_norm_fwd(const float* o, const float* w_out, const float* b_out, const float* x_resid,
                              const float* n1w, float eps, int64_t T, int D, float* s1_out, float* r1_out,
                              float* x1_out, void* stream);

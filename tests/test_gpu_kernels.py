@@ -393,6 +393,38 @@ def test_attn_tc_matches_fp32_kernels(dev, B, K, p, impl, do_scale):
     assert dq16.dtype == torch.bfloat16 and torch.equal(dq16, dq.to(torch.bfloat16))
 
 
+# fp16 qkv hand-off: the in-projection writes fp16 with q pre-scaled, the packed-half attention stages it with copies.  Both
+# halves of the hand-off are exact restatements of what the fp32 route computes, so every result must be BIT-identical.
+H2_QSCALE = np.float32(0.51006972789764404297)
+
+
+@pytest.mark.parametrize("B,K,p", [(3, 60, 0.1), (2, 100, 0.0), (2, 148, 0.1), (5, 7, 0.1), (1, 1, 0.0), (2, 33, 0.2)])
+def test_attn_h16_fp16_qkv_is_bit_identical_to_the_fp32_route(dev, B, K, p):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(7 * B + K)
+    x = _rand(g, B * K, 64).to(dev)
+    w_in, b_in = (_rand(g, 192, 64) * 0.2).to(dev), (_rand(g, 192) * 0.1).to(dev)
+    relmean = (_rand(g, 2 * K + 1) * 0.5).to(dev)
+    d_o = (_rand(g, B * K, 64) * 1e-5).to(dev)
+    with ops.precision("bf16"):
+        qkv32 = ops.inproj_fwd(x, w_in, b_in)
+        qkv16 = ops.inproj_fwd(x, w_in, b_in, h16=True)
+    assert qkv16.dtype == torch.float16 and qkv16.shape == qkv32.shape
+    want = torch.cat([(qkv32[:, :64] * float(H2_QSCALE)).half(), qkv32[:, 64:].half()], dim=1)
+    assert torch.equal(qkv16, want)
+    dr = ops.drop(p, 11, 5)
+    o32, lse32, keep32 = ops.attn_fwd(qkv32, relmean, K, B, K, 8, 64, dr, tc=True, save_keep=True, impl="h16")
+    o16, lse16, keep16 = ops.attn_fwd(qkv16, relmean, K, B, K, 8, 64, dr, tc=True, save_keep=True, impl="h16")
+    assert torch.equal(o16, o32) and torch.equal(lse16, lse32)
+    assert (keep16 is None and keep32 is None) or torch.equal(keep16, keep32)
+    r32, r16 = torch.zeros_like(relmean), torch.zeros_like(relmean)
+    dq32 = ops.attn_bwd(qkv32, relmean, K, o32, lse32, d_o, B, K, 8, 64, r32, dr, tc=True, keep=keep32, out_bf16=True, impl="h16")
+    dq16 = ops.attn_bwd(qkv16, relmean, K, o32, lse32, d_o, B, K, 8, 64, r16, dr, tc=True, keep=keep16, out_bf16=True, impl="h16")
+    assert torch.equal(dq16, dq32) and torch.equal(r16, r32)
+    with pytest.raises(Exception):
+        ops.attn_fwd(qkv16, relmean, K, B, K, 8, 64, dr, tc=True, impl="tf32")        # the TF32 kernels take the fp32 tensor only
+
+
 @pytest.mark.parametrize("B,H,R,P", [(1000, 6, 16, 192), (7, 6, 16, 192), (300, 8, 32, 128), (64, 2, 4, 24)])
 def test_headproj_matches_einsum(dev, B, H, R, P):
     from b200ctr import ops

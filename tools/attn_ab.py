@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--impl", nargs="*", default=["tf32", "h16"])
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--warm", type=int, default=3)
+    ap.add_argument("--in16", action="store_true", help="h16 only: feed the fp16 qkv tensor of inproj_fwd(h16=True)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     B, reps = 8192, a.reps
@@ -30,6 +31,8 @@ def main():
         dr = ops.drop(0.1, 7, 3)
         for impl in a.impl:
             res = {}
+            if a.in16 and impl == "h16":
+                qkv = torch.cat([(qkv[:, :64] * 0.51006972789764404297).half(), qkv[:, 64:].half()], dim=1).contiguous()
             for name in ("fwd", "bwd"):
                 o, lse, keep = ops.attn_fwd(qkv, relmean, K, B, K, 8, 64, dr, tc=True, save_keep=True, impl=impl)
                 drel = torch.zeros_like(relmean)
@@ -49,7 +52,7 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 res[name + "_ms"] = round(e0.elapsed_time(e1) / reps, 4)
-            rec = {"K": K, "impl": impl, **res}
+            rec = {"K": K, "impl": impl, "in16": bool(a.in16 and impl == "h16"), **res}
             print(json.dumps(rec), flush=True)
             out.append(rec)
     return out

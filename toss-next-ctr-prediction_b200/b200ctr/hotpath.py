@@ -133,7 +133,8 @@ def encoder_layer_fwd(x: Tensor, P: Dict[str, Tensor], i: int, spec: ModelSpec, 
     relmean = ops.relmean_fwd(P[n["rel"]]) if spec.pos_bias else None
     fused_proj = ops.get_precision() == "bf16" and D == 64 and H == 8
     if fused_proj:        # persistent tcgen05 kernels with resident weights (csrc/proj_fused.cu)
-        qkv = ops.inproj_fwd(x, P[n["in_w"]], P[n["in_b"]])
+        # packed-half attention: qkv leaves the projection as fp16 (q pre-scaled), the attention kernels stage it with copies
+        qkv = ops.inproj_fwd(x, P[n["in_w"]], P[n["in_b"]], h16=ops.attn_takes_h16(K, H, D))
         o, lse, keep = ops.attn_fwd(qkv, relmean, spec.top_k, B, K, H, D, dc(spec.p_mha, SITE_LAYER0 + 2 * i), save_keep=True)
         s1, x1, r1 = ops.outproj_norm_fwd(o, P[n["out_w"]], P[n["out_b"]], x, P[n["n1"]])
     else:

@@ -542,6 +542,11 @@ def _attn_tc(tc: Optional[bool], K: int, H: int, D: int) -> bool:
     return bool(tc) and D == 64 and H == 8 and K <= 160
 
 
+def _qkv_f32(qkv):
+    if qkv.dtype != torch.float32:
+        raise _lib.B200CtrError("an fp16 qkv tensor (inproj_fwd(h16=True)) feeds the packed-half attention kernels only")
+
+
 def _attn_impl(impl: Optional[str]) -> str:
     """Tensor-core attention flavour: "h16" (packed-half kernels, csrc/attn_h16.cu; default) or "tf32" (csrc/attn_tc.cu).
     B200CTR_ATTN overrides the default for A/B runs."""
@@ -563,8 +568,13 @@ def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP, tc: Optional[bo
     if use_tc:
         if save_keep and dropout.p > 0.0:
             keep = torch.empty((int(lib.b200ctr_attn_tc_keep_words(B, K)),), device=qkv.device, dtype=torch.int32)
-        fn = lib.b200ctr_attn_h16_fwd if _attn_impl(impl) == "h16" else lib.b200ctr_attn_tc_fwd
-        _run("attn_tc_fwd", fn, _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), _p(keep), dropout, _stream())
+        if _attn_impl(impl) == "h16":
+            _run("attn_tc_fwd", lib.b200ctr_attn_h16_fwd, _p(qkv), int(qkv.dtype == torch.float16), _p(relmean), max_len, B, K, H, D,
+                 _p(o), _p(lse), _p(keep), dropout, _stream())
+        else:
+            _qkv_f32(qkv)
+            _run("attn_tc_fwd", lib.b200ctr_attn_tc_fwd, _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), _p(keep), dropout,
+                 _stream())
     else:
         _run("attn_fwd", lib.b200ctr_attn_fwd, _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), dropout, _stream())
     _count()
@@ -584,9 +594,13 @@ def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=N
         rows = int(lib.b200ctr_attn_h16_drel_rows(B)) if h16 else B
         drelmean = torch.zeros((rows, 2 * max_len + 1), device=qkv.device, dtype=torch.float32)
     if use_tc:
-        fn = lib.b200ctr_attn_h16_bwd if h16 else lib.b200ctr_attn_tc_bwd
-        _run("attn_tc_bwd", fn, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
-             int(out_bf16), _p(drelmean), _p(keep), dropout, _stream())
+        if h16:
+            _run("attn_tc_bwd", lib.b200ctr_attn_h16_bwd, _p(qkv), int(qkv.dtype == torch.float16), _p(relmean), max_len, _p(o), _p(lse),
+                 _p(d_o), B, K, H, D, _p(dqkv), int(out_bf16), _p(drelmean), _p(keep), dropout, _stream())
+        else:
+            _qkv_f32(qkv)
+            _run("attn_tc_bwd", lib.b200ctr_attn_tc_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
+                 int(out_bf16), _p(drelmean), _p(keep), dropout, _stream())
     else:
         _run("attn_bwd", lib.b200ctr_attn_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
              _p(drelmean), dropout, _stream())
@@ -608,13 +622,25 @@ def add_rmsnorm_fwd(a, b, w, eps=1e-6, save_sum=True):
 
 
 # ---- fused attention-side projections (csrc/proj_fused.cu) ---------------------------------------------------------
-def inproj_fwd(x, w_in, b_in):
+def inproj_fwd(x, w_in, b_in, h16: bool = False):
+    """qkv = x . w_in^T + b_in.  h16: as fp16 with the q third pre-multiplied by log2(e)/sqrt(8) -- the operand format of the
+    packed-half attention kernels (attn_fwd / attn_bwd recognise it by its dtype)."""
     lib = _lib.load()
     T, D = x.shape
-    qkv = torch.empty((T, 3 * D), device=x.device, dtype=torch.float32)
-    _run("inproj_fwd", lib.b200ctr_inproj_fwd, _p(_f32(x)), _p(w_in), _p(b_in), T, D, _p(qkv), _stream())
+    if h16:
+        qkv = torch.empty((T, 3 * D), device=x.device, dtype=torch.float16)
+        _run("inproj_fwd", lib.b200ctr_inproj_fwd_h16, _p(_f32(x)), _p(w_in), _p(b_in), T, D, _p(qkv), _stream())
+    else:
+        qkv = torch.empty((T, 3 * D), device=x.device, dtype=torch.float32)
+        _run("inproj_fwd", lib.b200ctr_inproj_fwd, _p(_f32(x)), _p(w_in), _p(b_in), T, D, _p(qkv), _stream())
     _count()
     return qkv
+
+
+def attn_takes_h16(K: int, H: int, D: int) -> bool:
+    """True when the attention of the current precision mode is the packed-half implementation (so the in-projection may hand
+    it fp16 operands)."""
+    return _attn_tc(None, K, H, D) and _attn_impl(None) == "h16"
 
 
 def outproj_norm_fwd(o, w_out, b_out, x_resid, n1w, eps=1e-6):

@@ -135,6 +135,41 @@ __device__ __forceinline__ float ha_stage_qkv(uint32_t* qT, uint32_t* kT, uint32
   return vmax;
 }
 
+// The same three images from an fp16 qkv tensor ((T, 96) words per row: q~ | k | v with q ALREADY times H2_QSCALE, written by
+// b200ctr_inproj_fwd_h16): a unit = (row pair, 8 dims), two 16-byte loads per image, eight byte-permutes and stores -- no
+// conversions, half the bytes.  The lanes of a warp are 32 row pairs of one dim octet: stores hit 32 consecutive words.
+template <int NTH, int KP, int QD>
+__device__ __forceinline__ float ha_stage_qkv16(uint32_t* qT, uint32_t* kT, uint32_t* vT, const uint32_t* __restrict__ base16, int K) {
+  constexpr int TSW = (KP + 8) / 2, NOCT = QD / 2, RPG = (KP / 2 + 31) / 32, UNITS = RPG * 32 * NOCT, UPT = (UNITS + NTH - 1) / NTH;
+  uint32_t vm2 = 0u;
+#pragma unroll
+  for (int it = 0; it < UPT; ++it) {
+    const int u = threadIdx.x + it * NTH;
+    const int rpl = u & 31, rest = u >> 5, oc = rest % NOCT, rp = (rest / NOCT) * 32 + rpl;
+    if (u >= UNITS || rp >= KP / 2) continue;
+    uint4 x[3][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = 2 * rp + r;
+      const uint4* src = reinterpret_cast<const uint4*>(base16 + (int64_t)row * (3 * HA_D / 2)) + oc;
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      x[0][r] = row < K ? src[0] : z; x[1][r] = row < K ? src[8] : z; x[2][r] = row < K ? src[16] : z;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      uint32_t* img = (a == 0 ? qT : (a == 1 ? kT : vT)) + (8 * oc) * TSW + rp;
+      const uint32_t w0[4] = {x[a][0].x, x[a][0].y, x[a][0].z, x[a][0].w}, w1[4] = {x[a][1].x, x[a][1].y, x[a][1].z, x[a][1].w};
+#pragma unroll
+      for (int d = 0; d < 8; ++d) img[d * TSW] = __byte_perm(w0[d >> 1], w1[d >> 1], (d & 1) ? 0x7632 : 0x5410);
+      if (a == 2) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) vm2 = __vmaxu2(vm2, __vmaxu2(w0[w] & 0x7fff7fffu, w1[w] & 0x7fff7fffu));     // |v| as ordered bit patterns
+      }
+    }
+  }
+  return fmaxf(h2_lo(vm2), h2_hi(vm2));
+}
+
 // bias pairs in log2 units: bp[8 + d] = half2(bias[d], bias[d + 1]), d = (key - query) + K - 1 in [0, 2K - 2]; zero elsewhere
 // (the 8 leading entries serve the rows g + 8 of the first key tile; the tail serves padded keys / clamped padded queries)
 template <int NTH>
@@ -167,7 +202,7 @@ __device__ __forceinline__ void ha_key_masks(int kc, int K, uint32_t& andm, uint
 // (one warp per head): half the staging per CTA, twice as many CTAs to hide it behind.
 template <int NT, bool DROP>
 __global__ void __launch_bounds__(32 * HA_HPC, (NT <= 14 ? 32 : 24) / HA_HPC)
-attn_h16_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, int K,
+attn_h16_fwd_kernel(const float* __restrict__ qkv, int in16, const float* __restrict__ relmean, int max_len, int K,
                     float* __restrict__ o, float* __restrict__ lse, uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
   constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2, NW = (NT + 7) / 8, TS = Kp + 8, TSW = TS / 2, NBP = 2 * Kp + 16;
   constexpr bool KEEP_S = NT <= 8;
@@ -180,8 +215,10 @@ attn_h16_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
   uint32_t* keys = bp + NBP;                 // [HPC][Kp] dropout row keys (DROP only)
   const int64_t b = blockIdx.x / (HA_H / HPC);
   const int hbase = (int)(blockIdx.x % (HA_H / HPC)) * HPC;
-  const float* base = qkv + b * (int64_t)K * 3 * HA_D + hbase * 8;
-  ha_stage_qkv<NTH, Kp, 2 * HPC>(qT, kT, vT, base, K, rsqrtf(8.f) * HA_LOG2E);
+  if (in16)      // (T, 96) words of fp16 pairs, q pre-scaled
+    ha_stage_qkv16<NTH, Kp, 2 * HPC>(qT, kT, vT, reinterpret_cast<const uint32_t*>(qkv) + b * (int64_t)K * (3 * HA_D / 2) + hbase * 4, K);
+  else
+    ha_stage_qkv<NTH, Kp, 2 * HPC>(qT, kT, vT, qkv + b * (int64_t)K * 3 * HA_D + hbase * 8, K, H2_QSCALE);
   ha_fill_bias<NTH>(bp, NBP, relmean, max_len, K);
   if (DROP)
     for (int i = threadIdx.x; i < HPC * Kp; i += NTH) {
@@ -314,7 +351,7 @@ __device__ __forceinline__ void ha_store2(float* base, int as_bf16, int64_t off,
 // DROP: dropout on; KEEP: the keep flags come from the words the forward stored (otherwise re-hashed: same mask).
 template <int NT, int KS, bool DROP, bool KEEP>
 __global__ void __launch_bounds__(32 * HA_HPC * KS, (KS == 1 ? 24 : 8) / HA_HPC)
-attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ relmean, int max_len, const float* __restrict__ o,
+attn_h16_bwd_kernel(const float* __restrict__ qkv, int in16, const float* __restrict__ relmean, int max_len, const float* __restrict__ o,
                     const float* __restrict__ lse, const float* __restrict__ d_o, int K, float* __restrict__ dqkv, int dq16,
                     float* __restrict__ drelmean, const uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
   constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2, NW = (NT + 7) / 8, TS = Kp + 8, TSW = TS / 2, NBP = 2 * Kp + 16;
@@ -364,7 +401,8 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ rel
       }
     }
   }
-  float vmax = ha_stage_qkv<NTH, Kp, QD>(qT, kT, vT, base, K, rsqrtf(8.f) * HA_LOG2E);
+  float vmax = in16 ? ha_stage_qkv16<NTH, Kp, QD>(qT, kT, vT, reinterpret_cast<const uint32_t*>(qkv) + b * (int64_t)K * (3 * HA_D / 2) + hbase * 4, K)
+                    : ha_stage_qkv<NTH, Kp, QD>(qT, kT, vT, base, K, H2_QSCALE);
 #pragma unroll
   for (int it = 0; it < UPT; ++it) domax = ha_absmax4(ha_absmax4(domax, xd[it][0]), xd[it][1]);
   vmax = warp_max(vmax); domax = warp_max(domax);
@@ -598,7 +636,7 @@ static int ha_set_smem(const void* fn, size_t bytes) {
 }
 
 template <int NT>
-static int ha_launch_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, float* o, float* lse,
+static int ha_launch_fwd(const float* qkv, int in16, const float* relmean, int max_len, int64_t B, int K, float* o, float* lse,
                          uint32_t* keep, b200ctr_dropout_t drop, cudaStream_t st) {
   constexpr int Kp = NT * 8, TSW = (Kp + 8) / 2;
   const bool on = drop.p > 0.f;
@@ -606,24 +644,24 @@ static int ha_launch_fwd(const float* qkv, const float* relmean, int max_len, in
   int rc = on ? ha_set_smem((const void*)attn_h16_fwd_kernel<NT, true>, smem) : ha_set_smem((const void*)attn_h16_fwd_kernel<NT, false>, smem);
   if (rc) return rc;
   const unsigned grid = (unsigned)(B * (HA_H / HA_HPC));
-  if (on) attn_h16_fwd_kernel<NT, true><<<grid, 32 * HA_HPC, smem, st>>>(qkv, relmean, max_len, K, o, lse, keep, drop);
-  else attn_h16_fwd_kernel<NT, false><<<grid, 32 * HA_HPC, smem, st>>>(qkv, relmean, max_len, K, o, lse, keep, drop);
+  if (on) attn_h16_fwd_kernel<NT, true><<<grid, 32 * HA_HPC, smem, st>>>(qkv, in16, relmean, max_len, K, o, lse, keep, drop);
+  else attn_h16_fwd_kernel<NT, false><<<grid, 32 * HA_HPC, smem, st>>>(qkv, in16, relmean, max_len, K, o, lse, keep, drop);
   return B200CTR_OK;
 }
 
 template <int NT, int KS, bool DROP, bool KEEP>
-static int ha_launch_bwd_inst(size_t smem, const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
+static int ha_launch_bwd_inst(size_t smem, const float* qkv, int in16, const float* relmean, int max_len, const float* o, const float* lse,
                               const float* d_o, int64_t B, int K, float* dqkv, int dq16, float* drelmean, const uint32_t* keep,
                               b200ctr_dropout_t drop, cudaStream_t st) {
   int rc = ha_set_smem((const void*)attn_h16_bwd_kernel<NT, KS, DROP, KEEP>, smem);
   if (rc) return rc;
   attn_h16_bwd_kernel<NT, KS, DROP, KEEP><<<(unsigned)(B * (HA_H / HA_HPC)), 32 * HA_HPC * KS, smem, st>>>(
-      qkv, relmean, max_len, o, lse, d_o, K, dqkv, dq16, drelmean, keep, drop);
+      qkv, in16, relmean, max_len, o, lse, d_o, K, dqkv, dq16, drelmean, keep, drop);
   return B200CTR_OK;
 }
 
 template <int NT>
-static int ha_launch_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse, const float* d_o,
+static int ha_launch_bwd(const float* qkv, int in16, const float* relmean, int max_len, const float* o, const float* lse, const float* d_o,
                          int64_t B, int K, float* dqkv, int dq16, float* drelmean, const uint32_t* keep, b200ctr_dropout_t drop,
                          cudaStream_t st) {
   constexpr int KS = NT <= 8 ? 1 : 2;
@@ -631,7 +669,7 @@ static int ha_launch_bwd(const float* qkv, const float* relmean, int max_len, co
   const bool on = drop.p > 0.f, use_keep = on && keep != nullptr;
   const size_t smem = ((size_t)4 * 8 * HA_HPC * TSW + 2 * HA_HPC * Kp + 2 * Kp + 16 + (size_t)(HA_HPC * KS) * (2 * KPA + 2) +
                        (KS > 1 ? HA_HPC * 2 * (KS - 1) * 128 : 0) + 64 + (on && !use_keep ? HA_HPC * Kp : 0)) * 4;
-#define HA_ARGS smem, qkv, relmean, max_len, o, lse, d_o, B, K, dqkv, dq16, drelmean, keep, drop, st
+#define HA_ARGS smem, qkv, in16, relmean, max_len, o, lse, d_o, B, K, dqkv, dq16, drelmean, keep, drop, st
   if (!on) return ha_launch_bwd_inst<NT, KS, false, false>(HA_ARGS);
   if (use_keep) return ha_launch_bwd_inst<NT, KS, true, true>(HA_ARGS);
   return ha_launch_bwd_inst<NT, KS, true, false>(HA_ARGS);
@@ -655,7 +693,7 @@ using namespace b200ctr;
 
 extern "C" int64_t b200ctr_attn_h16_drel_rows(int64_t B) { return B * (HA_H / HA_HPC); }
 
-extern "C" int b200ctr_attn_h16_fwd(const float* qkv, const float* relmean, int max_len, int64_t B, int K, int H, int D, float* o,
+extern "C" int b200ctr_attn_h16_fwd(const void* qkv, int qkv_f16, const float* relmean, int max_len, int64_t B, int K, int H, int D, float* o,
                                     float* lse, uint32_t* keep, b200ctr_dropout_t drop, void* stream) {
   B200_REQUIRE(qkv && o && lse, B200CTR_E_INVALID_ARG, "attn_h16_fwd: null pointer");
   B200_REQUIRE(D == HA_D && H == HA_H, B200CTR_E_UNSUPPORTED_SHAPE,
@@ -663,7 +701,7 @@ extern "C" int b200ctr_attn_h16_fwd(const float* qkv, const float* relmean, int 
   B200_REQUIRE(drop.p < 0.96f, B200CTR_E_INVALID_ARG, "attn_h16_fwd: dropout p=%g >= 0.96", (double)drop.p);
   if (B == 0 || K == 0) return B200CTR_OK;
   int rc;
-#define CALL(NT_) ha_launch_fwd<NT_>(qkv, relmean, max_len, B, K, o, lse, keep, drop, as_stream(stream))
+#define CALL(NT_) ha_launch_fwd<NT_>((const float*)qkv, qkv_f16, relmean, max_len, B, K, o, lse, keep, drop, as_stream(stream))
   HA_DISPATCH(CALL)
 #undef CALL
   if (rc) return rc;
@@ -671,7 +709,7 @@ extern "C" int b200ctr_attn_h16_fwd(const float* qkv, const float* relmean, int 
   return B200CTR_OK;
 }
 
-extern "C" int b200ctr_attn_h16_bwd(const float* qkv, const float* relmean, int max_len, const float* o, const float* lse,
+extern "C" int b200ctr_attn_h16_bwd(const void* qkv, int qkv_f16, const float* relmean, int max_len, const float* o, const float* lse,
                                     const float* d_o, int64_t B, int K, int H, int D, void* dqkv, int dqkv_bf16, float* drelmean,
                                     const uint32_t* keep, b200ctr_dropout_t drop, void* stream) {
   B200_REQUIRE(qkv && o && lse && d_o && dqkv, B200CTR_E_INVALID_ARG, "attn_h16_bwd: null pointer");
@@ -680,7 +718,7 @@ extern "C" int b200ctr_attn_h16_bwd(const float* qkv, const float* relmean, int 
   B200_REQUIRE(drop.p < 0.96f, B200CTR_E_INVALID_ARG, "attn_h16_bwd: dropout p=%g >= 0.96", (double)drop.p);
   if (B == 0 || K == 0) return B200CTR_OK;
   int rc;
-#define CALL(NT_) ha_launch_bwd<NT_>(qkv, relmean, max_len, o, lse, d_o, B, K, (float*)dqkv, dqkv_bf16, drelmean, keep, drop, as_stream(stream))
+#define CALL(NT_) ha_launch_bwd<NT_>((const float*)qkv, qkv_f16, relmean, max_len, o, lse, d_o, B, K, (float*)dqkv, dqkv_bf16, drelmean, keep, drop, as_stream(stream))
   HA_DISPATCH(CALL)
 #undef CALL
   if (rc) return rc;

@@ -6,6 +6,9 @@
 
 namespace b200ctr {
 
+// log2(e) / sqrt(head_dim = 8): q is carried times this factor (scores in log2 units); one constant for the kernels that form it
+constexpr float H2_QSCALE = 0.51006972789764404297f;
+
 __device__ __forceinline__ uint32_t h2_pack(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

@@ -13,6 +13,7 @@
 // of dY re-read MN-major) and gets the BIAS gradient from the same MMAs: the B operand (the activation tile viewed
 // MN-major, N = 64) is extended by 16 columns whose first one is all ones, so accumulator column 64 is colsum(dY).
 #include "tc_common.cuh"
+#include "h2_common.cuh"
 #include <cuda_bf16.h>
 #include <algorithm>
 
@@ -97,7 +98,9 @@ template <int NOUT, bool POST_NORM, bool COAL>
 __global__ void __launch_bounds__(PJ_NT, 1)
 lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                const float* __restrict__ resid, const float* __restrict__ nw, float eps, int64_t T,
-               float* __restrict__ y, float* __restrict__ s_out, float* __restrict__ r_out) {
+               float* __restrict__ y, float* __restrict__ s_out, float* __restrict__ r_out, uint32_t* __restrict__ y16, float qscale) {
+  // y16 (NOUT = 192 only): the output goes out as fp16 pairs, (T, NOUT / 2) words, with its first 64 columns (q) times qscale --
+  // the operand format of the packed-half attention kernels (attn_h16.cu), which otherwise convert the fp32 tensor themselves
   constexpr int ACC_STRIDE = NOUT <= 64 ? 64 : 256;
   constexpr int TMEM_COLS = NOUT <= 64 ? 128 : 512;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -220,9 +223,17 @@ lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[eg]));
           }
+          if (y16) {
+            const float sc = cc < 2 ? qscale : 1.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + bs[cc * 32 + j]);
-          warp_store_rows<32>(scr, v, y + m_w * NOUT + cc * 32, NOUT, rows_valid, lane);
+            for (int j = 0; j < 16; ++j)
+              v[j] = h2_pack((__uint_as_float(v[2 * j]) + bs[cc * 32 + 2 * j]) * sc, (__uint_as_float(v[2 * j + 1]) + bs[cc * 32 + 2 * j + 1]) * sc);
+            warp_store_rows<16>(scr, v, reinterpret_cast<float*>(y16) + m_w * (NOUT / 2) + cc * 16, NOUT / 2, rows_valid, lane);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + bs[cc * 32 + j]);
+            warp_store_rows<32>(scr, v, y + m_w * NOUT + cc * 32, NOUT, rows_valid, lane);
+          }
         }
       }
     }
@@ -513,7 +524,7 @@ __global__ void lin_bwd_reduce_kernel(const float* __restrict__ wsp, int n_cta, 
 
 template <int NOUT, bool POST_NORM>
 static int launch_lin_fwd(const float* x, const float* w, const float* bias, const float* resid, const float* nw, float eps,
-                          int64_t T, float* y, float* s_out, float* r_out, cudaStream_t st) {
+                          int64_t T, float* y, float* s_out, float* r_out, cudaStream_t st, uint32_t* y16 = nullptr, float qscale = 1.f) {
   const size_t smem = (size_t)NOUT * 128 + 2 * PJ_X_BYTES + ((size_t)NOUT + PJ_D) * 4 +
                       (size_t)8 * 32 * ((POST_NORM ? 64 : 32) + 4) * 4 + sizeof(PjFwdBars) + 16;
   // measured on B200: the coalesced loader wins for the 64-wide kernel (0.103 vs 0.117 ms per launch), the row-per-lane
@@ -522,7 +533,7 @@ static int launch_lin_fwd(const float* x, const float* w, const float* bias, con
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(lin_fwd smem)");
   const int grid = (int)std::min<int64_t>(ceil_div(T, (int64_t)PJ_TM), (int64_t)num_sms());
-  fn<<<grid, PJ_NT, smem, st>>>(x, w, bias, resid, nw, eps, T, y, s_out, r_out);
+  fn<<<grid, PJ_NT, smem, st>>>(x, w, bias, resid, nw, eps, T, y, s_out, r_out, y16, qscale);
   return B200CTR_OK;
 }
 
@@ -556,6 +567,18 @@ extern "C" int b200ctr_inproj_fwd(const float* x, const float* w_in, const float
   int rc = launch_lin_fwd<192, false>(x, w_in, b_in, nullptr, nullptr, 0.f, T, qkv, nullptr, nullptr, as_stream(stream));
   if (rc) return rc;
   B200_LAUNCH_CHECK("lin_fwd_kernel<192>");
+  return B200CTR_OK;
+}
+
+extern "C" int b200ctr_inproj_fwd_h16(const float* x, const float* w_in, const float* b_in, int64_t T, int D, void* qkv16, void* stream) {
+  B200_REQUIRE(x && w_in && qkv16, B200CTR_E_INVALID_ARG, "inproj_fwd_h16: null pointer");
+  B200_REQUIRE(D == PJ_D, B200CTR_E_UNSUPPORTED_SHAPE, "inproj_fwd_h16: D=%d unsupported (64 only)", D);
+  if (T == 0) return B200CTR_OK;
+  // q leaves pre-multiplied by log2(e) / sqrt(head_dim): exactly the value attn_h16 would form from the fp32 tensor
+  int rc = launch_lin_fwd<192, false>(x, w_in, b_in, nullptr, nullptr, 0.f, T, nullptr, nullptr, nullptr, as_stream(stream),
+                                      (uint32_t*)qkv16, H2_QSCALE);
+  if (rc) return rc;
+  B200_LAUNCH_CHECK("lin_fwd_kernel<192,h16>");
   return B200CTR_OK;
 }
 
