@@ -497,20 +497,25 @@ def rooflines(cfg, B, steps, prof, host, used, args):
                 M_, N_, K_ = tag[len(fn_) + 1:-3].split("x")
                 gemm_flops[fn_] += 2.0 * int(M_) * int(N_) * int(K_) * n
     keep_b = 4.0 * B * 8 * ((Kk + 15) // 16) * ((2 * ((Kk + 15) // 16) + 7) // 8) * 32      # attention keep-bit words per launch
+    # bytes per qkv element on the wire between the in-projection and the attention kernels: fp16 when the packed-half attention
+    # runs (ops.attn_takes_h16), fp32 otherwise
+    from b200ctr import ops as _ops
+    with _ops.precision("bf16" if cfg.get("amp") == "bf16" else "fp32"):
+        qkv_b = 2.0 if _ops.attn_takes_h16(Kk, 8, D) else 4.0
     models = {   # family -> (bound, work per launch [FLOP or byte], description); "both": the BINDING roof is reported
-        "attn_tc_bwd": ("both", (10.0 * Kk * Kk * D * B, T * (4.0 * 3 * D + 4.0 * D + 4.0 * D + 2.0 * 3 * D) + 4.0 * B * 8 * Kk + keep_b),
+        "attn_tc_bwd": ("both", (10.0 * Kk * Kk * D * B, T * (qkv_b * 3 * D + 4.0 * D + 4.0 * D + 2.0 * 3 * D) + 4.0 * B * 8 * Kk + keep_b),
                         "attn_h16_bwd_kernel (packed-half attention backward, head_dim 8: fp16-accumulate score MMAs, half2 exp / mask / dS, "
-                        "fp32-accumulate dQ / dK / dV MMAs; one pass = 10 K^2 D FLOP/sample; qkv, o, d_o, lse, keep bits in, bf16 dqkv out)"),
-        "attn_tc_fwd": ("both", (4.0 * Kk * Kk * D * B, T * (4.0 * 3 * D + 4.0 * D) + 4.0 * B * 8 * Kk + keep_b),
+                        "fp32-accumulate dQ / dK / dV MMAs; one pass = 10 K^2 D FLOP/sample; fp16 qkv, o, d_o, lse, keep bits in, bf16 dqkv out)"),
+        "attn_tc_fwd": ("both", (4.0 * Kk * Kk * D * B, T * (qkv_b * 3 * D + 4.0 * D) + 4.0 * B * 8 * Kk + keep_b),
                         "attn_h16_fwd_kernel (packed-half attention forward: QK^T + bias in one fp16-accumulate MMA, half2 softmax / dropout, "
-                        "PV and the row sums on fp32-accumulate MMAs = 4 K^2 D FLOP/sample; qkv in, o, lse, keep bits out)"),
+                        "PV and the row sums on fp32-accumulate MMAs = 4 K^2 D FLOP/sample; fp16 qkv in, o, lse, keep bits out)"),
         "ffn_fwd": ("both", (4.0 * T * D * hid, T * (4.0 * D * 3 + 4.0 + hid / 8.0)),
                     "ffn_fwd_kernel (tcgen05 fused FFN block: 2 contractions of T x 64 x ffn_hidden, half2 GELU / dropout epilogue, fp16 "
                     "activation operand; x1 in, s2, x2, r2, keep bits out)"),
         "ffn_bwd": ("both", (8.0 * T * D * hid, T * (4.0 * D * 4 + 4.0 + hid / 8.0)),
                     "ffn_bwd1/ffn_bwd2 (tcgen05 fused FFN backward: 4 algorithmic contractions, the recompute and the internal bf16 "
                     "dpre spill are not counted; dy, s2, x1, r2, keep bits in, dx1 out)"),
-        "inproj_fwd": ("hbm", 4.0 * T * (D + 3 * D), "lin_fwd_kernel<192> (x in, qkv out)"),
+        "inproj_fwd": ("hbm", T * (4.0 * D + qkv_b * 3 * D), "lin_fwd_kernel<192> (x in, qkv out -- fp16 for the packed-half attention)"),
         "outproj_norm_fwd": ("hbm", 4.0 * T * D * 4 + 4.0 * T, "lin_fwd_kernel<64,norm> (o, x in; s1, x1, r1 out)"),
         "outproj_norm_bwd": ("hbm", 4.0 * T * D * 5, "lin_bwd_kernel<64,norm> (dx1, s1, o in; d_s1, d_o out)"),
         "inproj_bwd": ("hbm", 2.0 * T * 3 * D + 4.0 * T * 3 * D, "lin_bwd_kernel<192> (bf16 dqkv, x, d_s1 in; dx out)"),
