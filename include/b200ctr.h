@@ -261,11 +261,13 @@ int b200ctr_attn_tc_bwd(const float* qkv, const float* relmean, int max_len, con
 int64_t b200ctr_attn_h16_drel_rows(int64_t B);
 /* qkv_f16 != 0: qkv is the (M, 3D) fp16 tensor written by b200ctr_inproj_fwd_h16 (q already times log2(e) / sqrt(hd)): the
  * kernels then stage their operands with plain copies -- same values, half the bytes; 0: the fp32 tensor of the other kernels. */
+/* o_bf16 / do_bf16 != 0: o (written by the forward, read by the backward) and d_o (read by the backward) are bf16 (M, D): see
+ * b200ctr_outproj_norm_fwd/bwd.                                                                                         */
 int b200ctr_attn_h16_fwd(const void* qkv, int qkv_f16, const float* relmean, int max_len, int64_t B, int K, int H, int D,
-                         float* o, float* lse, uint32_t* keep, b200ctr_dropout_t drop, void* stream);
-int b200ctr_attn_h16_bwd(const void* qkv, int qkv_f16, const float* relmean, int max_len, const float* o, const float* lse,
-                         const float* d_o, int64_t B, int K, int H, int D, void* dqkv, int dqkv_bf16, float* drelmean,
-                         const uint32_t* keep, b200ctr_dropout_t drop, void* stream);
+                         void* o, int o_bf16, float* lse, uint32_t* keep, b200ctr_dropout_t drop, void* stream);
+int b200ctr_attn_h16_bwd(const void* qkv, int qkv_f16, const float* relmean, int max_len, const void* o, int o_bf16,
+                         const float* lse, const void* d_o, int do_bf16, int64_t B, int K, int H, int D, void* dqkv,
+                         int dqkv_bf16, float* drelmean, const uint32_t* keep, b200ctr_dropout_t drop, void* stream);
 int b200ctr_add_rmsnorm_fwd(const float* a, const float* b, const float* w, float eps, int64_t M, int D,
                             float* s_out, float* y_out, float* r_out, void* stream);
 /* dx = rmsnorm'(dy) (+ dx_add) ; dw: (b200ctr_rmsnorm_bwd_rows(M), D) PARTIAL sums of dy*s*r, one row per CTA, every entry
@@ -312,12 +314,15 @@ int b200ctr_inproj_fwd(const float* x, const float* w_in, const float* b_in, int
 /* the same projection with qkv written as fp16 (T, 192), its q third times log2(e) / sqrt(head_dim = 8): the operand format of
  * b200ctr_attn_h16_fwd/bwd(qkv_f16 = 1) -- bit-identical attention results, half the qkv traffic in three kernels            */
 int b200ctr_inproj_fwd_h16(const float* x, const float* w_in, const float* b_in, int64_t T, int D, void* qkv16, void* stream);
-int b200ctr_outproj_norm_fwd(const float* o, const float* w_out, const float* b_out, const float* x_resid,
+/* o_bf16 / do_bf16: the attention output o and its gradient d_o travel as bf16 (T, 64) between the packed-half attention
+ * kernels and the out-projection: both projections' tensor-core products round them to bf16 in any case, so only the attention
+ * backward's D = dO . o sees the narrower type (the reference's autocast keeps both in bf16 as well).                        */
+int b200ctr_outproj_norm_fwd(const void* o, int o_bf16, const float* w_out, const float* b_out, const float* x_resid,
                              const float* n1w, float eps, int64_t T, int D, float* s1_out, float* r1_out,
                              float* x1_out, void* stream);
 int64_t b200ctr_proj_bwd_workspace_bytes(void);
-int b200ctr_outproj_norm_bwd(const float* dx1, const float* s1, const float* r1, const float* n1w, const float* o,
-                             const float* w_out, int64_t T, int D, float* ds1_out, float* d_o, float* dw_out,
+int b200ctr_outproj_norm_bwd(const float* dx1, const float* s1, const float* r1, const float* n1w, const void* o, int o_bf16,
+                             const float* w_out, int64_t T, int D, float* ds1_out, void* d_o, int do_bf16, float* dw_out,
                              float* db_out, float* dn1, void* workspace, void* stream);
 int b200ctr_inproj_bwd(const void* dqkv, int dqkv_bf16, const float* x, const float* w_in, const float* d_resid, int64_t T,
                        int D, float* dx, float* dw_in, float* db_in, void* workspace, void* stream);

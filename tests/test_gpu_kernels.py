@@ -425,6 +425,44 @@ def test_attn_h16_fp16_qkv_is_bit_identical_to_the_fp32_route(dev, B, K, p):
         ops.attn_fwd(qkv16, relmean, K, B, K, 8, 64, dr, tc=True, impl="tf32")        # the TF32 kernels take the fp32 tensor only
 
 
+# bf16 o / d_o hand-offs between the packed-half attention and the out-projection: every kernel with a bf16 port must give,
+# bit for bit, what its fp32 port gives when fed the bf16-rounded values (inputs), resp. its fp32 output rounded once (outputs).
+@pytest.mark.parametrize("B,K,p", [(3, 60, 0.1), (2, 100, 0.0), (3, 17, 0.1)])
+def test_bf16_o_and_do_handoffs_are_exact_restatements(dev, B, K, p):
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(3 * B + K)
+    T = B * K
+    qkv = (_rand(g, T, 192) * 0.8).to(dev)
+    relmean = (_rand(g, 2 * K + 1) * 0.5).to(dev)
+    dr = ops.drop(p, 21, 9)
+    bf = lambda t: t.to(torch.bfloat16)
+    # attention forward: bf16 o == fp32 o rounded once
+    o32, lse, keep = ops.attn_fwd(qkv, relmean, K, B, K, 8, 64, dr, tc=True, save_keep=True, impl="h16")
+    o16, lse2, keep2 = ops.attn_fwd(qkv, relmean, K, B, K, 8, 64, dr, tc=True, save_keep=True, impl="h16", out_bf16=True)
+    assert o16.dtype == torch.bfloat16 and torch.equal(o16, bf(o32)) and torch.equal(lse, lse2)
+    # attention backward: bf16 o / d_o ports == fp32 ports fed the rounded values
+    d_o = (_rand(g, T, 64) * 1e-4).to(dev)
+    ra, rb = torch.zeros_like(relmean), torch.zeros_like(relmean)
+    dq_a = ops.attn_bwd(qkv, relmean, K, o16.float(), lse, bf(d_o).float(), B, K, 8, 64, ra, dr, tc=True, keep=keep, out_bf16=True, impl="h16")
+    dq_b = ops.attn_bwd(qkv, relmean, K, o16, lse, bf(d_o), B, K, 8, 64, rb, dr, tc=True, keep=keep, out_bf16=True, impl="h16")
+    assert torch.equal(dq_a, dq_b) and torch.equal(ra, rb)
+    # out-projection forward / backward
+    w_out, b_out, n1 = (_rand(g, 64, 64) * 0.2).to(dev), (_rand(g, 64) * 0.1).to(dev), (1 + 0.1 * _rand(g, 64)).to(dev)
+    x = _rand(g, T, 64).to(dev)
+    with ops.precision("bf16"):
+        s1a, x1a, r1a = ops.outproj_norm_fwd(o16.float(), w_out, b_out, x, n1)
+        s1b, x1b, r1b = ops.outproj_norm_fwd(o16, w_out, b_out, x, n1)
+        assert torch.equal(s1a, s1b) and torch.equal(x1a, x1b) and torch.equal(r1a, r1b)
+        dx1 = (_rand(g, T, 64) * 1e-3).to(dev)
+        z = lambda *sh: torch.zeros(*sh, device=dev)
+        ga, gb = (z(64, 64), z(64), z(64)), (z(64, 64), z(64), z(64))
+        ds_a, do_a = ops.outproj_norm_bwd(dx1, s1a, r1a, n1, o16.float(), w_out, *ga)
+        ds_b, do_b = ops.outproj_norm_bwd(dx1, s1a, r1a, n1, o16, w_out, *gb, out_bf16=True)
+        assert do_b.dtype == torch.bfloat16 and torch.equal(do_b, bf(do_a)) and torch.equal(ds_a, ds_b)
+        for a_, b_ in zip(ga, gb):
+            assert torch.equal(a_, b_)
+
+
 @pytest.mark.parametrize("B,H,R,P", [(1000, 6, 16, 192), (7, 6, 16, 192), (300, 8, 32, 128), (64, 2, 4, 24)])
 def test_headproj_matches_einsum(dev, B, H, R, P):
     from b200ctr import ops

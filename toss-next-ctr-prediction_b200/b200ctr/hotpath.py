@@ -134,8 +134,11 @@ def encoder_layer_fwd(x: Tensor, P: Dict[str, Tensor], i: int, spec: ModelSpec, 
     fused_proj = ops.get_precision() == "bf16" and D == 64 and H == 8
     if fused_proj:        # persistent tcgen05 kernels with resident weights (csrc/proj_fused.cu)
         # packed-half attention: qkv leaves the projection as fp16 (q pre-scaled), the attention kernels stage it with copies
-        qkv = ops.inproj_fwd(x, P[n["in_w"]], P[n["in_b"]], h16=ops.attn_takes_h16(K, H, D))
-        o, lse, keep = ops.attn_fwd(qkv, relmean, spec.top_k, B, K, H, D, dc(spec.p_mha, SITE_LAYER0 + 2 * i), save_keep=True)
+        # and hand o to the out-projection as bf16 (its tensor-core products round it to bf16 in any case)
+        h16 = ops.attn_takes_h16(K, H, D)
+        qkv = ops.inproj_fwd(x, P[n["in_w"]], P[n["in_b"]], h16=h16)
+        o, lse, keep = ops.attn_fwd(qkv, relmean, spec.top_k, B, K, H, D, dc(spec.p_mha, SITE_LAYER0 + 2 * i), save_keep=True,
+                                    out_bf16=h16)
         s1, x1, r1 = ops.outproj_norm_fwd(o, P[n["out_w"]], P[n["out_b"]], x, P[n["n1"]])
     else:
         qkv = ops.gemm(x, P[n["in_w"]], trans_b=True, bias=P[n["in_b"]])
@@ -179,8 +182,9 @@ def encoder_layer_bwd(dy: Tensor, sv: dict, P: Dict[str, Tensor], i: int, spec: 
         dx1 = ops.gemm(dpre, P[n["f1_w"]], residual=d_s2)
     fused_proj = sv.get("fused_proj", False)
     if fused_proj:
+        # d_o goes to the packed-half attention backward as bf16 (recognised by the dtype of the saved qkv)
         d_s1, d_o = ops.outproj_norm_bwd(dx1, sv["s1"], sv["r1"], P[n["n1"]], sv["o"], P[n["out_w"]], G(n["out_w"]),
-                                         G(n["out_b"]), G(n["n1"]))
+                                         G(n["out_b"]), G(n["n1"]), out_bf16=sv["qkv"].dtype == torch.float16)
     else:
         d_s1 = ops.rmsnorm_bwd(dx1, sv["s1"], P[n["n1"]], sv["r1"], G(n["n1"]))
         ops.gemm(d_s1, sv["o"], trans_a=True, out=G(n["out_w"]))

@@ -557,20 +557,21 @@ def _attn_impl(impl: Optional[str]) -> str:
 
 
 def attn_fwd(qkv, relmean, max_len, B, K, H, D, dropout=NO_DROP, tc: Optional[bool] = None, save_keep: bool = False,
-             impl: Optional[str] = None):
+             impl: Optional[str] = None, out_bf16: bool = False):
     """Returns (o, lse), or (o, lse, keep) with save_keep: keep = the dropout keep-flag words the tensor-core backward reads
     instead of re-hashing (None when dropout is off or the fp32 kernels run)."""
     lib = _lib.load()
-    o = torch.empty((B * K, D), device=qkv.device, dtype=torch.float32)
-    lse = torch.empty((B, H, K), device=qkv.device, dtype=torch.float32)
     use_tc = _attn_tc(tc, K, H, D)
+    out_bf16 = bool(out_bf16 and use_tc and _attn_impl(impl) == "h16")      # packed-half kernels only: o as bf16 for the out-projection
+    o = torch.empty((B * K, D), device=qkv.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    lse = torch.empty((B, H, K), device=qkv.device, dtype=torch.float32)
     keep = None
     if use_tc:
         if save_keep and dropout.p > 0.0:
             keep = torch.empty((int(lib.b200ctr_attn_tc_keep_words(B, K)),), device=qkv.device, dtype=torch.int32)
         if _attn_impl(impl) == "h16":
             _run("attn_tc_fwd", lib.b200ctr_attn_h16_fwd, _p(qkv), int(qkv.dtype == torch.float16), _p(relmean), max_len, B, K, H, D,
-                 _p(o), _p(lse), _p(keep), dropout, _stream())
+                 _p(o), int(out_bf16), _p(lse), _p(keep), dropout, _stream())
         else:
             _qkv_f32(qkv)
             _run("attn_tc_fwd", lib.b200ctr_attn_tc_fwd, _p(qkv), _p(relmean), max_len, B, K, H, D, _p(o), _p(lse), _p(keep), dropout,
@@ -595,8 +596,9 @@ def attn_bwd(qkv, relmean, max_len, o, lse, d_o, B, K, H, D, drelmean, dropout=N
         drelmean = torch.zeros((rows, 2 * max_len + 1), device=qkv.device, dtype=torch.float32)
     if use_tc:
         if h16:
-            _run("attn_tc_bwd", lib.b200ctr_attn_h16_bwd, _p(qkv), int(qkv.dtype == torch.float16), _p(relmean), max_len, _p(o), _p(lse),
-                 _p(d_o), B, K, H, D, _p(dqkv), int(out_bf16), _p(drelmean), _p(keep), dropout, _stream())
+            _run("attn_tc_bwd", lib.b200ctr_attn_h16_bwd, _p(qkv), int(qkv.dtype == torch.float16), _p(relmean), max_len, _p(o),
+                 int(o.dtype == torch.bfloat16), _p(lse), _p(d_o), int(d_o.dtype == torch.bfloat16), B, K, H, D, _p(dqkv), int(out_bf16),
+                 _p(drelmean), _p(keep), dropout, _stream())
         else:
             _qkv_f32(qkv)
             _run("attn_tc_bwd", lib.b200ctr_attn_tc_bwd, _p(qkv), _p(relmean), max_len, _p(o), _p(lse), _p(d_o), B, K, H, D, _p(dqkv),
@@ -647,10 +649,11 @@ def outproj_norm_fwd(o, w_out, b_out, x_resid, n1w, eps=1e-6):
     """Returns (s1, x1, r1) like add_rmsnorm_fwd(x_resid, o @ w_out^T + b_out, n1w)."""
     lib = _lib.load()
     T, D = o.shape
-    s1, x1 = torch.empty_like(o), torch.empty_like(o)
+    s1, x1 = torch.empty_like(x_resid), torch.empty_like(x_resid)
     r1 = torch.empty((T,), device=o.device, dtype=torch.float32)
-    _run("outproj_norm_fwd", lib.b200ctr_outproj_norm_fwd, _p(_f32(o)), _p(w_out), _p(b_out), _p(x_resid), _p(n1w), eps, T, D,
-         _p(s1), _p(r1), _p(x1), _stream())
+    o16 = o.dtype == torch.bfloat16                 # bf16 o from attn_fwd(out_bf16=True): staged with plain copies
+    _run("outproj_norm_fwd", lib.b200ctr_outproj_norm_fwd, _p(o if o16 else _f32(o)), int(o16), _p(w_out), _p(b_out), _p(x_resid), _p(n1w),
+         eps, T, D, _p(s1), _p(r1), _p(x1), _stream())
     _count()
     return s1, x1, r1
 
@@ -659,14 +662,16 @@ def _proj_ws(dev):
     return torch.empty((_lib.load().b200ctr_proj_bwd_workspace_bytes(),), device=dev, dtype=torch.uint8)
 
 
-def outproj_norm_bwd(dx1, s1, r1, n1w, o, w_out, dw_out, db_out, dn1):
-    """Returns (d_s1, d_o); overwrites dw_out, db_out, dn1."""
+def outproj_norm_bwd(dx1, s1, r1, n1w, o, w_out, dw_out, db_out, dn1, out_bf16: bool = False):
+    """Returns (d_s1, d_o); overwrites dw_out, db_out, dn1.  o may be bf16 (attn_fwd(out_bf16=True)); out_bf16: d_o comes back as
+    bf16 for the packed-half attention backward."""
     lib = _lib.load()
     T, D = o.shape
-    ds1, d_o = torch.empty_like(o), torch.empty_like(o)
+    ds1 = torch.empty_like(s1)
+    d_o = torch.empty((T, D), device=o.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
     ws = _proj_ws(o.device)
-    _run("outproj_norm_bwd", lib.b200ctr_outproj_norm_bwd, _p(_f32(dx1)), _p(s1), _p(r1), _p(n1w), _p(o), _p(w_out), T, D, _p(ds1),
-         _p(d_o), _p(dw_out), _p(db_out), _p(dn1), _p(ws), _stream())
+    _run("outproj_norm_bwd", lib.b200ctr_outproj_norm_bwd, _p(_f32(dx1)), _p(s1), _p(r1), _p(n1w), _p(o), int(o.dtype == torch.bfloat16),
+         _p(w_out), T, D, _p(ds1), _p(d_o), int(out_bf16), _p(dw_out), _p(db_out), _p(dn1), _p(ws), _stream())
     _count(2)
     return ds1, d_o
 

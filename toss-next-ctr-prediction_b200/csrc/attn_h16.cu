@@ -198,12 +198,32 @@ __device__ __forceinline__ void ha_key_masks(int kc, int K, uint32_t& andm, uint
   orm = (v0 ? 0u : 0xfc00u) | (v1 ? 0u : 0xfc000000u);
 }
 
+// two adjacent elements at element offset `off` of an output tensor: fp32 pair or one packed bf16 pair
+__device__ __forceinline__ void ha_store2(float* base, int as_bf16, int64_t off, float a, float b) {
+  if (as_bf16) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    reinterpret_cast<uint32_t*>(base)[off >> 1] = r;
+  } else {
+    *reinterpret_cast<float2*>(base + off) = make_float2(a, b);
+  }
+}
+
+// four consecutive elements of an fp32 or bf16 tensor at element offset `off` (a multiple of 4)
+__device__ __forceinline__ float4 ha_load4(const float* base, int is_bf16, int64_t off) {
+  if (!is_bf16) return *reinterpret_cast<const float4*>(base + off);
+  const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + off);
+  return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xffff0000u));
+}
+
 // NT = number of 8-key tiles (keys padded to a multiple of 16).  Like the backward, two CTAs per sample with four heads each
 // (one warp per head): half the staging per CTA, twice as many CTAs to hide it behind.
 template <int NT, bool DROP>
 __global__ void __launch_bounds__(32 * HA_HPC, (NT <= 14 ? 32 : 24) / HA_HPC)
 attn_h16_fwd_kernel(const float* __restrict__ qkv, int in16, const float* __restrict__ relmean, int max_len, int K,
-                    float* __restrict__ o, float* __restrict__ lse, uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
+                    float* __restrict__ o, int o16, float* __restrict__ lse, uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
+  // o16: o is written as bf16 (same (M, 64) layout) -- both of its consumers' tensor-core products (the out-projection and its
+  // weight gradient) round it to bf16 anyway, so only the backward's D = dO . o sees the rounding
   constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2, NW = (NT + 7) / 8, TS = Kp + 8, TSW = TS / 2, NBP = 2 * Kp + 16;
   constexpr bool KEEP_S = NT <= 8;
   extern __shared__ __align__(16) uint32_t sm_u[];
@@ -320,25 +340,14 @@ attn_h16_fwd_kernel(const float* __restrict__ qkv, int in16, const float* __rest
     }
     if (qa < K) {
       const float inv = dctx.inv / ls[0];
-      *reinterpret_cast<float2*>(o + (b * K + qa) * (int64_t)HA_D + h * 8 + 2 * t) = make_float2(oc[0] * inv, oc[1] * inv);
+      ha_store2(o, o16, (b * K + qa) * (int64_t)HA_D + h * 8 + 2 * t, oc[0] * inv, oc[1] * inv);
       if (t == 0) lse[(b * HA_H + h) * (int64_t)K + qa] = (h2_lo(pk) + log2f(ls[0])) * HA_LN2;       // natural-log units
     }
     if (qb < K) {
       const float inv = dctx.inv / ls[2];
-      *reinterpret_cast<float2*>(o + (b * K + qb) * (int64_t)HA_D + h * 8 + 2 * t) = make_float2(oc[2] * inv, oc[3] * inv);
+      ha_store2(o, o16, (b * K + qb) * (int64_t)HA_D + h * 8 + 2 * t, oc[2] * inv, oc[3] * inv);
       if (t == 0) lse[(b * HA_H + h) * (int64_t)K + qb] = (h2_hi(pk) + log2f(ls[2])) * HA_LN2;
     }
-  }
-}
-
-// two adjacent gradient elements at element offset `off` of the (M, 192) tensor: fp32 pair or one packed bf16 pair
-__device__ __forceinline__ void ha_store2(float* base, int as_bf16, int64_t off, float a, float b) {
-  if (as_bf16) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-    reinterpret_cast<uint32_t*>(base)[off >> 1] = r;
-  } else {
-    *reinterpret_cast<float2*>(base + off) = make_float2(a, b);
   }
 }
 
@@ -352,8 +361,9 @@ __device__ __forceinline__ void ha_store2(float* base, int as_bf16, int64_t off,
 template <int NT, int KS, bool DROP, bool KEEP>
 __global__ void __launch_bounds__(32 * HA_HPC * KS, (KS == 1 ? 24 : 8) / HA_HPC)
 attn_h16_bwd_kernel(const float* __restrict__ qkv, int in16, const float* __restrict__ relmean, int max_len, const float* __restrict__ o,
-                    const float* __restrict__ lse, const float* __restrict__ d_o, int K, float* __restrict__ dqkv, int dq16,
-                    float* __restrict__ drelmean, const uint32_t* __restrict__ keep, b200ctr_dropout_t drop) {
+                    const float* __restrict__ lse, const float* __restrict__ d_o, int io16 /* bit 0: o is bf16, bit 1: d_o is bf16 */,
+                    int K, float* __restrict__ dqkv, int dq16, float* __restrict__ drelmean, const uint32_t* __restrict__ keep,
+                    b200ctr_dropout_t drop) {
   constexpr int Kp = NT * 8, MT = NT / 2, NB = NT / 2, NW = (NT + 7) / 8, TS = Kp + 8, TSW = TS / 2, NBP = 2 * Kp + 16;
   constexpr int NTH = 32 * HA_HPC * KS, HPC = HA_HPC, QD = 2 * HA_HPC;
   constexpr int NBW = (NB + KS - 1) / KS;                     // 16-key blocks per warp
@@ -375,8 +385,7 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, int in16, const float* __rest
   const int64_t b = blockIdx.x / (HA_H / HPC);
   const int hbase = (int)(blockIdx.x % (HA_H / HPC)) * HPC, dim0 = hbase * 8;      // first head / first column of this CTA
   const float* base = qkv + b * (int64_t)K * 3 * HA_D + dim0;
-  const float* dob = d_o + b * (int64_t)K * HA_D + dim0;
-  const float* ob = o + b * (int64_t)K * HA_D + dim0;
+  const int64_t io_off = b * (int64_t)K * HA_D + dim0;          // element offset of this CTA's columns of row 0 in o / d_o
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const DropCtx dctx = drop_ctx(drop);
   // dO, the head-partial dot product dO . o (D = sum_j P_ij c_ij dP_ij = dO_i . o_i holds with the dropped-and-rescaled o the
@@ -394,8 +403,8 @@ attn_h16_bwd_kernel(const float* __restrict__ qkv, int in16, const float* __rest
       const bool ok = un.act && row < K;
       xd[it][r] = make_float4(0.f, 0.f, 0.f, 0.f); Ls[it][r] = 0.f; dro[it][r] = 0.f;
       if (ok) {
-        xd[it][r] = *reinterpret_cast<const float4*>(dob + (int64_t)row * HA_D + 4 * un.c);
-        const float4 oo = *reinterpret_cast<const float4*>(ob + (int64_t)row * HA_D + 4 * un.c);
+        xd[it][r] = ha_load4(d_o, io16 & 2, io_off + (int64_t)row * HA_D + 4 * un.c);
+        const float4 oo = ha_load4(o, io16 & 1, io_off + (int64_t)row * HA_D + 4 * un.c);
         Ls[it][r] = lse[(b * HA_H + hbase + (un.c >> 1)) * (int64_t)K + row];
         dro[it][r] = xd[it][r].x * oo.x + xd[it][r].y * oo.y + xd[it][r].z * oo.z + xd[it][r].w * oo.w;
       }
@@ -636,7 +645,7 @@ static int ha_set_smem(const void* fn, size_t bytes) {
 }
 
 template <int NT>
-static int ha_launch_fwd(const float* qkv, int in16, const float* relmean, int max_len, int64_t B, int K, float* o, float* lse,
+static int ha_launch_fwd(const float* qkv, int in16, const float* relmean, int max_len, int64_t B, int K, float* o, int o16, float* lse,
                          uint32_t* keep, b200ctr_dropout_t drop, cudaStream_t st) {
   constexpr int Kp = NT * 8, TSW = (Kp + 8) / 2;
   const bool on = drop.p > 0.f;
@@ -644,32 +653,32 @@ static int ha_launch_fwd(const float* qkv, int in16, const float* relmean, int m
   int rc = on ? ha_set_smem((const void*)attn_h16_fwd_kernel<NT, true>, smem) : ha_set_smem((const void*)attn_h16_fwd_kernel<NT, false>, smem);
   if (rc) return rc;
   const unsigned grid = (unsigned)(B * (HA_H / HA_HPC));
-  if (on) attn_h16_fwd_kernel<NT, true><<<grid, 32 * HA_HPC, smem, st>>>(qkv, in16, relmean, max_len, K, o, lse, keep, drop);
-  else attn_h16_fwd_kernel<NT, false><<<grid, 32 * HA_HPC, smem, st>>>(qkv, in16, relmean, max_len, K, o, lse, keep, drop);
+  if (on) attn_h16_fwd_kernel<NT, true><<<grid, 32 * HA_HPC, smem, st>>>(qkv, in16, relmean, max_len, K, o, o16, lse, keep, drop);
+  else attn_h16_fwd_kernel<NT, false><<<grid, 32 * HA_HPC, smem, st>>>(qkv, in16, relmean, max_len, K, o, o16, lse, keep, drop);
   return B200CTR_OK;
 }
 
 template <int NT, int KS, bool DROP, bool KEEP>
 static int ha_launch_bwd_inst(size_t smem, const float* qkv, int in16, const float* relmean, int max_len, const float* o, const float* lse,
-                              const float* d_o, int64_t B, int K, float* dqkv, int dq16, float* drelmean, const uint32_t* keep,
+                              const float* d_o, int io16, int64_t B, int K, float* dqkv, int dq16, float* drelmean, const uint32_t* keep,
                               b200ctr_dropout_t drop, cudaStream_t st) {
   int rc = ha_set_smem((const void*)attn_h16_bwd_kernel<NT, KS, DROP, KEEP>, smem);
   if (rc) return rc;
   attn_h16_bwd_kernel<NT, KS, DROP, KEEP><<<(unsigned)(B * (HA_H / HA_HPC)), 32 * HA_HPC * KS, smem, st>>>(
-      qkv, in16, relmean, max_len, o, lse, d_o, K, dqkv, dq16, drelmean, keep, drop);
+      qkv, in16, relmean, max_len, o, lse, d_o, io16, K, dqkv, dq16, drelmean, keep, drop);
   return B200CTR_OK;
 }
 
 template <int NT>
 static int ha_launch_bwd(const float* qkv, int in16, const float* relmean, int max_len, const float* o, const float* lse, const float* d_o,
-                         int64_t B, int K, float* dqkv, int dq16, float* drelmean, const uint32_t* keep, b200ctr_dropout_t drop,
+                         int io16, int64_t B, int K, float* dqkv, int dq16, float* drelmean, const uint32_t* keep, b200ctr_dropout_t drop,
                          cudaStream_t st) {
   constexpr int KS = NT <= 8 ? 1 : 2;
   constexpr int Kp = NT * 8, TSW = (Kp + 8) / 2, NBW = (NT / 2 + KS - 1) / KS, KPA = 16 * NBW * KS;
   const bool on = drop.p > 0.f, use_keep = on && keep != nullptr;
   const size_t smem = ((size_t)4 * 8 * HA_HPC * TSW + 2 * HA_HPC * Kp + 2 * Kp + 16 + (size_t)(HA_HPC * KS) * (2 * KPA + 2) +
                        (KS > 1 ? HA_HPC * 2 * (KS - 1) * 128 : 0) + 64 + (on && !use_keep ? HA_HPC * Kp : 0)) * 4;
-#define HA_ARGS smem, qkv, in16, relmean, max_len, o, lse, d_o, B, K, dqkv, dq16, drelmean, keep, drop, st
+#define HA_ARGS smem, qkv, in16, relmean, max_len, o, lse, d_o, io16, B, K, dqkv, dq16, drelmean, keep, drop, st
   if (!on) return ha_launch_bwd_inst<NT, KS, false, false>(HA_ARGS);
   if (use_keep) return ha_launch_bwd_inst<NT, KS, true, true>(HA_ARGS);
   return ha_launch_bwd_inst<NT, KS, true, false>(HA_ARGS);
@@ -693,15 +702,15 @@ using namespace b200ctr;
 
 extern "C" int64_t b200ctr_attn_h16_drel_rows(int64_t B) { return B * (HA_H / HA_HPC); }
 
-extern "C" int b200ctr_attn_h16_fwd(const void* qkv, int qkv_f16, const float* relmean, int max_len, int64_t B, int K, int H, int D, float* o,
-                                    float* lse, uint32_t* keep, b200ctr_dropout_t drop, void* stream) {
+extern "C" int b200ctr_attn_h16_fwd(const void* qkv, int qkv_f16, const float* relmean, int max_len, int64_t B, int K, int H, int D, void* o,
+                                    int o_bf16, float* lse, uint32_t* keep, b200ctr_dropout_t drop, void* stream) {
   B200_REQUIRE(qkv && o && lse, B200CTR_E_INVALID_ARG, "attn_h16_fwd: null pointer");
   B200_REQUIRE(D == HA_D && H == HA_H, B200CTR_E_UNSUPPORTED_SHAPE,
                "attn_h16_fwd: only emb_dim=64 with 8 heads of head_dim=8 is built (got D=%d, H=%d)", D, H);
   B200_REQUIRE(drop.p < 0.96f, B200CTR_E_INVALID_ARG, "attn_h16_fwd: dropout p=%g >= 0.96", (double)drop.p);
   if (B == 0 || K == 0) return B200CTR_OK;
   int rc;
-#define CALL(NT_) ha_launch_fwd<NT_>((const float*)qkv, qkv_f16, relmean, max_len, B, K, o, lse, keep, drop, as_stream(stream))
+#define CALL(NT_) ha_launch_fwd<NT_>((const float*)qkv, qkv_f16, relmean, max_len, B, K, (float*)o, o_bf16, lse, keep, drop, as_stream(stream))
   HA_DISPATCH(CALL)
 #undef CALL
   if (rc) return rc;
@@ -709,8 +718,8 @@ extern "C" int b200ctr_attn_h16_fwd(const void* qkv, int qkv_f16, const float* r
   return B200CTR_OK;
 }
 
-extern "C" int b200ctr_attn_h16_bwd(const void* qkv, int qkv_f16, const float* relmean, int max_len, const float* o, const float* lse,
-                                    const float* d_o, int64_t B, int K, int H, int D, void* dqkv, int dqkv_bf16, float* drelmean,
+extern "C" int b200ctr_attn_h16_bwd(const void* qkv, int qkv_f16, const float* relmean, int max_len, const void* o, int o_bf16,
+                                    const float* lse, const void* d_o, int do_bf16, int64_t B, int K, int H, int D, void* dqkv, int dqkv_bf16, float* drelmean,
                                     const uint32_t* keep, b200ctr_dropout_t drop, void* stream) {
   B200_REQUIRE(qkv && o && lse && d_o && dqkv, B200CTR_E_INVALID_ARG, "attn_h16_bwd: null pointer");
   B200_REQUIRE(D == HA_D && H == HA_H, B200CTR_E_UNSUPPORTED_SHAPE,
@@ -718,7 +727,7 @@ extern "C" int b200ctr_attn_h16_bwd(const void* qkv, int qkv_f16, const float* r
   B200_REQUIRE(drop.p < 0.96f, B200CTR_E_INVALID_ARG, "attn_h16_bwd: dropout p=%g >= 0.96", (double)drop.p);
   if (B == 0 || K == 0) return B200CTR_OK;
   int rc;
-#define CALL(NT_) ha_launch_bwd<NT_>((const float*)qkv, qkv_f16, relmean, max_len, o, lse, d_o, B, K, (float*)dqkv, dqkv_bf16, drelmean, keep, drop, as_stream(stream))
+#define CALL(NT_) ha_launch_bwd<NT_>((const float*)qkv, qkv_f16, relmean, max_len, (const float*)o, lse, (const float*)d_o, (o_bf16 ? 1 : 0) | (do_bf16 ? 2 : 0), B, K, (float*)dqkv, dqkv_bf16, drelmean, keep, drop, as_stream(stream))
   HA_DISPATCH(CALL)
 #undef CALL
   if (rc) return rc;

@@ -98,7 +98,8 @@ template <int NOUT, bool POST_NORM, bool COAL>
 __global__ void __launch_bounds__(PJ_NT, 1)
 lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                const float* __restrict__ resid, const float* __restrict__ nw, float eps, int64_t T,
-               float* __restrict__ y, float* __restrict__ s_out, float* __restrict__ r_out, uint32_t* __restrict__ y16, float qscale) {
+               float* __restrict__ y, float* __restrict__ s_out, float* __restrict__ r_out, uint32_t* __restrict__ y16, float qscale,
+               int x16 /* x is bf16 (T, 64): a 16-byte chunk already is one core-matrix row of the A operand */) {
   // y16 (NOUT = 192 only): the output goes out as fp16 pairs, (T, NOUT / 2) words, with its first 64 columns (q) times qscale --
   // the operand format of the packed-half attention kernels (attn_h16.cu), which otherwise convert the fp32 tensor themselves
   constexpr int ACC_STRIDE = NOUT <= 64 ? 64 : 256;
@@ -142,12 +143,26 @@ lin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
     // ---- loaders: two batches of 4 pass pairs per tile; the next batch's loads are in flight while one is stored ----
     auto tile_m0 = [&](int it) { return ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * PJ_TM; };
     float4 ra[2][4], rb[2][4];
-    if (COAL && n_it > 0) pj_load_pairs<PJ_D, 128>(ra[0], rb[0], x, tile_m0(0), T, 0, tid);
+    if (COAL && !x16 && n_it > 0) pj_load_pairs<PJ_D, 128>(ra[0], rb[0], x, tile_m0(0), T, 0, tid);
     for (int it = 0; it < n_it; ++it) {
       const int ab = it & 1;
       if (it >= 2) mbar_wait(smem_u32(&bars->a_empty[ab]), (uint32_t)(((it >> 1) - 1) & 1));
       unsigned char* dst = as + ab * PJ_X_BYTES;
-      if (COAL) {
+      if (x16) {
+        const int64_t m0 = tile_m0(it);
+        uint4 c[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int q = k * 128 + tid, row = q >> 3;
+          c[k] = make_uint4(0u, 0u, 0u, 0u);
+          if (m0 + row < T) c[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(x) + (m0 + row) * PJ_D) + (q & 7));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int q = k * 128 + tid, row = q >> 3;
+          *reinterpret_cast<uint4*>(dst + (q & 7) * PJ_LBO + (row >> 3) * 128 + (row & 7) * 16) = c[k];
+        }
+      } else if (COAL) {
         pj_load_pairs<PJ_D, 128>(ra[1], rb[1], x, tile_m0(it), T, 4, tid);
         pj_store_pairs<PJ_D, 128>(dst, ra[0], rb[0], 0, tid);
         if (it + 1 < n_it) pj_load_pairs<PJ_D, 128>(ra[0], rb[0], x, tile_m0(it + 1), T, 0, tid);
@@ -278,7 +293,8 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
                const float* __restrict__ w,        // (NOUT,64)
                const float* __restrict__ resid,    // optional (T,64), added to dX
                int64_t T, float* __restrict__ dy_out /* PRE_NORM: d_s (T,64) */, float* __restrict__ dx,
-               float* __restrict__ wsp /* per-CTA partials */, int gin16 /* !PRE_NORM: dY is bf16 (T,NOUT) */) {
+               float* __restrict__ wsp /* per-CTA partials */, int gin16 /* !PRE_NORM: dY is bf16 (T,NOUT) */,
+               int xin16 /* xin is bf16 (T,64) */, int dx16 /* dX is written as bf16 (T,64); no residual */) {
   constexpr int NP = NOUT <= 128 ? 128 : 256;                   // dY columns padded to whole 128-row weight-gradient blocks
   constexpr int NBLK = NP / 128;
   constexpr int DY_BYTES = (NP / 8) * PJ_LBO;
@@ -345,7 +361,15 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
     // bf16 dY: a 16-byte chunk already is one core-matrix row (8 bf16), 128 * NOUT / 8 chunks = 4 passes per batch
     constexpr int C8 = NOUT / 8;
     auto load_batch = [&](int it, int bi, float4 (&va)[4], float4 (&vb)[4]) {
-      if (bi == 0) pj_load_pairs<PJ_D, 256>(va, vb, xin, tile_m0(it), T, 0, tid);
+      if (bi == 0 && xin16) {       // bf16 x tile: 128 rows x 8 chunks of 16 bytes, 4 per thread
+        const int64_t m0 = tile_m0(it);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int q = k * 256 + tid, row = q >> 3;
+          va[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m0 + row < T) va[k] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const uint16_t*>(xin) + (m0 + row) * PJ_D) + (q & 7));
+        }
+      } else if (bi == 0) pj_load_pairs<PJ_D, 256>(va, vb, xin, tile_m0(it), T, 0, tid);
       else if (!gin16) pj_load_pairs<NOUT, 256>(va, vb, gin, tile_m0(it), T, (bi - 1) * 4, tid);
       else {
         const int64_t m0 = tile_m0(it);
@@ -359,7 +383,13 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
       }
     };
     auto store_batch = [&](unsigned char* xs, unsigned char* dys, int bi, const float4 (&va)[4], const float4 (&vb)[4]) {
-      if (bi == 0) pj_store_pairs<PJ_D, 256>(xs, va, vb, 0, tid);
+      if (bi == 0 && xin16) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int q = k * 256 + tid, row = q >> 3;
+          *reinterpret_cast<float4*>(xs + (q & 7) * PJ_LBO + (row >> 3) * 128 + (row & 7) * 16) = va[k];
+        }
+      } else if (bi == 0) pj_store_pairs<PJ_D, 256>(xs, va, vb, 0, tid);
       else if (!gin16) pj_store_pairs<NOUT, 256>(dys, va, vb, (bi - 1) * 4, tid);
       else {
 #pragma unroll
@@ -445,8 +475,14 @@ lin_bwd_kernel(const float* __restrict__ gin,      // PRE_NORM: dOut (T,64) = gr
       const int64_t m = m_w + lane;
       const int rows_valid = (int)max((int64_t)0, min((int64_t)32, T - m_w));
       float* scr = scr_all + (warp - 8) * (32 * 36);
-      warp_store_rows_add<32>(scr, v, dx + m_w * PJ_D, PJ_D, resid ? resid + m_w * PJ_D : nullptr, PJ_D, rows_valid, lane);
-      warp_store_rows_add<32>(scr, v + 32, dx + m_w * PJ_D + 32, PJ_D, resid ? resid + m_w * PJ_D + 32 : nullptr, PJ_D, rows_valid, lane);
+      if (dx16) {               // bf16 pairs: 32 words per row
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        warp_store_rows<32>(scr, v, dx + m_w * (PJ_D / 2), PJ_D / 2, rows_valid, lane);
+      } else {
+        warp_store_rows_add<32>(scr, v, dx + m_w * PJ_D, PJ_D, resid ? resid + m_w * PJ_D : nullptr, PJ_D, rows_valid, lane);
+        warp_store_rows_add<32>(scr, v + 32, dx + m_w * PJ_D + 32, PJ_D, resid ? resid + m_w * PJ_D + 32 : nullptr, PJ_D, rows_valid, lane);
+      }
       (void)m;
     }
     mbar_wait(smem_u32(&bars->done), 0);
@@ -524,7 +560,8 @@ __global__ void lin_bwd_reduce_kernel(const float* __restrict__ wsp, int n_cta, 
 
 template <int NOUT, bool POST_NORM>
 static int launch_lin_fwd(const float* x, const float* w, const float* bias, const float* resid, const float* nw, float eps,
-                          int64_t T, float* y, float* s_out, float* r_out, cudaStream_t st, uint32_t* y16 = nullptr, float qscale = 1.f) {
+                          int64_t T, float* y, float* s_out, float* r_out, cudaStream_t st, uint32_t* y16 = nullptr, float qscale = 1.f,
+                          int x16 = 0) {
   const size_t smem = (size_t)NOUT * 128 + 2 * PJ_X_BYTES + ((size_t)NOUT + PJ_D) * 4 +
                       (size_t)8 * 32 * ((POST_NORM ? 64 : 32) + 4) * 4 + sizeof(PjFwdBars) + 16;
   // measured on B200: the coalesced loader wins for the 64-wide kernel (0.103 vs 0.117 ms per launch), the row-per-lane
@@ -533,14 +570,14 @@ static int launch_lin_fwd(const float* x, const float* w, const float* bias, con
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(lin_fwd smem)");
   const int grid = (int)std::min<int64_t>(ceil_div(T, (int64_t)PJ_TM), (int64_t)num_sms());
-  fn<<<grid, PJ_NT, smem, st>>>(x, w, bias, resid, nw, eps, T, y, s_out, r_out, y16, qscale);
+  fn<<<grid, PJ_NT, smem, st>>>(x, w, bias, resid, nw, eps, T, y, s_out, r_out, y16, qscale, x16);
   return B200CTR_OK;
 }
 
 template <int NOUT, bool PRE_NORM>
 static int launch_lin_bwd(const float* gin, const float* s, const float* r, const float* nw, const float* xin, const float* w,
                           const float* resid, int64_t T, float* dy_out, float* dx, float* dw, float* db, float* dn, float* wsp,
-                          int gin16, cudaStream_t st) {
+                          int gin16, cudaStream_t st, int xin16 = 0, int dx16 = 0) {
   constexpr int NP = NOUT <= 128 ? 128 : 256;
   const size_t smem = (size_t)NOUT * 128 + 2 * (size_t)(PJ_X_BYTES + PJ_ONES_BYTES + (NP / 8) * PJ_LBO) + 8 * PJ_D * 4 + (size_t)(4 * 32 * 36 * 4) +
                       sizeof(PjBwdBars) + 16;
@@ -548,7 +585,7 @@ static int launch_lin_bwd(const float* gin, const float* s, const float* r, cons
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(lin_bwd smem)");
   const int grid = (int)std::min<int64_t>(ceil_div(T, (int64_t)PJ_TM), (int64_t)num_sms());
-  fn<<<grid, PJ_NT, smem, st>>>(gin, s, r, nw, xin, w, resid, T, dy_out, dx, wsp, gin16);
+  fn<<<grid, PJ_NT, smem, st>>>(gin, s, r, nw, xin, w, resid, T, dy_out, dx, wsp, gin16, xin16, dx16);
   cudaError_t le = cudaPeekAtLastError();
   if (le != cudaSuccess) return cuda_fail(le, "lin_bwd_kernel");
   const int n_out = NOUT * 65 + PJ_D;
@@ -582,13 +619,14 @@ extern "C" int b200ctr_inproj_fwd_h16(const float* x, const float* w_in, const f
   return B200CTR_OK;
 }
 
-extern "C" int b200ctr_outproj_norm_fwd(const float* o, const float* w_out, const float* b_out, const float* x_resid,
+extern "C" int b200ctr_outproj_norm_fwd(const void* o, int o_bf16, const float* w_out, const float* b_out, const float* x_resid,
                                         const float* n1w, float eps, int64_t T, int D, float* s1_out, float* r1_out,
                                         float* x1_out, void* stream) {
   B200_REQUIRE(o && w_out && x_resid && n1w && x1_out, B200CTR_E_INVALID_ARG, "outproj_norm_fwd: null pointer");
   B200_REQUIRE(D == PJ_D, B200CTR_E_UNSUPPORTED_SHAPE, "outproj_norm_fwd: D=%d unsupported (64 only)", D);
   if (T == 0) return B200CTR_OK;
-  int rc = launch_lin_fwd<64, true>(o, w_out, b_out, x_resid, n1w, eps, T, x1_out, s1_out, r1_out, as_stream(stream));
+  int rc = launch_lin_fwd<64, true>((const float*)o, w_out, b_out, x_resid, n1w, eps, T, x1_out, s1_out, r1_out, as_stream(stream), nullptr,
+                                    1.f, o_bf16);
   if (rc) return rc;
   B200_LAUNCH_CHECK("lin_fwd_kernel<64,norm>");
   return B200CTR_OK;
@@ -596,15 +634,15 @@ extern "C" int b200ctr_outproj_norm_fwd(const float* o, const float* w_out, cons
 
 extern "C" int64_t b200ctr_proj_bwd_workspace_bytes(void) { return (int64_t)num_sms() * ((int64_t)256 * 80 + PJ_D) * 4; }
 
-extern "C" int b200ctr_outproj_norm_bwd(const float* dx1, const float* s1, const float* r1, const float* n1w, const float* o,
-                                        const float* w_out, int64_t T, int D, float* ds1_out, float* d_o, float* dw_out,
+extern "C" int b200ctr_outproj_norm_bwd(const float* dx1, const float* s1, const float* r1, const float* n1w, const void* o, int o_bf16,
+                                        const float* w_out, int64_t T, int D, float* ds1_out, void* d_o, int do_bf16, float* dw_out,
                                         float* db_out, float* dn1, void* workspace, void* stream) {
   B200_REQUIRE(dx1 && s1 && r1 && n1w && o && w_out && ds1_out && d_o && dw_out && db_out && dn1 && workspace, B200CTR_E_INVALID_ARG,
                "outproj_norm_bwd: null pointer");
   B200_REQUIRE(D == PJ_D, B200CTR_E_UNSUPPORTED_SHAPE, "outproj_norm_bwd: D=%d unsupported (64 only)", D);
   B200_REQUIRE(T > 0, B200CTR_E_INVALID_ARG, "outproj_norm_bwd: empty input");
-  int rc = launch_lin_bwd<64, true>(dx1, s1, r1, n1w, o, w_out, nullptr, T, ds1_out, d_o, dw_out, db_out, dn1, (float*)workspace,
-                                    0, as_stream(stream));
+  int rc = launch_lin_bwd<64, true>(dx1, s1, r1, n1w, (const float*)o, w_out, nullptr, T, ds1_out, (float*)d_o, dw_out, db_out, dn1,
+                                    (float*)workspace, 0, as_stream(stream), o_bf16, do_bf16);
   if (rc) return rc;
   B200_LAUNCH_CHECK("lin_bwd_kernel<64,norm>");
   return B200CTR_OK;
