@@ -145,7 +145,7 @@ cat_fwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
                float* __restrict__ mean_out, int64_t ld_mean, int q_idx, float* __restrict__ q_out,
                int64_t B, int Fc, b200ctr_dropout_t drop) {
   __shared__ float Wt[CAT_MAXDC][CAT_D + 1];               // W_c transposed: Wt[j][n]
-  __shared__ float rows[CAT_WARPS][CAT_SPW][CAT_MAXDC];
+  __shared__ __align__(16) float rows[CAT_WARPS][CAT_SPW][CAT_MAXDC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b_base = ((int64_t)blockIdx.x * CAT_WARPS + warp) * CAT_SPW;
   float m0[CAT_SPW], m1[CAT_SPW];
@@ -158,9 +158,15 @@ cat_fwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
     const int card = cards[c];
     const int64_t ldt = lds ? lds[c] : dc;                  // row stride of table c (row-lazy tables are stored 64 wide)
     __syncthreads();
-    for (int i = threadIdx.x; i < CAT_D * dc; i += blockDim.x) {
-      int n = i / dc, j = i % dc;
-      Wt[j][n] = W[i];
+    {
+      // W_c[n][j] -> Wt[j][n]; (n, j) of element i advance incrementally (a division per element cost as much as the products)
+      const int step_n = (int)blockDim.x / dc, step_j = (int)blockDim.x % dc;
+      int n = (int)threadIdx.x / dc, j = (int)threadIdx.x % dc;
+      for (int i = threadIdx.x; i < CAT_D * dc; i += blockDim.x) {
+        Wt[j][n] = W[i];
+        n += step_n; j += step_j;
+        if (j >= dc) { j -= dc; ++n; }
+      }
     }
 #pragma unroll
     for (int s = 0; s < CAT_SPW; ++s) {
@@ -169,25 +175,48 @@ cat_fwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
         int64_t id = (int64_t)x_cat[b * Fc + c];
         id = id < 0 ? 0 : (id >= card ? card - 1 : id);     // memory-safe clamp (reference would raise)
         for (int j = lane; j < dc; j += 32) rows[warp][s][j] = T[id * ldt + j];
+      } else {
+        for (int j = lane; j < dc; j += 32) rows[warp][s][j] = 0.f;
       }
     }
     __syncthreads();
+    // the warp's CAT_SPW samples share every W element read: per 4 table columns 8 W loads + CAT_SPW 16-byte row loads feed
+    // 8 * CAT_SPW FMAs (sample by sample it was 3 loads per 2 FMAs); each output still accumulates j in ascending order
+    float a0[CAT_SPW], a1[CAT_SPW];
+#pragma unroll
+    for (int s = 0; s < CAT_SPW; ++s) a0[s] = a1[s] = 0.f;
+    int j = 0;
+    for (; j + 4 <= dc; j += 4) {
+      float w0[4], w1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { w0[k] = Wt[j + k][lane]; w1[k] = Wt[j + k][lane + 32]; }
+#pragma unroll
+      for (int s = 0; s < CAT_SPW; ++s) {
+        const float4 r = *reinterpret_cast<const float4*>(&rows[warp][s][j]);
+        a0[s] = fmaf(r.x, w0[0], a0[s]); a1[s] = fmaf(r.x, w1[0], a1[s]);
+        a0[s] = fmaf(r.y, w0[1], a0[s]); a1[s] = fmaf(r.y, w1[1], a1[s]);
+        a0[s] = fmaf(r.z, w0[2], a0[s]); a1[s] = fmaf(r.z, w1[2], a1[s]);
+        a0[s] = fmaf(r.w, w0[3], a0[s]); a1[s] = fmaf(r.w, w1[3], a1[s]);
+      }
+    }
+    for (; j < dc; ++j) {
+      const float w0 = Wt[j][lane], w1 = Wt[j][lane + 32];
+#pragma unroll
+      for (int s = 0; s < CAT_SPW; ++s) {
+        const float r = rows[warp][s][j];
+        a0[s] = fmaf(r, w0, a0[s]); a1[s] = fmaf(r, w1, a1[s]);
+      }
+    }
 #pragma unroll
     for (int s = 0; s < CAT_SPW; ++s) {
       int64_t b = b_base + s;
       if (b >= B) continue;
-      float a0 = 0.f, a1 = 0.f;
-      for (int j = 0; j < dc; ++j) {
-        float r = rows[warp][s][j];
-        a0 = fmaf(r, Wt[j][lane], a0);
-        a1 = fmaf(r, Wt[j][lane + 32], a1);
-      }
-      m0[s] += a0; m1[s] += a1;
-      if (q_out && c == q_idx) { q_out[b * CAT_D + lane] = a0; q_out[b * CAT_D + lane + 32] = a1; }
+      m0[s] += a0[s]; m1[s] += a1[s];
+      if (q_out && c == q_idx) { q_out[b * CAT_D + lane] = a0[s]; q_out[b * CAT_D + lane + 32] = a1[s]; }
       uint64_t eid = ((uint64_t)b * Fc + c) * CAT_D;
       float* o = out + b * ld_b + (int64_t)c * CAT_D;
-      o[lane] = a0 * drop_scale(drop, eid + lane);
-      o[lane + 32] = a1 * drop_scale(drop, eid + lane + 32);
+      o[lane] = a0[s] * drop_scale(drop, eid + lane);
+      o[lane + 32] = a1[s] * drop_scale(drop, eid + lane + 32);
     }
   }
   if (mean_out) {
@@ -213,7 +242,7 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
                b200ctr_dropout_t drop, const int32_t* __restrict__ defer_slot, int n_defer, float* __restrict__ defer_rows,
                int32_t* __restrict__ defer_keys, int32_t sentinel) {
   __shared__ float Ws[CAT_D][CAT_MAXDC + 1];           // natural layout W[n][j]
-  __shared__ float gs[CATB_TS][CAT_D + 1];
+  __shared__ __align__(16) float gs[CATB_TS][CAT_D + 4];   // rows 16-byte aligned: four n per load
   __shared__ float rs[CATB_TS][CAT_MAXDC + 1];
   __shared__ int64_t ids[CATB_TS];
   const int c = blockIdx.y;
@@ -226,11 +255,26 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   const int64_t ldt = lds ? lds[c] : dc;
   const int dslot = defer_slot ? defer_slot[c] : -1;
   const int tid = threadIdx.x;
-  for (int i = tid; i < CAT_D * dc; i += blockDim.x) Ws[i / dc][i % dc] = W[i];
-  // this thread's dW elements: e = tid + k*256 < 64*dc  (<= 16 of them)
-  float acc[16];
+  // (row, column) of element i of a (., dc) array advance incrementally over the strided loops (no division per element)
+  const int step_r = 256 / dc, step_j = 256 % dc, r_first = tid / dc, j_first = tid % dc;
+  {
+    int n = r_first, j = j_first;
+    for (int i = tid; i < CAT_D * dc; i += 256) {
+      Ws[n][j] = W[i];
+      n += step_r; j += step_j;
+      if (j >= dc) { j -= dc; ++n; }
+    }
+  }
+  // register tiles of the two small products (thread per output element cost two shared-memory loads per FMA, and those
+  // loads were the kernel): the thread owns n0 .. n0+3 x columns jg, jg+16, jg+32, jg+48 of dW_c and samples s0, s0+1 x the same
+  // columns of dE_c; every output still accumulates its terms in the same (ascending) order
+  const int jg = tid & 15, n0 = (tid >> 4) * 4, s0 = (tid >> 4) * 2;
+  const int mcount = jg < dc ? (dc - jg + 15) >> 4 : 0;            // how many of the four columns exist
+  float acc[4][4];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) acc[i][m] = 0.f;
   const float invFc = 1.f / (float)Fc;
   const int64_t ntiles = ceil_div(B, (int64_t)CATB_TS);
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -254,35 +298,64 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
       gs[s][n] = g;
     }
     __syncthreads();
-    for (int i = tid; i < CATB_TS * dc; i += blockDim.x) {
-      int s = i / dc, j = i % dc;
-      rs[s][j] = (b0 + s < B) ? T[ids[s] * ldt + j] : 0.f;
-    }
-    __syncthreads();
-    // dW[n][j] += sum_s g[s][n] * row[s][j]
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      int e = tid + k * 256;
-      if (e < CAT_D * dc) {
-        int n = e / dc, j = e % dc;
-        float a = acc[k];
-#pragma unroll 8
-        for (int s = 0; s < CATB_TS; ++s) a = fmaf(gs[s][n], rs[s][j], a);
-        acc[k] = a;
+    {
+      int sr = r_first, j = j_first;
+      for (int i = tid; i < CATB_TS * dc; i += 256) {
+        rs[sr][j] = (b0 + sr < B) ? T[ids[sr] * ldt + j] : 0.f;
+        sr += step_r; j += step_j;
+        if (j >= dc) { j -= dc; ++sr; }
       }
     }
-    // dE[id][j] += sum_n W[n][j] * g[s][n]   (thread per (sample, j) pair: with a warp per sample and a lane per j, 24 of the
-    // 32 lanes idled on the 8-wide tables -- 24 of the 35 columns -- and this loop was two thirds of the kernel's LDS traffic)
-    for (int pr = tid; pr < CATB_TS * dc; pr += blockDim.x) {
-      const int s = pr / dc, j = pr - s * dc;
-      if (b0 + s >= B) continue;
-      float a = 0.f;
-#pragma unroll 8
-      for (int n = 0; n < CAT_D; ++n) a = fmaf(Ws[n][j], gs[s][n], a);
-      // this sample's contribution to dE_c[id], as a 64-wide row (columns >= d_c stay zero) of slot (b, c): the slots are
+    __syncthreads();
+    if (mcount > 0) {
+      // dW[n][j] += sum_s g[s][n] * row[s][j]
+#pragma unroll 4
+      for (int s = 0; s < CATB_TS; ++s) {
+        const float4 g4 = *reinterpret_cast<const float4*>(&gs[s][n0]);
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          if (m < mcount) {
+            const float r = rs[s][jg + 16 * m];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][m] = fmaf(gv[i], r, acc[i][m]);
+          }
+        }
+      }
+      // dE[id][j] += sum_n W[n][j] * g[s][n]
+      float de[2][4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) de[q][m] = 0.f;
+#pragma unroll 2
+      for (int n = 0; n < CAT_D; n += 4) {
+        const float4 ga = *reinterpret_cast<const float4*>(&gs[s0][n]);
+        const float4 gb = *reinterpret_cast<const float4*>(&gs[s0 + 1][n]);
+        const float g0[4] = {ga.x, ga.y, ga.z, ga.w}, g1[4] = {gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (m < mcount) {
+              const float w = Ws[n + k][jg + 16 * m];
+              de[0][m] = fmaf(w, g0[k], de[0][m]);
+              de[1][m] = fmaf(w, g1[k], de[1][m]);
+            }
+          }
+        }
+      }
+      // a sample's contribution to dE_c[id], as a 64-wide row (columns >= d_c stay zero) of slot (b, c): the slots are
       // sorted by global table row and reduced in slot order by b200ctr_scatter_rows (no float atomics)
-      if (dslot >= 0) defer_rows[((b0 + s) * n_defer + dslot) * (int64_t)CAT_D + j] = a;
-      else rowg[((b0 + s) * Fc + c) * (int64_t)CAT_D + j] = a;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int64_t b = b0 + s0 + q;
+        if (b >= B) continue;
+        float* dst = dslot >= 0 ? defer_rows + (b * n_defer + dslot) * (int64_t)CAT_D : rowg + (b * Fc + c) * (int64_t)CAT_D;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (m < mcount) dst[jg + 16 * m] = de[q][m];
+      }
     }
     if (tid < CATB_TS && b0 + tid < B) {
       // deferred column (data parallel, replicated row-lazy table): the slot leaves this call unreduced -- the trainer gathers
@@ -295,10 +368,10 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   // this CTA's partial dW_c; the partials are added in CTA order by cat_dw_reduce_kernel
   float* dwp = dwpart + (int64_t)blockIdx.x * CAT_D * sumdc + (int64_t)CAT_D * off_c;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    int e = tid + k * 256;
-    if (e < CAT_D * dc) dwp[e] = acc[k];
-  }
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+      if (m < mcount) dwp[(n0 + i) * dc + jg + 16 * m] = acc[i][m];
 }
 
 // dE_c[r, 0:d_c] += temp[row_base_c + r, 0:d_c]  (temp: the 64-wide reduced rows of all tables, one global row id per table row).
