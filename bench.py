@@ -353,9 +353,8 @@ def measure(env, cfg, vocab, dev_b, host, steps, warmup, profile=False, e2e=Fals
 
     def host_loop(n):
         """The call a user makes: pinned host batches through b200ctr.DeviceFeeder (batch t + 1 crosses PCIe on a copy stream
-        while step t runs; exactly one H2D per step, n in total) into FusedTrainer.step, every step's loss read back through
-        b200ctr.LossReader (asynchronous copy to pinned memory behind the step, collected while the next step runs; the last one
-        before the loop ends).  `host_loop_serial` is the naive form: copy, step, float(loss)."""
+        while step t runs; exactly one H2D per step, n in total) into FusedTrainer.step, the loss read back after every step.
+        `host_loop_serial` hands the pinned batch to step() itself: copy, then step, on one stream."""
         import b200ctr
 
         def gen():
@@ -363,10 +362,8 @@ def measure(env, cfg, vocab, dev_b, host, steps, warmup, profile=False, e2e=Fals
                 item = host[cursor[0] % NB]
                 cursor[0] += 1
                 yield item
-        losses = b200ctr.LossReader(env.dev)
         for bb, yy in b200ctr.DeviceFeeder(gen(), env.dev):
-            losses.push(tr.step(bb, yy))       # D2H read of every step's loss (train.py:202), one step late: the host never drains the queue
-        losses.flush()                         # the last step's loss, inside the timed region
+            float(tr.step(bb, yy))             # D2H read of the step's loss (train.py:202)
 
     dev_loop(max(3, warmup))
     torch.cuda.synchronize()
@@ -641,9 +638,9 @@ def run_cuda(args):
             "clocks": r["clocks"],
             "e2e": {"value": r["e2e"], "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": r["ms_e2e"] / args.steps,
-                    "api": "for batch, y in b200ctr.DeviceFeeder(host_batches, device): prev_loss = LossReader.push(FusedTrainer.step(batch, y)) "
-                           "-- one H2D per step on a copy stream under the previous step, every step's loss copied to pinned memory and read "
-                           "one step late (the last inside the timed region); ms_per_step_serial_copy = copy, step, float(loss) per step",
+                    "api": "for batch, y in b200ctr.DeviceFeeder(host_batches, device): loss = float(FusedTrainer.step(batch, y)) -- one H2D "
+                           "per step, issued on a copy stream one batch ahead; ms_per_step_serial_copy = float(FusedTrainer.step(host_batch, y)), "
+                           "the copy in front of the step on one stream",
                     "ms_per_step_serial_copy": r["ms_e2e_serial"] / args.steps},
             "gpu_launches": int(r["launches"]),
             "ms_per_step_profiled": r["ms_profiled"] / args.steps,

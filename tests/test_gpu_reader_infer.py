@@ -141,17 +141,3 @@ def test_device_feeder_hands_out_every_batch_once_in_order():
         assert dy.is_cuda and torch.equal(dy.cpu(), hy)
         n += 1
     assert n == 5
-
-
-def test_loss_reader_returns_every_loss_one_step_late():
-    from b200ctr import LossReader
-    dev = torch.device("cuda:0")
-    rd = LossReader(dev)
-    assert rd.flush() is None
-    got = []
-    vals = [0.25, 1.5, -3.0, 7.125, 0.0]
-    for v in vals:
-        t = torch.full((1,), v, device=dev)
-        got.append(rd.push(t))
-    got.append(rd.flush())
-    assert got == [None] + vals

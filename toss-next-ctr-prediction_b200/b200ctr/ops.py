@@ -321,8 +321,23 @@ class CatTables:
         return self._key == tuple(t.data_ptr() for t in tables) + tuple(p.data_ptr() for p in projs)
 
 
+_PTR_TABLES: dict = {}
+
+
 def _ptr_table(ts: Sequence[torch.Tensor]) -> torch.Tensor:
-    return torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64, device=ts[0].device)
+    """Device array of the tensors' addresses, cached by the addresses themselves: `torch.tensor(list, device=cuda)` is a
+    pageable host-to-device copy, i.e. a host wait for everything queued on the stream -- made once per step (cat_bwd's two
+    gradient pointer tables) it drained the launch queue near the end of every backward and left the GPU waiting for the host
+    through the launch-bound start of the next step.  The trainer's gradient views live in one persistent buffer, so the
+    tables are built once."""
+    key = (ts[0].device, tuple(t.data_ptr() for t in ts))
+    tab = _PTR_TABLES.get(key)
+    if tab is None:
+        if len(_PTR_TABLES) >= 256:          # callers with ever-changing gradient tensors (autograd): do not grow without bound
+            _PTR_TABLES.clear()
+        tab = torch.tensor(key[1], dtype=torch.int64, device=ts[0].device)
+        _PTR_TABLES[key] = tab
+    return tab
 
 
 def _idx64(t: torch.Tensor) -> int:

@@ -78,35 +78,6 @@ import os as _os
 C5_MODE = _os.environ.get("B200CTR_C5", "gather")        # "allreduce": NCCL int64 sum (A/B timing)
 
 
-class LossReader:
-    """Per-step loss read-back (train.py:202 `loss.item()`) that does not drain the launch queue: `push(loss)` enqueues an
-    asynchronous copy of the step's 1-element loss into pinned memory right behind the step and returns the PREVIOUS step's
-    value (None on the first call), waiting only for that earlier copy; `flush()` returns the last one.  Every step's loss still
-    reaches the host, one step late -- `float(loss)` after every step makes the GPU wait for the host to launch the next step's
-    first kernels (0.3-0.6 ms of a 9.4 ms step)."""
-
-    def __init__(self, device):
-        self.device = torch.device(device)
-        self.slots = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.events = [torch.cuda.Event(), torch.cuda.Event()]
-        self.n = 0
-
-    def _take(self, i: int) -> float:
-        self.events[i].synchronize()
-        return float(self.slots[i][0])
-
-    def push(self, loss: torch.Tensor) -> Optional[float]:
-        i = self.n & 1
-        prev = self._take(i ^ 1) if self.n > 0 else None          # the other slot's copy was enqueued one step ago
-        self.slots[i].copy_(loss.detach().reshape(1), non_blocking=True)
-        self.events[i].record(torch.cuda.current_stream(self.device))
-        self.n += 1
-        return prev
-
-    def flush(self) -> Optional[float]:
-        return self._take((self.n - 1) & 1) if self.n > 0 else None
-
-
 class FusedTrainer:
     def __init__(self, model: CTRModel, cfg: dict, steps_per_epoch: int = 1, seed: Optional[int] = None,
                  process_group=None, lazy_tables: bool = True, shard_tables: Optional[bool] = None):
