@@ -581,6 +581,15 @@ def test_gemm_tma_kmajor(dev, M, N, K):
         assert torch.equal(t2.cpu(), a16.t().contiguous().cpu())
 
 
+@pytest.mark.parametrize("R,C", [(200, 136), (64, 64), (8, 8), (1000, 72), (130, 66), (8192, 1280)])
+def test_transpose_bf16_both_kernels(dev, R, C):
+    """bf16 (R, C) -> (C, R): the 16-byte kernel (R, C multiples of 8; ragged 64 x 64 tiles) and the 4-byte fallback."""
+    from b200ctr import ops
+    g = torch.Generator().manual_seed(R * 7 + C)
+    a16 = ops.to_bf16(_rand(g, R, C).to(dev))
+    assert torch.equal(ops.transpose_bf16(a16).cpu(), a16.t().contiguous().cpu())
+
+
 # ---- Linear(K -> 1) as row dot products (csrc/qnn.cu lin1_*) vs torch ---------------------------------------------
 @pytest.mark.parametrize("B,K", [(1000, 256), (7, 128), (4096, 512)])
 def test_lin1_matches_torch(dev, B, K):

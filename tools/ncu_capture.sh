@@ -8,8 +8,8 @@ OUT=gpurun_out
 mkdir -p $OUT
 CMD="python bench.py --quick --steps 2 --warmup 3 --no-cpu-baseline --batches 8"
 $CMD > $OUT/${TAG}_plain.json 2> $OUT/${TAG}_plain.err || { echo "plain run failed"; tail -5 $OUT/${TAG}_plain.err; exit 1; }
-# (1) every launch with its device time: 9 steps (3 warm-up + 2 timed + 2 + 2 host-fed); shares of a step, not absolutes
-ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu1.log 2>&1
+# (1) every launch with its device time: 15 steps (3 warm-up + 2 timed + 2 profiled + 2 x (2 + 2) host-fed); shares of a step, not absolutes
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3400 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu1.log 2>&1
 # (2) full counter set on the 36 fused / retrieval launches of the 4th step (3 x [attn fwd, attn bwd, ffn fwd, ffn bwd1, ffn bwd2,
 #     2 lin_fwd, 2 lin_bwd] + 2 fm + 5 gemm_tma + retrieve fwd / bwd)
 ncu --set full --clock-control none -k regex:'attn_tc|attn_h16|attn_mma|ffn_|lin_fwd|lin_bwd|fm_fwd|fm_bwd|gemm_tma|retrieve_fwd|retrieve_bwd' \

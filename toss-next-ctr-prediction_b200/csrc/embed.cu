@@ -137,6 +137,10 @@ constexpr int CAT_MAXDC = 64;
 constexpr int CAT_SPW = 4;            // samples per warp per block pass
 constexpr int CAT_WARPS = 8;
 
+// One CTA = CAT_WARPS x CAT_SPW samples, walking the Fc columns.  Column c + 1's operands (its W_c elements and the gathered
+// table rows) are loaded into registers BEFORE column c's products are issued and stored to shared memory after them: the
+// global-load latency of a column sits under the previous column's arithmetic (ncu r02ai: 65 % of the kernel's stall samples
+// were the W loads of the staging loop, one exposed round trip per element; 21 % of the warp slots active).
 template <typename IT>
 __global__ void __launch_bounds__(CAT_WARPS * 32)
 cat_fwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ tables, const float* const* __restrict__ projs,
@@ -146,40 +150,64 @@ cat_fwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
                int64_t B, int Fc, b200ctr_dropout_t drop) {
   __shared__ float Wt[CAT_MAXDC][CAT_D + 1];               // W_c transposed: Wt[j][n]
   __shared__ __align__(16) float rows[CAT_WARPS][CAT_SPW][CAT_MAXDC];
+  constexpr int NT = CAT_WARPS * 32;
+  constexpr int WPT = CAT_D * CAT_MAXDC / NT;              // W elements per thread (widest column)
+  constexpr int RPT = CAT_MAXDC / 32;                      // row elements per lane and sample
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b_base = ((int64_t)blockIdx.x * CAT_WARPS + warp) * CAT_SPW;
   float m0[CAT_SPW], m1[CAT_SPW];
 #pragma unroll
   for (int s = 0; s < CAT_SPW; ++s) m0[s] = m1[s] = 0.f;
-  for (int c = 0; c < Fc; ++c) {
+  float wreg[WPT], rreg[CAT_SPW][RPT];
+
+  auto fetch = [&](int c) {                                // global loads of column c, all independent
     const int dc = dims[c];
     const float* W = projs[c];
     const float* T = tables[c];
     const int card = cards[c];
     const int64_t ldt = lds ? lds[c] : dc;                  // row stride of table c (row-lazy tables are stored 64 wide)
-    __syncthreads();
-    {
-      // W_c[n][j] -> Wt[j][n]; (n, j) of element i advance incrementally (a division per element cost as much as the products)
-      const int step_n = (int)blockDim.x / dc, step_j = (int)blockDim.x % dc;
-      int n = (int)threadIdx.x / dc, j = (int)threadIdx.x % dc;
-      for (int i = threadIdx.x; i < CAT_D * dc; i += blockDim.x) {
-        Wt[j][n] = W[i];
-        n += step_n; j += step_j;
-        if (j >= dc) { j -= dc; ++n; }
-      }
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      const int i = (int)threadIdx.x + k * NT;
+      wreg[k] = i < CAT_D * dc ? W[i] : 0.f;
     }
 #pragma unroll
     for (int s = 0; s < CAT_SPW; ++s) {
-      int64_t b = b_base + s;
+      const int64_t b = b_base + s;
+      int64_t id = 0;
       if (b < B) {
-        int64_t id = (int64_t)x_cat[b * Fc + c];
+        id = (int64_t)x_cat[b * Fc + c];
         id = id < 0 ? 0 : (id >= card ? card - 1 : id);     // memory-safe clamp (reference would raise)
-        for (int j = lane; j < dc; j += 32) rows[warp][s][j] = T[id * ldt + j];
-      } else {
-        for (int j = lane; j < dc; j += 32) rows[warp][s][j] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const int j = lane + 32 * k;
+        rreg[s][k] = (b < B && j < dc) ? T[id * ldt + j] : 0.f;
       }
     }
-    __syncthreads();
+  };
+  auto stash = [&](int dc) {                               // registers -> shared memory
+    // W_c[n][j] -> Wt[j][n]; (n, j) of element i advance incrementally (a division per element cost as much as the products)
+    const int step_n = NT / dc, step_j = NT % dc;
+    int n = (int)threadIdx.x / dc, j = (int)threadIdx.x % dc;
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      if ((int)threadIdx.x + k * NT < CAT_D * dc) Wt[j][n] = wreg[k];
+      n += step_n; j += step_j;
+      if (j >= dc) { j -= dc; ++n; }
+    }
+#pragma unroll
+    for (int s = 0; s < CAT_SPW; ++s)
+#pragma unroll
+      for (int k = 0; k < RPT; ++k)
+        if (lane + 32 * k < dc) rows[warp][s][lane + 32 * k] = rreg[s][k];
+  };
+
+  if (Fc > 0) { fetch(0); stash(dims[0]); }
+  __syncthreads();
+  for (int c = 0; c < Fc; ++c) {
+    const int dc = dims[c];
+    if (c + 1 < Fc) fetch(c + 1);
     // the warp's CAT_SPW samples share every W element read: per 4 table columns 8 W loads + CAT_SPW 16-byte row loads feed
     // 8 * CAT_SPW FMAs (sample by sample it was 3 loads per 2 FMAs); each output still accumulates j in ascending order
     float a0[CAT_SPW], a1[CAT_SPW];
@@ -218,6 +246,9 @@ cat_fwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
       o[lane] = a0[s] * drop_scale(drop, eid + lane);
       o[lane + 32] = a1[s] * drop_scale(drop, eid + lane + 32);
     }
+    __syncthreads();                                       // column c's operands have been read by every warp
+    if (c + 1 < Fc) stash(dims[c + 1]);
+    __syncthreads();
   }
   if (mean_out) {
     float inv = 1.f / (float)Fc;
@@ -232,8 +263,53 @@ cat_fwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
 // grid (NBX, Fc).  Block (bx, c) walks sample tiles of 32 with stride NBX: stages g and the gathered rows,
 // accumulates dW_c in registers (one atomic per element per block at the end) and scatters dE_c rows.
 constexpr int CATB_TS = 32;
+// The two small products of one (32-sample tile, column) pair on register tiles: the thread owns n0 .. n0+3 x columns jg, jg+16, ..
+// of dW_c and samples s0, s0+1 x the same columns of dE_c (thread per output element cost two shared-memory loads per FMA).  MM =
+// ceil(d_c / 16) is uniform over the CTA and a template parameter: with the column count as a per-thread predicate every warp
+// issued all four column steps -- 3.8x the useful FMAs over the 35 shipped columns, 22 of which are 8 wide (ncu r02ai: 170 M warp
+// instructions, issue 74 %).  Columns >= d_c of the last step read don't-care shared memory and are never stored.  Every output
+// accumulates its terms in ascending order (bit-identical to the element-per-thread form).
+template <int MM>
+__device__ __forceinline__ void cat_bwd_products(const float (*gs)[CAT_D + 4], const float (*rs)[CAT_MAXDC + 1], const float (*Ws)[CAT_MAXDC + 1],
+                                                 int jg, int n0, int s0, float (&acc)[4][4], float (&de)[2][4]) {
+  // dW[n][j] += sum_s g[s][n] * row[s][j]
+#pragma unroll 4
+  for (int s = 0; s < CATB_TS; ++s) {
+    const float4 g4 = *reinterpret_cast<const float4*>(&gs[s][n0]);
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+    for (int m = 0; m < MM; ++m) {
+      const float r = rs[s][jg + 16 * m];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i][m] = fmaf(gv[i], r, acc[i][m]);
+    }
+  }
+  // dE[id][j] += sum_n W[n][j] * g[s][n]
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) de[q][m] = 0.f;
+#pragma unroll 2
+  for (int n = 0; n < CAT_D; n += 4) {
+    const float4 ga = *reinterpret_cast<const float4*>(&gs[s0][n]);
+    const float4 gb = *reinterpret_cast<const float4*>(&gs[s0 + 1][n]);
+    const float g0[4] = {ga.x, ga.y, ga.z, ga.w}, g1[4] = {gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int m = 0; m < MM; ++m) {
+        const float w = Ws[n + k][jg + 16 * m];
+        de[0][m] = fmaf(w, g0[k], de[0][m]);
+        de[1][m] = fmaf(w, g1[k], de[1][m]);
+      }
+    }
+  }
+}
+
+// grid (NBX, Fc).  Block (bx, c) walks sample tiles of 32 with stride NBX.  Per tile: every global load (the gradient rows, the
+// context-mean gradient, the ids and the gathered table rows) is issued before the first use, ONE barrier, then the products.
 template <typename IT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ tables, const float* const* __restrict__ projs,
                const int32_t* __restrict__ dims, const int32_t* __restrict__ cards, const int32_t* __restrict__ lds,
                const float* __restrict__ dout, int64_t ld_b,
@@ -244,7 +320,8 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   __shared__ float Ws[CAT_D][CAT_MAXDC + 1];           // natural layout W[n][j]
   __shared__ __align__(16) float gs[CATB_TS][CAT_D + 4];   // rows 16-byte aligned: four n per load
   __shared__ float rs[CATB_TS][CAT_MAXDC + 1];
-  __shared__ int64_t ids[CATB_TS];
+  constexpr int GPT = CATB_TS * CAT_D / 256;            // gradient elements per thread and tile
+  constexpr int RPT = CATB_TS * CAT_MAXDC / 256;        // gathered row elements per thread and tile (widest column)
   const int c = blockIdx.y;
   const int dc = dims[c];
   const int card = cards[c];
@@ -255,6 +332,7 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   const int64_t ldt = lds ? lds[c] : dc;
   const int dslot = defer_slot ? defer_slot[c] : -1;
   const int tid = threadIdx.x;
+  const bool use_dq = dq != nullptr && c == q_idx;
   // (row, column) of element i of a (., dc) array advance incrementally over the strided loops (no division per element)
   const int step_r = 256 / dc, step_j = 256 % dc, r_first = tid / dc, j_first = tid % dc;
   {
@@ -265,11 +343,8 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
       if (j >= dc) { j -= dc; ++n; }
     }
   }
-  // register tiles of the two small products (thread per output element cost two shared-memory loads per FMA, and those
-  // loads were the kernel): the thread owns n0 .. n0+3 x columns jg, jg+16, jg+32, jg+48 of dW_c and samples s0, s0+1 x the same
-  // columns of dE_c; every output still accumulates its terms in the same (ascending) order
   const int jg = tid & 15, n0 = (tid >> 4) * 4, s0 = (tid >> 4) * 2;
-  const int mcount = jg < dc ? (dc - jg + 15) >> 4 : 0;            // how many of the four columns exist
+  const int mm = (dc + 15) >> 4;                          // column steps of this table (uniform over the CTA)
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -279,88 +354,80 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   const int64_t ntiles = ceil_div(B, (int64_t)CATB_TS);
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t b0 = t * CATB_TS;
-    __syncthreads();
-    if (tid < CATB_TS) {
-      int64_t b = b0 + tid;
-      int64_t id = 0;
-      if (b < B) { id = (int64_t)x_cat[b * Fc + c]; id = id < 0 ? 0 : (id >= card ? card - 1 : id); }
-      ids[tid] = id;
-    }
-    for (int i = tid; i < CATB_TS * CAT_D; i += blockDim.x) {
-      int s = i / CAT_D, n = i % CAT_D;
-      int64_t b = b0 + s;
-      float g = 0.f;
+    // ---- all global loads of the tile ----
+    float gv[GPT], dmv[GPT], dqv[GPT], rv[RPT];
+#pragma unroll
+    for (int k = 0; k < GPT; ++k) {
+      const int i = tid + k * 256, sgl = i / CAT_D, n = i % CAT_D;
+      const int64_t b = b0 + sgl;
+      gv[k] = dmv[k] = dqv[k] = 0.f;
       if (b < B) {
-        if (dout) g = dout[b * ld_b + (int64_t)c * CAT_D + n] * drop_scale(drop, ((uint64_t)b * Fc + c) * CAT_D + n);
-        if (dmean) g = fmaf(dmean[b * ld_dmean + n], invFc, g);
-        if (dq && c == q_idx) g += dq[b * CAT_D + n];
+        if (dout) gv[k] = dout[b * ld_b + (int64_t)c * CAT_D + n];
+        if (dmean) dmv[k] = dmean[b * ld_dmean + n];
+        if (use_dq) dqv[k] = dq[b * CAT_D + n];
       }
-      gs[s][n] = g;
     }
-    __syncthreads();
     {
       int sr = r_first, j = j_first;
-      for (int i = tid; i < CATB_TS * dc; i += 256) {
-        rs[sr][j] = (b0 + sr < B) ? T[ids[sr] * ldt + j] : 0.f;
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        rv[k] = 0.f;
+        if (tid + k * 256 < CATB_TS * dc && b0 + sr < B) {
+          int64_t id = (int64_t)x_cat[(b0 + sr) * Fc + c];
+          id = id < 0 ? 0 : (id >= card ? card - 1 : id);
+          rv[k] = T[id * ldt + j];
+        }
+        sr += step_r; j += step_j;
+        if (j >= dc) { j -= dc; ++sr; }
+      }
+    }
+    __syncthreads();                                      // the previous tile's products have read gs / rs
+#pragma unroll
+    for (int k = 0; k < GPT; ++k) {
+      const int i = tid + k * 256, sgl = i / CAT_D, n = i % CAT_D;
+      const int64_t b = b0 + sgl;
+      float g = 0.f;
+      if (b < B) {
+        if (dout) g = gv[k] * drop_scale(drop, ((uint64_t)b * Fc + c) * CAT_D + n);
+        if (dmean) g = fmaf(dmv[k], invFc, g);
+        if (use_dq) g += dqv[k];
+      }
+      gs[sgl][n] = g;
+    }
+    {
+      int sr = r_first, j = j_first;
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        if (tid + k * 256 < CATB_TS * dc) rs[sr][j] = rv[k];
         sr += step_r; j += step_j;
         if (j >= dc) { j -= dc; ++sr; }
       }
     }
     __syncthreads();
-    if (mcount > 0) {
-      // dW[n][j] += sum_s g[s][n] * row[s][j]
-#pragma unroll 4
-      for (int s = 0; s < CATB_TS; ++s) {
-        const float4 g4 = *reinterpret_cast<const float4*>(&gs[s][n0]);
-        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+    float de[2][4];
+    switch (mm) {
+      case 1: cat_bwd_products<1>(gs, rs, Ws, jg, n0, s0, acc, de); break;
+      case 2: cat_bwd_products<2>(gs, rs, Ws, jg, n0, s0, acc, de); break;
+      case 3: cat_bwd_products<3>(gs, rs, Ws, jg, n0, s0, acc, de); break;
+      default: cat_bwd_products<4>(gs, rs, Ws, jg, n0, s0, acc, de); break;
+    }
+    // a sample's contribution to dE_c[id], as a 64-wide row (columns >= d_c stay zero) of slot (b, c): the slots are
+    // sorted by global table row and reduced in slot order by b200ctr_scatter_rows (no float atomics)
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          if (m < mcount) {
-            const float r = rs[s][jg + 16 * m];
+    for (int q = 0; q < 2; ++q) {
+      const int64_t b = b0 + s0 + q;
+      if (b >= B) continue;
+      float* dst = dslot >= 0 ? defer_rows + (b * n_defer + dslot) * (int64_t)CAT_D : rowg + (b * Fc + c) * (int64_t)CAT_D;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i][m] = fmaf(gv[i], r, acc[i][m]);
-          }
-        }
-      }
-      // dE[id][j] += sum_n W[n][j] * g[s][n]
-      float de[2][4];
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int m = 0; m < 4; ++m) de[q][m] = 0.f;
-#pragma unroll 2
-      for (int n = 0; n < CAT_D; n += 4) {
-        const float4 ga = *reinterpret_cast<const float4*>(&gs[s0][n]);
-        const float4 gb = *reinterpret_cast<const float4*>(&gs[s0 + 1][n]);
-        const float g0[4] = {ga.x, ga.y, ga.z, ga.w}, g1[4] = {gb.x, gb.y, gb.z, gb.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            if (m < mcount) {
-              const float w = Ws[n + k][jg + 16 * m];
-              de[0][m] = fmaf(w, g0[k], de[0][m]);
-              de[1][m] = fmaf(w, g1[k], de[1][m]);
-            }
-          }
-        }
-      }
-      // a sample's contribution to dE_c[id], as a 64-wide row (columns >= d_c stay zero) of slot (b, c): the slots are
-      // sorted by global table row and reduced in slot order by b200ctr_scatter_rows (no float atomics)
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int64_t b = b0 + s0 + q;
-        if (b >= B) continue;
-        float* dst = dslot >= 0 ? defer_rows + (b * n_defer + dslot) * (int64_t)CAT_D : rowg + (b * Fc + c) * (int64_t)CAT_D;
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-          if (m < mcount) dst[jg + 16 * m] = de[q][m];
-      }
+      for (int m = 0; m < 4; ++m)
+        if (jg + 16 * m < dc) dst[jg + 16 * m] = de[q][m];
     }
     if (tid < CATB_TS && b0 + tid < B) {
       // deferred column (data parallel, replicated row-lazy table): the slot leaves this call unreduced -- the trainer gathers
       // every rank's slots and reduces them once, identically on every replica; the local sort skips it (sentinel key)
-      const int32_t key = row_base + (int32_t)ids[tid];
+      int64_t id = (int64_t)x_cat[(b0 + tid) * Fc + c];
+      id = id < 0 ? 0 : (id >= card ? card - 1 : id);
+      const int32_t key = row_base + (int32_t)id;
       keys[(b0 + tid) * Fc + c] = dslot >= 0 ? sentinel : key;
       if (dslot >= 0) defer_keys[(b0 + tid) * n_defer + dslot] = key;
     }
@@ -371,7 +438,7 @@ cat_bwd_kernel(const IT* __restrict__ x_cat, const float* const* __restrict__ ta
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int m = 0; m < 4; ++m)
-      if (m < mcount) dwp[(n0 + i) * dc + jg + 16 * m] = acc[i][m];
+      if (jg + 16 * m < dc) dwp[(n0 + i) * dc + jg + 16 * m] = acc[i][m];
 }
 
 // dE_c[r, 0:d_c] += temp[row_base_c + r, 0:d_c]  (temp: the 64-wide reduced rows of all tables, one global row id per table row).
