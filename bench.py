@@ -345,25 +345,13 @@ def measure(env, cfg, vocab, dev_b, host, steps, warmup, profile=False, e2e=Fals
             cursor[0] += 1
             tr.step(bb, yy)
 
-    def host_loop_serial(n):
+    def host_loop(n):
+        """The call a user makes: the pinned host batch handed to FusedTrainer.step (H2D of the step's inputs on the step's own
+        stream, in front of its first kernel) and the loss read back after every step (train.py:202)."""
         for _ in range(n):
             hb, hy = host[cursor[0] % NB]
             cursor[0] += 1
-            float(tr.step(hb, hy))             # D2H read of the step's loss (train.py:202)
-
-    def host_loop(n):
-        """The call a user makes: pinned host batches through b200ctr.DeviceFeeder (batch t + 1 crosses PCIe on a copy stream
-        while step t runs; exactly one H2D per step, n in total) into FusedTrainer.step, the loss read back after every step.
-        `host_loop_serial` hands the pinned batch to step() itself: copy, then step, on one stream."""
-        import b200ctr
-
-        def gen():
-            for _ in range(n):
-                item = host[cursor[0] % NB]
-                cursor[0] += 1
-                yield item
-        for bb, yy in b200ctr.DeviceFeeder(gen(), env.dev):
-            float(tr.step(bb, yy))             # D2H read of the step's loss (train.py:202)
+            float(tr.step(hb, hy))
 
     dev_loop(max(3, warmup))
     torch.cuda.synchronize()
@@ -408,8 +396,6 @@ def measure(env, cfg, vocab, dev_b, host, steps, warmup, profile=False, e2e=Fals
         host_loop(2)
         ms2 = env.timed(host_loop, steps)
         out.update(ms_e2e=ms2, e2e=env.world * B * steps / (ms2 * 1e-3))
-        host_loop_serial(2)
-        out["ms_e2e_serial"] = env.timed(host_loop_serial, steps)      # the same without the feeder: copy, then step
     return model, tr, out
 
 
@@ -638,10 +624,9 @@ def run_cuda(args):
             "clocks": r["clocks"],
             "e2e": {"value": r["e2e"], "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": r["ms_e2e"] / args.steps,
-                    "api": "for batch, y in b200ctr.DeviceFeeder(host_batches, device): loss = float(FusedTrainer.step(batch, y)) -- one H2D "
-                           "per step, issued on a copy stream one batch ahead; ms_per_step_serial_copy = float(FusedTrainer.step(host_batch, y)), "
-                           "the copy in front of the step on one stream",
-                    "ms_per_step_serial_copy": r["ms_e2e_serial"] / args.steps},
+                    "api": "loss = float(FusedTrainer.step(pinned_host_batch, y)): the batch's H2D on the step's stream in front of its first "
+                           "kernel, the loss read back after every step (a copy stream that overlaps the next batch's H2D with this step's "
+                           "kernels measured SLOWER on this box: tools/e2e_ab.py, profiles/README.md)"},
             "gpu_launches": int(r["launches"]),
             "ms_per_step_profiled": r["ms_profiled"] / args.steps,
         }
@@ -659,7 +644,7 @@ def run_cuda(args):
                                                for k, v in sorted(r["prof"].items(), key=lambda kv: -kv[1][1])}}, fh, indent=1)
     # ---- the table optimizer's real cost: gap histogram of the next batch + the aged-rows stress (N = 1) ----
     if world == 1 and not args.quick:
-        rep = rowopt_report(env, tr, dev_b, 2 * args.steps + max(3, args.warmup) + 2 * (2 + args.steps), r["prof"], args.steps)
+        rep = rowopt_report(env, tr, dev_b, 2 * args.steps + max(3, args.warmup) + 2 + args.steps, r["prof"], args.steps)
         if rank == 0:
             line["rowopt"] = rep
     # ---- cold gather: token ids uniform over all 10 M rows (no Zipf-hot L2 hits) ----

@@ -111,33 +111,3 @@ def test_fold_ensemble_matches_the_reference_inference_loop(with_T):
     # one model, no calibrator: the clamped probability itself (infer.py:126-127)
     one = b200ctr.FoldEnsemble(models[:1]).predict(batch)
     assert float((one - p_list[0]).abs().max()) < 1e-6 or with_T
-
-
-def test_device_feeder_hands_out_every_batch_once_in_order():
-    """DeviceFeeder: every host batch is copied exactly once, handed out in order, dtypes kept (int64 / int32 ids, f32), and
-    the copy of batch t + 1 is already issued when batch t is returned."""
-    from b200ctr import DeviceFeeder
-    dev = torch.device("cuda:0")
-    rng = np.random.default_rng(3)
-    pulled = []
-
-    def gen():
-        for i in range(5):
-            pulled.append(i)
-            b = {"X_num": torch.from_numpy(rng.standard_normal((64, 7)).astype(np.float32)).pin_memory(),
-                 "X_mask": torch.from_numpy((rng.random((64, 7)) < 0.3).astype(np.float32)).pin_memory(),
-                 "X_cat": torch.from_numpy(rng.integers(0, 50, (64, 3))).pin_memory(),
-                 "seq": torch.from_numpy(rng.integers(0, 1000, (64, 20)).astype(np.int32 if i % 2 else np.int64)).pin_memory()}
-            yield b, torch.from_numpy((rng.random(64) < 0.2).astype(np.float32)).pin_memory()
-    src = []
-    feeder = DeviceFeeder(((src.append(item) or item) for item in gen()), dev)
-    assert pulled == [0]                                   # the first copy is issued at construction
-    n = 0
-    for db, dy in feeder:
-        assert pulled == list(range(min(n + 2, 5)))        # one batch ahead of the consumer
-        hb, hy = src[n]
-        for k, v in hb.items():
-            assert db[k].is_cuda and db[k].dtype == v.dtype and torch.equal(db[k].cpu(), v), k
-        assert dy.is_cuda and torch.equal(dy.cpu(), hy)
-        n += 1
-    assert n == 5

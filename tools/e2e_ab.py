@@ -1,7 +1,13 @@
-"""Development aid: where does the end-to-end step lose time against the device-resident one?  Variants of the host loop
-(feeder / serial copy / device batches) x (no read-back / float(loss) per step), GPU event time and host wall time per step.
-Finding (r02ah): with no per-step read-back the host runs many batches ahead of the GPU and the DeviceFeeder loop degrades
-(23 ms/step); with float(loss) per step -- the reference loop's own pattern -- it is 9.90 ms against 10.18 ms for copy-then-step."""
+"""Development aid: where does the end-to-end step lose time against the device-resident one?  Host-loop variants
+(device batches / pinned batch handed to step() / next batch's H2D on a copy stream, issued before or after the step is
+enqueued) x (no read-back / float(loss) per step); GPU event time and host wall time per step.
+Findings on the B200 boxes of this pool (r02ah / r02ak):
+  * device 9.27-9.40 ms, + float(loss) 9.44-9.58 ms, pinned batch through step() ("serial") 10.00-10.18 ms;
+  * copy stream, copy issued after a sync and before the step: 9.90 ms in one process, 12.0 ms in another;
+  * copy stream, copy issued once the step is enqueued (the H2D overlaps the step's heavy kernels): 18.8 ms;
+  * copy stream without any read-back (host many batches ahead): 14-23 ms.
+An H2D copy that runs concurrently with this step's kernels is slow and makes the step slow; bench.py therefore hands the pinned
+batch to step() (copy in front of the step, 0.6 ms) -- the robust path.  The cause was not isolated (no Nsight Systems here)."""
 import json
 import os
 import sys
@@ -36,9 +42,32 @@ def main():
             def consume(loss):
                 if read == "float":
                     float(loss)
-            if kind == "feeder":
-                for bb, yy in b200ctr.DeviceFeeder((nxt(host) for _ in range(n)), env.dev):
-                    consume(tr.step(bb, yy))
+            if kind.startswith("overlap"):
+                cs = torch.cuda.Stream(env.dev)
+                cur_s = torch.cuda.current_stream(env.dev)
+
+                def issue():
+                    hb, hy = nxt(host)
+                    with torch.cuda.stream(cs):
+                        d = {k: v.to(env.dev, non_blocking=True) for k, v in hb.items()}
+                        yd = hy.to(env.dev, non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(cs)
+                    return d, yd, ev
+                ready = issue()
+                for i in range(n):
+                    d, yd, ev = ready
+                    ready = None
+                    if kind == "overlap_before" and i + 1 < n:
+                        cur_s.synchronize()
+                        ready = issue()
+                    cur_s.wait_event(ev)
+                    for v in list(d.values()) + [yd]:
+                        v.record_stream(cur_s)
+                    loss = tr.step(d, yd)
+                    if kind == "overlap_after" and i + 1 < n:
+                        ready = issue()           # the next batch's copy is issued once this step is enqueued
+                    consume(loss)
             else:
                 for _ in range(n):
                     bb, yy = nxt(host if kind == "serial" else dev_b)
@@ -48,8 +77,10 @@ def main():
         tr.step(*nxt(dev_b))
     torch.cuda.synchronize()
     out = {}
-    for kind in ("device", "serial", "feeder"):
+    for kind in ("device", "serial", "overlap_before", "overlap_after"):
         for read in ("none", "float"):
+            if read == "none" and kind.startswith("overlap"):
+                continue                          # known to degrade (host many batches ahead)
             fn = loop(kind, read)
             fn(2)
             torch.cuda.synchronize()

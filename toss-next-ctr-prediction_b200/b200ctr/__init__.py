@@ -10,9 +10,9 @@ from .hotpath import DropCtl, ModelSpec  # noqa: F401
 from .modules import (BinaryFeatureEmbedding, CTRModel, DARE, DAREEncoderLayer, NumericFeatureEmbedding,  # noqa: F401
                       PositionalBias, QNNAlphaDetailed, RMSNorm, SEBlock, make_norm)
 from .trainer import FusedTrainer, cosine_warmup_lr, ema_decay_at  # noqa: F401
-from .data import BatchedShardReader, DeviceFeeder  # noqa: F401
+from .data import BatchedShardReader  # noqa: F401
 from .infer import FoldEnsemble  # noqa: F401
 
 __all__ = ["CTRModel", "DARE", "DAREEncoderLayer", "PositionalBias", "RMSNorm", "make_norm", "QNNAlphaDetailed",
-           "SEBlock", "NumericFeatureEmbedding", "BinaryFeatureEmbedding", "FusedTrainer", "BatchedShardReader", "DeviceFeeder", "FoldEnsemble", "ModelSpec", "DropCtl",
+           "SEBlock", "NumericFeatureEmbedding", "BinaryFeatureEmbedding", "FusedTrainer", "BatchedShardReader", "FoldEnsemble", "ModelSpec", "DropCtl",
            "build", "load", "B200CtrError"]

@@ -181,61 +181,3 @@ class BatchedShardReader:
             free[i % 2].set()
             yield b
         th.join()
-
-
-class DeviceFeeder:
-    """Host batches of the collate contract (dataset.py:98-124: a dict of CPU -- ideally pinned -- tensors and `y`) handed to
-    `FusedTrainer.step` as device tensors, the copy of batch t + 1 issued on a copy stream BEFORE batch t is handed out: the
-    H2D of the next batch runs under the current step instead of in front of the next one (the reference gets the same overlap
-    from DataLoader workers + `non_blocking=True`, train.py:106-110, 152-156).  Every batch is still copied exactly once.
-
-        for batch, y in DeviceFeeder(loader, device):      # loader yields (dict, y) or dicts carrying "y"
-            loss = trainer.step(batch, y)
-
-    Dtypes are kept (int64 or int32 ids, f32 features); nothing is converted on the host.
-
-    `pace=True` (default): before the next copy is issued the host waits for the consumer's stream, like the reference loop's
-    per-step `loss.item()` (train.py:202) -- the feeder then stays exactly one batch ahead of the GPU.  Measured
-    (tools/e2e_ab.py, B200): 9.90 ms per step against 10.18 ms for copy-then-step on one stream; a host that is allowed to run
-    many steps ahead (no read-back at all, pace=False) degrades to 14-23 ms per step."""
-
-    _COPY = ("X_num", "X_mask", "X_cat", "seq")
-
-    def __init__(self, batches, device, pace: bool = True):
-        self.it = iter(batches)
-        self.device = torch.device(device)
-        self.stream = torch.cuda.Stream(self.device)
-        self.pace = pace
-        self._next = None
-        self._issue()
-
-    def _issue(self):
-        try:
-            item = next(self.it)
-        except StopIteration:
-            self._next = None
-            return
-        batch, y = item if isinstance(item, (tuple, list)) else (item, item.get("y"))
-        with torch.cuda.stream(self.stream):
-            d = {k: (v.to(self.device, non_blocking=True) if k in self._COPY and torch.is_tensor(v) else v) for k, v in batch.items()}
-            yd = y.to(self.device, non_blocking=True) if torch.is_tensor(y) else y
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        self._next = (d, yd, ev)
-
-    def __iter__(self):
-        return self
-
-    def __next__(self):
-        if self._next is None:
-            raise StopIteration
-        d, yd, ev = self._next
-        cur = torch.cuda.current_stream(self.device)
-        if self.pace:
-            cur.synchronize()                           # step t - 1 is done (a no-op after the caller's own loss read-back)
-        self._issue()                                   # batch t + 1 starts crossing PCIe now
-        cur.wait_event(ev)
-        for v in list(d.values()) + [yd]:               # allocated on the copy stream, consumed on the caller's
-            if torch.is_tensor(v) and v.is_cuda:
-                v.record_stream(cur)
-        return d, yd
