@@ -38,37 +38,40 @@ rowrms_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
   if (threadIdx.x == 0) r[b] = rr;
 }
 
-// grid = n_partials CTAs; CTA p handles rows p, p+P, ...; per-thread register accumulators for dw.  The row's dz and x
-// stay in registers between the dot-product pass and the output pass (one HBM read of each, 25 loads in flight per lane).
-__global__ void __launch_bounds__(RR_THREADS, 1)
+// grid = n_partials CTAs; CTA p handles rows p, p+P, ...  The row's dz stays in registers between the dot-product pass and the
+// output pass; x is read again in the output pass (an L2 hit: the CTA read the same 51 KB a few microseconds earlier) and the
+// dw accumulators live in shared memory (each thread owns its elements: no conflicts, no atomics, same summation order as
+// register accumulators).  That is 2 CTAs per SM instead of 1 (247 registers before): one CTA's load phase overlaps the other's
+// reduction barrier and stores (ncu r02ai: 12.5 % of the warp slots active, 4.5 TB/s of DRAM traffic).
+__global__ void __launch_bounds__(RR_THREADS, 2)
 rowrms_bwd_kernel(const float* __restrict__ dz, int64_t ld_dz, const float* __restrict__ x, int64_t ldx,
                   const float* __restrict__ w, const float* __restrict__ r, int64_t B, int64_t N, float* __restrict__ dx,
                   int64_t ld_dx, float* __restrict__ dw_partial) {
+  extern __shared__ __align__(16) unsigned char rr_smem[];
+  float4* accs = reinterpret_cast<float4*>(rr_smem);       // [N / 4]
   __shared__ float red[32];
   const int n4 = (int)(N >> 2);
   const float4* w4 = reinterpret_cast<const float4*>(w);
-  float4 acc[RR_MAXV];
-#pragma unroll
-  for (int s = 0; s < RR_MAXV; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < n4; i += RR_THREADS) accs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
     const float4* dzr = reinterpret_cast<const float4*>(dz + b * ld_dz);
     const float4* xr = reinterpret_cast<const float4*>(x + b * ldx);
     float4* dxr = reinterpret_cast<float4*>(dx + b * ld_dx);
     const float rr = r[b];
-    float4 dreg[RR_MAXV], xreg[RR_MAXV];
-#pragma unroll
-    for (int s = 0; s < RR_MAXV; ++s) {
-      const int i = threadIdx.x + s * RR_THREADS;
-      dreg[s] = make_float4(0.f, 0.f, 0.f, 0.f); xreg[s] = dreg[s];
-      if (i < n4) { dreg[s] = dzr[i]; xreg[s] = xr[i]; }
-    }
+    float4 dreg[RR_MAXV];
     float dot = 0.f;
 #pragma unroll
     for (int s = 0; s < RR_MAXV; ++s) {
       const int i = threadIdx.x + s * RR_THREADS;
+      dreg[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n4) dreg[s] = dzr[i];
+    }
+#pragma unroll
+    for (int s = 0; s < RR_MAXV; ++s) {
+      const int i = threadIdx.x + s * RR_THREADS;
       if (i < n4) {
-        const float4 ww = __ldg(w4 + i);
-        dot += dreg[s].x * ww.x * xreg[s].x + dreg[s].y * ww.y * xreg[s].y + dreg[s].z * ww.z * xreg[s].z + dreg[s].w * ww.w * xreg[s].w;
+        const float4 ww = __ldg(w4 + i), xv = xr[i];
+        dot += dreg[s].x * ww.x * xv.x + dreg[s].y * ww.y * xv.y + dreg[s].z * ww.z * xv.z + dreg[s].w * ww.w * xv.w;
       }
     }
     dot = block_sum(dot, red) / (float)N;
@@ -77,19 +80,17 @@ rowrms_bwd_kernel(const float* __restrict__ dz, int64_t ld_dz, const float* __re
     for (int s = 0; s < RR_MAXV; ++s) {
       const int i = threadIdx.x + s * RR_THREADS;
       if (i < n4) {
-        const float4 d = dreg[s], v = xreg[s], ww = __ldg(w4 + i);   // w (51 KB, shared by every row) is an L1/L2 hit
+        const float4 d = dreg[s], v = xr[i], ww = __ldg(w4 + i);   // w (51 KB, shared by every row) is an L1/L2 hit
         dxr[i] = make_float4(rr * d.x * ww.x - v.x * c, rr * d.y * ww.y - v.y * c, rr * d.z * ww.z - v.z * c, rr * d.w * ww.w - v.w * c);
-        acc[s].x = fmaf(d.x * v.x, rr, acc[s].x); acc[s].y = fmaf(d.y * v.y, rr, acc[s].y);
-        acc[s].z = fmaf(d.z * v.z, rr, acc[s].z); acc[s].w = fmaf(d.w * v.w, rr, acc[s].w);
+        float4 a = accs[i];
+        a.x = fmaf(d.x * v.x, rr, a.x); a.y = fmaf(d.y * v.y, rr, a.y);
+        a.z = fmaf(d.z * v.z, rr, a.z); a.w = fmaf(d.w * v.w, rr, a.w);
+        accs[i] = a;
       }
     }
   }
   float4* out = reinterpret_cast<float4*>(dw_partial + (int64_t)blockIdx.x * N);
-#pragma unroll
-  for (int s = 0; s < RR_MAXV; ++s) {
-    int i = threadIdx.x + s * RR_THREADS;
-    if (i < n4) out[i] = acc[s];
-  }
+  for (int i = threadIdx.x; i < n4; i += RR_THREADS) out[i] = accs[i];
 }
 
 // A (B,F,C): s[b,c] = sum_f A, quad = s^2 - sum_f A^2.  One CTA per sample.
@@ -480,7 +481,10 @@ extern "C" int b200ctr_rowrms_bwd(const float* dz, int64_t ld_dz, const float* x
   B200_REQUIRE(N % 4 == 0 && ldx % 4 == 0 && ld_dz % 4 == 0 && ld_dx % 4 == 0, B200CTR_E_UNSUPPORTED_SHAPE, "rowrms_bwd: alignment");
   B200_REQUIRE(N <= (int64_t)RR_MAXV * 4 * RR_THREADS, B200CTR_E_UNSUPPORTED_SHAPE, "rowrms_bwd: F*D=%lld exceeds %d", (long long)N, RR_MAXV * 4 * RR_THREADS);
   B200_REQUIRE(n_partials >= 1, B200CTR_E_INVALID_ARG, "rowrms_bwd: n_partials");
-  rowrms_bwd_kernel<<<n_partials, RR_THREADS, 0, as_stream(stream)>>>(dz, ld_dz, x, ldx, w, r, B, N, dx, ld_dx, dw_partial);
+  const size_t smem = (size_t)N * 4;
+  cudaError_t e = cudaFuncSetAttribute(rowrms_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(rowrms_bwd smem)");
+  rowrms_bwd_kernel<<<n_partials, RR_THREADS, smem, as_stream(stream)>>>(dz, ld_dz, x, ldx, w, r, B, N, dx, ld_dx, dw_partial);
   B200_LAUNCH_CHECK("rowrms_bwd_kernel");
   return B200CTR_OK;
 }
