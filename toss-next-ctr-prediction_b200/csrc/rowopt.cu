@@ -268,7 +268,7 @@ __device__ __forceinline__ void row_catchup4(float4& p, float4& m, float4& v, fl
   v = make_float4(v0.x, v0.y, v1.x, v1.y); e = make_float4(e0.x, e0.y, e1.x, e1.y);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 rowopt_catchup_bm_kernel(const uint32_t* __restrict__ bm, int n_maps, int64_t words, int n_shards, int rank,
                          int32_t* __restrict__ state, float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ V,
                          float* __restrict__ E, int target, RowHist H) {

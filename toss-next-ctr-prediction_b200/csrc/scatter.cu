@@ -68,7 +68,7 @@ __device__ __forceinline__ void sc_load(const ScSrc& S, uint32_t slot, int hl, f
 __device__ __forceinline__ void f4_add(float4& x, const float4& y) { x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
 
 // meta[c] = {head_key, tail_key, head_continues, 0}; partial rows: part[(c * 2 + which) * 2 + table]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 sc_reduce_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n, uint32_t sentinel, int shift,
                  ScSrc S, float* __restrict__ g_att, float* __restrict__ g_rep, float4* __restrict__ part, int4* __restrict__ meta,
                  int64_t n_chunks) {
