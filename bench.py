@@ -13,9 +13,11 @@ mode (`fp32` key: tcgen05 split-precision contractions, the mode every shipped c
 One process per GPU; N > 1 = data parallel over the batch with the two sequence tables row-sharded across the GPUs, B per GPU
 fixed (weak scaling).
 
-Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM; `e2e` = the same step through
-FusedTrainer.step() with pinned HOST batches (H2D inside the timed region) and a D2H read of the loss every step.
-`roofline` describes the dominant kernel family of the step, timed live with CUDA events on the launch stream.
+Prints ONE JSON line (rank 0).  `value` = whole-job samples/s with inputs resident in HBM, timed over K plain steps (no
+instrumentation inside the region); `e2e` = the same step through FusedTrainer.step() with pinned HOST batches (H2D inside the
+timed region) and a D2H read of the loss every step.  `roofline` describes the dominant kernel family of the step, timed live
+with a CUDA event pair around every C-ABI call on the launch stream in a SECOND timed region of K steps (`ms_per_step_profiled`:
+the ~350 event records per step cost 0.7 ms, which is why they are not inside the region `value` is quoted on).
 """
 from __future__ import annotations
 
