@@ -207,6 +207,24 @@ __global__ void se_apply_bwd_kernel(const float* __restrict__ dout, int64_t ld_d
   if (gprod) gprod[i] = d * inter[i];
   if (dinter) dinter[i] = d * (gate ? gate[c] : 1.f) + (dmean ? dmean[c] * inv_B : 0.f);
 }
+// the same, one aligned element PAIR per thread (C even: a pair never straddles a row): one dropout hash word and one 64-bit
+// division per pair instead of per element
+__global__ void se_apply_bwd_pair_kernel(const float* __restrict__ dout, int64_t ld_dout, const float* __restrict__ inter,
+                                         const float* __restrict__ gate, const float* __restrict__ dmean, float inv_B, int64_t B,
+                                         int C, float* __restrict__ dinter, float* __restrict__ gprod, b200ctr_dropout_t drop) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i >= B * C) return;
+  const int64_t b = i / C;
+  const int c = (int)(i - b * C);
+  float s0 = 1.f, s1 = 1.f;
+  if (drop.p > 0.f) drop_scale2(drop, (uint64_t)i, s0, s1);
+  const float d0 = dout[b * ld_dout + c] * s0, d1 = dout[b * ld_dout + c + 1] * s1;
+  if (gprod) { gprod[i] = d0 * inter[i]; gprod[i + 1] = d1 * inter[i + 1]; }
+  if (dinter) {
+    dinter[i] = d0 * (gate ? gate[c] : 1.f) + (dmean ? dmean[c] * inv_B : 0.f);
+    dinter[i + 1] = d1 * (gate ? gate[c + 1] : 1.f) + (dmean ? dmean[c + 1] * inv_B : 0.f);
+  }
+}
 
 
 // ---- per-head value projection of the quadratic term (qnn_alpha.py:96: out_h = quad_h @ V_h) --------------------
@@ -544,7 +562,10 @@ extern "C" int b200ctr_se_apply_bwd(const float* dout, int64_t ld_dout, const fl
                                     float inv_B, int64_t B, int C, float* dinter, float* gprod, b200ctr_dropout_t drop, void* stream) {
   B200_REQUIRE(dout && inter && (dinter || gprod), B200CTR_E_INVALID_ARG, "se_apply_bwd: null pointer");
   if (B * C == 0) return B200CTR_OK;
-  se_apply_bwd_kernel<<<(unsigned)ceil_div(B * C, 256), 256, 0, as_stream(stream)>>>(dout, ld_dout, inter, gate, dmean, inv_B, B, C, dinter, gprod, drop);
+  if (C % 2 == 0)
+    se_apply_bwd_pair_kernel<<<(unsigned)ceil_div(B * C / 2, 256), 256, 0, as_stream(stream)>>>(dout, ld_dout, inter, gate, dmean, inv_B, B, C, dinter, gprod, drop);
+  else
+    se_apply_bwd_kernel<<<(unsigned)ceil_div(B * C, 256), 256, 0, as_stream(stream)>>>(dout, ld_dout, inter, gate, dmean, inv_B, B, C, dinter, gprod, drop);
   B200_LAUNCH_CHECK("se_apply_bwd_kernel");
   return B200CTR_OK;
 }
