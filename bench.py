@@ -347,13 +347,27 @@ def measure(env, cfg, vocab, dev_b, host, steps, warmup, profile=False, e2e=Fals
             cursor[0] += 1
             tr.step(bb, yy)
 
-    def host_loop(n):
-        """The call a user makes: the pinned host batch handed to FusedTrainer.step (H2D of the step's inputs on the step's own
-        stream, in front of its first kernel) and the loss read back after every step (train.py:202)."""
+    def host_loop_serial(n):
+        """The pinned host batch handed to FusedTrainer.step itself: H2D on the step's stream in front of its first kernel."""
         for _ in range(n):
             hb, hy = host[cursor[0] % NB]
             cursor[0] += 1
-            float(tr.step(hb, hy))
+            float(tr.step(hb, hy))             # D2H read of the step's loss (train.py:202)
+
+    def host_loop(n):
+        """The call a user makes: every pinned host batch goes through FusedTrainer.stage (H2D into one of the trainer's two
+        preallocated staging sets on its copy stream) -- batch t + 1 is staged right after step t is enqueued, so it crosses
+        PCIe under step t -- and the loss is read back after every step (train.py:202).  Exactly n copies and n reads."""
+        def take():
+            item = host[cursor[0] % NB]
+            cursor[0] += 1
+            return item
+        tr.stage(*take())
+        for i in range(n):
+            loss = tr.step()
+            if i + 1 < n:
+                tr.stage(*take())
+            float(loss)
 
     dev_loop(max(3, warmup))
     torch.cuda.synchronize()
@@ -398,6 +412,8 @@ def measure(env, cfg, vocab, dev_b, host, steps, warmup, profile=False, e2e=Fals
         host_loop(2)
         ms2 = env.timed(host_loop, steps)
         out.update(ms_e2e=ms2, e2e=env.world * B * steps / (ms2 * 1e-3))
+        host_loop_serial(2)
+        out["ms_e2e_serial"] = env.timed(host_loop_serial, steps)      # the same without staging: copy, then step, on one stream
     return model, tr, out
 
 
@@ -626,9 +642,10 @@ def run_cuda(args):
             "clocks": r["clocks"],
             "e2e": {"value": r["e2e"], "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": r["ms_e2e"] / args.steps,
-                    "api": "loss = float(FusedTrainer.step(pinned_host_batch, y)): the batch's H2D on the step's stream in front of its first "
-                           "kernel, the loss read back after every step (a copy stream that overlaps the next batch's H2D with this step's "
-                           "kernels measured SLOWER on this box: tools/e2e_ab.py, profiles/README.md)"},
+                    "api": "tr.stage(batch_0); for t: loss = tr.step(); tr.stage(batch_t+1); float(loss) -- FusedTrainer.stage copies the "
+                           "pinned host batch into one of two preallocated device staging sets on the trainer's copy stream (batch t+1 "
+                           "crosses PCIe under step t), the loss is read back after every step",
+                    "ms_per_step_serial_copy": r["ms_e2e_serial"] / args.steps},
             "gpu_launches": int(r["launches"]),
             "ms_per_step_profiled": r["ms_profiled"] / args.steps,
         }
@@ -646,7 +663,7 @@ def run_cuda(args):
                                                for k, v in sorted(r["prof"].items(), key=lambda kv: -kv[1][1])}}, fh, indent=1)
     # ---- the table optimizer's real cost: gap histogram of the next batch + the aged-rows stress (N = 1) ----
     if world == 1 and not args.quick:
-        rep = rowopt_report(env, tr, dev_b, 2 * args.steps + max(3, args.warmup) + 2 + args.steps, r["prof"], args.steps)
+        rep = rowopt_report(env, tr, dev_b, 2 * args.steps + max(3, args.warmup) + 2 * (2 + args.steps), r["prof"], args.steps)
         if rank == 0:
             line["rowopt"] = rep
     # ---- cold gather: token ids uniform over all 10 M rows (no Zipf-hot L2 hits) ----

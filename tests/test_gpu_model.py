@@ -391,6 +391,51 @@ def test_two_runs_are_bit_identical(kind, prec):
     assert torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
 
 
+def test_staged_batches_give_the_same_steps_as_batches_handed_to_step():
+    """FusedTrainer.stage (copy stream + two preallocated staging sets, the next batch staged while the current step runs)
+    feeds step() the same bytes as step(batch, y): parameters, EMA and the losses agree BITWISE over 5 steps, including a
+    batch of another shape in the middle (the slot is re-allocated) and the two-ahead limit."""
+    import b200ctr
+    dev = torch.device("cuda:0")
+    z, cfg = load_case("qnn_concat")
+    cfg = dict(cfg, amp="bf16")
+    batches = []
+    for s in range(5):
+        batch, y = batch_of(z, s % 3)
+        if s == 2:                                        # a ragged batch: half the rows
+            n = y.shape[0] // 2
+            batch, y = {k: v[:n].contiguous() for k, v in batch.items()}, y[:n].contiguous()
+        batches.append(({k: v.pin_memory() for k, v in batch.items()}, y.pin_memory()))
+    runs = []
+    for staged in (False, True):
+        m = _build(cfg, z, dev).train()
+        tr = b200ctr.FusedTrainer(m, cfg, steps_per_epoch=cfg["golden"]["steps_per_epoch"])
+        losses = []
+        if staged:
+            with pytest.raises(RuntimeError):
+                tr.step()                                  # nothing staged yet
+            tr.stage(*batches[0])
+            for i in range(5):
+                loss = tr.step()
+                if i + 1 < 5:
+                    tr.stage(*batches[i + 1])
+                losses.append(float(loss))
+            tr.stage(*batches[0]); tr.stage(*batches[1])
+            with pytest.raises(RuntimeError):
+                tr.stage(*batches[2])                      # two batches are already ahead
+        else:
+            for b, y in batches:
+                losses.append(float(tr.step(b, y)))
+        runs.append((losses, {k: v.detach().clone() for k, v in m.state_dict().items()},
+                     {k: v.clone() for k, v in tr.ema_state().items()}))
+    a, b = runs
+    assert a[0] == b[0]
+    for k in a[1]:
+        assert torch.equal(a[1][k], b[1][k]), k
+    for k in a[2]:
+        assert torch.equal(a[2][k], b[2][k]), ("ema", k)
+
+
 def test_sorted_scatter_equals_atomic_scatter_and_the_oracle():
     """b200ctr_scatter_rows (sort + segmented reduction) against the fp64 index_add of the same contributions, with heavy
     duplication (rows that collect thousands of slots and span many 32-slot chunks) and pad slots."""

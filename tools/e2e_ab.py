@@ -68,6 +68,30 @@ def main():
                     if kind == "overlap_after" and i + 1 < n:
                         ready = issue()           # the next batch's copy is issued once this step is enqueued
                     consume(loss)
+            elif kind.startswith("static"):
+                # two preallocated device staging sets (no allocator traffic, no record_stream), copies on a copy stream
+                cs = stat["cs"]
+                cur_s = torch.cuda.current_stream(env.dev)
+
+                def issue(slot):
+                    hb, hy = nxt(host)
+                    cs.wait_event(stat["used"][slot])               # the step that read this slot is done
+                    with torch.cuda.stream(cs):
+                        for k, v in hb.items():
+                            stat["b"][slot][k].copy_(v, non_blocking=True)
+                        stat["y"][slot].copy_(hy, non_blocking=True)
+                        stat["ready"][slot].record(cs)
+                issue(0)
+                for i in range(n):
+                    slot = i & 1
+                    if kind == "static_before" and i + 1 < n:
+                        issue(slot ^ 1)
+                    cur_s.wait_event(stat["ready"][slot])
+                    loss = tr.step(stat["b"][slot], stat["y"][slot])
+                    stat["used"][slot].record(cur_s)
+                    if kind == "static_after" and i + 1 < n:
+                        issue(slot ^ 1)                             # the next batch's copy is issued once this step is enqueued
+                    consume(loss)
             else:
                 for _ in range(n):
                     bb, yy = nxt(host if kind == "serial" else dev_b)
@@ -76,10 +100,17 @@ def main():
     for _ in range(4):
         tr.step(*nxt(dev_b))
     torch.cuda.synchronize()
+    stat = {"cs": torch.cuda.Stream(env.dev),
+            "b": [{k: torch.empty_like(v, device=env.dev) for k, v in host[0][0].items()} for _ in range(2)],
+            "y": [torch.empty_like(host[0][1], device=env.dev) for _ in range(2)],
+            "ready": [torch.cuda.Event(), torch.cuda.Event()], "used": [torch.cuda.Event(), torch.cuda.Event()]}
+    for e in stat["used"]:
+        e.record(torch.cuda.current_stream(env.dev))
+    torch.cuda.synchronize()
     out = {}
-    for kind in ("device", "serial", "overlap_before", "overlap_after"):
+    for kind in ("device", "serial", "static_before", "static_after", "overlap_before"):
         for read in ("none", "float"):
-            if read == "none" and kind.startswith("overlap"):
+            if read == "none" and (kind.startswith("overlap") or kind == "device" or kind == "serial"):
                 continue                          # known to degrade (host many batches ahead)
             fn = loop(kind, read)
             fn(2)
