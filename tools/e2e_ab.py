@@ -1,13 +1,13 @@
 """Development aid: where does the end-to-end step lose time against the device-resident one?  Host-loop variants
 (device batches / pinned batch handed to step() / next batch's H2D on a copy stream, issued before or after the step is
 enqueued) x (no read-back / float(loss) per step); GPU event time and host wall time per step.
-Findings on the B200 boxes of this pool (r02ah / r02ak):
-  * device 9.27-9.40 ms, + float(loss) 9.44-9.58 ms, pinned batch through step() ("serial") 10.00-10.18 ms;
-  * copy stream, copy issued after a sync and before the step: 9.90 ms in one process, 12.0 ms in another;
-  * copy stream, copy issued once the step is enqueued (the H2D overlaps the step's heavy kernels): 18.8 ms;
-  * copy stream without any read-back (host many batches ahead): 14-23 ms.
-An H2D copy that runs concurrently with this step's kernels is slow and makes the step slow; bench.py therefore hands the pinned
-batch to step() (copy in front of the step, 0.6 ms) -- the robust path.  The cause was not isolated (no Nsight Systems here)."""
+Findings on the B200 boxes of this pool (r02ah / r02ak / r02ap):
+  * device 9.18-9.40 ms, + float(loss) 9.44-9.58 ms, pinned batch through step() ("serial") 9.86-10.18 ms;
+  * copy stream with the device tensors ALLOCATED PER BATCH on the side stream ("overlap_*"): 9.6-9.9 ms in one process, 12.0 ms
+    in another, 18.8 ms with the copy issued once the step is enqueued, 14-23 ms without any read-back;
+  * copy stream into two PREALLOCATED staging sets ("static_*"): 9.27-9.38 ms whichever way the copy is issued.
+The slow cases were allocator traffic on the side stream (cudaMalloc while the GPU is busy, deferred reuse of blocks shared between
+streams), not DMA contention.  FusedTrainer.stage() is the static form; bench.py's e2e uses it."""
 import json
 import os
 import sys
